@@ -1,0 +1,158 @@
+/* jrystal_b200 -- C ABI of the B200-native energy+gradient path of sail-sg/jrystal.
+ *
+ * This header is the drop-in boundary (DESIGN.md "Boundary").  The reference
+ * has no native interface: its boundary is the Python function API of jrystal/{pw,energy,
+ * potential,hamiltonian}.py and the JAX primitive pair `ifftn_sharding` / `fftn_sharding`
+ * (jrystal/_src/spmd/fft.py:79-134).  Each entry point below names the reference function(s)
+ * it replaces; INTEGRATION.md shows the XLA-FFI / custom_vjp and ctypes bindings.
+ *
+ * Conventions
+ *   - plain `extern "C"`, no C++ types, no exceptions across the boundary;
+ *   - every call returns 0 on success, a negative JRB_E* code on failure; the message of the
+ *     last failure on the calling thread is available from jrb_last_error();
+ *   - all array arguments are DEVICE pointers owned by the caller unless the name ends in
+ *     `_host`; the library never frees or retains them past the call;
+ *   - calls are asynchronous on the passed CUDA stream (a `cudaStream_t` cast to void*),
+ *     never synchronise and never allocate (work space belongs to the plan), except the
+ *     `*_host` entry point which copies, runs and synchronises;
+ *   - complex arrays are interleaved (re, im) FP64 = numpy complex128 / jnp.complex128;
+ *   - array layouts are the reference's: parameters and sphere coefficients are
+ *     (ns, nk, ng, nb) with the band axis contiguous (jrystal/_src/pw.py:88-91), compact
+ *     index g enumerates mask==True in C order (jrystal/_src/utils.py:279-281), grids are
+ *     (..., nx, ny, nz) C order.
+ *   - there is NO CPU fallback: every entry point needs a CUDA device.
+ */
+#ifndef JRYSTAL_B200_H_
+#define JRYSTAL_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define JRB_OK 0
+#define JRB_EINVAL (-1)      /* bad argument (shape, null pointer, unsupported value) */
+#define JRB_EUNSUPPORTED (-2) /* FFT length without a compiled plan, xc functional ...  */
+#define JRB_ECUDA (-3)       /* CUDA runtime error                                      */
+#define JRB_ENOMEM (-4)      /* device allocation failed                                */
+
+/* xc functionals (jrystal/_src/xc.py:242-253, LDA branch).  Names joined by '+' in the
+ * reference are summed; the ids below are the combinations the kernels implement. */
+#define JRB_XC_LDA_X 1
+#define JRB_XC_LDA_X_C_PW 2 /* "lda_x+lda_c_pw" */
+
+#define JRB_FFT_FORWARD (-1) /* jnp.fft.fftn  : exp(-i...)            (fftn_sharding)  */
+#define JRB_FFT_INVERSE (+1) /* jnp.fft.ifftn : exp(+i...) and 1/N    (ifftn_sharding) */
+
+typedef struct jrb_plan jrb_plan;
+typedef void* jrb_stream; /* cudaStream_t */
+
+typedef struct {
+  int32_t nx, ny, nz;    /* FFT grid; each a 7-smooth length with a compiled line plan   */
+  int32_t ns, nk, nb;    /* spins (1|2), k-points and bands held by THIS rank            */
+  const uint8_t* mask;   /* host, nx*ny*nz bytes, C order, non-zero = kept plane wave    */
+  const double* kpts;    /* host, [nk][3] Cartesian k-vectors (1/Bohr)                   */
+  const double* cell;    /* host, [3][3] rows = lattice vectors (Bohr)                   */
+  int32_t device;        /* CUDA device ordinal                                          */
+  int32_t batch_groups;  /* band groups (8 bands) per pencil-pass batch; 0 = automatic   */
+} jrb_plan_desc;
+
+/* Builds everything the reference's drivers build before their loop
+ * (calc/calc_ground_state_energy_all_electrons.py:93-106: grids, mask-derived index maps,
+ * |G+k|^2 tables) plus twiddles and work space.  Replaces grid.g_vectors / spherical_mask
+ * consumers inside the hot loop. */
+int jrb_plan_create(const jrb_plan_desc* desc, jrb_plan** out);
+int jrb_plan_destroy(jrb_plan* plan);
+/* number of kept plane waves ng = mask.sum() (jrystal/_src/pw.py:89) */
+int64_t jrb_plan_num_g(const jrb_plan* plan);
+/* bytes of device work space owned by the plan */
+int64_t jrb_plan_workspace_bytes(const jrb_plan* plan);
+
+/* Pre-computes V_ext(G) once: potential.external_reciprocal (jrystal/_src/potential.py:
+ * 153-166), which the reference re-evaluates every step although it is parameter free. */
+int jrb_set_atoms(jrb_plan* plan, const double* positions_host, const double* charges_host,
+                  int32_t natoms, jrb_stream stream);
+
+/* unitary_module.unitary_matrix (jrystal/_src/unitary_module.py:66-81): Q R = w_re + i w_im per
+ * (spin, k).  Cholesky-QR2 on FP64 tensor cores; gauge: diag(R) real POSITIVE (LAPACK's
+ * Householder Q differs by a sign per column; energies, density and gradients are invariant).
+ * q: (ns,nk,ng,nb) complex, r: (ns,nk,nb,nb) complex upper triangular. */
+int jrb_qr_fwd(jrb_plan* plan, const double* w_re, const double* w_im, double* q, double* r,
+               jrb_stream stream);
+/* reverse mode of the above (what JAX's QR AD rule does for the reference):
+ * gq = dE/dQ* (complex, same layout as q); outputs dE/dw_re, dE/dw_im. */
+int jrb_qr_bwd(jrb_plan* plan, const double* q, const double* r, const double* gq, double* g_re,
+               double* g_im, jrb_stream stream);
+
+/* utils.expand_coefficient (jrystal/_src/utils.py:277-281): (ns,nk,ng,nb) -> dense
+ * (ns,nk,nb,nx,ny,nz).  Only for API parity; the fused paths never build the dense box. */
+int jrb_expand(jrb_plan* plan, const double* q, double* coeff_dense, jrb_stream stream);
+/* inverse of the above (utils.squeeze_coefficient, 284-308). */
+int jrb_squeeze(jrb_plan* plan, const double* coeff_dense, double* q, jrb_stream stream);
+
+/* pw.density_grid with occupation (jrystal/_src/pw.py:273-284) fused with pw.coeff's scatter
+ * and pw.wave_grid: rho[s,x,y,z] = sum_kb occ[s,k,b] |psi_skb(r)|^2; psi never reaches HBM.
+ * rho is OVERWRITTEN. */
+int jrb_density(jrb_plan* plan, const double* q, const double* occ, double* rho,
+                jrb_stream stream);
+
+/* per-orbital kinetic expectation t[s,k,b] = 1/2 sum_G |G+k|^2 |c_G|^2 on the sphere
+ * (energy.kinetic without occupation, jrystal/_src/energy.py:172-180; braket.expectation
+ * mode='kinetic', diagonal). */
+int jrb_kinetic(jrb_plan* plan, const double* q, double* t_skb, jrb_stream stream);
+
+/* energy.hartree + energy.external + energy.xc_energy (jrystal/_src/energy.py:68-82, 121-135,
+ * 204-211) and potential.effective (potential.py:255-279) in one sweep over the grid:
+ *   energies[0..2] = E_hartree, E_external, E_xc   (device doubles)
+ *   veff[s,x,y,z]  = dE/drho_s = Re ifftn(4 pi n(G)/G^2 + V_ext(G)) + v_xc,s(r)
+ * kohn_sham != 0 evaluates the terms the way hamiltonian_matrix_trace does (un-halved Hartree
+ * energy, v_xc as the xc "energy density"; potential.py:67-75, xc.py:247-250). */
+int jrb_grid_potential(jrb_plan* plan, const double* rho, int32_t xc_id, int32_t kohn_sham,
+                       double* energies, double* veff, jrb_stream stream);
+
+/* Hamiltonian apply on the sphere: hq = 1/2|G+k|^2 q + (sqrt(Omega)/N) fftn(veff * psi)|mask.
+ * This is the reverse pass of the energy w.r.t. Q (dE/dQ* = occ * hq) and the forward+reverse
+ * pass of hamiltonian.hamiltonian_matrix_trace (jrystal/_src/hamiltonian.py:147-168). */
+int jrb_hpsi(jrb_plan* plan, const double* q, const double* veff, double* hq, jrb_stream stream);
+
+/* eps[s,k,b] = Re sum_G conj(q) hq: diagonal of braket.expectation(real)+(kinetic)
+ * (jrystal/_src/braket.py:189-206) = dE/d occ[s,k,b]. */
+int jrb_band_expect(jrb_plan* plan, const double* q, const double* hq, double* eps_skb,
+                    jrb_stream stream);
+
+/* Dense batched 3-D C2C transform over the last three axes: exact drop-in for the
+ * primitives ifftn_sharding / fftn_sharding (jrystal/_src/spmd/fft.py:68-75), numpy
+ * normalisation (inverse divides by N).  in == out is allowed. */
+int jrb_fft3d(jrb_plan* plan, const double* in, double* out, int32_t direction, int64_t batch,
+              jrb_stream stream);
+
+/* One energy+gradient evaluation = value_and_grad(total_energy) of the energy-mode driver
+ * (calc/calc_ground_state_energy_all_electrons.py:119-137,175-181), optimiser excluded.
+ * Split in two so a multi-GPU host can all-reduce rho/E_kin between the halves:
+ *   begin : QR, fused scatter+IFFT+density, kinetic   -> rho (partial over this rank's k/bands),
+ *           e_kin (device double, partial)
+ *   finish: grid potential from the (all-reduced) rho, H-apply, QR adjoint
+ *           -> energies[4] = E_kin(as passed in), E_ext, E_har, E_xc; g_re, g_im; g_occ
+ *              (optional, may be NULL) = dE/d occ.
+ * The Q/R/HQ intermediates live in plan-owned work space. */
+int jrb_eval_begin(jrb_plan* plan, const double* w_re, const double* w_im, const double* occ,
+                   double* rho, double* e_kin, jrb_stream stream);
+int jrb_eval_finish(jrb_plan* plan, const double* occ, const double* rho, const double* e_kin,
+                    int32_t xc_id, double* energies, double* g_re, double* g_im, double* g_occ,
+                    jrb_stream stream);
+
+/* Same evaluation through HOST buffers (the reference-facing call a non-CUDA host makes):
+ * copies w_re/w_im/occ in, runs begin+finish, copies energies[4], g_re, g_im (and rho_host if
+ * non-NULL) back and synchronises.  Single GPU only. */
+int jrb_energy_grad_host(jrb_plan* plan, const double* w_re_host, const double* w_im_host,
+                         const double* occ_host, int32_t xc_id, double* energies_host,
+                         double* g_re_host, double* g_im_host, double* rho_host);
+
+const char* jrb_last_error(void);
+int jrb_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* JRYSTAL_B200_H_ */

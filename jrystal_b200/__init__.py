@@ -1,0 +1,11 @@
+"""jrystal_b200: B200-native (sm_100a CUDA) energy+gradient path of sail-sg/jrystal.
+
+Public surface mirrors the reference's Python API for this path (pw, grid, energy,
+potential, kinetic, hamiltonian, occupation, entropy) over the C ABI of
+include/jrystal_b200.h.  No CPU fallback: compute calls need the built
+jrystal_b200/csrc/libjrystal_b200.so and a CUDA device.
+"""
+from . import _lib  # noqa: F401
+from .plan import Plan  # noqa: F401
+
+__all__ = ['Plan']

@@ -1,0 +1,78 @@
+"""ctypes binding of libjrystal_b200.so (the C ABI of include/jrystal_b200.h).
+
+There is no CPU fallback: importing this module without the built CUDA library raises.
+"""
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, 'csrc', 'libjrystal_b200.so')
+
+XC_IDS = {'lda_x': 1, 'lda_x+lda_c_pw': 2}
+FFT_FORWARD, FFT_INVERSE = -1, 1
+
+
+class PlanDesc(ctypes.Structure):
+  _fields_ = [
+    ('nx', ctypes.c_int32), ('ny', ctypes.c_int32), ('nz', ctypes.c_int32),
+    ('ns', ctypes.c_int32), ('nk', ctypes.c_int32), ('nb', ctypes.c_int32),
+    ('mask', ctypes.c_void_p), ('kpts', ctypes.c_void_p), ('cell', ctypes.c_void_p),
+    ('device', ctypes.c_int32), ('batch_groups', ctypes.c_int32),
+  ]
+
+
+# name -> (restype, argtypes); every symbol include/jrystal_b200.h declares
+_P, _I32, _I64 = ctypes.c_void_p, ctypes.c_int32, ctypes.c_int64
+SYMBOLS = {
+  'jrb_plan_create': (ctypes.c_int, [ctypes.POINTER(PlanDesc), ctypes.POINTER(_P)]),
+  'jrb_plan_destroy': (ctypes.c_int, [_P]),
+  'jrb_plan_num_g': (_I64, [_P]),
+  'jrb_plan_workspace_bytes': (_I64, [_P]),
+  'jrb_set_atoms': (ctypes.c_int, [_P, _P, _P, _I32, _P]),
+  'jrb_qr_fwd': (ctypes.c_int, [_P, _P, _P, _P, _P, _P]),
+  'jrb_qr_bwd': (ctypes.c_int, [_P, _P, _P, _P, _P, _P, _P]),
+  'jrb_expand': (ctypes.c_int, [_P, _P, _P, _P]),
+  'jrb_squeeze': (ctypes.c_int, [_P, _P, _P, _P]),
+  'jrb_density': (ctypes.c_int, [_P, _P, _P, _P, _P]),
+  'jrb_kinetic': (ctypes.c_int, [_P, _P, _P, _P]),
+  'jrb_grid_potential': (ctypes.c_int, [_P, _P, _I32, _I32, _P, _P, _P]),
+  'jrb_hpsi': (ctypes.c_int, [_P, _P, _P, _P, _P]),
+  'jrb_band_expect': (ctypes.c_int, [_P, _P, _P, _P, _P]),
+  'jrb_fft3d': (ctypes.c_int, [_P, _P, _P, _I32, _I64, _P]),
+  'jrb_eval_begin': (ctypes.c_int, [_P, _P, _P, _P, _P, _P, _P]),
+  'jrb_eval_finish': (ctypes.c_int, [_P, _P, _P, _P, _I32, _P, _P, _P, _P, _P]),
+  'jrb_energy_grad_host': (ctypes.c_int, [_P, _P, _P, _P, _I32, _P, _P, _P, _P]),
+  'jrb_last_error': (ctypes.c_char_p, []),
+  'jrb_version': (ctypes.c_int, []),
+}
+
+_lib = None
+
+
+def load():
+  """Load the shared library (once) and set the prototypes.  Fails loudly."""
+  global _lib
+  if _lib is not None:
+    return _lib
+  if not os.path.exists(LIB_PATH):
+    raise ImportError(
+      f'{LIB_PATH} is missing: build it with jrystal_b200/csrc/build.sh or '
+      '`python -c "import __graft_entry__ as g; g.build()"`. There is no CPU fallback.'
+    )
+  lib = ctypes.CDLL(LIB_PATH)
+  for name, (res, args) in SYMBOLS.items():
+    fn = getattr(lib, name)
+    fn.restype = res
+    fn.argtypes = args
+  _lib = lib
+  return lib
+
+
+class JrbError(RuntimeError):
+  pass
+
+
+def check(rc):
+  if rc != 0:
+    msg = load().jrb_last_error()
+    raise JrbError(f'jrystal_b200 error {rc}: {msg.decode() if msg else "?"}')

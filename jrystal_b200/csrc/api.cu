@@ -1,0 +1,206 @@
+// extern "C" entry points declared in include/jrystal_b200.h: argument checks and
+// composition of the kernels into the reference's operations.
+#include <string>
+
+#include "plan.h"
+
+using namespace jrb;
+
+#define REQUIRE(cond, msg)                           \
+  do {                                               \
+    if (!(cond)) {                                   \
+      set_error(std::string(__func__) + ": " + msg); \
+      return JRB_EINVAL;                             \
+    }                                                \
+  } while (0)
+
+static inline cudaStream_t S(jrb_stream s) { return reinterpret_cast<cudaStream_t>(s); }
+static inline const cplx* C(const double* p) { return reinterpret_cast<const cplx*>(p); }
+static inline cplx* C(double* p) { return reinterpret_cast<cplx*>(p); }
+
+static int enter(jrb_plan* p) {
+  if (!p) {
+    set_error("null plan");
+    return JRB_EINVAL;
+  }
+  JRB_CUDA(cudaSetDevice(p->device));
+  return 0;
+}
+
+extern "C" int jrb_set_atoms(jrb_plan* p, const double* pos_h, const double* chg_h, int32_t na,
+                             jrb_stream st) {
+  int rc = enter(p);
+  if (rc) return rc;
+  return launch_set_atoms(p, pos_h, chg_h, na, S(st));
+}
+
+extern "C" int jrb_qr_fwd(jrb_plan* p, const double* w_re, const double* w_im, double* q,
+                          double* r, jrb_stream st) {
+  int rc = enter(p);
+  if (rc) return rc;
+  REQUIRE(w_re && w_im && q && r, "null array");
+  return launch_qr_fwd(p, w_re, w_im, C(q), C(r), S(st));
+}
+
+extern "C" int jrb_qr_bwd(jrb_plan* p, const double* q, const double* r, const double* gq,
+                          double* g_re, double* g_im, jrb_stream st) {
+  int rc = enter(p);
+  if (rc) return rc;
+  REQUIRE(q && r && gq && g_re && g_im, "null array");
+  return launch_qr_bwd(p, C(q), C(r), C(gq), nullptr, g_re, g_im, S(st));
+}
+
+extern "C" int jrb_expand(jrb_plan* p, const double* q, double* dense, jrb_stream st) {
+  int rc = enter(p);
+  if (rc) return rc;
+  REQUIRE(q && dense, "null array");
+  return launch_expand(p, C(q), C(dense), S(st));
+}
+
+extern "C" int jrb_squeeze(jrb_plan* p, const double* dense, double* q, jrb_stream st) {
+  int rc = enter(p);
+  if (rc) return rc;
+  REQUIRE(q && dense, "null array");
+  return launch_squeeze(p, C(dense), C(q), S(st));
+}
+
+extern "C" int jrb_density(jrb_plan* p, const double* q, const double* occ, double* rho,
+                           jrb_stream st) {
+  int rc = enter(p);
+  if (rc) return rc;
+  REQUIRE(q && occ && rho, "null array");
+  return launch_density(p, C(q), occ, rho, S(st));
+}
+
+extern "C" int jrb_kinetic(jrb_plan* p, const double* q, double* t_skb, jrb_stream st) {
+  int rc = enter(p);
+  if (rc) return rc;
+  REQUIRE(q && t_skb, "null array");
+  return launch_kinetic(p, C(q), t_skb, S(st));
+}
+
+extern "C" int jrb_grid_potential(jrb_plan* p, const double* rho, int32_t xc_id,
+                                  int32_t kohn_sham, double* energies, double* veff,
+                                  jrb_stream st) {
+  int rc = enter(p);
+  if (rc) return rc;
+  REQUIRE(rho && energies && veff, "null array");
+  return launch_grid_potential(p, rho, xc_id, kohn_sham, energies, veff, S(st));
+}
+
+extern "C" int jrb_hpsi(jrb_plan* p, const double* q, const double* veff, double* hq,
+                        jrb_stream st) {
+  int rc = enter(p);
+  if (rc) return rc;
+  REQUIRE(q && veff && hq, "null array");
+  REQUIRE(q != hq, "hq must not alias q");
+  return launch_hpsi(p, C(q), veff, C(hq), S(st));
+}
+
+extern "C" int jrb_band_expect(jrb_plan* p, const double* q, const double* hq, double* eps,
+                               jrb_stream st) {
+  int rc = enter(p);
+  if (rc) return rc;
+  REQUIRE(q && hq && eps, "null array");
+  return launch_band_expect(p, C(q), C(hq), eps, S(st));
+}
+
+extern "C" int jrb_fft3d(jrb_plan* p, const double* in, double* out, int32_t direction,
+                         int64_t batch, jrb_stream st) {
+  int rc = enter(p);
+  if (rc) return rc;
+  REQUIRE(in && out, "null array");
+  REQUIRE(direction == JRB_FFT_FORWARD || direction == JRB_FFT_INVERSE, "bad direction");
+  REQUIRE(batch >= 0, "negative batch");
+  if (batch == 0) return 0;
+  const double scale = direction == JRB_FFT_INVERSE ? 1.0 / (double)p->ngrid : 1.0;
+  return launch_fft3d_dense(p, C(in), C(out), direction, batch, scale, S(st));
+}
+
+extern "C" int jrb_eval_begin(jrb_plan* p, const double* w_re, const double* w_im,
+                              const double* occ, double* rho, double* e_kin, jrb_stream st) {
+  int rc = enter(p);
+  if (rc) return rc;
+  REQUIRE(w_re && w_im && occ && rho && e_kin, "null array");
+  if ((rc = launch_qr_fwd(p, w_re, w_im, p->d_q, p->d_r, S(st)))) return rc;
+  if ((rc = launch_density(p, p->d_q, occ, rho, S(st)))) return rc;
+  if ((rc = launch_kinetic(p, p->d_q, p->d_tkb, S(st)))) return rc;
+  return launch_weighted_sum(p, p->d_tkb, occ, (int64_t)p->ns * p->nk * p->nb, e_kin, S(st));
+}
+
+__global__ void k_pack_energies(const double* e_kin, const double* grid_e, double* out) {
+  // reference order of total_energy(split=True): kinetic, external, hartree, xc
+  out[0] = e_kin[0];
+  out[1] = grid_e[1];
+  out[2] = grid_e[0];
+  out[3] = grid_e[2];
+}
+
+extern "C" int jrb_eval_finish(jrb_plan* p, const double* occ, const double* rho,
+                               const double* e_kin, int32_t xc_id, double* energies, double* g_re,
+                               double* g_im, double* g_occ, jrb_stream st) {
+  int rc = enter(p);
+  if (rc) return rc;
+  REQUIRE(occ && rho && e_kin && energies && g_re && g_im, "null array");
+  double* grid_e = p->d_scal;            // E_H, E_ext, E_xc
+  double* veff = p->d_veff;
+  if ((rc = launch_grid_potential(p, rho, xc_id, 0, grid_e, veff, S(st)))) return rc;
+  if ((rc = launch_hpsi(p, p->d_q, veff, p->d_hq, S(st)))) return rc;
+  if (g_occ) {
+    if ((rc = launch_band_expect(p, p->d_q, p->d_hq, g_occ, S(st)))) return rc;
+  }
+  if ((rc = launch_qr_bwd(p, p->d_q, p->d_r, p->d_hq, occ, g_re, g_im, S(st)))) return rc;
+  k_pack_energies<<<1, 1, 0, S(st)>>>(e_kin, grid_e, energies);
+  JRB_CHECK_LAUNCH("k_pack_energies");
+  return 0;
+}
+
+static int ensure_host_buffers(jrb_plan* p) {
+  if (p->d_wre) return 0;
+  const size_t nw = (size_t)p->ns * p->nk * p->ng * p->nb;
+  const size_t no = (size_t)p->ns * p->nk * p->nb;
+  JRB_CUDA(cudaMalloc(&p->d_wre, nw * sizeof(double)));
+  JRB_CUDA(cudaMalloc(&p->d_wim, nw * sizeof(double)));
+  JRB_CUDA(cudaMalloc(&p->d_gre, nw * sizeof(double)));
+  JRB_CUDA(cudaMalloc(&p->d_gim, nw * sizeof(double)));
+  JRB_CUDA(cudaMalloc(&p->d_occ, no * sizeof(double)));
+  JRB_CUDA(cudaMalloc(&p->d_rho, (size_t)p->ns * p->ngrid * sizeof(double)));
+  JRB_CUDA(cudaMalloc(&p->d_en, 8 * sizeof(double)));
+  p->ws_bytes += (int64_t)((4 * nw + no + 8) * sizeof(double) + (size_t)p->ns * p->ngrid * 8);
+  return 0;
+}
+
+extern "C" int jrb_energy_grad_host(jrb_plan* p, const double* w_re_h, const double* w_im_h,
+                                    const double* occ_h, int32_t xc_id, double* energies_h,
+                                    double* g_re_h, double* g_im_h, double* rho_h) {
+  int rc = enter(p);
+  if (rc) return rc;
+  REQUIRE(w_re_h && w_im_h && occ_h && energies_h && g_re_h && g_im_h, "null array");
+  if ((rc = ensure_host_buffers(p))) return rc;
+  cudaStream_t st = p->own_stream;
+  const size_t nw = (size_t)p->ns * p->nk * p->ng * p->nb * sizeof(double);
+  const size_t no = (size_t)p->ns * p->nk * p->nb * sizeof(double);
+  double* rho = p->d_rho;
+  JRB_CUDA(cudaMemcpyAsync(p->d_wre, w_re_h, nw, cudaMemcpyHostToDevice, st));
+  JRB_CUDA(cudaMemcpyAsync(p->d_wim, w_im_h, nw, cudaMemcpyHostToDevice, st));
+  JRB_CUDA(cudaMemcpyAsync(p->d_occ, occ_h, no, cudaMemcpyHostToDevice, st));
+  if ((rc = jrb_eval_begin(p, p->d_wre, p->d_wim, p->d_occ, rho, p->d_en + 4, st))) return rc;
+  if ((rc = jrb_eval_finish(p, p->d_occ, rho, p->d_en + 4, xc_id, p->d_en, p->d_gre, p->d_gim,
+                            nullptr, st)))
+    return rc;
+  JRB_CUDA(cudaMemcpyAsync(energies_h, p->d_en, 4 * sizeof(double), cudaMemcpyDeviceToHost, st));
+  JRB_CUDA(cudaMemcpyAsync(g_re_h, p->d_gre, nw, cudaMemcpyDeviceToHost, st));
+  JRB_CUDA(cudaMemcpyAsync(g_im_h, p->d_gim, nw, cudaMemcpyDeviceToHost, st));
+  if (rho_h)
+    JRB_CUDA(cudaMemcpyAsync(rho_h, rho, (size_t)p->ns * p->ngrid * sizeof(double),
+                             cudaMemcpyDeviceToHost, st));
+  JRB_CUDA(cudaStreamSynchronize(st));
+  int fail = 0;
+  JRB_CUDA(cudaMemcpy(&fail, reinterpret_cast<int*>(p->d_scal + 32), sizeof(int),
+                      cudaMemcpyDeviceToHost));
+  if (fail) {
+    set_error("Cholesky-QR: Gram matrix not positive definite (rank-deficient parameters)");
+    return JRB_EINVAL;
+  }
+  return 0;
+}

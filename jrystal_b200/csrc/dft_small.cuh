@@ -19,7 +19,7 @@
 
 namespace jrb {
 
-struct cplx {
+struct alignas(16) cplx {
   double x, y;
 };
 

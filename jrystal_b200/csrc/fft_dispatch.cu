@@ -1,0 +1,129 @@
+// Host-side orchestration of the pencil passes: batching of band groups, spin handling,
+// and the dense 3-pass transform behind jrb_fft3d.
+#include <algorithm>
+
+#include "fft_passes.cuh"
+#include "plan.h"
+
+namespace jrb {
+
+static int run_pass(PassKind kind, int n, const PassArgs& a, cudaStream_t st) {
+  int rc = pass_group0(kind, n, a, st);
+  if (rc == 1) rc = pass_group1(kind, n, a, st);
+  if (rc == 1) rc = pass_group2(kind, n, a, st);
+  if (rc == 1) rc = pass_group3(kind, n, a, st);
+  if (rc == 1) {
+    set_error("no compiled pencil pass for axis length " + std::to_string(n));
+    return JRB_EUNSUPPORTED;
+  }
+  return rc;
+}
+
+static int run_dense(int n, const DenseArgs& a, int dir, long long batch, cudaStream_t st) {
+  int rc = dense_group0(n, a, dir, batch, st);
+  if (rc == 1) rc = dense_group1(n, a, dir, batch, st);
+  if (rc == 1) rc = dense_group2(n, a, dir, batch, st);
+  if (rc == 1) rc = dense_group3(n, a, dir, batch, st);
+  if (rc == 1) {
+    set_error("no compiled dense line FFT for axis length " + std::to_string(n));
+    return JRB_EUNSUPPORTED;
+  }
+  return rc;
+}
+
+static PassArgs base_args(jrb_plan* p) {
+  PassArgs a{};
+  a.m = p->maps;
+  a.wa = p->d_ws_a;
+  a.wb = p->d_ws_b;
+  a.focc = p->d_focc;
+  a.gk2 = p->d_gk2;
+  a.nb = p->nb;
+  a.nk = p->nk;
+  a.ngpk = p->ngroups_per_k;
+  a.vscale = 1.0 / (double)p->ngrid;
+  return a;
+}
+
+// rho[s] = sum_{k,b} occ |psi|^2  (jrb_density).  d_focc must hold occ / Omega per group lane.
+int launch_density(jrb_plan* p, const cplx* q, const double* occ, double* rho, cudaStream_t st) {
+  int rc = launch_focc(p, occ, st);
+  if (rc) return rc;
+  JRB_CUDA(cudaMemsetAsync(rho, 0, sizeof(double) * (size_t)p->ns * p->ngrid, st));
+  const int per_spin = p->nk * p->ngroups_per_k;
+  for (int s = 0; s < p->ns; ++s) {
+    for (int g0 = 0; g0 < per_spin; g0 += p->batch_groups) {
+      PassArgs a = base_args(p);
+      a.q = q;
+      a.g0 = s * per_spin + g0;
+      a.ngroups = std::min(p->batch_groups, per_spin - g0);
+      a.rho = rho + (size_t)s * p->ngrid;
+      a.tw = p->d_tw_z;
+      if ((rc = run_pass(PASS_Z_INV_SCATTER, p->nz, a, st))) return rc;
+      a.tw = p->d_tw_y;
+      if ((rc = run_pass(PASS_Y_INV, p->ny, a, st))) return rc;
+      a.tw = p->d_tw_x;
+      if ((rc = run_pass(PASS_X_DENSITY, p->nx, a, st))) return rc;
+    }
+  }
+  return 0;
+}
+
+// hq = 1/2|G+k|^2 q + (sqrt(Omega)/N) fftn(veff psi)|mask   (jrb_hpsi)
+int launch_hpsi(jrb_plan* p, const cplx* q, const double* veff, cplx* hq, cudaStream_t st) {
+  int rc = 0;
+  const int per_spin = p->nk * p->ngroups_per_k;
+  for (int s = 0; s < p->ns; ++s) {
+    for (int g0 = 0; g0 < per_spin; g0 += p->batch_groups) {
+      PassArgs a = base_args(p);
+      a.q = q;
+      a.hq = hq;
+      a.g0 = s * per_spin + g0;
+      a.ngroups = std::min(p->batch_groups, per_spin - g0);
+      a.veff = veff + (size_t)s * p->ngrid;
+      a.tw = p->d_tw_z;
+      if ((rc = run_pass(PASS_Z_INV_SCATTER, p->nz, a, st))) return rc;
+      a.tw = p->d_tw_y;
+      if ((rc = run_pass(PASS_Y_INV, p->ny, a, st))) return rc;
+      a.tw = p->d_tw_x;
+      if ((rc = run_pass(PASS_X_VMUL, p->nx, a, st))) return rc;
+      a.tw = p->d_tw_y;
+      if ((rc = run_pass(PASS_Y_FWD, p->ny, a, st))) return rc;
+      a.tw = p->d_tw_z;
+      if ((rc = run_pass(PASS_Z_FWD_GATHER, p->nz, a, st))) return rc;
+    }
+  }
+  return 0;
+}
+
+// Dense batched 3-D transform over (nx, ny, nz), C order; `scale` applied on the last pass.
+int launch_fft3d_dense(jrb_plan* p, const cplx* in, cplx* out, int dir, int64_t batch,
+                       double scale, cudaStream_t st) {
+  const long long nx = p->nx, ny = p->ny, nz = p->nz;
+  int rc = 0;
+  for (int64_t b0 = 0; b0 < batch; b0 += 32768) {
+    const long long nbat = std::min<int64_t>(32768, batch - b0);
+    const cplx* src = in + (size_t)b0 * p->ngrid;
+    cplx* dst = out + (size_t)b0 * p->ngrid;
+    DenseArgs a{};
+    a.batch_stride = p->ngrid;
+    // z lines: lanes over y (stride nz), one line group set per x
+    a.in = src; a.out = dst; a.tw = p->d_tw_z;
+    a.n0 = (int)nx; a.stride0 = ny * nz; a.lane_total = (int)ny; a.lane_stride = nz;
+    a.elem_stride = 1; a.scale = 1.0;
+    if ((rc = run_dense((int)nz, a, dir, nbat, st))) return rc;
+    // y lines: lanes over z
+    a.in = dst; a.out = dst; a.tw = p->d_tw_y;
+    a.n0 = (int)nx; a.stride0 = ny * nz; a.lane_total = (int)nz; a.lane_stride = 1;
+    a.elem_stride = nz; a.scale = 1.0;
+    if ((rc = run_dense((int)ny, a, dir, nbat, st))) return rc;
+    // x lines: lanes over z
+    a.in = dst; a.out = dst; a.tw = p->d_tw_x;
+    a.n0 = (int)ny; a.stride0 = nz; a.lane_total = (int)nz; a.lane_stride = 1;
+    a.elem_stride = ny * nz; a.scale = scale;
+    if ((rc = run_dense((int)nx, a, dir, nbat, st))) return rc;
+  }
+  return 0;
+}
+
+}  // namespace jrb

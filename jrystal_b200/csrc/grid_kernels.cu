@@ -1,0 +1,400 @@
+// Fused elementwise + reduction kernels on the FFT grid and on the plane-wave sphere:
+// Hartree / external / LDA-XC energies and the effective potential in one sweep each
+// (jrystal/_src/potential.py:58-77,153-166,255-279; energy.py:68-82,121-135,204-211;
+// xc.py:54-64,109-124), the per-orbital kinetic and band expectations on the sphere
+// (energy.py:172-180; braket.py:189-206) and the scatter/gather API-parity helpers
+// (utils.py:277-308).  All HBM-bound, FP64, deterministic two-stage reductions.
+#include <cmath>
+#include <vector>
+
+#include "plan.h"
+
+namespace jrb {
+
+constexpr int RED_THREADS = 256;
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// block-wide sum of up to NV values per thread; result valid on thread 0
+template <int NV>
+__device__ __forceinline__ void block_sum(double (&v)[NV], double* out /* [NV] */) {
+  __shared__ double sh[NV][RED_THREADS / 32];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    double s = warp_sum(v[i]);
+    if (lane == 0) sh[i][w] = s;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      double s = 0;
+      for (int j = 0; j < (int)(blockDim.x >> 5); ++j) s += sh[i][j];
+      out[i] = s;
+    }
+  }
+  __syncthreads();
+}
+
+__device__ __forceinline__ int fftfreq_int(int i, int n) { return i < (n + 1) / 2 ? i : i - n; }
+
+struct GridGeom {
+  int nx, ny, nz;
+  long long n;
+  double b[9];  // rows b1, b2, b3
+  double vol;
+};
+
+__device__ __forceinline__ void g_of(const GridGeom& g, long long lin, double& gx, double& gy,
+                                     double& gz) {
+  const int z = (int)(lin % g.nz);
+  const int y = (int)((lin / g.nz) % g.ny);
+  const int x = (int)(lin / ((long long)g.nz * g.ny));
+  const double fx = fftfreq_int(x, g.nx), fy = fftfreq_int(y, g.ny), fz = fftfreq_int(z, g.nz);
+  gx = fx * g.b[0] + fy * g.b[3] + fz * g.b[6];
+  gy = fx * g.b[1] + fy * g.b[4] + fz * g.b[7];
+  gz = fx * g.b[2] + fy * g.b[5] + fz * g.b[8];
+}
+
+static GridGeom geom_of(const jrb_plan* p) {
+  GridGeom g;
+  g.nx = p->nx; g.ny = p->ny; g.nz = p->nz; g.n = p->ngrid; g.vol = p->vol;
+  for (int i = 0; i < 9; ++i) g.b[i] = p->recip[i];
+  return g;
+}
+
+// ---------------------------------------------------------------------------------------
+// V_ext(G) = -(N/Omega) 4 pi sum_a Z_a exp(-i G.R_a) / (|G|^2 + 1e-10), V_ext(0) = 0
+__global__ void k_vext(GridGeom g, const double* __restrict__ pos, const double* __restrict__ chg,
+                       int na, cplx* __restrict__ vext) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < g.n;
+       i += (long long)gridDim.x * blockDim.x) {
+    double gx, gy, gz;
+    g_of(g, i, gx, gy, gz);
+    const double g2 = gx * gx + gy * gy + gz * gz;
+    double re = 0, im = 0;
+    if (i != 0) {
+      for (int a = 0; a < na; ++a) {
+        const double ph = gx * pos[3 * a] + gy * pos[3 * a + 1] + gz * pos[3 * a + 2];
+        double s, c;
+        sincos(ph, &s, &c);
+        const double vi = chg[a] / (g2 + 1e-10) * (4.0 * M_PI);
+        re += vi * c;
+        im -= vi * s;
+      }
+    }
+    const double f = -(double)g.n / g.vol;
+    vext[i] = cmake(re * f, im * f);
+  }
+}
+
+int launch_set_atoms(jrb_plan* p, const double* pos_h, const double* chg_h, int na,
+                     cudaStream_t st) {
+  if (na <= 0 || !pos_h || !chg_h) {
+    set_error("jrb_set_atoms: need natoms > 0 and non-null positions/charges");
+    return JRB_EINVAL;
+  }
+  double *dpos = nullptr, *dchg = nullptr;
+  JRB_CUDA(cudaMalloc(&dpos, sizeof(double) * 3 * na));
+  JRB_CUDA(cudaMalloc(&dchg, sizeof(double) * na));
+  JRB_CUDA(cudaMemcpyAsync(dpos, pos_h, sizeof(double) * 3 * na, cudaMemcpyHostToDevice, st));
+  JRB_CUDA(cudaMemcpyAsync(dchg, chg_h, sizeof(double) * na, cudaMemcpyHostToDevice, st));
+  const int blocks = (int)std::min<long long>((p->ngrid + 255) / 256, 148 * 8);
+  k_vext<<<blocks, 256, 0, st>>>(geom_of(p), dpos, dchg, na, p->d_vext);
+  JRB_CHECK_LAUNCH("k_vext");
+  JRB_CUDA(cudaStreamSynchronize(st));
+  cudaFree(dpos);
+  cudaFree(dchg);
+  p->natoms = na;
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------
+__global__ void k_rho_to_complex(const double* __restrict__ rho, int ns, long long n,
+                                 cplx* __restrict__ grid) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
+       i += (long long)gridDim.x * blockDim.x) {
+    double v = rho[i];
+    if (ns == 2) v += rho[n + i];
+    grid[i] = cmake(v, 0.0);
+  }
+}
+
+// n(G) -> E_H, E_ext partial sums and v_H(G) + V_ext(G) in place.
+__global__ void __launch_bounds__(RED_THREADS)
+k_hartree_ext(GridGeom g, cplx* __restrict__ grid, const cplx* __restrict__ vext, int kohn_sham,
+              double* __restrict__ partials) {
+  double acc[2] = {0.0, 0.0};
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < g.n;
+       i += (long long)gridDim.x * blockDim.x) {
+    double gx, gy, gz;
+    g_of(g, i, gx, gy, gz);
+    const double g2 = gx * gx + gy * gy + gz * gz;
+    const cplx nG = grid[i];
+    const cplx ve = vext[i];
+    cplx vh = cmake(0.0, 0.0);
+    if (i != 0) {
+      const double f = 4.0 * M_PI / g2;
+      vh = cmake(nG.x * f, nG.y * f);
+    }
+    // Re conj(v) n
+    acc[0] += vh.x * nG.x + vh.y * nG.y;
+    acc[1] += ve.x * nG.x + ve.y * nG.y;
+    grid[i] = cmake(vh.x + ve.x, vh.y + ve.y);
+  }
+  double out[2];
+  block_sum<2>(acc, out);
+  if (threadIdx.x == 0) {
+    const double w = g.vol / ((double)g.n * (double)g.n);
+    partials[blockIdx.x * 4 + 0] = out[0] * w * (kohn_sham ? 1.0 : 0.5);
+    partials[blockIdx.x * 4 + 1] = out[1] * w;
+  }
+}
+
+// LDA energy density per particle and its derivative for the unpolarised gas.
+__device__ __forceinline__ void lda_eps(int xc_id, double n, double& eps, double& deps) {
+  const double thr = 1e-15;  // LibXC dens_threshold
+  eps = 0.0;
+  deps = 0.0;
+  if (!(n > thr)) return;
+  const double cx = -0.73855876638202240588;  // -3/4 (3/pi)^(1/3)
+  const double c13 = cbrt(n);
+  eps = cx * c13;
+  deps = eps / (3.0 * n);
+  if (xc_id == JRB_XC_LDA_X_C_PW) {
+    const double A = 0.031091, a1 = 0.21370, b1 = 7.5957, b2 = 3.5876, b3 = 1.6382, b4 = 0.49294;
+    const double rs = cbrt(3.0 / (4.0 * M_PI * n));
+    const double sr = sqrt(rs);
+    const double Q = 2.0 * A * (b1 * sr + b2 * rs + b3 * rs * sr + b4 * rs * rs);
+    const double dQ = 2.0 * A * (0.5 * b1 / sr + b2 + 1.5 * b3 * sr + 2.0 * b4 * rs);
+    const double L = log1p(1.0 / Q);
+    const double ec = -2.0 * A * (1.0 + a1 * rs) * L;
+    const double dec_drs = -2.0 * A * a1 * L + 2.0 * A * (1.0 + a1 * rs) * dQ / (Q * Q + Q);
+    eps += ec;
+    deps += dec_drs * (-rs / (3.0 * n));
+  }
+}
+
+// v_HE(r) (complex, already / N) + xc -> veff[s], E_xc partial sums.
+__global__ void __launch_bounds__(RED_THREADS)
+k_veff_xc(GridGeom g, const cplx* __restrict__ grid, const double* __restrict__ rho, int ns,
+          int xc_id, int kohn_sham, double* __restrict__ veff, double* __restrict__ partials) {
+  double acc[1] = {0.0};
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < g.n;
+       i += (long long)gridDim.x * blockDim.x) {
+    const double vhe = grid[i].x;
+    if (ns == 1) {
+      const double n = rho[i];
+      double e, de;
+      lda_eps(xc_id, n, e, de);
+      const double vxc = e + n * de;
+      veff[i] = vhe + vxc;
+      acc[0] += (kohn_sham ? vxc : e) * n;
+    } else {
+      // exchange only: eps = 1/2 [eps_x(2 rho_up) + eps_x(2 rho_dn)]  (xc.py:56-59)
+      const double ru = rho[i], rd = rho[g.n + i];
+      double eu, deu, ed, ded;
+      lda_eps(JRB_XC_LDA_X, 2.0 * ru, eu, deu);
+      lda_eps(JRB_XC_LDA_X, 2.0 * rd, ed, ded);
+      const double e = 0.5 * (eu + ed);
+      const double n = ru + rd;
+      // d eps / d rho_s = eps_x'(2 rho_s)
+      if (kohn_sham) {
+        // reference vxc_lda (xc.py:114-122): v_s = eps + rho_s d eps/d rho_s
+        const double vu = e + ru * deu, vd = e + rd * ded;
+        veff[i] = vhe + vu;
+        veff[g.n + i] = vhe + vd;
+        acc[0] += vu * ru + vd * rd;
+      } else {
+        veff[i] = vhe + e + n * deu;
+        veff[g.n + i] = vhe + e + n * ded;
+        acc[0] += e * n;
+      }
+    }
+  }
+  double out[1];
+  block_sum<1>(acc, out);
+  if (threadIdx.x == 0) partials[blockIdx.x * 4 + 2] = out[0] * g.vol / (double)g.n;
+}
+
+__global__ void k_reduce_partials(const double* __restrict__ partials, int nblocks, int ncomp,
+                                  double* __restrict__ out) {
+  // one warp per component, fixed order -> deterministic
+  const int c = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (c >= ncomp) return;
+  double s = 0.0;
+  for (int i = lane; i < nblocks; i += 32) s += partials[i * 4 + c];
+  s = warp_sum(s);
+  if (lane == 0) out[c] = s;
+}
+
+int launch_grid_potential(jrb_plan* p, const double* rho, int xc_id, int kohn_sham,
+                          double* energies, double* veff, cudaStream_t st) {
+  if (xc_id != JRB_XC_LDA_X && xc_id != JRB_XC_LDA_X_C_PW) {
+    set_error("jrb_grid_potential: unsupported xc id (LDA only: lda_x, lda_x+lda_c_pw)");
+    return JRB_EUNSUPPORTED;
+  }
+  if (p->ns == 2 && xc_id != JRB_XC_LDA_X) {
+    set_error("jrb_grid_potential: spin-polarised correlation is not implemented");
+    return JRB_EUNSUPPORTED;
+  }
+  if (p->natoms <= 0) {
+    set_error("jrb_grid_potential: call jrb_set_atoms first");
+    return JRB_EINVAL;
+  }
+  const GridGeom g = geom_of(p);
+  const int blocks = (int)std::min<long long>((p->ngrid + RED_THREADS - 1) / RED_THREADS,
+                                              (long long)p->n_partial_blocks);
+  k_rho_to_complex<<<blocks, RED_THREADS, 0, st>>>(rho, p->ns, p->ngrid, p->d_grid);
+  JRB_CHECK_LAUNCH("k_rho_to_complex");
+  int rc = launch_fft3d_dense(p, p->d_grid, p->d_grid, JRB_FFT_FORWARD, 1, 1.0, st);
+  if (rc) return rc;
+  k_hartree_ext<<<blocks, RED_THREADS, 0, st>>>(g, p->d_grid, p->d_vext, kohn_sham, p->d_partials);
+  JRB_CHECK_LAUNCH("k_hartree_ext");
+  rc = launch_fft3d_dense(p, p->d_grid, p->d_grid, JRB_FFT_INVERSE, 1, 1.0 / (double)p->ngrid, st);
+  if (rc) return rc;
+  k_veff_xc<<<blocks, RED_THREADS, 0, st>>>(g, p->d_grid, rho, p->ns, xc_id, kohn_sham, veff,
+                                           p->d_partials);
+  JRB_CHECK_LAUNCH("k_veff_xc");
+  k_reduce_partials<<<1, 96, 0, st>>>(p->d_partials, blocks, 3, energies);
+  JRB_CHECK_LAUNCH("k_reduce_partials");
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------
+// sphere reductions: out[sk][b] = sum_g w(g) * f(q, hq)
+//   MODE 0: 1/2 |G+k|^2 |q|^2        (kinetic)
+//   MODE 1: Re conj(q) hq            (band expectation)
+// grid: (ceil(nb / 32), ns*nk), block (32, 8)
+template <int MODE>
+__global__ void __launch_bounds__(256)
+k_sphere_reduce(const cplx* __restrict__ q, const cplx* __restrict__ hq,
+                const double* __restrict__ gk2, long long ng, int nb, int nk,
+                double* __restrict__ out) {
+  const int b = blockIdx.x * 32 + threadIdx.x;
+  const int sk = blockIdx.y;
+  const int k = sk % nk;
+  double acc = 0.0;
+  if (b < nb) {
+    const cplx* qp = q + ((long long)sk * ng) * nb + b;
+    const cplx* hp = MODE == 1 ? hq + ((long long)sk * ng) * nb + b : nullptr;
+    for (long long g = threadIdx.y; g < ng; g += blockDim.y) {
+      const cplx c = qp[g * nb];
+      if (MODE == 0) {
+        acc += gk2[(long long)k * ng + g] * (c.x * c.x + c.y * c.y);
+      } else {
+        const cplx h = hp[g * nb];
+        acc += c.x * h.x + c.y * h.y;
+      }
+    }
+  }
+  __shared__ double sh[8][33];
+  sh[threadIdx.y][threadIdx.x] = acc;
+  __syncthreads();
+  if (threadIdx.y == 0 && b < nb) {
+    double s = 0.0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) s += sh[j][threadIdx.x];
+    out[(long long)sk * nb + b] = MODE == 0 ? 0.5 * s : s;
+  }
+}
+
+int launch_kinetic(jrb_plan* p, const cplx* q, double* t_skb, cudaStream_t st) {
+  dim3 grid((p->nb + 31) / 32, p->ns * p->nk), block(32, 8);
+  k_sphere_reduce<0><<<grid, block, 0, st>>>(q, nullptr, p->d_gk2, p->ng, p->nb, p->nk, t_skb);
+  JRB_CHECK_LAUNCH("k_sphere_reduce<kinetic>");
+  return 0;
+}
+
+int launch_band_expect(jrb_plan* p, const cplx* q, const cplx* hq, double* eps, cudaStream_t st) {
+  dim3 grid((p->nb + 31) / 32, p->ns * p->nk), block(32, 8);
+  k_sphere_reduce<1><<<grid, block, 0, st>>>(q, hq, p->d_gk2, p->ng, p->nb, p->nk, eps);
+  JRB_CHECK_LAUNCH("k_sphere_reduce<expect>");
+  return 0;
+}
+
+// out[0] = sum_i a[i] w[i]   (single block, fixed order)
+__global__ void __launch_bounds__(RED_THREADS)
+k_weighted_sum(const double* __restrict__ a, const double* __restrict__ w, long long n,
+               double* __restrict__ out) {
+  double acc[1] = {0.0};
+  for (long long i = threadIdx.x; i < n; i += blockDim.x) acc[0] += a[i] * w[i];
+  double r[1];
+  block_sum<1>(acc, r);
+  if (threadIdx.x == 0) out[0] = r[0];
+}
+
+int launch_weighted_sum(jrb_plan* p, const double* a, const double* w, int64_t n, double* out,
+                        cudaStream_t st) {
+  (void)p;
+  k_weighted_sum<<<1, RED_THREADS, 0, st>>>(a, w, n, out);
+  JRB_CHECK_LAUNCH("k_weighted_sum");
+  return 0;
+}
+
+// focc[group][lane] = occ[sk][b0 + lane] / Omega, zero padded
+__global__ void k_focc(const double* __restrict__ occ, int nb, int ngpk, int total_groups,
+                       double inv_vol, double* __restrict__ focc) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total_groups * NB) return;
+  const int gid = i / NB, lane = i % NB;
+  const int sk = gid / ngpk, b = (gid % ngpk) * NB + lane;
+  focc[i] = b < nb ? occ[(long long)sk * nb + b] * inv_vol : 0.0;
+}
+
+int launch_focc(jrb_plan* p, const double* occ, cudaStream_t st) {
+  const int total = p->ns * p->nk * p->ngroups_per_k;
+  k_focc<<<(total * NB + 255) / 256, 256, 0, st>>>(occ, p->nb, p->ngroups_per_k, total,
+                                                  1.0 / p->vol, p->d_focc);
+  JRB_CHECK_LAUNCH("k_focc");
+  return 0;
+}
+
+// dense[(sk*nb + b)*N + gidx[g]] = q[(sk*ng + g)*nb + b]   (dense pre-zeroed)
+__global__ void k_expand(const cplx* __restrict__ q, const int32_t* __restrict__ gidx,
+                         long long ng, int nb, long long n, long long total,
+                         cplx* __restrict__ dense) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int b = (int)(i % nb);
+    const long long g = (i / nb) % ng;
+    const long long sk = i / ((long long)nb * ng);
+    dense[(sk * nb + b) * n + gidx[g]] = q[i];
+  }
+}
+
+__global__ void k_squeeze(const cplx* __restrict__ dense, const int32_t* __restrict__ gidx,
+                          long long ng, int nb, long long n, long long total,
+                          cplx* __restrict__ q) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int b = (int)(i % nb);
+    const long long g = (i / nb) % ng;
+    const long long sk = i / ((long long)nb * ng);
+    q[i] = dense[(sk * nb + b) * n + gidx[g]];
+  }
+}
+
+int launch_expand(jrb_plan* p, const cplx* q, cplx* dense, cudaStream_t st) {
+  const long long total = (long long)p->ns * p->nk * p->ng * p->nb;
+  JRB_CUDA(cudaMemsetAsync(dense, 0, sizeof(cplx) * (size_t)p->ns * p->nk * p->nb * p->ngrid, st));
+  const int blocks = (int)std::min<long long>((total + 255) / 256, 148 * 16);
+  k_expand<<<blocks, 256, 0, st>>>(q, p->d_gidx, p->ng, p->nb, p->ngrid, total, dense);
+  JRB_CHECK_LAUNCH("k_expand");
+  return 0;
+}
+
+int launch_squeeze(jrb_plan* p, const cplx* dense, cplx* q, cudaStream_t st) {
+  const long long total = (long long)p->ns * p->nk * p->ng * p->nb;
+  const int blocks = (int)std::min<long long>((total + 255) / 256, 148 * 16);
+  k_squeeze<<<blocks, 256, 0, st>>>(dense, p->d_gidx, p->ng, p->nb, p->ngrid, total, q);
+  JRB_CHECK_LAUNCH("k_squeeze");
+  return 0;
+}
+
+}  // namespace jrb

@@ -1,0 +1,289 @@
+// Plan construction: mask -> pruning index maps, |G+k|^2 tables, twiddles, work space.
+// Host-side restatement of what the reference's drivers prepare before the loop
+// (jrystal/calc/calc_ground_state_energy_all_electrons.py:93-106 via grid.g_vectors,
+// jrystal/_src/grid.py:93-149, and the C-order mask enumeration of utils.py:279-281).
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+#include "fft_passes.cuh"
+#include "plan.h"
+
+namespace jrb {
+
+static thread_local std::string g_last_error;
+
+void set_error(const std::string& msg) { g_last_error = msg; }
+
+int cuda_fail(cudaError_t e, const char* what) {
+  g_last_error = std::string("CUDA error: ") + cudaGetErrorString(e) + " in " + what;
+  return JRB_ECUDA;
+}
+
+const char* last_error_cstr() { return g_last_error.c_str(); }
+
+bool line_length_supported(int n) {
+  PassArgs dummy{};
+  (void)dummy;
+  switch (n) {
+    case 7: case 8: case 9: case 12: case 16: case 24: case 32: case 48: case 64: case 72:
+    case 96: case 128:
+      return true;
+    default:
+      return false;
+  }
+}
+
+// np.fft.fftfreq(n, 1/n): 0..ceil(n/2)-1, -floor(n/2)..-1   (jrystal/_src/grid.py:115-117)
+static inline int fftfreq_int(int i, int n) { return i < (n + 1) / 2 ? i : i - n; }
+
+static void invert3x3(const double* a, double* inv, double* det_out) {
+  const double det = a[0] * (a[4] * a[8] - a[5] * a[7]) - a[1] * (a[3] * a[8] - a[5] * a[6]) +
+                     a[2] * (a[3] * a[7] - a[4] * a[6]);
+  *det_out = det;
+  inv[0] = (a[4] * a[8] - a[5] * a[7]) / det;
+  inv[1] = (a[2] * a[7] - a[1] * a[8]) / det;
+  inv[2] = (a[1] * a[5] - a[2] * a[4]) / det;
+  inv[3] = (a[5] * a[6] - a[3] * a[8]) / det;
+  inv[4] = (a[0] * a[8] - a[2] * a[6]) / det;
+  inv[5] = (a[2] * a[3] - a[0] * a[5]) / det;
+  inv[6] = (a[3] * a[7] - a[4] * a[6]) / det;
+  inv[7] = (a[1] * a[6] - a[0] * a[7]) / det;
+  inv[8] = (a[0] * a[4] - a[1] * a[3]) / det;
+}
+
+template <class T>
+static int dev_alloc(T** p, size_t count, int64_t* total) {
+  *p = nullptr;
+  if (count == 0) count = 1;
+  cudaError_t e = cudaMalloc((void**)p, count * sizeof(T));
+  if (e != cudaSuccess) {
+    set_error(std::string("cudaMalloc failed: ") + cudaGetErrorString(e));
+    return JRB_ENOMEM;
+  }
+  *total += (int64_t)(count * sizeof(T));
+  return 0;
+}
+
+template <class T>
+static int upload(T** dptr, const std::vector<T>& h, int64_t* total) {
+  int rc = dev_alloc(dptr, h.size(), total);
+  if (rc) return rc;
+  if (!h.empty()) JRB_CUDA(cudaMemcpy(*dptr, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice));
+  return 0;
+}
+
+static std::vector<cplx> twiddle_table(int n) {
+  std::vector<cplx> t(n);
+  for (int i = 0; i < n; ++i) {
+    // exact quadrant reduction keeps the table accurate to < 1 ulp
+    const long double ang = 2.0L * 3.141592653589793238462643383279502884L * (long double)i / n;
+    t[i] = cmake((double)cosl(ang), (double)(-sinl(ang)));
+    if ((4 * i) % n == 0) {
+      const int q = (4 * i) / n;
+      const double c[4] = {1, 0, -1, 0}, s[4] = {0, -1, 0, 1};
+      t[i] = cmake(c[q], s[q]);
+    }
+  }
+  return t;
+}
+
+}  // namespace jrb
+
+using namespace jrb;
+
+extern "C" const char* jrb_last_error(void) { return jrb::last_error_cstr(); }
+extern "C" int jrb_version(void) { return 100; }
+
+extern "C" int64_t jrb_plan_num_g(const jrb_plan* p) { return p ? p->ng : -1; }
+extern "C" int64_t jrb_plan_workspace_bytes(const jrb_plan* p) { return p ? p->ws_bytes : -1; }
+
+extern "C" int jrb_plan_destroy(jrb_plan* p) {
+  if (!p) return 0;
+  cudaSetDevice(p->device);
+  void* ptrs[] = {p->d_zmap, p->d_ycol, p->d_xmap, p->d_gidx, p->d_gk2, p->d_tw_x, p->d_tw_y,
+                  p->d_tw_z, p->d_ws_a, p->d_ws_b, p->d_focc, p->d_grid, p->d_vext,
+                  p->d_partials, p->d_veff, p->d_q, p->d_hq, p->d_tmp, p->d_r, p->d_rinv, p->d_small, p->d_gpart,
+                  p->d_tkb, p->d_eps, p->d_scal, p->d_wre, p->d_wim, p->d_gre, p->d_gim,
+                  p->d_occ, p->d_rho, p->d_en};
+  for (void* q : ptrs)
+    if (q) cudaFree(q);
+  if (p->own_stream) cudaStreamDestroy(p->own_stream);
+  delete p;
+  return 0;
+}
+
+extern "C" int jrb_plan_create(const jrb_plan_desc* d, jrb_plan** out) {
+  if (!d || !out || !d->mask || !d->kpts || !d->cell) {
+    set_error("jrb_plan_create: null argument");
+    return JRB_EINVAL;
+  }
+  if (d->nx <= 0 || d->ny <= 0 || d->nz <= 0 || d->nk <= 0 || d->nb <= 0 ||
+      (d->ns != 1 && d->ns != 2)) {
+    set_error("jrb_plan_create: bad sizes (need nx,ny,nz,nk,nb > 0 and ns in {1,2})");
+    return JRB_EINVAL;
+  }
+  const int dims[3] = {d->nx, d->ny, d->nz};
+  for (int i = 0; i < 3; ++i) {
+    if (!line_length_supported(dims[i])) {
+      set_error("jrb_plan_create: FFT length " + std::to_string(dims[i]) +
+                " has no compiled line plan (supported: 7 8 9 12 16 24 32 48 64 72 96 128)");
+      return JRB_EUNSUPPORTED;
+    }
+  }
+  int ndev = 0;
+  JRB_CUDA(cudaGetDeviceCount(&ndev));
+  if (d->device < 0 || d->device >= ndev) {
+    set_error("jrb_plan_create: bad device ordinal");
+    return JRB_EINVAL;
+  }
+  JRB_CUDA(cudaSetDevice(d->device));
+
+  jrb_plan* p = new jrb_plan();
+  std::memset(p, 0, sizeof(*p));
+  p->nx = d->nx; p->ny = d->ny; p->nz = d->nz;
+  p->ns = d->ns; p->nk = d->nk; p->nb = d->nb;
+  p->device = d->device;
+  p->ngrid = (int64_t)d->nx * d->ny * d->nz;
+  p->ngroups_per_k = (d->nb + NB - 1) / NB;
+  std::memcpy(p->cell, d->cell, sizeof(double) * 9);
+  double inv[9], det;
+  invert3x3(p->cell, inv, &det);
+  p->vol = std::fabs(det);
+  if (!(p->vol > 0)) {
+    delete p;
+    set_error("jrb_plan_create: singular cell");
+    return JRB_EINVAL;
+  }
+  // B = 2 pi inv(A)^T, rows b_i
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) p->recip[i * 3 + j] = 2.0 * M_PI * inv[j * 3 + i];
+
+  const int nx = p->nx, ny = p->ny, nz = p->nz;
+  // --- index maps -------------------------------------------------------------------
+  std::vector<int32_t> colid((size_t)nx * ny, -1), xmap(nx, -1), gidx;
+  std::vector<int32_t> zmap, ycol;
+  int ncol = 0, nxo = 0;
+  int64_t ng = 0;
+  for (int x = 0; x < nx; ++x) {
+    bool any_x = false;
+    for (int y = 0; y < ny; ++y) {
+      bool any = false;
+      for (int z = 0; z < nz; ++z)
+        if (d->mask[((size_t)x * ny + y) * nz + z]) { any = true; break; }
+      if (any) { colid[(size_t)x * ny + y] = ncol++; any_x = true; }
+    }
+    if (any_x) xmap[x] = nxo++;
+  }
+  zmap.assign((size_t)std::max(ncol, 1) * nz, -1);
+  ycol.assign((size_t)std::max(nxo, 1) * ny, -1);
+  for (int x = 0; x < nx; ++x)
+    for (int y = 0; y < ny; ++y) {
+      const int c = colid[(size_t)x * ny + y];
+      if (c < 0) continue;
+      ycol[(size_t)xmap[x] * ny + y] = c;
+      for (int z = 0; z < nz; ++z)
+        if (d->mask[((size_t)x * ny + y) * nz + z]) {
+          zmap[(size_t)c * nz + z] = (int32_t)ng++;
+          gidx.push_back((int32_t)(((size_t)x * ny + y) * nz + z));
+        }
+    }
+  if (ng == 0) {
+    delete p;
+    set_error("jrb_plan_create: empty mask");
+    return JRB_EINVAL;
+  }
+  p->ng = ng;
+  // --- |G+k|^2 on the sphere --------------------------------------------------------
+  std::vector<double> gk2((size_t)p->nk * ng);
+  {
+    std::vector<double> gv((size_t)ng * 3);
+    for (int64_t g = 0; g < ng; ++g) {
+      const int lin = gidx[g];
+      const int z = lin % nz, y = (lin / nz) % ny, x = lin / (nz * ny);
+      const double fx = fftfreq_int(x, nx), fy = fftfreq_int(y, ny), fz = fftfreq_int(z, nz);
+      for (int c = 0; c < 3; ++c)
+        gv[g * 3 + c] = fx * p->recip[0 + c] + fy * p->recip[3 + c] + fz * p->recip[6 + c];
+    }
+    for (int k = 0; k < p->nk; ++k)
+      for (int64_t g = 0; g < ng; ++g) {
+        double s = 0;
+        for (int c = 0; c < 3; ++c) {
+          const double v = gv[g * 3 + c] + d->kpts[k * 3 + c];
+          s += v * v;
+        }
+        gk2[(size_t)k * ng + g] = s;
+      }
+  }
+
+  int rc = 0;
+  int64_t tot = 0;
+#define TRY(x)                 \
+  do {                         \
+    rc = (x);                  \
+    if (rc) {                  \
+      jrb_plan_destroy(p);     \
+      return rc;               \
+    }                          \
+  } while (0)
+  TRY(upload(&p->d_zmap, zmap, &tot));
+  TRY(upload(&p->d_ycol, ycol, &tot));
+  TRY(upload(&p->d_xmap, xmap, &tot));
+  TRY(upload(&p->d_gidx, gidx, &tot));
+  TRY(upload(&p->d_gk2, gk2, &tot));
+  TRY(upload(&p->d_tw_x, twiddle_table(nx), &tot));
+  TRY(upload(&p->d_tw_y, twiddle_table(ny), &tot));
+  TRY(upload(&p->d_tw_z, twiddle_table(nz), &tot));
+  p->maps.nx = nx; p->maps.ny = ny; p->maps.nz = nz;
+  p->maps.ncol = ncol; p->maps.nxo = nxo; p->maps.ng = ng;
+  p->maps.zmap = p->d_zmap; p->maps.ycol = p->d_ycol; p->maps.xmap = p->d_xmap;
+  p->maps.gidx = p->d_gidx;
+
+  // --- pencil work space ------------------------------------------------------------
+  const int total_groups = p->ns * p->nk * p->ngroups_per_k;
+  const size_t b_per_group = (size_t)nxo * ny * nz * NB;  // complex numbers
+  const size_t a_per_group = (size_t)ncol * nz * NB;
+  int bg = d->batch_groups;
+  if (const char* env = std::getenv("JRB_BATCH_GROUPS")) bg = std::atoi(env);
+  if (bg <= 0) {
+    // automatic: keep the B slab of a batch near 48 MB so that a batch stays L2 resident
+    // (126 MB L2), but never fewer than 2 groups.
+    const double target = 48.0 * 1024 * 1024;
+    bg = (int)(target / ((double)b_per_group * sizeof(cplx)));
+    if (bg < 2) bg = 2;
+  }
+  if (bg > p->nk * p->ngroups_per_k) bg = p->nk * p->ngroups_per_k;  // never straddle a spin
+  if (bg > 65535) bg = 65535;
+  p->batch_groups = bg;
+  TRY(dev_alloc(&p->d_ws_a, a_per_group * bg, &tot));
+  TRY(dev_alloc(&p->d_ws_b, b_per_group * bg, &tot));
+  TRY(dev_alloc(&p->d_focc, (size_t)total_groups * NB, &tot));
+  // --- grid work space --------------------------------------------------------------
+  TRY(dev_alloc(&p->d_grid, (size_t)p->ngrid, &tot));
+  TRY(dev_alloc(&p->d_vext, (size_t)p->ngrid, &tot));
+  JRB_CUDA(cudaMemset(p->d_vext, 0, (size_t)p->ngrid * sizeof(cplx)));
+  TRY(dev_alloc(&p->d_veff, (size_t)p->ns * p->ngrid, &tot));
+  p->n_partial_blocks = 1024;
+  TRY(dev_alloc(&p->d_partials, (size_t)p->n_partial_blocks * 4, &tot));
+  // --- evaluation work space --------------------------------------------------------
+  const size_t nsphere = (size_t)p->ns * p->nk * ng * p->nb;
+  const size_t nsmall = (size_t)p->ns * p->nk * p->nb * p->nb;
+  TRY(dev_alloc(&p->d_q, nsphere, &tot));
+  TRY(dev_alloc(&p->d_hq, nsphere, &tot));
+  TRY(dev_alloc(&p->d_tmp, nsphere, &tot));
+  TRY(dev_alloc(&p->d_r, nsmall, &tot));
+  TRY(dev_alloc(&p->d_rinv, nsmall, &tot));
+  TRY(dev_alloc(&p->d_small, nsmall * 4, &tot));
+  TRY(dev_alloc(&p->d_gpart, nsmall * (size_t)qr_gram_chunks(p), &tot));
+  TRY(dev_alloc(&p->d_tkb, (size_t)p->ns * p->nk * p->nb, &tot));
+  TRY(dev_alloc(&p->d_eps, (size_t)p->ns * p->nk * p->nb, &tot));
+  TRY(dev_alloc(&p->d_scal, 64, &tot));
+  JRB_CUDA(cudaMemset(p->d_scal, 0, 64 * sizeof(double)));
+  JRB_CUDA(cudaStreamCreateWithFlags(&p->own_stream, cudaStreamNonBlocking));
+#undef TRY
+  p->ws_bytes = tot;
+  *out = p;
+  return 0;
+}

@@ -1,0 +1,107 @@
+// Internal plan object behind the opaque `jrb_plan` of include/jrystal_b200.h.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string>
+
+#include "../../include/jrystal_b200.h"
+#include "dft_small.cuh"
+
+namespace jrb {
+
+constexpr int NB = 8;  // band lanes per group: 8 x 16 B = one 128-byte line
+
+void set_error(const std::string& msg);
+int cuda_fail(cudaError_t e, const char* what);
+
+#define JRB_CUDA(expr)                                     \
+  do {                                                     \
+    cudaError_t e__ = (expr);                              \
+    if (e__ != cudaSuccess) return ::jrb::cuda_fail(e__, #expr); \
+  } while (0)
+
+#define JRB_CHECK_LAUNCH(name)                             \
+  do {                                                     \
+    cudaError_t e__ = cudaGetLastError();                  \
+    if (e__ != cudaSuccess) return ::jrb::cuda_fail(e__, name); \
+  } while (0)
+
+// Index maps derived from the frequency mask (all device pointers).
+struct SphereMaps {
+  int nx, ny, nz;
+  int ncol;   // (x, y) columns that contain at least one kept plane wave
+  int nxo;    // x planes that contain at least one such column
+  int64_t ng;
+  const int32_t* zmap;  // [ncol][nz]  compact index g of (col, z) or -1
+  const int32_t* ycol;  // [nxo][ny]   column id of (x plane, y) or -1
+  const int32_t* xmap;  // [nx]        x-plane id of x or -1
+  const int32_t* gidx;  // [ng]        linear index into the dense (nx,ny,nz) box
+};
+
+}  // namespace jrb
+
+struct jrb_plan {
+  int nx, ny, nz, ns, nk, nb;
+  int64_t ng, ngrid;
+  int device;
+  int ngroups_per_k;  // ceil(nb / NB)
+  int batch_groups;
+  double cell[9], recip[9], vol;
+  jrb::SphereMaps maps;
+  // owned device tables
+  int32_t *d_zmap, *d_ycol, *d_xmap, *d_gidx;
+  double* d_gk2;                 // [nk][ng]  |G+k|^2
+  jrb::cplx *d_tw_x, *d_tw_y, *d_tw_z;  // exp(-2 pi i t / n)
+  // pencil work space
+  jrb::cplx* d_ws_a;  // [batch][ncol][nz][NB]
+  jrb::cplx* d_ws_b;  // [batch][nxo][ny][nz][NB]
+  double* d_focc;     // [ns*nk*ngroups_per_k][NB] occupation / Omega, zero padded
+  // grid work space
+  jrb::cplx* d_grid;      // [ngrid] dense complex grid
+  jrb::cplx* d_vext;      // [ngrid] V_ext(G) incl. the reference's -N/Omega factor
+  double* d_partials;     // block partial sums for the grid reductions
+  double* d_veff;         // [ns][ngrid] effective potential of the fused evaluation
+  int n_partial_blocks;
+  int natoms;
+  // evaluation work space (Q, R, R^-1, HQ, W-sized temp)
+  jrb::cplx *d_q, *d_hq, *d_tmp;
+  jrb::cplx *d_r, *d_rinv, *d_small;  // [ns*nk][nb][nb] each (d_small: 4 of them)
+  jrb::cplx* d_gpart;                 // [chunks][ns*nk][nb][nb] split-K Gram partials
+  double *d_tkb, *d_eps;              // [ns*nk*nb]
+  double* d_scal;                     // small device scalars
+  cudaStream_t own_stream;
+  // host staging for jrb_energy_grad_host
+  double *d_wre, *d_wim, *d_gre, *d_gim, *d_occ, *d_rho, *d_en;
+  int64_t ws_bytes;
+};
+
+namespace jrb {
+
+// fft_passes_*.cu : pencil passes, dispatched on the axis length
+int launch_density(jrb_plan* p, const cplx* q, const double* occ, double* rho, cudaStream_t st);
+int launch_hpsi(jrb_plan* p, const cplx* q, const double* veff, cplx* hq, cudaStream_t st);
+int launch_fft3d_dense(jrb_plan* p, const cplx* in, cplx* out, int dir, int64_t batch,
+                       double scale, cudaStream_t st);
+bool line_length_supported(int n);
+
+// grid_kernels.cu
+int launch_set_atoms(jrb_plan* p, const double* pos_h, const double* chg_h, int na,
+                     cudaStream_t st);
+int launch_grid_potential(jrb_plan* p, const double* rho, int xc_id, int kohn_sham,
+                          double* energies, double* veff, cudaStream_t st);
+int launch_kinetic(jrb_plan* p, const cplx* q, double* t_skb, cudaStream_t st);
+int launch_band_expect(jrb_plan* p, const cplx* q, const cplx* hq, double* eps, cudaStream_t st);
+int launch_weighted_sum(jrb_plan* p, const double* a, const double* w, int64_t n, double* out,
+                        cudaStream_t st);
+int launch_expand(jrb_plan* p, const cplx* q, cplx* dense, cudaStream_t st);
+int launch_squeeze(jrb_plan* p, const cplx* dense, cplx* q, cudaStream_t st);
+int launch_focc(jrb_plan* p, const double* occ, cudaStream_t st);
+
+// qr.cu
+int qr_gram_chunks(const jrb_plan* p);
+int launch_qr_fwd(jrb_plan* p, const double* w_re, const double* w_im, cplx* q, cplx* r,
+                  cudaStream_t st);
+int launch_qr_bwd(jrb_plan* p, const cplx* q, const cplx* r, const cplx* gq, const double* occ,
+                  double* g_re, double* g_im, cudaStream_t st);
+
+}  // namespace jrb

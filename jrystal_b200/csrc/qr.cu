@@ -1,0 +1,548 @@
+// Orthonormalisation of the plane-wave coefficient matrix and its adjoint (K1).
+//
+// Replaces jnp.linalg.qr(w_re + i w_im, mode='reduced')[0] batched over (spin, k)
+// (jrystal/_src/unitary_module.py:66-81; XLA: cuSOLVER geqrf+orgqr) and the QR AD rule that
+// jax.value_and_grad applies to it (calc/calc_ground_state_energy_all_electrons.py:178).
+//
+// Algorithm: Cholesky-QR2.  S = W^H W (tall-skinny Gram on the FP64 tensor cores, DMMA
+// mma.sync.m8n8k4.f64 -- tcgen05/TMEM have no FP64 type), R = chol(S)^H, Q1 = W R1^-1, then the
+// same once more on Q1 for orthogonality at round-off level; R = R2 R1 has a real positive
+// diagonal (gauge documented in include/jrystal_b200.h).
+// Adjoint (DESIGN.md "Math"):  M = Q^H G,  X = -(up(M) + up(M)^H + diag Re M),
+//   dE/dW* = (G + Q X) R^-H  with G = HQ diag(occ)  ->  dE/dW* = HQ (F R^-H) + Q (X R^-H),
+// i.e. one more Gram-shaped product and one two-term tall-skinny product, both on DMMA.
+//
+// Complex products are 4 real DMMA products on separate re/im planes in shared memory
+// (leading dimensions == 4 mod 16 doubles make every fragment load bank-conflict free).
+#include <algorithm>
+#include <cmath>
+
+#include "plan.h"
+
+namespace jrb {
+
+constexpr int QT = 72;    // CTA tile edge: 3 x 3 warps of 24 x 24 (= 3 x 3 DMMA 8 x 8 tiles)
+constexpr int QK = 16;    // reduction rows staged per step
+constexpr int QLD = 84;   // padded leading dimension of [k][72] planes   (84 % 16 == 4)
+constexpr int QLDA = 20;  // padded leading dimension of [72][k=16] planes (20 % 16 == 4)
+constexpr int QTHREADS = 288;
+
+__device__ __forceinline__ void dmma(double (&c)[2], double a, double b) {
+  asm volatile(
+    "mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+    : "+d"(c[0]), "+d"(c[1])
+    : "d"(a), "d"(b));
+}
+
+// A tall matrix [rows][ld] given either as interleaved complex or as split re / im arrays.
+struct TallMat {
+  const double* re;
+  const double* im;  // nullptr => interleaved complex at `re`
+  long long ld;
+  __device__ __forceinline__ cplx get(long long r, int c) const {
+    if (im == nullptr) return reinterpret_cast<const cplx*>(re)[r * ld + c];
+    return cmake(re[r * ld + c], im[r * ld + c]);
+  }
+};
+
+// ---------------------------------------------------------------------------------------
+// partial[chunk][sk][i][j] = sum_{g in chunk} conj(A[g][i]) B[g][j]
+// grid: (tiles_i * tiles_j, nchunks, nsk), block 288
+__global__ void __launch_bounds__(QTHREADS)
+k_gram(TallMat A, TallMat B, long long ng, int nb, long long sk_stride_a, long long sk_stride_b,
+       int tiles, long long rows_per_chunk, cplx* __restrict__ partial) {
+  extern __shared__ __align__(16) unsigned char smem_raw_[];
+  double* sAre = reinterpret_cast<double*>(smem_raw_);
+  double* sAim = sAre + QK * QLD;
+  double* sBre = sAim + QK * QLD;
+  double* sBim = sBre + QK * QLD;
+
+  const int ti = blockIdx.x / tiles, tj = blockIdx.x % tiles;
+  const int chunk = blockIdx.y, sk = blockIdx.z;
+  const int nsk = gridDim.z;
+  const long long g_begin = (long long)chunk * rows_per_chunk;
+  const long long g_end = min(ng, g_begin + rows_per_chunk);
+  const int i0 = ti * QT, j0 = tj * QT;
+  TallMat a = A, bm = B;
+  a.re += sk * sk_stride_a * (a.im ? 1 : 2);
+  if (a.im) a.im += sk * sk_stride_a;
+  bm.re += sk * sk_stride_b * (bm.im ? 1 : 2);
+  if (bm.im) bm.im += sk * sk_stride_b;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int wi = warp / 3, wj = warp % 3;
+  const int lr = lane >> 2, lc = lane & 3;
+
+  double cre[3][3][2], cim[3][3][2];
+#pragma unroll
+  for (int s = 0; s < 3; ++s)
+#pragma unroll
+    for (int u = 0; u < 3; ++u) {
+      cre[s][u][0] = cre[s][u][1] = 0.0;
+      cim[s][u][0] = cim[s][u][1] = 0.0;
+    }
+
+  for (long long g0 = g_begin; g0 < g_end; g0 += QK) {
+    for (int e = threadIdx.x; e < QK * QT; e += QTHREADS) {
+      const int r = e / QT, c = e % QT;
+      const long long g = g0 + r;
+      cplx va = cmake(0.0, 0.0), vb = cmake(0.0, 0.0);
+      if (g < g_end) {
+        if (i0 + c < nb) va = a.get(g, i0 + c);
+        if (j0 + c < nb) vb = bm.get(g, j0 + c);
+      }
+      sAre[r * QLD + c] = va.x;
+      sAim[r * QLD + c] = va.y;
+      sBre[r * QLD + c] = vb.x;
+      sBim[r * QLD + c] = vb.y;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k4 = 0; k4 < QK / 4; ++k4) {
+      double ar[3], ai[3], nai[3], br[3], bi[3];
+#pragma unroll
+      for (int s = 0; s < 3; ++s) {
+        // A fragment (row = i, col = k): conj(A[g][i]) -> (re, -im)
+        const int ia = (k4 * 4 + lc) * QLD + wi * 24 + s * 8 + lr;
+        ar[s] = sAre[ia];
+        ai[s] = sAim[ia];
+        nai[s] = -ai[s];
+        // B fragment (row = k, col = j)
+        const int ib = (k4 * 4 + lc) * QLD + wj * 24 + s * 8 + lr;
+        br[s] = sBre[ib];
+        bi[s] = sBim[ib];
+      }
+#pragma unroll
+      for (int s = 0; s < 3; ++s)
+#pragma unroll
+        for (int u = 0; u < 3; ++u) {
+          dmma(cre[s][u], ar[s], br[u]);
+          dmma(cre[s][u], ai[s], bi[u]);
+          dmma(cim[s][u], ar[s], bi[u]);
+          dmma(cim[s][u], nai[s], br[u]);
+        }
+    }
+    __syncthreads();
+  }
+  cplx* out = partial + ((long long)chunk * nsk + sk) * nb * nb;
+#pragma unroll
+  for (int s = 0; s < 3; ++s)
+#pragma unroll
+    for (int u = 0; u < 3; ++u) {
+      const int i = i0 + wi * 24 + s * 8 + lr;
+      const int j = j0 + wj * 24 + u * 8 + 2 * lc;
+      if (i < nb) {
+        if (j < nb) out[(long long)i * nb + j] = cmake(cre[s][u][0], cim[s][u][0]);
+        if (j + 1 < nb) out[(long long)i * nb + j + 1] = cmake(cre[s][u][1], cim[s][u][1]);
+      }
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// Out[g][j] = sum_i In1[g][i] T1[i][j] (+ sum_i In2[g][i] T2[i][j])
+// MODE 0: store interleaved complex;  MODE 1: store 2 Re / 2 Im into split real arrays.
+// grid: (row tiles, col tiles, nsk), block 288
+template <int MODE>
+__global__ void __launch_bounds__(QTHREADS)
+k_apply(TallMat In1, const cplx* __restrict__ T1, TallMat In2, const cplx* __restrict__ T2,
+        int nterms, long long ng, int nb, long long sk_stride, double* __restrict__ out_a,
+        double* __restrict__ out_b) {
+  extern __shared__ __align__(16) unsigned char smem_raw_[];
+  double* sAre = reinterpret_cast<double*>(smem_raw_);
+  double* sAim = sAre + QT * QLDA;
+  double* sBre = sAim + QT * QLDA;
+  double* sBim = sBre + QK * QLD;
+
+  const long long g0 = (long long)blockIdx.x * QT;
+  const int j0 = blockIdx.y * QT;
+  const int sk = blockIdx.z;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int wi = warp / 3, wj = warp % 3;
+  const int lr = lane >> 2, lc = lane & 3;
+
+  double cre[3][3][2], cim[3][3][2];
+#pragma unroll
+  for (int s = 0; s < 3; ++s)
+#pragma unroll
+    for (int u = 0; u < 3; ++u) {
+      cre[s][u][0] = cre[s][u][1] = 0.0;
+      cim[s][u][0] = cim[s][u][1] = 0.0;
+    }
+
+  for (int term = 0; term < nterms; ++term) {
+    TallMat in = term == 0 ? In1 : In2;
+    const cplx* T = (term == 0 ? T1 : T2) + (long long)sk * nb * nb;
+    in.re += sk * sk_stride * (in.im ? 1 : 2);
+    if (in.im) in.im += sk * sk_stride;
+    for (int k0 = 0; k0 < nb; k0 += QK) {
+      for (int e = threadIdx.x; e < QT * QK; e += QTHREADS) {
+        const int r = e / QK, c = e % QK;
+        cplx v = cmake(0.0, 0.0);
+        if (g0 + r < ng && k0 + c < nb) v = in.get(g0 + r, k0 + c);
+        sAre[r * QLDA + c] = v.x;
+        sAim[r * QLDA + c] = v.y;
+      }
+      for (int e = threadIdx.x; e < QK * QT; e += QTHREADS) {
+        const int r = e / QT, c = e % QT;
+        cplx v = cmake(0.0, 0.0);
+        if (k0 + r < nb && j0 + c < nb) v = T[(long long)(k0 + r) * nb + j0 + c];
+        sBre[r * QLD + c] = v.x;
+        sBim[r * QLD + c] = v.y;
+      }
+      __syncthreads();
+#pragma unroll
+      for (int k4 = 0; k4 < QK / 4; ++k4) {
+        double ar[3], ai[3], nai[3], br[3], bi[3];
+#pragma unroll
+        for (int s = 0; s < 3; ++s) {
+          const int ia = (wi * 24 + s * 8 + lr) * QLDA + k4 * 4 + lc;  // (row = g, col = k)
+          ar[s] = sAre[ia];
+          ai[s] = sAim[ia];
+          nai[s] = -ai[s];
+          const int ib = (k4 * 4 + lc) * QLD + wj * 24 + s * 8 + lr;   // (row = k, col = j)
+          br[s] = sBre[ib];
+          bi[s] = sBim[ib];
+        }
+#pragma unroll
+        for (int s = 0; s < 3; ++s)
+#pragma unroll
+          for (int u = 0; u < 3; ++u) {
+            dmma(cre[s][u], ar[s], br[u]);
+            dmma(cre[s][u], nai[s], bi[u]);
+            dmma(cim[s][u], ar[s], bi[u]);
+            dmma(cim[s][u], ai[s], br[u]);
+          }
+      }
+      __syncthreads();
+    }
+  }
+  const long long base = (long long)sk * sk_stride;
+#pragma unroll
+  for (int s = 0; s < 3; ++s)
+#pragma unroll
+    for (int u = 0; u < 3; ++u) {
+      const long long g = g0 + wi * 24 + s * 8 + lr;
+      const int j = j0 + wj * 24 + u * 8 + 2 * lc;
+      if (g < ng) {
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          if (j + e < nb) {
+            const long long o = base + g * nb + j + e;
+            if (MODE == 0) {
+              reinterpret_cast<cplx*>(out_a)[o] = cmake(cre[s][u][e], cim[s][u][e]);
+            } else {
+              out_a[o] = 2.0 * cre[s][u][e];
+              out_b[o] = 2.0 * cim[s][u][e];
+            }
+          }
+        }
+      }
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// Small (nb x nb) per-(spin,k) work: one CTA each, operating in global/L2 memory.
+__device__ __forceinline__ cplx cmulc(cplx a, cplx b) {  // a * conj(b)
+  return cmake(a.x * b.x + a.y * b.y, a.y * b.x - a.x * b.y);
+}
+
+// S = sum_chunks partial; in-place Cholesky S = L L^H; R = L^H; Rinv = R^-1.
+// If r_prev != nullptr (second pass): r_out = R * r_prev, rinv_out = rinv_prev * Rinv.
+__global__ void __launch_bounds__(1024)
+k_chol_inv(const cplx* __restrict__ partial, int nchunks, int nb, cplx* __restrict__ S,
+           cplx* __restrict__ Rt, cplx* __restrict__ Rit, const cplx* __restrict__ r_prev,
+           const cplx* __restrict__ rinv_prev, cplx* __restrict__ r_out,
+           cplx* __restrict__ rinv_out, cplx* __restrict__ scratch, int* __restrict__ fail_flag) {
+  const int sk = blockIdx.x, nsk = gridDim.x;
+  const long long nn = (long long)nb * nb;
+  S += sk * nn; Rt += sk * nn; Rit += sk * nn;
+  r_out += sk * nn; rinv_out += sk * nn; scratch += sk * nn;
+  const int tid = threadIdx.x, nt = blockDim.x;
+  for (long long e = tid; e < nn; e += nt) {
+    cplx s = cmake(0.0, 0.0);
+    for (int c = 0; c < nchunks; ++c) {
+      const cplx v = partial[((long long)c * nsk + sk) * nn + e];
+      s.x += v.x; s.y += v.y;
+    }
+    S[e] = s;
+  }
+  __syncthreads();
+  // right-looking Cholesky on the lower triangle
+  for (int j = 0; j < nb; ++j) {
+    const double djj = S[(long long)j * nb + j].x;
+    if (!(djj > 0.0)) {
+      if (tid == 0) atomicExch(fail_flag, 1);
+    }
+    const double d = sqrt(djj > 0.0 ? djj : 1.0);
+    __syncthreads();
+    for (int i = j + 1 + tid; i < nb; i += nt) {
+      cplx v = S[(long long)i * nb + j];
+      S[(long long)i * nb + j] = cmake(v.x / d, v.y / d);
+    }
+    if (tid == 0) S[(long long)j * nb + j] = cmake(d, 0.0);
+    __syncthreads();
+    const int m = nb - j - 1;
+    for (long long e = tid; e < (long long)m * m; e += nt) {
+      const int i = j + 1 + (int)(e / m), k = j + 1 + (int)(e % m);
+      if (k <= i) {
+        const cplx p = cmulc(S[(long long)i * nb + j], S[(long long)k * nb + j]);
+        cplx v = S[(long long)i * nb + k];
+        S[(long long)i * nb + k] = cmake(v.x - p.x, v.y - p.y);
+      }
+    }
+    __syncthreads();
+  }
+  // R = L^H (upper), zeros below
+  for (long long e = tid; e < nn; e += nt) {
+    const int i = (int)(e / nb), j = (int)(e % nb);
+    Rt[e] = j >= i ? cconj(S[(long long)j * nb + i]) : cmake(0.0, 0.0);
+    Rit[e] = cmake(0.0, 0.0);
+  }
+  __syncthreads();
+  // Rinv by back substitution, one warp per column
+  const int warp = tid >> 5, lane = tid & 31, nwarps = nt >> 5;
+  for (int j = warp; j < nb; j += nwarps) {
+    if (lane == 0) Rit[(long long)j * nb + j] = cmake(1.0 / Rt[(long long)j * nb + j].x, 0.0);
+    __syncwarp();
+    for (int i = j - 1; i >= 0; --i) {
+      double sx = 0.0, sy = 0.0;
+      for (int k = i + 1 + lane; k <= j; k += 32) {
+        const cplx p = cmul(Rt[(long long)i * nb + k], Rit[(long long)k * nb + j]);
+        sx += p.x; sy += p.y;
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        sx += __shfl_xor_sync(0xffffffffu, sx, o);
+        sy += __shfl_xor_sync(0xffffffffu, sy, o);
+      }
+      if (lane == 0) {
+        const double rii = Rt[(long long)i * nb + i].x;
+        Rit[(long long)i * nb + j] = cmake(-sx / rii, -sy / rii);
+      }
+      __syncwarp();
+    }
+  }
+  __syncthreads();
+  if (r_prev == nullptr) {
+    for (long long e = tid; e < nn; e += nt) {
+      r_out[e] = Rt[e];
+      rinv_out[e] = Rit[e];
+    }
+  } else {
+    r_prev += sk * nn; rinv_prev += sk * nn;
+    // both products are upper triangular
+    for (long long e = tid; e < nn; e += nt) {
+      const int i = (int)(e / nb), j = (int)(e % nb);
+      cplx a = cmake(0.0, 0.0), b = cmake(0.0, 0.0);
+      if (j >= i) {
+        for (int k = i; k <= j; ++k) {
+          const cplx p = cmul(Rt[(long long)i * nb + k], r_prev[(long long)k * nb + j]);
+          a.x += p.x; a.y += p.y;
+          const cplx q = cmul(rinv_prev[(long long)i * nb + k], Rit[(long long)k * nb + j]);
+          b.x += q.x; b.y += q.y;
+        }
+      }
+      S[e] = a;       // staged (L is dead by now): r_out may alias r_prev
+      scratch[e] = b;
+    }
+    __syncthreads();
+    for (long long e = tid; e < nn; e += nt) {
+      r_out[e] = S[e];
+      rinv_out[e] = scratch[e];
+    }
+  }
+}
+
+// Rinv = R^-1 for an upper-triangular R supplied by the caller (jrb_qr_bwd with foreign r).
+__global__ void __launch_bounds__(1024)
+k_tri_inv(const cplx* __restrict__ R, int nb, cplx* __restrict__ Rinv) {
+  const long long nn = (long long)nb * nb;
+  R += blockIdx.x * nn; Rinv += blockIdx.x * nn;
+  const int tid = threadIdx.x, nt = blockDim.x;
+  for (long long e = tid; e < nn; e += nt) Rinv[e] = cmake(0.0, 0.0);
+  __syncthreads();
+  const int warp = tid >> 5, lane = tid & 31, nwarps = nt >> 5;
+  for (int j = warp; j < nb; j += nwarps) {
+    if (lane == 0) {
+      const cplx d = R[(long long)j * nb + j];
+      const double n2 = d.x * d.x + d.y * d.y;
+      Rinv[(long long)j * nb + j] = cmake(d.x / n2, -d.y / n2);
+    }
+    __syncwarp();
+    for (int i = j - 1; i >= 0; --i) {
+      double sx = 0.0, sy = 0.0;
+      for (int k = i + 1 + lane; k <= j; k += 32) {
+        const cplx p = cmul(R[(long long)i * nb + k], Rinv[(long long)k * nb + j]);
+        sx += p.x; sy += p.y;
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        sx += __shfl_xor_sync(0xffffffffu, sx, o);
+        sy += __shfl_xor_sync(0xffffffffu, sy, o);
+      }
+      if (lane == 0) {
+        const cplx d = R[(long long)i * nb + i];
+        const double n2 = d.x * d.x + d.y * d.y;
+        // -(s / d)
+        Rinv[(long long)i * nb + j] =
+          cmake(-(sx * d.x + sy * d.y) / n2, -(sy * d.x - sx * d.y) / n2);
+      }
+      __syncwarp();
+    }
+  }
+}
+
+// Backward small step: M = (sum partial) diag(f); X = -(up(M) + up(M)^H + diag Re M);
+// T1 = diag(f) Rinv^H ; T2 = X Rinv^H.
+__global__ void __launch_bounds__(1024)
+k_bwd_small(const cplx* __restrict__ partial, int nchunks, int nb, const double* __restrict__ occ,
+            const cplx* __restrict__ rinv, cplx* __restrict__ X, cplx* __restrict__ T1,
+            cplx* __restrict__ T2) {
+  const int sk = blockIdx.x, nsk = gridDim.x;
+  const long long nn = (long long)nb * nb;
+  X += sk * nn; T1 += sk * nn; T2 += sk * nn; rinv += sk * nn;
+  const double* f = occ ? occ + (long long)sk * nb : nullptr;
+  const int tid = threadIdx.x, nt = blockDim.x;
+  // M staged in T2
+  for (long long e = tid; e < nn; e += nt) {
+    const int j = (int)(e % nb);
+    cplx s = cmake(0.0, 0.0);
+    for (int c = 0; c < nchunks; ++c) {
+      const cplx v = partial[((long long)c * nsk + sk) * nn + e];
+      s.x += v.x; s.y += v.y;
+    }
+    const double fj = f ? f[j] : 1.0;
+    T2[e] = cmake(s.x * fj, s.y * fj);
+  }
+  __syncthreads();
+  for (long long e = tid; e < nn; e += nt) {
+    const int i = (int)(e / nb), j = (int)(e % nb);
+    cplx x;
+    if (j > i) {
+      const cplx m = T2[(long long)i * nb + j];
+      x = cmake(-m.x, -m.y);
+    } else if (j < i) {
+      const cplx m = T2[(long long)j * nb + i];
+      x = cmake(-m.x, m.y);
+    } else {
+      x = cmake(-T2[e].x, 0.0);
+    }
+    X[e] = x;
+    // T1[i][j] = f_i conj(rinv[j][i])
+    const double fi = f ? f[i] : 1.0;
+    const cplx r = rinv[(long long)j * nb + i];
+    T1[e] = cmake(fi * r.x, -fi * r.y);
+  }
+  __syncthreads();
+  // T2[i][j] = sum_k X[i][k] conj(rinv[j][k]); rinv upper triangular -> k >= j
+  for (long long e = tid; e < nn; e += nt) {
+    const int i = (int)(e / nb), j = (int)(e % nb);
+    cplx s = cmake(0.0, 0.0);
+    for (int k = j; k < nb; ++k) {
+      const cplx p = cmulc(X[(long long)i * nb + k], rinv[(long long)j * nb + k]);
+      s.x += p.x; s.y += p.y;
+    }
+    T2[e] = s;
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+static int gram_chunks(const jrb_plan* p, int tiles) {
+  const int nsk = p->ns * p->nk;
+  int want = (2 * 148 + nsk * tiles * tiles - 1) / (nsk * tiles * tiles);
+  const int max_chunks = (int)std::max<int64_t>(1, p->ng / 256);
+  want = std::max(1, std::min(want, max_chunks));
+  return std::min(want, 64);
+}
+
+int qr_gram_chunks(const jrb_plan* p) {
+  const int tiles = (p->nb + QT - 1) / QT;
+  return gram_chunks(p, tiles);
+}
+
+static int run_gram(jrb_plan* p, TallMat A, TallMat B, cplx* partial, int* nchunks_out,
+                    cudaStream_t st) {
+  const int nsk = p->ns * p->nk;
+  const int tiles = (p->nb + QT - 1) / QT;
+  const int nchunks = gram_chunks(p, tiles);
+  long long rows = (p->ng + nchunks - 1) / nchunks;
+  rows = (rows + QK - 1) / QK * QK;
+  const int smem = 4 * QK * QLD * (int)sizeof(double);
+  dim3 grid(tiles * tiles, nchunks, nsk);
+  k_gram<<<grid, QTHREADS, smem, st>>>(A, B, p->ng, p->nb, p->ng * p->nb, p->ng * p->nb, tiles,
+                                      rows, partial);
+  JRB_CHECK_LAUNCH("k_gram");
+  *nchunks_out = nchunks;
+  return 0;
+}
+
+template <int MODE>
+static int run_apply(jrb_plan* p, TallMat in1, const cplx* t1, TallMat in2, const cplx* t2,
+                     int nterms, double* out_a, double* out_b, cudaStream_t st) {
+  const int nsk = p->ns * p->nk;
+  const int smem = (2 * QT * QLDA + 2 * QK * QLD) * (int)sizeof(double);
+  dim3 grid((unsigned)((p->ng + QT - 1) / QT), (p->nb + QT - 1) / QT, nsk);
+  k_apply<MODE><<<grid, QTHREADS, smem, st>>>(in1, t1, in2, t2, nterms, p->ng, p->nb,
+                                             p->ng * p->nb, out_a, out_b);
+  JRB_CHECK_LAUNCH("k_apply");
+  return 0;
+}
+
+int launch_qr_fwd(jrb_plan* p, const double* w_re, const double* w_im, cplx* q, cplx* r,
+                  cudaStream_t st) {
+  const int nsk = p->ns * p->nk;
+  const long long nn = (long long)p->nb * p->nb;
+  cplx* S = p->d_small;                 // slot 0: Gram / Cholesky work
+  cplx* Rt = p->d_small + nsk * nn;     // slot 1
+  cplx* Rit = p->d_small + 2 * nsk * nn;  // slot 2
+  int* fail = reinterpret_cast<int*>(p->d_scal + 32);
+  int nchunks = 0, rc = 0;
+  TallMat W{w_re, w_im, p->nb};
+  TallMat none{nullptr, nullptr, 0};
+  // pass 1
+  if ((rc = run_gram(p, W, W, p->d_gpart, &nchunks, st))) return rc;
+  cplx* R2inv = p->d_small + 3 * nsk * nn;  // slot 3: staging, then R2^-1 for the last apply
+  k_chol_inv<<<nsk, 1024, 0, st>>>(p->d_gpart, nchunks, p->nb, S, Rt, Rit, nullptr, nullptr, r,
+                                   p->d_rinv, R2inv, fail);
+  JRB_CHECK_LAUNCH("k_chol_inv");
+  if ((rc = run_apply<0>(p, W, p->d_rinv, none, nullptr, 1, reinterpret_cast<double*>(p->d_tmp),
+                         nullptr, st)))
+    return rc;
+  // pass 2
+  TallMat Q1{reinterpret_cast<const double*>(p->d_tmp), nullptr, p->nb};
+  if ((rc = run_gram(p, Q1, Q1, p->d_gpart, &nchunks, st))) return rc;
+  k_chol_inv<<<nsk, 1024, 0, st>>>(p->d_gpart, nchunks, p->nb, S, Rt, Rit, r, p->d_rinv, r,
+                                   p->d_rinv, R2inv, fail);
+  JRB_CHECK_LAUNCH("k_chol_inv");
+  // Rit still holds R2^-1 (only Rt and S were reused for staging)
+  JRB_CUDA(cudaMemcpyAsync(R2inv, Rit, sizeof(cplx) * nsk * nn, cudaMemcpyDeviceToDevice, st));
+  if ((rc = run_apply<0>(p, Q1, R2inv, none, nullptr, 1, reinterpret_cast<double*>(q), nullptr,
+                         st)))
+    return rc;
+  return 0;
+}
+
+int launch_qr_bwd(jrb_plan* p, const cplx* q, const cplx* r, const cplx* gq, const double* occ,
+                  double* g_re, double* g_im, cudaStream_t st) {
+  const int nsk = p->ns * p->nk;
+  const long long nn = (long long)p->nb * p->nb;
+  const cplx* rinv = p->d_rinv;  // R^-1 of the plan's own forward call
+  if (r != p->d_r) {
+    cplx* ri = p->d_small + 3 * nsk * nn;
+    k_tri_inv<<<nsk, 1024, 0, st>>>(r, p->nb, ri);
+    JRB_CHECK_LAUNCH("k_tri_inv");
+    rinv = ri;
+  }
+  cplx* X = p->d_small;
+  cplx* T1 = p->d_small + nsk * nn;
+  cplx* T2 = p->d_small + 2 * nsk * nn;
+  int nchunks = 0, rc = 0;
+  TallMat Q{reinterpret_cast<const double*>(q), nullptr, p->nb};
+  TallMat G{reinterpret_cast<const double*>(gq), nullptr, p->nb};
+  if ((rc = run_gram(p, Q, G, p->d_gpart, &nchunks, st))) return rc;
+  k_bwd_small<<<nsk, 1024, 0, st>>>(p->d_gpart, nchunks, p->nb, occ, rinv, X, T1, T2);
+  JRB_CHECK_LAUNCH("k_bwd_small");
+  return run_apply<1>(p, G, T1, Q, T2, 2, g_re, g_im, st);
+}
+
+}  // namespace jrb

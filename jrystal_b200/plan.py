@@ -1,0 +1,234 @@
+"""Host-side handle of a `jrb_plan`: owns the C plan, checks shapes, passes torch CUDA
+tensors (device memory + stream plumbing only) through the C ABI.
+
+One plan per (device, grid, mask, k-points, bands): it is what the reference's drivers
+build before their loop (calc/calc_ground_state_energy_all_electrons.py:93-106).
+"""
+import ctypes
+from typing import Optional
+
+import numpy as np
+import torch
+
+from . import _lib
+
+
+def _ptr(t: Optional[torch.Tensor]):
+  return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+def _stream():
+  return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+class Plan:
+
+  def __init__(self, cell_vectors, freq_mask, kpts, num_bands: int, num_spin: int = 1,
+               device: Optional[int] = None, batch_groups: int = 0):
+    if not torch.cuda.is_available():
+      raise RuntimeError('jrystal_b200 needs a CUDA device (there is no CPU fallback)')
+    self.lib = _lib.load()
+    self.device = torch.cuda.current_device() if device is None else int(device)
+    self.cell = np.ascontiguousarray(np.asarray(cell_vectors, dtype=np.float64).reshape(3, 3))
+    mask = np.asarray(freq_mask)
+    if mask.ndim != 3:
+      raise ValueError(f'freq_mask must be 3-D, got shape {mask.shape}')
+    self.mask = np.ascontiguousarray(mask.astype(np.uint8))
+    self.kpts = np.ascontiguousarray(np.asarray(kpts, dtype=np.float64).reshape(-1, 3))
+    self.nx, self.ny, self.nz = (int(v) for v in mask.shape)
+    self.ns, self.nk, self.nb = int(num_spin), int(self.kpts.shape[0]), int(num_bands)
+    self.ngrid = self.nx * self.ny * self.nz
+    self.vol = float(abs(np.linalg.det(self.cell)))
+    desc = _lib.PlanDesc(
+      self.nx, self.ny, self.nz, self.ns, self.nk, self.nb,
+      self.mask.ctypes.data, self.kpts.ctypes.data, self.cell.ctypes.data,
+      self.device, int(batch_groups)
+    )
+    handle = ctypes.c_void_p()
+    _lib.check(self.lib.jrb_plan_create(ctypes.byref(desc), ctypes.byref(handle)))
+    self._h = handle
+    self.ng = int(self.lib.jrb_plan_num_g(self._h))
+    self.tdev = torch.device('cuda', self.device)
+    self._atoms = False
+
+  def __del__(self):
+    h = getattr(self, '_h', None)
+    if h:
+      self.lib.jrb_plan_destroy(h)
+      self._h = None
+
+  # -- shapes -----------------------------------------------------------------------
+  @property
+  def sphere_shape(self):
+    return (self.ns, self.nk, self.ng, self.nb)
+
+  @property
+  def workspace_bytes(self):
+    return int(self.lib.jrb_plan_workspace_bytes(self._h))
+
+  def _chk(self, t, shape, dtype, name):
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+      raise TypeError(f'{name} must be a CUDA tensor')
+    if t.device.index != self.device:
+      raise ValueError(f'{name} is on {t.device}, plan is on cuda:{self.device}')
+    if tuple(t.shape) != tuple(shape):
+      raise ValueError(f'{name} has shape {tuple(t.shape)}, expected {tuple(shape)}')
+    if t.dtype != dtype:
+      raise TypeError(f'{name} has dtype {t.dtype}, expected {dtype}')
+    if not t.is_contiguous():
+      raise ValueError(f'{name} must be contiguous')
+    return t
+
+  def _new(self, shape, dtype):
+    return torch.empty(shape, dtype=dtype, device=self.tdev)
+
+  # -- setup ------------------------------------------------------------------------
+  def set_atoms(self, positions, charges):
+    pos = np.ascontiguousarray(np.asarray(positions, dtype=np.float64).reshape(-1, 3))
+    chg = np.ascontiguousarray(np.asarray(charges, dtype=np.float64).reshape(-1))
+    if pos.shape[0] != chg.shape[0]:
+      raise ValueError('positions and charges disagree on the number of atoms')
+    _lib.check(self.lib.jrb_set_atoms(self._h, pos.ctypes.data, chg.ctypes.data,
+                                      pos.shape[0], _stream()))
+    self._atoms = True
+
+  # -- orthonormalisation -------------------------------------------------------------
+  def qr_fwd(self, w_re, w_im):
+    self._chk(w_re, self.sphere_shape, torch.float64, 'w_re')
+    self._chk(w_im, self.sphere_shape, torch.float64, 'w_im')
+    q = self._new(self.sphere_shape, torch.complex128)
+    r = self._new((self.ns, self.nk, self.nb, self.nb), torch.complex128)
+    _lib.check(self.lib.jrb_qr_fwd(self._h, _ptr(w_re), _ptr(w_im), _ptr(q), _ptr(r), _stream()))
+    return q, r
+
+  def qr_bwd(self, q, r, gq):
+    self._chk(q, self.sphere_shape, torch.complex128, 'q')
+    self._chk(r, (self.ns, self.nk, self.nb, self.nb), torch.complex128, 'r')
+    self._chk(gq, self.sphere_shape, torch.complex128, 'gq')
+    g_re = self._new(self.sphere_shape, torch.float64)
+    g_im = self._new(self.sphere_shape, torch.float64)
+    _lib.check(self.lib.jrb_qr_bwd(self._h, _ptr(q), _ptr(r), _ptr(gq), _ptr(g_re), _ptr(g_im),
+                                   _stream()))
+    return g_re, g_im
+
+  # -- sphere <-> box ---------------------------------------------------------------
+  def expand(self, q):
+    self._chk(q, self.sphere_shape, torch.complex128, 'q')
+    out = self._new((self.ns, self.nk, self.nb, self.nx, self.ny, self.nz), torch.complex128)
+    _lib.check(self.lib.jrb_expand(self._h, _ptr(q), _ptr(out), _stream()))
+    return out
+
+  def squeeze(self, coeff_dense):
+    self._chk(coeff_dense, (self.ns, self.nk, self.nb, self.nx, self.ny, self.nz),
+              torch.complex128, 'coeff')
+    q = self._new(self.sphere_shape, torch.complex128)
+    _lib.check(self.lib.jrb_squeeze(self._h, _ptr(coeff_dense), _ptr(q), _stream()))
+    return q
+
+  # -- hot path pieces --------------------------------------------------------------
+  def density(self, q, occ):
+    self._chk(q, self.sphere_shape, torch.complex128, 'q')
+    self._chk(occ, (self.ns, self.nk, self.nb), torch.float64, 'occupation')
+    rho = self._new((self.ns, self.nx, self.ny, self.nz), torch.float64)
+    _lib.check(self.lib.jrb_density(self._h, _ptr(q), _ptr(occ), _ptr(rho), _stream()))
+    return rho
+
+  def kinetic(self, q):
+    self._chk(q, self.sphere_shape, torch.complex128, 'q')
+    t = self._new((self.ns, self.nk, self.nb), torch.float64)
+    _lib.check(self.lib.jrb_kinetic(self._h, _ptr(q), _ptr(t), _stream()))
+    return t
+
+  def grid_potential(self, rho, xc: str = 'lda_x', kohn_sham: bool = False):
+    if not self._atoms:
+      raise RuntimeError('call set_atoms(positions, charges) first')
+    self._chk(rho, (self.ns, self.nx, self.ny, self.nz), torch.float64, 'density')
+    if xc not in _lib.XC_IDS:
+      raise NotImplementedError(f'xc "{xc}" is not implemented (LDA only: {list(_lib.XC_IDS)})')
+    en = self._new((3,), torch.float64)
+    veff = self._new((self.ns, self.nx, self.ny, self.nz), torch.float64)
+    _lib.check(self.lib.jrb_grid_potential(self._h, _ptr(rho), _lib.XC_IDS[xc],
+                                           int(bool(kohn_sham)), _ptr(en), _ptr(veff), _stream()))
+    return en, veff
+
+  def hpsi(self, q, veff):
+    self._chk(q, self.sphere_shape, torch.complex128, 'q')
+    self._chk(veff, (self.ns, self.nx, self.ny, self.nz), torch.float64, 'veff')
+    hq = self._new(self.sphere_shape, torch.complex128)
+    _lib.check(self.lib.jrb_hpsi(self._h, _ptr(q), _ptr(veff), _ptr(hq), _stream()))
+    return hq
+
+  def band_expect(self, q, hq):
+    self._chk(q, self.sphere_shape, torch.complex128, 'q')
+    self._chk(hq, self.sphere_shape, torch.complex128, 'hq')
+    eps = self._new((self.ns, self.nk, self.nb), torch.float64)
+    _lib.check(self.lib.jrb_band_expect(self._h, _ptr(q), _ptr(hq), _ptr(eps), _stream()))
+    return eps
+
+  def fft3d(self, x, inverse: bool, out=None):
+    if x.dtype != torch.complex128 or not x.is_cuda or not x.is_contiguous():
+      raise TypeError('fft3d needs a contiguous complex128 CUDA tensor')
+    if x.ndim < 3:
+      raise ValueError(f'Input must have at least 3 dimensions, got {x.ndim}')
+    if tuple(x.shape[-3:]) != (self.nx, self.ny, self.nz):
+      raise ValueError(f'last three axes {tuple(x.shape[-3:])} do not match the plan grid')
+    out = torch.empty_like(x) if out is None else out
+    batch = int(np.prod(x.shape[:-3])) if x.ndim > 3 else 1
+    _lib.check(self.lib.jrb_fft3d(self._h, _ptr(x), _ptr(out),
+                                  _lib.FFT_INVERSE if inverse else _lib.FFT_FORWARD, batch,
+                                  _stream()))
+    return out
+
+  # -- fused evaluation ---------------------------------------------------------------
+  def eval_begin(self, w_re, w_im, occ, rho=None, e_kin=None):
+    self._chk(w_re, self.sphere_shape, torch.float64, 'w_re')
+    self._chk(w_im, self.sphere_shape, torch.float64, 'w_im')
+    self._chk(occ, (self.ns, self.nk, self.nb), torch.float64, 'occupation')
+    rho = self._new((self.ns, self.nx, self.ny, self.nz), torch.float64) if rho is None else rho
+    e_kin = self._new((1,), torch.float64) if e_kin is None else e_kin
+    _lib.check(self.lib.jrb_eval_begin(self._h, _ptr(w_re), _ptr(w_im), _ptr(occ), _ptr(rho),
+                                       _ptr(e_kin), _stream()))
+    return rho, e_kin
+
+  def eval_finish(self, occ, rho, e_kin, xc: str = 'lda_x', want_occ_grad: bool = False,
+                  out=None):
+    if not self._atoms:
+      raise RuntimeError('call set_atoms(positions, charges) first')
+    if xc not in _lib.XC_IDS:
+      raise NotImplementedError(f'xc "{xc}" is not implemented (LDA only: {list(_lib.XC_IDS)})')
+    if out is None:
+      energies = self._new((4,), torch.float64)
+      g_re = self._new(self.sphere_shape, torch.float64)
+      g_im = self._new(self.sphere_shape, torch.float64)
+    else:
+      energies, g_re, g_im = out
+    g_occ = self._new((self.ns, self.nk, self.nb), torch.float64) if want_occ_grad else None
+    _lib.check(self.lib.jrb_eval_finish(self._h, _ptr(occ), _ptr(rho), _ptr(e_kin),
+                                        _lib.XC_IDS[xc], _ptr(energies), _ptr(g_re), _ptr(g_im),
+                                        _ptr(g_occ), _stream()))
+    return energies, g_re, g_im, g_occ
+
+  def energy_grad_host(self, w_re, w_im, occ, xc: str = 'lda_x', out=None, want_rho=False):
+    """Host (numpy / pinned torch CPU) buffers in and out through jrb_energy_grad_host."""
+    if not self._atoms:
+      raise RuntimeError('call set_atoms(positions, charges) first')
+
+    def host_ptr(a):
+      if isinstance(a, torch.Tensor):
+        assert not a.is_cuda and a.is_contiguous() and a.dtype == torch.float64
+        return ctypes.c_void_p(a.data_ptr())
+      assert a.flags['C_CONTIGUOUS'] and a.dtype == np.float64
+      return ctypes.c_void_p(a.ctypes.data)
+
+    if out is None:
+      energies = np.empty(4)
+      g_re = np.empty(self.sphere_shape)
+      g_im = np.empty(self.sphere_shape)
+    else:
+      energies, g_re, g_im = out
+    rho = np.empty((self.ns, self.nx, self.ny, self.nz)) if want_rho else None
+    _lib.check(self.lib.jrb_energy_grad_host(
+      self._h, host_ptr(w_re), host_ptr(w_im), host_ptr(occ), _lib.XC_IDS[xc],
+      host_ptr(energies), host_ptr(g_re), host_ptr(g_im),
+      None if rho is None else host_ptr(rho)))
+    return energies, g_re, g_im, rho

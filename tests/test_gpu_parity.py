@@ -1,0 +1,188 @@
+"""GPU parity: every C-ABI entry point against the oracle on seeded inputs.
+
+Tolerances (BASELINE.json north_star): total energy 1e-10 relative, gradients and density
+1e-8 relative, FP64.
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import analytic
+from oracle import reference_port as rp
+from tests.common import make_inputs, make_plan, make_system, relerr, to_dev
+
+pytestmark = pytest.mark.gpu
+
+E_TOL = 1e-10
+G_TOL = 1e-8
+
+CASES = {
+  # the reference's own test fixture: diamond, grid [7,8,9], cubic mask (pw_test.py:33-34)
+  'diamond_789_cubic': dict(name='diamond', grid=[7, 8, 9], kgrid=[2, 2, 1], mask='cubic',
+                            cutoff=None, nb=12),
+  'diamond_16': dict(name='diamond', grid=16, kgrid=[1, 1, 1], mask='spherical', cutoff=20, nb=9),
+  'si_32': dict(name='si', grid=32, kgrid=[2, 1, 1], mask='spherical', cutoff=12, nb=18),
+  'diamond_24x32x48': dict(name='diamond', grid=[24, 32, 48], kgrid=[1, 1, 2], mask='spherical',
+                           cutoff=30, nb=10),
+}
+
+
+def _setup(case, **plan_kw):
+  c = CASES[case]
+  s = make_system(c['name'], c['grid'], c['kgrid'], c['cutoff'], c['mask'])
+  w_re, w_im, occ = make_inputs(s, c['nb'], jitter=0.1)
+  plan = make_plan(s, c['nb'], **plan_kw)
+  return s, plan, w_re, w_im, occ
+
+
+@pytest.mark.parametrize('case', list(CASES))
+def test_fft3d_dense(cuda_device, case):
+  s, plan, *_ = _setup(case)
+  rng = np.random.default_rng(5)
+  x = rng.standard_normal((3,) + tuple(s.grid_sizes)) + 1j * rng.standard_normal((3,) + tuple(s.grid_sizes))
+  xd = to_dev(x)
+  f = plan.fft3d(xd, inverse=False).cpu().numpy()
+  i = plan.fft3d(xd, inverse=True).cpu().numpy()
+  assert relerr(f, np.fft.fftn(x, axes=(-3, -2, -1))) < 1e-13
+  assert relerr(i, np.fft.ifftn(x, axes=(-3, -2, -1))) < 1e-13
+  # in place
+  y = xd.clone()
+  plan.fft3d(y, inverse=False, out=y)
+  assert relerr(y.cpu().numpy(), f) == 0.0
+
+
+@pytest.mark.parametrize('case', list(CASES))
+def test_qr(cuda_device, case):
+  s, plan, w_re, w_im, occ = _setup(case)
+  q, r = plan.qr_fwd(to_dev(w_re), to_dev(w_im))
+  q = q.cpu().numpy()
+  r = r.cpu().numpy()
+  w = w_re + 1j * w_im
+  nb = w.shape[-1]
+  for k in range(w.shape[1]):
+    assert np.abs(q[0, k].conj().T @ q[0, k] - np.eye(nb)).max() < 1e-13
+    assert relerr(q[0, k] @ r[0, k], w[0, k]) < 1e-13
+    assert np.abs(np.tril(r[0, k], -1)).max() == 0.0
+    assert (np.diag(r[0, k]).real > 0).all() and np.abs(np.diag(r[0, k]).imag).max() < 1e-14
+    # reference (Householder) Q up to the documented per-column sign
+    q_ref = np.linalg.qr(w[0, k])[0]
+    d = np.sign(np.real(np.sum(q_ref.conj() * q[0, k], axis=0)))
+    assert relerr(q[0, k] * d[None, :], q_ref) < 1e-12
+
+
+@pytest.mark.parametrize('case', list(CASES))
+def test_qr_bwd(cuda_device, case):
+  s, plan, w_re, w_im, occ = _setup(case)
+  rng = np.random.default_rng(11)
+  gq = rng.standard_normal(w_re.shape) + 1j * rng.standard_normal(w_re.shape)
+  q, r = plan.qr_fwd(to_dev(w_re), to_dev(w_im))
+  g_re, g_im = plan.qr_bwd(q, r, to_dev(gq))
+  for k in range(w_re.shape[1]):
+    gw = analytic.qr_backward(q[0, k].cpu().numpy(), r[0, k].cpu().numpy(), gq[0, k])
+    assert relerr(g_re[0, k].cpu().numpy(), 2 * gw.real) < 1e-11
+    assert relerr(g_im[0, k].cpu().numpy(), 2 * gw.imag) < 1e-11
+
+
+@pytest.mark.parametrize('case', list(CASES))
+def test_density_kinetic(cuda_device, case):
+  s, plan, w_re, w_im, occ = _setup(case)
+  q = rp.unitary_matrix(torch.from_numpy(w_re), torch.from_numpy(w_im))
+  c = rp.expand_coefficient(q, s.mask)
+  rho_ref = rp.density_grid(c, s.vol, torch.from_numpy(occ)).numpy()
+  t_ref = rp.energy_kinetic(s.g_vec, s.kpts, c).numpy()
+  qd = q.cuda().contiguous()
+  rho = plan.density(qd, to_dev(occ)).cpu().numpy()
+  t = plan.kinetic(qd).cpu().numpy()
+  assert relerr(rho, rho_ref) < G_TOL
+  assert relerr(rho, rho_ref) < 1e-12
+  assert relerr(t, t_ref) < 1e-12
+  # expand / squeeze round trip and parity with utils.expand_coefficient
+  dense = plan.expand(qd)
+  assert relerr(dense.cpu().numpy(), c.numpy()) == 0.0
+  assert relerr(plan.squeeze(dense).cpu().numpy(), q.numpy()) == 0.0
+
+
+@pytest.mark.parametrize('case', list(CASES))
+@pytest.mark.parametrize('kohn_sham', [False, True])
+@pytest.mark.parametrize('xc', ['lda_x', 'lda_x+lda_c_pw'])
+def test_grid_potential(cuda_device, case, kohn_sham, xc):
+  s, plan, w_re, w_im, occ = _setup(case)
+  q = rp.unitary_matrix(torch.from_numpy(w_re), torch.from_numpy(w_im))
+  c = rp.expand_coefficient(q, s.mask)
+  rho = rp.density_grid(c, s.vol, torch.from_numpy(occ))
+  rho_g = torch.fft.fftn(rho, dim=(-3, -2, -1))
+  e_h = rp.energy_hartree(rho_g, s.g_vec, s.vol, kohn_sham).item()
+  e_e = rp.energy_external(rho_g, s.positions, s.charges, s.g_vec, s.vol).item()
+  e_x = rp.energy_xc(rho, s.vol, xc, kohn_sham).item()
+  en, veff = plan.grid_potential(rho.cuda().contiguous(), xc, kohn_sham)
+  en = en.cpu().numpy()
+  assert abs(en[0] - e_h) / abs(e_h) < E_TOL
+  assert abs(en[1] - e_e) / abs(e_e) < E_TOL
+  assert abs(en[2] - e_x) / abs(e_x) < E_TOL
+  v_ref = rp.effective(rho, s.positions, s.charges, s.g_vec, s.vol, False, xc, True)
+  assert np.abs(v_ref.imag.numpy()).max() < 1e-10
+  assert relerr(veff.cpu().numpy(), v_ref.real.numpy()) < 1e-11
+
+
+@pytest.mark.parametrize('case', list(CASES))
+def test_hpsi_and_band_trace(cuda_device, case):
+  """hamiltonian_matrix_trace value + gradient (band mode) through jrb_hpsi."""
+  s, plan, w_re, w_im, occ = _setup(case)
+  q = rp.unitary_matrix(torch.from_numpy(w_re), torch.from_numpy(w_im))
+  c = rp.expand_coefficient(q, s.mask)
+  rho = rp.density_grid(c, s.vol, torch.from_numpy(occ))
+  ref = rp.band_trace_and_grad(s, w_re, w_im, rho.numpy())
+  qd, r = plan.qr_fwd(to_dev(w_re), to_dev(w_im))
+  _, veff = plan.grid_potential(rho.cuda().contiguous(), 'lda_x', True)
+  hq = plan.hpsi(qd, veff)
+  eps = plan.band_expect(qd, hq).cpu().numpy()
+  assert relerr(eps, ref['per_band']) < 1e-11
+  assert abs(eps.sum() - ref['trace']) / abs(ref['trace']) < E_TOL
+  g_re, g_im = plan.qr_bwd(qd, r, hq)
+  assert relerr(g_re.cpu().numpy(), ref['g_re']) < G_TOL
+  assert relerr(g_im.cpu().numpy(), ref['g_im']) < G_TOL
+
+
+@pytest.mark.parametrize('case', list(CASES))
+@pytest.mark.parametrize('batch_groups', [0, 1, 3])
+def test_energy_and_grad(cuda_device, case, batch_groups):
+  s, plan, w_re, w_im, occ = _setup(case, batch_groups=batch_groups)
+  ref = rp.energy_and_grad(s, w_re, w_im, occ, occ_grad=True)
+  occ_d = to_dev(occ)
+  rho, e_kin = plan.eval_begin(to_dev(w_re), to_dev(w_im), occ_d)
+  en, g_re, g_im, g_occ = plan.eval_finish(occ_d, rho, e_kin, 'lda_x', want_occ_grad=True)
+  torch.cuda.synchronize()
+  en = en.cpu().numpy()
+  for i, key in enumerate(['e_kin', 'e_ext', 'e_har', 'e_xc']):
+    assert abs(en[i] - ref[key]) / abs(ref[key]) < E_TOL, key
+  assert abs(en.sum() - ref['e_tot']) / abs(ref['e_tot']) < E_TOL
+  assert relerr(rho.cpu().numpy(), ref['density']) < G_TOL
+  assert relerr(g_re.cpu().numpy(), ref['g_re']) < G_TOL
+  assert relerr(g_im.cpu().numpy(), ref['g_im']) < G_TOL
+  assert relerr(g_occ.cpu().numpy(), ref['g_occ']) < G_TOL
+
+
+def test_energy_grad_host(cuda_device):
+  s, plan, w_re, w_im, occ = _setup('diamond_16')
+  ref = rp.energy_and_grad(s, w_re, w_im, occ)
+  en, g_re, g_im, rho = plan.energy_grad_host(w_re, w_im, occ, want_rho=True)
+  assert abs(en.sum() - ref['e_tot']) / abs(ref['e_tot']) < E_TOL
+  assert relerr(g_re, ref['g_re']) < G_TOL
+  assert relerr(g_im, ref['g_im']) < G_TOL
+  assert relerr(rho, ref['density']) < G_TOL
+
+
+def test_errors(cuda_device):
+  import jrystal_b200 as jb
+  from jrystal_b200._lib import JrbError
+  s = make_system('diamond', [7, 8, 9], [1, 1, 1], None, 'cubic')
+  with pytest.raises(JrbError):
+    jb.Plan(s.cell, np.ones((11, 8, 9), dtype=bool), s.kpts, 4)  # 11 is not 7-smooth
+  with pytest.raises(JrbError):
+    jb.Plan(s.cell, np.zeros((7, 8, 9), dtype=bool), s.kpts, 4)  # empty mask
+  plan = jb.Plan(s.cell, s.mask, s.kpts, 4)
+  with pytest.raises(RuntimeError):
+    plan.grid_potential(torch.zeros((1, 7, 8, 9), dtype=torch.float64, device='cuda'))
+  with pytest.raises(ValueError):
+    plan.density(torch.zeros((1, 1, 3, 4), dtype=torch.complex128, device='cuda'),
+                 torch.zeros((1, 1, 4), dtype=torch.float64, device='cuda'))
