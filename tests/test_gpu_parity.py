@@ -120,7 +120,8 @@ def test_grid_potential(cuda_device, case, kohn_sham, xc):
   assert abs(en[1] - e_e) / abs(e_e) < E_TOL
   assert abs(en[2] - e_x) / abs(e_x) < E_TOL
   v_ref = rp.effective(rho, s.positions, s.charges, s.g_vec, s.vol, False, xc, True)
-  assert np.abs(v_ref.imag.numpy()).max() < 1e-10
+  # ifftn(V_ext) is complex on even grids (Nyquist planes are not Hermitian); the reference
+  # keeps only the real part of <psi|v|psi> (hamiltonian.py:164) and d E/d rho is its real part.
   assert relerr(veff.cpu().numpy(), v_ref.real.numpy()) < 1e-11
 
 
