@@ -1,0 +1,370 @@
+#!/usr/bin/env python
+"""Benchmark of the hot path: energy+gradient evaluations / second (BASELINE.json metric).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--config C1|C2|C3a|C3b] [--impl reference]
+
+One "step" = one evaluation = value_and_grad(total_energy) of jrystal's energy-mode driver
+(calc/calc_ground_state_energy_all_electrons.py:119-137,175-181), optimiser excluded:
+(w_re, w_im, occ) -> (E_kin, E_ext, E_har, E_xc, dE/dw_re, dE/dw_im, rho).
+Default workload: BASELINE config C2 (Si8, 64^3, 30 Ha, 4x4x4 k, 66 bands, M = 4224 orbitals).
+Inputs are synthetic (U[0,1) parameters from numpy default_rng(123), uniform occupations).
+Multi-GPU: one process per GPU (torchrun), k-points sharded over ranks, partial densities
+all-reduced with NCCL; total work is fixed => "strong" scaling.
+
+Prints ONE JSON line (rank 0).  `--impl reference` times the CPU restatement of the
+reference (oracle/, torch FP64, all host cores) on a bounded sample of the same workload.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+  sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+  # name: (crystal, repeat, grid, cutoff Ha, k-grid, empty bands)            BASELINE.md sec. 3
+  'C1': dict(crystal='si', repeat=None, grid=32, cutoff=20.0, kgrid=(2, 2, 2), empty=10,
+             text='C1: Si2 primitive, 32^3, 20 Ha, 2x2x2 k, 24 bands'),
+  'C2': dict(crystal='si8', repeat=None, grid=64, cutoff=30.0, kgrid=(4, 4, 4), empty=10,
+             text='C2: Si8 conventional, 64^3, 30 Ha, 4x4x4 k, 66 bands'),
+  'C3a': dict(crystal='diamond8', repeat=(2, 2, 2), grid=128, cutoff=40.0, kgrid=(1, 1, 1),
+              empty=16, text='C3a: diamond-64 supercell, 128^3, 40 Ha, Gamma, 208 bands'),
+  'C3b': dict(crystal='diamond8', repeat=(2, 2, 2), grid=128, cutoff=40.0, kgrid=(2, 2, 2),
+              empty=16, text='C3b: diamond-64 supercell, 128^3, 40 Ha, 2x2x2 k, 208 bands'),
+}
+METRIC = 'energy+grad evals/sec'
+UNIT = 'eval/s'
+
+
+def build_workload(name):
+  from jrystal_b200 import grid, occupation
+  from jrystal_b200.crystal import Crystal
+  w = WORKLOADS[name]
+  crystal = Crystal.create_builtin(w['crystal'], repeat=w['repeat'])
+  gs = grid.proper_grid_size(w['grid'])
+  mask = grid.spherical_mask(crystal.cell_vectors, gs, w['cutoff'])
+  kpts = grid.k_vectors(crystal.cell_vectors, grid.proper_grid_size(w['kgrid']))
+  nb = int(np.ceil(crystal.num_electron / 2)) + w['empty']
+  occ = occupation.uniform(kpts.shape[0], crystal.num_electron, crystal.spin, nb)
+  return dict(crystal=crystal, grid=[int(g) for g in gs], mask=mask, kpts=kpts, nb=nb, occ=occ,
+              ng=int(mask.sum()), text=w['text'])
+
+
+def synthetic_params(ng, nk, nb, k0, k1):
+  """U[0,1) FP64 parameters (ns=1, nk, ng, nb) from default_rng(123), rows [k0, k1)."""
+  rng = np.random.default_rng(123)
+  w_re = np.empty((1, k1 - k0, ng, nb))
+  w_im = np.empty((1, k1 - k0, ng, nb))
+  # generate k by k so that every rank sees the same global stream
+  for which in (w_re, w_im):
+    for k in range(nk):
+      blk = rng.random((ng, nb))
+      if k0 <= k < k1:
+        which[0, k - k0] = blk
+  return w_re, w_im
+
+
+class ClockSampler:
+  """nvidia-smi clocks / throttle reasons during the timed region."""
+  Q = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,'
+       'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
+       'clocks_event_reasons.sw_power_cap')
+
+  def __init__(self, index):
+    self.index = index
+    self.samples = []
+    self._stop = threading.Event()
+    self._t = threading.Thread(target=self._run, daemon=True)
+
+  def _run(self):
+    while not self._stop.is_set():
+      try:
+        out = subprocess.run(
+          ['nvidia-smi', f'--query-gpu={self.Q}', '--format=csv,noheader,nounits', '-i',
+           str(self.index)], capture_output=True, text=True, timeout=5).stdout.strip()
+        if out:
+          self.samples.append([x.strip() for x in out.split(',')])
+      except Exception:
+        pass
+      self._stop.wait(0.2)
+
+  def __enter__(self):
+    self._t.start()
+    return self
+
+  def __exit__(self, *a):
+    self._stop.set()
+    self._t.join(timeout=6)
+
+  def summary(self):
+    sm, mx, reasons = [], [], set()
+    names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+    for s in self.samples:
+      try:
+        sm.append(float(s[0]))
+        mx.append(float(s[1]))
+        for n, v in zip(names, s[3:7]):
+          if v.lower().startswith('active'):
+            reasons.add(n)
+      except Exception:
+        continue
+    return {'sm_mhz': float(np.median(sm)) if sm else None,
+            'sm_max_mhz': float(max(mx)) if mx else None, 'reasons': sorted(reasons),
+            'samples': len(sm)}
+
+
+def measured_peak():
+  path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+  if os.path.exists(path):
+    try:
+      return float(json.load(open(path))['hbm_gbs']), 'measured (MEASURED_PEAKS.json hbm_gbs)'
+    except Exception:
+      pass
+  return 6650.0, 'fallback (B200_PROFILING.md)'
+
+
+def cpu_sample_eval(wl, nk_sample, steps, warmup):
+  """Oracle (CPU restatement of the reference dataflow) on `nk_sample` k-points of the
+  workload, all host threads.  Returns (eval/s scaled to the full workload, seconds/sample)."""
+  import torch
+  from oracle import reference_port as rp
+  cores = os.cpu_count() or 1
+  torch.set_num_threads(cores)
+  c = wl['crystal']
+  nk = wl['kpts'].shape[0]
+  nk_sample = min(nk_sample, nk)
+  s = rp.System(c.cell_vectors, c.positions, c.charges, wl['grid'], kpts=wl['kpts'][:nk_sample],
+                cutoff_energy=None, mask_method='cubic')
+  s.mask = wl['mask']
+  s.num_g = wl['ng']
+  w_re, w_im = synthetic_params(wl['ng'], nk, wl['nb'], 0, nk_sample)
+  occ = wl['occ'][:, :nk_sample]
+  times = []
+  for i in range(warmup + steps):
+    t0 = time.perf_counter()
+    rp.energy_and_grad(s, w_re, w_im, occ)
+    dt = time.perf_counter() - t0
+    if i >= warmup:
+      times.append(dt)
+  t = float(np.mean(times))
+  return 1.0 / (t * nk / nk_sample), t, cores, nk_sample
+
+
+def run_reference(args):
+  rank = int(os.environ.get('RANK', '0'))
+  if rank != 0:
+    return
+  wl = build_workload(args.config)
+  nk = wl['kpts'].shape[0]
+  nk_sample = {'C1': 8, 'C2': 1, 'C3a': 1, 'C3b': 1}[args.config]
+  steps = max(1, min(args.steps, 3))
+  value, t, cores, nks = cpu_sample_eval(wl, nk_sample, steps, min(args.warmup, 1))
+  sample = (f'{nks} of {nk} k-points x {wl["nb"]} bands at {wl["grid"]} per step, time scaled '
+            f'by {nk / nks:g}; oracle port (torch FP64 autograd), {cores} threads')
+  line = {
+    'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': args.gpus,
+    'steps': steps, 'warmup': min(args.warmup, 1), 'ms_per_step': 1e3 / value,
+    'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None, 'dtype': 'f64',
+    'data': 'synthetic',
+    'config': {'workload': wl['text'], 'note': 'CPU restatement of the reference (JAX absent)'},
+    'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': cores, 'kind': 'port',
+                     'sample': sample},
+    'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+    'gpu_launches': 0,
+  }
+  print(json.dumps(line), flush=True)
+
+
+def run_b200(args):
+  import torch
+  import torch.distributed as dist
+  import jrystal_b200 as jb
+  from jrystal_b200 import _lib, parallel
+
+  world = int(os.environ.get('WORLD_SIZE', '1'))
+  rank = int(os.environ.get('RANK', '0'))
+  local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+  if world != args.gpus:
+    if world == 1 and args.gpus > 1:
+      raise SystemExit('launch with torchrun --nproc-per-node N for --gpus N > 1')
+  torch.cuda.set_device(local_rank)
+  if world > 1:
+    dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
+
+  wl = build_workload(args.config)
+  c = wl['crystal']
+  nk, nb, ng = wl['kpts'].shape[0], wl['nb'], wl['ng']
+  ngrid = int(np.prod(wl['grid']))
+  if nk % world == 0:
+    k0, k1 = parallel.shard_kpoints(nk, world, rank)
+    b0, b1 = 0, nb
+    sharding = f'k{world}' if world > 1 else 'none'
+  else:
+    raise SystemExit(f'{args.config}: nk={nk} not divisible by {world} ranks '
+                     '(band-block sharding of a single k-point is not implemented yet)')
+  plan = jb.Plan(c.cell_vectors, wl['mask'], wl['kpts'][k0:k1], nb, device=local_rank)
+  plan.set_atoms(c.positions, c.charges)
+  w_re_h, w_im_h = synthetic_params(ng, nk, nb, k0, k1)
+  occ_h = np.ascontiguousarray(wl['occ'][:, k0:k1])
+  w_re = torch.from_numpy(w_re_h).cuda()
+  w_im = torch.from_numpy(w_im_h).cuda()
+  occ = torch.from_numpy(occ_h).cuda()
+  rho = torch.empty((1,) + tuple(wl['grid']), dtype=torch.float64, device='cuda')
+  e_kin = torch.empty(1, dtype=torch.float64, device='cuda')
+  out = (torch.empty(4, dtype=torch.float64, device='cuda'), torch.empty_like(w_re),
+         torch.empty_like(w_im))
+
+  def step():
+    plan.eval_begin(w_re, w_im, occ, rho, e_kin)
+    parallel.allreduce_density(rho, e_kin)
+    plan.eval_finish(occ, rho, e_kin, 'lda_x', out=out)
+
+  def barrier():
+    if world > 1:
+      dist.barrier()
+    torch.cuda.synchronize()
+
+  def timed(fn, steps):
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record()
+    for _ in range(steps):
+      fn()
+    ev1.record()
+    barrier()
+    ms = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device='cuda')
+    if world > 1:
+      dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    return float(ms.item())
+
+  lib = _lib.load()
+  for _ in range(max(args.warmup, 3)):
+    step()
+  barrier()
+  launches0 = lib.jrb_launch_count()
+  with ClockSampler(local_rank) as clk:
+    total_ms = timed(step, args.steps)
+  launches = int(lib.jrb_launch_count() - launches0)
+  ms_per_step = total_ms / args.steps
+  value = 1e3 / ms_per_step
+  energies = out[0].cpu().numpy().tolist()
+
+  # ---- end to end through host buffers --------------------------------------------------
+  nw = w_re_h.size
+  h2d = 2 * nw * 8 + occ_h.size * 8
+  d2h = 2 * nw * 8 + 4 * 8
+  pin = lambda a: torch.from_numpy(a).pin_memory()
+  w_re_p, w_im_p, occ_p = pin(w_re_h), pin(w_im_h), pin(occ_h)
+  en_p = torch.empty(4, dtype=torch.float64).pin_memory()
+  g_re_p = torch.empty(w_re_h.shape, dtype=torch.float64).pin_memory()
+  g_im_p = torch.empty(w_re_h.shape, dtype=torch.float64).pin_memory()
+  if world == 1:
+    def e2e_step():
+      plan.energy_grad_host(w_re_p, w_im_p, occ_p, 'lda_x', out=(en_p, g_re_p, g_im_p))
+    e2e_path = 'jrb_energy_grad_host (C ABI, pinned host buffers)'
+  else:
+    def e2e_step():
+      w_re.copy_(w_re_p, non_blocking=True)
+      w_im.copy_(w_im_p, non_blocking=True)
+      occ.copy_(occ_p, non_blocking=True)
+      step()
+      en_p.copy_(out[0], non_blocking=True)
+      g_re_p.copy_(out[1], non_blocking=True)
+      g_im_p.copy_(out[2], non_blocking=True)
+      torch.cuda.current_stream().synchronize()
+    e2e_path = 'pinned H2D + jrb_eval_begin/NCCL all-reduce/jrb_eval_finish + D2H per rank'
+  e2e_steps = max(1, min(args.steps, 5))
+  e2e_step()
+  barrier()
+  t0 = time.perf_counter()
+  for _ in range(e2e_steps):
+    e2e_step()
+  barrier()
+  e2e_s = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device='cuda')
+  if world > 1:
+    dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
+  e2e_value = e2e_steps / float(e2e_s.item())
+
+  # ---- phase split (outside the timed region; explains the number) ----------------------
+  phases = {}
+  q, r = plan.qr_fwd(w_re, w_im)
+  rho2 = plan.density(q, occ)
+  _, veff = plan.grid_potential(rho2, 'lda_x', False)
+  hq = plan.hpsi(q, veff)
+  reps = 3
+  phases['qr_fwd'] = timed(lambda: plan.qr_fwd(w_re, w_im), reps) / reps
+  phases['density'] = timed(lambda: plan.density(q, occ), reps) / reps
+  phases['grid_potential'] = timed(lambda: plan.grid_potential(rho2, 'lda_x', False), reps) / reps
+  phases['hpsi'] = timed(lambda: plan.hpsi(q, veff), reps) / reps
+  phases['qr_bwd'] = timed(lambda: plan.qr_bwd(q, r, hq), reps) / reps
+  del q, r, hq, rho2, veff
+
+  # ---- roofline: algorithmic bytes of SURVEY 8(d), per GPU ------------------------------
+  m_local = (k1 - k0) * (b1 - b0)
+  bytes_alg = 64.0 * m_local * (ngrid + ng)
+  peak, peak_src = measured_peak()
+  achieved = bytes_alg / (ms_per_step * 1e-3) / 1e9
+  fft_ms = phases['density'] + phases['hpsi']
+  fft_bytes = 64.0 * m_local * ngrid
+  roofline = {
+    'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
+    'traffic': None, 'peak_source': peak_src,
+    'kernel': 'whole evaluation (bytes_alg = 64*M*(N+ng) per GPU, SURVEY 8d)',
+    'fft_density_path': {'ms': fft_ms, 'achieved': fft_bytes / (fft_ms * 1e-3) / 1e9,
+                         'frac': fft_bytes / (fft_ms * 1e-3) / 1e9 / peak,
+                         'bytes': '64*M*N (two dense 3-D transforms per orbital)'},
+  }
+
+  if rank == 0:
+    line = {
+      'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
+      'warmup': max(args.warmup, 3), 'ms_per_step': ms_per_step, 'higher_is_better': True,
+      'scaling': 'strong', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
+      'config': {'workload': wl['text'], 'orbitals': nk * nb, 'ng': ng, 'grid': wl['grid'],
+                 'sharding': sharding, 'xc': 'lda_x',
+                 'l2': f'inputs larger than L2 ({2 * nw * 8 / 2**20:.0f} MiB of parameters per '
+                       'GPU); no flush' if 2 * nw * 8 > 126 * 2**20 else
+                       'working set fits L2; parameters rewritten by an L2 flush is NOT done',
+                 'batch_groups': int(os.environ.get('JRB_BATCH_GROUPS', 0))},
+      'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': h2d,
+              'd2h_bytes_per_step': d2h, 'path': e2e_path},
+      'gpu_launches': launches, 'roofline': roofline, 'clocks': clk.summary(),
+      'phases_ms': phases, 'energies_ha': energies,
+      'workspace_mib': plan.workspace_bytes / 2**20,
+    }
+    if world == 1 and not args.no_cpu:
+      nks = {'C1': 8, 'C2': 1, 'C3a': 1, 'C3b': 1}[args.config]
+      v, t, cores, nks = cpu_sample_eval(wl, nks, 1, 1)
+      line['cpu_baseline'] = {
+        'value': v, 'unit': UNIT, 'cores': cores, 'kind': 'port',
+        'sample': f'{nks} of {nk} k-points x {nb} bands ({t:.2f} s), scaled by {nk / nks:g}; '
+                  'oracle port (torch FP64 autograd)'}
+    print(json.dumps(line), flush=True)
+  if world > 1:
+    dist.destroy_process_group()
+
+
+def main():
+  ap = argparse.ArgumentParser()
+  ap.add_argument('--gpus', type=int, default=1)
+  ap.add_argument('--steps', type=int, default=10)
+  ap.add_argument('--warmup', type=int, default=3)
+  ap.add_argument('--config', default='C2', choices=list(WORKLOADS))
+  ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+  ap.add_argument('--no-cpu', action='store_true', help='skip the cpu_baseline leg')
+  args = ap.parse_args()
+  if args.impl == 'reference':
+    run_reference(args)
+  else:
+    run_b200(args)
+
+
+if __name__ == '__main__':
+  main()

@@ -151,6 +151,8 @@ int jrb_energy_grad_host(jrb_plan* plan, const double* w_re_host, const double* 
 
 const char* jrb_last_error(void);
 int jrb_version(void);
+/* number of CUDA kernels this library has launched in the calling process (bench evidence) */
+int64_t jrb_launch_count(void);
 
 #ifdef __cplusplus
 }

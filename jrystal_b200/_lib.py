@@ -44,6 +44,7 @@ SYMBOLS = {
   'jrb_energy_grad_host': (ctypes.c_int, [_P, _P, _P, _P, _I32, _P, _P, _P, _P]),
   'jrb_last_error': (ctypes.c_char_p, []),
   'jrb_version': (ctypes.c_int, []),
+  'jrb_launch_count': (_I64, []),
 }
 
 _lib = None

@@ -2,6 +2,7 @@
 // Host-side restatement of what the reference's drivers prepare before the loop
 // (jrystal/calc/calc_ground_state_energy_all_electrons.py:93-106 via grid.g_vectors,
 // jrystal/_src/grid.py:93-149, and the C-order mask enumeration of utils.py:279-281).
+#include <atomic>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -23,6 +24,10 @@ int cuda_fail(cudaError_t e, const char* what) {
 }
 
 const char* last_error_cstr() { return g_last_error.c_str(); }
+
+static std::atomic<long long> g_launches{0};
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+long long launch_count() { return g_launches.load(std::memory_order_relaxed); }
 
 bool line_length_supported(int n) {
   PassArgs dummy{};
@@ -96,6 +101,8 @@ using namespace jrb;
 
 extern "C" const char* jrb_last_error(void) { return jrb::last_error_cstr(); }
 extern "C" int jrb_version(void) { return 100; }
+namespace jrb { long long launch_count(); }
+extern "C" int64_t jrb_launch_count(void) { return jrb::launch_count(); }
 
 extern "C" int64_t jrb_plan_num_g(const jrb_plan* p) { return p ? p->ng : -1; }
 extern "C" int64_t jrb_plan_workspace_bytes(const jrb_plan* p) { return p ? p->ws_bytes : -1; }
@@ -248,10 +255,12 @@ extern "C" int jrb_plan_create(const jrb_plan_desc* d, jrb_plan** out) {
   int bg = d->batch_groups;
   if (const char* env = std::getenv("JRB_BATCH_GROUPS")) bg = std::atoi(env);
   if (bg <= 0) {
-    // automatic: keep the B slab of a batch near 48 MB so that a batch stays L2 resident
-    // (126 MB L2), but never fewer than 2 groups.
-    const double target = 48.0 * 1024 * 1024;
+    // automatic: measured on B200 (profiles/r01_first_bench.md) large batches win over
+    // L2-resident small ones (fewer, fatter launches; the passes are FP64-issue bound, not
+    // HBM bound), so take up to 128 groups within a 2 GiB slab budget.
+    const double target = 2048.0 * 1024 * 1024;
     bg = (int)(target / ((double)b_per_group * sizeof(cplx)));
+    if (bg > 128) bg = 128;
     if (bg < 2) bg = 2;
   }
   if (bg > p->nk * p->ngroups_per_k) bg = p->nk * p->ngroups_per_k;  // never straddle a spin

@@ -20,8 +20,11 @@ int cuda_fail(cudaError_t e, const char* what);
     if (e__ != cudaSuccess) return ::jrb::cuda_fail(e__, #expr); \
   } while (0)
 
+void count_launch();
+
 #define JRB_CHECK_LAUNCH(name)                             \
   do {                                                     \
+    ::jrb::count_launch();                                 \
     cudaError_t e__ = cudaGetLastError();                  \
     if (e__ != cudaSuccess) return ::jrb::cuda_fail(e__, name); \
   } while (0)

@@ -18,227 +18,9 @@
 #include <cmath>
 
 #include "plan.h"
+#include "qr_gemm.cuh"
 
 namespace jrb {
-
-constexpr int QT = 72;    // CTA tile edge: 3 x 3 warps of 24 x 24 (= 3 x 3 DMMA 8 x 8 tiles)
-constexpr int QK = 16;    // reduction rows staged per step
-constexpr int QLD = 84;   // padded leading dimension of [k][72] planes   (84 % 16 == 4)
-constexpr int QLDA = 20;  // padded leading dimension of [72][k=16] planes (20 % 16 == 4)
-constexpr int QTHREADS = 288;
-
-__device__ __forceinline__ void dmma(double (&c)[2], double a, double b) {
-  asm volatile(
-    "mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
-    : "+d"(c[0]), "+d"(c[1])
-    : "d"(a), "d"(b));
-}
-
-// A tall matrix [rows][ld] given either as interleaved complex or as split re / im arrays.
-struct TallMat {
-  const double* re;
-  const double* im;  // nullptr => interleaved complex at `re`
-  long long ld;
-  __device__ __forceinline__ cplx get(long long r, int c) const {
-    if (im == nullptr) return reinterpret_cast<const cplx*>(re)[r * ld + c];
-    return cmake(re[r * ld + c], im[r * ld + c]);
-  }
-};
-
-// ---------------------------------------------------------------------------------------
-// partial[chunk][sk][i][j] = sum_{g in chunk} conj(A[g][i]) B[g][j]
-// grid: (tiles_i * tiles_j, nchunks, nsk), block 288
-__global__ void __launch_bounds__(QTHREADS)
-k_gram(TallMat A, TallMat B, long long ng, int nb, long long sk_stride_a, long long sk_stride_b,
-       int tiles, long long rows_per_chunk, cplx* __restrict__ partial) {
-  extern __shared__ __align__(16) unsigned char smem_raw_[];
-  double* sAre = reinterpret_cast<double*>(smem_raw_);
-  double* sAim = sAre + QK * QLD;
-  double* sBre = sAim + QK * QLD;
-  double* sBim = sBre + QK * QLD;
-
-  const int ti = blockIdx.x / tiles, tj = blockIdx.x % tiles;
-  const int chunk = blockIdx.y, sk = blockIdx.z;
-  const int nsk = gridDim.z;
-  const long long g_begin = (long long)chunk * rows_per_chunk;
-  const long long g_end = min(ng, g_begin + rows_per_chunk);
-  const int i0 = ti * QT, j0 = tj * QT;
-  TallMat a = A, bm = B;
-  a.re += sk * sk_stride_a * (a.im ? 1 : 2);
-  if (a.im) a.im += sk * sk_stride_a;
-  bm.re += sk * sk_stride_b * (bm.im ? 1 : 2);
-  if (bm.im) bm.im += sk * sk_stride_b;
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int wi = warp / 3, wj = warp % 3;
-  const int lr = lane >> 2, lc = lane & 3;
-
-  double cre[3][3][2], cim[3][3][2];
-#pragma unroll
-  for (int s = 0; s < 3; ++s)
-#pragma unroll
-    for (int u = 0; u < 3; ++u) {
-      cre[s][u][0] = cre[s][u][1] = 0.0;
-      cim[s][u][0] = cim[s][u][1] = 0.0;
-    }
-
-  for (long long g0 = g_begin; g0 < g_end; g0 += QK) {
-    for (int e = threadIdx.x; e < QK * QT; e += QTHREADS) {
-      const int r = e / QT, c = e % QT;
-      const long long g = g0 + r;
-      cplx va = cmake(0.0, 0.0), vb = cmake(0.0, 0.0);
-      if (g < g_end) {
-        if (i0 + c < nb) va = a.get(g, i0 + c);
-        if (j0 + c < nb) vb = bm.get(g, j0 + c);
-      }
-      sAre[r * QLD + c] = va.x;
-      sAim[r * QLD + c] = va.y;
-      sBre[r * QLD + c] = vb.x;
-      sBim[r * QLD + c] = vb.y;
-    }
-    __syncthreads();
-#pragma unroll
-    for (int k4 = 0; k4 < QK / 4; ++k4) {
-      double ar[3], ai[3], nai[3], br[3], bi[3];
-#pragma unroll
-      for (int s = 0; s < 3; ++s) {
-        // A fragment (row = i, col = k): conj(A[g][i]) -> (re, -im)
-        const int ia = (k4 * 4 + lc) * QLD + wi * 24 + s * 8 + lr;
-        ar[s] = sAre[ia];
-        ai[s] = sAim[ia];
-        nai[s] = -ai[s];
-        // B fragment (row = k, col = j)
-        const int ib = (k4 * 4 + lc) * QLD + wj * 24 + s * 8 + lr;
-        br[s] = sBre[ib];
-        bi[s] = sBim[ib];
-      }
-#pragma unroll
-      for (int s = 0; s < 3; ++s)
-#pragma unroll
-        for (int u = 0; u < 3; ++u) {
-          dmma(cre[s][u], ar[s], br[u]);
-          dmma(cre[s][u], ai[s], bi[u]);
-          dmma(cim[s][u], ar[s], bi[u]);
-          dmma(cim[s][u], nai[s], br[u]);
-        }
-    }
-    __syncthreads();
-  }
-  cplx* out = partial + ((long long)chunk * nsk + sk) * nb * nb;
-#pragma unroll
-  for (int s = 0; s < 3; ++s)
-#pragma unroll
-    for (int u = 0; u < 3; ++u) {
-      const int i = i0 + wi * 24 + s * 8 + lr;
-      const int j = j0 + wj * 24 + u * 8 + 2 * lc;
-      if (i < nb) {
-        if (j < nb) out[(long long)i * nb + j] = cmake(cre[s][u][0], cim[s][u][0]);
-        if (j + 1 < nb) out[(long long)i * nb + j + 1] = cmake(cre[s][u][1], cim[s][u][1]);
-      }
-    }
-}
-
-// ---------------------------------------------------------------------------------------
-// Out[g][j] = sum_i In1[g][i] T1[i][j] (+ sum_i In2[g][i] T2[i][j])
-// MODE 0: store interleaved complex;  MODE 1: store 2 Re / 2 Im into split real arrays.
-// grid: (row tiles, col tiles, nsk), block 288
-template <int MODE>
-__global__ void __launch_bounds__(QTHREADS)
-k_apply(TallMat In1, const cplx* __restrict__ T1, TallMat In2, const cplx* __restrict__ T2,
-        int nterms, long long ng, int nb, long long sk_stride, double* __restrict__ out_a,
-        double* __restrict__ out_b) {
-  extern __shared__ __align__(16) unsigned char smem_raw_[];
-  double* sAre = reinterpret_cast<double*>(smem_raw_);
-  double* sAim = sAre + QT * QLDA;
-  double* sBre = sAim + QT * QLDA;
-  double* sBim = sBre + QK * QLD;
-
-  const long long g0 = (long long)blockIdx.x * QT;
-  const int j0 = blockIdx.y * QT;
-  const int sk = blockIdx.z;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int wi = warp / 3, wj = warp % 3;
-  const int lr = lane >> 2, lc = lane & 3;
-
-  double cre[3][3][2], cim[3][3][2];
-#pragma unroll
-  for (int s = 0; s < 3; ++s)
-#pragma unroll
-    for (int u = 0; u < 3; ++u) {
-      cre[s][u][0] = cre[s][u][1] = 0.0;
-      cim[s][u][0] = cim[s][u][1] = 0.0;
-    }
-
-  for (int term = 0; term < nterms; ++term) {
-    TallMat in = term == 0 ? In1 : In2;
-    const cplx* T = (term == 0 ? T1 : T2) + (long long)sk * nb * nb;
-    in.re += sk * sk_stride * (in.im ? 1 : 2);
-    if (in.im) in.im += sk * sk_stride;
-    for (int k0 = 0; k0 < nb; k0 += QK) {
-      for (int e = threadIdx.x; e < QT * QK; e += QTHREADS) {
-        const int r = e / QK, c = e % QK;
-        cplx v = cmake(0.0, 0.0);
-        if (g0 + r < ng && k0 + c < nb) v = in.get(g0 + r, k0 + c);
-        sAre[r * QLDA + c] = v.x;
-        sAim[r * QLDA + c] = v.y;
-      }
-      for (int e = threadIdx.x; e < QK * QT; e += QTHREADS) {
-        const int r = e / QT, c = e % QT;
-        cplx v = cmake(0.0, 0.0);
-        if (k0 + r < nb && j0 + c < nb) v = T[(long long)(k0 + r) * nb + j0 + c];
-        sBre[r * QLD + c] = v.x;
-        sBim[r * QLD + c] = v.y;
-      }
-      __syncthreads();
-#pragma unroll
-      for (int k4 = 0; k4 < QK / 4; ++k4) {
-        double ar[3], ai[3], nai[3], br[3], bi[3];
-#pragma unroll
-        for (int s = 0; s < 3; ++s) {
-          const int ia = (wi * 24 + s * 8 + lr) * QLDA + k4 * 4 + lc;  // (row = g, col = k)
-          ar[s] = sAre[ia];
-          ai[s] = sAim[ia];
-          nai[s] = -ai[s];
-          const int ib = (k4 * 4 + lc) * QLD + wj * 24 + s * 8 + lr;   // (row = k, col = j)
-          br[s] = sBre[ib];
-          bi[s] = sBim[ib];
-        }
-#pragma unroll
-        for (int s = 0; s < 3; ++s)
-#pragma unroll
-          for (int u = 0; u < 3; ++u) {
-            dmma(cre[s][u], ar[s], br[u]);
-            dmma(cre[s][u], nai[s], bi[u]);
-            dmma(cim[s][u], ar[s], bi[u]);
-            dmma(cim[s][u], ai[s], br[u]);
-          }
-      }
-      __syncthreads();
-    }
-  }
-  const long long base = (long long)sk * sk_stride;
-#pragma unroll
-  for (int s = 0; s < 3; ++s)
-#pragma unroll
-    for (int u = 0; u < 3; ++u) {
-      const long long g = g0 + wi * 24 + s * 8 + lr;
-      const int j = j0 + wj * 24 + u * 8 + 2 * lc;
-      if (g < ng) {
-#pragma unroll
-        for (int e = 0; e < 2; ++e) {
-          if (j + e < nb) {
-            const long long o = base + g * nb + j + e;
-            if (MODE == 0) {
-              reinterpret_cast<cplx*>(out_a)[o] = cmake(cre[s][u][e], cim[s][u][e]);
-            } else {
-              out_a[o] = 2.0 * cre[s][u][e];
-              out_b[o] = 2.0 * cim[s][u][e];
-            }
-          }
-        }
-      }
-    }
-}
 
 // ---------------------------------------------------------------------------------------
 // Small (nb x nb) per-(spin,k) work: one CTA each, operating in global/L2 memory.
@@ -448,11 +230,13 @@ k_bwd_small(const cplx* __restrict__ partial, int nchunks, int nb, const double*
 
 // ---------------------------------------------------------------------------------------
 static int gram_chunks(const jrb_plan* p, int tiles) {
+  // about four waves of one CTA per SM, never fewer than 256 rows per chunk
   const int nsk = p->ns * p->nk;
-  int want = (2 * 148 + nsk * tiles * tiles - 1) / (nsk * tiles * tiles);
+  const int per_chunk = nsk * tiles * tiles;
+  int want = (4 * 148 + per_chunk - 1) / per_chunk;
   const int max_chunks = (int)std::max<int64_t>(1, p->ng / 256);
   want = std::max(1, std::min(want, max_chunks));
-  return std::min(want, 64);
+  return std::min(want, 128);
 }
 
 int qr_gram_chunks(const jrb_plan* p) {
@@ -460,17 +244,35 @@ int qr_gram_chunks(const jrb_plan* p) {
   return gram_chunks(p, tiles);
 }
 
-static int run_gram(jrb_plan* p, TallMat A, TallMat B, cplx* partial, int* nchunks_out,
+template <class K>
+static int opt_in_smem(K kernel, int bytes) {
+  if (bytes > 48 * 1024)
+    JRB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+  return 0;
+}
+
+static int run_gram(jrb_plan* p, TallMat A, TallMat B, bool same, cplx* partial, int* nchunks_out,
                     cudaStream_t st) {
   const int nsk = p->ns * p->nk;
   const int tiles = (p->nb + QT - 1) / QT;
   const int nchunks = gram_chunks(p, tiles);
   long long rows = (p->ng + nchunks - 1) / nchunks;
   rows = (rows + QK - 1) / QK * QK;
-  const int smem = 4 * QK * QLD * (int)sizeof(double);
   dim3 grid(tiles * tiles, nchunks, nsk);
-  k_gram<<<grid, QTHREADS, smem, st>>>(A, B, p->ng, p->nb, p->ng * p->nb, p->ng * p->nb, tiles,
-                                      rows, partial);
+  const long long sks = p->ng * p->nb;
+  if (same && tiles == 1) {
+    constexpr int ST = 3;
+    const int smem = ST * QK * QLDB * (int)sizeof(cplx);
+    static int once = opt_in_smem(k_gram<ST, true>, smem);
+    if (once) return once;
+    k_gram<ST, true><<<grid, QTHREADS, smem, st>>>(A, B, p->ng, p->nb, sks, tiles, rows, partial);
+  } else {
+    constexpr int ST = 3;
+    const int smem = 2 * ST * QK * QLDB * (int)sizeof(cplx);
+    static int once = opt_in_smem(k_gram<ST, false>, smem);
+    if (once) return once;
+    k_gram<ST, false><<<grid, QTHREADS, smem, st>>>(A, B, p->ng, p->nb, sks, tiles, rows, partial);
+  }
   JRB_CHECK_LAUNCH("k_gram");
   *nchunks_out = nchunks;
   return 0;
@@ -479,11 +281,14 @@ static int run_gram(jrb_plan* p, TallMat A, TallMat B, cplx* partial, int* nchun
 template <int MODE>
 static int run_apply(jrb_plan* p, TallMat in1, const cplx* t1, TallMat in2, const cplx* t2,
                      int nterms, double* out_a, double* out_b, cudaStream_t st) {
+  constexpr int ST = 3;
   const int nsk = p->ns * p->nk;
-  const int smem = (2 * QT * QLDA + 2 * QK * QLD) * (int)sizeof(double);
+  const int smem = ST * (QT * QLDA + QK * QLDB) * (int)sizeof(cplx);
+  static int once = opt_in_smem(k_apply<MODE, ST>, smem);
+  if (once) return once;
   dim3 grid((unsigned)((p->ng + QT - 1) / QT), (p->nb + QT - 1) / QT, nsk);
-  k_apply<MODE><<<grid, QTHREADS, smem, st>>>(in1, t1, in2, t2, nterms, p->ng, p->nb,
-                                             p->ng * p->nb, out_a, out_b);
+  k_apply<MODE, ST><<<grid, QTHREADS, smem, st>>>(in1, t1, in2, t2, nterms, p->ng, p->nb,
+                                                 p->ng * p->nb, out_a, out_b);
   JRB_CHECK_LAUNCH("k_apply");
   return 0;
 }
@@ -500,7 +305,7 @@ int launch_qr_fwd(jrb_plan* p, const double* w_re, const double* w_im, cplx* q, 
   TallMat W{w_re, w_im, p->nb};
   TallMat none{nullptr, nullptr, 0};
   // pass 1
-  if ((rc = run_gram(p, W, W, p->d_gpart, &nchunks, st))) return rc;
+  if ((rc = run_gram(p, W, W, true, p->d_gpart, &nchunks, st))) return rc;
   cplx* R2inv = p->d_small + 3 * nsk * nn;  // slot 3: staging, then R2^-1 for the last apply
   k_chol_inv<<<nsk, 1024, 0, st>>>(p->d_gpart, nchunks, p->nb, S, Rt, Rit, nullptr, nullptr, r,
                                    p->d_rinv, R2inv, fail);
@@ -510,7 +315,7 @@ int launch_qr_fwd(jrb_plan* p, const double* w_re, const double* w_im, cplx* q, 
     return rc;
   // pass 2
   TallMat Q1{reinterpret_cast<const double*>(p->d_tmp), nullptr, p->nb};
-  if ((rc = run_gram(p, Q1, Q1, p->d_gpart, &nchunks, st))) return rc;
+  if ((rc = run_gram(p, Q1, Q1, true, p->d_gpart, &nchunks, st))) return rc;
   k_chol_inv<<<nsk, 1024, 0, st>>>(p->d_gpart, nchunks, p->nb, S, Rt, Rit, r, p->d_rinv, r,
                                    p->d_rinv, R2inv, fail);
   JRB_CHECK_LAUNCH("k_chol_inv");
@@ -539,7 +344,7 @@ int launch_qr_bwd(jrb_plan* p, const cplx* q, const cplx* r, const cplx* gq, con
   int nchunks = 0, rc = 0;
   TallMat Q{reinterpret_cast<const double*>(q), nullptr, p->nb};
   TallMat G{reinterpret_cast<const double*>(gq), nullptr, p->nb};
-  if ((rc = run_gram(p, Q, G, p->d_gpart, &nchunks, st))) return rc;
+  if ((rc = run_gram(p, Q, G, false, p->d_gpart, &nchunks, st))) return rc;
   k_bwd_small<<<nsk, 1024, 0, st>>>(p->d_gpart, nchunks, p->nb, occ, rinv, X, T1, T2);
   JRB_CHECK_LAUNCH("k_bwd_small");
   return run_apply<1>(p, G, T1, Q, T2, 2, g_re, g_im, st);

@@ -1,0 +1,95 @@
+"""Grid constructors (host side, setup time): G / R / k vector grids, cut-off masks, FFT
+sizing.  Same names, arguments and results as jrystal.grid (jrystal/_src/grid.py), numpy
+FP64; the index maps the CUDA kernels consume are derived from these masks by the plan.
+"""
+import numpy as np
+
+_MAX_FFT = 2048  # jrystal/_src/utils.py:250
+
+
+def _smooth7(n):
+  for p in (2, 3, 5, 7):
+    while n % p == 0:
+      n //= p
+  return n == 1
+
+
+def fft_factor(n: int) -> int:
+  """Smallest 7-smooth integer >= n (jrystal/_src/utils.py:227-254, const.CUFFT_FACTORS)."""
+  if n > _MAX_FFT:
+    raise ValueError(f"The grid number {n} is too large!")
+  n = max(int(n), 1)
+  while not _smooth7(n):
+    n += 1
+  return n
+
+
+def proper_grid_size(grid_sizes):
+  """jrystal/_src/grid.py:181-210."""
+  if hasattr(grid_sizes, '__len__'):
+    sizes = np.array(grid_sizes)
+  else:
+    try:
+      sizes = np.ones(3, dtype=int) * int(grid_sizes)
+    except Exception:
+      raise TypeError('mesh should be a scalar, tuple, list or np.array.')
+  return np.array([fft_factor(int(i)) for i in sizes])
+
+
+def _frequency_grid(rows, grid_sizes, fractional):
+  rows = np.asarray(rows, dtype=np.float64)
+  out = 0.0
+  for axis, n in enumerate(grid_sizes):
+    n = int(n)
+    f = np.fft.fftfreq(n, 1.0 if fractional else 1.0 / n)
+    shape = [1, 1, 1, 3]
+    shape[axis] = n
+    out = out + (f[:, None] * rows[axis][None, :]).reshape(shape)
+  return out
+
+
+def g_vectors(cell_vectors, grid_sizes):
+  """[x, y, z, 3] reciprocal lattice vectors, integer fftfreq order (grid.py:122-149)."""
+  b = 2 * np.pi * np.linalg.inv(np.asarray(cell_vectors, dtype=np.float64)).T
+  return _frequency_grid(b, grid_sizes, False)
+
+
+def r_vectors(cell_vectors, grid_sizes):
+  """[x, y, z, 3] real-space sampling points of the FFT grid (grid.py:152-178)."""
+  return _frequency_grid(cell_vectors, grid_sizes, True)
+
+
+def monkhorst_pack(grid_sizes):
+  sizes = [int(s) for s in grid_sizes]
+  idx = np.stack(np.meshgrid(*[np.arange(s) for s in sizes], indexing='ij'), axis=-1)
+  return (idx.reshape(-1, 3) + 0.5) / np.array(sizes) - 0.5
+
+
+def k_vectors(cell_vectors, grid_sizes):
+  """Monkhorst-Pack k-points in Cartesian 1/Bohr (grid.py:239-262)."""
+  b = 2 * np.pi * np.linalg.inv(np.asarray(cell_vectors, dtype=np.float64)).T
+  return monkhorst_pack(grid_sizes) @ b
+
+
+def spherical_mask(cell_vectors, grid_sizes, cutoff_energy: float):
+  """|G|^2 <= 2 E_cut (grid.py:265-293)."""
+  g = g_vectors(cell_vectors, grid_sizes)
+  return np.linalg.norm(g, axis=-1)**2 <= cutoff_energy * 2
+
+
+def cubic_mask(grid_sizes):
+  """Per-axis half-frequency box (grid.py:296-325)."""
+  per_axis = []
+  for n in grid_sizes:
+    n = int(n)
+    g_max = (n - 1) // 2
+    keep = np.ones(n, dtype=bool)
+    keep[g_max // 2 + 1:(-g_max // 2)] = False
+    per_axis.append(keep)
+  return per_axis[0][:, None, None] & per_axis[1][None, :, None] & per_axis[2][None, None, :]
+
+
+def estimate_max_cutoff_energy(cell_vectors, mask):
+  """grid.py:328-349."""
+  g = g_vectors(cell_vectors, mask.shape)
+  return float(np.max(np.linalg.norm(g, axis=-1)**2 / 2 * mask))
