@@ -1,0 +1,97 @@
+"""Host-side logic (no GPU): grid / occupation / crystal mirrors against the oracle, k-point
+and band sharding, and the N>1 density all-reduce over gloo with world_size 2."""
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from jrystal_b200 import grid, occupation, parallel
+from jrystal_b200.crystal import Crystal
+from oracle import reference_port as rp
+from oracle import structures
+
+
+@pytest.mark.parametrize('name', ['diamond', 'si', 'si8', 'diamond8'])
+def test_builtin_crystals_match_shipped_geometry(name):
+  cell, pos, chg = structures.load(name)
+  c = Crystal.create_builtin(name)
+  np.testing.assert_allclose(c.cell_vectors, cell, atol=1e-7)
+  np.testing.assert_allclose(c.positions, pos, atol=1e-7)
+  np.testing.assert_array_equal(c.charges, chg)
+
+
+def test_grid_mirrors_oracle():
+  cell, _, _ = structures.load('diamond')
+  for gs in ([7, 8, 9], [16, 12, 24]):
+    np.testing.assert_allclose(grid.g_vectors(cell, gs), rp.g_vectors(cell, gs), atol=1e-14)
+    np.testing.assert_allclose(grid.r_vectors(cell, gs), rp.r_vectors(cell, gs), atol=1e-14)
+    np.testing.assert_array_equal(grid.cubic_mask(gs), rp.cubic_mask(gs))
+    np.testing.assert_array_equal(grid.spherical_mask(cell, gs, 15.0),
+                                  rp.spherical_mask(cell, gs, 15.0))
+  np.testing.assert_allclose(grid.k_vectors(cell, [2, 3, 1]), rp.k_vectors(cell, [2, 3, 1]),
+                             atol=1e-15)
+  assert list(grid.proper_grid_size([11, 13, 17])) == [12, 14, 18]
+  with pytest.raises(ValueError):
+    grid.fft_factor(4096)
+
+
+def test_occupation_mirrors_oracle():
+  np.testing.assert_array_equal(occupation.uniform(4, 12, 0, 10),
+                                rp.occupation_uniform(4, 12, num_bands=10).numpy())
+  np.testing.assert_array_equal(occupation.gamma(4, 12, 0, 10),
+                                rp.occupation_gamma(4, 12, num_bands=10).numpy())
+  f = occupation.uniform(2, 8, 0, 6)
+  assert abs(occupation.fermi_dirac_entropy(f) -
+             rp.entropy_fermi_dirac(torch.from_numpy(f)).item()) < 1e-12
+  with pytest.raises(ValueError):
+    occupation.param_init(None, 4, 8, 2, method='nope')
+
+
+def test_sharding():
+  assert [parallel.shard_kpoints(64, 8, r) for r in (0, 7)] == [(0, 8), (56, 64)]
+  with pytest.raises(ValueError):
+    parallel.shard_kpoints(6, 4, 0)   # reference: nk % ndev == 0 (spmd/uniform.py:22-24)
+  blocks = [parallel.shard_bands(208, 8, r) for r in range(8)]
+  assert blocks[0] == (0, 26) and blocks[-1] == (182, 208)
+  blocks = [parallel.shard_bands(10, 4, r) for r in range(4)]
+  assert blocks == [(0, 3), (3, 6), (6, 8), (8, 10)]
+
+
+def _rank_density(rank, world, port, out_dir):
+  os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
+  dist.init_process_group('gloo', rank=rank, world_size=world)
+  try:
+    s = rp.System.from_name('diamond', [7, 8, 9], [2, 1, 1], mask_method='cubic')
+    nb = 6
+    p = rp.param_init(5, nb, s.num_k, s.mask)
+    occ = rp.occupation_uniform(s.num_k, s.num_electrons, num_bands=nb)
+    k0, k1 = parallel.shard_kpoints(s.num_k, world, rank)
+    c = rp.coeff(torch.from_numpy(p['w_re'][:, k0:k1]), torch.from_numpy(p['w_im'][:, k0:k1]),
+                 s.mask)
+    rho = rp.density_grid(c, s.vol, occ[:, k0:k1]).contiguous()
+    e_kin = rp.energy_kinetic(s.g_vec, s.kpts[k0:k1], c, occ[:, k0:k1]).reshape(1).contiguous()
+    parallel.allreduce_density(rho, e_kin)
+    np.save(os.path.join(out_dir, f'rho{rank}.npy'), rho.numpy())
+    np.save(os.path.join(out_dir, f'ekin{rank}.npy'), e_kin.numpy())
+  finally:
+    dist.destroy_process_group()
+
+
+def test_gloo_world2_density_allreduce(tmp_path):
+  """k-sharded partial densities summed over 2 ranks equal the unsharded density (the only
+  data-path collective of the evaluation; pw.py:278 under the reference's k mesh)."""
+  port = 29500 + (os.getpid() % 2000)
+  mp.spawn(_rank_density, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+  s = rp.System.from_name('diamond', [7, 8, 9], [2, 1, 1], mask_method='cubic')
+  nb = 6
+  p = rp.param_init(5, nb, s.num_k, s.mask)
+  occ = rp.occupation_uniform(s.num_k, s.num_electrons, num_bands=nb)
+  c = rp.coeff(torch.from_numpy(p['w_re']), torch.from_numpy(p['w_im']), s.mask)
+  rho = rp.density_grid(c, s.vol, occ).numpy()
+  e_kin = rp.energy_kinetic(s.g_vec, s.kpts, c, occ).item()
+  for r in range(2):
+    np.testing.assert_allclose(np.load(tmp_path / f'rho{r}.npy'), rho, rtol=1e-13, atol=1e-15)
+    assert abs(np.load(tmp_path / f'ekin{r}.npy')[0] - e_kin) < 1e-12 * abs(e_kin)
