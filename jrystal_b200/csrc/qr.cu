@@ -40,13 +40,16 @@ k_chol_inv(const cplx* __restrict__ partial, int nchunks, int nb, cplx* __restri
   S += sk * nn; Rt += sk * nn; Rit += sk * nn;
   r_out += sk * nn; rinv_out += sk * nn; scratch += sk * nn;
   const int tid = threadIdx.x, nt = blockDim.x;
+  // k_gram writes only the blocks on and above the block diagonal: mirror (Hermitian)
   for (long long e = tid; e < nn; e += nt) {
+    const int i = (int)(e / nb), j = (int)(e % nb);
+    const long long src = j >= i ? e : (long long)j * nb + i;
     cplx s = cmake(0.0, 0.0);
     for (int c = 0; c < nchunks; ++c) {
-      const cplx v = partial[((long long)c * nsk + sk) * nn + e];
+      const cplx v = partial[((long long)c * nsk + sk) * nn + src];
       s.x += v.x; s.y += v.y;
     }
-    S[e] = s;
+    S[e] = j >= i ? s : cconj(s);
   }
   __syncthreads();
   // right-looking Cholesky on the lower triangle
@@ -187,11 +190,13 @@ k_bwd_small(const cplx* __restrict__ partial, int nchunks, int nb, const double*
   const int tid = threadIdx.x, nt = blockDim.x;
   // M staged in T2
   for (long long e = tid; e < nn; e += nt) {
-    const int j = (int)(e % nb);
+    const int i = (int)(e / nb), j = (int)(e % nb);
     cplx s = cmake(0.0, 0.0);
-    for (int c = 0; c < nchunks; ++c) {
-      const cplx v = partial[((long long)c * nsk + sk) * nn + e];
-      s.x += v.x; s.y += v.y;
+    if (j >= i) {  // k_gram computes only the upper blocks; only up(M) and diag are used
+      for (int c = 0; c < nchunks; ++c) {
+        const cplx v = partial[((long long)c * nsk + sk) * nn + e];
+        s.x += v.x; s.y += v.y;
+      }
     }
     const double fj = f ? f[j] : 1.0;
     T2[e] = cmake(s.x * fj, s.y * fj);
@@ -230,13 +235,25 @@ k_bwd_small(const cplx* __restrict__ partial, int nchunks, int nb, const double*
 
 // ---------------------------------------------------------------------------------------
 static int gram_chunks(const jrb_plan* p, int tiles) {
-  // about four waves of one CTA per SM, never fewer than 256 rows per chunk
+  // CTAs = upper super-tile pairs x chunks x (spin,k); two CTAs are resident per SM.  Pick the
+  // chunk count (>= 256 rows each) whose last wave is fullest, preferring >= 2 waves.
   const int nsk = p->ns * p->nk;
-  const int per_chunk = nsk * tiles * tiles;
-  int want = (4 * 148 + per_chunk - 1) / per_chunk;
-  const int max_chunks = (int)std::max<int64_t>(1, p->ng / 256);
-  want = std::max(1, std::min(want, max_chunks));
-  return std::min(want, 128);
+  const int per_chunk = nsk * (tiles * (tiles + 1) / 2);
+  const int slots = 2 * 148;
+  const int max_chunks = (int)std::max<int64_t>(1, std::min<int64_t>(128, p->ng / 256));
+  int best = 1;
+  double best_score = -1.0;
+  for (int c = 1; c <= max_chunks; ++c) {
+    const double waves = (double)per_chunk * c / slots;
+    double eff = waves / std::ceil(waves);
+    if (waves < 2.0) eff *= 0.5 + 0.25 * waves;      // too few CTAs to hide the prologues
+    if (waves > 6.0) eff *= 6.0 / waves;             // shorter k-loops cost more per row
+    if (eff > best_score + 1e-9) {
+      best_score = eff;
+      best = c;
+    }
+  }
+  return best;
 }
 
 int qr_gram_chunks(const jrb_plan* p) {
@@ -251,46 +268,57 @@ static int opt_in_smem(K kernel, int bytes) {
   return 0;
 }
 
+// partial = upper blocks of A^H B, split over row chunks
 static int run_gram(jrb_plan* p, TallMat A, TallMat B, bool same, cplx* partial, int* nchunks_out,
                     cudaStream_t st) {
+  constexpr int ST = 3;
   const int nsk = p->ns * p->nk;
   const int tiles = (p->nb + QT - 1) / QT;
   const int nchunks = gram_chunks(p, tiles);
   long long rows = (p->ng + nchunks - 1) / nchunks;
   rows = (rows + QK - 1) / QK * QK;
-  dim3 grid(tiles * tiles, nchunks, nsk);
+  dim3 grid(tiles * (tiles + 1) / 2, nchunks, nsk);
   const long long sks = p->ng * p->nb;
-  if (same && tiles == 1) {
-    constexpr int ST = 3;
-    const int smem = ST * QK * QLDB * (int)sizeof(cplx);
-    static int once = opt_in_smem(k_gram<ST, true>, smem);
-    if (once) return once;
-    k_gram<ST, true><<<grid, QTHREADS, smem, st>>>(A, B, p->ng, p->nb, sks, tiles, rows, partial);
-  } else {
-    constexpr int ST = 3;
-    const int smem = 2 * ST * QK * QLDB * (int)sizeof(cplx);
-    static int once = opt_in_smem(k_gram<ST, false>, smem);
-    if (once) return once;
-    k_gram<ST, false><<<grid, QTHREADS, smem, st>>>(A, B, p->ng, p->nb, sks, tiles, rows, partial);
-  }
+  const int panels = (same && tiles == 1) ? 1 : 2;
+  const int smem = panels * ST * QK * QLDB * (int)sizeof(cplx);
+  static int once = opt_in_smem(k_gram<ST>, 2 * ST * QK * QLDB * (int)sizeof(cplx));
+  if (once) return once;
+  k_gram<ST><<<grid, QTHREADS, smem, st>>>(A, B, same ? 1 : 0, p->ng, p->nb, sks, tiles, rows,
+                                           partial);
   JRB_CHECK_LAUNCH("k_gram");
   *nchunks_out = nchunks;
   return 0;
 }
 
-template <int MODE>
-static int run_apply(jrb_plan* p, TallMat in1, const cplx* t1, TallMat in2, const cplx* t2,
-                     int nterms, double* out_a, double* out_b, cudaStream_t st) {
-  constexpr int ST = 3;
+template <int MODE, int NCB>
+static int run_apply_ncb(jrb_plan* p, TallMat in1, const cplx* t1, int tri1, TallMat in2,
+                         const cplx* t2, int tri2, int nterms, double* out_a, double* out_b,
+                         cudaStream_t st) {
+  constexpr int ST = 2;
   const int nsk = p->ns * p->nk;
-  const int smem = ST * (QT * QLDA + QK * QLDB) * (int)sizeof(cplx);
-  static int once = opt_in_smem(k_apply<MODE, ST>, smem);
+  const int smem = ST * (QROWS * QLDA + QK * (8 * NCB + 2)) * (int)sizeof(cplx);
+  static int once = opt_in_smem(k_apply<MODE, NCB, ST>, smem);
   if (once) return once;
-  dim3 grid((unsigned)((p->ng + QT - 1) / QT), (p->nb + QT - 1) / QT, nsk);
-  k_apply<MODE, ST><<<grid, QTHREADS, smem, st>>>(in1, t1, in2, t2, nterms, p->ng, p->nb,
-                                                 p->ng * p->nb, out_a, out_b);
+  dim3 grid((unsigned)((p->ng + QROWS - 1) / QROWS), (p->nb + 8 * NCB - 1) / (8 * NCB), nsk);
+  k_apply<MODE, NCB, ST><<<grid, QTHREADS, smem, st>>>(in1, t1, tri1, in2, t2, tri2, nterms,
+                                                      p->ng, p->nb, p->ng * p->nb, out_a, out_b);
   JRB_CHECK_LAUNCH("k_apply");
   return 0;
+}
+
+// column-tile width: the smallest of 32 / 72 / 104 columns that covers nb in the fewest tiles
+template <int MODE>
+static int run_apply(jrb_plan* p, TallMat in1, const cplx* t1, int tri1, TallMat in2,
+                     const cplx* t2, int tri2, int nterms, double* out_a, double* out_b,
+                     cudaStream_t st) {
+  const int nb = p->nb;
+  if (nb <= 32) return run_apply_ncb<MODE, 4>(p, in1, t1, tri1, in2, t2, tri2, nterms, out_a, out_b, st);
+  if (nb <= 72) return run_apply_ncb<MODE, 9>(p, in1, t1, tri1, in2, t2, tri2, nterms, out_a, out_b, st);
+  const int t104 = (nb + 103) / 104, t72 = (nb + 71) / 72;
+  // padded column count decides (tensor work scales with it)
+  if (t104 * 104 <= t72 * 72 || t104 < t72)
+    return run_apply_ncb<MODE, 13>(p, in1, t1, tri1, in2, t2, tri2, nterms, out_a, out_b, st);
+  return run_apply_ncb<MODE, 9>(p, in1, t1, tri1, in2, t2, tri2, nterms, out_a, out_b, st);
 }
 
 int launch_qr_fwd(jrb_plan* p, const double* w_re, const double* w_im, cplx* q, cplx* r,
@@ -310,8 +338,8 @@ int launch_qr_fwd(jrb_plan* p, const double* w_re, const double* w_im, cplx* q, 
   k_chol_inv<<<nsk, 1024, 0, st>>>(p->d_gpart, nchunks, p->nb, S, Rt, Rit, nullptr, nullptr, r,
                                    p->d_rinv, R2inv, fail);
   JRB_CHECK_LAUNCH("k_chol_inv");
-  if ((rc = run_apply<0>(p, W, p->d_rinv, none, nullptr, 1, reinterpret_cast<double*>(p->d_tmp),
-                         nullptr, st)))
+  if ((rc = run_apply<0>(p, W, p->d_rinv, TRI_UPPER, none, nullptr, TRI_FULL, 1,
+                         reinterpret_cast<double*>(p->d_tmp), nullptr, st)))
     return rc;
   // pass 2
   TallMat Q1{reinterpret_cast<const double*>(p->d_tmp), nullptr, p->nb};
@@ -321,8 +349,8 @@ int launch_qr_fwd(jrb_plan* p, const double* w_re, const double* w_im, cplx* q, 
   JRB_CHECK_LAUNCH("k_chol_inv");
   // Rit still holds R2^-1 (only Rt and S were reused for staging)
   JRB_CUDA(cudaMemcpyAsync(R2inv, Rit, sizeof(cplx) * nsk * nn, cudaMemcpyDeviceToDevice, st));
-  if ((rc = run_apply<0>(p, Q1, R2inv, none, nullptr, 1, reinterpret_cast<double*>(q), nullptr,
-                         st)))
+  if ((rc = run_apply<0>(p, Q1, R2inv, TRI_UPPER, none, nullptr, TRI_FULL, 1,
+                         reinterpret_cast<double*>(q), nullptr, st)))
     return rc;
   return 0;
 }
@@ -347,7 +375,7 @@ int launch_qr_bwd(jrb_plan* p, const cplx* q, const cplx* r, const cplx* gq, con
   if ((rc = run_gram(p, Q, G, false, p->d_gpart, &nchunks, st))) return rc;
   k_bwd_small<<<nsk, 1024, 0, st>>>(p->d_gpart, nchunks, p->nb, occ, rinv, X, T1, T2);
   JRB_CHECK_LAUNCH("k_bwd_small");
-  return run_apply<1>(p, G, T1, Q, T2, 2, g_re, g_im, st);
+  return run_apply<1>(p, G, T1, TRI_LOWER, Q, T2, TRI_FULL, 2, g_re, g_im, st);
 }
 
 }  // namespace jrb

@@ -1,12 +1,20 @@
-// Tall-skinny complex-FP64 products on the FP64 tensor cores (DMMA mma.sync.m8n8k4.f64):
-//   k_gram : partial[chunk][sk] = A^H B over a chunk of rows           (split-K Gram)
-//   k_apply: Out = In1 T1 (+ In2 T2)                                   (tall times small)
-// CTA = 288 threads = 3 x 3 warps, CTA tile 72 x 72, warp tile 24 x 24 = 3 x 3 DMMA tiles;
-// a complex product is 4 real DMMAs.  Operands are staged as interleaved complex in shared
-// memory by cp.async (LDGSTS) in a multi-stage ring so global loads overlap the tensor pipe;
-// fragment loads are LDS.128 (re, im together) and conflict free by construction:
-// leading dimensions are == 2 (mod 8) complex for [k][72] panels and == 4 (mod 8) for
-// [72][k] panels.
+// Tall-skinny complex-FP64 products on the FP64 tensor cores (DMMA mma.sync.m8n8k4.f64;
+// tcgen05/TMEM have no FP64 kind):
+//   k_gram : partial[chunk][sk] = upper blocks of A^H B over a chunk of rows  (split-K Gram)
+//   k_apply: Out = In1 T1 (+ In2 T2), T1/T2 small, optionally triangular       (tall x small)
+// Measured on B200 (tools/fp64_peak.cu): DMMA peaks at 36.9 TFLOP/s = the DFMA rate, so the
+// only way to go faster is to issue fewer of them.  Both kernels therefore skip the 8x8 blocks
+// that are structurally zero or not needed:
+//   * Gram matrices are Hermitian (W^H W) or only their upper triangle is consumed (the QR
+//     adjoint uses up(Q^H G) and Re diag) -> only blocks bi <= bj are computed (45 of 81 per
+//     72 x 72 super-tile on the diagonal);
+//   * R^-1 is upper triangular and diag(f) R^-H lower triangular -> the k-range of every
+//     8-column block of the apply is clipped to its non-zero part.
+// CTA = 256 threads = 8 warps (2 per SM sub-partition).  Operands are staged as interleaved
+// complex in shared memory by cp.async (LDGSTS) in a multi-stage ring; fragment loads are
+// LDS.128 (re, im together) and bank-conflict free by construction: leading dimensions are
+// == 2 (mod 8) complex for [k][cols] panels and == 4 (mod 8) for [rows][k] panels.  A complex
+// product is 4 real DMMAs.
 #pragma once
 #include <cuda_runtime.h>
 
@@ -14,11 +22,16 @@
 
 namespace jrb {
 
-constexpr int QT = 72;     // CTA tile edge
-constexpr int QK = 16;     // reduction depth per stage
-constexpr int QLDB = 74;   // [k][72] panel leading dimension (complex), 74 % 8 == 2
-constexpr int QLDA = 20;   // [72][k] panel leading dimension (complex), 20 % 8 == 4
-constexpr int QTHREADS = 288;
+constexpr int QT = 72;        // Gram super-tile edge = 9 blocks of 8
+constexpr int QK = 16;        // reduction depth per pipeline stage
+constexpr int QLDB = QT + 2;  // [k][72] panel leading dimension (complex), 74 % 8 == 2
+constexpr int QLDA = QK + 4;  // [rows][k] panel leading dimension (complex), 20 % 8 == 4
+constexpr int QTHREADS = 256;
+constexpr int QWARPS = 8;
+constexpr int QROWS = 8 * QWARPS;  // rows of the apply CTA tile (one 8-row block per warp)
+constexpr int QMAXSLOT = 11;       // ceil(81 / 8) Gram blocks per warp
+
+enum TriKind { TRI_FULL = 0, TRI_UPPER = 1, TRI_LOWER = 2 };
 
 __device__ __forceinline__ void dmma(double (&c)[2], double a, double b) {
   asm volatile(
@@ -66,52 +79,75 @@ struct TallMat {
   }
 };
 
-struct Acc {
-  double re[3][3][2], im[3][3][2];
-  __device__ __forceinline__ void zero() {
-#pragma unroll
-    for (int s = 0; s < 3; ++s)
-#pragma unroll
-      for (int u = 0; u < 3; ++u) re[s][u][0] = re[s][u][1] = im[s][u][0] = im[s][u][1] = 0.0;
-  }
-};
-
 // ---------------------------------------------------------------------------------------
-// partial[chunk][sk][i][j] = sum_{g in chunk} conj(A[g][i]) B[g][j]
-// grid: (tiles * tiles, nchunks, nsk); dynamic smem: STAGES * (SAME ? 1 : 2) panels
-template <int STAGES, bool SAME>
-__global__ void __launch_bounds__(QTHREADS, 1)
-k_gram(TallMat A, TallMat B, long long ng, int nb, long long sk_stride, int tiles,
+// partial[chunk][sk][i][j] = sum_{g in chunk} conj(A[g][i]) B[g][j]   for 8x8 blocks bi <= bj
+// (entries below the block diagonal are NOT written; consumers mirror / ignore them).
+// grid: (ntiles (ntiles + 1) / 2 upper super-tiles, nchunks, nsk)
+// dynamic smem: STAGES * 2 panels [QK][QLDB]
+template <int STAGES>
+__global__ void __launch_bounds__(QTHREADS, 2)
+k_gram(TallMat A, TallMat B, int same, long long ng, int nb, long long sk_stride, int ntiles,
        long long rows_per_chunk, cplx* __restrict__ partial) {
   extern __shared__ __align__(16) unsigned char smem_raw_[];
   cplx* sA = reinterpret_cast<cplx*>(smem_raw_);
-  cplx* sB = SAME ? sA : sA + STAGES * QK * QLDB;
+  // upper super-tile (ti <= tj) of this CTA
+  int ti = 0, rem = blockIdx.x;
+  while (rem >= ntiles - ti) {
+    rem -= ntiles - ti;
+    ++ti;
+  }
+  const int tj = ti + rem;
+  const bool diag = ti == tj;
+  const bool one_panel = same && diag;
+  cplx* sB = one_panel ? sA : sA + STAGES * QK * QLDB;
 
-  const int ti = blockIdx.x / tiles, tj = blockIdx.x % tiles;
   const int chunk = blockIdx.y, sk = blockIdx.z, nsk = gridDim.z;
   const long long g_begin = (long long)chunk * rows_per_chunk;
   const long long g_end = min(ng, g_begin + rows_per_chunk);
   const int i0 = ti * QT, j0 = tj * QT;
+  const int wi_cols = min(QT, nb - i0), wj_cols = min(QT, nb - j0);
+  const int nbi = (wi_cols + 7) >> 3, nbj = (wj_cols + 7) >> 3;
   const TallMat a = A.offset(sk * sk_stride), bm = B.offset(sk * sk_stride);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int wi = warp / 3, wj = warp % 3;
   const int lr = lane >> 2, lc = lane & 3;
   const int nsteps = g_end > g_begin ? (int)((g_end - g_begin + QK - 1) / QK) : 0;
 
+  // blocks of this warp: ids warp, warp + 8, ... in the row-major list of needed blocks
+  // packed per slot: 8 bi in the low half, 8 bj in the high half, -1 = no block
+  int blk[QMAXSLOT];
+#pragma unroll
+  for (int s = 0; s < QMAXSLOT; ++s) {
+    int id = warp + QWARPS * s, bi, bj;
+    if (diag) {
+      bi = 0;
+      while (bi < nbi && id >= nbj - bi) {
+        id -= nbj - bi;
+        ++bi;
+      }
+      bj = bi + id;
+    } else {
+      bi = id / nbj;
+      bj = id % nbj;
+    }
+    blk[s] = bi < nbi ? (8 * bi) | ((8 * bj) << 16) : -1;
+  }
+  const int lofs = lc * QLDB + lr;
+
   auto load_stage = [&](int step, int stage) {
     const long long g0 = g_begin + (long long)step * QK;
-#pragma unroll
-    for (int e0 = 0; e0 < QK * QT; e0 += QTHREADS) {
-      const int e = e0 + threadIdx.x;
+    for (int e = threadIdx.x; e < QK * QT; e += QTHREADS) {
       const int r = e / QT, c = e % QT;
       const long long g = g0 + r;
-      a.fetch(&sA[(stage * QK + r) * QLDB + c], g, i0 + c, g < g_end && i0 + c < nb);
-      if (!SAME) bm.fetch(&sB[(stage * QK + r) * QLDB + c], g, j0 + c, g < g_end && j0 + c < nb);
+      a.fetch(&sA[(stage * QK + r) * QLDB + c], g, i0 + c, g < g_end && c < wi_cols);
+      if (!one_panel)
+        bm.fetch(&sB[(stage * QK + r) * QLDB + c], g, j0 + c, g < g_end && c < wj_cols);
     }
   };
 
-  Acc acc;
-  acc.zero();
+  double cre[QMAXSLOT][2], cim[QMAXSLOT][2];
+#pragma unroll
+  for (int s = 0; s < QMAXSLOT; ++s) cre[s][0] = cre[s][1] = cim[s][0] = cim[s][1] = 0.0;
+
 #pragma unroll
   for (int s = 0; s < STAGES - 1; ++s) {
     if (s < nsteps) load_stage(s, s);
@@ -126,22 +162,16 @@ k_gram(TallMat A, TallMat B, long long ng, int nb, long long sk_stride, int tile
     const cplx* pb = sB + (it % STAGES) * QK * QLDB;
 #pragma unroll
     for (int k4 = 0; k4 < QK / 4; ++k4) {
-      cplx fa[3], fb[3];
 #pragma unroll
-      for (int s = 0; s < 3; ++s) {
-        fa[s] = pa[(k4 * 4 + lc) * QLDB + wi * 24 + s * 8 + lr];  // A frag (row i, col k)
-        fb[s] = pb[(k4 * 4 + lc) * QLDB + wj * 24 + s * 8 + lr];  // B frag (row k, col j)
-      }
-#pragma unroll
-      for (int s = 0; s < 3; ++s) {
-        const double nai = -fa[s].y;
-#pragma unroll
-        for (int u = 0; u < 3; ++u) {
+      for (int s = 0; s < QMAXSLOT; ++s) {
+        if (blk[s] >= 0) {
+          const cplx fa = pa[k4 * 4 * QLDB + lofs + (blk[s] & 0xffff)];  // A frag (row i, col k)
+          const cplx fb = pb[k4 * 4 * QLDB + lofs + (blk[s] >> 16)];     // B frag (row k, col j)
           // conj(a) b = (ar br + ai bi) + i (ar bi - ai br)
-          dmma(acc.re[s][u], fa[s].x, fb[u].x);
-          dmma(acc.im[s][u], fa[s].x, fb[u].y);
-          dmma(acc.re[s][u], fa[s].y, fb[u].y);
-          dmma(acc.im[s][u], nai, fb[u].x);
+          dmma(cre[s], fa.x, fb.x);
+          dmma(cim[s], fa.x, fb.y);
+          dmma(cre[s], fa.y, fb.y);
+          dmma(cim[s], -fa.y, fb.x);
         }
       }
     }
@@ -149,67 +179,76 @@ k_gram(TallMat A, TallMat B, long long ng, int nb, long long sk_stride, int tile
   cp_async_wait<0>();
   cplx* out = partial + ((long long)chunk * nsk + sk) * nb * nb;
 #pragma unroll
-  for (int s = 0; s < 3; ++s)
-#pragma unroll
-    for (int u = 0; u < 3; ++u) {
-      const int i = i0 + wi * 24 + s * 8 + lr;
-      const int j = j0 + wj * 24 + u * 8 + 2 * lc;
+  for (int s = 0; s < QMAXSLOT; ++s) {
+    if (blk[s] >= 0) {
+      const int i = i0 + (blk[s] & 0xffff) + lr;
+      const int j = j0 + (blk[s] >> 16) + 2 * lc;
       if (i < nb) {
-        if (j < nb) out[(long long)i * nb + j] = cmake(acc.re[s][u][0], acc.im[s][u][0]);
-        if (j + 1 < nb) out[(long long)i * nb + j + 1] = cmake(acc.re[s][u][1], acc.im[s][u][1]);
+        if (j < nb) out[(long long)i * nb + j] = cmake(cre[s][0], cim[s][0]);
+        if (j + 1 < nb) out[(long long)i * nb + j + 1] = cmake(cre[s][1], cim[s][1]);
       }
     }
+  }
 }
 
 // ---------------------------------------------------------------------------------------
 // Out[g][j] = sum_i In1[g][i] T1[i][j] (+ sum_i In2[g][i] T2[i][j])
+// tri1 / tri2 say which part of T1 / T2 is structurally zero (TriKind); the k-range of each
+// 8-column block is clipped accordingly.
 // MODE 0: store interleaved complex;  MODE 1: store 2 Re / 2 Im into split real arrays.
-// grid: (row tiles, col tiles, nsk)
-template <int MODE, int STAGES>
-__global__ void __launch_bounds__(QTHREADS, 1)
-k_apply(TallMat In1, const cplx* __restrict__ T1, TallMat In2, const cplx* __restrict__ T2,
-        int nterms, long long ng, int nb, long long sk_stride, double* __restrict__ out_a,
-        double* __restrict__ out_b) {
+// CTA tile: 64 rows (one 8-row block per warp) x 8 NCB columns.
+// grid: (ceil(ng / 64), ceil(nb / (8 NCB)), nsk)
+template <int MODE, int NCB, int STAGES>
+__global__ void __launch_bounds__(QTHREADS, 2)
+k_apply(TallMat In1, const cplx* __restrict__ T1, int tri1, TallMat In2,
+        const cplx* __restrict__ T2, int tri2, int nterms, long long ng, int nb,
+        long long sk_stride, double* __restrict__ out_a, double* __restrict__ out_b) {
+  constexpr int LDB = 8 * NCB + 2;
   extern __shared__ __align__(16) unsigned char smem_raw_[];
-  cplx* sA = reinterpret_cast<cplx*>(smem_raw_);           // [STAGES][72][QLDA]
-  cplx* sB = sA + STAGES * QT * QLDA;                       // [STAGES][QK][QLDB]
+  cplx* sA = reinterpret_cast<cplx*>(smem_raw_);  // [STAGES][64][QLDA]
+  cplx* sB = sA + STAGES * QROWS * QLDA;          // [STAGES][QK][LDB]
 
-  const long long g0 = (long long)blockIdx.x * QT;
-  const int j0 = blockIdx.y * QT;
+  const long long g0 = (long long)blockIdx.x * QROWS;
+  const int j0 = blockIdx.y * 8 * NCB;
+  const int jend = min(nb, j0 + 8 * NCB);
   const int sk = blockIdx.z;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int wi = warp / 3, wj = warp % 3;
   const int lr = lane >> 2, lc = lane & 3;
-  const int ksteps = (nb + QK - 1) / QK;
-  const int nsteps = ksteps * nterms;
   const TallMat in1 = In1.offset(sk * sk_stride);
   const TallMat in2 = nterms > 1 ? In2.offset(sk * sk_stride) : in1;
   const cplx* t1 = T1 + (long long)sk * nb * nb;
   const cplx* t2 = nterms > 1 ? T2 + (long long)sk * nb * nb : t1;
 
+  // k-range of each term for this column tile (multiples of 4 at the lower end)
+  auto kbeg_of = [&](int tri) { return tri == TRI_LOWER ? (j0 & ~3) : 0; };
+  auto kend_of = [&](int tri) { return tri == TRI_UPPER ? jend : nb; };
+  const int kb1 = kbeg_of(tri1), ke1 = kend_of(tri1);
+  const int kb2 = kbeg_of(tri2), ke2 = nterms > 1 ? kend_of(tri2) : kb2;
+  const int ns1 = (ke1 - kb1 + QK - 1) / QK;
+  const int ns2 = nterms > 1 ? (ke2 - kb2 + QK - 1) / QK : 0;
+  const int nsteps = ns1 + ns2;
+
   auto load_stage = [&](int step, int stage) {
-    const bool second = step >= ksteps;
-    const int k0 = (second ? step - ksteps : step) * QK;
+    const bool second = step >= ns1;
+    const int k0 = second ? kb2 + (step - ns1) * QK : kb1 + step * QK;
+    const int kend = second ? ke2 : ke1;
     const TallMat& in = second ? in2 : in1;
     const cplx* T = second ? t2 : t1;
-#pragma unroll
-    for (int e0 = 0; e0 < QT * QK; e0 += QTHREADS) {
-      const int e = e0 + threadIdx.x;
-      {
-        const int r = e / QK, c = e % QK;
-        in.fetch(&sA[(stage * QT + r) * QLDA + c], g0 + r, k0 + c, g0 + r < ng && k0 + c < nb);
-      }
-      {
-        const int r = e / QT, c = e % QT;
-        const bool v = k0 + r < nb && j0 + c < nb;
-        cp_async16(&sB[(stage * QK + r) * QLDB + c], T + (v ? (long long)(k0 + r) * nb + j0 + c : 0),
-                   v);
-      }
+    for (int e = threadIdx.x; e < QROWS * QK; e += QTHREADS) {
+      const int r = e / QK, c = e % QK;
+      in.fetch(&sA[(stage * QROWS + r) * QLDA + c], g0 + r, k0 + c, g0 + r < ng && k0 + c < kend);
+    }
+    for (int e = threadIdx.x; e < QK * 8 * NCB; e += QTHREADS) {
+      const int r = e / (8 * NCB), c = e % (8 * NCB);
+      const bool v = k0 + r < kend && j0 + c < nb;
+      cp_async16(&sB[(stage * QK + r) * LDB + c], T + (v ? (long long)(k0 + r) * nb + j0 + c : 0), v);
     }
   };
 
-  Acc acc;
-  acc.zero();
+  double cre[NCB][2], cim[NCB][2];
+#pragma unroll
+  for (int u = 0; u < NCB; ++u) cre[u][0] = cre[u][1] = cim[u][0] = cim[u][1] = 0.0;
+
 #pragma unroll
   for (int s = 0; s < STAGES - 1; ++s) {
     if (s < nsteps) load_stage(s, s);
@@ -220,56 +259,60 @@ k_apply(TallMat In1, const cplx* __restrict__ T1, TallMat In2, const cplx* __res
     __syncthreads();
     if (it + STAGES - 1 < nsteps) load_stage(it + STAGES - 1, (it + STAGES - 1) % STAGES);
     cp_async_commit();
-    const cplx* pa = sA + (it % STAGES) * QT * QLDA;
-    const cplx* pb = sB + (it % STAGES) * QK * QLDB;
+    const bool second = it >= ns1;
+    const int k0 = second ? kb2 + (it - ns1) * QK : kb1 + it * QK;
+    const int kend = second ? ke2 : ke1;
+    const int tri = second ? tri2 : tri1;
+    const cplx* pa = sA + ((it % STAGES) * QROWS + warp * 8 + lr) * QLDA + lc;
+    const cplx* pb = sB + (it % STAGES) * QK * LDB + lc * LDB + lr;
 #pragma unroll
     for (int k4 = 0; k4 < QK / 4; ++k4) {
-      cplx fa[3], fb[3];
+      const int kk = k0 + 4 * k4;  // this sub-step covers i in [kk, kk + 4)
+      if (kk < kend) {
+        const cplx fa = pa[k4 * 4];  // A frag (row g, col k)
+        const double nai = -fa.y;
 #pragma unroll
-      for (int s = 0; s < 3; ++s) {
-        fa[s] = pa[(wi * 24 + s * 8 + lr) * QLDA + k4 * 4 + lc];  // A frag (row g, col k)
-        fb[s] = pb[(k4 * 4 + lc) * QLDB + wj * 24 + s * 8 + lr];  // B frag (row k, col j)
-      }
-#pragma unroll
-      for (int s = 0; s < 3; ++s) {
-        const double nai = -fa[s].y;
-#pragma unroll
-        for (int u = 0; u < 3; ++u) {
-          // a b = (ar br - ai bi) + i (ar bi + ai br)
-          dmma(acc.re[s][u], fa[s].x, fb[u].x);
-          dmma(acc.im[s][u], fa[s].x, fb[u].y);
-          dmma(acc.re[s][u], nai, fb[u].y);
-          dmma(acc.im[s][u], fa[s].y, fb[u].x);
+        for (int u = 0; u < NCB; ++u) {
+          const int jlo = j0 + 8 * u;  // columns [jlo, jlo + 8)
+          // upper T: zero for i > j -> need kk <= jlo + 7; lower T: zero for i < j -> kk + 3 >= jlo
+          const bool need = jlo < nb && (tri == TRI_UPPER ? kk <= jlo + 7
+                                                          : (tri == TRI_LOWER ? kk + 3 >= jlo : true));
+          if (need) {
+            const cplx fb = pb[k4 * 4 * LDB + 8 * u];  // B frag (row k, col j)
+            // a b = (ar br - ai bi) + i (ar bi + ai br)
+            dmma(cre[u], fa.x, fb.x);
+            dmma(cim[u], fa.x, fb.y);
+            dmma(cre[u], nai, fb.y);
+            dmma(cim[u], fa.y, fb.x);
+          }
         }
       }
     }
   }
   cp_async_wait<0>();
   const long long base = (long long)sk * sk_stride;
+  const long long g = g0 + warp * 8 + lr;
+  if (g < ng) {
 #pragma unroll
-  for (int s = 0; s < 3; ++s)
-#pragma unroll
-    for (int u = 0; u < 3; ++u) {
-      const long long g = g0 + wi * 24 + s * 8 + lr;
-      const int j = j0 + wj * 24 + u * 8 + 2 * lc;
-      if (g < ng) {
-        if (MODE == 0) {
-          cplx* o = reinterpret_cast<cplx*>(out_a) + base + g * nb + j;
-          if (j < nb) o[0] = cmake(acc.re[s][u][0], acc.im[s][u][0]);
-          if (j + 1 < nb) o[1] = cmake(acc.re[s][u][1], acc.im[s][u][1]);
-        } else {
-          const long long o = base + g * nb + j;
-          if (j < nb) {
-            out_a[o] = 2.0 * acc.re[s][u][0];
-            out_b[o] = 2.0 * acc.im[s][u][0];
-          }
-          if (j + 1 < nb) {
-            out_a[o + 1] = 2.0 * acc.re[s][u][1];
-            out_b[o + 1] = 2.0 * acc.im[s][u][1];
-          }
+    for (int u = 0; u < NCB; ++u) {
+      const int j = j0 + 8 * u + 2 * lc;
+      if (MODE == 0) {
+        cplx* o = reinterpret_cast<cplx*>(out_a) + base + g * nb + j;
+        if (j < nb) o[0] = cmake(cre[u][0], cim[u][0]);
+        if (j + 1 < nb) o[1] = cmake(cre[u][1], cim[u][1]);
+      } else {
+        const long long o = base + g * nb + j;
+        if (j < nb) {
+          out_a[o] = 2.0 * cre[u][0];
+          out_b[o] = 2.0 * cim[u][0];
+        }
+        if (j + 1 < nb) {
+          out_a[o + 1] = 2.0 * cre[u][1];
+          out_b[o + 1] = 2.0 * cim[u][1];
         }
       }
     }
+  }
 }
 
 }  // namespace jrb
