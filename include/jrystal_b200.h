@@ -111,6 +111,24 @@ int jrb_kinetic(jrb_plan* plan, const double* q, double* t_skb, jrb_stream strea
 int jrb_grid_potential(jrb_plan* plan, const double* rho, int32_t xc_id, int32_t kohn_sham,
                        double* energies, double* veff, jrb_stream stream);
 
+/* potential.effective (jrystal/_src/potential.py:203-279) with the reference's own semantics,
+ * real part: `parts` selects the terms (split=True returns them one by one).  Unlike
+ * jrb_grid_potential's veff (= dE/drho), the Hartree term is HALVED and the xc term is eps_xc
+ * unless kohn_sham != 0 (potential.py:67-75, xc.py:247-250) -- the form the reference's
+ * energy_test.py:61-112 identity uses. */
+#define JRB_V_HARTREE 1
+#define JRB_V_EXTERNAL 2
+#define JRB_V_XC 4
+int jrb_potential(jrb_plan* plan, const double* rho, int32_t xc_id, int32_t kohn_sham,
+                  int32_t parts, double* v_out, jrb_stream stream);
+
+/* pw.density_grid_reciprocal (jrystal/_src/pw.py:333-334): rho_hat[s] = fftn(rho[s]), complex. */
+int jrb_density_reciprocal(jrb_plan* plan, const double* rho, double* rho_hat, jrb_stream stream);
+
+/* pw.wave_grid o pw.coeff (jrystal/_src/pw.py:208-211): psi[s,k,b,x,y,z] = ifftn(expand(q)) *
+ * N / sqrt(Omega), dense (API parity / diagnostics; the hot path never materialises it). */
+int jrb_wave_grid(jrb_plan* plan, const double* q, double* psi, jrb_stream stream);
+
 /* Hamiltonian apply on the sphere: hq = 1/2|G+k|^2 q + (sqrt(Omega)/N) fftn(veff * psi)|mask.
  * This is the reverse pass of the energy w.r.t. Q (dE/dQ* = occ * hq) and the forward+reverse
  * pass of hamiltonian.hamiltonian_matrix_trace (jrystal/_src/hamiltonian.py:147-168). */
@@ -120,6 +138,13 @@ int jrb_hpsi(jrb_plan* plan, const double* q, const double* veff, double* hq, jr
  * (jrystal/_src/braket.py:189-206) = dE/d occ[s,k,b]. */
 int jrb_band_expect(jrb_plan* plan, const double* q, const double* hq, double* eps_skb,
                     jrb_stream stream);
+
+/* hamiltonian.hamiltonian_matrix (jrystal/_src/hamiltonian.py:171-240; the reference takes nb
+ * Hessian-vector products through AD, hessian.py:21-55): H[s,k,i,j] = <q_i| hq_j> with
+ * hq = jrb_hpsi(q), one Gram on the FP64 tensor cores; H is Hermitian (upper blocks computed,
+ * lower mirrored).  h: (ns, nk, nb, nb) complex. */
+int jrb_hamiltonian_matrix(jrb_plan* plan, const double* q, const double* hq, double* h,
+                           jrb_stream stream);
 
 /* Dense batched 3-D C2C transform over the last three axes: exact drop-in for the
  * primitives ifftn_sharding / fftn_sharding (jrystal/_src/spmd/fft.py:68-75), numpy

@@ -36,8 +36,12 @@ SYMBOLS = {
   'jrb_density': (ctypes.c_int, [_P, _P, _P, _P, _P]),
   'jrb_kinetic': (ctypes.c_int, [_P, _P, _P, _P]),
   'jrb_grid_potential': (ctypes.c_int, [_P, _P, _I32, _I32, _P, _P, _P]),
+  'jrb_potential': (ctypes.c_int, [_P, _P, _I32, _I32, _I32, _P, _P]),
+  'jrb_density_reciprocal': (ctypes.c_int, [_P, _P, _P, _P]),
+  'jrb_wave_grid': (ctypes.c_int, [_P, _P, _P, _P]),
   'jrb_hpsi': (ctypes.c_int, [_P, _P, _P, _P, _P]),
   'jrb_band_expect': (ctypes.c_int, [_P, _P, _P, _P, _P]),
+  'jrb_hamiltonian_matrix': (ctypes.c_int, [_P, _P, _P, _P, _P]),
   'jrb_fft3d': (ctypes.c_int, [_P, _P, _P, _I32, _I64, _P]),
   'jrb_eval_begin': (ctypes.c_int, [_P, _P, _P, _P, _P, _P, _P]),
   'jrb_eval_finish': (ctypes.c_int, [_P, _P, _P, _P, _I32, _P, _P, _P, _P, _P]),

@@ -1,5 +1,6 @@
 // extern "C" entry points declared in include/jrystal_b200.h: argument checks and
 // composition of the kernels into the reference's operations.
+#include <cmath>
 #include <string>
 
 #include "plan.h"
@@ -85,7 +86,34 @@ extern "C" int jrb_grid_potential(jrb_plan* p, const double* rho, int32_t xc_id,
   int rc = enter(p);
   if (rc) return rc;
   REQUIRE(rho && energies && veff, "null array");
-  return launch_grid_potential(p, rho, xc_id, kohn_sham, energies, veff, S(st));
+  return launch_grid_potential(p, rho, xc_id, kohn_sham, 7, energies, veff, S(st));
+}
+
+extern "C" int jrb_potential(jrb_plan* p, const double* rho, int32_t xc_id, int32_t kohn_sham,
+                             int32_t parts, double* v_out, jrb_stream st) {
+  int rc = enter(p);
+  if (rc) return rc;
+  REQUIRE(rho && v_out, "null array");
+  REQUIRE(parts >= 1 && parts <= 7, "parts must be a non-empty subset of JRB_V_HARTREE|EXTERNAL|XC");
+  return launch_grid_potential(p, rho, xc_id, kohn_sham, parts | 8, nullptr, v_out, S(st));
+}
+
+extern "C" int jrb_density_reciprocal(jrb_plan* p, const double* rho, double* rho_hat,
+                                      jrb_stream st) {
+  int rc = enter(p);
+  if (rc) return rc;
+  REQUIRE(rho && rho_hat, "null array");
+  return launch_density_reciprocal(p, rho, C(rho_hat), S(st));
+}
+
+extern "C" int jrb_wave_grid(jrb_plan* p, const double* q, double* psi, jrb_stream st) {
+  int rc = enter(p);
+  if (rc) return rc;
+  REQUIRE(q && psi, "null array");
+  if ((rc = launch_expand(p, C(q), C(psi), S(st)))) return rc;
+  // ifftn(c) * N / sqrt(Omega)   (jrystal/_src/pw.py:209-210)
+  return launch_fft3d_dense(p, C(psi), C(psi), JRB_FFT_INVERSE, (int64_t)p->ns * p->nk * p->nb,
+                            1.0 / std::sqrt(p->vol), S(st));
 }
 
 extern "C" int jrb_hpsi(jrb_plan* p, const double* q, const double* veff, double* hq,
@@ -103,6 +131,14 @@ extern "C" int jrb_band_expect(jrb_plan* p, const double* q, const double* hq, d
   if (rc) return rc;
   REQUIRE(q && hq && eps, "null array");
   return launch_band_expect(p, C(q), C(hq), eps, S(st));
+}
+
+extern "C" int jrb_hamiltonian_matrix(jrb_plan* p, const double* q, const double* hq, double* h,
+                                      jrb_stream st) {
+  int rc = enter(p);
+  if (rc) return rc;
+  REQUIRE(q && hq && h, "null array");
+  return launch_hamiltonian_matrix(p, C(q), C(hq), C(h), S(st));
 }
 
 extern "C" int jrb_fft3d(jrb_plan* p, const double* in, double* out, int32_t direction,
@@ -144,7 +180,7 @@ extern "C" int jrb_eval_finish(jrb_plan* p, const double* occ, const double* rho
   REQUIRE(occ && rho && e_kin && energies && g_re && g_im, "null array");
   double* grid_e = p->d_scal;            // E_H, E_ext, E_xc
   double* veff = p->d_veff;
-  if ((rc = launch_grid_potential(p, rho, xc_id, 0, grid_e, veff, S(st)))) return rc;
+  if ((rc = launch_grid_potential(p, rho, xc_id, 0, 7, grid_e, veff, S(st)))) return rc;
   if ((rc = launch_hpsi(p, p->d_q, veff, p->d_hq, S(st)))) return rc;
   if (g_occ) {
     if ((rc = launch_band_expect(p, p->d_q, p->d_hq, g_occ, S(st)))) return rc;

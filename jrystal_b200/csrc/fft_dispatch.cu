@@ -2,6 +2,9 @@
 // and the dense 3-pass transform behind jrb_fft3d.
 #include <algorithm>
 
+#include <cstdlib>
+
+#include "fft_fused.cuh"
 #include "fft_passes.cuh"
 #include "plan.h"
 
@@ -29,6 +32,77 @@ static int run_dense(int n, const DenseArgs& a, int dir, long long batch, cudaSt
     return JRB_EUNSUPPORTED;
   }
   return rc;
+}
+
+int fused_smem_group0(int n, int nxo, int ncol);
+int fused_smem_group1(int n, int nxo, int ncol);
+int fused_smem_group2(int n, int nxo, int ncol);
+int fused_threads_group0(int n);
+int fused_threads_group1(int n);
+int fused_threads_group2(int n);
+
+int fused_smem_need(int n, int nxo, int ncol) {
+  int r = fused_smem_group0(n, nxo, ncol);
+  if (r < 0) r = fused_smem_group1(n, nxo, ncol);
+  if (r < 0) r = fused_smem_group2(n, nxo, ncol);
+  return r;
+}
+
+// The fused y+x kernels need nx == ny, a compiled size and slabs that fit shared memory.
+bool fused_available(int nx, int ny, int nxo, int ncol) {
+  if (const char* env = std::getenv("JRB_NO_FUSE"))
+    if (std::atoi(env) != 0) return false;
+  if (nx != ny) return false;
+  const int need = fused_smem_need(nx, nxo, ncol);
+  return need > 0 && need <= 200 * 1024;
+}
+
+// persistent CTAs of the fused kernels: one per resident slot
+int fused_cta_count(int n, int nxo, int ncol) {
+  int nt = fused_threads_group0(n);
+  if (nt < 0) nt = fused_threads_group1(n);
+  if (nt < 0) nt = fused_threads_group2(n);
+  const int smem = fused_smem_need(n, nxo, ncol);
+  int per_sm = nt <= 256 ? 2 : 1;
+  if (2 * (smem + 1024) > 227 * 1024) per_sm = 1;
+  if (const char* env = std::getenv("JRB_FUSED_CTAS_PER_SM")) per_sm = std::max(1, std::atoi(env));
+  return 148 * per_sm;
+}
+
+static int run_fused(int kind, int n, const FusedArgs& a, int ctas, cudaStream_t st) {
+  int rc = fused_group0(kind, n, a, ctas, st);
+  if (rc == 1) rc = fused_group1(kind, n, a, ctas, st);
+  if (rc == 1) rc = fused_group2(kind, n, a, ctas, st);
+  if (rc == 1) {
+    set_error("no compiled fused pass for axis length " + std::to_string(n));
+    return JRB_EUNSUPPORTED;
+  }
+  return rc;
+}
+
+// segments (distinct z planes) one persistent CTA can touch for a batch of `ngroups`
+static int fused_segmax(const jrb_plan* p, int ngroups) {
+  const long long W = (long long)p->nz * ngroups;
+  const long long items = (W + p->fused_ctas - 1) / p->fused_ctas;
+  return (int)((items - 1) / ngroups + 2);
+}
+
+static FusedArgs fused_args(jrb_plan* p, const PassArgs& a) {
+  FusedArgs f{};
+  f.m = a.m;
+  f.wa = a.wa;
+  f.tw = p->d_tw_x;
+  f.focc = a.focc;
+  f.veff = a.veff;
+  f.rho_part = p->d_rho_part;
+  f.seg_z = p->d_seg_z;
+  f.segmax = fused_segmax(p, a.ngroups);
+  f.nb = a.nb;
+  f.ngpk = a.ngpk;
+  f.g0 = a.g0;
+  f.ngroups = a.ngroups;
+  f.vscale = a.vscale;
+  return f;
 }
 
 static PassArgs base_args(jrb_plan* p) {
@@ -60,6 +134,15 @@ int launch_density(jrb_plan* p, const cplx* q, const double* occ, double* rho, c
       a.rho = rho + (size_t)s * p->ngrid;
       a.tw = p->d_tw_z;
       if ((rc = run_pass(PASS_Z_INV_SCATTER, p->nz, a, st))) return rc;
+      if (p->fused) {
+        FusedArgs f = fused_args(p, a);
+        if ((rc = run_fused(0, p->nx, f, p->fused_ctas, st))) return rc;
+        dim3 grid((p->nx * p->ny + 31) / 32, p->nz), block(32, 8);
+        k_rho_reduce<<<grid, block, 0, st>>>(p->d_rho_part, p->d_seg_z, p->fused_ctas * f.segmax,
+                                             p->nx * p->ny, p->nz, a.rho);
+        JRB_CHECK_LAUNCH("k_rho_reduce");
+        continue;
+      }
       a.tw = p->d_tw_y;
       if ((rc = run_pass(PASS_Y_INV, p->ny, a, st))) return rc;
       a.tw = p->d_tw_x;
@@ -83,12 +166,17 @@ int launch_hpsi(jrb_plan* p, const cplx* q, const double* veff, cplx* hq, cudaSt
       a.veff = veff + (size_t)s * p->ngrid;
       a.tw = p->d_tw_z;
       if ((rc = run_pass(PASS_Z_INV_SCATTER, p->nz, a, st))) return rc;
-      a.tw = p->d_tw_y;
-      if ((rc = run_pass(PASS_Y_INV, p->ny, a, st))) return rc;
-      a.tw = p->d_tw_x;
-      if ((rc = run_pass(PASS_X_VMUL, p->nx, a, st))) return rc;
-      a.tw = p->d_tw_y;
-      if ((rc = run_pass(PASS_Y_FWD, p->ny, a, st))) return rc;
+      if (p->fused) {
+        FusedArgs f = fused_args(p, a);
+        if ((rc = run_fused(1, p->nx, f, p->fused_ctas, st))) return rc;
+      } else {
+        a.tw = p->d_tw_y;
+        if ((rc = run_pass(PASS_Y_INV, p->ny, a, st))) return rc;
+        a.tw = p->d_tw_x;
+        if ((rc = run_pass(PASS_X_VMUL, p->nx, a, st))) return rc;
+        a.tw = p->d_tw_y;
+        if ((rc = run_pass(PASS_Y_FWD, p->ny, a, st))) return rc;
+      }
       a.tw = p->d_tw_z;
       if ((rc = run_pass(PASS_Z_FWD_GATHER, p->nz, a, st))) return rc;
     }

@@ -1,0 +1,525 @@
+// Fused y+x pencil passes on z-planes (hand-written sm_100a kernels).
+//
+// After the z pass the only global intermediate is A[group][z][col][NB] (occupied (x,y)
+// columns, 2-5 % of the box).  Work item = (z-plane, band group); the CTAs are persistent and
+// split the z-major item list evenly (grid = resident CTA slots, so every SM is busy to the
+// end).  Band by band a CTA runs
+//   stage  : cp.async (LDGSTS) of the NEXT band's plane columns into a shared-memory staging
+//            buffer while the current band is being transformed (no exposed global latency)
+//   y stage: y-transforms the occupied x planes into a shared-memory slab Y[xo][y]
+//   x stage: zero-pads the occupied x entries to nx, x-transforms every y line and
+//     k_yx_density : accumulates f |psi|^2 in registers (a thread owns the same (x, y) points
+//                    for every band of a plane) -> one partial-plane write per (CTA, z segment),
+//                    summed in a fixed order by k_rho_reduce (deterministic, no atomics);
+//     k_yx_vmul    : multiplies by v_eff(r) / N, transforms back along x in registers, keeps the
+//                    occupied x planes in Y, then y-transforms back and scatters into A in place.
+// psi(r), v psi(r) and the half-transformed slab never reach global memory.  Per 64^3 band-plane
+// the kernel needs ~1.7 k cycles of the SM's FP64 pipe and ~1.8 k cycles of its shared-memory
+// pipe (every element crosses the Stockham exchange once per line), so it is bound by those two
+// on-chip pipes, not by HBM.
+//
+// Thread layout: t = lane + 8 (tj + TPL slot); the 8 "lanes" are 8 ADJACENT LINES of the
+// dimension that is not being transformed (x planes in the y stage, y lines in the x stage), so
+// every shared-memory access of a quarter warp is 8 consecutive complex numbers (conflict
+// free).  Y is double buffered: the x stage of band b and the y stage of band b+1 run without
+// a CTA-wide barrier in between (only the 2-warp slot barriers of the exchange buffers).
+#pragma once
+#include "fft_passes.cuh"
+
+namespace jrb {
+
+struct FusedArgs {
+  SphereMaps m;
+  cplx* wa;            // A[group][z][col][NB]
+  const cplx* tw;      // exp(-2 pi i t / n), n = nx = ny
+  const double* focc;  // [groups][NB] occupation / Omega
+  const double* veff;  // [nx*ny*nz] of the current spin
+  double* rho_part;    // [gridDim.x * segmax][nx*ny] partial density planes of this launch
+  int* seg_z;          // [gridDim.x * segmax] z of each partial plane, -1 = unused
+  int segmax;
+  int nb, ngpk;
+  int g0, ngroups;     // first global group id, number of groups in the batch
+  double vscale;
+};
+
+constexpr int fused_slots(int tpl) {
+  int s = 256 / (NB * tpl);
+  if (s < 1) s = 1;
+  while ((NB * tpl * s) % 32 != 0) ++s;
+  return s;
+}
+
+template <int N>
+struct FCfg {
+  static constexpr int TPL = LinePlan<N>::tpl;
+  static constexpr int SLOT_THREADS = NB * TPL;
+  static constexpr int SLOTS = fused_slots(TPL);
+  static constexpr int NT = SLOT_THREADS * SLOTS;
+  static constexpr bool WARP_SLOTS = SLOT_THREADS % 32 == 0;  // slot = whole warps -> named barriers
+  static constexpr int NG = (N + NB - 1) / NB;         // x-stage line groups (8 y lines each)
+  static constexpr int NR = (NG + SLOTS - 1) / SLOTS;  // x-stage rounds
+  static constexpr int SX = N + ((N % 8 == 1) ? 0 : (9 - N % 8) % 8);  // Y row stride == 1 (mod 8)
+  static constexpr int EXCH = SLOTS * N * NB;          // exchange buffers (complex)
+  // shared memory (complex numbers): 2 Y slabs, exchange buffers, 2 staging buffers
+  static JRB_HD int ybuf_elems(int nxo) { return nxo * SX; }
+  static JRB_HD int stage_elems(int ncol) { return (ncol + 7) / 8 * 8; }
+  static JRB_HD int smem_bytes(int nxo, int ncol) {
+    return (2 * ybuf_elems(nxo) + EXCH + 2 * stage_elems(ncol)) * (int)sizeof(cplx);
+  }
+};
+
+template <int N>
+__device__ __forceinline__ void slot_barrier(int slot) {
+  if constexpr (FCfg<N>::WARP_SLOTS && FCfg<N>::SLOTS > 1 && FCfg<N>::SLOTS < 15) {
+    asm volatile("bar.sync %0, %1;" ::"r"(slot + 1), "n"(FCfg<N>::SLOT_THREADS) : "memory");
+  } else {
+    __syncthreads();
+  }
+}
+
+__device__ __forceinline__ void fused_cp_async16(void* smem_dst, const void* gsrc) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(gsrc));
+}
+__device__ __forceinline__ void fused_cp_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+__device__ __forceinline__ void fused_cp_wait_all() {
+  asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+}
+
+// Flat iterator over the (item, band) pairs of a CTA: item w = z * ngroups + gl.
+struct BandIter {
+  long long w, w_end;
+  int band, nband;
+  int z, gl;
+  __device__ __forceinline__ void set_item(const FusedArgs& a) {
+    z = (int)(w / a.ngroups);
+    gl = (int)(w % a.ngroups);
+    const int b0 = ((a.g0 + gl) % a.ngpk) * NB;
+    nband = min(NB, a.nb - b0);
+    band = 0;
+  }
+  __device__ __forceinline__ bool valid() const { return w < w_end; }
+  __device__ __forceinline__ void next(const FusedArgs& a) {
+    if (++band >= nband) {
+      ++w;
+      if (w < w_end) set_item(a);
+    }
+  }
+  __device__ __forceinline__ cplx* plane(const FusedArgs& a) const {
+    return a.wa + ((long long)gl * a.m.nz + z) * a.m.ncol * NB + band;
+  }
+};
+
+// stage the plane columns of one band: stage[col] = A[gl][z][col][band]
+template <int NT>
+__device__ __forceinline__ void fused_stage(const FusedArgs& a, const BandIter& it, cplx* stage) {
+  if (it.valid()) {
+    const cplx* src = it.plane(a);
+    for (int c = threadIdx.x; c < a.m.ncol; c += NT)
+      fused_cp_async16(stage + c, src + (long long)c * NB);
+  }
+  fused_cp_commit();
+}
+
+// y stage, inverse: staged columns of one band-plane -> Y[xo][y].  All threads call it.
+template <int N>
+__device__ __forceinline__ void fused_y_inverse(
+  const FusedArgs& a, const cplx* stage, cplx* ybuf, cplx* ex,
+  const cplx (&tw)[LineFFT<N, +1>::CB][LineFFT<N, +1>::NTW], int lane, int tj, int slot) {
+  using F = LineFFT<N, +1>;
+  using C = FCfg<N>;
+  const int ngx = (a.m.nxo + NB - 1) / NB;
+  for (int grp = slot; grp < (ngx + C::SLOTS - 1) / C::SLOTS * C::SLOTS; grp += C::SLOTS) {
+    const int xo = grp * NB + lane;
+    const bool ok = grp < ngx && xo < a.m.nxo;
+    const int32_t* yc = a.m.ycol + (long long)(ok ? xo : 0) * N;
+    cplx va[F::CA][F::RA];
+#pragma unroll
+    for (int i = 0; i < F::CA; ++i) {
+#pragma unroll
+      for (int m = 0; m < F::RA; ++m) {
+        cplx v = czero();
+        if (F::activeA(i, tj) && ok) {
+          const int col = yc[F::idxA(i, m, tj)];
+          if (col >= 0) v = stage[col];
+        }
+        va[i][m] = v;
+      }
+    }
+    F::template stageA_store<NB>(va, ex, tj);
+    slot_barrier<N>(slot);
+    cplx vb[F::CB][F::RB];
+    F::template stageB_load<NB>(vb, ex, tw, tj);
+    if (ok) {
+      cplx* out = ybuf + (long long)xo * C::SX;
+#pragma unroll
+      for (int i = 0; i < F::CB; ++i) {
+        if (F::activeB(i, tj)) {
+#pragma unroll
+          for (int m = 0; m < F::RB; ++m) out[F::idxB(i, m, tj)] = vb[i][m];
+        }
+      }
+    }
+    slot_barrier<N>(slot);
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// grid: (G) persistent CTAs; dynamic smem: FCfg<N>::smem_bytes(nxo, ncol)
+template <int N>
+__global__ void __launch_bounds__(FCfg<N>::NT, (FCfg<N>::NT <= 256 ? 2 : 1))
+k_yx_density(FusedArgs a) {
+  using F = LineFFT<N, +1>;
+  using C = FCfg<N>;
+  extern __shared__ __align__(16) unsigned char smem_raw_[];
+  cplx* ybuf0 = reinterpret_cast<cplx*>(smem_raw_);
+  const int ysz = C::ybuf_elems(a.m.nxo);
+  cplx* exbase = ybuf0 + 2 * ysz;
+  cplx* stage0 = exbase + C::EXCH;
+  const int ssz = C::stage_elems(a.m.ncol);
+  const int t = threadIdx.x;
+  const int lane = t % NB;
+  const int tj = (t / NB) % C::TPL;
+  const int slot = t / C::SLOT_THREADS;
+  cplx* ex = exbase + (size_t)slot * N * NB + lane;
+  cplx tw[F::CB][F::NTW];
+  F::load_twiddles(tw, a.tw, tj);
+
+  // x-stage inputs of this thread: row of Y (or -1) for each strided x index
+  int yrow[F::CA][F::RA];
+#pragma unroll
+  for (int i = 0; i < F::CA; ++i)
+#pragma unroll
+    for (int m = 0; m < F::RA; ++m) {
+      int r = -1;
+      if (F::activeA(i, tj)) {
+        const int xo = a.m.xmap[F::idxA(i, m, tj)];
+        if (xo >= 0) r = xo * C::SX;
+      }
+      yrow[i][m] = r;
+    }
+  double acc[C::NR][F::CB][F::RB];
+#pragma unroll
+  for (int r = 0; r < C::NR; ++r)
+#pragma unroll
+    for (int i = 0; i < F::CB; ++i)
+#pragma unroll
+      for (int m = 0; m < F::RB; ++m) acc[r][i][m] = 0.0;
+
+  const long long W = (long long)a.m.nz * a.ngroups;
+  const int c = blockIdx.x, G = gridDim.x;
+  BandIter cur, nxt;
+  cur.w = c * W / G;
+  cur.w_end = (c + 1) * W / G;
+  int seg = 0;
+  auto flush = [&](int z) {
+    double* out = a.rho_part + ((long long)c * a.segmax + seg) * N * N;
+#pragma unroll
+    for (int r = 0; r < C::NR; ++r) {
+      const int y = (r * C::SLOTS + slot) * NB + lane;
+#pragma unroll
+      for (int i = 0; i < F::CB; ++i)
+#pragma unroll
+        for (int m = 0; m < F::RB; ++m) {
+          if (F::activeB(i, tj) && y < N) out[(long long)F::idxB(i, m, tj) * N + y] = acc[r][i][m];
+          acc[r][i][m] = 0.0;
+        }
+    }
+    if (t == 0) a.seg_z[c * a.segmax + seg] = z;
+    ++seg;
+  };
+
+  if (cur.valid()) {
+    cur.set_item(a);
+    nxt = cur;
+    // prologue: stage band 0, run its y stage, stage band 1
+    fused_stage<C::NT>(a, cur, stage0);
+    fused_cp_wait_all();
+    __syncthreads();
+    nxt.next(a);
+    fused_stage<C::NT>(a, nxt, stage0 + ssz);
+    fused_y_inverse<N>(a, stage0, ybuf0, ex, tw, lane, tj, slot);
+    int par = 0;  // parity of the current band: it lives in Y[par]
+    int cur_z = cur.z;
+    while (cur.valid()) {
+      // Y[par] complete (y stage of the current band by every slot); staged data of the next
+      // band landed and visible; everybody is done with Y[par ^ 1] and stage[par]
+      fused_cp_wait_all();
+      __syncthreads();
+      // nxt = band b+1 (staged in stage[par ^ 1]); prefetch band b+2 into stage[par]
+      BandIter nn = nxt;
+      if (nn.valid()) nn.next(a);
+      fused_stage<C::NT>(a, nn, stage0 + par * ssz);
+      if (cur.z != cur_z) {
+        flush(cur_z);
+        cur_z = cur.z;
+      }
+      const double fw = a.focc[(long long)(a.g0 + cur.gl) * NB + cur.band];
+      const cplx* ybuf = ybuf0 + par * ysz;
+#pragma unroll
+      for (int r = 0; r < C::NR; ++r) {
+        const int y = (r * C::SLOTS + slot) * NB + lane;
+        const bool ok = y < N;
+        cplx va[F::CA][F::RA];
+#pragma unroll
+        for (int i = 0; i < F::CA; ++i)
+#pragma unroll
+          for (int m = 0; m < F::RA; ++m)
+            va[i][m] = (yrow[i][m] >= 0 && ok) ? ybuf[yrow[i][m] + y] : czero();
+        F::template stageA_store<NB>(va, ex, tj);
+        slot_barrier<N>(slot);
+        cplx vb[F::CB][F::RB];
+        F::template stageB_load<NB>(vb, ex, tw, tj);
+#pragma unroll
+        for (int i = 0; i < F::CB; ++i)
+#pragma unroll
+          for (int m = 0; m < F::RB; ++m)
+            if (F::activeB(i, tj))
+              acc[r][i][m] += fw * (vb[i][m].x * vb[i][m].x + vb[i][m].y * vb[i][m].y);
+        slot_barrier<N>(slot);
+      }
+      // y stage of the next band into the other Y buffer
+      if (nxt.valid())
+        fused_y_inverse<N>(a, stage0 + (par ^ 1) * ssz, ybuf0 + (par ^ 1) * ysz, ex, tw, lane, tj,
+                           slot);
+      cur = nxt;
+      nxt = nn;
+      par ^= 1;
+    }
+    fused_cp_wait_all();
+    flush(cur_z);
+  }
+  if (t == 0)
+    for (int s = seg; s < a.segmax; ++s) a.seg_z[c * a.segmax + s] = -1;
+}
+
+// rho[x][y][z] += sum of the partial planes tagged z, in slot order (deterministic)
+// grid: (ceil(nx*ny / 32), nz), block 32 x 8: thread (tx, ty) sums slots ty, ty+8, ...
+static __global__ void __launch_bounds__(256)
+k_rho_reduce(const double* __restrict__ part, const int* __restrict__ seg_z, int nslots, int nxy,
+             int nz, double* __restrict__ rho) {
+  __shared__ double sh[8][33];
+  const int xy = blockIdx.x * 32 + threadIdx.x;
+  const int z = blockIdx.y;
+  double s = 0.0;
+  if (xy < nxy)
+    for (int k = threadIdx.y; k < nslots; k += 8)
+      if (seg_z[k] == z) s += part[(long long)k * nxy + xy];
+  sh[threadIdx.y][threadIdx.x] = s;
+  __syncthreads();
+  if (threadIdx.y == 0 && xy < nxy) {
+    double r = 0.0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) r += sh[j][threadIdx.x];
+    rho[(long long)xy * nz + z] += r;
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// Hamiltonian-apply middle: A (plane z) -> y inverse -> x inverse -> * v_eff / N -> x forward
+// -> y forward -> A (in place).   grid: (G) persistent CTAs; dynamic smem as above.
+template <int N>
+__global__ void __launch_bounds__(FCfg<N>::NT, (FCfg<N>::NT <= 256 ? 2 : 1))
+k_yx_vmul(FusedArgs a) {
+  using FI = LineFFT<N, +1>;
+  using FF = LineFFT<N, -1>;
+  using C = FCfg<N>;
+  static_assert(FI::CB == FF::CA && FI::RB == FF::RA, "register chaining contract");
+  extern __shared__ __align__(16) unsigned char smem_raw_[];
+  cplx* ybuf0 = reinterpret_cast<cplx*>(smem_raw_);
+  const int ysz = C::ybuf_elems(a.m.nxo);
+  cplx* exbase = ybuf0 + 2 * ysz;
+  cplx* stage0 = exbase + C::EXCH;
+  const int ssz = C::stage_elems(a.m.ncol);
+  const int t = threadIdx.x;
+  const int lane = t % NB;
+  const int tj = (t / NB) % C::TPL;
+  const int slot = t / C::SLOT_THREADS;
+  cplx* ex = exbase + (size_t)slot * N * NB + lane;
+  const long long nyz = (long long)N * a.m.nz;
+  cplx twi[FI::CB][FI::NTW];
+  cplx twf[FF::CB][FF::NTW];
+  FI::load_twiddles(twi, a.tw, tj);
+  FF::load_twiddles(twf, a.tw, tj);
+
+  int yrow[FI::CA][FI::RA];
+#pragma unroll
+  for (int i = 0; i < FI::CA; ++i)
+#pragma unroll
+    for (int m = 0; m < FI::RA; ++m) {
+      int r = -1;
+      if (FI::activeA(i, tj)) {
+        const int xo = a.m.xmap[FI::idxA(i, m, tj)];
+        if (xo >= 0) r = xo * C::SX;
+      }
+      yrow[i][m] = r;
+    }
+  int orow[FF::CB][FF::RB];
+#pragma unroll
+  for (int i = 0; i < FF::CB; ++i)
+#pragma unroll
+    for (int m = 0; m < FF::RB; ++m) {
+      int r = -1;
+      if (FF::activeB(i, tj)) {
+        const int xo = a.m.xmap[FF::idxB(i, m, tj)];
+        if (xo >= 0) r = xo * C::SX;
+      }
+      orow[i][m] = r;
+    }
+  // v_eff(x, y, z) / N at the points this thread owns in the x stage (reloaded when z changes)
+  double vv[C::NR][FI::CB][FI::RB];
+  auto load_v = [&](int z) {
+#pragma unroll
+    for (int r = 0; r < C::NR; ++r) {
+      const int y = (r * C::SLOTS + slot) * NB + lane;
+#pragma unroll
+      for (int i = 0; i < FI::CB; ++i)
+#pragma unroll
+        for (int m = 0; m < FI::RB; ++m) {
+          double v = 0.0;
+          if (FI::activeB(i, tj) && y < N)
+            v = a.veff[(long long)FI::idxB(i, m, tj) * nyz + (long long)y * a.m.nz + z] * a.vscale;
+          vv[r][i][m] = v;
+        }
+    }
+  };
+
+  const int ngx = (a.m.nxo + NB - 1) / NB;
+  const long long W = (long long)a.m.nz * a.ngroups;
+  const int c = blockIdx.x, G = gridDim.x;
+  BandIter cur, nxt;
+  cur.w = c * W / G;
+  cur.w_end = (c + 1) * W / G;
+  if (!cur.valid()) return;
+  cur.set_item(a);
+  nxt = cur;
+  fused_stage<C::NT>(a, cur, stage0);
+  fused_cp_wait_all();
+  __syncthreads();
+  nxt.next(a);
+  fused_stage<C::NT>(a, nxt, stage0 + ssz);
+  fused_y_inverse<N>(a, stage0, ybuf0, ex, twi, lane, tj, slot);
+  int par = 0;
+  int cur_z = cur.z;
+  load_v(cur_z);
+  while (cur.valid()) {
+    fused_cp_wait_all();
+    __syncthreads();
+    BandIter nn = nxt;
+    if (nn.valid()) nn.next(a);
+    fused_stage<C::NT>(a, nn, stage0 + par * ssz);
+    if (cur.z != cur_z) {
+      cur_z = cur.z;
+      load_v(cur_z);
+    }
+    cplx* ybuf = ybuf0 + par * ysz;
+    // x stage: inverse, multiply, forward; occupied x planes written back into Y
+#pragma unroll
+    for (int r = 0; r < C::NR; ++r) {
+      const int y = (r * C::SLOTS + slot) * NB + lane;
+      const bool ok = y < N;
+      cplx va[FI::CA][FI::RA];
+#pragma unroll
+      for (int i = 0; i < FI::CA; ++i)
+#pragma unroll
+        for (int m = 0; m < FI::RA; ++m)
+          va[i][m] = (yrow[i][m] >= 0 && ok) ? ybuf[yrow[i][m] + y] : czero();
+      FI::template stageA_store<NB>(va, ex, tj);
+      slot_barrier<N>(slot);
+      cplx vb[FI::CB][FI::RB];
+      FI::template stageB_load<NB>(vb, ex, twi, tj);
+#pragma unroll
+      for (int i = 0; i < FI::CB; ++i)
+#pragma unroll
+        for (int m = 0; m < FI::RB; ++m) vb[i][m] = cscale(vb[i][m], vv[r][i][m]);
+      slot_barrier<N>(slot);
+      FF::template stageA_store<NB>(vb, ex, tj);
+      slot_barrier<N>(slot);
+      cplx vc[FF::CB][FF::RB];
+      FF::template stageB_load<NB>(vc, ex, twf, tj);
+      if (ok) {
+#pragma unroll
+        for (int i = 0; i < FF::CB; ++i)
+#pragma unroll
+          for (int m = 0; m < FF::RB; ++m)
+            if (orow[i][m] >= 0) ybuf[orow[i][m] + y] = vc[i][m];
+      }
+      slot_barrier<N>(slot);
+    }
+    __syncthreads();
+    // y stage, forward: Y -> occupied columns of A (global, in place)
+    cplx* dst = cur.plane(a);
+    for (int grp = slot; grp < (ngx + C::SLOTS - 1) / C::SLOTS * C::SLOTS; grp += C::SLOTS) {
+      const int xo = grp * NB + lane;
+      const bool ok = grp < ngx && xo < a.m.nxo;
+      const cplx* in = ybuf + (long long)(ok ? xo : 0) * C::SX;
+      cplx va[FF::CA][FF::RA];
+#pragma unroll
+      for (int i = 0; i < FF::CA; ++i)
+#pragma unroll
+        for (int m = 0; m < FF::RA; ++m)
+          va[i][m] = (FF::activeA(i, tj) && ok) ? in[FF::idxA(i, m, tj)] : czero();
+      FF::template stageA_store<NB>(va, ex, tj);
+      slot_barrier<N>(slot);
+      cplx vb[FF::CB][FF::RB];
+      FF::template stageB_load<NB>(vb, ex, twf, tj);
+      if (ok) {
+        const int32_t* yc = a.m.ycol + (long long)xo * N;
+#pragma unroll
+        for (int i = 0; i < FF::CB; ++i) {
+          if (FF::activeB(i, tj)) {
+#pragma unroll
+            for (int m = 0; m < FF::RB; ++m) {
+              const int col = yc[FF::idxB(i, m, tj)];
+              if (col >= 0) dst[(long long)col * NB] = vb[i][m];
+            }
+          }
+        }
+      }
+      slot_barrier<N>(slot);
+    }
+    if (nxt.valid())
+      fused_y_inverse<N>(a, stage0 + (par ^ 1) * ssz, ybuf0 + (par ^ 1) * ysz, ex, twi, lane, tj,
+                         slot);
+    cur = nxt;
+    nxt = nn;
+    par ^= 1;
+  }
+  fused_cp_wait_all();
+}
+
+// ---------------------------------------------------------------------------------------
+template <int N>
+int launch_fused(int kind, const FusedArgs& a, int ctas, cudaStream_t st) {
+  using C = FCfg<N>;
+  const int smem = C::smem_bytes(a.m.nxo, a.m.ncol);
+  if (kind == 0) {
+    static int once = set_smem_attr(k_yx_density<N>, 200 * 1024);
+    if (once) return once;
+    k_yx_density<N><<<ctas, C::NT, smem, st>>>(a);
+  } else {
+    static int once = set_smem_attr(k_yx_vmul<N>, 200 * 1024);
+    if (once) return once;
+    k_yx_vmul<N><<<ctas, C::NT, smem, st>>>(a);
+  }
+  JRB_CHECK_LAUNCH("fused yx pass launch");
+  return 0;
+}
+
+template <int N>
+int fused_smem_bytes(int nxo, int ncol) {
+  return FCfg<N>::smem_bytes(nxo, ncol);
+}
+template <int N>
+int fused_threads() {
+  return FCfg<N>::NT;
+}
+
+// per-translation-unit dispatch (fft_fused_g*.cu); return 1 if n is not in the group
+int fused_group0(int kind, int n, const FusedArgs& a, int ctas, cudaStream_t st);
+int fused_group1(int kind, int n, const FusedArgs& a, int ctas, cudaStream_t st);
+int fused_group2(int kind, int n, const FusedArgs& a, int ctas, cudaStream_t st);
+// shared memory the fused kernels need for axis length n (or -1 if not compiled)
+int fused_smem_need(int n, int nxo, int ncol);
+
+}  // namespace jrb

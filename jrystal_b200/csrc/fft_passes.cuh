@@ -15,7 +15,9 @@
 // transpose into the last forward pass.
 //
 // Work-space layouts (NB = 8 band lanes innermost -> every access is a 128-byte line):
-//   A[group][col][z][NB]          col = occupied (x, y) column
+//   A[group][z][col][NB]          col = occupied (x, y) column (z-major: a z-plane of one
+//                                 group is contiguous, which is what the fused y+x kernels of
+//                                 fft_fused.cuh read)
 //   B[group][xo][y][z][NB]        xo  = occupied x plane
 #pragma once
 #include <cuda_runtime.h>
@@ -127,12 +129,13 @@ __global__ void __launch_bounds__(Cfg<NZ>::NT) k_z_inv_scatter(PassArgs a) {
   cplx vb[F::CB][F::RB];
   F::template stageB_load<NB>(vb, sm, tw, tj);
   if (line_ok) {
-    cplx* out = a.wa + (((long long)gl * a.m.ncol + col) * NZ) * NB + b;
+    cplx* out = a.wa + ((long long)gl * NZ * a.m.ncol + col) * NB + b;
+    const long long zs = (long long)a.m.ncol * NB;
 #pragma unroll
     for (int i = 0; i < F::CB; ++i) {
       if (F::activeB(i, tj)) {
 #pragma unroll
-        for (int m = 0; m < F::RB; ++m) out[(long long)F::idxB(i, m, tj) * NB] = vb[i][m];
+        for (int m = 0; m < F::RB; ++m) out[F::idxB(i, m, tj) * zs] = vb[i][m];
       }
     }
   }
@@ -156,7 +159,7 @@ __global__ void __launch_bounds__(Cfg<NY>::NT) k_y_inv(PassArgs a) {
   cplx tw[F::CB][F::NTW];
   F::load_twiddles(tw, a.tw, tj);
 
-  const cplx* in = a.wa + ((long long)gl * a.m.ncol * nz + z) * NB + b;
+  const cplx* in = a.wa + (((long long)gl * nz + z) * a.m.ncol) * NB + b;
   const int32_t* yc = a.m.ycol + (long long)xo * NY;
   cplx va[F::CA][F::RA];
 #pragma unroll
@@ -166,7 +169,7 @@ __global__ void __launch_bounds__(Cfg<NY>::NT) k_y_inv(PassArgs a) {
       cplx v = czero();
       if (F::activeA(i, tj) && line_ok) {
         const int col = yc[F::idxA(i, m, tj)];
-        if (col >= 0) v = in[(long long)col * nz * NB];
+        if (col >= 0) v = in[(long long)col * NB];
       }
       va[i][m] = v;
     }
@@ -384,7 +387,7 @@ __global__ void __launch_bounds__(Cfg<NY>::NT) k_y_fwd(PassArgs a) {
   cplx vb[F::CB][F::RB];
   F::template stageB_load<NB>(vb, sm, tw, tj);
   if (line_ok) {
-    cplx* out = a.wa + ((long long)gl * a.m.ncol * nz + z) * NB + b;
+    cplx* out = a.wa + (((long long)gl * nz + z) * a.m.ncol) * NB + b;
     const int32_t* yc = a.m.ycol + (long long)xo * NY;
 #pragma unroll
     for (int i = 0; i < F::CB; ++i) {
@@ -392,7 +395,7 @@ __global__ void __launch_bounds__(Cfg<NY>::NT) k_y_fwd(PassArgs a) {
 #pragma unroll
         for (int m = 0; m < F::RB; ++m) {
           const int col = yc[F::idxB(i, m, tj)];
-          if (col >= 0) out[(long long)col * nz * NB] = vb[i][m];
+          if (col >= 0) out[(long long)col * NB] = vb[i][m];
         }
       }
     }
@@ -420,14 +423,15 @@ __global__ void __launch_bounds__(Cfg<NZ>::NT) k_z_fwd_gather(PassArgs a) {
   cplx tw[F::CB][F::NTW];
   F::load_twiddles(tw, a.tw, tj);
 
-  const cplx* in = a.wa + (((long long)gl * a.m.ncol + (line_ok ? col : 0)) * NZ) * NB + b;
+  const cplx* in = a.wa + ((long long)gl * NZ * a.m.ncol + (line_ok ? col : 0)) * NB + b;
+  const long long zs = (long long)a.m.ncol * NB;
   cplx va[F::CA][F::RA];
 #pragma unroll
   for (int i = 0; i < F::CA; ++i) {
 #pragma unroll
     for (int m = 0; m < F::RA; ++m) {
       cplx v = czero();
-      if (F::activeA(i, tj) && line_ok) v = in[(long long)F::idxA(i, m, tj) * NB];
+      if (F::activeA(i, tj) && line_ok) v = in[F::idxA(i, m, tj) * zs];
       va[i][m] = v;
     }
   }

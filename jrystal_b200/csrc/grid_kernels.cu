@@ -128,7 +128,11 @@ __global__ void k_rho_to_complex(const double* __restrict__ rho, int ns, long lo
 // n(G) -> E_H, E_ext partial sums and v_H(G) + V_ext(G) in place.
 __global__ void __launch_bounds__(RED_THREADS)
 k_hartree_ext(GridGeom g, cplx* __restrict__ grid, const cplx* __restrict__ vext, int kohn_sham,
-              double* __restrict__ partials) {
+              int parts, double* __restrict__ partials) {
+  // potential written back: parts bit 0 = Hartree, bit 1 = external; bit 3 = the reference's
+  // potential.effective semantics (Hartree potential halved unless kohn_sham, potential.py:67-75)
+  const double hs = (parts & 1) ? (((parts & 8) && !kohn_sham) ? 0.5 : 1.0) : 0.0;
+  const double es = (parts & 2) ? 1.0 : 0.0;
   double acc[2] = {0.0, 0.0};
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < g.n;
        i += (long long)gridDim.x * blockDim.x) {
@@ -145,7 +149,7 @@ k_hartree_ext(GridGeom g, cplx* __restrict__ grid, const cplx* __restrict__ vext
     // Re conj(v) n
     acc[0] += vh.x * nG.x + vh.y * nG.y;
     acc[1] += ve.x * nG.x + ve.y * nG.y;
-    grid[i] = cmake(vh.x + ve.x, vh.y + ve.y);
+    grid[i] = cmake(hs * vh.x + es * ve.x, hs * vh.y + es * ve.y);
   }
   double out[2];
   block_sum<2>(acc, out);
@@ -183,7 +187,12 @@ __device__ __forceinline__ void lda_eps(int xc_id, double n, double& eps, double
 // v_HE(r) (complex, already / N) + xc -> veff[s], E_xc partial sums.
 __global__ void __launch_bounds__(RED_THREADS)
 k_veff_xc(GridGeom g, const cplx* __restrict__ grid, const double* __restrict__ rho, int ns,
-          int xc_id, int kohn_sham, double* __restrict__ veff, double* __restrict__ partials) {
+          int xc_id, int kohn_sham, int parts, double* __restrict__ veff,
+          double* __restrict__ partials) {
+  // parts bit 2 = add the xc term; bit 3 = reference semantics: eps_xc unless kohn_sham
+  // (xc.py:247-250), otherwise the functional derivative v_xc = eps + rho eps'
+  const double xs = (parts & 4) ? 1.0 : 0.0;
+  const bool as_eps = (parts & 8) && !kohn_sham;
   double acc[1] = {0.0};
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < g.n;
        i += (long long)gridDim.x * blockDim.x) {
@@ -193,7 +202,7 @@ k_veff_xc(GridGeom g, const cplx* __restrict__ grid, const double* __restrict__ 
       double e, de;
       lda_eps(xc_id, n, e, de);
       const double vxc = e + n * de;
-      veff[i] = vhe + vxc;
+      veff[i] = vhe + xs * (as_eps ? e : vxc);
       acc[0] += (kohn_sham ? vxc : e) * n;
     } else {
       // exchange only: eps = 1/2 [eps_x(2 rho_up) + eps_x(2 rho_dn)]  (xc.py:56-59)
@@ -207,12 +216,12 @@ k_veff_xc(GridGeom g, const cplx* __restrict__ grid, const double* __restrict__ 
       if (kohn_sham) {
         // reference vxc_lda (xc.py:114-122): v_s = eps + rho_s d eps/d rho_s
         const double vu = e + ru * deu, vd = e + rd * ded;
-        veff[i] = vhe + vu;
-        veff[g.n + i] = vhe + vd;
+        veff[i] = vhe + xs * vu;
+        veff[g.n + i] = vhe + xs * vd;
         acc[0] += vu * ru + vd * rd;
       } else {
-        veff[i] = vhe + e + n * deu;
-        veff[g.n + i] = vhe + e + n * ded;
+        veff[i] = vhe + xs * (as_eps ? e : e + n * deu);
+        veff[g.n + i] = vhe + xs * (as_eps ? e : e + n * ded);
         acc[0] += e * n;
       }
     }
@@ -233,7 +242,7 @@ __global__ void k_reduce_partials(const double* __restrict__ partials, int nbloc
   if (lane == 0) out[c] = s;
 }
 
-int launch_grid_potential(jrb_plan* p, const double* rho, int xc_id, int kohn_sham,
+int launch_grid_potential(jrb_plan* p, const double* rho, int xc_id, int kohn_sham, int parts,
                           double* energies, double* veff, cudaStream_t st) {
   if (xc_id != JRB_XC_LDA_X && xc_id != JRB_XC_LDA_X_C_PW) {
     set_error("jrb_grid_potential: unsupported xc id (LDA only: lda_x, lda_x+lda_c_pw)");
@@ -254,16 +263,34 @@ int launch_grid_potential(jrb_plan* p, const double* rho, int xc_id, int kohn_sh
   JRB_CHECK_LAUNCH("k_rho_to_complex");
   int rc = launch_fft3d_dense(p, p->d_grid, p->d_grid, JRB_FFT_FORWARD, 1, 1.0, st);
   if (rc) return rc;
-  k_hartree_ext<<<blocks, RED_THREADS, 0, st>>>(g, p->d_grid, p->d_vext, kohn_sham, p->d_partials);
+  k_hartree_ext<<<blocks, RED_THREADS, 0, st>>>(g, p->d_grid, p->d_vext, kohn_sham, parts,
+                                               p->d_partials);
   JRB_CHECK_LAUNCH("k_hartree_ext");
   rc = launch_fft3d_dense(p, p->d_grid, p->d_grid, JRB_FFT_INVERSE, 1, 1.0 / (double)p->ngrid, st);
   if (rc) return rc;
-  k_veff_xc<<<blocks, RED_THREADS, 0, st>>>(g, p->d_grid, rho, p->ns, xc_id, kohn_sham, veff,
+  k_veff_xc<<<blocks, RED_THREADS, 0, st>>>(g, p->d_grid, rho, p->ns, xc_id, kohn_sham, parts, veff,
                                            p->d_partials);
   JRB_CHECK_LAUNCH("k_veff_xc");
-  k_reduce_partials<<<1, 96, 0, st>>>(p->d_partials, blocks, 3, energies);
-  JRB_CHECK_LAUNCH("k_reduce_partials");
+  if (energies) {
+    k_reduce_partials<<<1, 96, 0, st>>>(p->d_partials, blocks, 3, energies);
+    JRB_CHECK_LAUNCH("k_reduce_partials");
+  }
   return 0;
+}
+
+// out[s] = complex(rho[s]) for every spin, then forward FFT: pw.density_grid_reciprocal
+__global__ void k_real_to_complex(const double* __restrict__ in, long long n, cplx* __restrict__ out) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
+       i += (long long)gridDim.x * blockDim.x)
+    out[i] = cmake(in[i], 0.0);
+}
+
+int launch_density_reciprocal(jrb_plan* p, const double* rho, cplx* rho_hat, cudaStream_t st) {
+  const long long n = (long long)p->ns * p->ngrid;
+  const int blocks = (int)std::min<long long>((n + 255) / 256, 148 * 8);
+  k_real_to_complex<<<blocks, 256, 0, st>>>(rho, n, rho_hat);
+  JRB_CHECK_LAUNCH("k_real_to_complex");
+  return launch_fft3d_dense(p, rho_hat, rho_hat, JRB_FFT_FORWARD, p->ns, 1.0, st);
 }
 
 // ---------------------------------------------------------------------------------------

@@ -111,7 +111,7 @@ extern "C" int jrb_plan_destroy(jrb_plan* p) {
   if (!p) return 0;
   cudaSetDevice(p->device);
   void* ptrs[] = {p->d_zmap, p->d_ycol, p->d_xmap, p->d_gidx, p->d_gk2, p->d_tw_x, p->d_tw_y,
-                  p->d_tw_z, p->d_ws_a, p->d_ws_b, p->d_focc, p->d_grid, p->d_vext,
+                  p->d_tw_z, p->d_ws_a, p->d_ws_b, p->d_rho_part, p->d_seg_z, p->d_focc, p->d_grid, p->d_vext,
                   p->d_partials, p->d_veff, p->d_q, p->d_hq, p->d_tmp, p->d_r, p->d_rinv, p->d_small, p->d_gpart,
                   p->d_tkb, p->d_eps, p->d_scal, p->d_wre, p->d_wim, p->d_gre, p->d_gim,
                   p->d_occ, p->d_rho, p->d_en};
@@ -252,22 +252,34 @@ extern "C" int jrb_plan_create(const jrb_plan_desc* d, jrb_plan** out) {
   const int total_groups = p->ns * p->nk * p->ngroups_per_k;
   const size_t b_per_group = (size_t)nxo * ny * nz * NB;  // complex numbers
   const size_t a_per_group = (size_t)ncol * nz * NB;
+  p->fused = fused_available(nx, ny, nxo, ncol) ? 1 : 0;
   int bg = d->batch_groups;
   if (const char* env = std::getenv("JRB_BATCH_GROUPS")) bg = std::atoi(env);
   if (bg <= 0) {
-    // automatic: measured on B200 (profiles/r01_first_bench.md) large batches win over
-    // L2-resident small ones (fewer, fatter launches; the passes are FP64-issue bound, not
-    // HBM bound), so take up to 128 groups within a 2 GiB slab budget.
-    const double target = 2048.0 * 1024 * 1024;
-    bg = (int)(target / ((double)b_per_group * sizeof(cplx)));
-    if (bg > 128) bg = 128;
+    // automatic: fat launches (the passes are FP64-issue bound, not HBM bound).  Unfused: up to
+    // 128 groups within a 2 GiB B slab; fused (only the column buffer A exists): up to 256
+    // groups within 1.5 GiB.
+    if (p->fused) {
+      bg = (int)(1536.0 * 1024 * 1024 / ((double)a_per_group * sizeof(cplx)));
+      if (bg > 256) bg = 256;
+    } else {
+      bg = (int)(2048.0 * 1024 * 1024 / ((double)b_per_group * sizeof(cplx)));
+      if (bg > 128) bg = 128;
+    }
     if (bg < 2) bg = 2;
   }
   if (bg > p->nk * p->ngroups_per_k) bg = p->nk * p->ngroups_per_k;  // never straddle a spin
   if (bg > 65535) bg = 65535;
   p->batch_groups = bg;
+  // fused kernels: persistent CTAs; a CTA touches at most fused_segmax z-planes per launch
+  // (worst case over batch sizes 1..bg: one group per batch)
+  p->fused_ctas = p->fused ? fused_cta_count(nx, nxo, ncol) : 0;
+  p->fused_segmax = p->fused ? (nz + p->fused_ctas - 1) / p->fused_ctas + 2 : 0;
   TRY(dev_alloc(&p->d_ws_a, a_per_group * bg, &tot));
-  TRY(dev_alloc(&p->d_ws_b, b_per_group * bg, &tot));
+  TRY(dev_alloc(&p->d_ws_b, p->fused ? 1 : b_per_group * bg, &tot));
+  TRY(dev_alloc(&p->d_rho_part,
+                p->fused ? (size_t)p->fused_ctas * p->fused_segmax * nx * ny : 1, &tot));
+  TRY(dev_alloc(&p->d_seg_z, p->fused ? (size_t)p->fused_ctas * p->fused_segmax : 1, &tot));
   TRY(dev_alloc(&p->d_focc, (size_t)total_groups * NB, &tot));
   // --- grid work space --------------------------------------------------------------
   TRY(dev_alloc(&p->d_grid, (size_t)p->ngrid, &tot));

@@ -59,6 +59,11 @@ struct jrb_plan {
   jrb::cplx* d_ws_a;  // [batch][ncol][nz][NB]
   jrb::cplx* d_ws_b;  // [batch][nxo][ny][nz][NB]
   double* d_focc;     // [ns*nk*ngroups_per_k][NB] occupation / Omega, zero padded
+  int fused;          // 1: y and x passes fused per z-plane (fft_fused.cuh); B slab unused
+  int fused_ctas;     // persistent CTAs of the fused kernels (resident slots)
+  int fused_segmax;   // partial density planes per CTA (upper bound over batch sizes)
+  double* d_rho_part; // [fused_ctas * fused_segmax][nx*ny] partial density planes
+  int* d_seg_z;       // [fused_ctas * fused_segmax] z of each partial plane or -1
   // grid work space
   jrb::cplx* d_grid;      // [ngrid] dense complex grid
   jrb::cplx* d_vext;      // [ngrid] V_ext(G) incl. the reference's -N/Omega factor
@@ -86,12 +91,15 @@ int launch_hpsi(jrb_plan* p, const cplx* q, const double* veff, cplx* hq, cudaSt
 int launch_fft3d_dense(jrb_plan* p, const cplx* in, cplx* out, int dir, int64_t batch,
                        double scale, cudaStream_t st);
 bool line_length_supported(int n);
+bool fused_available(int nx, int ny, int nxo, int ncol);
+int fused_cta_count(int n, int nxo, int ncol);
 
 // grid_kernels.cu
 int launch_set_atoms(jrb_plan* p, const double* pos_h, const double* chg_h, int na,
                      cudaStream_t st);
-int launch_grid_potential(jrb_plan* p, const double* rho, int xc_id, int kohn_sham,
+int launch_grid_potential(jrb_plan* p, const double* rho, int xc_id, int kohn_sham, int parts,
                           double* energies, double* veff, cudaStream_t st);
+int launch_density_reciprocal(jrb_plan* p, const double* rho, cplx* rho_hat, cudaStream_t st);
 int launch_kinetic(jrb_plan* p, const cplx* q, double* t_skb, cudaStream_t st);
 int launch_band_expect(jrb_plan* p, const cplx* q, const cplx* hq, double* eps, cudaStream_t st);
 int launch_weighted_sum(jrb_plan* p, const double* a, const double* w, int64_t n, double* out,
@@ -104,6 +112,7 @@ int launch_focc(jrb_plan* p, const double* occ, cudaStream_t st);
 int qr_gram_chunks(const jrb_plan* p);
 int launch_qr_fwd(jrb_plan* p, const double* w_re, const double* w_im, cplx* q, cplx* r,
                   cudaStream_t st);
+int launch_hamiltonian_matrix(jrb_plan* p, const cplx* q, const cplx* hq, cplx* h, cudaStream_t st);
 int launch_qr_bwd(jrb_plan* p, const cplx* q, const cplx* r, const cplx* gq, const double* occ,
                   double* g_re, double* g_im, cudaStream_t st);
 

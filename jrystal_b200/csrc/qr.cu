@@ -281,44 +281,82 @@ static int run_gram(jrb_plan* p, TallMat A, TallMat B, bool same, cplx* partial,
   const long long sks = p->ng * p->nb;
   const int panels = (same && tiles == 1) ? 1 : 2;
   const int smem = panels * ST * QK * QLDB * (int)sizeof(cplx);
-  static int once = opt_in_smem(k_gram<ST>, 2 * ST * QK * QLDB * (int)sizeof(cplx));
-  if (once) return once;
-  k_gram<ST><<<grid, QTHREADS, smem, st>>>(A, B, same ? 1 : 0, p->ng, p->nb, sks, tiles, rows,
-                                           partial);
+  if (tiles == 1) {
+    static int once = opt_in_smem(k_gram<ST, QSLOT_DIAG>, 2 * ST * QK * QLDB * (int)sizeof(cplx));
+    if (once) return once;
+    k_gram<ST, QSLOT_DIAG><<<grid, QTHREADS, smem, st>>>(A, B, same ? 1 : 0, p->ng, p->nb, sks,
+                                                        tiles, rows, partial);
+  } else {
+    static int once = opt_in_smem(k_gram<ST, QMAXSLOT>, 2 * ST * QK * QLDB * (int)sizeof(cplx));
+    if (once) return once;
+    k_gram<ST, QMAXSLOT><<<grid, QTHREADS, smem, st>>>(A, B, same ? 1 : 0, p->ng, p->nb, sks,
+                                                      tiles, rows, partial);
+  }
   JRB_CHECK_LAUNCH("k_gram");
   *nchunks_out = nchunks;
   return 0;
 }
 
-template <int MODE, int NCB>
+template <int MODE, int NCB, bool SPLIT>
 static int run_apply_ncb(jrb_plan* p, TallMat in1, const cplx* t1, int tri1, TallMat in2,
                          const cplx* t2, int tri2, int nterms, double* out_a, double* out_b,
                          cudaStream_t st) {
   constexpr int ST = 2;
   const int nsk = p->ns * p->nk;
   const int smem = ST * (QROWS * QLDA + QK * (8 * NCB + 2)) * (int)sizeof(cplx);
-  static int once = opt_in_smem(k_apply<MODE, NCB, ST>, smem);
+  static int once = opt_in_smem(k_apply<MODE, NCB, ST, SPLIT>, smem);
   if (once) return once;
   dim3 grid((unsigned)((p->ng + QROWS - 1) / QROWS), (p->nb + 8 * NCB - 1) / (8 * NCB), nsk);
-  k_apply<MODE, NCB, ST><<<grid, QTHREADS, smem, st>>>(in1, t1, tri1, in2, t2, tri2, nterms,
-                                                      p->ng, p->nb, p->ng * p->nb, out_a, out_b);
+  k_apply<MODE, NCB, ST, SPLIT><<<grid, QTHREADS, smem, st>>>(
+    in1.re, in1.im, t1, tri1, reinterpret_cast<const cplx*>(in2.re), t2, tri2, nterms, p->ng,
+    p->nb, p->ng * p->nb, out_a, out_b);
   JRB_CHECK_LAUNCH("k_apply");
   return 0;
 }
 
-// column-tile width: the smallest of 32 / 72 / 104 columns that covers nb in the fewest tiles
+// column-tile width: 32 columns for few bands, else 72 (blocks past nb cost no tensor work)
 template <int MODE>
 static int run_apply(jrb_plan* p, TallMat in1, const cplx* t1, int tri1, TallMat in2,
                      const cplx* t2, int tri2, int nterms, double* out_a, double* out_b,
                      cudaStream_t st) {
   const int nb = p->nb;
-  if (nb <= 32) return run_apply_ncb<MODE, 4>(p, in1, t1, tri1, in2, t2, tri2, nterms, out_a, out_b, st);
-  if (nb <= 72) return run_apply_ncb<MODE, 9>(p, in1, t1, tri1, in2, t2, tri2, nterms, out_a, out_b, st);
-  const int t104 = (nb + 103) / 104, t72 = (nb + 71) / 72;
-  // padded column count decides (tensor work scales with it)
-  if (t104 * 104 <= t72 * 72 || t104 < t72)
-    return run_apply_ncb<MODE, 13>(p, in1, t1, tri1, in2, t2, tri2, nterms, out_a, out_b, st);
-  return run_apply_ncb<MODE, 9>(p, in1, t1, tri1, in2, t2, tri2, nterms, out_a, out_b, st);
+  const bool split = in1.im != nullptr;
+  if (MODE == 0 && split) {
+    if (nb <= 32)
+      return run_apply_ncb<0, 4, true>(p, in1, t1, tri1, in2, t2, tri2, nterms, out_a, out_b, st);
+    return run_apply_ncb<0, 9, true>(p, in1, t1, tri1, in2, t2, tri2, nterms, out_a, out_b, st);
+  }
+  if (nb <= 32)
+    return run_apply_ncb<MODE, 4, false>(p, in1, t1, tri1, in2, t2, tri2, nterms, out_a, out_b, st);
+  return run_apply_ncb<MODE, 9, false>(p, in1, t1, tri1, in2, t2, tri2, nterms, out_a, out_b, st);
+}
+
+// H[sk][i][j] = sum_chunks partial (upper blocks), mirrored as a Hermitian matrix
+__global__ void __launch_bounds__(256)
+k_sum_partials_herm(const cplx* __restrict__ partial, int nchunks, int nb, cplx* __restrict__ H) {
+  const int sk = blockIdx.x, nsk = gridDim.x;
+  const long long nn = (long long)nb * nb;
+  for (long long e = threadIdx.x; e < nn; e += blockDim.x) {
+    const int i = (int)(e / nb), j = (int)(e % nb);
+    const long long src = j >= i ? e : (long long)j * nb + i;
+    cplx s = cmake(0.0, 0.0);
+    for (int c = 0; c < nchunks; ++c) {
+      const cplx v = partial[((long long)c * nsk + sk) * nn + src];
+      s.x += v.x; s.y += v.y;
+    }
+    H[sk * nn + e] = j >= i ? s : cconj(s);
+  }
+}
+
+// H_ij = <q_i | hq_j> for Hermitian H (hamiltonian.hamiltonian_matrix): one Gram on DMMA
+int launch_hamiltonian_matrix(jrb_plan* p, const cplx* q, const cplx* hq, cplx* h, cudaStream_t st) {
+  int nchunks = 0, rc = 0;
+  TallMat Q{reinterpret_cast<const double*>(q), nullptr, p->nb};
+  TallMat G{reinterpret_cast<const double*>(hq), nullptr, p->nb};
+  if ((rc = run_gram(p, Q, G, false, p->d_gpart, &nchunks, st))) return rc;
+  k_sum_partials_herm<<<p->ns * p->nk, 256, 0, st>>>(p->d_gpart, nchunks, p->nb, h);
+  JRB_CHECK_LAUNCH("k_sum_partials_herm");
+  return 0;
 }
 
 int launch_qr_fwd(jrb_plan* p, const double* w_re, const double* w_im, cplx* q, cplx* r,

@@ -30,10 +30,13 @@ constexpr int QTHREADS = 256;
 constexpr int QWARPS = 8;
 constexpr int QROWS = 8 * QWARPS;  // rows of the apply CTA tile (one 8-row block per warp)
 constexpr int QMAXSLOT = 11;       // ceil(81 / 8) Gram blocks per warp
+constexpr int QGRP = 3;            // Gram blocks whose DMMAs are interleaved
+constexpr int QSLOT_DIAG = 6;      // ceil(45 / 8): one diagonal super-tile only (nb <= 72)
 
 enum TriKind { TRI_FULL = 0, TRI_UPPER = 1, TRI_LOWER = 2 };
 
 __device__ __forceinline__ void dmma(double (&c)[2], double a, double b) {
+  // volatile: keeps the hand-interleaved issue order (and the register pressure) as written
   asm volatile(
     "mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
     : "+d"(c[0]), "+d"(c[1])
@@ -84,8 +87,8 @@ struct TallMat {
 // (entries below the block diagonal are NOT written; consumers mirror / ignore them).
 // grid: (ntiles (ntiles + 1) / 2 upper super-tiles, nchunks, nsk)
 // dynamic smem: STAGES * 2 panels [QK][QLDB]
-template <int STAGES>
-__global__ void __launch_bounds__(QTHREADS, 2)
+template <int STAGES, int MAXSLOT>
+__global__ void __launch_bounds__(QTHREADS, (MAXSLOT <= 6 ? 2 : 1))
 k_gram(TallMat A, TallMat B, int same, long long ng, int nb, long long sk_stride, int ntiles,
        long long rows_per_chunk, cplx* __restrict__ partial) {
   extern __shared__ __align__(16) unsigned char smem_raw_[];
@@ -114,9 +117,9 @@ k_gram(TallMat A, TallMat B, int same, long long ng, int nb, long long sk_stride
 
   // blocks of this warp: ids warp, warp + 8, ... in the row-major list of needed blocks
   // packed per slot: 8 bi in the low half, 8 bj in the high half, -1 = no block
-  int blk[QMAXSLOT];
+  int blk[MAXSLOT];
 #pragma unroll
-  for (int s = 0; s < QMAXSLOT; ++s) {
+  for (int s = 0; s < MAXSLOT; ++s) {
     int id = warp + QWARPS * s, bi, bj;
     if (diag) {
       bi = 0;
@@ -133,20 +136,31 @@ k_gram(TallMat A, TallMat B, int same, long long ng, int nb, long long sk_stride
   }
   const int lofs = lc * QLDB + lr;
 
+  // panel elements of this thread: e = tid + 256 q -> (row e / 72, col e % 72), fixed per thread
+  constexpr int GLOADS = (QK * QT + QTHREADS - 1) / QTHREADS;
+  int lrc[GLOADS];
+#pragma unroll
+  for (int q = 0; q < GLOADS; ++q) {
+    const int e = threadIdx.x + QTHREADS * q;
+    lrc[q] = e < QK * QT ? (e / QT) | ((e % QT) << 8) : -1;
+  }
   auto load_stage = [&](int step, int stage) {
     const long long g0 = g_begin + (long long)step * QK;
-    for (int e = threadIdx.x; e < QK * QT; e += QTHREADS) {
-      const int r = e / QT, c = e % QT;
-      const long long g = g0 + r;
-      a.fetch(&sA[(stage * QK + r) * QLDB + c], g, i0 + c, g < g_end && c < wi_cols);
-      if (!one_panel)
-        bm.fetch(&sB[(stage * QK + r) * QLDB + c], g, j0 + c, g < g_end && c < wj_cols);
+#pragma unroll
+    for (int q = 0; q < GLOADS; ++q) {
+      if (lrc[q] >= 0) {
+        const int r = lrc[q] & 0xff, c = lrc[q] >> 8;
+        const long long g = g0 + r;
+        a.fetch(&sA[(stage * QK + r) * QLDB + c], g, i0 + c, g < g_end && c < wi_cols);
+        if (!one_panel)
+          bm.fetch(&sB[(stage * QK + r) * QLDB + c], g, j0 + c, g < g_end && c < wj_cols);
+      }
     }
   };
 
-  double cre[QMAXSLOT][2], cim[QMAXSLOT][2];
+  double cre[MAXSLOT][2], cim[MAXSLOT][2];
 #pragma unroll
-  for (int s = 0; s < QMAXSLOT; ++s) cre[s][0] = cre[s][1] = cim[s][0] = cim[s][1] = 0.0;
+  for (int s = 0; s < MAXSLOT; ++s) cre[s][0] = cre[s][1] = cim[s][0] = cim[s][1] = 0.0;
 
 #pragma unroll
   for (int s = 0; s < STAGES - 1; ++s) {
@@ -162,16 +176,35 @@ k_gram(TallMat A, TallMat B, int same, long long ng, int nb, long long sk_stride
     const cplx* pb = sB + (it % STAGES) * QK * QLDB;
 #pragma unroll
     for (int k4 = 0; k4 < QK / 4; ++k4) {
+      // slots in groups of QGRP: all first products, then all second products, so that the two
+      // DMMAs accumulating into the same registers are QGRP * 2 - 1 issues apart
 #pragma unroll
-      for (int s = 0; s < QMAXSLOT; ++s) {
-        if (blk[s] >= 0) {
-          const cplx fa = pa[k4 * 4 * QLDB + lofs + (blk[s] & 0xffff)];  // A frag (row i, col k)
-          const cplx fb = pb[k4 * 4 * QLDB + lofs + (blk[s] >> 16)];     // B frag (row k, col j)
-          // conj(a) b = (ar br + ai bi) + i (ar bi - ai br)
-          dmma(cre[s], fa.x, fb.x);
-          dmma(cim[s], fa.x, fb.y);
-          dmma(cre[s], fa.y, fb.y);
-          dmma(cim[s], -fa.y, fb.x);
+      for (int s0 = 0; s0 < MAXSLOT; s0 += QGRP) {
+        cplx fa[QGRP], fb[QGRP];
+#pragma unroll
+        for (int q = 0; q < QGRP; ++q) {
+          const int s = s0 + q;
+          if (s < MAXSLOT && blk[s] >= 0) {
+            fa[q] = pa[k4 * 4 * QLDB + lofs + (blk[s] & 0xffff)];  // A frag (row i, col k)
+            fb[q] = pb[k4 * 4 * QLDB + lofs + (blk[s] >> 16)];     // B frag (row k, col j)
+          }
+        }
+        // conj(a) b = (ar br + ai bi) + i (ar bi - ai br)
+#pragma unroll
+        for (int q = 0; q < QGRP; ++q) {
+          const int s = s0 + q;
+          if (s < MAXSLOT && blk[s] >= 0) {
+            dmma(cre[s], fa[q].x, fb[q].x);
+            dmma(cim[s], fa[q].x, fb[q].y);
+          }
+        }
+#pragma unroll
+        for (int q = 0; q < QGRP; ++q) {
+          const int s = s0 + q;
+          if (s < MAXSLOT && blk[s] >= 0) {
+            dmma(cre[s], fa[q].y, fb[q].y);
+            dmma(cim[s], -fa[q].y, fb[q].x);
+          }
         }
       }
     }
@@ -179,7 +212,7 @@ k_gram(TallMat A, TallMat B, int same, long long ng, int nb, long long sk_stride
   cp_async_wait<0>();
   cplx* out = partial + ((long long)chunk * nsk + sk) * nb * nb;
 #pragma unroll
-  for (int s = 0; s < QMAXSLOT; ++s) {
+  for (int s = 0; s < MAXSLOT; ++s) {
     if (blk[s] >= 0) {
       const int i = i0 + (blk[s] & 0xffff) + lr;
       const int j = j0 + (blk[s] >> 16) + 2 * lc;
@@ -193,17 +226,75 @@ k_gram(TallMat A, TallMat B, int same, long long ng, int nb, long long sk_stride
 
 // ---------------------------------------------------------------------------------------
 // Out[g][j] = sum_i In1[g][i] T1[i][j] (+ sum_i In2[g][i] T2[i][j])
-// tri1 / tri2 say which part of T1 / T2 is structurally zero (TriKind); the k-range of each
-// 8-column block is clipped accordingly.
+// tri1 / tri2 say which part of T1 / T2 is structurally zero (TriKind).  Per 16-deep k-step
+// the needed 8-column blocks are a contiguous range [UB, UE): the step body is instantiated
+// for every range start (upper T) / end (lower T), so the hot code is straight-line DMMAs.
 // MODE 0: store interleaved complex;  MODE 1: store 2 Re / 2 Im into split real arrays.
+// SPLIT: In1 is given as separate re / im arrays (the parameters w_re, w_im).
 // CTA tile: 64 rows (one 8-row block per warp) x 8 NCB columns.
 // grid: (ceil(ng / 64), ceil(nb / (8 NCB)), nsk)
-template <int MODE, int NCB, int STAGES>
+
+// one k-step on blocks [UB, UE): nk4 sub-steps of depth 4
+template <int NCB, int UB, int UE>
+__device__ __forceinline__ void apply_step(double (&cre)[NCB][2], double (&cim)[NCB][2],
+                                           const cplx* __restrict__ pa,
+                                           const cplx* __restrict__ pb, int nk4) {
+  constexpr int LDB = 8 * NCB + 2;
+#pragma unroll
+  for (int k4 = 0; k4 < QK / 4; ++k4) {
+    if (k4 < nk4) {
+      const cplx fa = pa[k4 * 4];  // A frag (row g, col k)
+      const double nai = -fa.y;
+      cplx fb[UE - UB];
+#pragma unroll
+      for (int u = UB; u < UE; ++u) fb[u - UB] = pb[k4 * 4 * LDB + 8 * u];  // B frag (row k, col j)
+      // a b = (ar br - ai bi) + i (ar bi + ai br): first products of every block, then the
+      // second ones, so the two DMMAs into one accumulator are far apart
+#pragma unroll
+      for (int u = UB; u < UE; ++u) {
+        dmma(cre[u], fa.x, fb[u - UB].x);
+        dmma(cim[u], fa.x, fb[u - UB].y);
+      }
+#pragma unroll
+      for (int u = UB; u < UE; ++u) {
+        dmma(cre[u], nai, fb[u - UB].y);
+        dmma(cim[u], fa.y, fb[u - UB].x);
+      }
+    }
+  }
+}
+
+template <int NCB, int U>
+struct ApplyDispatch {
+  // blocks [ub, NCB)
+  static __device__ __forceinline__ void from(int ub, double (&cre)[NCB][2], double (&cim)[NCB][2],
+                                              const cplx* pa, const cplx* pb, int nk4) {
+    if (ub <= U) {
+      apply_step<NCB, U, NCB>(cre, cim, pa, pb, nk4);
+    } else if constexpr (U + 1 < NCB) {
+      ApplyDispatch<NCB, U + 1>::from(ub, cre, cim, pa, pb, nk4);
+    }
+  }
+  // blocks [0, ue), ue >= 1
+  static __device__ __forceinline__ void upto(int ue, double (&cre)[NCB][2], double (&cim)[NCB][2],
+                                              const cplx* pa, const cplx* pb, int nk4) {
+    if (ue >= NCB - U) {
+      apply_step<NCB, 0, NCB - U>(cre, cim, pa, pb, nk4);
+    } else if constexpr (U + 1 < NCB) {
+      ApplyDispatch<NCB, U + 1>::upto(ue, cre, cim, pa, pb, nk4);
+    }
+  }
+};
+
+template <int MODE, int NCB, int STAGES, bool SPLIT>
 __global__ void __launch_bounds__(QTHREADS, 2)
-k_apply(TallMat In1, const cplx* __restrict__ T1, int tri1, TallMat In2,
+k_apply(const double* __restrict__ in1_re, const double* __restrict__ in1_im,
+        const cplx* __restrict__ T1, int tri1, const cplx* __restrict__ in2,
         const cplx* __restrict__ T2, int tri2, int nterms, long long ng, int nb,
         long long sk_stride, double* __restrict__ out_a, double* __restrict__ out_b) {
   constexpr int LDB = 8 * NCB + 2;
+  constexpr int ALOADS = QROWS * QK / QTHREADS;                    // 4
+  constexpr int BLOADS = (QK * 8 * NCB + QTHREADS - 1) / QTHREADS;
   extern __shared__ __align__(16) unsigned char smem_raw_[];
   cplx* sA = reinterpret_cast<cplx*>(smem_raw_);  // [STAGES][64][QLDA]
   cplx* sB = sA + STAGES * QROWS * QLDA;          // [STAGES][QK][LDB]
@@ -211,37 +302,64 @@ k_apply(TallMat In1, const cplx* __restrict__ T1, int tri1, TallMat In2,
   const long long g0 = (long long)blockIdx.x * QROWS;
   const int j0 = blockIdx.y * 8 * NCB;
   const int jend = min(nb, j0 + 8 * NCB);
+  const int nblk = (jend - j0 + 7) >> 3;  // column blocks that exist in this tile
   const int sk = blockIdx.z;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int lr = lane >> 2, lc = lane & 3;
-  const TallMat in1 = In1.offset(sk * sk_stride);
-  const TallMat in2 = nterms > 1 ? In2.offset(sk * sk_stride) : in1;
+  const long long skoff = (long long)sk * sk_stride;
   const cplx* t1 = T1 + (long long)sk * nb * nb;
   const cplx* t2 = nterms > 1 ? T2 + (long long)sk * nb * nb : t1;
 
   // k-range of each term for this column tile (multiples of 4 at the lower end)
-  auto kbeg_of = [&](int tri) { return tri == TRI_LOWER ? (j0 & ~3) : 0; };
-  auto kend_of = [&](int tri) { return tri == TRI_UPPER ? jend : nb; };
-  const int kb1 = kbeg_of(tri1), ke1 = kend_of(tri1);
-  const int kb2 = kbeg_of(tri2), ke2 = nterms > 1 ? kend_of(tri2) : kb2;
+  const int kb1 = tri1 == TRI_LOWER ? (j0 & ~3) : 0;
+  const int ke1 = tri1 == TRI_UPPER ? jend : nb;
+  const int kb2 = tri2 == TRI_LOWER ? (j0 & ~3) : 0;
+  const int ke2 = nterms > 1 ? (tri2 == TRI_UPPER ? jend : nb) : kb2;
   const int ns1 = (ke1 - kb1 + QK - 1) / QK;
   const int ns2 = nterms > 1 ? (ke2 - kb2 + QK - 1) / QK : 0;
   const int nsteps = ns1 + ns2;
+
+  // fixed per-thread load coordinates
+  const int ar = threadIdx.x / QK, ac = threadIdx.x % QK;  // A rows ar + 16 q, column ac
+  bool arow_ok[ALOADS];
+#pragma unroll
+  for (int q = 0; q < ALOADS; ++q) arow_ok[q] = g0 + ar + (QTHREADS / QK) * q < ng;
+  const long long a_off = skoff + (g0 + ar) * (long long)nb + ac;  // + 16 q nb + k0
+  int b_r[BLOADS], b_c[BLOADS];
+#pragma unroll
+  for (int q = 0; q < BLOADS; ++q) {
+    const int e = threadIdx.x + QTHREADS * q;
+    b_r[q] = e / (8 * NCB);
+    b_c[q] = e % (8 * NCB);
+  }
 
   auto load_stage = [&](int step, int stage) {
     const bool second = step >= ns1;
     const int k0 = second ? kb2 + (step - ns1) * QK : kb1 + step * QK;
     const int kend = second ? ke2 : ke1;
-    const TallMat& in = second ? in2 : in1;
     const cplx* T = second ? t2 : t1;
-    for (int e = threadIdx.x; e < QROWS * QK; e += QTHREADS) {
-      const int r = e / QK, c = e % QK;
-      in.fetch(&sA[(stage * QROWS + r) * QLDA + c], g0 + r, k0 + c, g0 + r < ng && k0 + c < kend);
+    cplx* da = sA + (stage * QROWS + ar) * QLDA + ac;
+    const bool kok = k0 + ac < kend;
+#pragma unroll
+    for (int q = 0; q < ALOADS; ++q) {
+      const bool v = arow_ok[q] && kok;
+      const long long o = v ? a_off + (long long)(QTHREADS / QK) * q * nb + k0 : 0;
+      cplx* d = da + (QTHREADS / QK) * q * QLDA;
+      if (SPLIT && !second) {
+        cp_async8(&d->x, in1_re + o, v);
+        cp_async8(&d->y, in1_im + o, v);
+      } else {
+        const cplx* src = second ? in2 : reinterpret_cast<const cplx*>(in1_re);
+        cp_async16(d, src + o, v);
+      }
     }
-    for (int e = threadIdx.x; e < QK * 8 * NCB; e += QTHREADS) {
-      const int r = e / (8 * NCB), c = e % (8 * NCB);
-      const bool v = k0 + r < kend && j0 + c < nb;
-      cp_async16(&sB[(stage * QK + r) * LDB + c], T + (v ? (long long)(k0 + r) * nb + j0 + c : 0), v);
+#pragma unroll
+    for (int q = 0; q < BLOADS; ++q) {
+      if (BLOADS * QTHREADS == QK * 8 * NCB || b_r[q] < QK) {
+        const bool v = k0 + b_r[q] < kend && j0 + b_c[q] < nb;
+        cp_async16(&sB[(stage * QK + b_r[q]) * LDB + b_c[q]],
+                   T + (v ? (long long)(k0 + b_r[q]) * nb + j0 + b_c[q] : 0), v);
+      }
     }
   };
 
@@ -263,45 +381,33 @@ k_apply(TallMat In1, const cplx* __restrict__ T1, int tri1, TallMat In2,
     const int k0 = second ? kb2 + (it - ns1) * QK : kb1 + it * QK;
     const int kend = second ? ke2 : ke1;
     const int tri = second ? tri2 : tri1;
+    const int nk4 = min(QK / 4, (kend - k0 + 3) >> 2);
     const cplx* pa = sA + ((it % STAGES) * QROWS + warp * 8 + lr) * QLDA + lc;
     const cplx* pb = sB + (it % STAGES) * QK * LDB + lc * LDB + lr;
-#pragma unroll
-    for (int k4 = 0; k4 < QK / 4; ++k4) {
-      const int kk = k0 + 4 * k4;  // this sub-step covers i in [kk, kk + 4)
-      if (kk < kend) {
-        const cplx fa = pa[k4 * 4];  // A frag (row g, col k)
-        const double nai = -fa.y;
-#pragma unroll
-        for (int u = 0; u < NCB; ++u) {
-          const int jlo = j0 + 8 * u;  // columns [jlo, jlo + 8)
-          // upper T: zero for i > j -> need kk <= jlo + 7; lower T: zero for i < j -> kk + 3 >= jlo
-          const bool need = jlo < nb && (tri == TRI_UPPER ? kk <= jlo + 7
-                                                          : (tri == TRI_LOWER ? kk + 3 >= jlo : true));
-          if (need) {
-            const cplx fb = pb[k4 * 4 * LDB + 8 * u];  // B frag (row k, col j)
-            // a b = (ar br - ai bi) + i (ar bi + ai br)
-            dmma(cre[u], fa.x, fb.x);
-            dmma(cim[u], fa.x, fb.y);
-            dmma(cre[u], nai, fb.y);
-            dmma(cim[u], fa.y, fb.x);
-          }
-        }
-      }
+    if (tri == TRI_UPPER) {
+      // T[i][j] = 0 for i > j: block u is needed while k0 <= j0 + 8 u + 7
+      const int ub = max(0, (k0 - j0 - 7 + 7) >> 3);
+      ApplyDispatch<NCB, 0>::from(ub, cre, cim, pa, pb, nk4);
+    } else if (tri == TRI_LOWER) {
+      // T[i][j] = 0 for i < j: block u is needed once k0 + 15 >= j0 + 8 u
+      const int ue = min(nblk, ((k0 + QK - 1 - j0) >> 3) + 1);
+      ApplyDispatch<NCB, 0>::upto(ue, cre, cim, pa, pb, nk4);
+    } else {
+      ApplyDispatch<NCB, 0>::upto(nblk, cre, cim, pa, pb, nk4);
     }
   }
   cp_async_wait<0>();
-  const long long base = (long long)sk * sk_stride;
   const long long g = g0 + warp * 8 + lr;
   if (g < ng) {
 #pragma unroll
     for (int u = 0; u < NCB; ++u) {
       const int j = j0 + 8 * u + 2 * lc;
       if (MODE == 0) {
-        cplx* o = reinterpret_cast<cplx*>(out_a) + base + g * nb + j;
+        cplx* o = reinterpret_cast<cplx*>(out_a) + skoff + g * nb + j;
         if (j < nb) o[0] = cmake(cre[u][0], cim[u][0]);
         if (j + 1 < nb) o[1] = cmake(cre[u][1], cim[u][1]);
       } else {
-        const long long o = base + g * nb + j;
+        const long long o = skoff + g * nb + j;
         if (j < nb) {
           out_a[o] = 2.0 * cre[u][0];
           out_b[o] = 2.0 * cim[u][0];

@@ -1,0 +1,89 @@
+"""Energy module: same names as jrystal.energy (jrystal/_src/energy.py) on the CUDA kernels.
+All grid terms come from one fused sweep (`Plan.grid_potential`); results are device scalars
+(0-d float64 tensors)."""
+import numpy as np
+import torch
+
+from . import pw as _pw
+from .context import current_plan
+
+
+def _plan_with_atoms(position, charge):
+  plan = current_plan()
+  pos = np.asarray(position, dtype=np.float64).reshape(-1, 3)
+  chg = np.asarray(charge, dtype=np.float64).reshape(-1)
+  cur = getattr(plan, '_atom_key', None)
+  key = (pos.tobytes(), chg.tobytes())
+  if cur != key:
+    plan.set_atoms(pos, chg)
+    plan._atom_key = key
+  return plan
+
+
+def _real_density(plan, density_grid_reciprocal):
+  """rho(r) from fftn(rho): the grid kernels start from the real-space density."""
+  rho = plan.fft3d(density_grid_reciprocal.contiguous(), inverse=True)
+  return torch.view_as_real(rho)[..., 0].contiguous()
+
+
+def hartree(density_grid_reciprocal, g_vector_grid, vol, kohn_sham: bool = False):
+  """jrystal/_src/energy.py:29-82."""
+  del g_vector_grid
+  plan = current_plan()
+  _pw._check_vol(plan, vol)
+  if not plan._atoms:
+    raise RuntimeError('call Plan.set_atoms (or energy.external) before energy.hartree')
+  en, _ = plan.grid_potential(_real_density(plan, density_grid_reciprocal), 'lda_x', kohn_sham)
+  return en[0]
+
+
+def external(density_grid_reciprocal, position, charge, g_vector_grid, vol):
+  """jrystal/_src/energy.py:85-135."""
+  del g_vector_grid
+  plan = _plan_with_atoms(position, charge)
+  _pw._check_vol(plan, vol)
+  en, _ = plan.grid_potential(_real_density(plan, density_grid_reciprocal), 'lda_x', False)
+  return en[1]
+
+
+def kinetic(g_vector_grid, kpts, coeff_grid, occupation=None):
+  """jrystal/_src/energy.py:138-182: scalar with occupation, else per (spin, kpt, band)."""
+  del g_vector_grid, kpts
+  c = _pw._as_coeff(coeff_grid)
+  t = c.plan.kinetic(c.q)
+  if occupation is None:
+    return t
+  return torch.sum(t * _pw._occ(c.plan, occupation))
+
+
+def xc_energy(density_grid, g_vector_grid, vol, xc_type: str = 'lda_x', kohn_sham: bool = False):
+  """jrystal/_src/energy.py:185-211 (LDA functionals)."""
+  del g_vector_grid
+  plan = current_plan()
+  _pw._check_vol(plan, vol)
+  if not plan._atoms:
+    raise RuntimeError('call Plan.set_atoms before energy.xc_energy')
+  en, _ = plan.grid_potential(density_grid.contiguous(), xc_type, kohn_sham)
+  return en[2]
+
+
+xc_lda = xc_energy  # name used by BASELINE.json / the reference's older tests
+
+
+def total_energy(coefficient, position, charge, g_vector_grid, kpts, vol, occupation=None,
+                 kohn_sham: bool = False, xc: str = 'lda_x', split: bool = False):
+  """jrystal/_src/energy.py:246-307: E_kin + E_ext + E_har + E_xc (split: that tuple)."""
+  del g_vector_grid, kpts
+  c = _pw._as_coeff(coefficient)
+  plan = _plan_with_atoms(position, charge)
+  if c.plan is not plan:
+    raise ValueError('coefficients belong to a different plan')
+  _pw._check_vol(plan, vol)
+  if occupation is None:
+    occupation = torch.ones((plan.ns, plan.nk, plan.nb), dtype=torch.float64, device=plan.tdev)
+  occ = _pw._occ(plan, occupation)
+  rho = plan.density(c.q, occ)
+  en, _ = plan.grid_potential(rho, xc, kohn_sham)
+  e_kin = torch.sum(plan.kinetic(c.q) * occ)
+  parts = (e_kin, en[1], en[0], en[2])
+  return parts if split else e_kin + en[1] + en[0] + en[2]

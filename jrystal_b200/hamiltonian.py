@@ -1,0 +1,47 @@
+"""jrystal.hamiltonian (jrystal/_src/hamiltonian.py) on the CUDA H-apply.
+
+`hamiltonian_matrix_trace` is the band-mode loss (hamiltonian.py:105-168); `hamiltonian_matrix`
+(171-240, nb Hessian-vector products through AD in the reference) is evaluated analytically as
+C^H (T C + FFT(v IFFT C)) from ONE H-apply."""
+import torch
+
+from . import pw as _pw
+from .energy import _plan_with_atoms
+
+
+def _apply(band_coefficient, positions, charges, effictive_density_grid, xc, kohn_sham):
+  c = _pw._as_coeff(band_coefficient)
+  plan = _plan_with_atoms(positions, charges)
+  if c.plan is not plan:
+    raise ValueError('coefficients belong to a different plan')
+  rho = effictive_density_grid
+  if rho.ndim == 3:
+    rho = rho[None]
+  # v_eff of hamiltonian.py:147-156 = potential.effective(kohn_sham) = dE/drho for kohn_sham
+  v = plan.potential(rho.contiguous(), xc, kohn_sham, 7)
+  return c, plan, plan.hpsi(c.q, v)
+
+
+def hamiltonian_matrix_trace(band_coefficient, positions, charges, effictive_density_grid,
+                             g_vector_grid, kpts, vol, xc: str = 'lda_x', kohn_sham: bool = True,
+                             keep_kpts_axis: bool = False, keep_spin_axis: bool = False):
+  """Sum_i <psi_i| T + v_eff |psi_i> per (spin, kpt), summed unless the keep_* flags say
+  otherwise (jrystal/_src/hamiltonian.py:105-168)."""
+  del g_vector_grid, kpts, vol
+  c, plan, hq = _apply(band_coefficient, positions, charges, effictive_density_grid, xc, kohn_sham)
+  eps = plan.band_expect(c.q, hq)          # (ns, nk, nb)
+  out = eps.sum(dim=-1)
+  if not keep_kpts_axis:
+    out = out.sum(dim=1)
+  if not keep_spin_axis:
+    out = out.sum(dim=0)
+  return out
+
+
+def hamiltonian_matrix(band_coefficient, positions, charges, effictive_density_grid,
+                       g_vector_grid, kpts, vol, xc: str = 'lda_x', kohn_sham: bool = True):
+  """H_ij = <psi_i| T + v_eff |psi_j>, shape (spin, kpt, band, band)
+  (jrystal/_src/hamiltonian.py:171-240)."""
+  del g_vector_grid, kpts, vol
+  c, plan, hq = _apply(band_coefficient, positions, charges, effictive_density_grid, xc, kohn_sham)
+  return plan.overlap(c.q, hq)

@@ -151,6 +151,31 @@ class Plan:
                                            int(bool(kohn_sham)), _ptr(en), _ptr(veff), _stream()))
     return en, veff
 
+  def potential(self, rho, xc: str = 'lda_x', kohn_sham: bool = False, parts: int = 7):
+    """potential.effective with the reference's semantics (real part); parts: 1 Hartree,
+    2 external, 4 xc (bitmask)."""
+    if not self._atoms:
+      raise RuntimeError('call set_atoms(positions, charges) first')
+    self._chk(rho, (self.ns, self.nx, self.ny, self.nz), torch.float64, 'density')
+    if xc not in _lib.XC_IDS:
+      raise NotImplementedError(f'xc "{xc}" is not implemented (LDA only: {list(_lib.XC_IDS)})')
+    v = self._new((self.ns, self.nx, self.ny, self.nz), torch.float64)
+    _lib.check(self.lib.jrb_potential(self._h, _ptr(rho), _lib.XC_IDS[xc], int(bool(kohn_sham)),
+                                      int(parts), _ptr(v), _stream()))
+    return v
+
+  def density_reciprocal(self, rho):
+    self._chk(rho, (self.ns, self.nx, self.ny, self.nz), torch.float64, 'density')
+    out = self._new((self.ns, self.nx, self.ny, self.nz), torch.complex128)
+    _lib.check(self.lib.jrb_density_reciprocal(self._h, _ptr(rho), _ptr(out), _stream()))
+    return out
+
+  def wave_grid(self, q):
+    self._chk(q, self.sphere_shape, torch.complex128, 'q')
+    out = self._new((self.ns, self.nk, self.nb, self.nx, self.ny, self.nz), torch.complex128)
+    _lib.check(self.lib.jrb_wave_grid(self._h, _ptr(q), _ptr(out), _stream()))
+    return out
+
   def hpsi(self, q, veff):
     self._chk(q, self.sphere_shape, torch.complex128, 'q')
     self._chk(veff, (self.ns, self.nx, self.ny, self.nz), torch.float64, 'veff')
@@ -164,6 +189,14 @@ class Plan:
     eps = self._new((self.ns, self.nk, self.nb), torch.float64)
     _lib.check(self.lib.jrb_band_expect(self._h, _ptr(q), _ptr(hq), _ptr(eps), _stream()))
     return eps
+
+  def overlap(self, q, hq):
+    """H[s,k,i,j] = <q_i|hq_j> (Hermitian), jrb_hamiltonian_matrix."""
+    self._chk(q, self.sphere_shape, torch.complex128, 'q')
+    self._chk(hq, self.sphere_shape, torch.complex128, 'hq')
+    h = self._new((self.ns, self.nk, self.nb, self.nb), torch.complex128)
+    _lib.check(self.lib.jrb_hamiltonian_matrix(self._h, _ptr(q), _ptr(hq), _ptr(h), _stream()))
+    return h
 
   def fft3d(self, x, inverse: bool, out=None):
     if x.dtype != torch.complex128 or not x.is_cuda or not x.is_contiguous():

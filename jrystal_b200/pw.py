@@ -1,0 +1,110 @@
+"""Plane-wave module: same names and argument meaning as jrystal.pw (jrystal/_src/pw.py), on the
+CUDA kernels.  Coefficients travel as a `Coefficients` handle (compact sphere layout + plan)
+instead of the reference's zero-padded (spin, kpt, band, x, y, z) array, which is only built on
+request (`.dense()`); every function also accepts that dense array where the reference does.
+"""
+from typing import Optional, Union
+
+import numpy as np
+import torch
+
+from .context import current_plan
+
+
+class Coefficients:
+  """Orthonormal plane-wave coefficients of pw.coeff: Q[s, k, g, b] on the cut-off sphere."""
+
+  def __init__(self, plan, q, r=None):
+    self.plan, self.q, self.r = plan, q, r
+
+  @property
+  def shape(self):  # the shape the reference's array has
+    p = self.plan
+    return (p.ns, p.nk, p.nb, p.nx, p.ny, p.nz)
+
+  def dense(self) -> torch.Tensor:
+    """utils.expand_coefficient (jrystal/_src/utils.py:277-281)."""
+    return self.plan.expand(self.q)
+
+
+def _as_coeff(coeff) -> Coefficients:
+  if isinstance(coeff, Coefficients):
+    return coeff
+  plan = current_plan()
+  if not isinstance(coeff, torch.Tensor):
+    coeff = torch.as_tensor(np.asarray(coeff), dtype=torch.complex128).to(plan.tdev)
+  if coeff.ndim != 6:
+    raise ValueError(f'coeff must have 6 axes (spin, kpt, band, x, y, z), got {coeff.ndim}')
+  return Coefficients(plan, plan.squeeze(coeff.contiguous()))
+
+
+def param_init(key, num_bands: int, num_kpts: int, freq_mask, spin_restricted: bool = True,
+               sharding=None) -> dict:
+  """jrystal/_src/pw.py:29-91: {'w_re','w_im'} ~ U[0,1), shape (ns, nk, ng, nb) float64.
+  `key` is an integer seed or a numpy Generator (JAX's threefry stream is not reproducible
+  without jax; parity is defined on given parameters)."""
+  del sharding
+  ns = 1 if spin_restricted else 2
+  ng = int(np.sum(np.asarray(freq_mask)))
+  rng = key if isinstance(key, np.random.Generator) else np.random.default_rng(key)
+  shape = (ns, int(num_kpts), ng, int(num_bands))
+  dev = torch.device('cuda', torch.cuda.current_device())
+  return {'w_re': torch.from_numpy(rng.random(shape)).to(dev),
+          'w_im': torch.from_numpy(rng.random(shape)).to(dev)}
+
+
+def coeff(pw_param: Union[dict, tuple, list], freq_mask, sharding=None) -> Coefficients:
+  """jrystal/_src/pw.py:94-137: QR-orthonormalise w_re + i w_im (Cholesky-QR2 on DMMA)."""
+  del sharding
+  plan = current_plan()
+  if not np.array_equal(np.asarray(freq_mask).astype(bool), plan.mask.astype(bool)):
+    raise ValueError('freq_mask differs from the mask of the current plan')
+  if isinstance(pw_param, dict):
+    w_re, w_im = pw_param['w_re'], pw_param['w_im']
+  else:
+    w_re, w_im = pw_param
+  q, r = plan.qr_fwd(w_re, w_im)
+  return Coefficients(plan, q, r)
+
+
+def wave_grid(coeff, vol: float) -> torch.Tensor:
+  """jrystal/_src/pw.py:140-211: psi = ifftn(coeff) * N / sqrt(vol), dense."""
+  c = _as_coeff(coeff)
+  _check_vol(c.plan, vol)
+  return c.plan.wave_grid(c.q)
+
+
+def density_grid(coeff, vol: float, occupation: Optional[torch.Tensor] = None) -> torch.Tensor:
+  """jrystal/_src/pw.py:214-284: rho[s, x, y, z] = sum_kb occ |psi|^2 (fused scatter + IFFT +
+  accumulation; psi(r) never reaches global memory)."""
+  c = _as_coeff(coeff)
+  _check_vol(c.plan, vol)
+  if occupation is None:
+    raise NotImplementedError(
+      'density_grid without occupation returns M*N per-orbital densities; use '
+      'abs(wave_grid(coeff, vol))**2 for that diagnostic')
+  p = c.plan
+  occ = _occ(p, occupation)
+  return p.density(c.q, occ)
+
+
+def density_grid_reciprocal(coeff, vol: float, occupation=None) -> torch.Tensor:
+  """jrystal/_src/pw.py:287-334: fftn(density_grid)."""
+  c = _as_coeff(coeff)
+  return c.plan.density_reciprocal(density_grid(c, vol, occupation))
+
+
+def _occ(plan, occupation):
+  if not isinstance(occupation, torch.Tensor):
+    occupation = torch.as_tensor(np.asarray(occupation), dtype=torch.float64)
+  occupation = occupation.to(plan.tdev, torch.float64).contiguous()
+  if tuple(occupation.shape) != (plan.ns, plan.nk, plan.nb):
+    # pw.py:279-283
+    raise ValueError(
+      f'Occupation should have shape {(plan.ns, plan.nk, plan.nb)}, got {tuple(occupation.shape)}')
+  return occupation
+
+
+def _check_vol(plan, vol):
+  if abs(float(vol) - plan.vol) > 1e-9 * plan.vol:
+    raise ValueError(f'vol={vol} differs from the cell volume of the current plan ({plan.vol})')

@@ -17,6 +17,9 @@ E_TOL = 1e-10
 G_TOL = 1e-8
 
 CASES = {
+  # cubic grids with radix-3 lengths and several band groups (fused y+x kernels, chunked density)
+  'si_48_cubic': dict(name='si', grid=48, kgrid=[1, 1, 2], mask='spherical', cutoff=15, nb=21),
+  'diamond_12': dict(name='diamond', grid=12, kgrid=[2, 1, 1], mask='spherical', cutoff=10, nb=5),
   # the reference's own test fixture: diamond, grid [7,8,9], cubic mask (pw_test.py:33-34)
   'diamond_789_cubic': dict(name='diamond', grid=[7, 8, 9], kgrid=[2, 2, 1], mask='cubic',
                             cutoff=None, nb=12),
@@ -146,7 +149,10 @@ def test_hpsi_and_band_trace(cuda_device, case):
 
 @pytest.mark.parametrize('case', list(CASES))
 @pytest.mark.parametrize('batch_groups', [0, 1, 3])
-def test_energy_and_grad(cuda_device, case, batch_groups):
+@pytest.mark.parametrize('fuse', [True, False])
+def test_energy_and_grad(cuda_device, case, batch_groups, fuse, monkeypatch):
+  # fuse=False forces the single-pass pencil kernels (the path non-cubic grids and 128^3 take)
+  monkeypatch.setenv('JRB_NO_FUSE', '0' if fuse else '1')
   s, plan, w_re, w_im, occ = _setup(case, batch_groups=batch_groups)
   ref = rp.energy_and_grad(s, w_re, w_im, occ, occ_grad=True)
   occ_d = to_dev(occ)

@@ -95,3 +95,24 @@ def test_gloo_world2_density_allreduce(tmp_path):
   for r in range(2):
     np.testing.assert_allclose(np.load(tmp_path / f'rho{r}.npy'), rho, rtol=1e-13, atol=1e-15)
     assert abs(np.load(tmp_path / f'ekin{r}.npy')[0] - e_kin) < 1e-12 * abs(e_kin)
+
+
+def test_kinetic_operator_mirrors_oracle():
+  from jrystal_b200 import kinetic
+  cell, _, _ = structures.load('diamond')
+  g = grid.g_vectors(cell, [7, 8, 9])
+  k = grid.k_vectors(cell, [2, 1, 1])
+  np.testing.assert_allclose(kinetic.kinetic_operator(g, k), rp.kinetic_operator(g, k).numpy(),
+                             rtol=1e-14)
+  np.testing.assert_allclose(kinetic.kinetic_operator(g), rp.kinetic_operator(g).numpy(),
+                             rtol=1e-14)
+
+
+def test_use_plan_context():
+  from jrystal_b200 import context
+  with pytest.raises(RuntimeError):
+    context.current_plan()
+  with context.use_plan('sentinel') as p:
+    assert p == 'sentinel' and context.current_plan() == 'sentinel'
+  with pytest.raises(RuntimeError):
+    context.current_plan()
