@@ -1,6 +1,8 @@
 // extern "C" entry points declared in include/jrystal_b200.h: argument checks and
 // composition of the kernels into the reference's operations.
+#include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <string>
 
 #include "plan.h"
@@ -158,6 +160,7 @@ extern "C" int jrb_eval_begin(jrb_plan* p, const double* w_re, const double* w_i
   int rc = enter(p);
   if (rc) return rc;
   REQUIRE(w_re && w_im && occ && rho && e_kin, "null array");
+  JRB_CUDA(cudaMemsetAsync(p->d_scal + 32, 0, sizeof(double), S(st)));  // Cholesky failure flag
   if ((rc = launch_qr_fwd(p, w_re, w_im, p->d_q, p->d_r, S(st)))) return rc;
   if ((rc = launch_density(p, p->d_q, occ, rho, S(st)))) return rc;
   if ((rc = launch_kinetic(p, p->d_q, p->d_tkb, S(st)))) return rc;
@@ -202,8 +205,22 @@ static int ensure_host_buffers(jrb_plan* p) {
   JRB_CUDA(cudaMalloc(&p->d_occ, no * sizeof(double)));
   JRB_CUDA(cudaMalloc(&p->d_rho, (size_t)p->ns * p->ngrid * sizeof(double)));
   JRB_CUDA(cudaMalloc(&p->d_en, 8 * sizeof(double)));
+  JRB_CUDA(cudaStreamCreateWithFlags(&p->h2d_stream, cudaStreamNonBlocking));
+  JRB_CUDA(cudaStreamCreateWithFlags(&p->d2h_stream, cudaStreamNonBlocking));
+  for (int i = 0; i < 16; ++i) {
+    JRB_CUDA(cudaEventCreateWithFlags(&p->ev_in[i], cudaEventDisableTiming));
+    JRB_CUDA(cudaEventCreateWithFlags(&p->ev_out[i], cudaEventDisableTiming));
+  }
   p->ws_bytes += (int64_t)((4 * nw + no + 8) * sizeof(double) + (size_t)p->ns * p->ngrid * 8);
   return 0;
+}
+
+// k-point chunks of the host path: copies of chunk c+1 overlap the kernels of chunk c
+static int host_chunks(const jrb_plan* p) {
+  int n = (p->ns == 1 && p->nk >= 4) ? std::min(8, p->nk / 2) : 1;
+  if (const char* env = std::getenv("JRB_HOST_CHUNKS")) n = std::atoi(env);
+  if (p->ns != 1) n = 1;
+  return std::max(1, std::min(std::min(n, 16), p->nk));
 }
 
 extern "C" int jrb_energy_grad_host(jrb_plan* p, const double* w_re_h, const double* w_im_h,
@@ -214,23 +231,70 @@ extern "C" int jrb_energy_grad_host(jrb_plan* p, const double* w_re_h, const dou
   REQUIRE(w_re_h && w_im_h && occ_h && energies_h && g_re_h && g_im_h, "null array");
   if ((rc = ensure_host_buffers(p))) return rc;
   cudaStream_t st = p->own_stream;
-  const size_t nw = (size_t)p->ns * p->nk * p->ng * p->nb * sizeof(double);
   const size_t no = (size_t)p->ns * p->nk * p->nb * sizeof(double);
+  const size_t per_k = (size_t)p->ng * p->nb;  // parameters per k-point
   double* rho = p->d_rho;
-  JRB_CUDA(cudaMemcpyAsync(p->d_wre, w_re_h, nw, cudaMemcpyHostToDevice, st));
-  JRB_CUDA(cudaMemcpyAsync(p->d_wim, w_im_h, nw, cudaMemcpyHostToDevice, st));
+  double* e_kin = p->d_en + 4;
+  const int nch = host_chunks(p);
   JRB_CUDA(cudaMemcpyAsync(p->d_occ, occ_h, no, cudaMemcpyHostToDevice, st));
-  if ((rc = jrb_eval_begin(p, p->d_wre, p->d_wim, p->d_occ, rho, p->d_en + 4, st))) return rc;
-  if ((rc = jrb_eval_finish(p, p->d_occ, rho, p->d_en + 4, xc_id, p->d_en, p->d_gre, p->d_gim,
-                            nullptr, st)))
-    return rc;
+  if (nch == 1) {
+    const size_t nw = (size_t)p->ns * p->nk * per_k * sizeof(double);
+    JRB_CUDA(cudaMemcpyAsync(p->d_wre, w_re_h, nw, cudaMemcpyHostToDevice, st));
+    JRB_CUDA(cudaMemcpyAsync(p->d_wim, w_im_h, nw, cudaMemcpyHostToDevice, st));
+    if ((rc = jrb_eval_begin(p, p->d_wre, p->d_wim, p->d_occ, rho, e_kin, st))) return rc;
+    if ((rc = jrb_eval_finish(p, p->d_occ, rho, e_kin, xc_id, p->d_en, p->d_gre, p->d_gim, nullptr,
+                              st)))
+      return rc;
+    JRB_CUDA(cudaMemcpyAsync(g_re_h, p->d_gre, nw, cudaMemcpyDeviceToHost, st));
+    JRB_CUDA(cudaMemcpyAsync(g_im_h, p->d_gim, nw, cudaMemcpyDeviceToHost, st));
+  } else {
+    // forward: H2D of chunk c+1 (copy stream) under QR + density of chunk c (compute stream)
+    auto k_of = [&](int c) { return (int)((long long)c * p->nk / nch); };
+    for (int c = 0; c < nch; ++c) {
+      const size_t off = (size_t)k_of(c) * per_k, n = (size_t)(k_of(c + 1) - k_of(c)) * per_k;
+      JRB_CUDA(cudaMemcpyAsync(p->d_wre + off, w_re_h + off, n * sizeof(double),
+                               cudaMemcpyHostToDevice, p->h2d_stream));
+      JRB_CUDA(cudaMemcpyAsync(p->d_wim + off, w_im_h + off, n * sizeof(double),
+                               cudaMemcpyHostToDevice, p->h2d_stream));
+      JRB_CUDA(cudaEventRecord(p->ev_in[c], p->h2d_stream));
+    }
+    if ((rc = launch_focc(p, p->d_occ, st))) return rc;
+    JRB_CUDA(cudaMemsetAsync(p->d_scal + 32, 0, sizeof(double), st));  // Cholesky failure flag
+    JRB_CUDA(cudaMemsetAsync(rho, 0, sizeof(double) * (size_t)p->ngrid, st));
+    for (int c = 0; c < nch; ++c) {
+      const int k0 = k_of(c), k1 = k_of(c + 1);
+      JRB_CUDA(cudaStreamWaitEvent(st, p->ev_in[c], 0));
+      if ((rc = launch_qr_fwd_range(p, k0, k1 - k0, p->d_wre, p->d_wim, p->d_q, p->d_r, st))) return rc;
+      if ((rc = launch_density_krange(p, p->d_q, rho, k0, k1, st))) return rc;
+      if ((rc = launch_kinetic_range(p, k0, k1 - k0, p->d_q, p->d_tkb, st))) return rc;
+    }
+    if ((rc = launch_weighted_sum(p, p->d_tkb, p->d_occ, (int64_t)p->nk * p->nb, e_kin, st))) return rc;
+    // backward: D2H of chunk c (copy stream) under H-apply + QR adjoint of chunk c+1
+    double* grid_e = p->d_scal;
+    if ((rc = launch_grid_potential(p, rho, xc_id, 0, 7, grid_e, p->d_veff, st))) return rc;
+    for (int c = 0; c < nch; ++c) {
+      const int k0 = k_of(c), k1 = k_of(c + 1);
+      const size_t off = (size_t)k0 * per_k, n = (size_t)(k1 - k0) * per_k;
+      if ((rc = launch_hpsi_krange(p, p->d_q, p->d_veff, p->d_hq, k0, k1, st))) return rc;
+      if ((rc = launch_qr_bwd_range(p, k0, k1 - k0, p->d_q, p->d_r, p->d_hq, p->d_occ, p->d_gre,
+                                    p->d_gim, st)))
+        return rc;
+      JRB_CUDA(cudaEventRecord(p->ev_out[c], st));
+      JRB_CUDA(cudaStreamWaitEvent(p->d2h_stream, p->ev_out[c], 0));
+      JRB_CUDA(cudaMemcpyAsync(g_re_h + off, p->d_gre + off, n * sizeof(double),
+                               cudaMemcpyDeviceToHost, p->d2h_stream));
+      JRB_CUDA(cudaMemcpyAsync(g_im_h + off, p->d_gim + off, n * sizeof(double),
+                               cudaMemcpyDeviceToHost, p->d2h_stream));
+    }
+    k_pack_energies<<<1, 1, 0, st>>>(e_kin, grid_e, p->d_en);
+    JRB_CHECK_LAUNCH("k_pack_energies");
+  }
   JRB_CUDA(cudaMemcpyAsync(energies_h, p->d_en, 4 * sizeof(double), cudaMemcpyDeviceToHost, st));
-  JRB_CUDA(cudaMemcpyAsync(g_re_h, p->d_gre, nw, cudaMemcpyDeviceToHost, st));
-  JRB_CUDA(cudaMemcpyAsync(g_im_h, p->d_gim, nw, cudaMemcpyDeviceToHost, st));
   if (rho_h)
     JRB_CUDA(cudaMemcpyAsync(rho_h, rho, (size_t)p->ns * p->ngrid * sizeof(double),
                              cudaMemcpyDeviceToHost, st));
   JRB_CUDA(cudaStreamSynchronize(st));
+  if (nch > 1) JRB_CUDA(cudaStreamSynchronize(p->d2h_stream));
   int fail = 0;
   JRB_CUDA(cudaMemcpy(&fail, reinterpret_cast<int*>(p->d_scal + 32), sizeof(int),
                       cudaMemcpyDeviceToHost));

@@ -54,7 +54,8 @@ bool fused_available(int nx, int ny, int nxo, int ncol) {
     if (std::atoi(env) != 0) return false;
   if (nx != ny) return false;
   const int need = fused_smem_need(nx, nxo, ncol);
-  return need > 0 && need <= 200 * 1024;
+  // column and Y-row indices are packed in 16 bits each (fft_fused.cuh)
+  return need > 0 && need <= 200 * 1024 && ncol < 65000 && nxo * (nx + 8) < 65000;
 }
 
 // persistent CTAs of the fused kernels: one per resident slot
@@ -119,35 +120,78 @@ static PassArgs base_args(jrb_plan* p) {
   return a;
 }
 
-// rho[s] = sum_{k,b} occ |psi|^2  (jrb_density).  d_focc must hold occ / Omega per group lane.
+// Adds sum_{groups in [ga, gb)} occ |psi|^2 of spin s to rho_spin (d_focc must be current).
+static int density_groups(jrb_plan* p, const cplx* q, double* rho_spin, int s, int ga, int gb,
+                          cudaStream_t st) {
+  int rc = 0;
+  const int per_spin = p->nk * p->ngroups_per_k;
+  for (int g0 = ga; g0 < gb; g0 += p->batch_groups) {
+    PassArgs a = base_args(p);
+    a.q = q;
+    a.g0 = s * per_spin + g0;
+    a.ngroups = std::min(p->batch_groups, gb - g0);
+    a.rho = rho_spin;
+    a.tw = p->d_tw_z;
+    if ((rc = run_pass(PASS_Z_INV_SCATTER, p->nz, a, st))) return rc;
+    if (p->fused) {
+      FusedArgs f = fused_args(p, a);
+      if ((rc = run_fused(0, p->nx, f, p->fused_ctas, st))) return rc;
+      dim3 grid((p->nx * p->ny + 31) / 32, p->nz), block(32, 8);
+      k_rho_reduce<<<grid, block, 0, st>>>(p->d_rho_part, p->d_seg_z, p->fused_ctas, f.segmax,
+                                           a.ngroups, p->nx * p->ny, p->nz, a.rho);
+      JRB_CHECK_LAUNCH("k_rho_reduce");
+      continue;
+    }
+    a.tw = p->d_tw_y;
+    if ((rc = run_pass(PASS_Y_INV, p->ny, a, st))) return rc;
+    a.tw = p->d_tw_x;
+    if ((rc = run_pass(PASS_X_DENSITY, p->nx, a, st))) return rc;
+  }
+  return 0;
+}
+
+// rho[s] = sum_{k,b} occ |psi|^2  (jrb_density).
 int launch_density(jrb_plan* p, const cplx* q, const double* occ, double* rho, cudaStream_t st) {
   int rc = launch_focc(p, occ, st);
   if (rc) return rc;
   JRB_CUDA(cudaMemsetAsync(rho, 0, sizeof(double) * (size_t)p->ns * p->ngrid, st));
   const int per_spin = p->nk * p->ngroups_per_k;
-  for (int s = 0; s < p->ns; ++s) {
-    for (int g0 = 0; g0 < per_spin; g0 += p->batch_groups) {
-      PassArgs a = base_args(p);
-      a.q = q;
-      a.g0 = s * per_spin + g0;
-      a.ngroups = std::min(p->batch_groups, per_spin - g0);
-      a.rho = rho + (size_t)s * p->ngrid;
-      a.tw = p->d_tw_z;
-      if ((rc = run_pass(PASS_Z_INV_SCATTER, p->nz, a, st))) return rc;
-      if (p->fused) {
-        FusedArgs f = fused_args(p, a);
-        if ((rc = run_fused(0, p->nx, f, p->fused_ctas, st))) return rc;
-        dim3 grid((p->nx * p->ny + 31) / 32, p->nz), block(32, 8);
-        k_rho_reduce<<<grid, block, 0, st>>>(p->d_rho_part, p->d_seg_z, p->fused_ctas * f.segmax,
-                                             p->nx * p->ny, p->nz, a.rho);
-        JRB_CHECK_LAUNCH("k_rho_reduce");
-        continue;
-      }
+  for (int s = 0; s < p->ns; ++s)
+    if ((rc = density_groups(p, q, rho + (size_t)s * p->ngrid, s, 0, per_spin, st))) return rc;
+  return 0;
+}
+
+// the k-points [k0, k1) of spin 0 only, accumulated into rho (no memset, no focc refresh)
+int launch_density_krange(jrb_plan* p, const cplx* q, double* rho, int k0, int k1, cudaStream_t st) {
+  return density_groups(p, q, rho, 0, k0 * p->ngroups_per_k, k1 * p->ngroups_per_k, st);
+}
+
+static int hpsi_groups(jrb_plan* p, const cplx* q, const double* veff_spin, cplx* hq, int s, int ga,
+                       int gb, cudaStream_t st) {
+  int rc = 0;
+  const int per_spin = p->nk * p->ngroups_per_k;
+  for (int g0 = ga; g0 < gb; g0 += p->batch_groups) {
+    PassArgs a = base_args(p);
+    a.q = q;
+    a.hq = hq;
+    a.g0 = s * per_spin + g0;
+    a.ngroups = std::min(p->batch_groups, gb - g0);
+    a.veff = veff_spin;
+    a.tw = p->d_tw_z;
+    if ((rc = run_pass(PASS_Z_INV_SCATTER, p->nz, a, st))) return rc;
+    if (p->fused) {
+      FusedArgs f = fused_args(p, a);
+      if ((rc = run_fused(1, p->nx, f, p->fused_ctas, st))) return rc;
+    } else {
       a.tw = p->d_tw_y;
       if ((rc = run_pass(PASS_Y_INV, p->ny, a, st))) return rc;
       a.tw = p->d_tw_x;
-      if ((rc = run_pass(PASS_X_DENSITY, p->nx, a, st))) return rc;
+      if ((rc = run_pass(PASS_X_VMUL, p->nx, a, st))) return rc;
+      a.tw = p->d_tw_y;
+      if ((rc = run_pass(PASS_Y_FWD, p->ny, a, st))) return rc;
     }
+    a.tw = p->d_tw_z;
+    if ((rc = run_pass(PASS_Z_FWD_GATHER, p->nz, a, st))) return rc;
   }
   return 0;
 }
@@ -156,32 +200,14 @@ int launch_density(jrb_plan* p, const cplx* q, const double* occ, double* rho, c
 int launch_hpsi(jrb_plan* p, const cplx* q, const double* veff, cplx* hq, cudaStream_t st) {
   int rc = 0;
   const int per_spin = p->nk * p->ngroups_per_k;
-  for (int s = 0; s < p->ns; ++s) {
-    for (int g0 = 0; g0 < per_spin; g0 += p->batch_groups) {
-      PassArgs a = base_args(p);
-      a.q = q;
-      a.hq = hq;
-      a.g0 = s * per_spin + g0;
-      a.ngroups = std::min(p->batch_groups, per_spin - g0);
-      a.veff = veff + (size_t)s * p->ngrid;
-      a.tw = p->d_tw_z;
-      if ((rc = run_pass(PASS_Z_INV_SCATTER, p->nz, a, st))) return rc;
-      if (p->fused) {
-        FusedArgs f = fused_args(p, a);
-        if ((rc = run_fused(1, p->nx, f, p->fused_ctas, st))) return rc;
-      } else {
-        a.tw = p->d_tw_y;
-        if ((rc = run_pass(PASS_Y_INV, p->ny, a, st))) return rc;
-        a.tw = p->d_tw_x;
-        if ((rc = run_pass(PASS_X_VMUL, p->nx, a, st))) return rc;
-        a.tw = p->d_tw_y;
-        if ((rc = run_pass(PASS_Y_FWD, p->ny, a, st))) return rc;
-      }
-      a.tw = p->d_tw_z;
-      if ((rc = run_pass(PASS_Z_FWD_GATHER, p->nz, a, st))) return rc;
-    }
-  }
+  for (int s = 0; s < p->ns; ++s)
+    if ((rc = hpsi_groups(p, q, veff + (size_t)s * p->ngrid, hq, s, 0, per_spin, st))) return rc;
   return 0;
+}
+
+int launch_hpsi_krange(jrb_plan* p, const cplx* q, const double* veff, cplx* hq, int k0, int k1,
+                       cudaStream_t st) {
+  return hpsi_groups(p, q, veff, hq, 0, k0 * p->ngroups_per_k, k1 * p->ngroups_per_k, st);
 }
 
 // Dense batched 3-D transform over (nx, ny, nz), C order; `scale` applied on the last pass.

@@ -86,35 +86,41 @@ __device__ __forceinline__ void fused_cp_wait_all() {
   asm volatile("cp.async.wait_group 0;\n" ::: "memory");
 }
 
-// Flat iterator over the (item, band) pairs of a CTA: item w = z * ngroups + gl.
-struct BandIter {
-  long long w, w_end;
-  int band, nband;
-  int z, gl;
-  __device__ __forceinline__ void set_item(const FusedArgs& a) {
-    z = (int)(w / a.ngroups);
-    gl = (int)(w % a.ngroups);
-    const int b0 = ((a.g0 + gl) % a.ngpk) * NB;
-    nband = min(NB, a.nb - b0);
-    band = 0;
-  }
-  __device__ __forceinline__ bool valid() const { return w < w_end; }
-  __device__ __forceinline__ void next(const FusedArgs& a) {
-    if (++band >= nband) {
-      ++w;
-      if (w < w_end) set_item(a);
+// Position in the flat (item, band) list of a CTA: item w = z * ngroups + gl.  Only (w, band)
+// are carried in registers; z / gl / band count are recomputed when needed.
+struct BandPos {
+  int w, band;
+};
+struct BandInfo {
+  int z, gl, nband;
+};
+__device__ __forceinline__ BandInfo band_info(const FusedArgs& a, int w) {
+  BandInfo r;
+  r.z = w / a.ngroups;
+  r.gl = w - r.z * a.ngroups;
+  const int b0 = ((a.g0 + r.gl) % a.ngpk) * NB;
+  r.nband = min(NB, a.nb - b0);
+  return r;
+}
+__device__ __forceinline__ BandPos band_next(const FusedArgs& a, BandPos p, int w_end) {
+  if (p.w < w_end) {
+    if (++p.band >= band_info(a, p.w).nband) {
+      ++p.w;
+      p.band = 0;
     }
   }
-  __device__ __forceinline__ cplx* plane(const FusedArgs& a) const {
-    return a.wa + ((long long)gl * a.m.nz + z) * a.m.ncol * NB + band;
-  }
-};
+  return p;
+}
+__device__ __forceinline__ cplx* band_plane(const FusedArgs& a, BandPos p) {
+  const BandInfo i = band_info(a, p.w);
+  return a.wa + ((long long)i.gl * a.m.nz + i.z) * a.m.ncol * NB + p.band;
+}
 
 // stage the plane columns of one band: stage[col] = A[gl][z][col][band]
 template <int NT>
-__device__ __forceinline__ void fused_stage(const FusedArgs& a, const BandIter& it, cplx* stage) {
-  if (it.valid()) {
-    const cplx* src = it.plane(a);
+__device__ __forceinline__ void fused_stage(const FusedArgs& a, BandPos p, int w_end, cplx* stage) {
+  if (p.w < w_end) {
+    const cplx* src = band_plane(a, p);
     for (int c = threadIdx.x; c < a.m.ncol; c += NT)
       fused_cp_async16(stage + c, src + (long long)c * NB);
   }
@@ -122,28 +128,41 @@ __device__ __forceinline__ void fused_stage(const FusedArgs& a, const BandIter& 
 }
 
 // y stage, inverse: staged columns of one band-plane -> Y[xo][y].  All threads call it.
+// pk: per-thread packed indices, low 16 bits = column + 1 of (x plane slot * 8 + lane, y =
+// idxA) for the first y-stage iteration, high 16 bits = Y row offset + 1 of x = idxA (x stage).
 template <int N>
 __device__ __forceinline__ void fused_y_inverse(
   const FusedArgs& a, const cplx* stage, cplx* ybuf, cplx* ex,
-  const cplx (&tw)[LineFFT<N, +1>::CB][LineFFT<N, +1>::NTW], int lane, int tj, int slot) {
+  const cplx (&tw)[LineFFT<N, +1>::CB][LineFFT<N, +1>::NTW],
+  const unsigned (&pk)[LineFFT<N, +1>::CA][LineFFT<N, +1>::RA], int lane, int tj, int slot) {
   using F = LineFFT<N, +1>;
   using C = FCfg<N>;
   const int ngx = (a.m.nxo + NB - 1) / NB;
   for (int grp = slot; grp < (ngx + C::SLOTS - 1) / C::SLOTS * C::SLOTS; grp += C::SLOTS) {
     const int xo = grp * NB + lane;
     const bool ok = grp < ngx && xo < a.m.nxo;
-    const int32_t* yc = a.m.ycol + (long long)(ok ? xo : 0) * N;
     cplx va[F::CA][F::RA];
+    if (grp == slot) {
 #pragma unroll
-    for (int i = 0; i < F::CA; ++i) {
+      for (int i = 0; i < F::CA; ++i)
 #pragma unroll
-      for (int m = 0; m < F::RA; ++m) {
-        cplx v = czero();
-        if (F::activeA(i, tj) && ok) {
-          const int col = yc[F::idxA(i, m, tj)];
-          if (col >= 0) v = stage[col];
+        for (int m = 0; m < F::RA; ++m) {
+          const int col = (int)(pk[i][m] & 0xffffu) - 1;
+          va[i][m] = col >= 0 ? stage[col] : czero();
         }
-        va[i][m] = v;
+    } else {
+      const int32_t* yc = a.m.ycol + (long long)(ok ? xo : 0) * N;
+#pragma unroll
+      for (int i = 0; i < F::CA; ++i) {
+#pragma unroll
+        for (int m = 0; m < F::RA; ++m) {
+          cplx v = czero();
+          if (F::activeA(i, tj) && ok) {
+            const int col = yc[F::idxA(i, m, tj)];
+            if (col >= 0) v = stage[col];
+          }
+          va[i][m] = v;
+        }
       }
     }
     F::template stageA_store<NB>(va, ex, tj);
@@ -185,19 +204,23 @@ k_yx_density(FusedArgs a) {
   cplx tw[F::CB][F::NTW];
   F::load_twiddles(tw, a.tw, tj);
 
-  // x-stage inputs of this thread: row of Y (or -1) for each strided x index
-  int yrow[F::CA][F::RA];
+  // packed per-thread indices (see fused_y_inverse): x-stage Y rows and y-stage columns
+  unsigned pk[F::CA][F::RA];
+  {
+    const int xo0 = slot * NB + lane;
 #pragma unroll
-  for (int i = 0; i < F::CA; ++i)
+    for (int i = 0; i < F::CA; ++i)
 #pragma unroll
-    for (int m = 0; m < F::RA; ++m) {
-      int r = -1;
-      if (F::activeA(i, tj)) {
-        const int xo = a.m.xmap[F::idxA(i, m, tj)];
-        if (xo >= 0) r = xo * C::SX;
+      for (int m = 0; m < F::RA; ++m) {
+        unsigned lo = 0, hi = 0;
+        if (F::activeA(i, tj)) {
+          const int xo = a.m.xmap[F::idxA(i, m, tj)];
+          if (xo >= 0) hi = (unsigned)(xo * C::SX + 1);
+          if (xo0 < a.m.nxo) lo = (unsigned)(a.m.ycol[(long long)xo0 * N + F::idxA(i, m, tj)] + 1);
+        }
+        pk[i][m] = lo | (hi << 16);
       }
-      yrow[i][m] = r;
-    }
+  }
   double acc[C::NR][F::CB][F::RB];
 #pragma unroll
   for (int r = 0; r < C::NR; ++r)
@@ -208,9 +231,8 @@ k_yx_density(FusedArgs a) {
 
   const long long W = (long long)a.m.nz * a.ngroups;
   const int c = blockIdx.x, G = gridDim.x;
-  BandIter cur, nxt;
-  cur.w = c * W / G;
-  cur.w_end = (c + 1) * W / G;
+  BandPos cur{(int)(c * W / G), 0};
+  const int w_end = (int)((c + 1) * W / G);
   int seg = 0;
   auto flush = [&](int z) {
     double* out = a.rho_part + ((long long)c * a.segmax + seg) * N * N;
@@ -229,32 +251,32 @@ k_yx_density(FusedArgs a) {
     ++seg;
   };
 
-  if (cur.valid()) {
-    cur.set_item(a);
-    nxt = cur;
+  if (cur.w < w_end) {
     // prologue: stage band 0, run its y stage, stage band 1
-    fused_stage<C::NT>(a, cur, stage0);
+    fused_stage<C::NT>(a, cur, w_end, stage0);
     fused_cp_wait_all();
     __syncthreads();
-    nxt.next(a);
-    fused_stage<C::NT>(a, nxt, stage0 + ssz);
-    fused_y_inverse<N>(a, stage0, ybuf0, ex, tw, lane, tj, slot);
+    fused_stage<C::NT>(a, band_next(a, cur, w_end), w_end, stage0 + ssz);
+    fused_y_inverse<N>(a, stage0, ybuf0, ex, tw, pk, lane, tj, slot);
     int par = 0;  // parity of the current band: it lives in Y[par]
-    int cur_z = cur.z;
-    while (cur.valid()) {
+    int cur_z = band_info(a, cur.w).z;
+    double fw_next = a.focc[(long long)(a.g0 + band_info(a, cur.w).gl) * NB + cur.band];
+    while (cur.w < w_end) {
       // Y[par] complete (y stage of the current band by every slot); staged data of the next
       // band landed and visible; everybody is done with Y[par ^ 1] and stage[par]
       fused_cp_wait_all();
       __syncthreads();
-      // nxt = band b+1 (staged in stage[par ^ 1]); prefetch band b+2 into stage[par]
-      BandIter nn = nxt;
-      if (nn.valid()) nn.next(a);
-      fused_stage<C::NT>(a, nn, stage0 + par * ssz);
-      if (cur.z != cur_z) {
+      // band b+1 is staged in stage[par ^ 1]; prefetch band b+2 into stage[par]
+      const BandPos nxt = band_next(a, cur, w_end);
+      fused_stage<C::NT>(a, band_next(a, nxt, w_end), w_end, stage0 + par * ssz);
+      const int z = band_info(a, cur.w).z;
+      if (z != cur_z) {
         flush(cur_z);
-        cur_z = cur.z;
+        cur_z = z;
       }
-      const double fw = a.focc[(long long)(a.g0 + cur.gl) * NB + cur.band];
+      const double fw = fw_next;
+      if (nxt.w < w_end)
+        fw_next = a.focc[(long long)(a.g0 + band_info(a, nxt.w).gl) * NB + nxt.band];
       const cplx* ybuf = ybuf0 + par * ysz;
 #pragma unroll
       for (int r = 0; r < C::NR; ++r) {
@@ -265,7 +287,7 @@ k_yx_density(FusedArgs a) {
         for (int i = 0; i < F::CA; ++i)
 #pragma unroll
           for (int m = 0; m < F::RA; ++m)
-            va[i][m] = (yrow[i][m] >= 0 && ok) ? ybuf[yrow[i][m] + y] : czero();
+            va[i][m] = ((pk[i][m] >> 16) != 0 && ok) ? ybuf[(int)(pk[i][m] >> 16) - 1 + y] : czero();
         F::template stageA_store<NB>(va, ex, tj);
         slot_barrier<N>(slot);
         cplx vb[F::CB][F::RB];
@@ -279,11 +301,10 @@ k_yx_density(FusedArgs a) {
         slot_barrier<N>(slot);
       }
       // y stage of the next band into the other Y buffer
-      if (nxt.valid())
-        fused_y_inverse<N>(a, stage0 + (par ^ 1) * ssz, ybuf0 + (par ^ 1) * ysz, ex, tw, lane, tj,
-                           slot);
+      if (nxt.w < w_end)
+        fused_y_inverse<N>(a, stage0 + (par ^ 1) * ssz, ybuf0 + (par ^ 1) * ysz, ex, tw, pk, lane,
+                           tj, slot);
       cur = nxt;
-      nxt = nn;
       par ^= 1;
     }
     fused_cp_wait_all();
@@ -296,14 +317,18 @@ k_yx_density(FusedArgs a) {
 // rho[x][y][z] += sum of the partial planes tagged z, in slot order (deterministic)
 // grid: (ceil(nx*ny / 32), nz), block 32 x 8: thread (tx, ty) sums slots ty, ty+8, ...
 static __global__ void __launch_bounds__(256)
-k_rho_reduce(const double* __restrict__ part, const int* __restrict__ seg_z, int nslots, int nxy,
-             int nz, double* __restrict__ rho) {
+k_rho_reduce(const double* __restrict__ part, const int* __restrict__ seg_z, int nctas, int segmax,
+             int ngroups, int nxy, int nz, double* __restrict__ rho) {
   __shared__ double sh[8][33];
   const int xy = blockIdx.x * 32 + threadIdx.x;
   const int z = blockIdx.y;
+  // CTA c covers items [c W / G, (c + 1) W / G), W = nz ngroups: candidates for plane z
+  const long long W = (long long)nz * ngroups;
+  const int c_lo = max(0, (int)(((long long)z * ngroups * nctas) / W) - 1);
+  const int c_hi = min(nctas - 1, (int)((((long long)z + 1) * ngroups * nctas) / W) + 1);
   double s = 0.0;
   if (xy < nxy)
-    for (int k = threadIdx.y; k < nslots; k += 8)
+    for (int k = c_lo * segmax + threadIdx.y; k < (c_hi + 1) * segmax; k += 8)
       if (seg_z[k] == z) s += part[(long long)k * nxy + xy];
   sh[threadIdx.y][threadIdx.x] = s;
   __syncthreads();
@@ -337,35 +362,40 @@ k_yx_vmul(FusedArgs a) {
   const int slot = t / C::SLOT_THREADS;
   cplx* ex = exbase + (size_t)slot * N * NB + lane;
   const long long nyz = (long long)N * a.m.nz;
+  // equal radices: the forward twiddles are the conjugates of the inverse ones -> one register set
+  constexpr bool SHARE_TW = LinePlan<N>::r1 == LinePlan<N>::r2;
   cplx twi[FI::CB][FI::NTW];
-  cplx twf[FF::CB][FF::NTW];
+  cplx twf[SHARE_TW ? 1 : FF::CB][SHARE_TW ? 1 : FF::NTW];
   FI::load_twiddles(twi, a.tw, tj);
-  FF::load_twiddles(twf, a.tw, tj);
+  if constexpr (!SHARE_TW) FF::load_twiddles(twf, a.tw, tj);
+  auto fwd_stageB = [&](cplx (&v)[FF::CB][FF::RB]) {
+    if constexpr (SHARE_TW) {
+      FF::template stageB_load<NB, true>(v, ex, twi, tj);
+    } else {
+      FF::template stageB_load<NB, false>(v, ex, twf, tj);
+    }
+  };
 
-  int yrow[FI::CA][FI::RA];
+  // packed per-thread indices (see fused_y_inverse): x-stage Y rows and y-stage columns
+  unsigned pk[FI::CA][FI::RA];
+  {
+    const int xo0 = slot * NB + lane;
 #pragma unroll
-  for (int i = 0; i < FI::CA; ++i)
+    for (int i = 0; i < FI::CA; ++i)
 #pragma unroll
-    for (int m = 0; m < FI::RA; ++m) {
-      int r = -1;
-      if (FI::activeA(i, tj)) {
-        const int xo = a.m.xmap[FI::idxA(i, m, tj)];
-        if (xo >= 0) r = xo * C::SX;
+      for (int m = 0; m < FI::RA; ++m) {
+        unsigned lo = 0, hi = 0;
+        if (FI::activeA(i, tj)) {
+          const int xo = a.m.xmap[FI::idxA(i, m, tj)];
+          if (xo >= 0) hi = (unsigned)(xo * C::SX + 1);
+          if (xo0 < a.m.nxo) lo = (unsigned)(a.m.ycol[(long long)xo0 * N + FI::idxA(i, m, tj)] + 1);
+        }
+        pk[i][m] = lo | (hi << 16);
       }
-      yrow[i][m] = r;
-    }
-  int orow[FF::CB][FF::RB];
-#pragma unroll
-  for (int i = 0; i < FF::CB; ++i)
-#pragma unroll
-    for (int m = 0; m < FF::RB; ++m) {
-      int r = -1;
-      if (FF::activeB(i, tj)) {
-        const int xo = a.m.xmap[FF::idxB(i, m, tj)];
-        if (xo >= 0) r = xo * C::SX;
-      }
-      orow[i][m] = r;
-    }
+  }
+  // forward stage-B outputs land on the same x indices as the inverse stage-A inputs
+  // (idxB of the forward plan == idxA of the inverse plan), so pk's Y-row field serves both
+  static_assert(FF::CB == FI::CA && FF::RB == FI::RA, "x index sets of inverse-in / forward-out");
   // v_eff(x, y, z) / N at the points this thread owns in the x stage (reloaded when z changes)
   double vv[C::NR][FI::CB][FI::RB];
   auto load_v = [&](int z) {
@@ -387,29 +417,25 @@ k_yx_vmul(FusedArgs a) {
   const int ngx = (a.m.nxo + NB - 1) / NB;
   const long long W = (long long)a.m.nz * a.ngroups;
   const int c = blockIdx.x, G = gridDim.x;
-  BandIter cur, nxt;
-  cur.w = c * W / G;
-  cur.w_end = (c + 1) * W / G;
-  if (!cur.valid()) return;
-  cur.set_item(a);
-  nxt = cur;
-  fused_stage<C::NT>(a, cur, stage0);
+  BandPos cur{(int)(c * W / G), 0};
+  const int w_end = (int)((c + 1) * W / G);
+  if (cur.w >= w_end) return;
+  fused_stage<C::NT>(a, cur, w_end, stage0);
   fused_cp_wait_all();
   __syncthreads();
-  nxt.next(a);
-  fused_stage<C::NT>(a, nxt, stage0 + ssz);
-  fused_y_inverse<N>(a, stage0, ybuf0, ex, twi, lane, tj, slot);
+  fused_stage<C::NT>(a, band_next(a, cur, w_end), w_end, stage0 + ssz);
+  fused_y_inverse<N>(a, stage0, ybuf0, ex, twi, pk, lane, tj, slot);
   int par = 0;
-  int cur_z = cur.z;
+  int cur_z = band_info(a, cur.w).z;
   load_v(cur_z);
-  while (cur.valid()) {
+  while (cur.w < w_end) {
     fused_cp_wait_all();
     __syncthreads();
-    BandIter nn = nxt;
-    if (nn.valid()) nn.next(a);
-    fused_stage<C::NT>(a, nn, stage0 + par * ssz);
-    if (cur.z != cur_z) {
-      cur_z = cur.z;
+    const BandPos nxt = band_next(a, cur, w_end);
+    fused_stage<C::NT>(a, band_next(a, nxt, w_end), w_end, stage0 + par * ssz);
+    const int z = band_info(a, cur.w).z;
+    if (z != cur_z) {
+      cur_z = z;
       load_v(cur_z);
     }
     cplx* ybuf = ybuf0 + par * ysz;
@@ -423,7 +449,7 @@ k_yx_vmul(FusedArgs a) {
       for (int i = 0; i < FI::CA; ++i)
 #pragma unroll
         for (int m = 0; m < FI::RA; ++m)
-          va[i][m] = (yrow[i][m] >= 0 && ok) ? ybuf[yrow[i][m] + y] : czero();
+          va[i][m] = ((pk[i][m] >> 16) != 0 && ok) ? ybuf[(int)(pk[i][m] >> 16) - 1 + y] : czero();
       FI::template stageA_store<NB>(va, ex, tj);
       slot_barrier<N>(slot);
       cplx vb[FI::CB][FI::RB];
@@ -436,19 +462,19 @@ k_yx_vmul(FusedArgs a) {
       FF::template stageA_store<NB>(vb, ex, tj);
       slot_barrier<N>(slot);
       cplx vc[FF::CB][FF::RB];
-      FF::template stageB_load<NB>(vc, ex, twf, tj);
+      fwd_stageB(vc);
       if (ok) {
 #pragma unroll
         for (int i = 0; i < FF::CB; ++i)
 #pragma unroll
           for (int m = 0; m < FF::RB; ++m)
-            if (orow[i][m] >= 0) ybuf[orow[i][m] + y] = vc[i][m];
+            if ((pk[i][m] >> 16) != 0) ybuf[(int)(pk[i][m] >> 16) - 1 + y] = vc[i][m];
       }
       slot_barrier<N>(slot);
     }
     __syncthreads();
     // y stage, forward: Y -> occupied columns of A (global, in place)
-    cplx* dst = cur.plane(a);
+    cplx* dst = band_plane(a, cur);
     for (int grp = slot; grp < (ngx + C::SLOTS - 1) / C::SLOTS * C::SLOTS; grp += C::SLOTS) {
       const int xo = grp * NB + lane;
       const bool ok = grp < ngx && xo < a.m.nxo;
@@ -462,7 +488,7 @@ k_yx_vmul(FusedArgs a) {
       FF::template stageA_store<NB>(va, ex, tj);
       slot_barrier<N>(slot);
       cplx vb[FF::CB][FF::RB];
-      FF::template stageB_load<NB>(vb, ex, twf, tj);
+      fwd_stageB(vb);
       if (ok) {
         const int32_t* yc = a.m.ycol + (long long)xo * N;
 #pragma unroll
@@ -478,11 +504,10 @@ k_yx_vmul(FusedArgs a) {
       }
       slot_barrier<N>(slot);
     }
-    if (nxt.valid())
-      fused_y_inverse<N>(a, stage0 + (par ^ 1) * ssz, ybuf0 + (par ^ 1) * ysz, ex, twi, lane, tj,
-                         slot);
+    if (nxt.w < w_end)
+      fused_y_inverse<N>(a, stage0 + (par ^ 1) * ssz, ybuf0 + (par ^ 1) * ysz, ex, twi, pk, lane,
+                         tj, slot);
     cur = nxt;
-    nxt = nn;
     par ^= 1;
   }
   fused_cp_wait_all();

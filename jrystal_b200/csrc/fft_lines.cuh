@@ -126,7 +126,9 @@ struct LineFFT {
 
   // Stage B: gather from the exchange buffer, twiddle, butterflies; vb[i][m] then holds
   // X[idxB(i, m)].
-  template <int S>
+  // CONJ_TW: multiply by the conjugates of `tw` (lets a forward transform reuse the inverse
+  // transform's twiddle registers when both stages have the same radix).
+  template <int S, bool CONJ_TW = false>
   static JRB_HD void stageB_load(cplx (&vb)[CB][RB], const cplx* sm,
                                  const cplx (&tw)[CB][NTW], int tj) {
 #pragma unroll
@@ -138,6 +140,8 @@ struct LineFFT {
         for (int m = 1; m < RB; ++m) {
           if constexpr (RA == 1) {
             vb[i][m] = sm[(jB + m * RA) * S];
+          } else if constexpr (CONJ_TW) {
+            vb[i][m] = cmul(sm[(jB + m * RA) * S], cconj(tw[i][m - 1]));
           } else {
             vb[i][m] = cmul(sm[(jB + m * RA) * S], tw[i][m - 1]);
           }

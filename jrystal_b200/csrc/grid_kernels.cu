@@ -301,10 +301,10 @@ int launch_density_reciprocal(jrb_plan* p, const double* rho, cplx* rho_hat, cud
 template <int MODE>
 __global__ void __launch_bounds__(256)
 k_sphere_reduce(const cplx* __restrict__ q, const cplx* __restrict__ hq,
-                const double* __restrict__ gk2, long long ng, int nb, int nk,
+                const double* __restrict__ gk2, long long ng, int nb, int nk, int sk0,
                 double* __restrict__ out) {
   const int b = blockIdx.x * 32 + threadIdx.x;
-  const int sk = blockIdx.y;
+  const int sk = sk0 + blockIdx.y;
   const int k = sk % nk;
   double acc = 0.0;
   if (b < nb) {
@@ -331,16 +331,21 @@ k_sphere_reduce(const cplx* __restrict__ q, const cplx* __restrict__ hq,
   }
 }
 
-int launch_kinetic(jrb_plan* p, const cplx* q, double* t_skb, cudaStream_t st) {
-  dim3 grid((p->nb + 31) / 32, p->ns * p->nk), block(32, 8);
-  k_sphere_reduce<0><<<grid, block, 0, st>>>(q, nullptr, p->d_gk2, p->ng, p->nb, p->nk, t_skb);
+int launch_kinetic_range(jrb_plan* p, int sk0, int nsk, const cplx* q, double* t_skb,
+                         cudaStream_t st) {
+  dim3 grid((p->nb + 31) / 32, nsk), block(32, 8);
+  k_sphere_reduce<0><<<grid, block, 0, st>>>(q, nullptr, p->d_gk2, p->ng, p->nb, p->nk, sk0, t_skb);
   JRB_CHECK_LAUNCH("k_sphere_reduce<kinetic>");
   return 0;
 }
 
+int launch_kinetic(jrb_plan* p, const cplx* q, double* t_skb, cudaStream_t st) {
+  return launch_kinetic_range(p, 0, p->ns * p->nk, q, t_skb, st);
+}
+
 int launch_band_expect(jrb_plan* p, const cplx* q, const cplx* hq, double* eps, cudaStream_t st) {
   dim3 grid((p->nb + 31) / 32, p->ns * p->nk), block(32, 8);
-  k_sphere_reduce<1><<<grid, block, 0, st>>>(q, hq, p->d_gk2, p->ng, p->nb, p->nk, eps);
+  k_sphere_reduce<1><<<grid, block, 0, st>>>(q, hq, p->d_gk2, p->ng, p->nb, p->nk, 0, eps);
   JRB_CHECK_LAUNCH("k_sphere_reduce<expect>");
   return 0;
 }

@@ -118,6 +118,12 @@ extern "C" int jrb_plan_destroy(jrb_plan* p) {
   for (void* q : ptrs)
     if (q) cudaFree(q);
   if (p->own_stream) cudaStreamDestroy(p->own_stream);
+  if (p->h2d_stream) cudaStreamDestroy(p->h2d_stream);
+  if (p->d2h_stream) cudaStreamDestroy(p->d2h_stream);
+  for (int i = 0; i < 16; ++i) {
+    if (p->ev_in[i]) cudaEventDestroy(p->ev_in[i]);
+    if (p->ev_out[i]) cudaEventDestroy(p->ev_out[i]);
+  }
   delete p;
   return 0;
 }
@@ -296,8 +302,8 @@ extern "C" int jrb_plan_create(const jrb_plan_desc* d, jrb_plan** out) {
   TRY(dev_alloc(&p->d_tmp, nsphere, &tot));
   TRY(dev_alloc(&p->d_r, nsmall, &tot));
   TRY(dev_alloc(&p->d_rinv, nsmall, &tot));
-  TRY(dev_alloc(&p->d_small, nsmall * 4, &tot));
-  TRY(dev_alloc(&p->d_gpart, nsmall * (size_t)qr_gram_chunks(p), &tot));
+  TRY(dev_alloc(&p->d_small, nsmall * 5, &tot));
+  TRY(dev_alloc(&p->d_gpart, (size_t)p->nb * p->nb * (size_t)qr_gram_partial_mats(p), &tot));
   TRY(dev_alloc(&p->d_tkb, (size_t)p->ns * p->nk * p->nb, &tot));
   TRY(dev_alloc(&p->d_eps, (size_t)p->ns * p->nk * p->nb, &tot));
   TRY(dev_alloc(&p->d_scal, 64, &tot));

@@ -73,11 +73,12 @@ struct jrb_plan {
   int natoms;
   // evaluation work space (Q, R, R^-1, HQ, W-sized temp)
   jrb::cplx *d_q, *d_hq, *d_tmp;
-  jrb::cplx *d_r, *d_rinv, *d_small;  // [ns*nk][nb][nb] each (d_small: 4 of them)
+  jrb::cplx *d_r, *d_rinv, *d_small;  // [ns*nk][nb][nb] each (d_small: 5 of them)
   jrb::cplx* d_gpart;                 // [chunks][ns*nk][nb][nb] split-K Gram partials
   double *d_tkb, *d_eps;              // [ns*nk*nb]
   double* d_scal;                     // small device scalars
-  cudaStream_t own_stream;
+  cudaStream_t own_stream, h2d_stream, d2h_stream;
+  cudaEvent_t ev_in[16], ev_out[16];  // per k-chunk events of jrb_energy_grad_host
   // host staging for jrb_energy_grad_host
   double *d_wre, *d_wim, *d_gre, *d_gim, *d_occ, *d_rho, *d_en;
   int64_t ws_bytes;
@@ -88,6 +89,11 @@ namespace jrb {
 // fft_passes_*.cu : pencil passes, dispatched on the axis length
 int launch_density(jrb_plan* p, const cplx* q, const double* occ, double* rho, cudaStream_t st);
 int launch_hpsi(jrb_plan* p, const cplx* q, const double* veff, cplx* hq, cudaStream_t st);
+int launch_density_krange(jrb_plan* p, const cplx* q, double* rho, int k0, int k1, cudaStream_t st);
+int launch_hpsi_krange(jrb_plan* p, const cplx* q, const double* veff, cplx* hq, int k0, int k1,
+                       cudaStream_t st);
+int launch_kinetic_range(jrb_plan* p, int sk0, int nsk, const cplx* q, double* t_skb,
+                         cudaStream_t st);
 int launch_fft3d_dense(jrb_plan* p, const cplx* in, cplx* out, int dir, int64_t batch,
                        double scale, cudaStream_t st);
 bool line_length_supported(int n);
@@ -109,7 +115,12 @@ int launch_squeeze(jrb_plan* p, const cplx* dense, cplx* q, cudaStream_t st);
 int launch_focc(jrb_plan* p, const double* occ, cudaStream_t st);
 
 // qr.cu
-int qr_gram_chunks(const jrb_plan* p);
+int qr_gram_partial_mats(const jrb_plan* p);
+int launch_qr_fwd_range(jrb_plan* p, int sk0, int nsk, const double* w_re, const double* w_im,
+                        cplx* q, cplx* r, cudaStream_t st);
+int launch_qr_bwd_range(jrb_plan* p, int sk0, int nsk, const cplx* q, const cplx* r,
+                        const cplx* gq, const double* occ, double* g_re, double* g_im,
+                        cudaStream_t st);
 int launch_qr_fwd(jrb_plan* p, const double* w_re, const double* w_im, cplx* q, cplx* r,
                   cudaStream_t st);
 int launch_hamiltonian_matrix(jrb_plan* p, const cplx* q, const cplx* hq, cplx* h, cudaStream_t st);

@@ -23,221 +23,234 @@
 namespace jrb {
 
 // ---------------------------------------------------------------------------------------
-// Small (nb x nb) per-(spin,k) work: one CTA each, operating in global/L2 memory.
+// Small (nb x nb) per-(spin,k) algebra.  Everything that is element-parallel runs on a
+// (tiles, nsk) grid; only the Cholesky recurrence is one CTA per (spin,k), blocked so that the
+// active 32-column panel lives in shared memory.
 __device__ __forceinline__ cplx cmulc(cplx a, cplx b) {  // a * conj(b)
   return cmake(a.x * b.x + a.y * b.y, a.y * b.x - a.x * b.y);
 }
 
-// S = sum_chunks partial; in-place Cholesky S = L L^H; R = L^H; Rinv = R^-1.
-// If r_prev != nullptr (second pass): r_out = R * r_prev, rinv_out = rinv_prev * Rinv.
-__global__ void __launch_bounds__(1024)
-k_chol_inv(const cplx* __restrict__ partial, int nchunks, int nb, cplx* __restrict__ S,
-           cplx* __restrict__ Rt, cplx* __restrict__ Rit, const cplx* __restrict__ r_prev,
-           const cplx* __restrict__ rinv_prev, cplx* __restrict__ r_out,
-           cplx* __restrict__ rinv_out, cplx* __restrict__ scratch, int* __restrict__ fail_flag) {
-  const int sk = blockIdx.x, nsk = gridDim.x;
+constexpr int SMALL_T = 256;  // threads of the element-parallel kernels
+constexpr int CHOL_PB = 32;   // Cholesky panel width
+constexpr int CHOL_KC = 16;   // depth of one staged slice of the left-looking update
+constexpr int CHOL_T = 512;
+
+// S[sk] = sum over chunks of the Gram partials (upper blocks), mirrored as Hermitian.
+// grid: (ceil(nb^2 / 256), nsk)
+__global__ void __launch_bounds__(SMALL_T)
+k_gram_reduce(const cplx* __restrict__ partial, int nchunks, int nb, cplx* __restrict__ S) {
+  const int sk = blockIdx.y, nsk = gridDim.y;
   const long long nn = (long long)nb * nb;
-  S += sk * nn; Rt += sk * nn; Rit += sk * nn;
-  r_out += sk * nn; rinv_out += sk * nn; scratch += sk * nn;
-  const int tid = threadIdx.x, nt = blockDim.x;
-  // k_gram writes only the blocks on and above the block diagonal: mirror (Hermitian)
-  for (long long e = tid; e < nn; e += nt) {
-    const int i = (int)(e / nb), j = (int)(e % nb);
-    const long long src = j >= i ? e : (long long)j * nb + i;
-    cplx s = cmake(0.0, 0.0);
-    for (int c = 0; c < nchunks; ++c) {
-      const cplx v = partial[((long long)c * nsk + sk) * nn + src];
-      s.x += v.x; s.y += v.y;
-    }
-    S[e] = j >= i ? s : cconj(s);
+  const long long e = (long long)blockIdx.x * SMALL_T + threadIdx.x;
+  if (e >= nn) return;
+  const int i = (int)(e / nb), j = (int)(e % nb);
+  const long long src = j >= i ? e : (long long)j * nb + i;
+  cplx s = cmake(0.0, 0.0);
+  for (int c = 0; c < nchunks; ++c) {
+    const cplx v = partial[((long long)c * nsk + sk) * nn + src];
+    s.x += v.x; s.y += v.y;
   }
-  __syncthreads();
-  // right-looking Cholesky on the lower triangle
-  for (int j = 0; j < nb; ++j) {
-    const double djj = S[(long long)j * nb + j].x;
-    if (!(djj > 0.0)) {
-      if (tid == 0) atomicExch(fail_flag, 1);
+  S[sk * nn + e] = j >= i ? s : cconj(s);
+}
+
+// In-place blocked left-looking Cholesky S = L L^H of one Hermitian nb x nb matrix per CTA.
+// On exit the lower triangle of S holds L and Rt = L^H (upper triangular, zeros below).
+// dynamic smem: panel [nb][PB + 1] + stage [nb][KC + 1] complex
+__global__ void __launch_bounds__(CHOL_T)
+k_chol_blocked(cplx* __restrict__ S, cplx* __restrict__ Rt, int nb, int* __restrict__ fail_flag) {
+  extern __shared__ __align__(16) unsigned char smem_raw_[];
+  cplx* P = reinterpret_cast<cplx*>(smem_raw_);     // [rows][PB + 1]
+  cplx* T = P + (size_t)nb * (CHOL_PB + 1);         // [rows][KC + 1]
+  constexpr int LP = CHOL_PB + 1, LT = CHOL_KC + 1;
+  const long long nn = (long long)nb * nb;
+  S += blockIdx.x * nn;
+  Rt += blockIdx.x * nn;
+  const int tid = threadIdx.x;
+  for (int p0 = 0; p0 < nb; p0 += CHOL_PB) {
+    const int pw = min(CHOL_PB, nb - p0), rows = nb - p0;
+    // panel <- S[p0.., p0..p0+pw)
+    for (int e = tid; e < rows * pw; e += CHOL_T) {
+      const int r = e / pw, c = e % pw;
+      P[r * LP + c] = S[(long long)(p0 + r) * nb + p0 + c];
     }
-    const double d = sqrt(djj > 0.0 ? djj : 1.0);
-    __syncthreads();
-    for (int i = j + 1 + tid; i < nb; i += nt) {
-      cplx v = S[(long long)i * nb + j];
-      S[(long long)i * nb + j] = cmake(v.x / d, v.y / d);
-    }
-    if (tid == 0) S[(long long)j * nb + j] = cmake(d, 0.0);
-    __syncthreads();
-    const int m = nb - j - 1;
-    for (long long e = tid; e < (long long)m * m; e += nt) {
-      const int i = j + 1 + (int)(e / m), k = j + 1 + (int)(e % m);
-      if (k <= i) {
-        const cplx p = cmulc(S[(long long)i * nb + j], S[(long long)k * nb + j]);
-        cplx v = S[(long long)i * nb + k];
-        S[(long long)i * nb + k] = cmake(v.x - p.x, v.y - p.y);
+    // left-looking update with the finished columns k < p0, KC at a time:
+    //   P[r][c] -= sum_k L[p0 + r][k] conj(L[p0 + c][k])
+    for (int k0 = 0; k0 < p0; k0 += CHOL_KC) {
+      __syncthreads();
+      for (int e = tid; e < rows * CHOL_KC; e += CHOL_T) {
+        const int r = e / CHOL_KC, k = e % CHOL_KC;
+        T[r * LT + k] = S[(long long)(p0 + r) * nb + k0 + k];  // k0 + k < p0 (p0 multiple of KC)
       }
-    }
-    __syncthreads();
-  }
-  // R = L^H (upper), zeros below
-  for (long long e = tid; e < nn; e += nt) {
-    const int i = (int)(e / nb), j = (int)(e % nb);
-    Rt[e] = j >= i ? cconj(S[(long long)j * nb + i]) : cmake(0.0, 0.0);
-    Rit[e] = cmake(0.0, 0.0);
-  }
-  __syncthreads();
-  // Rinv by back substitution, one warp per column
-  const int warp = tid >> 5, lane = tid & 31, nwarps = nt >> 5;
-  for (int j = warp; j < nb; j += nwarps) {
-    if (lane == 0) Rit[(long long)j * nb + j] = cmake(1.0 / Rt[(long long)j * nb + j].x, 0.0);
-    __syncwarp();
-    for (int i = j - 1; i >= 0; --i) {
-      double sx = 0.0, sy = 0.0;
-      for (int k = i + 1 + lane; k <= j; k += 32) {
-        const cplx p = cmul(Rt[(long long)i * nb + k], Rit[(long long)k * nb + j]);
-        sx += p.x; sy += p.y;
-      }
+      __syncthreads();
+      for (int e = tid; e < rows * pw; e += CHOL_T) {
+        const int r = e / pw, c = e % pw;
+        if (r >= c) {
+          cplx acc = P[r * LP + c];
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-        sx += __shfl_xor_sync(0xffffffffu, sx, o);
-        sy += __shfl_xor_sync(0xffffffffu, sy, o);
-      }
-      if (lane == 0) {
-        const double rii = Rt[(long long)i * nb + i].x;
-        Rit[(long long)i * nb + j] = cmake(-sx / rii, -sy / rii);
-      }
-      __syncwarp();
-    }
-  }
-  __syncthreads();
-  if (r_prev == nullptr) {
-    for (long long e = tid; e < nn; e += nt) {
-      r_out[e] = Rt[e];
-      rinv_out[e] = Rit[e];
-    }
-  } else {
-    r_prev += sk * nn; rinv_prev += sk * nn;
-    // both products are upper triangular
-    for (long long e = tid; e < nn; e += nt) {
-      const int i = (int)(e / nb), j = (int)(e % nb);
-      cplx a = cmake(0.0, 0.0), b = cmake(0.0, 0.0);
-      if (j >= i) {
-        for (int k = i; k <= j; ++k) {
-          const cplx p = cmul(Rt[(long long)i * nb + k], r_prev[(long long)k * nb + j]);
-          a.x += p.x; a.y += p.y;
-          const cplx q = cmul(rinv_prev[(long long)i * nb + k], Rit[(long long)k * nb + j]);
-          b.x += q.x; b.y += q.y;
+          for (int k = 0; k < CHOL_KC; ++k) {
+            const cplx v = cmulc(T[r * LT + k], T[c * LT + k]);
+            acc.x -= v.x; acc.y -= v.y;
+          }
+          P[r * LP + c] = acc;
         }
       }
-      S[e] = a;       // staged (L is dead by now): r_out may alias r_prev
-      scratch[e] = b;
     }
     __syncthreads();
-    for (long long e = tid; e < nn; e += nt) {
-      r_out[e] = S[e];
-      rinv_out[e] = scratch[e];
+    // factor the panel in shared memory
+    for (int j = 0; j < pw; ++j) {
+      const double djj = P[j * LP + j].x;
+      if (!(djj > 0.0) && tid == 0) atomicExch(fail_flag, 1);
+      const double d = sqrt(djj > 0.0 ? djj : 1.0);
+      const double inv = 1.0 / d;
+      __syncthreads();
+      for (int r = j + tid; r < rows; r += CHOL_T) {
+        cplx v = P[r * LP + j];
+        P[r * LP + j] = r == j ? cmake(d, 0.0) : cmake(v.x * inv, v.y * inv);
+      }
+      __syncthreads();
+      const int wrem = pw - j - 1;
+      for (int e = tid; e < (rows - j - 1) * wrem; e += CHOL_T) {
+        const int r = j + 1 + e / wrem, c = j + 1 + e % wrem;
+        if (r >= c) {
+          const cplx v = cmulc(P[r * LP + j], P[c * LP + j]);
+          cplx u = P[r * LP + c];
+          P[r * LP + c] = cmake(u.x - v.x, u.y - v.y);
+        }
+      }
+      __syncthreads();
     }
+    // write L (lower) back and R = L^H
+    for (int e = tid; e < rows * pw; e += CHOL_T) {
+      const int r = e / pw, c = e % pw;
+      const cplx v = r >= c ? P[r * LP + c] : cmake(0.0, 0.0);
+      S[(long long)(p0 + r) * nb + p0 + c] = v;
+      Rt[(long long)(p0 + c) * nb + p0 + r] = cconj(v);
+      if (r < c) Rt[(long long)(p0 + c) * nb + p0 + r] = cmake(0.0, 0.0);
+    }
+    __syncthreads();
+  }
+  // strictly lower part of Rt that no panel touched (columns left of each panel)
+  for (long long e = tid; e < nn; e += CHOL_T) {
+    const int i = (int)(e / nb), j = (int)(e % nb);
+    if (j < i && (i / CHOL_PB) != (j / CHOL_PB)) Rt[e] = cmake(0.0, 0.0);
   }
 }
 
-// Rinv = R^-1 for an upper-triangular R supplied by the caller (jrb_qr_bwd with foreign r).
-__global__ void __launch_bounds__(1024)
-k_tri_inv(const cplx* __restrict__ R, int nb, cplx* __restrict__ Rinv) {
+// Rinv = R^-1 for upper-triangular R (complex diagonal allowed): one warp per column of the
+// inverse (columns are independent), back substitution with the column kept in shared memory.
+// grid: (ceil(nb / 8), nsk), block 256; dynamic smem: 8 * nb complex
+__global__ void __launch_bounds__(256)
+k_tri_inv_cols(const cplx* __restrict__ R, int nb, cplx* __restrict__ Rinv) {
+  extern __shared__ __align__(16) unsigned char smem_raw_[];
   const long long nn = (long long)nb * nb;
-  R += blockIdx.x * nn; Rinv += blockIdx.x * nn;
-  const int tid = threadIdx.x, nt = blockDim.x;
-  for (long long e = tid; e < nn; e += nt) Rinv[e] = cmake(0.0, 0.0);
-  __syncthreads();
-  const int warp = tid >> 5, lane = tid & 31, nwarps = nt >> 5;
-  for (int j = warp; j < nb; j += nwarps) {
+  R += blockIdx.y * nn;
+  Rinv += blockIdx.y * nn;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int j = blockIdx.x * 8 + warp;
+  if (j >= nb) return;
+  cplx* x = reinterpret_cast<cplx*>(smem_raw_) + (size_t)warp * nb;
+  {
+    const cplx d = R[(long long)j * nb + j];
+    const double n2 = d.x * d.x + d.y * d.y;
+    if (lane == 0) x[j] = cmake(d.x / n2, -d.y / n2);
+  }
+  __syncwarp();
+  for (int i = j - 1; i >= 0; --i) {
+    double sx = 0.0, sy = 0.0;
+    const cplx* row = R + (long long)i * nb;
+    for (int k = i + 1 + lane; k <= j; k += 32) {
+      const cplx v = cmul(row[k], x[k]);
+      sx += v.x; sy += v.y;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      sx += __shfl_xor_sync(0xffffffffu, sx, o);
+      sy += __shfl_xor_sync(0xffffffffu, sy, o);
+    }
     if (lane == 0) {
-      const cplx d = R[(long long)j * nb + j];
+      const cplx d = row[i];
       const double n2 = d.x * d.x + d.y * d.y;
-      Rinv[(long long)j * nb + j] = cmake(d.x / n2, -d.y / n2);
+      x[i] = cmake(-(sx * d.x + sy * d.y) / n2, -(sy * d.x - sx * d.y) / n2);  // -(s / d)
     }
     __syncwarp();
-    for (int i = j - 1; i >= 0; --i) {
-      double sx = 0.0, sy = 0.0;
-      for (int k = i + 1 + lane; k <= j; k += 32) {
-        const cplx p = cmul(R[(long long)i * nb + k], Rinv[(long long)k * nb + j]);
-        sx += p.x; sy += p.y;
-      }
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-        sx += __shfl_xor_sync(0xffffffffu, sx, o);
-        sy += __shfl_xor_sync(0xffffffffu, sy, o);
-      }
-      if (lane == 0) {
-        const cplx d = R[(long long)i * nb + i];
-        const double n2 = d.x * d.x + d.y * d.y;
-        // -(s / d)
-        Rinv[(long long)i * nb + j] =
-          cmake(-(sx * d.x + sy * d.y) / n2, -(sy * d.x - sx * d.y) / n2);
-      }
-      __syncwarp();
-    }
   }
+  for (int i = lane; i < nb; i += 32) Rinv[(long long)i * nb + j] = i <= j ? x[i] : cmake(0.0, 0.0);
 }
 
-// Backward small step: M = (sum partial) diag(f); X = -(up(M) + up(M)^H + diag Re M);
-// T1 = diag(f) Rinv^H ; T2 = X Rinv^H.
-__global__ void __launch_bounds__(1024)
-k_bwd_small(const cplx* __restrict__ partial, int nchunks, int nb, const double* __restrict__ occ,
-            const cplx* __restrict__ rinv, cplx* __restrict__ X, cplx* __restrict__ T1,
-            cplx* __restrict__ T2) {
-  const int sk = blockIdx.x, nsk = gridDim.x;
+// Second Cholesky-QR pass: r = R2 r_prev, rinv = rinv_prev R2inv (all upper triangular).
+// Outputs must not alias the inputs.   grid: (ceil(nb^2 / 256), nsk)
+__global__ void __launch_bounds__(SMALL_T)
+k_tri_compose(const cplx* __restrict__ R2, const cplx* __restrict__ R2inv,
+              const cplx* __restrict__ r_prev, const cplx* __restrict__ rinv_prev, int nb,
+              cplx* __restrict__ r_out, cplx* __restrict__ rinv_out) {
   const long long nn = (long long)nb * nb;
-  X += sk * nn; T1 += sk * nn; T2 += sk * nn; rinv += sk * nn;
+  const long long off = blockIdx.y * nn;
+  const long long e = (long long)blockIdx.x * SMALL_T + threadIdx.x;
+  if (e >= nn) return;
+  const int i = (int)(e / nb), j = (int)(e % nb);
+  cplx a = cmake(0.0, 0.0), b = cmake(0.0, 0.0);
+  if (j >= i) {
+    for (int k = i; k <= j; ++k) {
+      const cplx u = cmul(R2[off + (long long)i * nb + k], r_prev[off + (long long)k * nb + j]);
+      a.x += u.x; a.y += u.y;
+      const cplx v = cmul(rinv_prev[off + (long long)i * nb + k], R2inv[off + (long long)k * nb + j]);
+      b.x += v.x; b.y += v.y;
+    }
+  }
+  r_out[off + e] = a;
+  rinv_out[off + e] = b;
+}
+
+// Adjoint, step 1: M = (sum partial) diag(f); X = -(up(M) + up(M)^H + diag Re M);
+// T1 = diag(f) Rinv^H.   grid: (ceil(nb^2 / 256), nsk)
+__global__ void __launch_bounds__(SMALL_T)
+k_bwd_x(const cplx* __restrict__ partial, int nchunks, int nb, const double* __restrict__ occ,
+        const cplx* __restrict__ rinv, cplx* __restrict__ X, cplx* __restrict__ T1) {
+  const int sk = blockIdx.y, nsk = gridDim.y;
+  const long long nn = (long long)nb * nb;
+  const long long e = (long long)blockIdx.x * SMALL_T + threadIdx.x;
+  if (e >= nn) return;
+  const int i = (int)(e / nb), j = (int)(e % nb);
   const double* f = occ ? occ + (long long)sk * nb : nullptr;
-  const int tid = threadIdx.x, nt = blockDim.x;
-  // M staged in T2
-  for (long long e = tid; e < nn; e += nt) {
-    const int i = (int)(e / nb), j = (int)(e % nb);
-    cplx s = cmake(0.0, 0.0);
-    if (j >= i) {  // k_gram computes only the upper blocks; only up(M) and diag are used
-      for (int c = 0; c < nchunks; ++c) {
-        const cplx v = partial[((long long)c * nsk + sk) * nn + e];
-        s.x += v.x; s.y += v.y;
-      }
-    }
-    const double fj = f ? f[j] : 1.0;
-    T2[e] = cmake(s.x * fj, s.y * fj);
+  // only the upper triangle of M (written by k_gram) is needed: m = M[min][max]
+  const int a = min(i, j), b = max(i, j);
+  cplx m = cmake(0.0, 0.0);
+  for (int c = 0; c < nchunks; ++c) {
+    const cplx v = partial[((long long)c * nsk + sk) * nn + (long long)a * nb + b];
+    m.x += v.x; m.y += v.y;
   }
-  __syncthreads();
-  for (long long e = tid; e < nn; e += nt) {
-    const int i = (int)(e / nb), j = (int)(e % nb);
-    cplx x;
-    if (j > i) {
-      const cplx m = T2[(long long)i * nb + j];
-      x = cmake(-m.x, -m.y);
-    } else if (j < i) {
-      const cplx m = T2[(long long)j * nb + i];
-      x = cmake(-m.x, m.y);
-    } else {
-      x = cmake(-T2[e].x, 0.0);
-    }
-    X[e] = x;
-    // T1[i][j] = f_i conj(rinv[j][i])
-    const double fi = f ? f[i] : 1.0;
-    const cplx r = rinv[(long long)j * nb + i];
-    T1[e] = cmake(fi * r.x, -fi * r.y);
+  const double fb = f ? f[b] : 1.0;  // M = Q^H (HQ diag f): column scaling
+  m = cmake(m.x * fb, m.y * fb);
+  cplx x;
+  if (j > i) x = cmake(-m.x, -m.y);
+  else if (j < i) x = cmake(-m.x, m.y);
+  else x = cmake(-m.x, 0.0);
+  X[sk * nn + e] = x;
+  const double fi = f ? f[i] : 1.0;
+  const cplx r = rinv[sk * nn + (long long)j * nb + i];
+  T1[sk * nn + e] = cmake(fi * r.x, -fi * r.y);  // f_i conj(rinv[j][i])
+}
+
+// Adjoint, step 2: T2 = X Rinv^H  (rinv upper triangular -> k >= j).  grid as above.
+__global__ void __launch_bounds__(SMALL_T)
+k_bwd_t2(const cplx* __restrict__ X, const cplx* __restrict__ rinv, int nb, cplx* __restrict__ T2) {
+  const long long nn = (long long)nb * nb;
+  const long long off = blockIdx.y * nn;
+  const long long e = (long long)blockIdx.x * SMALL_T + threadIdx.x;
+  if (e >= nn) return;
+  const int i = (int)(e / nb), j = (int)(e % nb);
+  cplx s = cmake(0.0, 0.0);
+  for (int k = j; k < nb; ++k) {
+    const cplx v = cmulc(X[off + (long long)i * nb + k], rinv[off + (long long)j * nb + k]);
+    s.x += v.x; s.y += v.y;
   }
-  __syncthreads();
-  // T2[i][j] = sum_k X[i][k] conj(rinv[j][k]); rinv upper triangular -> k >= j
-  for (long long e = tid; e < nn; e += nt) {
-    const int i = (int)(e / nb), j = (int)(e % nb);
-    cplx s = cmake(0.0, 0.0);
-    for (int k = j; k < nb; ++k) {
-      const cplx p = cmulc(X[(long long)i * nb + k], rinv[(long long)j * nb + k]);
-      s.x += p.x; s.y += p.y;
-    }
-    T2[e] = s;
-  }
+  T2[off + e] = s;
 }
 
 // ---------------------------------------------------------------------------------------
-static int gram_chunks(const jrb_plan* p, int tiles) {
+static int gram_chunks(const jrb_plan* p, int tiles, int nsk) {
   // CTAs = upper super-tile pairs x chunks x (spin,k); two CTAs are resident per SM.  Pick the
   // chunk count (>= 256 rows each) whose last wave is fullest, preferring >= 2 waves.
-  const int nsk = p->ns * p->nk;
   const int per_chunk = nsk * (tiles * (tiles + 1) / 2);
   const int slots = 2 * 148;
   const int max_chunks = (int)std::max<int64_t>(1, std::min<int64_t>(128, p->ng / 256));
@@ -256,9 +269,12 @@ static int gram_chunks(const jrb_plan* p, int tiles) {
   return best;
 }
 
-int qr_gram_chunks(const jrb_plan* p) {
+// upper bound of chunks x nsk for sizing the partial buffer (any sub-range of (spin,k))
+int qr_gram_partial_mats(const jrb_plan* p) {
   const int tiles = (p->nb + QT - 1) / QT;
-  return gram_chunks(p, tiles);
+  int worst = 1;
+  for (int n = 1; n <= p->ns * p->nk; ++n) worst = std::max(worst, n * gram_chunks(p, tiles, n));
+  return worst;
 }
 
 template <class K>
@@ -269,12 +285,11 @@ static int opt_in_smem(K kernel, int bytes) {
 }
 
 // partial = upper blocks of A^H B, split over row chunks
-static int run_gram(jrb_plan* p, TallMat A, TallMat B, bool same, cplx* partial, int* nchunks_out,
-                    cudaStream_t st) {
+static int run_gram(jrb_plan* p, int nsk, TallMat A, TallMat B, bool same, cplx* partial,
+                    int* nchunks_out, cudaStream_t st) {
   constexpr int ST = 3;
-  const int nsk = p->ns * p->nk;
   const int tiles = (p->nb + QT - 1) / QT;
-  const int nchunks = gram_chunks(p, tiles);
+  const int nchunks = gram_chunks(p, tiles, nsk);
   long long rows = (p->ng + nchunks - 1) / nchunks;
   rows = (rows + QK - 1) / QK * QK;
   dim3 grid(tiles * (tiles + 1) / 2, nchunks, nsk);
@@ -298,11 +313,10 @@ static int run_gram(jrb_plan* p, TallMat A, TallMat B, bool same, cplx* partial,
 }
 
 template <int MODE, int NCB, bool SPLIT>
-static int run_apply_ncb(jrb_plan* p, TallMat in1, const cplx* t1, int tri1, TallMat in2,
+static int run_apply_ncb(jrb_plan* p, int nsk, TallMat in1, const cplx* t1, int tri1, TallMat in2,
                          const cplx* t2, int tri2, int nterms, double* out_a, double* out_b,
                          cudaStream_t st) {
   constexpr int ST = 2;
-  const int nsk = p->ns * p->nk;
   const int smem = ST * (QROWS * QLDA + QK * (8 * NCB + 2)) * (int)sizeof(cplx);
   static int once = opt_in_smem(k_apply<MODE, NCB, ST, SPLIT>, smem);
   if (once) return once;
@@ -316,104 +330,130 @@ static int run_apply_ncb(jrb_plan* p, TallMat in1, const cplx* t1, int tri1, Tal
 
 // column-tile width: 32 columns for few bands, else 72 (blocks past nb cost no tensor work)
 template <int MODE>
-static int run_apply(jrb_plan* p, TallMat in1, const cplx* t1, int tri1, TallMat in2,
+static int run_apply(jrb_plan* p, int nsk, TallMat in1, const cplx* t1, int tri1, TallMat in2,
                      const cplx* t2, int tri2, int nterms, double* out_a, double* out_b,
                      cudaStream_t st) {
   const int nb = p->nb;
   const bool split = in1.im != nullptr;
   if (MODE == 0 && split) {
     if (nb <= 32)
-      return run_apply_ncb<0, 4, true>(p, in1, t1, tri1, in2, t2, tri2, nterms, out_a, out_b, st);
-    return run_apply_ncb<0, 9, true>(p, in1, t1, tri1, in2, t2, tri2, nterms, out_a, out_b, st);
+      return run_apply_ncb<0, 4, true>(p, nsk, in1, t1, tri1, in2, t2, tri2, nterms, out_a, out_b, st);
+    return run_apply_ncb<0, 9, true>(p, nsk, in1, t1, tri1, in2, t2, tri2, nterms, out_a, out_b, st);
   }
   if (nb <= 32)
-    return run_apply_ncb<MODE, 4, false>(p, in1, t1, tri1, in2, t2, tri2, nterms, out_a, out_b, st);
-  return run_apply_ncb<MODE, 9, false>(p, in1, t1, tri1, in2, t2, tri2, nterms, out_a, out_b, st);
-}
-
-// H[sk][i][j] = sum_chunks partial (upper blocks), mirrored as a Hermitian matrix
-__global__ void __launch_bounds__(256)
-k_sum_partials_herm(const cplx* __restrict__ partial, int nchunks, int nb, cplx* __restrict__ H) {
-  const int sk = blockIdx.x, nsk = gridDim.x;
-  const long long nn = (long long)nb * nb;
-  for (long long e = threadIdx.x; e < nn; e += blockDim.x) {
-    const int i = (int)(e / nb), j = (int)(e % nb);
-    const long long src = j >= i ? e : (long long)j * nb + i;
-    cplx s = cmake(0.0, 0.0);
-    for (int c = 0; c < nchunks; ++c) {
-      const cplx v = partial[((long long)c * nsk + sk) * nn + src];
-      s.x += v.x; s.y += v.y;
-    }
-    H[sk * nn + e] = j >= i ? s : cconj(s);
-  }
+    return run_apply_ncb<MODE, 4, false>(p, nsk, in1, t1, tri1, in2, t2, tri2, nterms, out_a, out_b, st);
+  return run_apply_ncb<MODE, 9, false>(p, nsk, in1, t1, tri1, in2, t2, tri2, nterms, out_a, out_b, st);
 }
 
 // H_ij = <q_i | hq_j> for Hermitian H (hamiltonian.hamiltonian_matrix): one Gram on DMMA
 int launch_hamiltonian_matrix(jrb_plan* p, const cplx* q, const cplx* hq, cplx* h, cudaStream_t st) {
   int nchunks = 0, rc = 0;
+  const int nsk = p->ns * p->nk;
   TallMat Q{reinterpret_cast<const double*>(q), nullptr, p->nb};
   TallMat G{reinterpret_cast<const double*>(hq), nullptr, p->nb};
-  if ((rc = run_gram(p, Q, G, false, p->d_gpart, &nchunks, st))) return rc;
-  k_sum_partials_herm<<<p->ns * p->nk, 256, 0, st>>>(p->d_gpart, nchunks, p->nb, h);
-  JRB_CHECK_LAUNCH("k_sum_partials_herm");
+  if ((rc = run_gram(p, nsk, Q, G, false, p->d_gpart, &nchunks, st))) return rc;
+  dim3 grid((unsigned)(((long long)p->nb * p->nb + SMALL_T - 1) / SMALL_T), nsk);
+  k_gram_reduce<<<grid, SMALL_T, 0, st>>>(p->d_gpart, nchunks, p->nb, h);
+  JRB_CHECK_LAUNCH("k_gram_reduce");
   return 0;
+}
+
+static int chol_and_inverse(jrb_plan* p, int nsk, int nchunks, cplx* S, cplx* Rt, cplx* Rit,
+                            cudaStream_t st) {
+  const int nb = p->nb;
+  dim3 egrid((unsigned)(((long long)nb * nb + SMALL_T - 1) / SMALL_T), nsk);
+  k_gram_reduce<<<egrid, SMALL_T, 0, st>>>(p->d_gpart, nchunks, nb, S);
+  JRB_CHECK_LAUNCH("k_gram_reduce");
+  const int smem = nb * (CHOL_PB + 1 + CHOL_KC + 1) * (int)sizeof(cplx);
+  static int once = opt_in_smem(k_chol_blocked, 200 * 1024);
+  if (once) return once;
+  if (smem > 200 * 1024) {
+    set_error("Cholesky panel does not fit shared memory (too many bands)");
+    return JRB_EUNSUPPORTED;
+  }
+  int* fail = reinterpret_cast<int*>(p->d_scal + 32);
+  k_chol_blocked<<<nsk, CHOL_T, smem, st>>>(S, Rt, nb, fail);
+  JRB_CHECK_LAUNCH("k_chol_blocked");
+  dim3 igrid((nb + 7) / 8, nsk);
+  k_tri_inv_cols<<<igrid, 256, 8 * nb * (int)sizeof(cplx), st>>>(Rt, nb, Rit);
+  JRB_CHECK_LAUNCH("k_tri_inv_cols");
+  return 0;
+}
+
+// Cholesky-QR2 of the (spin,k) range [sk0, sk0 + nsk).  q / r are indexed from sk0.
+int launch_qr_fwd_range(jrb_plan* p, int sk0, int nsk, const double* w_re, const double* w_im,
+                        cplx* q, cplx* r, cudaStream_t st) {
+  const int nb = p->nb;
+  const long long nn = (long long)nb * nb;
+  const long long nall = (long long)p->ns * p->nk * nn;
+  const long long soff = (long long)sk0 * p->ng * nb, moff = (long long)sk0 * nn;
+  cplx* S = p->d_small + moff;                // slot 0: Gram / Cholesky work
+  cplx* Rt = p->d_small + nall + moff;        // slot 1: R of the current pass
+  cplx* Rit = p->d_small + 2 * nall + moff;   // slot 2: its inverse
+  cplx* R1 = p->d_small + 3 * nall + moff;    // slot 3: R1 (first pass), kept for the compose
+  cplx* R1inv = p->d_small + 4 * nall + moff; // slot 4
+  cplx* tmp = p->d_tmp + soff;
+  cplx* rinv = p->d_rinv + moff;
+  int nchunks = 0, rc = 0;
+  TallMat W{w_re + soff, w_im + soff, nb};
+  TallMat none{nullptr, nullptr, 0};
+  // pass 1: R1, Q1 = W R1^-1
+  if ((rc = run_gram(p, nsk, W, W, true, p->d_gpart, &nchunks, st))) return rc;
+  if ((rc = chol_and_inverse(p, nsk, nchunks, S, R1, R1inv, st))) return rc;
+  if ((rc = run_apply<0>(p, nsk, W, R1inv, TRI_UPPER, none, nullptr, TRI_FULL, 1,
+                         reinterpret_cast<double*>(tmp), nullptr, st)))
+    return rc;
+  // pass 2: R2, Q = Q1 R2^-1; R = R2 R1, R^-1 = R1^-1 R2^-1
+  TallMat Q1{reinterpret_cast<const double*>(tmp), nullptr, nb};
+  if ((rc = run_gram(p, nsk, Q1, Q1, true, p->d_gpart, &nchunks, st))) return rc;
+  if ((rc = chol_and_inverse(p, nsk, nchunks, S, Rt, Rit, st))) return rc;
+  dim3 egrid((unsigned)((nn + SMALL_T - 1) / SMALL_T), nsk);
+  k_tri_compose<<<egrid, SMALL_T, 0, st>>>(Rt, Rit, R1, R1inv, nb, r + moff, rinv);
+  JRB_CHECK_LAUNCH("k_tri_compose");
+  return run_apply<0>(p, nsk, Q1, Rit, TRI_UPPER, none, nullptr, TRI_FULL, 1,
+                      reinterpret_cast<double*>(q + soff), nullptr, st);
 }
 
 int launch_qr_fwd(jrb_plan* p, const double* w_re, const double* w_im, cplx* q, cplx* r,
                   cudaStream_t st) {
-  const int nsk = p->ns * p->nk;
-  const long long nn = (long long)p->nb * p->nb;
-  cplx* S = p->d_small;                 // slot 0: Gram / Cholesky work
-  cplx* Rt = p->d_small + nsk * nn;     // slot 1
-  cplx* Rit = p->d_small + 2 * nsk * nn;  // slot 2
-  int* fail = reinterpret_cast<int*>(p->d_scal + 32);
+  return launch_qr_fwd_range(p, 0, p->ns * p->nk, w_re, w_im, q, r, st);
+}
+
+// Adjoint for the (spin,k) range [sk0, sk0 + nsk); all arrays indexed from (spin,k) 0.
+int launch_qr_bwd_range(jrb_plan* p, int sk0, int nsk, const cplx* q, const cplx* r,
+                        const cplx* gq, const double* occ, double* g_re, double* g_im,
+                        cudaStream_t st) {
+  const int nb = p->nb;
+  const long long nn = (long long)nb * nb;
+  const long long nall = (long long)p->ns * p->nk * nn;
+  const long long soff = (long long)sk0 * p->ng * nb, moff = (long long)sk0 * nn;
+  const cplx* rinv = p->d_rinv + moff;  // R^-1 of the plan's own forward call
+  if (r != p->d_r) {
+    cplx* ri = p->d_small + 3 * nall + moff;
+    dim3 igrid((nb + 7) / 8, nsk);
+    k_tri_inv_cols<<<igrid, 256, 8 * nb * (int)sizeof(cplx), st>>>(r + moff, nb, ri);
+    JRB_CHECK_LAUNCH("k_tri_inv_cols");
+    rinv = ri;
+  }
+  cplx* X = p->d_small + moff;
+  cplx* T1 = p->d_small + nall + moff;
+  cplx* T2 = p->d_small + 2 * nall + moff;
   int nchunks = 0, rc = 0;
-  TallMat W{w_re, w_im, p->nb};
-  TallMat none{nullptr, nullptr, 0};
-  // pass 1
-  if ((rc = run_gram(p, W, W, true, p->d_gpart, &nchunks, st))) return rc;
-  cplx* R2inv = p->d_small + 3 * nsk * nn;  // slot 3: staging, then R2^-1 for the last apply
-  k_chol_inv<<<nsk, 1024, 0, st>>>(p->d_gpart, nchunks, p->nb, S, Rt, Rit, nullptr, nullptr, r,
-                                   p->d_rinv, R2inv, fail);
-  JRB_CHECK_LAUNCH("k_chol_inv");
-  if ((rc = run_apply<0>(p, W, p->d_rinv, TRI_UPPER, none, nullptr, TRI_FULL, 1,
-                         reinterpret_cast<double*>(p->d_tmp), nullptr, st)))
-    return rc;
-  // pass 2
-  TallMat Q1{reinterpret_cast<const double*>(p->d_tmp), nullptr, p->nb};
-  if ((rc = run_gram(p, Q1, Q1, true, p->d_gpart, &nchunks, st))) return rc;
-  k_chol_inv<<<nsk, 1024, 0, st>>>(p->d_gpart, nchunks, p->nb, S, Rt, Rit, r, p->d_rinv, r,
-                                   p->d_rinv, R2inv, fail);
-  JRB_CHECK_LAUNCH("k_chol_inv");
-  // Rit still holds R2^-1 (only Rt and S were reused for staging)
-  JRB_CUDA(cudaMemcpyAsync(R2inv, Rit, sizeof(cplx) * nsk * nn, cudaMemcpyDeviceToDevice, st));
-  if ((rc = run_apply<0>(p, Q1, R2inv, TRI_UPPER, none, nullptr, TRI_FULL, 1,
-                         reinterpret_cast<double*>(q), nullptr, st)))
-    return rc;
-  return 0;
+  TallMat Q{reinterpret_cast<const double*>(q + soff), nullptr, nb};
+  TallMat G{reinterpret_cast<const double*>(gq + soff), nullptr, nb};
+  if ((rc = run_gram(p, nsk, Q, G, false, p->d_gpart, &nchunks, st))) return rc;
+  dim3 egrid((unsigned)((nn + SMALL_T - 1) / SMALL_T), nsk);
+  k_bwd_x<<<egrid, SMALL_T, 0, st>>>(p->d_gpart, nchunks, nb, occ ? occ + (long long)sk0 * nb : nullptr,
+                                     rinv, X, T1);
+  JRB_CHECK_LAUNCH("k_bwd_x");
+  k_bwd_t2<<<egrid, SMALL_T, 0, st>>>(X, rinv, nb, T2);
+  JRB_CHECK_LAUNCH("k_bwd_t2");
+  return run_apply<1>(p, nsk, G, T1, TRI_LOWER, Q, T2, TRI_FULL, 2, g_re + soff, g_im + soff, st);
 }
 
 int launch_qr_bwd(jrb_plan* p, const cplx* q, const cplx* r, const cplx* gq, const double* occ,
                   double* g_re, double* g_im, cudaStream_t st) {
-  const int nsk = p->ns * p->nk;
-  const long long nn = (long long)p->nb * p->nb;
-  const cplx* rinv = p->d_rinv;  // R^-1 of the plan's own forward call
-  if (r != p->d_r) {
-    cplx* ri = p->d_small + 3 * nsk * nn;
-    k_tri_inv<<<nsk, 1024, 0, st>>>(r, p->nb, ri);
-    JRB_CHECK_LAUNCH("k_tri_inv");
-    rinv = ri;
-  }
-  cplx* X = p->d_small;
-  cplx* T1 = p->d_small + nsk * nn;
-  cplx* T2 = p->d_small + 2 * nsk * nn;
-  int nchunks = 0, rc = 0;
-  TallMat Q{reinterpret_cast<const double*>(q), nullptr, p->nb};
-  TallMat G{reinterpret_cast<const double*>(gq), nullptr, p->nb};
-  if ((rc = run_gram(p, Q, G, false, p->d_gpart, &nchunks, st))) return rc;
-  k_bwd_small<<<nsk, 1024, 0, st>>>(p->d_gpart, nchunks, p->nb, occ, rinv, X, T1, T2);
-  JRB_CHECK_LAUNCH("k_bwd_small");
-  return run_apply<1>(p, G, T1, TRI_LOWER, Q, T2, TRI_FULL, 2, g_re, g_im, st);
+  return launch_qr_bwd_range(p, 0, p->ns * p->nk, q, r, gq, occ, g_re, g_im, st);
 }
 
 }  // namespace jrb

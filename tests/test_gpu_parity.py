@@ -179,6 +179,59 @@ def test_energy_grad_host(cuda_device):
   assert relerr(rho, ref['density']) < G_TOL
 
 
+@pytest.mark.parametrize('chunks', ['1', '2', '3'])
+def test_energy_grad_host_chunked(cuda_device, chunks, monkeypatch):
+  """jrb_energy_grad_host with k-point chunks (copies overlapped with kernels)."""
+  monkeypatch.setenv('JRB_HOST_CHUNKS', chunks)
+  s = make_system('diamond', 12, [2, 2, 1], 10, 'spherical')
+  w_re, w_im, occ = make_inputs(s, 7, jitter=0.1)
+  plan = make_plan(s, 7)
+  ref = rp.energy_and_grad(s, w_re, w_im, occ)
+  for _ in range(2):  # second call: reused buffers / events
+    en, g_re, g_im, rho = plan.energy_grad_host(w_re, w_im, occ, want_rho=True)
+    assert abs(en.sum() - ref['e_tot']) / abs(ref['e_tot']) < E_TOL
+    assert relerr(g_re, ref['g_re']) < G_TOL
+    assert relerr(g_im, ref['g_im']) < G_TOL
+    assert relerr(rho, ref['density']) < G_TOL
+
+
+def test_rank_deficient_parameters_are_reported(cuda_device):
+  """Cholesky-QR cannot orthonormalise linearly dependent columns: the host call says so."""
+  from jrystal_b200._lib import JrbError
+  s = make_system('diamond', 12, [1, 1, 1], 10, 'spherical')
+  w_re, w_im, occ = make_inputs(s, 4)
+  w_re[..., 1] = w_re[..., 0]
+  w_im[..., 1] = w_im[..., 0]
+  plan = make_plan(s, 4)
+  with pytest.raises(JrbError):
+    plan.energy_grad_host(w_re, w_im, occ)
+  # the flag does not stick: a well-posed call on the same plan succeeds afterwards
+  w_re2, w_im2, _ = make_inputs(s, 4)
+  plan.energy_grad_host(w_re2, w_im2, occ)
+
+
+def test_large_band_count_qr(cuda_device):
+  """nb > 72: several Gram super-tiles, several Cholesky panels, several apply column tiles."""
+  s = make_system('si', 16, [1, 1, 1], 30, 'spherical')
+  nb = 100
+  assert s.num_g > 2 * nb
+  rng = np.random.default_rng(3)
+  w_re = rng.random((1, 1, s.num_g, nb))
+  w_im = rng.random((1, 1, s.num_g, nb))
+  plan = make_plan(s, nb)
+  q, r = plan.qr_fwd(to_dev(w_re), to_dev(w_im))
+  qn, rn = q.cpu().numpy()[0, 0], r.cpu().numpy()[0, 0]
+  w = (w_re + 1j * w_im)[0, 0]
+  assert np.abs(qn.conj().T @ qn - np.eye(nb)).max() < 1e-12
+  assert relerr(qn @ rn, w) < 1e-12
+  assert np.abs(np.tril(rn, -1)).max() == 0.0
+  gq = rng.standard_normal(w_re.shape) + 1j * rng.standard_normal(w_re.shape)
+  g_re, g_im = plan.qr_bwd(q, r, to_dev(gq))
+  gw = analytic.qr_backward(qn, rn, gq[0, 0])
+  assert relerr(g_re[0, 0].cpu().numpy(), 2 * gw.real) < 1e-10
+  assert relerr(g_im[0, 0].cpu().numpy(), 2 * gw.imag) < 1e-10
+
+
 def test_errors(cuda_device):
   import jrystal_b200 as jb
   from jrystal_b200._lib import JrbError
