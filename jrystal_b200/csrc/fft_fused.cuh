@@ -86,39 +86,45 @@ __device__ __forceinline__ void fused_cp_wait_all() {
   asm volatile("cp.async.wait_group 0;\n" ::: "memory");
 }
 
-// Position in the flat (item, band) list of a CTA: item w = z * ngroups + gl.  Only (w, band)
-// are carried in registers; z / gl / band count are recomputed when needed.
+// Position in the flat (item, band) list of a CTA: item w = z * ngroups + gl.  Stepping is
+// incremental (no divisions in the band loop).
 struct BandPos {
-  int w, band;
+  int w, z, gl, gmod, band;  // gmod = (g0 + gl) % ngpk: group index within its (spin, k)
 };
-struct BandInfo {
-  int z, gl, nband;
-};
-__device__ __forceinline__ BandInfo band_info(const FusedArgs& a, int w) {
-  BandInfo r;
-  r.z = w / a.ngroups;
-  r.gl = w - r.z * a.ngroups;
-  const int b0 = ((a.g0 + r.gl) % a.ngpk) * NB;
-  r.nband = min(NB, a.nb - b0);
-  return r;
+__device__ __forceinline__ int band_count(const FusedArgs& a, const BandPos& p) {
+  return min(NB, a.nb - p.gmod * NB);
 }
-__device__ __forceinline__ BandPos band_next(const FusedArgs& a, BandPos p, int w_end) {
-  if (p.w < w_end) {
-    if (++p.band >= band_info(a, p.w).nband) {
-      ++p.w;
-      p.band = 0;
+__device__ __forceinline__ BandPos band_first(const FusedArgs& a, int w) {
+  BandPos p;
+  p.w = w;
+  p.z = w / a.ngroups;
+  p.gl = w - p.z * a.ngroups;
+  p.gmod = (a.g0 + p.gl) % a.ngpk;
+  p.band = 0;
+  return p;
+}
+__device__ __forceinline__ BandPos band_next(const FusedArgs& a, BandPos p, int w_end, int gmod0) {
+  if (p.w < w_end && ++p.band >= band_count(a, p)) {
+    p.band = 0;
+    ++p.w;
+    ++p.gl;
+    if (++p.gmod == a.ngpk) p.gmod = 0;
+    if (p.gl == a.ngroups) {
+      p.gl = 0;
+      ++p.z;
+      p.gmod = gmod0;
     }
   }
   return p;
 }
-__device__ __forceinline__ cplx* band_plane(const FusedArgs& a, BandPos p) {
-  const BandInfo i = band_info(a, p.w);
-  return a.wa + ((long long)i.gl * a.m.nz + i.z) * a.m.ncol * NB + p.band;
+__device__ __forceinline__ cplx* band_plane(const FusedArgs& a, const BandPos& p) {
+  return a.wa + (long long)(p.gl * a.m.nz + p.z) * (a.m.ncol * NB) + p.band;
 }
 
 // stage the plane columns of one band: stage[col] = A[gl][z][col][band]
 template <int NT>
-__device__ __forceinline__ void fused_stage(const FusedArgs& a, BandPos p, int w_end, cplx* stage) {
+__device__ __forceinline__ void fused_stage(const FusedArgs& a, const BandPos& p, int w_end,
+                                            cplx* stage) {
   if (p.w < w_end) {
     const cplx* src = band_plane(a, p);
     for (int c = threadIdx.x; c < a.m.ncol; c += NT)
@@ -231,8 +237,9 @@ k_yx_density(FusedArgs a) {
 
   const long long W = (long long)a.m.nz * a.ngroups;
   const int c = blockIdx.x, G = gridDim.x;
-  BandPos cur{(int)(c * W / G), 0};
   const int w_end = (int)((c + 1) * W / G);
+  const int gmod0 = a.g0 % a.ngpk;
+  BandPos cur = band_first(a, (int)(c * W / G));
   int seg = 0;
   auto flush = [&](int z) {
     double* out = a.rho_part + ((long long)c * a.segmax + seg) * N * N;
@@ -256,27 +263,25 @@ k_yx_density(FusedArgs a) {
     fused_stage<C::NT>(a, cur, w_end, stage0);
     fused_cp_wait_all();
     __syncthreads();
-    fused_stage<C::NT>(a, band_next(a, cur, w_end), w_end, stage0 + ssz);
+    fused_stage<C::NT>(a, band_next(a, cur, w_end, gmod0), w_end, stage0 + ssz);
     fused_y_inverse<N>(a, stage0, ybuf0, ex, tw, pk, lane, tj, slot);
     int par = 0;  // parity of the current band: it lives in Y[par]
-    int cur_z = band_info(a, cur.w).z;
-    double fw_next = a.focc[(long long)(a.g0 + band_info(a, cur.w).gl) * NB + cur.band];
+    int cur_z = cur.z;
+    double fw_next = a.focc[(a.g0 + cur.gl) * NB + cur.band];
     while (cur.w < w_end) {
       // Y[par] complete (y stage of the current band by every slot); staged data of the next
       // band landed and visible; everybody is done with Y[par ^ 1] and stage[par]
       fused_cp_wait_all();
       __syncthreads();
       // band b+1 is staged in stage[par ^ 1]; prefetch band b+2 into stage[par]
-      const BandPos nxt = band_next(a, cur, w_end);
-      fused_stage<C::NT>(a, band_next(a, nxt, w_end), w_end, stage0 + par * ssz);
-      const int z = band_info(a, cur.w).z;
-      if (z != cur_z) {
+      const BandPos nxt = band_next(a, cur, w_end, gmod0);
+      fused_stage<C::NT>(a, band_next(a, nxt, w_end, gmod0), w_end, stage0 + par * ssz);
+      if (cur.z != cur_z) {
         flush(cur_z);
-        cur_z = z;
+        cur_z = cur.z;
       }
       const double fw = fw_next;
-      if (nxt.w < w_end)
-        fw_next = a.focc[(long long)(a.g0 + band_info(a, nxt.w).gl) * NB + nxt.band];
+      if (nxt.w < w_end) fw_next = a.focc[(a.g0 + nxt.gl) * NB + nxt.band];
       const cplx* ybuf = ybuf0 + par * ysz;
 #pragma unroll
       for (int r = 0; r < C::NR; ++r) {
@@ -417,25 +422,25 @@ k_yx_vmul(FusedArgs a) {
   const int ngx = (a.m.nxo + NB - 1) / NB;
   const long long W = (long long)a.m.nz * a.ngroups;
   const int c = blockIdx.x, G = gridDim.x;
-  BandPos cur{(int)(c * W / G), 0};
   const int w_end = (int)((c + 1) * W / G);
+  const int gmod0 = a.g0 % a.ngpk;
+  BandPos cur = band_first(a, (int)(c * W / G));
   if (cur.w >= w_end) return;
   fused_stage<C::NT>(a, cur, w_end, stage0);
   fused_cp_wait_all();
   __syncthreads();
-  fused_stage<C::NT>(a, band_next(a, cur, w_end), w_end, stage0 + ssz);
+  fused_stage<C::NT>(a, band_next(a, cur, w_end, gmod0), w_end, stage0 + ssz);
   fused_y_inverse<N>(a, stage0, ybuf0, ex, twi, pk, lane, tj, slot);
   int par = 0;
-  int cur_z = band_info(a, cur.w).z;
+  int cur_z = cur.z;
   load_v(cur_z);
   while (cur.w < w_end) {
     fused_cp_wait_all();
     __syncthreads();
-    const BandPos nxt = band_next(a, cur, w_end);
-    fused_stage<C::NT>(a, band_next(a, nxt, w_end), w_end, stage0 + par * ssz);
-    const int z = band_info(a, cur.w).z;
-    if (z != cur_z) {
-      cur_z = z;
+    const BandPos nxt = band_next(a, cur, w_end, gmod0);
+    fused_stage<C::NT>(a, band_next(a, nxt, w_end, gmod0), w_end, stage0 + par * ssz);
+    if (cur.z != cur_z) {
+      cur_z = cur.z;
       load_v(cur_z);
     }
     cplx* ybuf = ybuf0 + par * ysz;
