@@ -163,7 +163,7 @@ def run_reference(args):
     return
   wl = build_workload(args.config)
   nk = wl['kpts'].shape[0]
-  nk_sample = {'C1': 8, 'C2': 1, 'C3a': 1, 'C3b': 1}[args.config]
+  nk_sample = {'C1': 8, 'C2': 8, 'C3a': 1, 'C3b': 1}[args.config]
   steps = max(1, min(args.steps, 3))
   value, t, cores, nks = cpu_sample_eval(wl, nk_sample, steps, min(args.warmup, 1))
   sample = (f'{nks} of {nk} k-points x {wl["nb"]} bands at {wl["grid"]} per step, time scaled '
@@ -293,30 +293,62 @@ def run_b200(args):
   e2e_value = e2e_steps / float(e2e_s.item())
 
   # ---- phase split (outside the timed region; explains the number) ----------------------
+  # CUDA events on torch's current stream = the stream every kernel of the phase is launched on;
+  # outputs are preallocated so no allocator call lands inside a timed phase.
   phases = {}
-  q, r = plan.qr_fwd(w_re, w_im)
-  rho2 = plan.density(q, occ)
+  cdt = torch.complex128
+  q = torch.empty(w_re.shape, dtype=cdt, device='cuda')
+  r = torch.empty((1, k1 - k0, nb, nb), dtype=cdt, device='cuda')
+  hq = torch.empty_like(q)
+  rho2 = torch.empty_like(rho)
+  g_out = (torch.empty_like(w_re), torch.empty_like(w_im))
+  plan.qr_fwd(w_re, w_im, out=(q, r))
+  plan.density(q, occ, out=rho2)
   _, veff = plan.grid_potential(rho2, 'lda_x', False)
-  hq = plan.hpsi(q, veff)
+  plan.hpsi(q, veff, out=hq)
+  plan.qr_bwd(q, r, hq, out=g_out)
   reps = 3
-  phases['qr_fwd'] = timed(lambda: plan.qr_fwd(w_re, w_im), reps) / reps
-  phases['density'] = timed(lambda: plan.density(q, occ), reps) / reps
+  phases['qr_fwd'] = timed(lambda: plan.qr_fwd(w_re, w_im, out=(q, r)), reps) / reps
+  phases['density'] = timed(lambda: plan.density(q, occ, out=rho2), reps) / reps
   phases['grid_potential'] = timed(lambda: plan.grid_potential(rho2, 'lda_x', False), reps) / reps
-  phases['hpsi'] = timed(lambda: plan.hpsi(q, veff), reps) / reps
-  phases['qr_bwd'] = timed(lambda: plan.qr_bwd(q, r, hq), reps) / reps
-  del q, r, hq, rho2, veff
+  phases['hpsi'] = timed(lambda: plan.hpsi(q, veff, out=hq), reps) / reps
+  phases['qr_bwd'] = timed(lambda: plan.qr_bwd(q, r, hq, out=g_out), reps) / reps
+  del q, r, hq, rho2, veff, g_out
 
-  # ---- roofline: algorithmic bytes of SURVEY 8(d), per GPU ------------------------------
+  # ---- roofline (a dense 3-D transform is charged one read + one write of its box,
+  # sphere data its true size), per GPU -------------------------------------------------------
   m_local = (k1 - k0) * (b1 - b0)
-  bytes_alg = 64.0 * m_local * (ngrid + ng)
   peak, peak_src = measured_peak()
-  achieved = bytes_alg / (ms_per_step * 1e-3) / 1e9
+  # dominant kernel group: the H-apply sweep k_z_inv_scatter + k_yx_vmul + k_z_fwd_gather
+  # (k_yx_vmul alone is ~45 % of the step, profiles/); it performs the backward dense transform
+  # of every orbital and reads Q / writes HQ on the sphere
+  happly_bytes = m_local * (32.0 * ngrid + 32.0 * ng)
+  happly_achieved = happly_bytes / (phases['hpsi'] * 1e-3) / 1e9
+  bytes_alg = 64.0 * m_local * (ngrid + ng)
+  whole_achieved = bytes_alg / (ms_per_step * 1e-3) / 1e9
   fft_ms = phases['density'] + phases['hpsi']
   fft_bytes = 64.0 * m_local * ngrid
+  traffic = None
+  try:
+    prof = json.load(open(os.path.join(ROOT, 'profiles', 'traffic.json')))
+    ent = prof.get(args.config)
+    if ent and world == 1:
+      traffic = ent['happly_dram_bytes_per_eval']
+  except Exception:
+    pass
   roofline = {
-    'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
-    'traffic': None, 'peak_source': peak_src,
-    'kernel': 'whole evaluation (bytes_alg = 64*M*(N+ng) per GPU, SURVEY 8d)',
+    'bound': 'hbm', 'achieved': happly_achieved, 'peak': peak, 'unit': 'GB/s',
+    'frac': happly_achieved / peak, 'traffic': traffic, 'peak_source': peak_src,
+    'kernel': 'H-apply sweep (k_z_inv_scatter + k_yx_vmul + k_z_fwd_gather; k_yx_vmul is the '
+              'dominant kernel)',
+    'bytes_per_launch': happly_bytes,
+    'bytes_formula': 'M*(32*N + 32*ng): one dense transform (read+write of the box) per orbital '
+                     '+ Q read + HQ write, SURVEY 8d',
+    'ms_per_launch': phases['hpsi'],
+    'note': 'the sweep keeps psi(r) in shared memory, so it is bound by FP64 issue + the smem '
+            'exchange (see DESIGN.md), measured DRAM traffic is far below the algorithmic bytes',
+    'whole_evaluation': {'achieved': whole_achieved, 'frac': whole_achieved / peak,
+                         'bytes': '64*M*(N+ng)'},
     'fft_density_path': {'ms': fft_ms, 'achieved': fft_bytes / (fft_ms * 1e-3) / 1e9,
                          'frac': fft_bytes / (fft_ms * 1e-3) / 1e9 / peak,
                          'bytes': '64*M*N (two dense 3-D transforms per orbital)'},
@@ -340,8 +372,9 @@ def run_b200(args):
       'workspace_mib': plan.workspace_bytes / 2**20,
     }
     if world == 1 and not args.no_cpu:
-      nks = {'C1': 8, 'C2': 1, 'C3a': 1, 'C3b': 1}[args.config]
-      v, t, cores, nks = cpu_sample_eval(wl, nks, 1, 1)
+      # bounded sample: ~10-20 s of CPU work
+      nks = {'C1': 8, 'C2': 8, 'C3a': 1, 'C3b': 1}[args.config]
+      v, t, cores, nks = cpu_sample_eval(wl, nks, 2 if args.config != 'C1' else 20, 1)
       line['cpu_baseline'] = {
         'value': v, 'unit': UNIT, 'cores': cores, 'kind': 'port',
         'sample': f'{nks} of {nk} k-points x {nb} bands ({t:.2f} s), scaled by {nk / nks:g}; '

@@ -297,20 +297,25 @@ int launch_density_reciprocal(jrb_plan* p, const double* rho, cplx* rho_hat, cud
 // sphere reductions: out[sk][b] = sum_g w(g) * f(q, hq)
 //   MODE 0: 1/2 |G+k|^2 |q|^2        (kinetic)
 //   MODE 1: Re conj(q) hq            (band expectation)
-// grid: (ceil(nb / 32), ns*nk), block (32, 8)
+// The rows g are split over gridDim.z chunks (enough CTAs to stream Q at HBM speed); the chunk
+// partials are summed in a fixed order by k_sum_chunks (deterministic).
+// grid: (ceil(nb / 32), nsk, nchunks), block (32, 8)
+constexpr int SPHERE_CHUNKS = 8;
 template <int MODE>
 __global__ void __launch_bounds__(256)
 k_sphere_reduce(const cplx* __restrict__ q, const cplx* __restrict__ hq,
                 const double* __restrict__ gk2, long long ng, int nb, int nk, int sk0,
-                double* __restrict__ out) {
+                double* __restrict__ part) {
   const int b = blockIdx.x * 32 + threadIdx.x;
   const int sk = sk0 + blockIdx.y;
   const int k = sk % nk;
+  const long long rows = (ng + gridDim.z - 1) / gridDim.z;
+  const long long g_lo = blockIdx.z * rows, g_hi = min(ng, g_lo + rows);
   double acc = 0.0;
   if (b < nb) {
     const cplx* qp = q + ((long long)sk * ng) * nb + b;
     const cplx* hp = MODE == 1 ? hq + ((long long)sk * ng) * nb + b : nullptr;
-    for (long long g = threadIdx.y; g < ng; g += blockDim.y) {
+    for (long long g = g_lo + threadIdx.y; g < g_hi; g += blockDim.y) {
       const cplx c = qp[g * nb];
       if (MODE == 0) {
         acc += gk2[(long long)k * ng + g] * (c.x * c.x + c.y * c.y);
@@ -327,16 +332,38 @@ k_sphere_reduce(const cplx* __restrict__ q, const cplx* __restrict__ hq,
     double s = 0.0;
 #pragma unroll
     for (int j = 0; j < 8; ++j) s += sh[j][threadIdx.x];
-    out[(long long)sk * nb + b] = MODE == 0 ? 0.5 * s : s;
+    // part[chunk][local sk][b]
+    part[((long long)blockIdx.z * gridDim.y + blockIdx.y) * nb + b] = MODE == 0 ? 0.5 * s : s;
   }
+}
+
+// out[i] = sum_chunks part[chunk][i]
+__global__ void k_sum_chunks(const double* __restrict__ part, int nchunks, long long n,
+                             double* __restrict__ out) {
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double s = 0.0;
+  for (int c = 0; c < nchunks; ++c) s += part[c * n + i];
+  out[i] = s;
+}
+
+template <int MODE>
+static int sphere_reduce(jrb_plan* p, int sk0, int nsk, const cplx* q, const cplx* hq, double* out,
+                         cudaStream_t st) {
+  dim3 grid((p->nb + 31) / 32, nsk, SPHERE_CHUNKS), block(32, 8);
+  k_sphere_reduce<MODE><<<grid, block, 0, st>>>(q, hq, p->d_gk2, p->ng, p->nb, p->nk, sk0,
+                                               p->d_sphere_part);
+  JRB_CHECK_LAUNCH("k_sphere_reduce");
+  const long long n = (long long)nsk * p->nb;
+  k_sum_chunks<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(p->d_sphere_part, SPHERE_CHUNKS, n,
+                                                            out + (long long)sk0 * p->nb);
+  JRB_CHECK_LAUNCH("k_sum_chunks");
+  return 0;
 }
 
 int launch_kinetic_range(jrb_plan* p, int sk0, int nsk, const cplx* q, double* t_skb,
                          cudaStream_t st) {
-  dim3 grid((p->nb + 31) / 32, nsk), block(32, 8);
-  k_sphere_reduce<0><<<grid, block, 0, st>>>(q, nullptr, p->d_gk2, p->ng, p->nb, p->nk, sk0, t_skb);
-  JRB_CHECK_LAUNCH("k_sphere_reduce<kinetic>");
-  return 0;
+  return sphere_reduce<0>(p, sk0, nsk, q, nullptr, t_skb, st);
 }
 
 int launch_kinetic(jrb_plan* p, const cplx* q, double* t_skb, cudaStream_t st) {
@@ -344,10 +371,7 @@ int launch_kinetic(jrb_plan* p, const cplx* q, double* t_skb, cudaStream_t st) {
 }
 
 int launch_band_expect(jrb_plan* p, const cplx* q, const cplx* hq, double* eps, cudaStream_t st) {
-  dim3 grid((p->nb + 31) / 32, p->ns * p->nk), block(32, 8);
-  k_sphere_reduce<1><<<grid, block, 0, st>>>(q, hq, p->d_gk2, p->ng, p->nb, p->nk, 0, eps);
-  JRB_CHECK_LAUNCH("k_sphere_reduce<expect>");
-  return 0;
+  return sphere_reduce<1>(p, 0, p->ns * p->nk, q, hq, eps, st);
 }
 
 // out[0] = sum_i a[i] w[i]   (single block, fixed order)

@@ -76,6 +76,7 @@ struct jrb_plan {
   jrb::cplx *d_r, *d_rinv, *d_small;  // [ns*nk][nb][nb] each (d_small: 5 of them)
   jrb::cplx* d_gpart;                 // [chunks][ns*nk][nb][nb] split-K Gram partials
   double *d_tkb, *d_eps;              // [ns*nk*nb]
+  double* d_sphere_part;              // [8 chunks][ns*nk*nb] partials of the sphere reductions
   double* d_scal;                     // small device scalars
   cudaStream_t own_stream, h2d_stream, d2h_stream;
   cudaEvent_t ev_in[16], ev_out[16];  // per k-chunk events of jrb_energy_grad_host

@@ -93,20 +93,26 @@ class Plan:
     self._atoms = True
 
   # -- orthonormalisation -------------------------------------------------------------
-  def qr_fwd(self, w_re, w_im):
+  def qr_fwd(self, w_re, w_im, out=None):
     self._chk(w_re, self.sphere_shape, torch.float64, 'w_re')
     self._chk(w_im, self.sphere_shape, torch.float64, 'w_im')
-    q = self._new(self.sphere_shape, torch.complex128)
-    r = self._new((self.ns, self.nk, self.nb, self.nb), torch.complex128)
+    if out is None:
+      q = self._new(self.sphere_shape, torch.complex128)
+      r = self._new((self.ns, self.nk, self.nb, self.nb), torch.complex128)
+    else:
+      q, r = out
     _lib.check(self.lib.jrb_qr_fwd(self._h, _ptr(w_re), _ptr(w_im), _ptr(q), _ptr(r), _stream()))
     return q, r
 
-  def qr_bwd(self, q, r, gq):
+  def qr_bwd(self, q, r, gq, out=None):
     self._chk(q, self.sphere_shape, torch.complex128, 'q')
     self._chk(r, (self.ns, self.nk, self.nb, self.nb), torch.complex128, 'r')
     self._chk(gq, self.sphere_shape, torch.complex128, 'gq')
-    g_re = self._new(self.sphere_shape, torch.float64)
-    g_im = self._new(self.sphere_shape, torch.float64)
+    if out is None:
+      g_re = self._new(self.sphere_shape, torch.float64)
+      g_im = self._new(self.sphere_shape, torch.float64)
+    else:
+      g_re, g_im = out
     _lib.check(self.lib.jrb_qr_bwd(self._h, _ptr(q), _ptr(r), _ptr(gq), _ptr(g_re), _ptr(g_im),
                                    _stream()))
     return g_re, g_im
@@ -126,10 +132,10 @@ class Plan:
     return q
 
   # -- hot path pieces --------------------------------------------------------------
-  def density(self, q, occ):
+  def density(self, q, occ, out=None):
     self._chk(q, self.sphere_shape, torch.complex128, 'q')
     self._chk(occ, (self.ns, self.nk, self.nb), torch.float64, 'occupation')
-    rho = self._new((self.ns, self.nx, self.ny, self.nz), torch.float64)
+    rho = self._new((self.ns, self.nx, self.ny, self.nz), torch.float64) if out is None else out
     _lib.check(self.lib.jrb_density(self._h, _ptr(q), _ptr(occ), _ptr(rho), _stream()))
     return rho
 
@@ -176,10 +182,10 @@ class Plan:
     _lib.check(self.lib.jrb_wave_grid(self._h, _ptr(q), _ptr(out), _stream()))
     return out
 
-  def hpsi(self, q, veff):
+  def hpsi(self, q, veff, out=None):
     self._chk(q, self.sphere_shape, torch.complex128, 'q')
     self._chk(veff, (self.ns, self.nx, self.ny, self.nz), torch.float64, 'veff')
-    hq = self._new(self.sphere_shape, torch.complex128)
+    hq = self._new(self.sphere_shape, torch.complex128) if out is None else out
     _lib.check(self.lib.jrb_hpsi(self._h, _ptr(q), _ptr(veff), _ptr(hq), _stream()))
     return hq
 
