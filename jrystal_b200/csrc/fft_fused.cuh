@@ -136,7 +136,7 @@ __device__ __forceinline__ void fused_stage(const FusedArgs& a, const BandPos& p
 // y stage, inverse: staged columns of one band-plane -> Y[xo][y].  All threads call it.
 // pk: per-thread packed indices, low 16 bits = column + 1 of (x plane slot * 8 + lane, y =
 // idxA) for the first y-stage iteration, high 16 bits = Y row offset + 1 of x = idxA (x stage).
-template <int N>
+template <int N, bool ONE_ITER>
 __device__ __forceinline__ void fused_y_inverse(
   const FusedArgs& a, const cplx* stage, cplx* ybuf, cplx* ex,
   const cplx (&tw)[LineFFT<N, +1>::CB][LineFFT<N, +1>::NTW],
@@ -144,11 +144,12 @@ __device__ __forceinline__ void fused_y_inverse(
   using F = LineFFT<N, +1>;
   using C = FCfg<N>;
   const int ngx = (a.m.nxo + NB - 1) / NB;
-  for (int grp = slot; grp < (ngx + C::SLOTS - 1) / C::SLOTS * C::SLOTS; grp += C::SLOTS) {
+  const int grp_end = ONE_ITER ? slot + 1 : (ngx + C::SLOTS - 1) / C::SLOTS * C::SLOTS;
+  for (int grp = slot; grp < grp_end; grp += C::SLOTS) {
     const int xo = grp * NB + lane;
     const bool ok = grp < ngx && xo < a.m.nxo;
     cplx va[F::CA][F::RA];
-    if (grp == slot) {
+    if (ONE_ITER || grp == slot) {
 #pragma unroll
       for (int i = 0; i < F::CA; ++i)
 #pragma unroll
@@ -191,7 +192,7 @@ __device__ __forceinline__ void fused_y_inverse(
 
 // ---------------------------------------------------------------------------------------
 // grid: (G) persistent CTAs; dynamic smem: FCfg<N>::smem_bytes(nxo, ncol)
-template <int N>
+template <int N, bool ONE_ITER>
 __global__ void __launch_bounds__(FCfg<N>::NT, (FCfg<N>::NT <= 256 ? 2 : 1))
 k_yx_density(FusedArgs a) {
   using F = LineFFT<N, +1>;
@@ -264,7 +265,7 @@ k_yx_density(FusedArgs a) {
     fused_cp_wait_all();
     __syncthreads();
     fused_stage<C::NT>(a, band_next(a, cur, w_end, gmod0), w_end, stage0 + ssz);
-    fused_y_inverse<N>(a, stage0, ybuf0, ex, tw, pk, lane, tj, slot);
+    fused_y_inverse<N, ONE_ITER>(a, stage0, ybuf0, ex, tw, pk, lane, tj, slot);
     int par = 0;  // parity of the current band: it lives in Y[par]
     int cur_z = cur.z;
     double fw_next = a.focc[(a.g0 + cur.gl) * NB + cur.band];
@@ -307,7 +308,7 @@ k_yx_density(FusedArgs a) {
       }
       // y stage of the next band into the other Y buffer
       if (nxt.w < w_end)
-        fused_y_inverse<N>(a, stage0 + (par ^ 1) * ssz, ybuf0 + (par ^ 1) * ysz, ex, tw, pk, lane,
+        fused_y_inverse<N, ONE_ITER>(a, stage0 + (par ^ 1) * ssz, ybuf0 + (par ^ 1) * ysz, ex, tw, pk, lane,
                            tj, slot);
       cur = nxt;
       par ^= 1;
@@ -348,7 +349,7 @@ k_rho_reduce(const double* __restrict__ part, const int* __restrict__ seg_z, int
 // ---------------------------------------------------------------------------------------
 // Hamiltonian-apply middle: A (plane z) -> y inverse -> x inverse -> * v_eff / N -> x forward
 // -> y forward -> A (in place).   grid: (G) persistent CTAs; dynamic smem as above.
-template <int N>
+template <int N, bool ONE_ITER>
 __global__ void __launch_bounds__(FCfg<N>::NT, (FCfg<N>::NT <= 256 ? 2 : 1))
 k_yx_vmul(FusedArgs a) {
   using FI = LineFFT<N, +1>;
@@ -430,7 +431,7 @@ k_yx_vmul(FusedArgs a) {
   fused_cp_wait_all();
   __syncthreads();
   fused_stage<C::NT>(a, band_next(a, cur, w_end, gmod0), w_end, stage0 + ssz);
-  fused_y_inverse<N>(a, stage0, ybuf0, ex, twi, pk, lane, tj, slot);
+  fused_y_inverse<N, ONE_ITER>(a, stage0, ybuf0, ex, twi, pk, lane, tj, slot);
   int par = 0;
   int cur_z = cur.z;
   load_v(cur_z);
@@ -480,7 +481,8 @@ k_yx_vmul(FusedArgs a) {
     __syncthreads();
     // y stage, forward: Y -> occupied columns of A (global, in place)
     cplx* dst = band_plane(a, cur);
-    for (int grp = slot; grp < (ngx + C::SLOTS - 1) / C::SLOTS * C::SLOTS; grp += C::SLOTS) {
+    const int grp_end = ONE_ITER ? slot + 1 : (ngx + C::SLOTS - 1) / C::SLOTS * C::SLOTS;
+    for (int grp = slot; grp < grp_end; grp += C::SLOTS) {
       const int xo = grp * NB + lane;
       const bool ok = grp < ngx && xo < a.m.nxo;
       const cplx* in = ybuf + (long long)(ok ? xo : 0) * C::SX;
@@ -510,7 +512,7 @@ k_yx_vmul(FusedArgs a) {
       slot_barrier<N>(slot);
     }
     if (nxt.w < w_end)
-      fused_y_inverse<N>(a, stage0 + (par ^ 1) * ssz, ybuf0 + (par ^ 1) * ysz, ex, twi, pk, lane,
+      fused_y_inverse<N, ONE_ITER>(a, stage0 + (par ^ 1) * ssz, ybuf0 + (par ^ 1) * ysz, ex, twi, pk, lane,
                          tj, slot);
     cur = nxt;
     par ^= 1;
@@ -523,14 +525,20 @@ template <int N>
 int launch_fused(int kind, const FusedArgs& a, int ctas, cudaStream_t st) {
   using C = FCfg<N>;
   const int smem = C::smem_bytes(a.m.nxo, a.m.ncol);
+  // all occupied x planes fit one pass of the slots (the common case): leaner y stages
+  const bool one = (a.m.nxo + NB - 1) / NB <= C::SLOTS;
   if (kind == 0) {
-    static int once = set_smem_attr(k_yx_density<N>, 200 * 1024);
+    static int once = set_smem_attr(k_yx_density<N, true>, 200 * 1024) |
+                      set_smem_attr(k_yx_density<N, false>, 200 * 1024);
     if (once) return once;
-    k_yx_density<N><<<ctas, C::NT, smem, st>>>(a);
+    if (one) k_yx_density<N, true><<<ctas, C::NT, smem, st>>>(a);
+    else k_yx_density<N, false><<<ctas, C::NT, smem, st>>>(a);
   } else {
-    static int once = set_smem_attr(k_yx_vmul<N>, 200 * 1024);
+    static int once = set_smem_attr(k_yx_vmul<N, true>, 200 * 1024) |
+                      set_smem_attr(k_yx_vmul<N, false>, 200 * 1024);
     if (once) return once;
-    k_yx_vmul<N><<<ctas, C::NT, smem, st>>>(a);
+    if (one) k_yx_vmul<N, true><<<ctas, C::NT, smem, st>>>(a);
+    else k_yx_vmul<N, false><<<ctas, C::NT, smem, st>>>(a);
   }
   JRB_CHECK_LAUNCH("fused yx pass launch");
   return 0;
