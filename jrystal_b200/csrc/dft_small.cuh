@@ -156,6 +156,49 @@ struct Dft<5, DIR> : DftOddPrime<5, DIR> {};
 template <int DIR>
 struct Dft<7, DIR> : DftOddPrime<7, DIR> {};
 
+// Radix-8 butterflies for band-limited data.  With stride-8 decimation of a 64-point line whose
+// non-zero entries are the frequencies |f| < 16 (indices [0,16) u [48,64)), a first-stage
+// butterfly only sees inputs m in {0, 1, 6, 7}, and a last-stage butterfly only has to produce
+// those outputs.  Exploiting the zeros by hand saves 20 / 8 of the 56 FP64 instructions.
+//
+// Inputs v[0], v[1], v[6], v[7] (others ignored) -> all 8 outputs.  36 FP64 instructions.
+template <int DIR>
+JRB_HD void dft8_sparse_in(cplx (&v)[8]) {
+  constexpr double r = 0.70710678118654752440;
+  const cplx a0 = v[0], a1 = v[1], a6 = v[6], a7 = v[7];
+  auto rot = [](cplx z) { return DIR > 0 ? cmul_pi(z) : cmul_mi(z); };  // z * (DIR * i)
+  const cplx s = cadd(a1, a7), d = csub(a1, a7);
+  const cplx S = cscale(s, r), D = rot(cscale(d, r)), E = rot(d), J = rot(a6);
+  const cplx P = cadd(a0, a6), M = csub(a0, a6), Q1 = csub(a0, J), Q3 = cadd(a0, J);
+  const cplx SpD = cadd(S, D), DmS = csub(D, S);
+  v[0] = cadd(P, s);
+  v[4] = csub(P, s);
+  v[2] = cadd(M, E);
+  v[6] = csub(M, E);
+  v[1] = cadd(Q1, SpD);
+  v[5] = csub(Q1, SpD);
+  v[3] = cadd(Q3, DmS);
+  v[7] = csub(Q3, DmS);
+}
+
+// All 8 inputs -> outputs v[0], v[1], v[6], v[7] only (others left unspecified).  48 FP64
+// instructions.
+template <int DIR>
+JRB_HD void dft8_sparse_out(cplx (&v)[8]) {
+  constexpr double r = 0.70710678118654752440;
+  auto rot = [](cplx z) { return DIR > 0 ? cmul_pi(z) : cmul_mi(z); };  // z * (DIR * i)
+  const cplx e0 = cadd(v[0], v[4]), e1 = cadd(v[1], v[5]), e2 = cadd(v[2], v[6]), e3 = cadd(v[3], v[7]);
+  const cplx o0 = csub(v[0], v[4]), o1 = csub(v[1], v[5]), o2 = csub(v[2], v[6]), o3 = csub(v[3], v[7]);
+  v[0] = cadd(cadd(e0, e2), cadd(e1, e3));
+  // w^6 = -DIR i
+  v[6] = csub(csub(e0, e2), rot(csub(e1, e3)));
+  const cplx u = cscale(csub(o1, o3), r), w = rot(cscale(cadd(o1, o3), r));
+  const cplx g = rot(o2);
+  const cplx A = cadd(cadd(o0, g), u), B = cadd(csub(o0, g), u);
+  v[1] = cadd(A, w);
+  v[7] = csub(B, w);
+}
+
 // Composite: R = A * B, decimation in time, natural-order output.
 //   X[k1 + A k2] = sum_{n2<B} w_B^{n2 k2} w_R^{n2 k1} sum_{n1<A} x[n1 B + n2] w_A^{n1 k1}
 template <int R, int DIR>

@@ -103,6 +103,9 @@ static FusedArgs fused_args(jrb_plan* p, const PassArgs& a) {
   f.g0 = a.g0;
   f.ngroups = a.ngroups;
   f.vscale = a.vscale;
+  f.band_limited = p->band_limited;
+  if (const char* env = std::getenv("JRB_NO_SPARSE"))
+    if (std::atoi(env) != 0) f.band_limited = 0;
   return f;
 }
 

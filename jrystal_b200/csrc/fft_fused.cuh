@@ -40,7 +40,11 @@ struct FusedArgs {
   int nb, ngpk;
   int g0, ngroups;     // first global group id, number of groups in the batch
   double vscale;
+  int band_limited;    // every occupied x and y index lies in [0, 2 RB) u [n - 2 RB, n)
 };
+
+// butterfly slots that can be non-zero for band-limited data (see dft_small.cuh)
+#define JRB_SPARSE_M(m) ((m) < 2 || (m) >= 6)
 
 constexpr int fused_slots(int tpl) {
   int s = 256 / (NB * tpl);
@@ -136,7 +140,7 @@ __device__ __forceinline__ void fused_stage(const FusedArgs& a, const BandPos& p
 // y stage, inverse: staged columns of one band-plane -> Y[xo][y].  All threads call it.
 // pk: per-thread packed indices, low 16 bits = column + 1 of (x plane slot * 8 + lane, y =
 // idxA) for the first y-stage iteration, high 16 bits = Y row offset + 1 of x = idxA (x stage).
-template <int N, bool ONE_ITER>
+template <int N, bool ONE_ITER, bool SP>
 __device__ __forceinline__ void fused_y_inverse(
   const FusedArgs& a, const cplx* stage, cplx* ybuf, cplx* ex,
   const cplx (&tw)[LineFFT<N, +1>::CB][LineFFT<N, +1>::NTW],
@@ -154,6 +158,7 @@ __device__ __forceinline__ void fused_y_inverse(
       for (int i = 0; i < F::CA; ++i)
 #pragma unroll
         for (int m = 0; m < F::RA; ++m) {
+          if (SP && !JRB_SPARSE_M(m)) continue;  // structurally zero, never read
           const int col = (int)(pk[i][m] & 0xffffu) - 1;
           va[i][m] = col >= 0 ? stage[col] : czero();
         }
@@ -172,7 +177,11 @@ __device__ __forceinline__ void fused_y_inverse(
         }
       }
     }
-    F::template stageA_store<NB>(va, ex, tj);
+    if constexpr (SP) {
+      F::template stageA_store_sparse<NB>(va, ex, tj);
+    } else {
+      F::template stageA_store<NB>(va, ex, tj);
+    }
     slot_barrier<N>(slot);
     cplx vb[F::CB][F::RB];
     F::template stageB_load<NB>(vb, ex, tw, tj);
@@ -192,7 +201,7 @@ __device__ __forceinline__ void fused_y_inverse(
 
 // ---------------------------------------------------------------------------------------
 // grid: (G) persistent CTAs; dynamic smem: FCfg<N>::smem_bytes(nxo, ncol)
-template <int N, bool ONE_ITER>
+template <int N, bool ONE_ITER, bool SP>
 __global__ void __launch_bounds__(FCfg<N>::NT, (FCfg<N>::NT <= 256 ? 2 : 1))
 k_yx_density(FusedArgs a) {
   using F = LineFFT<N, +1>;
@@ -265,7 +274,7 @@ k_yx_density(FusedArgs a) {
     fused_cp_wait_all();
     __syncthreads();
     fused_stage<C::NT>(a, band_next(a, cur, w_end, gmod0), w_end, stage0 + ssz);
-    fused_y_inverse<N, ONE_ITER>(a, stage0, ybuf0, ex, tw, pk, lane, tj, slot);
+    fused_y_inverse<N, ONE_ITER, SP>(a, stage0, ybuf0, ex, tw, pk, lane, tj, slot);
     int par = 0;  // parity of the current band: it lives in Y[par]
     int cur_z = cur.z;
     double fw_next = a.focc[(a.g0 + cur.gl) * NB + cur.band];
@@ -292,9 +301,15 @@ k_yx_density(FusedArgs a) {
 #pragma unroll
         for (int i = 0; i < F::CA; ++i)
 #pragma unroll
-          for (int m = 0; m < F::RA; ++m)
+          for (int m = 0; m < F::RA; ++m) {
+            if (SP && !JRB_SPARSE_M(m)) continue;
             va[i][m] = ((pk[i][m] >> 16) != 0 && ok) ? ybuf[(int)(pk[i][m] >> 16) - 1 + y] : czero();
-        F::template stageA_store<NB>(va, ex, tj);
+          }
+        if constexpr (SP) {
+          F::template stageA_store_sparse<NB>(va, ex, tj);
+        } else {
+          F::template stageA_store<NB>(va, ex, tj);
+        }
         slot_barrier<N>(slot);
         cplx vb[F::CB][F::RB];
         F::template stageB_load<NB>(vb, ex, tw, tj);
@@ -308,7 +323,7 @@ k_yx_density(FusedArgs a) {
       }
       // y stage of the next band into the other Y buffer
       if (nxt.w < w_end)
-        fused_y_inverse<N, ONE_ITER>(a, stage0 + (par ^ 1) * ssz, ybuf0 + (par ^ 1) * ysz, ex, tw, pk, lane,
+        fused_y_inverse<N, ONE_ITER, SP>(a, stage0 + (par ^ 1) * ssz, ybuf0 + (par ^ 1) * ysz, ex, tw, pk, lane,
                            tj, slot);
       cur = nxt;
       par ^= 1;
@@ -349,7 +364,7 @@ k_rho_reduce(const double* __restrict__ part, const int* __restrict__ seg_z, int
 // ---------------------------------------------------------------------------------------
 // Hamiltonian-apply middle: A (plane z) -> y inverse -> x inverse -> * v_eff / N -> x forward
 // -> y forward -> A (in place).   grid: (G) persistent CTAs; dynamic smem as above.
-template <int N, bool ONE_ITER>
+template <int N, bool ONE_ITER, bool SP>
 __global__ void __launch_bounds__(FCfg<N>::NT, (FCfg<N>::NT <= 256 ? 2 : 1))
 k_yx_vmul(FusedArgs a) {
   using FI = LineFFT<N, +1>;
@@ -374,8 +389,12 @@ k_yx_vmul(FusedArgs a) {
   cplx twf[SHARE_TW ? 1 : FF::CB][SHARE_TW ? 1 : FF::NTW];
   FI::load_twiddles(twi, a.tw, tj);
   if constexpr (!SHARE_TW) FF::load_twiddles(twf, a.tw, tj);
+  // forward stage B; band-limited data: only the outputs m in {0, 1, 6, 7} are produced
   auto fwd_stageB = [&](cplx (&v)[FF::CB][FF::RB]) {
-    if constexpr (SHARE_TW) {
+    if constexpr (SP) {
+      static_assert(!SP || SHARE_TW, "band-limited variant needs equal radices");
+      FF::template stageB_load_sparse<NB, true>(v, ex, twi, tj);
+    } else if constexpr (SHARE_TW) {
       FF::template stageB_load<NB, true>(v, ex, twi, tj);
     } else {
       FF::template stageB_load<NB, false>(v, ex, twf, tj);
@@ -431,7 +450,7 @@ k_yx_vmul(FusedArgs a) {
   fused_cp_wait_all();
   __syncthreads();
   fused_stage<C::NT>(a, band_next(a, cur, w_end, gmod0), w_end, stage0 + ssz);
-  fused_y_inverse<N, ONE_ITER>(a, stage0, ybuf0, ex, twi, pk, lane, tj, slot);
+  fused_y_inverse<N, ONE_ITER, SP>(a, stage0, ybuf0, ex, twi, pk, lane, tj, slot);
   int par = 0;
   int cur_z = cur.z;
   load_v(cur_z);
@@ -454,9 +473,15 @@ k_yx_vmul(FusedArgs a) {
 #pragma unroll
       for (int i = 0; i < FI::CA; ++i)
 #pragma unroll
-        for (int m = 0; m < FI::RA; ++m)
+        for (int m = 0; m < FI::RA; ++m) {
+          if (SP && !JRB_SPARSE_M(m)) continue;
           va[i][m] = ((pk[i][m] >> 16) != 0 && ok) ? ybuf[(int)(pk[i][m] >> 16) - 1 + y] : czero();
-      FI::template stageA_store<NB>(va, ex, tj);
+        }
+      if constexpr (SP) {
+        FI::template stageA_store_sparse<NB>(va, ex, tj);
+      } else {
+        FI::template stageA_store<NB>(va, ex, tj);
+      }
       slot_barrier<N>(slot);
       cplx vb[FI::CB][FI::RB];
       FI::template stageB_load<NB>(vb, ex, twi, tj);
@@ -473,8 +498,10 @@ k_yx_vmul(FusedArgs a) {
 #pragma unroll
         for (int i = 0; i < FF::CB; ++i)
 #pragma unroll
-          for (int m = 0; m < FF::RB; ++m)
+          for (int m = 0; m < FF::RB; ++m) {
+            if (SP && !JRB_SPARSE_M(m)) continue;
             if ((pk[i][m] >> 16) != 0) ybuf[(int)(pk[i][m] >> 16) - 1 + y] = vc[i][m];
+          }
       }
       slot_barrier<N>(slot);
     }
@@ -503,6 +530,7 @@ k_yx_vmul(FusedArgs a) {
           if (FF::activeB(i, tj)) {
 #pragma unroll
             for (int m = 0; m < FF::RB; ++m) {
+              if (SP && !JRB_SPARSE_M(m)) continue;
               const int col = yc[FF::idxB(i, m, tj)];
               if (col >= 0) dst[(long long)col * NB] = vb[i][m];
             }
@@ -512,7 +540,7 @@ k_yx_vmul(FusedArgs a) {
       slot_barrier<N>(slot);
     }
     if (nxt.w < w_end)
-      fused_y_inverse<N, ONE_ITER>(a, stage0 + (par ^ 1) * ssz, ybuf0 + (par ^ 1) * ysz, ex, twi, pk, lane,
+      fused_y_inverse<N, ONE_ITER, SP>(a, stage0 + (par ^ 1) * ssz, ybuf0 + (par ^ 1) * ysz, ex, twi, pk, lane,
                          tj, slot);
     cur = nxt;
     par ^= 1;
@@ -525,20 +553,27 @@ template <int N>
 int launch_fused(int kind, const FusedArgs& a, int ctas, cudaStream_t st) {
   using C = FCfg<N>;
   const int smem = C::smem_bytes(a.m.nxo, a.m.ncol);
-  // all occupied x planes fit one pass of the slots (the common case): leaner y stages
+  // all occupied x planes fit one pass of the slots (the common case): leaner y stages;
+  // band-limited radix-8 x radix-8 lines additionally use the sparse butterflies
   const bool one = (a.m.nxo + NB - 1) / NB <= C::SLOTS;
+  constexpr bool SP_OK = LineFFT<N, +1>::SPARSE_OK && LineFFT<N, -1>::SPARSE_OK;
+  const bool sp = SP_OK && one && a.band_limited;
   if (kind == 0) {
-    static int once = set_smem_attr(k_yx_density<N, true>, 200 * 1024) |
-                      set_smem_attr(k_yx_density<N, false>, 200 * 1024);
+    static int once = set_smem_attr(k_yx_density<N, true, false>, 200 * 1024) |
+                      set_smem_attr(k_yx_density<N, false, false>, 200 * 1024) |
+                      set_smem_attr(k_yx_density<N, true, SP_OK>, 200 * 1024);
     if (once) return once;
-    if (one) k_yx_density<N, true><<<ctas, C::NT, smem, st>>>(a);
-    else k_yx_density<N, false><<<ctas, C::NT, smem, st>>>(a);
+    if (sp) k_yx_density<N, true, SP_OK><<<ctas, C::NT, smem, st>>>(a);
+    else if (one) k_yx_density<N, true, false><<<ctas, C::NT, smem, st>>>(a);
+    else k_yx_density<N, false, false><<<ctas, C::NT, smem, st>>>(a);
   } else {
-    static int once = set_smem_attr(k_yx_vmul<N, true>, 200 * 1024) |
-                      set_smem_attr(k_yx_vmul<N, false>, 200 * 1024);
+    static int once = set_smem_attr(k_yx_vmul<N, true, false>, 200 * 1024) |
+                      set_smem_attr(k_yx_vmul<N, false, false>, 200 * 1024) |
+                      set_smem_attr(k_yx_vmul<N, true, SP_OK>, 200 * 1024);
     if (once) return once;
-    if (one) k_yx_vmul<N, true><<<ctas, C::NT, smem, st>>>(a);
-    else k_yx_vmul<N, false><<<ctas, C::NT, smem, st>>>(a);
+    if (sp) k_yx_vmul<N, true, SP_OK><<<ctas, C::NT, smem, st>>>(a);
+    else if (one) k_yx_vmul<N, true, false><<<ctas, C::NT, smem, st>>>(a);
+    else k_yx_vmul<N, false, false><<<ctas, C::NT, smem, st>>>(a);
   }
   JRB_CHECK_LAUNCH("fused yx pass launch");
   return 0;

@@ -124,6 +124,44 @@ struct LineFFT {
     }
   }
 
+  // Band-limited variants (radix-8 stages only, see dft_small.cuh): stage A whose butterfly
+  // inputs are non-zero only for m in {0, 1, 6, 7}; stage B that only produces those outputs.
+  static constexpr bool SPARSE_OK = (RA == 8 && RB == 8);
+  template <int S>
+  static JRB_HD void stageA_store_sparse(cplx (&va)[CA][RA], cplx* sm, int tj) {
+    static_assert(RA == 8, "sparse butterflies are radix 8");
+#pragma unroll
+    for (int i = 0; i < CA; ++i) {
+      if (activeA(i, tj)) {
+        dft8_sparse_in<DIR>(va[i]);
+        const int jA = tj + i * TPL;
+#pragma unroll
+        for (int q = 0; q < RA; ++q) sm[(jA * RA + q) * S] = va[i][q];
+      }
+    }
+  }
+  template <int S, bool CONJ_TW = false>
+  static JRB_HD void stageB_load_sparse(cplx (&vb)[CB][RB], const cplx* sm,
+                                        const cplx (&tw)[CB][NTW], int tj) {
+    static_assert(RB == 8, "sparse butterflies are radix 8");
+#pragma unroll
+    for (int i = 0; i < CB; ++i) {
+      if (activeB(i, tj)) {
+        const int jB = tj + i * TPL;
+        vb[i][0] = sm[jB * S];
+#pragma unroll
+        for (int m = 1; m < RB; ++m) {
+          if constexpr (CONJ_TW) {
+            vb[i][m] = cmul(sm[(jB + m * RA) * S], cconj(tw[i][m - 1]));
+          } else {
+            vb[i][m] = cmul(sm[(jB + m * RA) * S], tw[i][m - 1]);
+          }
+        }
+        dft8_sparse_out<DIR>(vb[i]);
+      }
+    }
+  }
+
   // Stage B: gather from the exchange buffer, twiddle, butterflies; vb[i][m] then holds
   // X[idxB(i, m)].
   // CONJ_TW: multiply by the conjugates of `tw` (lets a forward transform reuse the inverse

@@ -203,6 +203,13 @@ extern "C" int jrb_plan_create(const jrb_plan_desc* d, jrb_plan** out) {
           gidx.push_back((int32_t)(((size_t)x * ny + y) * nz + z));
         }
     }
+  // band-limited in x and y: |frequency| < 16 (what the sparse radix-8 butterflies assume)
+  p->band_limited = 1;
+  for (int x = 0; x < nx; ++x)
+    for (int y = 0; y < ny; ++y)
+      if (colid[(size_t)x * ny + y] >= 0 &&
+          !((x < 16 || x >= nx - 16) && (y < 16 || y >= ny - 16)))
+        p->band_limited = 0;
   if (ng == 0) {
     delete p;
     set_error("jrb_plan_create: empty mask");

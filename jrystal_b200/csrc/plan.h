@@ -61,6 +61,7 @@ struct jrb_plan {
   double* d_focc;     // [ns*nk*ngroups_per_k][NB] occupation / Omega, zero padded
   int fused;          // 1: y and x passes fused per z-plane (fft_fused.cuh); B slab unused
   int fused_ctas;     // persistent CTAs of the fused kernels (resident slots)
+  int band_limited;   // occupied x and y indices all in [0, 16) u [n - 16, n) (sparse radix-8 butterflies)
   int fused_segmax;   // partial density planes per CTA (upper bound over batch sizes)
   double* d_rho_part; // [fused_ctas * fused_segmax][nx*ny] partial density planes
   int* d_seg_z;       // [fused_ctas * fused_segmax] z of each partial plane or -1

@@ -17,6 +17,10 @@ E_TOL = 1e-10
 G_TOL = 1e-8
 
 CASES = {
+  # 64^3 (the C2 benchmark grid): band-limited sphere -> sparse radix-8 butterflies in the fused
+  # kernels; the high cut-off case is NOT band-limited and takes the dense butterflies
+  'si8_64': dict(name='si8', grid=64, kgrid=[1, 1, 1], mask='spherical', cutoff=30, nb=11),
+  'si8_64_hicut': dict(name='si8', grid=64, kgrid=[1, 1, 1], mask='spherical', cutoff=75, nb=9),
   # cubic grids with radix-3 lengths and several band groups (fused y+x kernels, chunked density)
   'si_48_cubic': dict(name='si', grid=48, kgrid=[1, 1, 2], mask='spherical', cutoff=15, nb=21),
   'diamond_12': dict(name='diamond', grid=12, kgrid=[2, 1, 1], mask='spherical', cutoff=10, nb=5),
@@ -149,10 +153,14 @@ def test_hpsi_and_band_trace(cuda_device, case):
 
 @pytest.mark.parametrize('case', list(CASES))
 @pytest.mark.parametrize('batch_groups', [0, 1, 3])
-@pytest.mark.parametrize('fuse', [True, False])
+@pytest.mark.parametrize('fuse', ['fused', 'fused_dense_butterflies', 'unfused'])
 def test_energy_and_grad(cuda_device, case, batch_groups, fuse, monkeypatch):
-  # fuse=False forces the single-pass pencil kernels (the path non-cubic grids and 128^3 take)
-  monkeypatch.setenv('JRB_NO_FUSE', '0' if fuse else '1')
+  # 'unfused' forces the single-pass pencil kernels (the path non-cubic grids and 128^3 take);
+  # 'fused_dense_butterflies' disables the band-limited (sparse radix-8) variant
+  monkeypatch.setenv('JRB_NO_FUSE', '1' if fuse == 'unfused' else '0')
+  monkeypatch.setenv('JRB_NO_SPARSE', '1' if fuse == 'fused_dense_butterflies' else '0')
+  if fuse == 'fused_dense_butterflies' and case != 'si8_64':
+    pytest.skip('only the band-limited 64^3 case has a sparse variant to switch off')
   s, plan, w_re, w_im, occ = _setup(case, batch_groups=batch_groups)
   ref = rp.energy_and_grad(s, w_re, w_im, occ, occ_grad=True)
   occ_d = to_dev(occ)
