@@ -524,6 +524,8 @@ k_yx_vmul(FusedArgs a) {
       cplx vb[FF::CB][FF::RB];
       fwd_stageB(vb);
       if (ok) {
+        // forward stage-B outputs sit on the y indices of the inverse stage-A inputs, so in the
+        // single-pass case the packed column indices of pk apply (no map lookups)
         const int32_t* yc = a.m.ycol + (long long)xo * N;
 #pragma unroll
         for (int i = 0; i < FF::CB; ++i) {
@@ -531,7 +533,7 @@ k_yx_vmul(FusedArgs a) {
 #pragma unroll
             for (int m = 0; m < FF::RB; ++m) {
               if (SP && !JRB_SPARSE_M(m)) continue;
-              const int col = yc[FF::idxB(i, m, tj)];
+              const int col = ONE_ITER ? (int)(pk[i][m] & 0xffffu) - 1 : yc[FF::idxB(i, m, tj)];
               if (col >= 0) dst[(long long)col * NB] = vb[i][m];
             }
           }
