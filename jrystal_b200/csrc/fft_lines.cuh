@@ -85,7 +85,29 @@ struct LineFFT {
   static constexpr int TPL = P::tpl;
   static constexpr int CA = (RB + TPL - 1) / TPL;  // stage-A butterflies per thread
   static constexpr int CB = (RA + TPL - 1) / TPL;  // stage-B butterflies per thread
-  static constexpr int NTW = RB > 1 ? RB - 1 : 1;
+  // Long lines keep their inter-stage twiddles in the (L1-resident) table instead of registers:
+  // 16 elements per thread leave no room for CB x (RB - 1) complex twiddles next to them, and
+  // the register count decides how many CTAs are resident (profiles/r02_ncu_c3a_baseline.md).
+  // In that mode tw[0][0] only carries the table pointer.
+  static constexpr bool TW_TABLE = N > 96;
+  static constexpr int NTW = TW_TABLE ? 1 : (RB > 1 ? RB - 1 : 1);
+
+  static JRB_HD const cplx* tw_table_ptr(const cplx& slot) {
+    union { double d; const cplx* p; } u;
+    u.d = slot.x;
+    return u.p;
+  }
+  // w_N^{DIR * jB * m} from the table
+  template <bool CONJ_TW>
+  static JRB_HD cplx tw_lookup(const cplx* table, int jB, int m) {
+#if defined(__CUDA_ARCH__)
+    const double2 t = __ldg(reinterpret_cast<const double2*>(table) + (jB * m) % N);
+    const cplx w = cmake(t.x, t.y);
+#else
+    const cplx w = table[(jB * m) % N];
+#endif
+    return ((DIR > 0) != CONJ_TW) ? cconj(w) : w;
+  }
 
   // element index a thread touches: input of stage A / output of stage B
   static JRB_HD int idxA(int i, int m, int tj) { return (tj + i * TPL) + m * RB; }
@@ -97,6 +119,13 @@ struct LineFFT {
   static JRB_HD void load_twiddles(cplx (&tw)[CB][NTW], const cplx* __restrict__ table,
                                    int tj) {
     if constexpr (RA == 1) return;  // single butterfly: all twiddles are 1
+    if constexpr (TW_TABLE) {
+      union { double d; const cplx* p; } u;
+      u.d = 0.0;
+      u.p = table;
+      tw[0][0] = cmake(u.d, 0.0);
+      return;
+    }
 #pragma unroll
     for (int i = 0; i < CB; ++i) {
       int jB = tj + i * TPL;
@@ -178,6 +207,9 @@ struct LineFFT {
         for (int m = 1; m < RB; ++m) {
           if constexpr (RA == 1) {
             vb[i][m] = sm[(jB + m * RA) * S];
+          } else if constexpr (TW_TABLE) {
+            vb[i][m] = cmul(sm[(jB + m * RA) * S],
+                            tw_lookup<CONJ_TW>(tw_table_ptr(tw[0][0]), jB, m));
           } else if constexpr (CONJ_TW) {
             vb[i][m] = cmul(sm[(jB + m * RA) * S], cconj(tw[i][m - 1]));
           } else {

@@ -92,7 +92,11 @@ __device__ __forceinline__ cplx czero() { return cmake(0.0, 0.0); }
 
 // The z passes are latency bound gathers/scatters: 4 resident CTAs (64 registers) instead of 3
 // where that costs no real spilling (checked with -Xptxas -v).
-constexpr int z_min_blocks(int n) { return n == 64 ? 4 : 1; }
+constexpr bool vmul_two_buffers(int n) { return n <= 96; }
+constexpr int z_min_blocks(int n) { return n == 64 ? 4 : (n > 96 ? 2 : 1); }
+// Long lines (16 elements per thread): cap the registers at 128 so that two CTAs are resident
+// (one CTA of 8 warps per SM left every 128-point pass latency bound at 12 % occupancy).
+constexpr int long_min_blocks(int n) { return n > 96 ? 2 : 1; }
 
 // ---------------------------------------------------------------------------------------
 // z pass, inverse, with the sphere scatter fused into the loads.
@@ -149,7 +153,7 @@ __global__ void __launch_bounds__(Cfg<NZ>::NT, z_min_blocks(NZ)) k_z_inv_scatter
 // y pass, inverse: A (occupied columns) -> B (all y) on the occupied x planes.
 // grid: (ceil(nxo * nz / LPC), ngroups)
 template <int NY>
-__global__ void __launch_bounds__(Cfg<NY>::NT) k_y_inv(PassArgs a) {
+__global__ void __launch_bounds__(Cfg<NY>::NT, long_min_blocks(NY)) k_y_inv(PassArgs a) {
   using F = LineFFT<NY, +1>;
   using C = Cfg<NY>;
   JRB_THREAD_COORDS(NY)
@@ -201,7 +205,7 @@ __global__ void __launch_bounds__(Cfg<NY>::NT) k_y_inv(PassArgs a) {
 // atomics (deterministic summation order).
 // grid: (ceil(ny * nz / LPC))
 template <int NX>
-__global__ void __launch_bounds__(Cfg<NX>::NT) k_x_inv_density(PassArgs a) {
+__global__ void __launch_bounds__(Cfg<NX>::NT, long_min_blocks(NX)) k_x_inv_density(PassArgs a) {
   using F = LineFFT<NX, +1>;
   using C = Cfg<NX>;
   JRB_THREAD_COORDS(NX)
@@ -212,15 +216,16 @@ __global__ void __launch_bounds__(Cfg<NX>::NT) k_x_inv_density(PassArgs a) {
   cplx tw[F::CB][F::NTW];
   F::load_twiddles(tw, a.tw, tj);
 
-  long long ioff[F::CA][F::RA];
+  // element offsets inside one group's slab (nxo * ny * nz * NB < 2^31, checked at plan creation)
+  int ioff[F::CA][F::RA];
 #pragma unroll
   for (int i = 0; i < F::CA; ++i) {
 #pragma unroll
     for (int m = 0; m < F::RA; ++m) {
-      long long o = -1;
+      int o = -1;
       if (F::activeA(i, tj) && line_ok) {
         const int xo = a.m.xmap[F::idxA(i, m, tj)];
-        if (xo >= 0) o = ((long long)xo * nyz + yz) * NB + b;
+        if (xo >= 0) o = (int)(((long long)xo * nyz + yz) * NB + b);
       }
       ioff[i][m] = o;
     }
@@ -276,7 +281,7 @@ __global__ void __launch_bounds__(Cfg<NX>::NT) k_x_inv_density(PassArgs a) {
 // v_eff psi(r) live in registers only.
 // grid: (ceil(ny * nz / LPC)); dynamic smem: 2 exchange buffers
 template <int NX>
-__global__ void __launch_bounds__(Cfg<NX>::NT) k_x_vmul(PassArgs a) {
+__global__ void __launch_bounds__(Cfg<NX>::NT, long_min_blocks(NX)) k_x_vmul(PassArgs a) {
   using FI = LineFFT<NX, +1>;
   using FF = LineFFT<NX, -1>;
   using C = Cfg<NX>;
@@ -285,37 +290,29 @@ __global__ void __launch_bounds__(Cfg<NX>::NT) k_x_vmul(PassArgs a) {
   const long long nyz = (long long)a.m.ny * a.m.nz;
   const long long yz = (long long)blockIdx.x * C::LPC + ls;
   const bool line_ok = yz < nyz;
+  // long lines: one exchange buffer (plus a barrier) so that two CTAs fit the shared memory
+  constexpr bool TWO_BUF = NX <= 96;  // == vmul_two_buffers(NX)
   cplx* sm0 = smem + (size_t)ls * NX * NB + b;
-  cplx* sm1 = sm0 + (size_t)C::LPC * NX * NB;
+  cplx* sm1 = TWO_BUF ? sm0 + (size_t)C::LPC * NX * NB : sm0;
   cplx twi[FI::CB][FI::NTW];
   cplx twf[FF::CB][FF::NTW];
   FI::load_twiddles(twi, a.tw, tj);
   FF::load_twiddles(twf, a.tw, tj);
 
-  long long ioff[FI::CA][FI::RA];
+  // The forward stage-B outputs sit on the x indices of the inverse stage-A inputs (idxB of the
+  // forward plan == idxA of the inverse plan), so one offset table serves loads and stores.
+  static_assert(FF::CB == FI::CA && FF::RB == FI::RA, "x index sets of inverse-in / forward-out");
+  int ioff[FI::CA][FI::RA];
 #pragma unroll
   for (int i = 0; i < FI::CA; ++i) {
 #pragma unroll
     for (int m = 0; m < FI::RA; ++m) {
-      long long o = -1;
+      int o = -1;
       if (FI::activeA(i, tj) && line_ok) {
         const int xo = a.m.xmap[FI::idxA(i, m, tj)];
-        if (xo >= 0) o = ((long long)xo * nyz + yz) * NB + b;
+        if (xo >= 0) o = (int)(((long long)xo * nyz + yz) * NB + b);
       }
       ioff[i][m] = o;
-    }
-  }
-  long long ooff[FF::CB][FF::RB];
-#pragma unroll
-  for (int i = 0; i < FF::CB; ++i) {
-#pragma unroll
-    for (int m = 0; m < FF::RB; ++m) {
-      long long o = -1;
-      if (FF::activeB(i, tj) && line_ok) {
-        const int xo = a.m.xmap[FF::idxB(i, m, tj)];
-        if (xo >= 0) o = ((long long)xo * nyz + yz) * NB + b;
-      }
-      ooff[i][m] = o;
     }
   }
   double vv[FI::CB][FI::RB];
@@ -346,6 +343,7 @@ __global__ void __launch_bounds__(Cfg<NX>::NT) k_x_vmul(PassArgs a) {
     for (int i = 0; i < FI::CB; ++i)
 #pragma unroll
       for (int m = 0; m < FI::RB; ++m) vb[i][m] = cscale(vb[i][m], vv[i][m]);
+    if constexpr (!TWO_BUF) __syncthreads();
     FF::template stageA_store<NB>(vb, sm1, tj);
     __syncthreads();
     cplx vc[FF::CB][FF::RB];
@@ -354,14 +352,15 @@ __global__ void __launch_bounds__(Cfg<NX>::NT) k_x_vmul(PassArgs a) {
     for (int i = 0; i < FF::CB; ++i)
 #pragma unroll
       for (int m = 0; m < FF::RB; ++m)
-        if (ooff[i][m] >= 0) buf[ooff[i][m]] = vc[i][m];
+        if (ioff[i][m] >= 0) buf[ioff[i][m]] = vc[i][m];
+    if constexpr (!TWO_BUF) __syncthreads();
   }
 }
 
 // ---------------------------------------------------------------------------------------
 // y pass, forward: B (all y) -> A (occupied columns).   grid: (ceil(nxo * nz / LPC), ngroups)
 template <int NY>
-__global__ void __launch_bounds__(Cfg<NY>::NT) k_y_fwd(PassArgs a) {
+__global__ void __launch_bounds__(Cfg<NY>::NT, long_min_blocks(NY)) k_y_fwd(PassArgs a) {
   using F = LineFFT<NY, -1>;
   using C = Cfg<NY>;
   JRB_THREAD_COORDS(NY)
@@ -470,7 +469,7 @@ __global__ void __launch_bounds__(Cfg<NZ>::NT, z_min_blocks(NZ)) k_z_fwd_gather(
 // run over `lane_total` neighbouring lines (stride lane_stride); elements of a line are
 // elem_stride apart.   grid: (ceil(n0 * ceil(lane_total/NB) / LPC), batch)
 template <int N, int DIR>
-__global__ void __launch_bounds__(Cfg<N>::NT) k_dense_line(DenseArgs a) {
+__global__ void __launch_bounds__(Cfg<N>::NT, long_min_blocks(N)) k_dense_line(DenseArgs a) {
   using F = LineFFT<N, DIR>;
   using C = Cfg<N>;
   JRB_THREAD_COORDS(N)
@@ -550,10 +549,11 @@ int launch_pass(PassKind kind, const PassArgs& a, cudaStream_t st) {
       break;
     }
     case PASS_X_VMUL: {
-      static int once = set_smem_attr(k_x_vmul<N>, 2 * C::SMEM);
+      constexpr int smem = (vmul_two_buffers(N) ? 2 : 1) * C::SMEM;
+      static int once = set_smem_attr(k_x_vmul<N>, smem);
       if (once) return once;
       dim3 grid((a.m.ny * a.m.nz + lpc - 1) / lpc);
-      k_x_vmul<N><<<grid, C::NT, 2 * C::SMEM, st>>>(a);
+      k_x_vmul<N><<<grid, C::NT, smem, st>>>(a);
       break;
     }
     case PASS_Y_FWD: {

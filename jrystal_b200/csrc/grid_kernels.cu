@@ -4,6 +4,7 @@
 // xc.py:54-64,109-124), the per-orbital kinetic and band expectations on the sphere
 // (energy.py:172-180; braket.py:189-206) and the scatter/gather API-parity helpers
 // (utils.py:277-308).  All HBM-bound, FP64, deterministic two-stage reductions.
+#include <algorithm>
 #include <cmath>
 #include <vector>
 
@@ -350,12 +351,16 @@ __global__ void k_sum_chunks(const double* __restrict__ part, int nchunks, long 
 template <int MODE>
 static int sphere_reduce(jrb_plan* p, int sk0, int nsk, const cplx* q, const cplx* hq, double* out,
                          cudaStream_t st) {
-  dim3 grid((p->nb + 31) / 32, nsk, SPHERE_CHUNKS), block(32, 8);
+  // few (spin, k) items (Gamma-only supercells): more row chunks so that ~4 CTAs per SM stream Q
+  // (d_sphere_part holds (8 ns nk + 640) nb partials, plan.cu)
+  const int nbx = (p->nb + 31) / 32;
+  const int chunks = std::max(SPHERE_CHUNKS, std::min(64, 592 / (nbx * nsk)));
+  dim3 grid(nbx, nsk, chunks), block(32, 8);
   k_sphere_reduce<MODE><<<grid, block, 0, st>>>(q, hq, p->d_gk2, p->ng, p->nb, p->nk, sk0,
                                                p->d_sphere_part);
   JRB_CHECK_LAUNCH("k_sphere_reduce");
   const long long n = (long long)nsk * p->nb;
-  k_sum_chunks<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(p->d_sphere_part, SPHERE_CHUNKS, n,
+  k_sum_chunks<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(p->d_sphere_part, chunks, n,
                                                             out + (long long)sk0 * p->nb);
   JRB_CHECK_LAUNCH("k_sum_chunks");
   return 0;

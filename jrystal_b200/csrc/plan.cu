@@ -313,7 +313,7 @@ extern "C" int jrb_plan_create(const jrb_plan_desc* d, jrb_plan** out) {
   TRY(dev_alloc(&p->d_gpart, (size_t)p->nb * p->nb * (size_t)qr_gram_partial_mats(p), &tot));
   TRY(dev_alloc(&p->d_tkb, (size_t)p->ns * p->nk * p->nb, &tot));
   TRY(dev_alloc(&p->d_eps, (size_t)p->ns * p->nk * p->nb, &tot));
-  TRY(dev_alloc(&p->d_sphere_part, (size_t)8 * p->ns * p->nk * p->nb, &tot));
+  TRY(dev_alloc(&p->d_sphere_part, ((size_t)8 * p->ns * p->nk + 640) * p->nb, &tot));
   TRY(dev_alloc(&p->d_scal, 64, &tot));
   JRB_CUDA(cudaMemset(p->d_scal, 0, 64 * sizeof(double)));
   JRB_CUDA(cudaStreamCreateWithFlags(&p->own_stream, cudaStreamNonBlocking));

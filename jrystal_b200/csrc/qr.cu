@@ -177,6 +177,235 @@ k_tri_inv_cols(const cplx* __restrict__ R, int nb, cplx* __restrict__ Rinv) {
   for (int i = lane; i < nb; i += 32) Rinv[(long long)i * nb + j] = i <= j ? x[i] : cmake(0.0, 0.0);
 }
 
+// ---------------------------------------------------------------------------------------
+// Large matrices (Gamma-only supercells: one or a few 200 x 200 matrices): the one-CTA
+// recurrences above are pure latency (0.45 ms + 0.27 ms per call at nb = 208,
+// profiles/r01_ncu_c3a_baseline.md), so the work of one panel is spread over a CTA per
+// 32-row tile and the inverse over a CTA per 8 columns.
+//
+// Left-looking panel step of the Cholesky factorisation, one launch per 32-column panel p0.
+// Tile 0 owns the diagonal block, tile t > 0 the rows [p0 + 32 t, p0 + 32 t + 32).  Every CTA
+// updates and factors the diagonal block itself (redundant, but it removes a grid-wide
+// dependency), then solves its own rows against it.
+// grid: (1 + ceil((nb - p0 - 32) / 32), nsk), block 256
+constexpr int CP = 32;        // panel width == tile height
+constexpr int CP_LD = CP + 1;
+constexpr int CP_KC = 8;
+constexpr int CP_LK = CP_KC + 1;
+__global__ void __launch_bounds__(256)
+k_chol_panel(cplx* __restrict__ S, cplx* __restrict__ Rt, int nb, int p0, int* __restrict__ fail_flag) {
+  __shared__ cplx D[CP * CP_LD], T[CP * CP_LD], Ld[CP * CP_LK], Lr[CP * CP_LK];
+  const long long nn = (long long)nb * nb;
+  S += blockIdx.y * nn;
+  Rt += blockIdx.y * nn;
+  const int tid = threadIdx.x;
+  const int tile = blockIdx.x;
+  const int pw = min(CP, nb - p0);
+  const int r0 = p0 + CP * tile;
+  const int nr = tile > 0 ? min(CP, nb - r0) : 0;
+  // each thread owns the entries (r, c), r = tid / 32 + 8 j, c = tid % 32
+  const int c = tid & 31, rb = tid >> 5;
+  cplx accD[4], accT[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int r = rb + 8 * j;
+    accD[j] = (r < pw && c < pw) ? S[(long long)(p0 + r) * nb + p0 + c] : cmake(0.0, 0.0);
+    accT[j] = (r < nr && c < pw) ? S[(long long)(r0 + r) * nb + p0 + c] : cmake(0.0, 0.0);
+  }
+  for (int k0 = 0; k0 < p0; k0 += CP_KC) {  // p0 is a multiple of CP_KC
+    __syncthreads();
+    for (int e = tid; e < CP * CP_KC; e += 256) {
+      const int r = e / CP_KC, k = e % CP_KC;
+      Ld[r * CP_LK + k] = r < pw ? S[(long long)(p0 + r) * nb + k0 + k] : cmake(0.0, 0.0);
+      Lr[r * CP_LK + k] = r < nr ? S[(long long)(r0 + r) * nb + k0 + k] : cmake(0.0, 0.0);
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < CP_KC; ++k) {
+      const cplx lc = Ld[c * CP_LK + k];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int r = rb + 8 * j;
+        const cplx u = cmulc(Ld[r * CP_LK + k], lc);
+        accD[j].x -= u.x; accD[j].y -= u.y;
+        const cplx v = cmulc(Lr[r * CP_LK + k], lc);
+        accT[j].x -= v.x; accT[j].y -= v.y;
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    D[(rb + 8 * j) * CP_LD + c] = accD[j];
+    T[(rb + 8 * j) * CP_LD + c] = accT[j];
+  }
+  __syncthreads();
+  // factor the diagonal block (lower triangle) in shared memory
+  for (int j = 0; j < pw; ++j) {
+    const double djj = D[j * CP_LD + j].x;
+    if (!(djj > 0.0) && tid == 0 && tile == 0) atomicExch(fail_flag, 1);
+    const double d = sqrt(djj > 0.0 ? djj : 1.0);
+    const double inv = 1.0 / d;
+    __syncthreads();
+    if (tid >= j && tid < pw) {
+      const cplx v = D[tid * CP_LD + j];
+      D[tid * CP_LD + j] = tid == j ? cmake(d, 0.0) : cmake(v.x * inv, v.y * inv);
+    }
+    __syncthreads();
+    if (c > j && c < pw) {
+      const cplx lc = D[c * CP_LD + j];
+#pragma unroll
+      for (int jj = 0; jj < 4; ++jj) {
+        const int r = rb + 8 * jj;
+        if (r >= c && r < pw) {
+          const cplx v = cmulc(D[r * CP_LD + j], lc);
+          D[r * CP_LD + c].x -= v.x;
+          D[r * CP_LD + c].y -= v.y;
+        }
+      }
+    }
+  }
+  __syncthreads();
+  if (tile == 0) {
+    // L (lower) back into S, R = L^H into Rt (zeros below its diagonal)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int r = rb + 8 * j;
+      if (r < pw && c < pw) {
+        const cplx v = r >= c ? D[r * CP_LD + c] : cmake(0.0, 0.0);
+        S[(long long)(p0 + r) * nb + p0 + c] = v;
+        Rt[(long long)(p0 + c) * nb + p0 + r] = cconj(v);
+      }
+    }
+    return;
+  }
+  // rows below: X L11^H = T, column by column (right-looking inside the tile)
+  for (int j = 0; j < pw; ++j) {
+    const double inv = 1.0 / D[j * CP_LD + j].x;
+    if (tid < nr) {
+      const cplx v = T[tid * CP_LD + j];
+      T[tid * CP_LD + j] = cmake(v.x * inv, v.y * inv);
+    }
+    __syncthreads();
+    if (c > j && c < pw) {
+      const cplx lc = D[c * CP_LD + j];
+#pragma unroll
+      for (int jj = 0; jj < 4; ++jj) {
+        const int r = rb + 8 * jj;
+        if (r < nr) {
+          const cplx v = cmulc(T[r * CP_LD + j], lc);
+          T[r * CP_LD + c].x -= v.x;
+          T[r * CP_LD + c].y -= v.y;
+        }
+      }
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int r = rb + 8 * j;
+    if (r < nr && c < pw) {
+      const cplx v = T[r * CP_LD + c];
+      S[(long long)(r0 + r) * nb + p0 + c] = v;
+      Rt[(long long)(p0 + c) * nb + r0 + r] = cconj(v);
+      Rt[(long long)(r0 + r) * nb + p0 + c] = cmake(0.0, 0.0);
+    }
+  }
+}
+
+// Blocked inverse of an upper-triangular R, step 1: the 32 x 32 diagonal blocks (one thread per
+// column, the block staged in shared memory).   grid: (ceil(nb / 32), nsk), block 32
+__global__ void __launch_bounds__(32)
+k_tri_inv_diag(const cplx* __restrict__ R, int nb, cplx* __restrict__ Rinv) {
+  __shared__ cplx U[CP * CP_LD], X[CP * CP_LD];
+  const long long nn = (long long)nb * nb;
+  R += blockIdx.y * nn;
+  Rinv += blockIdx.y * nn;
+  const int b0 = blockIdx.x * CP, bw = min(CP, nb - b0);
+  const int j = threadIdx.x;
+  for (int i = 0; i < bw; ++i)
+    if (j < bw) U[i * CP_LD + j] = R[(long long)(b0 + i) * nb + b0 + j];
+  __syncwarp();
+  if (j < bw) {
+    for (int i = bw - 1; i > j; --i) X[i * CP_LD + j] = cmake(0.0, 0.0);
+    {
+      const cplx d = U[j * CP_LD + j];
+      const double n2 = d.x * d.x + d.y * d.y;
+      X[j * CP_LD + j] = cmake(d.x / n2, -d.y / n2);
+    }
+    for (int i = j - 1; i >= 0; --i) {
+      double sx = 0.0, sy = 0.0;
+      for (int k = i + 1; k <= j; ++k) {
+        const cplx v = cmul(U[i * CP_LD + k], X[k * CP_LD + j]);
+        sx += v.x; sy += v.y;
+      }
+      const cplx d = U[i * CP_LD + i];
+      const double n2 = d.x * d.x + d.y * d.y;
+      X[i * CP_LD + j] = cmake(-(sx * d.x + sy * d.y) / n2, -(sy * d.x - sx * d.y) / n2);
+    }
+  }
+  __syncwarp();
+  for (int i = 0; i < bw; ++i)
+    if (j < bw) Rinv[(long long)(b0 + i) * nb + b0 + j] = X[i * CP_LD + j];
+}
+
+// Step 2: the blocks above the diagonal.  A CTA owns 8 columns of block column J and walks the
+// block rows I = J-1 .. 0:  X[I] = -Xd[I] (sum_{K = I+1..J} R[I][K] X[K]),  Xd = diagonal-block
+// inverses of step 1 (already in Rinv).  Also zeroes its columns below the diagonal block.
+// grid: (4 * ceil(nb / 32), nsk), block 256 = 32 rows x 8 columns;
+// dynamic smem: (ceil(nb / 32) * 32) x 8 complex (the CTA's columns of X)
+__global__ void __launch_bounds__(256)
+k_tri_inv_offdiag(const cplx* __restrict__ R, int nb, cplx* __restrict__ Rinv) {
+  extern __shared__ __align__(16) unsigned char smem_raw_[];
+  cplx* Xc = reinterpret_cast<cplx*>(smem_raw_);  // [rows][8]
+  __shared__ cplx A[CP * CP_LD], Y[CP * 8];
+  const long long nn = (long long)nb * nb;
+  R += blockIdx.y * nn;
+  Rinv += blockIdx.y * nn;
+  const int J = blockIdx.x >> 2, c0 = J * CP + (blockIdx.x & 3) * 8;
+  const int tid = threadIdx.x, r = tid >> 3, c = tid & 7;
+  const int col = c0 + c;
+  const bool col_ok = col < nb;
+  // diagonal block rows of these columns (from step 1); rows below the block are zero
+  {
+    const int row = J * CP + r;
+    Xc[row * 8 + c] = (row < nb && col_ok) ? Rinv[(long long)row * nb + col] : cmake(0.0, 0.0);
+    for (int rr = (J + 1) * CP + r; rr < nb; rr += CP)
+      if (col_ok) Rinv[(long long)rr * nb + col] = cmake(0.0, 0.0);
+  }
+  for (int I = J - 1; I >= 0; --I) {
+    cplx acc = cmake(0.0, 0.0);
+    for (int K = I + 1; K <= J; ++K) {
+      __syncthreads();
+      for (int e = tid; e < CP * CP; e += 256) {
+        const int i = e >> 5, k = e & 31;
+        const int gc = K * CP + k;
+        A[i * CP_LD + k] = gc < nb ? R[(long long)(I * CP + i) * nb + gc] : cmake(0.0, 0.0);
+      }
+      __syncthreads();
+#pragma unroll 8
+      for (int k = 0; k < CP; ++k) {
+        const cplx v = cmul(A[r * CP_LD + k], Xc[(K * CP + k) * 8 + c]);
+        acc.x += v.x; acc.y += v.y;
+      }
+    }
+    __syncthreads();
+    Y[r * 8 + c] = acc;
+    for (int e = tid; e < CP * CP; e += 256) {
+      const int i = e >> 5, k = e & 31;
+      A[i * CP_LD + k] = Rinv[(long long)(I * CP + i) * nb + I * CP + k];  // I < J: full block
+    }
+    __syncthreads();
+    cplx out = cmake(0.0, 0.0);
+#pragma unroll 8
+    for (int k = 0; k < CP; ++k) {
+      const cplx v = cmul(A[r * CP_LD + k], Y[k * 8 + c]);
+      out.x -= v.x; out.y -= v.y;
+    }
+    Xc[(I * CP + r) * 8 + c] = out;
+    if (col_ok) Rinv[(long long)(I * CP + r) * nb + col] = out;
+  }
+}
+
 // Second Cholesky-QR pass: r = R2 r_prev, rinv = rinv_prev R2inv (all upper triangular).
 // Outputs must not alias the inputs.   grid: (ceil(nb^2 / 256), nsk)
 __global__ void __launch_bounds__(SMALL_T)
@@ -358,12 +587,42 @@ int launch_hamiltonian_matrix(jrb_plan* p, const cplx* q, const cplx* hq, cplx* 
   return 0;
 }
 
+// Above this size the per-matrix recurrences are spread over several CTAs (more launches, far
+// less latency); below it one CTA per (spin,k) with batch parallelism is the better shape.
+constexpr int LARGE_NB = 96;
+
+// Rinv = R^-1 (upper triangular)
+static int tri_inverse(const cplx* R, int nb, int nsk, cplx* Rinv, cudaStream_t st) {
+  if (nb > LARGE_NB) {
+    const int nblk = (nb + CP - 1) / CP;
+    k_tri_inv_diag<<<dim3(nblk, nsk), 32, 0, st>>>(R, nb, Rinv);
+    JRB_CHECK_LAUNCH("k_tri_inv_diag");
+    k_tri_inv_offdiag<<<dim3(4 * nblk, nsk), 256, nblk * CP * 8 * (int)sizeof(cplx), st>>>(R, nb, Rinv);
+    JRB_CHECK_LAUNCH("k_tri_inv_offdiag");
+    return 0;
+  }
+  dim3 igrid((nb + 7) / 8, nsk);
+  k_tri_inv_cols<<<igrid, 256, 8 * nb * (int)sizeof(cplx), st>>>(R, nb, Rinv);
+  JRB_CHECK_LAUNCH("k_tri_inv_cols");
+  return 0;
+}
+
 static int chol_and_inverse(jrb_plan* p, int nsk, int nchunks, cplx* S, cplx* Rt, cplx* Rit,
                             cudaStream_t st) {
   const int nb = p->nb;
   dim3 egrid((unsigned)(((long long)nb * nb + SMALL_T - 1) / SMALL_T), nsk);
   k_gram_reduce<<<egrid, SMALL_T, 0, st>>>(p->d_gpart, nchunks, nb, S);
   JRB_CHECK_LAUNCH("k_gram_reduce");
+  int* fail = reinterpret_cast<int*>(p->d_scal + 32);
+  if (nb > LARGE_NB) {
+    for (int p0 = 0; p0 < nb; p0 += CP) {
+      const int below = std::max(0, nb - p0 - CP);
+      dim3 grid(1 + (below + CP - 1) / CP, nsk);
+      k_chol_panel<<<grid, 256, 0, st>>>(S, Rt, nb, p0, fail);
+      JRB_CHECK_LAUNCH("k_chol_panel");
+    }
+    return tri_inverse(Rt, nb, nsk, Rit, st);
+  }
   const int smem = nb * (CHOL_PB + 1 + CHOL_KC + 1) * (int)sizeof(cplx);
   static int once = opt_in_smem(k_chol_blocked, 200 * 1024);
   if (once) return once;
@@ -371,13 +630,9 @@ static int chol_and_inverse(jrb_plan* p, int nsk, int nchunks, cplx* S, cplx* Rt
     set_error("Cholesky panel does not fit shared memory (too many bands)");
     return JRB_EUNSUPPORTED;
   }
-  int* fail = reinterpret_cast<int*>(p->d_scal + 32);
   k_chol_blocked<<<nsk, CHOL_T, smem, st>>>(S, Rt, nb, fail);
   JRB_CHECK_LAUNCH("k_chol_blocked");
-  dim3 igrid((nb + 7) / 8, nsk);
-  k_tri_inv_cols<<<igrid, 256, 8 * nb * (int)sizeof(cplx), st>>>(Rt, nb, Rit);
-  JRB_CHECK_LAUNCH("k_tri_inv_cols");
-  return 0;
+  return tri_inverse(Rt, nb, nsk, Rit, st);
 }
 
 // Cholesky-QR2 of the (spin,k) range [sk0, sk0 + nsk).  q / r are indexed from sk0.
@@ -428,11 +683,10 @@ int launch_qr_bwd_range(jrb_plan* p, int sk0, int nsk, const cplx* q, const cplx
   const long long nall = (long long)p->ns * p->nk * nn;
   const long long soff = (long long)sk0 * p->ng * nb, moff = (long long)sk0 * nn;
   const cplx* rinv = p->d_rinv + moff;  // R^-1 of the plan's own forward call
+  int rc0 = 0;
   if (r != p->d_r) {
     cplx* ri = p->d_small + 3 * nall + moff;
-    dim3 igrid((nb + 7) / 8, nsk);
-    k_tri_inv_cols<<<igrid, 256, 8 * nb * (int)sizeof(cplx), st>>>(r + moff, nb, ri);
-    JRB_CHECK_LAUNCH("k_tri_inv_cols");
+    if ((rc0 = tri_inverse(r + moff, nb, nsk, ri, st))) return rc0;
     rinv = ri;
   }
   cplx* X = p->d_small + moff;
