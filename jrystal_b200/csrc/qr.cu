@@ -263,8 +263,8 @@ k_chol_panel(cplx* __restrict__ S, cplx* __restrict__ Rt, int nb, int p0, int* _
         }
       }
     }
+    __syncthreads();
   }
-  __syncthreads();
   if (tile == 0) {
     // L (lower) back into S, R = L^H into Rt (zeros below its diagonal)
 #pragma unroll
@@ -597,6 +597,8 @@ static int tri_inverse(const cplx* R, int nb, int nsk, cplx* Rinv, cudaStream_t 
     const int nblk = (nb + CP - 1) / CP;
     k_tri_inv_diag<<<dim3(nblk, nsk), 32, 0, st>>>(R, nb, Rinv);
     JRB_CHECK_LAUNCH("k_tri_inv_diag");
+    static int once = opt_in_smem(k_tri_inv_offdiag, 160 * 1024);
+    if (once) return once;
     k_tri_inv_offdiag<<<dim3(4 * nblk, nsk), 256, nblk * CP * 8 * (int)sizeof(cplx), st>>>(R, nb, Rinv);
     JRB_CHECK_LAUNCH("k_tri_inv_offdiag");
     return 0;

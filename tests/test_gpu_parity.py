@@ -29,6 +29,10 @@ CASES = {
                             cutoff=None, nb=12),
   'diamond_16': dict(name='diamond', grid=16, kgrid=[1, 1, 1], mask='spherical', cutoff=20, nb=9),
   'si_32': dict(name='si', grid=32, kgrid=[2, 1, 1], mask='spherical', cutoff=12, nb=18),
+  # 128^3 (the C3 benchmark grid): table twiddles, two resident CTAs per SM, unfused passes
+  'si8_128': dict(name='si8', grid=128, kgrid=[1, 1, 1], mask='spherical', cutoff=40, nb=6),
+  # more than 96 bands: multi-CTA panel Cholesky + blocked triangular inverse (C3-style QR)
+  'si8_32_nb130': dict(name='si8', grid=32, kgrid=[1, 1, 1], mask='spherical', cutoff=8, nb=130),
   'diamond_24x32x48': dict(name='diamond', grid=[24, 32, 48], kgrid=[1, 1, 2], mask='spherical',
                            cutoff=30, nb=10),
 }
