@@ -182,6 +182,113 @@ def run_reference(args):
   print(json.dumps(line), flush=True)
 
 
+def run_b200_rows(args, wl, world, rank, local_rank):
+  """Fewer k-points than GPUs (C3a, Gamma only): rows of the parameters sharded for the QR, bands
+  for the FFTs (jrystal_b200.parallel.RowShardedEvaluator); strong scaling."""
+  import torch
+  import torch.distributed as dist
+  from jrystal_b200 import _lib
+  from jrystal_b200.parallel import RowShardedEvaluator
+
+  c = wl['crystal']
+  nk, nb, ng = wl['kpts'].shape[0], wl['nb'], wl['ng']
+  ngrid = int(np.prod(wl['grid']))
+  ev = RowShardedEvaluator(c.cell_vectors, wl['mask'], wl['kpts'], nb, c.positions, c.charges,
+                           device=local_rank)
+  w_re_f, w_im_f = synthetic_params(ng, nk, nb, 0, nk)
+  w_re_h = np.ascontiguousarray(w_re_f[:, :, ev.g0:ev.g1])
+  w_im_h = np.ascontiguousarray(w_im_f[:, :, ev.g0:ev.g1])
+  del w_re_f, w_im_f
+  occ_h = np.ascontiguousarray(wl['occ'])
+  w_re, w_im, occ = (torch.from_numpy(a).cuda() for a in (w_re_h, w_im_h, occ_h))
+  result = {}
+
+  def step():
+    result['out'] = ev.evaluate(w_re, w_im, occ, 'lda_x')
+
+  def barrier():
+    dist.barrier()
+    torch.cuda.synchronize()
+
+  def timed(fn, steps):
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record()
+    for _ in range(steps):
+      fn()
+    ev1.record()
+    barrier()
+    ms = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device='cuda')
+    dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    return float(ms.item())
+
+  lib = _lib.load()
+  for _ in range(max(args.warmup, 3)):
+    step()
+  barrier()
+  launches0 = lib.jrb_launch_count()
+  with ClockSampler(local_rank) as clk:
+    total_ms = timed(step, args.steps)
+  launches = int(lib.jrb_launch_count() - launches0)
+  ms_per_step = total_ms / args.steps
+  value = 1e3 / ms_per_step
+  energies = result['out'][0].cpu().numpy().tolist()
+
+  pin = lambda a: torch.from_numpy(a).pin_memory()
+  w_re_p, w_im_p, occ_p = pin(w_re_h), pin(w_im_h), pin(occ_h)
+  en_p = torch.empty(4, dtype=torch.float64).pin_memory()
+  g_re_p = torch.empty(w_re_h.shape, dtype=torch.float64).pin_memory()
+  g_im_p = torch.empty(w_re_h.shape, dtype=torch.float64).pin_memory()
+
+  def e2e_step():
+    w_re.copy_(w_re_p, non_blocking=True)
+    w_im.copy_(w_im_p, non_blocking=True)
+    occ.copy_(occ_p, non_blocking=True)
+    step()
+    en, g_re, g_im, _ = result['out']
+    en_p.copy_(en, non_blocking=True)
+    g_re_p.copy_(g_re, non_blocking=True)
+    g_im_p.copy_(g_im, non_blocking=True)
+    torch.cuda.current_stream().synchronize()
+
+  e2e_steps = max(1, min(args.steps, 5))
+  e2e_step()
+  barrier()
+  t0 = time.perf_counter()
+  for _ in range(e2e_steps):
+    e2e_step()
+  barrier()
+  e2e_s = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device='cuda')
+  dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
+  e2e_value = e2e_steps / float(e2e_s.item())
+  nw = w_re_h.size
+  peak, peak_src = measured_peak()
+  m_local = nk * (ev.b1 - ev.b0)
+  bytes_alg = 64.0 * nk * nb * (ngrid + ng) / world  # per GPU share of the whole evaluation
+  whole_achieved = bytes_alg / (ms_per_step * 1e-3) / 1e9
+  if rank == 0:
+    line = {
+      'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
+      'warmup': max(args.warmup, 3), 'ms_per_step': ms_per_step, 'higher_is_better': True,
+      'scaling': 'strong', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
+      'config': {'workload': wl['text'], 'orbitals': nk * nb, 'ng': ng, 'grid': wl['grid'],
+                 'sharding': f'rows{world} (QR) + bands{world} (FFT), all-to-all between',
+                 'xc': 'lda_x', 'bands_per_rank': ev.b1 - ev.b0, 'rows_per_rank': ev.g1 - ev.g0,
+                 'l2': 'working set larger than L2 (pencil work space); no flush'},
+      'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': 2 * nw * 8 + occ_h.size * 8,
+              'd2h_bytes_per_step': 2 * nw * 8 + 32,
+              'path': 'pinned H2D of the row block + RowShardedEvaluator.evaluate (NCCL) + D2H'},
+      'gpu_launches': launches,
+      'roofline': {'bound': 'hbm', 'achieved': whole_achieved, 'peak': peak, 'unit': 'GB/s',
+                   'frac': whole_achieved / peak, 'traffic': None, 'peak_source': peak_src,
+                   'kernel': 'whole evaluation per GPU (64*M*(N+ng)/n_gpus algorithmic bytes)',
+                   'orbitals_per_gpu': m_local},
+      'clocks': clk.summary(), 'energies_ha': energies,
+    }
+    print(json.dumps(line), flush=True)
+  dist.destroy_process_group()
+
+
 def run_b200(args):
   import torch
   import torch.distributed as dist
@@ -202,13 +309,11 @@ def run_b200(args):
   c = wl['crystal']
   nk, nb, ng = wl['kpts'].shape[0], wl['nb'], wl['ng']
   ngrid = int(np.prod(wl['grid']))
-  if nk % world == 0:
-    k0, k1 = parallel.shard_kpoints(nk, world, rank)
-    b0, b1 = 0, nb
-    sharding = f'k{world}' if world > 1 else 'none'
-  else:
-    raise SystemExit(f'{args.config}: nk={nk} not divisible by {world} ranks '
-                     '(band-block sharding of a single k-point is not implemented yet)')
+  if nk % world != 0:
+    return run_b200_rows(args, wl, world, rank, local_rank)
+  k0, k1 = parallel.shard_kpoints(nk, world, rank)
+  b0, b1 = 0, nb
+  sharding = f'k{world}' if world > 1 else 'none'
   plan = jb.Plan(c.cell_vectors, wl['mask'], wl['kpts'][k0:k1], nb, device=local_rank)
   plan.set_atoms(c.positions, c.charges)
   w_re_h, w_im_h = synthetic_params(ng, nk, nb, k0, k1)

@@ -85,6 +85,33 @@ int jrb_qr_fwd(jrb_plan* plan, const double* w_re, const double* w_im, double* q
 int jrb_qr_bwd(jrb_plan* plan, const double* q, const double* r, const double* gq, double* g_re,
                double* g_im, jrb_stream stream);
 
+/* Row-sharded orthonormalisation (Gamma-only supercells have fewer k-points than
+ * GPUs, so the rows g of W are split over ranks for the QR while the bands are split for the
+ * FFTs).  Same mathematics as jrb_qr_fwd / jrb_qr_bwd (unitary_module.py:66-81 and its AD rule),
+ * cut where a sum over the row axis crosses ranks; the caller all-reduces (SUM) the small
+ * (ns, nk, nb, nb) complex matrices between the phases:
+ *     for pass in 0, 1:  jrb_qr_rows_gram(pass) -> all-reduce S -> jrb_qr_rows_apply(pass)
+ *     jrb_qr_rows_bwd_gram -> all-reduce M -> jrb_qr_rows_bwd_apply
+ * They work on the plan's ng rows: a full plan (then they equal jrb_qr_fwd/bwd on one rank) or a
+ * rows-only plan from jrb_plan_create_rows (this rank's row block; no grid, QR entry points only).
+ * w_re/w_im/q/gq/g_re/g_im: (ns, nk, nrows, nb).  pass 1 ignores w_re/w_im (it reads the Q1 of
+ * pass 0 from plan work space) and writes q and r.  S is overwritten by the factorisation.
+ * jrb_qr_rows_bwd_apply uses the R^-1 of the plan's own last forward call. */
+int jrb_plan_create_rows(int64_t nrows, int32_t ns, int32_t nk, int32_t nb, int32_t device,
+                         jrb_plan** out);
+int jrb_qr_rows_gram(jrb_plan* plan, const double* w_re, const double* w_im, int32_t pass,
+                     double* s_out, jrb_stream stream);
+int jrb_qr_rows_apply(jrb_plan* plan, const double* w_re, const double* w_im, int32_t pass,
+                      double* s_inout, double* q, double* r, jrb_stream stream);
+int jrb_qr_rows_bwd_gram(jrb_plan* plan, const double* q, const double* gq, double* m_out,
+                         jrb_stream stream);
+int jrb_qr_rows_bwd_apply(jrb_plan* plan, const double* q, const double* gq, const double* occ,
+                          const double* m, double* g_re, double* g_im, jrb_stream stream);
+
+/* Synchronises `stream` and reports a deferred numerical failure of the asynchronous calls
+ * (Cholesky breakdown on rank-deficient parameters): 0 or JRB_EINVAL. */
+int jrb_check_status(jrb_plan* plan, jrb_stream stream);
+
 /* utils.expand_coefficient (jrystal/_src/utils.py:277-281): (ns,nk,ng,nb) -> dense
  * (ns,nk,nb,nx,ny,nz).  Only for API parity; the fused paths never build the dense box. */
 int jrb_expand(jrb_plan* plan, const double* q, double* coeff_dense, jrb_stream stream);

@@ -31,6 +31,12 @@ SYMBOLS = {
   'jrb_set_atoms': (ctypes.c_int, [_P, _P, _P, _I32, _P]),
   'jrb_qr_fwd': (ctypes.c_int, [_P, _P, _P, _P, _P, _P]),
   'jrb_qr_bwd': (ctypes.c_int, [_P, _P, _P, _P, _P, _P, _P]),
+  'jrb_plan_create_rows': (ctypes.c_int, [_I64, _I32, _I32, _I32, _I32, ctypes.POINTER(_P)]),
+  'jrb_qr_rows_gram': (ctypes.c_int, [_P, _P, _P, _I32, _P, _P]),
+  'jrb_qr_rows_apply': (ctypes.c_int, [_P, _P, _P, _I32, _P, _P, _P, _P]),
+  'jrb_qr_rows_bwd_gram': (ctypes.c_int, [_P, _P, _P, _P, _P]),
+  'jrb_qr_rows_bwd_apply': (ctypes.c_int, [_P, _P, _P, _P, _P, _P, _P, _P]),
+  'jrb_check_status': (ctypes.c_int, [_P, _P]),
   'jrb_expand': (ctypes.c_int, [_P, _P, _P, _P]),
   'jrb_squeeze': (ctypes.c_int, [_P, _P, _P, _P]),
   'jrb_density': (ctypes.c_int, [_P, _P, _P, _P, _P]),

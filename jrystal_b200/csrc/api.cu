@@ -21,9 +21,13 @@ static inline cudaStream_t S(jrb_stream s) { return reinterpret_cast<cudaStream_
 static inline const cplx* C(const double* p) { return reinterpret_cast<const cplx*>(p); }
 static inline cplx* C(double* p) { return reinterpret_cast<cplx*>(p); }
 
-static int enter(jrb_plan* p) {
+static int enter(jrb_plan* p, bool needs_grid = true) {
   if (!p) {
     set_error("null plan");
+    return JRB_EINVAL;
+  }
+  if (needs_grid && p->ngrid == 0) {
+    set_error("this entry point needs a full plan (jrb_plan_create), not a rows-only plan");
     return JRB_EINVAL;
   }
   JRB_CUDA(cudaSetDevice(p->device));
@@ -39,7 +43,7 @@ extern "C" int jrb_set_atoms(jrb_plan* p, const double* pos_h, const double* chg
 
 extern "C" int jrb_qr_fwd(jrb_plan* p, const double* w_re, const double* w_im, double* q,
                           double* r, jrb_stream st) {
-  int rc = enter(p);
+  int rc = enter(p, false);
   if (rc) return rc;
   REQUIRE(w_re && w_im && q && r, "null array");
   return launch_qr_fwd(p, w_re, w_im, C(q), C(r), S(st));
@@ -47,10 +51,61 @@ extern "C" int jrb_qr_fwd(jrb_plan* p, const double* w_re, const double* w_im, d
 
 extern "C" int jrb_qr_bwd(jrb_plan* p, const double* q, const double* r, const double* gq,
                           double* g_re, double* g_im, jrb_stream st) {
-  int rc = enter(p);
+  int rc = enter(p, false);
   if (rc) return rc;
   REQUIRE(q && r && gq && g_re && g_im, "null array");
   return launch_qr_bwd(p, C(q), C(r), C(gq), nullptr, g_re, g_im, S(st));
+}
+
+extern "C" int jrb_qr_rows_gram(jrb_plan* p, const double* w_re, const double* w_im, int32_t pass,
+                                double* s_out, jrb_stream st) {
+  int rc = enter(p, false);
+  if (rc) return rc;
+  REQUIRE(pass == 0 || pass == 1, "pass must be 0 or 1");
+  REQUIRE(s_out && (pass == 1 || (w_re && w_im)), "null array");
+  if (pass == 0) JRB_CUDA(cudaMemsetAsync(p->d_scal + 32, 0, sizeof(double), S(st)));
+  return launch_qr_gram_phase(p, 0, p->ns * p->nk, w_re, w_im, pass, C(s_out), S(st));
+}
+
+extern "C" int jrb_qr_rows_apply(jrb_plan* p, const double* w_re, const double* w_im, int32_t pass,
+                                 double* s_inout, double* q, double* r, jrb_stream st) {
+  int rc = enter(p, false);
+  if (rc) return rc;
+  REQUIRE(pass == 0 || pass == 1, "pass must be 0 or 1");
+  REQUIRE(s_inout && (pass == 1 ? (q && r) : (w_re && w_im)), "null array");
+  return launch_qr_apply_phase(p, 0, p->ns * p->nk, w_re, w_im, pass, C(s_inout), C(q), C(r), S(st));
+}
+
+extern "C" int jrb_qr_rows_bwd_gram(jrb_plan* p, const double* q, const double* gq, double* m_out,
+                                    jrb_stream st) {
+  int rc = enter(p, false);
+  if (rc) return rc;
+  REQUIRE(q && gq && m_out, "null array");
+  return launch_qr_bwd_gram_phase(p, 0, p->ns * p->nk, C(q), C(gq), C(m_out), S(st));
+}
+
+extern "C" int jrb_qr_rows_bwd_apply(jrb_plan* p, const double* q, const double* gq,
+                                     const double* occ, const double* m, double* g_re,
+                                     double* g_im, jrb_stream st) {
+  int rc = enter(p, false);
+  if (rc) return rc;
+  REQUIRE(q && gq && m && g_re && g_im, "null array");
+  return launch_qr_bwd_apply_phase(p, 0, p->ns * p->nk, C(q), p->d_r, C(gq), occ, C(m), g_re, g_im,
+                                   S(st));
+}
+
+extern "C" int jrb_check_status(jrb_plan* p, jrb_stream st) {
+  int rc = enter(p, false);
+  if (rc) return rc;
+  JRB_CUDA(cudaStreamSynchronize(S(st)));
+  int fail = 0;
+  JRB_CUDA(cudaMemcpy(&fail, reinterpret_cast<int*>(p->d_scal + 32), sizeof(int),
+                      cudaMemcpyDeviceToHost));
+  if (fail) {
+    set_error("Cholesky-QR: Gram matrix not positive definite (rank-deficient parameters)");
+    return JRB_EINVAL;
+  }
+  return 0;
 }
 
 extern "C" int jrb_expand(jrb_plan* p, const double* q, double* dense, jrb_stream st) {

@@ -128,6 +128,53 @@ extern "C" int jrb_plan_destroy(jrb_plan* p) {
   return 0;
 }
 
+// QR-only plan over `nrows` rows of the coefficient matrices (row-sharded orthonormalisation of
+// Gamma-only supercells): no grid, no index maps; only the jrb_qr_rows_* entry
+// points accept it.
+extern "C" int jrb_plan_create_rows(int64_t nrows, int32_t ns, int32_t nk, int32_t nb,
+                                    int32_t device, jrb_plan** out) {
+  if (!out || nrows <= 0 || nk <= 0 || nb <= 0 || (ns != 1 && ns != 2)) {
+    set_error("jrb_plan_create_rows: bad sizes (need nrows,nk,nb > 0 and ns in {1,2})");
+    return JRB_EINVAL;
+  }
+  int ndev = 0;
+  JRB_CUDA(cudaGetDeviceCount(&ndev));
+  if (device < 0 || device >= ndev) {
+    set_error("jrb_plan_create_rows: bad device ordinal");
+    return JRB_EINVAL;
+  }
+  JRB_CUDA(cudaSetDevice(device));
+  jrb_plan* p = new jrb_plan();
+  std::memset(p, 0, sizeof(*p));
+  p->ns = ns; p->nk = nk; p->nb = nb;
+  p->ng = nrows;
+  p->device = device;
+  p->ngroups_per_k = (nb + NB - 1) / NB;
+  int rc = 0;
+  int64_t tot = 0;
+#define TRY(x)                 \
+  do {                         \
+    rc = (x);                  \
+    if (rc) {                  \
+      jrb_plan_destroy(p);     \
+      return rc;               \
+    }                          \
+  } while (0)
+  const size_t nsphere = (size_t)ns * nk * nrows * nb;
+  const size_t nsmall = (size_t)ns * nk * nb * nb;
+  TRY(dev_alloc(&p->d_tmp, nsphere, &tot));
+  TRY(dev_alloc(&p->d_r, nsmall, &tot));
+  TRY(dev_alloc(&p->d_rinv, nsmall, &tot));
+  TRY(dev_alloc(&p->d_small, nsmall * 5, &tot));
+  TRY(dev_alloc(&p->d_gpart, (size_t)nb * nb * (size_t)qr_gram_partial_mats(p), &tot));
+  TRY(dev_alloc(&p->d_scal, 64, &tot));
+  JRB_CUDA(cudaMemset(p->d_scal, 0, 64 * sizeof(double)));
+#undef TRY
+  p->ws_bytes = tot;
+  *out = p;
+  return 0;
+}
+
 extern "C" int jrb_plan_create(const jrb_plan_desc* d, jrb_plan** out) {
   if (!d || !out || !d->mask || !d->kpts || !d->cell) {
     set_error("jrb_plan_create: null argument");

@@ -118,6 +118,16 @@ int launch_focc(jrb_plan* p, const double* occ, cudaStream_t st);
 
 // qr.cu
 int qr_gram_partial_mats(const jrb_plan* p);
+// split-phase QR (row-sharded callers all-reduce S / M between the phases)
+int launch_qr_gram_phase(jrb_plan* p, int sk0, int nsk, const double* w_re, const double* w_im,
+                         int pass, cplx* S, cudaStream_t st);
+int launch_qr_apply_phase(jrb_plan* p, int sk0, int nsk, const double* w_re, const double* w_im,
+                          int pass, cplx* S, cplx* qout, cplx* r, cudaStream_t st);
+int launch_qr_bwd_gram_phase(jrb_plan* p, int sk0, int nsk, const cplx* q, const cplx* gq, cplx* M,
+                             cudaStream_t st);
+int launch_qr_bwd_apply_phase(jrb_plan* p, int sk0, int nsk, const cplx* q, const cplx* r,
+                              const cplx* gq, const double* occ, const cplx* M, double* g_re,
+                              double* g_im, cudaStream_t st);
 int launch_qr_fwd_range(jrb_plan* p, int sk0, int nsk, const double* w_re, const double* w_im,
                         cplx* q, cplx* r, cudaStream_t st);
 int launch_qr_bwd_range(jrb_plan* p, int sk0, int nsk, const cplx* q, const cplx* r,

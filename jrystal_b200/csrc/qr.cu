@@ -609,12 +609,17 @@ static int tri_inverse(const cplx* R, int nb, int nsk, cplx* Rinv, cudaStream_t 
   return 0;
 }
 
-static int chol_and_inverse(jrb_plan* p, int nsk, int nchunks, cplx* S, cplx* Rt, cplx* Rit,
-                            cudaStream_t st) {
-  const int nb = p->nb;
-  dim3 egrid((unsigned)(((long long)nb * nb + SMALL_T - 1) / SMALL_T), nsk);
-  k_gram_reduce<<<egrid, SMALL_T, 0, st>>>(p->d_gpart, nchunks, nb, S);
+// S[sk] = Hermitian sum of the Gram partials in d_gpart
+static int reduce_gram(jrb_plan* p, int nsk, int nchunks, cplx* S, cudaStream_t st) {
+  dim3 egrid((unsigned)(((long long)p->nb * p->nb + SMALL_T - 1) / SMALL_T), nsk);
+  k_gram_reduce<<<egrid, SMALL_T, 0, st>>>(p->d_gpart, nchunks, p->nb, S);
   JRB_CHECK_LAUNCH("k_gram_reduce");
+  return 0;
+}
+
+// S (Hermitian, destroyed) -> Rt = chol(S)^H, Rit = Rt^-1
+static int chol_and_inverse(jrb_plan* p, int nsk, cplx* S, cplx* Rt, cplx* Rit, cudaStream_t st) {
+  const int nb = p->nb;
   int* fail = reinterpret_cast<int*>(p->d_scal + 32);
   if (nb > LARGE_NB) {
     for (int p0 = 0; p0 < nb; p0 += CP) {
@@ -637,38 +642,72 @@ static int chol_and_inverse(jrb_plan* p, int nsk, int nchunks, cplx* S, cplx* Rt
   return tri_inverse(Rt, nb, nsk, Rit, st);
 }
 
-// Cholesky-QR2 of the (spin,k) range [sk0, sk0 + nsk).  q / r are indexed from sk0.
+// Cholesky-QR2 of the (spin,k) range [sk0, sk0 + nsk), in phases so that a row-sharded caller can
+// all-reduce the Gram matrices in between (jrb_qr_rows_*): pass 0 works on W, pass 1 on Q1.
+struct QrSlots {
+  cplx *S, *Rt, *Rit, *R1, *R1inv, *tmp, *rinv;
+  long long soff, moff;
+};
+static QrSlots qr_slots(jrb_plan* p, int sk0) {
+  const long long nn = (long long)p->nb * p->nb;
+  const long long nall = (long long)p->ns * p->nk * nn;
+  QrSlots q;
+  q.soff = (long long)sk0 * p->ng * p->nb;
+  q.moff = (long long)sk0 * nn;
+  q.S = p->d_small + q.moff;                 // slot 0: Gram / Cholesky work
+  q.Rt = p->d_small + nall + q.moff;         // slot 1: R of the current pass
+  q.Rit = p->d_small + 2 * nall + q.moff;    // slot 2: its inverse
+  q.R1 = p->d_small + 3 * nall + q.moff;     // slot 3: R1 (first pass), kept for the compose
+  q.R1inv = p->d_small + 4 * nall + q.moff;  // slot 4
+  q.tmp = p->d_tmp + q.soff;
+  q.rinv = p->d_rinv + q.moff;
+  return q;
+}
+
+// Gram matrix of pass `pass` into S (Hermitian, full storage), S indexed from sk0
+int launch_qr_gram_phase(jrb_plan* p, int sk0, int nsk, const double* w_re, const double* w_im,
+                         int pass, cplx* S, cudaStream_t st) {
+  const QrSlots q = qr_slots(p, sk0);
+  int nchunks = 0, rc = 0;
+  TallMat A = pass == 0 ? TallMat{w_re + q.soff, w_im + q.soff, p->nb}
+                        : TallMat{reinterpret_cast<const double*>(q.tmp), nullptr, p->nb};
+  if ((rc = run_gram(p, nsk, A, A, true, p->d_gpart, &nchunks, st))) return rc;
+  return reduce_gram(p, nsk, nchunks, S, st);
+}
+
+// Factor S (destroyed) and apply: pass 0: Q1 = W R1^-1 (plan work space); pass 1: R2, Q = Q1 R2^-1,
+// R = R2 R1, R^-1 = R1^-1 R2^-1.
+int launch_qr_apply_phase(jrb_plan* p, int sk0, int nsk, const double* w_re, const double* w_im,
+                          int pass, cplx* S, cplx* qout, cplx* r, cudaStream_t st) {
+  const QrSlots q = qr_slots(p, sk0);
+  const int nb = p->nb;
+  int rc = 0;
+  TallMat none{nullptr, nullptr, 0};
+  if (pass == 0) {
+    TallMat W{w_re + q.soff, w_im + q.soff, nb};
+    if ((rc = chol_and_inverse(p, nsk, S, q.R1, q.R1inv, st))) return rc;
+    return run_apply<0>(p, nsk, W, q.R1inv, TRI_UPPER, none, nullptr, TRI_FULL, 1,
+                        reinterpret_cast<double*>(q.tmp), nullptr, st);
+  }
+  TallMat Q1{reinterpret_cast<const double*>(q.tmp), nullptr, nb};
+  if ((rc = chol_and_inverse(p, nsk, S, q.Rt, q.Rit, st))) return rc;
+  const long long nn = (long long)nb * nb;
+  dim3 egrid((unsigned)((nn + SMALL_T - 1) / SMALL_T), nsk);
+  k_tri_compose<<<egrid, SMALL_T, 0, st>>>(q.Rt, q.Rit, q.R1, q.R1inv, nb, r + q.moff, q.rinv);
+  JRB_CHECK_LAUNCH("k_tri_compose");
+  return run_apply<0>(p, nsk, Q1, q.Rit, TRI_UPPER, none, nullptr, TRI_FULL, 1,
+                      reinterpret_cast<double*>(qout + q.soff), nullptr, st);
+}
+
 int launch_qr_fwd_range(jrb_plan* p, int sk0, int nsk, const double* w_re, const double* w_im,
                         cplx* q, cplx* r, cudaStream_t st) {
-  const int nb = p->nb;
-  const long long nn = (long long)nb * nb;
-  const long long nall = (long long)p->ns * p->nk * nn;
-  const long long soff = (long long)sk0 * p->ng * nb, moff = (long long)sk0 * nn;
-  cplx* S = p->d_small + moff;                // slot 0: Gram / Cholesky work
-  cplx* Rt = p->d_small + nall + moff;        // slot 1: R of the current pass
-  cplx* Rit = p->d_small + 2 * nall + moff;   // slot 2: its inverse
-  cplx* R1 = p->d_small + 3 * nall + moff;    // slot 3: R1 (first pass), kept for the compose
-  cplx* R1inv = p->d_small + 4 * nall + moff; // slot 4
-  cplx* tmp = p->d_tmp + soff;
-  cplx* rinv = p->d_rinv + moff;
-  int nchunks = 0, rc = 0;
-  TallMat W{w_re + soff, w_im + soff, nb};
-  TallMat none{nullptr, nullptr, 0};
-  // pass 1: R1, Q1 = W R1^-1
-  if ((rc = run_gram(p, nsk, W, W, true, p->d_gpart, &nchunks, st))) return rc;
-  if ((rc = chol_and_inverse(p, nsk, nchunks, S, R1, R1inv, st))) return rc;
-  if ((rc = run_apply<0>(p, nsk, W, R1inv, TRI_UPPER, none, nullptr, TRI_FULL, 1,
-                         reinterpret_cast<double*>(tmp), nullptr, st)))
-    return rc;
-  // pass 2: R2, Q = Q1 R2^-1; R = R2 R1, R^-1 = R1^-1 R2^-1
-  TallMat Q1{reinterpret_cast<const double*>(tmp), nullptr, nb};
-  if ((rc = run_gram(p, nsk, Q1, Q1, true, p->d_gpart, &nchunks, st))) return rc;
-  if ((rc = chol_and_inverse(p, nsk, nchunks, S, Rt, Rit, st))) return rc;
-  dim3 egrid((unsigned)((nn + SMALL_T - 1) / SMALL_T), nsk);
-  k_tri_compose<<<egrid, SMALL_T, 0, st>>>(Rt, Rit, R1, R1inv, nb, r + moff, rinv);
-  JRB_CHECK_LAUNCH("k_tri_compose");
-  return run_apply<0>(p, nsk, Q1, Rit, TRI_UPPER, none, nullptr, TRI_FULL, 1,
-                      reinterpret_cast<double*>(q + soff), nullptr, st);
+  const QrSlots sl = qr_slots(p, sk0);
+  int rc = 0;
+  for (int pass = 0; pass < 2; ++pass) {
+    if ((rc = launch_qr_gram_phase(p, sk0, nsk, w_re, w_im, pass, sl.S, st))) return rc;
+    if ((rc = launch_qr_apply_phase(p, sk0, nsk, w_re, w_im, pass, sl.S, q, r, st))) return rc;
+  }
+  return 0;
 }
 
 int launch_qr_fwd(jrb_plan* p, const double* w_re, const double* w_im, cplx* q, cplx* r,
@@ -676,35 +715,51 @@ int launch_qr_fwd(jrb_plan* p, const double* w_re, const double* w_im, cplx* q, 
   return launch_qr_fwd_range(p, 0, p->ns * p->nk, w_re, w_im, q, r, st);
 }
 
-// Adjoint for the (spin,k) range [sk0, sk0 + nsk); all arrays indexed from (spin,k) 0.
-int launch_qr_bwd_range(jrb_plan* p, int sk0, int nsk, const cplx* q, const cplx* r,
-                        const cplx* gq, const double* occ, double* g_re, double* g_im,
-                        cudaStream_t st) {
+// Adjoint for the (spin,k) range [sk0, sk0 + nsk); all arrays indexed from (spin,k) 0.  Two phases
+// (M = Q^H G, then the small algebra + the tall product) for the same reason as the forward.
+int launch_qr_bwd_gram_phase(jrb_plan* p, int sk0, int nsk, const cplx* q, const cplx* gq, cplx* M,
+                             cudaStream_t st) {
+  const QrSlots sl = qr_slots(p, sk0);
+  int nchunks = 0, rc = 0;
+  TallMat Q{reinterpret_cast<const double*>(q + sl.soff), nullptr, p->nb};
+  TallMat G{reinterpret_cast<const double*>(gq + sl.soff), nullptr, p->nb};
+  if ((rc = run_gram(p, nsk, Q, G, false, p->d_gpart, &nchunks, st))) return rc;
+  return reduce_gram(p, nsk, nchunks, M, st);  // only the upper triangle of M is consumed
+}
+
+// M: (nsk, nb, nb) reduced Q^H G of this range (upper triangle), must not alias the plan's slots 0-2
+int launch_qr_bwd_apply_phase(jrb_plan* p, int sk0, int nsk, const cplx* q, const cplx* r,
+                              const cplx* gq, const double* occ, const cplx* M, double* g_re,
+                              double* g_im, cudaStream_t st) {
   const int nb = p->nb;
   const long long nn = (long long)nb * nb;
-  const long long nall = (long long)p->ns * p->nk * nn;
-  const long long soff = (long long)sk0 * p->ng * nb, moff = (long long)sk0 * nn;
-  const cplx* rinv = p->d_rinv + moff;  // R^-1 of the plan's own forward call
-  int rc0 = 0;
+  const QrSlots sl = qr_slots(p, sk0);
+  const cplx* rinv = sl.rinv;  // R^-1 of the plan's own forward call
+  int rc = 0;
   if (r != p->d_r) {
-    cplx* ri = p->d_small + 3 * nall + moff;
-    if ((rc0 = tri_inverse(r + moff, nb, nsk, ri, st))) return rc0;
-    rinv = ri;
+    if ((rc = tri_inverse(r + sl.moff, nb, nsk, sl.R1, st))) return rc;
+    rinv = sl.R1;
   }
-  cplx* X = p->d_small + moff;
-  cplx* T1 = p->d_small + nall + moff;
-  cplx* T2 = p->d_small + 2 * nall + moff;
-  int nchunks = 0, rc = 0;
-  TallMat Q{reinterpret_cast<const double*>(q + soff), nullptr, nb};
-  TallMat G{reinterpret_cast<const double*>(gq + soff), nullptr, nb};
-  if ((rc = run_gram(p, nsk, Q, G, false, p->d_gpart, &nchunks, st))) return rc;
+  cplx* X = sl.S;
+  cplx* T1 = sl.Rt;
+  cplx* T2 = sl.Rit;
+  TallMat Q{reinterpret_cast<const double*>(q + sl.soff), nullptr, nb};
+  TallMat G{reinterpret_cast<const double*>(gq + sl.soff), nullptr, nb};
   dim3 egrid((unsigned)((nn + SMALL_T - 1) / SMALL_T), nsk);
-  k_bwd_x<<<egrid, SMALL_T, 0, st>>>(p->d_gpart, nchunks, nb, occ ? occ + (long long)sk0 * nb : nullptr,
-                                     rinv, X, T1);
+  k_bwd_x<<<egrid, SMALL_T, 0, st>>>(M, 1, nb, occ ? occ + (long long)sk0 * nb : nullptr, rinv, X, T1);
   JRB_CHECK_LAUNCH("k_bwd_x");
   k_bwd_t2<<<egrid, SMALL_T, 0, st>>>(X, rinv, nb, T2);
   JRB_CHECK_LAUNCH("k_bwd_t2");
-  return run_apply<1>(p, nsk, G, T1, TRI_LOWER, Q, T2, TRI_FULL, 2, g_re + soff, g_im + soff, st);
+  return run_apply<1>(p, nsk, G, T1, TRI_LOWER, Q, T2, TRI_FULL, 2, g_re + sl.soff, g_im + sl.soff, st);
+}
+
+int launch_qr_bwd_range(jrb_plan* p, int sk0, int nsk, const cplx* q, const cplx* r,
+                        const cplx* gq, const double* occ, double* g_re, double* g_im,
+                        cudaStream_t st) {
+  const QrSlots sl = qr_slots(p, sk0);
+  int rc = 0;
+  if ((rc = launch_qr_bwd_gram_phase(p, sk0, nsk, q, gq, sl.R1inv, st))) return rc;
+  return launch_qr_bwd_apply_phase(p, sk0, nsk, q, r, gq, occ, sl.R1inv, g_re, g_im, st);
 }
 
 int launch_qr_bwd(jrb_plan* p, const cplx* q, const cplx* r, const cplx* gq, const double* occ,

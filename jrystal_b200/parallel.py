@@ -5,8 +5,9 @@ Mirrors the reference's `parallel_over_k_mesh` layout, NamedSharding(P('s','k'))
 parameters (calc/calc_ground_state_energy_all_electrons.py:83-91,151-158), where XLA inserts the
 all-reduce of rho where einsum('skb...,skb->s...') contracts the sharded k axis (pw.py:278).
 """
-from typing import Tuple
+from typing import List, Optional, Sequence, Tuple
 
+import numpy as np
 import torch
 import torch.distributed as dist
 
@@ -38,3 +39,125 @@ def allreduce_density(rho: torch.Tensor, e_kin: torch.Tensor) -> None:
   if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
     dist.all_reduce(rho, op=dist.ReduceOp.SUM)
     dist.all_reduce(e_kin, op=dist.ReduceOp.SUM)
+
+
+def shard_rows(num_g: int, world_size: int, rank: int) -> Tuple[int, int]:
+  """Contiguous block of sphere rows g of `rank` (row-sharded orthonormalisation)."""
+  return shard_bands(num_g, world_size, rank)
+
+
+def _world(group=None) -> Tuple[int, int]:
+  if dist.is_available() and dist.is_initialized():
+    return dist.get_world_size(group), dist.get_rank(group)
+  return 1, 0
+
+
+def allreduce_sum(*tensors: torch.Tensor, group=None) -> None:
+  if _world(group)[0] > 1:
+    for t in tensors:
+      dist.all_reduce(torch.view_as_real(t) if t.is_complex() else t, op=dist.ReduceOp.SUM,
+                      group=group)
+
+
+def rows_to_bands(x_rows: torch.Tensor, row_blocks: Sequence[Tuple[int, int]],
+                  band_blocks: Sequence[Tuple[int, int]], group=None) -> torch.Tensor:
+  """(ns, nk, rows of this rank, nb) -> (ns, nk, ng, bands of this rank): the all-to-all that
+  turns the row-sharded Q of the QR into the band-sharded Q of the FFTs.  Rank j
+  receives from every rank i that rank's row block of j's bands; row blocks are contiguous and
+  in rank order, so the received pieces concatenate to the full sphere."""
+  world, rank = _world(group)
+  b0, b1 = band_blocks[rank]
+  if world == 1:
+    return x_rows[..., b0:b1].contiguous()
+  lead = x_rows.shape[:2]
+  nlead = int(np.prod(lead))
+  send = torch.cat([x_rows[..., a:b].reshape(-1) for a, b in band_blocks])
+  in_splits = [nlead * (row_blocks[rank][1] - row_blocks[rank][0]) * (b - a) for a, b in band_blocks]
+  out_splits = [nlead * (g1 - g0) * (b1 - b0) for g0, g1 in row_blocks]
+  recv = torch.empty(sum(out_splits), dtype=x_rows.dtype, device=x_rows.device)
+  dist.all_to_all_single(torch.view_as_real(recv), torch.view_as_real(send),
+                         out_splits, in_splits, group=group)
+  pieces, off = [], 0
+  for (g0, g1), n in zip(row_blocks, out_splits):
+    pieces.append(recv[off:off + n].view(*lead, g1 - g0, b1 - b0))
+    off += n
+  return torch.cat(pieces, dim=2)
+
+
+def bands_to_rows(x_bands: torch.Tensor, row_blocks: Sequence[Tuple[int, int]],
+                  band_blocks: Sequence[Tuple[int, int]], group=None) -> torch.Tensor:
+  """Inverse of rows_to_bands: (ns, nk, ng, bands of this rank) -> (ns, nk, rows of this rank, nb)."""
+  world, rank = _world(group)
+  g0, g1 = row_blocks[rank]
+  if world == 1:
+    return x_bands[:, :, g0:g1].contiguous()
+  lead = x_bands.shape[:2]
+  nlead = int(np.prod(lead))
+  nbl = x_bands.shape[-1]
+  send = torch.cat([x_bands[:, :, a:b].reshape(-1) for a, b in row_blocks])
+  in_splits = [nlead * (b - a) * nbl for a, b in row_blocks]
+  out_splits = [nlead * (g1 - g0) * (b - a) for a, b in band_blocks]
+  recv = torch.empty(sum(out_splits), dtype=x_bands.dtype, device=x_bands.device)
+  dist.all_to_all_single(torch.view_as_real(recv), torch.view_as_real(send), out_splits, in_splits,
+                         group=group)
+  pieces, off = [], 0
+  for (a, b), n in zip(band_blocks, out_splits):
+    pieces.append(recv[off:off + n].view(*lead, g1 - g0, b - a))
+    off += n
+  return torch.cat(pieces, dim=3)
+
+
+class RowShardedEvaluator:
+  """Energy+gradient evaluation when there are fewer k-points than GPUs (Gamma-only supercells,
+  BASELINE config C3a): every rank owns a contiguous block of sphere ROWS of the parameters for
+  the orthonormalisation (Gram matrices all-reduced, Cholesky replicated) and a contiguous block
+  of BANDS for the FFT / density / H-apply work; two all-to-alls per evaluation move Q and HQ
+  between the layouts, and the partial densities are all-reduced as in the k-sharded case.
+  Parameters and gradients stay row-sharded: (ns, nk, rows of this rank, nb).
+
+  The reference has no such mode (its pmap mesh needs nk % ndev == 0, spmd/uniform.py:22-24); the
+  mathematics is that of the single-device evaluation, cut where sums cross ranks."""
+
+  def __init__(self, cell_vectors, freq_mask, kpts, num_bands, positions, charges, group=None,
+               device: Optional[int] = None, batch_groups: int = 0):
+    from .plan import Plan, RowsPlan
+    self.group = group
+    self.world, self.rank = _world(group)
+    mask = np.asarray(freq_mask)
+    self.ng = int(mask.sum())
+    self.nb = int(num_bands)
+    self.nk = int(np.asarray(kpts).reshape(-1, 3).shape[0])
+    self.row_blocks: List[Tuple[int, int]] = [shard_rows(self.ng, self.world, r)
+                                              for r in range(self.world)]
+    self.band_blocks: List[Tuple[int, int]] = [shard_bands(self.nb, self.world, r)
+                                               for r in range(self.world)]
+    self.g0, self.g1 = self.row_blocks[self.rank]
+    self.b0, self.b1 = self.band_blocks[self.rank]
+    if self.b1 == self.b0 or self.g1 == self.g0:
+      raise ValueError('more ranks than bands / rows')
+    self.rows = RowsPlan(self.g1 - self.g0, self.nk, self.nb, 1, device=device)
+    self.bands = Plan(cell_vectors, mask, kpts, self.b1 - self.b0, device=device,
+                      batch_groups=batch_groups)
+    self.bands.set_atoms(positions, charges)
+
+  def evaluate(self, w_re_rows, w_im_rows, occ, xc: str = 'lda_x'):
+    """w_re_rows, w_im_rows: (1, nk, rows of this rank, nb); occ: (1, nk, nb) full.
+    Returns energies[4] = (E_kin, E_ext, E_har, E_xc), dE/dw_re, dE/dw_im (row blocks), rho."""
+    rp, bp = self.rows, self.bands
+    for pass_ in (0, 1):
+      s = rp.gram(w_re_rows, w_im_rows, pass_)
+      allreduce_sum(s, group=self.group)
+      q_rows, _ = rp.apply(w_re_rows, w_im_rows, pass_, s)
+    q_band = rows_to_bands(q_rows, self.row_blocks, self.band_blocks, self.group)
+    occ_band = occ[:, :, self.b0:self.b1].contiguous()
+    rho = bp.density(q_band, occ_band)
+    e_kin = (bp.kinetic(q_band) * occ_band).sum().reshape(1)
+    allreduce_density(rho, e_kin) if self.group is None else allreduce_sum(rho, e_kin, group=self.group)
+    en, veff = bp.grid_potential(rho, xc, False)
+    hq_band = bp.hpsi(q_band, veff)
+    hq_rows = bands_to_rows(hq_band, self.row_blocks, self.band_blocks, self.group)
+    m = rp.bwd_gram(q_rows, hq_rows)
+    allreduce_sum(m, group=self.group)
+    g_re, g_im = rp.bwd_apply(q_rows, hq_rows, occ, m)
+    energies = torch.stack([e_kin[0], en[1], en[0], en[2]])
+    return energies, g_re, g_im, rho

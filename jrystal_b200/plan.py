@@ -271,3 +271,72 @@ class Plan:
       host_ptr(energies), host_ptr(g_re), host_ptr(g_im),
       None if rho is None else host_ptr(rho)))
     return energies, g_re, g_im, rho
+
+
+class RowsPlan:
+  """QR-only plan over a block of `nrows` rows of the (ns, nk, ng, nb) coefficient matrices
+  (jrb_plan_create_rows): the row-sharded half of the Gamma-only multi-GPU layout, SURVEY 8e.
+  The split-phase methods also exist on nothing else; between `gram` and `apply` the caller
+  all-reduces the small matrices over the ranks that hold the other row blocks."""
+
+  def __init__(self, nrows: int, num_k: int, num_bands: int, num_spin: int = 1,
+               device: Optional[int] = None):
+    if not torch.cuda.is_available():
+      raise RuntimeError('jrystal_b200 needs a CUDA device (there is no CPU fallback)')
+    self.lib = _lib.load()
+    self.device = torch.cuda.current_device() if device is None else int(device)
+    self.ns, self.nk, self.nb, self.ng = int(num_spin), int(num_k), int(num_bands), int(nrows)
+    handle = ctypes.c_void_p()
+    _lib.check(self.lib.jrb_plan_create_rows(self.ng, self.ns, self.nk, self.nb, self.device,
+                                             ctypes.byref(handle)))
+    self._h = handle
+    self.tdev = torch.device('cuda', self.device)
+
+  def __del__(self):
+    h = getattr(self, '_h', None)
+    if h:
+      self.lib.jrb_plan_destroy(h)
+      self._h = None
+
+  @property
+  def rows_shape(self):
+    return (self.ns, self.nk, self.ng, self.nb)
+
+  @property
+  def small_shape(self):
+    return (self.ns, self.nk, self.nb, self.nb)
+
+  def _new(self, shape, dtype):
+    return torch.empty(shape, dtype=dtype, device=self.tdev)
+
+  def gram(self, w_re, w_im, pass_: int, out=None):
+    s = self._new(self.small_shape, torch.complex128) if out is None else out
+    _lib.check(self.lib.jrb_qr_rows_gram(self._h, _ptr(w_re), _ptr(w_im), int(pass_), _ptr(s),
+                                         _stream()))
+    return s
+
+  def apply(self, w_re, w_im, pass_: int, s, q=None, r=None):
+    if pass_ == 1:
+      q = self._new(self.rows_shape, torch.complex128) if q is None else q
+      r = self._new(self.small_shape, torch.complex128) if r is None else r
+    _lib.check(self.lib.jrb_qr_rows_apply(self._h, _ptr(w_re), _ptr(w_im), int(pass_), _ptr(s),
+                                          _ptr(q), _ptr(r), _stream()))
+    return q, r
+
+  def bwd_gram(self, q, gq, out=None):
+    m = self._new(self.small_shape, torch.complex128) if out is None else out
+    _lib.check(self.lib.jrb_qr_rows_bwd_gram(self._h, _ptr(q), _ptr(gq), _ptr(m), _stream()))
+    return m
+
+  def bwd_apply(self, q, gq, occ, m, out=None):
+    if out is None:
+      g_re = self._new(self.rows_shape, torch.float64)
+      g_im = self._new(self.rows_shape, torch.float64)
+    else:
+      g_re, g_im = out
+    _lib.check(self.lib.jrb_qr_rows_bwd_apply(self._h, _ptr(q), _ptr(gq), _ptr(occ), _ptr(m),
+                                              _ptr(g_re), _ptr(g_im), _stream()))
+    return g_re, g_im
+
+  def check_status(self):
+    _lib.check(self.lib.jrb_check_status(self._h, _stream()))

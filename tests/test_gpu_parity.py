@@ -244,6 +244,35 @@ def test_large_band_count_qr(cuda_device):
   assert relerr(g_im[0, 0].cpu().numpy(), 2 * gw.imag) < 1e-10
 
 
+@pytest.mark.parametrize('case', ['diamond_16', 'si8_32_nb130'])
+def test_row_sharded_evaluator_single_rank(cuda_device, case):
+  """The split-phase QR (jrb_qr_rows_*) + band plan of the Gamma-only multi-GPU layout, world 1:
+  must equal the oracle like the fused evaluation does."""
+  from jrystal_b200.parallel import RowShardedEvaluator
+  c = CASES[case]
+  s = make_system(c['name'], c['grid'], c['kgrid'], c['cutoff'], c['mask'])
+  w_re, w_im, occ = make_inputs(s, c['nb'], jitter=0.1)
+  ref = rp.energy_and_grad(s, w_re, w_im, occ)
+  ev = RowShardedEvaluator(s.cell, s.mask, s.kpts, c['nb'], s.positions, s.charges)
+  en, g_re, g_im, rho = ev.evaluate(to_dev(w_re), to_dev(w_im), to_dev(occ))
+  ev.rows.check_status()
+  en = en.cpu().numpy()
+  assert abs(en.sum() - ref['e_tot']) / abs(ref['e_tot']) < E_TOL
+  assert relerr(rho.cpu().numpy(), ref['density']) < G_TOL
+  assert relerr(g_re.cpu().numpy(), ref['g_re']) < G_TOL
+  assert relerr(g_im.cpu().numpy(), ref['g_im']) < G_TOL
+
+
+def test_rows_plan_rejects_grid_calls(cuda_device):
+  from jrystal_b200._lib import JrbError, load
+  from jrystal_b200.plan import RowsPlan
+  rows = RowsPlan(100, 1, 4)
+  with pytest.raises(JrbError):
+    _check = load().jrb_density(rows._h, None, None, None, None)
+    from jrystal_b200._lib import check
+    check(_check)
+
+
 def test_errors(cuda_device):
   import jrystal_b200 as jb
   from jrystal_b200._lib import JrbError

@@ -97,6 +97,38 @@ def test_gloo_world2_density_allreduce(tmp_path):
     assert abs(np.load(tmp_path / f'ekin{r}.npy')[0] - e_kin) < 1e-12 * abs(e_kin)
 
 
+def _rank_transposes(rank, world, port, out_dir):
+  os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
+  dist.init_process_group('gloo', rank=rank, world_size=world)
+  try:
+    ng, nb, nk = 23, 7, 2
+    rng = np.random.default_rng(0)
+    full = torch.from_numpy(rng.standard_normal((1, nk, ng, nb)) +
+                            1j * rng.standard_normal((1, nk, ng, nb)))
+    rows = [parallel.shard_rows(ng, world, r) for r in range(world)]
+    bands = [parallel.shard_bands(nb, world, r) for r in range(world)]
+    g0, g1 = rows[rank]
+    b0, b1 = bands[rank]
+    x_rows = full[:, :, g0:g1].contiguous()
+    x_bands = parallel.rows_to_bands(x_rows, rows, bands)
+    assert torch.equal(x_bands, full[..., b0:b1])
+    back = parallel.bands_to_rows(x_bands, rows, bands)
+    assert torch.equal(back, x_rows)
+    s = torch.full((2, 2), float(rank + 1), dtype=torch.complex128)
+    parallel.allreduce_sum(s)
+    assert torch.equal(s, torch.full((2, 2), 3.0, dtype=torch.complex128))
+    open(os.path.join(out_dir, f'ok{rank}'), 'w').write('ok')
+  finally:
+    dist.destroy_process_group()
+
+
+def test_gloo_world2_row_band_transposes(tmp_path):
+  """The two all-to-alls of the row-sharded (Gamma-only) layout: rows -> bands -> rows."""
+  port = 31500 + (os.getpid() % 2000)
+  mp.spawn(_rank_transposes, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+  assert (tmp_path / 'ok0').exists() and (tmp_path / 'ok1').exists()
+
+
 def test_kinetic_operator_mirrors_oracle():
   from jrystal_b200 import kinetic
   cell, _, _ = structures.load('diamond')
