@@ -34,6 +34,9 @@ static int run_dense(int n, const DenseArgs& a, int dir, long long batch, cudaSt
   return rc;
 }
 
+int fused128_launch(int kind, const FusedArgs& a, int ctas, cudaStream_t st);
+int fused128_smem(int nxo, int ncol);
+int fused128_rho_reduce(const FusedArgs& a, int ctas, double* rho, cudaStream_t st);
 int fused_smem_group0(int n, int nxo, int ncol);
 int fused_smem_group1(int n, int nxo, int ncol);
 int fused_smem_group2(int n, int nxo, int ncol);
@@ -56,6 +59,14 @@ bool fused_available(int nx, int ny, int nxo, int ncol) {
   const int need = fused_smem_need(nx, nxo, ncol);
   // column and Y-row indices are packed in 16 bits each (fft_fused.cuh)
   return need > 0 && need <= 200 * 1024 && ncol < 65000 && nxo * (nx + 8) < 65000;
+}
+
+// The 128 x 128 variant: occupied frequencies |f| < 32 in x and y, everything in shared memory.
+bool fused128_available(int nx, int ny, int nxo, int ncol, int band_limited32) {
+  if (const char* env = std::getenv("JRB_NO_FUSE"))
+    if (std::atoi(env) != 0) return false;
+  return nx == 128 && ny == 128 && band_limited32 && nxo <= 64 && ncol < 65000 &&
+         fused128_smem(nxo, ncol) <= 226 * 1024;
 }
 
 // persistent CTAs of the fused kernels: one per resident slot
@@ -83,7 +94,7 @@ static int run_fused(int kind, int n, const FusedArgs& a, int ctas, cudaStream_t
 
 // segments (distinct z planes) one persistent CTA can touch for a batch of `ngroups`
 static int fused_segmax(const jrb_plan* p, int ngroups) {
-  const long long W = (long long)p->nz * ngroups;
+  const long long W = (long long)p->nz * (p->fused == 2 ? 2 : 1) * ngroups;
   const long long items = (W + p->fused_ctas - 1) / p->fused_ctas;
   return (int)((items - 1) / ngroups + 2);
 }
@@ -93,6 +104,10 @@ static FusedArgs fused_args(jrb_plan* p, const PassArgs& a) {
   f.m = a.m;
   f.wa = a.wa;
   f.tw = p->d_tw_x;
+  f.tw64 = p->d_tw_half;
+  // fused == 2: the work space holds three copies of A (input, y-parity 0 and 1 outputs)
+  f.wout[0] = p->d_ws_a + p->a_copy_elems;
+  f.wout[1] = p->d_ws_a + 2 * p->a_copy_elems;
   f.focc = a.focc;
   f.veff = a.veff;
   f.rho_part = p->d_rho_part;
@@ -136,6 +151,12 @@ static int density_groups(jrb_plan* p, const cplx* q, double* rho_spin, int s, i
     a.rho = rho_spin;
     a.tw = p->d_tw_z;
     if ((rc = run_pass(PASS_Z_INV_SCATTER, p->nz, a, st))) return rc;
+    if (p->fused == 2) {
+      FusedArgs f = fused_args(p, a);
+      if ((rc = fused128_launch(0, f, p->fused_ctas, st))) return rc;
+      if ((rc = fused128_rho_reduce(f, p->fused_ctas, a.rho, st))) return rc;
+      continue;
+    }
     if (p->fused) {
       FusedArgs f = fused_args(p, a);
       if ((rc = run_fused(0, p->nx, f, p->fused_ctas, st))) return rc;
@@ -182,7 +203,12 @@ static int hpsi_groups(jrb_plan* p, const cplx* q, const double* veff_spin, cplx
     a.veff = veff_spin;
     a.tw = p->d_tw_z;
     if ((rc = run_pass(PASS_Z_INV_SCATTER, p->nz, a, st))) return rc;
-    if (p->fused) {
+    if (p->fused == 2) {
+      FusedArgs f = fused_args(p, a);
+      if ((rc = fused128_launch(1, f, p->fused_ctas, st))) return rc;
+      a.wa = f.wout[0];
+      a.wa_add = f.wout[1];
+    } else if (p->fused) {
       FusedArgs f = fused_args(p, a);
       if ((rc = run_fused(1, p->nx, f, p->fused_ctas, st))) return rc;
     } else {

@@ -31,7 +31,9 @@ namespace jrb {
 struct FusedArgs {
   SphereMaps m;
   cplx* wa;            // A[group][z][col][NB]
+  cplx* wout[2];       // fft_fused128.cuh: per-y-parity output copies of A
   const cplx* tw;      // exp(-2 pi i t / n), n = nx = ny
+  const cplx* tw64;    // exp(-2 pi i t / (n / 2)) (128-point planes, fft_fused128.cuh)
   const double* focc;  // [groups][NB] occupation / Omega
   const double* veff;  // [nx*ny*nz] of the current spin
   double* rho_part;    // [gridDim.x * segmax][nx*ny] partial density planes of this launch

@@ -42,6 +42,7 @@ struct PassArgs {
   cplx* hq;         // [ns*nk][ng][nb]
   cplx* wa;
   cplx* wb;
+  const cplx* wa_add;  // k_z_fwd_gather: optional second share of A, added on load (fused 128)
   const cplx* tw;   // exp(-2 pi i t / n) of the pass axis
   const double* focc;  // [groups][NB] occupation / Omega
   const double* gk2;   // [nk][ng]
@@ -426,7 +427,8 @@ __global__ void __launch_bounds__(Cfg<NZ>::NT, z_min_blocks(NZ)) k_z_fwd_gather(
   cplx tw[F::CB][F::NTW];
   F::load_twiddles(tw, a.tw, tj);
 
-  const cplx* in = a.wa + ((long long)gl * NZ * a.m.ncol + (line_ok ? col : 0)) * NB + b;
+  const long long in_off = ((long long)gl * NZ * a.m.ncol + (line_ok ? col : 0)) * NB + b;
+  const cplx* in = a.wa + in_off;
   const long long zs = (long long)a.m.ncol * NB;
   cplx va[F::CA][F::RA];
 #pragma unroll
@@ -434,7 +436,10 @@ __global__ void __launch_bounds__(Cfg<NZ>::NT, z_min_blocks(NZ)) k_z_fwd_gather(
 #pragma unroll
     for (int m = 0; m < F::RA; ++m) {
       cplx v = czero();
-      if (F::activeA(i, tj) && line_ok) v = in[F::idxA(i, m, tj) * zs];
+      if (F::activeA(i, tj) && line_ok) {
+        v = in[F::idxA(i, m, tj) * zs];
+        if (a.wa_add) v = cadd(v, a.wa_add[in_off + F::idxA(i, m, tj) * zs]);
+      }
       va[i][m] = v;
     }
   }

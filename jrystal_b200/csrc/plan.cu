@@ -111,7 +111,7 @@ extern "C" int jrb_plan_destroy(jrb_plan* p) {
   if (!p) return 0;
   cudaSetDevice(p->device);
   void* ptrs[] = {p->d_zmap, p->d_ycol, p->d_xmap, p->d_gidx, p->d_gk2, p->d_tw_x, p->d_tw_y,
-                  p->d_tw_z, p->d_ws_a, p->d_ws_b, p->d_rho_part, p->d_seg_z, p->d_focc, p->d_grid, p->d_vext,
+                  p->d_tw_z, p->d_tw_half, p->d_ws_a, p->d_ws_b, p->d_rho_part, p->d_seg_z, p->d_focc, p->d_grid, p->d_vext,
                   p->d_partials, p->d_veff, p->d_q, p->d_hq, p->d_tmp, p->d_r, p->d_rinv, p->d_small, p->d_gpart,
                   p->d_tkb, p->d_eps, p->d_sphere_part, p->d_scal, p->d_wre, p->d_wim, p->d_gre, p->d_gim,
                   p->d_occ, p->d_rho, p->d_en};
@@ -257,6 +257,12 @@ extern "C" int jrb_plan_create(const jrb_plan_desc* d, jrb_plan** out) {
       if (colid[(size_t)x * ny + y] >= 0 &&
           !((x < 16 || x >= nx - 16) && (y < 16 || y >= ny - 16)))
         p->band_limited = 0;
+  p->band_limited32 = 1;
+  for (int x = 0; x < nx; ++x)
+    for (int y = 0; y < ny; ++y)
+      if (colid[(size_t)x * ny + y] >= 0 &&
+          !((x < 32 || x >= nx - 32) && (y < 32 || y >= ny - 32)))
+        p->band_limited32 = 0;
   if (ng == 0) {
     delete p;
     set_error("jrb_plan_create: empty mask");
@@ -303,6 +309,7 @@ extern "C" int jrb_plan_create(const jrb_plan_desc* d, jrb_plan** out) {
   TRY(upload(&p->d_tw_x, twiddle_table(nx), &tot));
   TRY(upload(&p->d_tw_y, twiddle_table(ny), &tot));
   TRY(upload(&p->d_tw_z, twiddle_table(nz), &tot));
+  TRY(upload(&p->d_tw_half, twiddle_table(nx % 2 == 0 ? nx / 2 : nx), &tot));
   p->maps.nx = nx; p->maps.ny = ny; p->maps.nz = nz;
   p->maps.ncol = ncol; p->maps.nxo = nxo; p->maps.ng = ng;
   p->maps.zmap = p->d_zmap; p->maps.ycol = p->d_ycol; p->maps.xmap = p->d_xmap;
@@ -313,6 +320,7 @@ extern "C" int jrb_plan_create(const jrb_plan_desc* d, jrb_plan** out) {
   const size_t b_per_group = (size_t)nxo * ny * nz * NB;  // complex numbers
   const size_t a_per_group = (size_t)ncol * nz * NB;
   p->fused = fused_available(nx, ny, nxo, ncol) ? 1 : 0;
+  if (!p->fused && fused128_available(nx, ny, nxo, ncol, p->band_limited32)) p->fused = 2;
   int bg = d->batch_groups;
   if (const char* env = std::getenv("JRB_BATCH_GROUPS")) bg = std::atoi(env);
   if (bg <= 0) {
@@ -333,12 +341,16 @@ extern "C" int jrb_plan_create(const jrb_plan_desc* d, jrb_plan** out) {
   p->batch_groups = bg;
   // fused kernels: persistent CTAs; a CTA touches at most fused_segmax z-planes per launch
   // (worst case over batch sizes 1..bg: one group per batch)
-  p->fused_ctas = p->fused ? fused_cta_count(nx, nxo, ncol) : 0;
-  p->fused_segmax = p->fused ? (nz + p->fused_ctas - 1) / p->fused_ctas + 2 : 0;
-  TRY(dev_alloc(&p->d_ws_a, a_per_group * bg, &tot));
+  p->fused_ctas = p->fused == 2 ? 148 : (p->fused ? fused_cta_count(nx, nxo, ncol) : 0);
+  // partial density planes per CTA: whole planes (fused == 1) or y-parity half planes (fused == 2)
+  const int nplanes = p->fused == 2 ? 2 * nz : nz;
+  p->fused_segmax = p->fused ? (nplanes + p->fused_ctas - 1) / p->fused_ctas + 2 : 0;
+  p->a_copy_elems = (long long)(a_per_group * bg);
+  TRY(dev_alloc(&p->d_ws_a, a_per_group * bg * (p->fused == 2 ? 3 : 1), &tot));
   TRY(dev_alloc(&p->d_ws_b, p->fused ? 1 : b_per_group * bg, &tot));
   TRY(dev_alloc(&p->d_rho_part,
-                p->fused ? (size_t)p->fused_ctas * p->fused_segmax * nx * ny : 1, &tot));
+                p->fused ? (size_t)p->fused_ctas * p->fused_segmax * nx * ny / (p->fused == 2 ? 2 : 1) : 1,
+                &tot));
   TRY(dev_alloc(&p->d_seg_z, p->fused ? (size_t)p->fused_ctas * p->fused_segmax : 1, &tot));
   TRY(dev_alloc(&p->d_focc, (size_t)total_groups * NB, &tot));
   // --- grid work space --------------------------------------------------------------

@@ -56,10 +56,14 @@ struct jrb_plan {
   double* d_gk2;                 // [nk][ng]  |G+k|^2
   jrb::cplx *d_tw_x, *d_tw_y, *d_tw_z;  // exp(-2 pi i t / n)
   // pencil work space
-  jrb::cplx* d_ws_a;  // [batch][ncol][nz][NB]
+  jrb::cplx* d_ws_a;  // [batch][ncol][nz][NB] (three copies when fused == 2)
+  long long a_copy_elems;  // elements of one copy
   jrb::cplx* d_ws_b;  // [batch][nxo][ny][nz][NB]
   double* d_focc;     // [ns*nk*ngroups_per_k][NB] occupation / Omega, zero padded
-  int fused;          // 1: y and x passes fused per z-plane (fft_fused.cuh); B slab unused
+  int fused;          // 1: y and x passes fused per z-plane (fft_fused.cuh); B slab unused;
+                      // 2: the 128 x 128 variant (fft_fused128.cuh)
+  int band_limited32; // occupied x and y indices all in [0, 32) u [n - 32, n)
+  jrb::cplx* d_tw_half;  // exp(-2 pi i t / (nx / 2)) (fused == 2)
   int fused_ctas;     // persistent CTAs of the fused kernels (resident slots)
   int band_limited;   // occupied x and y indices all in [0, 16) u [n - 16, n) (sparse radix-8 butterflies)
   int fused_segmax;   // partial density planes per CTA (upper bound over batch sizes)
@@ -100,6 +104,7 @@ int launch_fft3d_dense(jrb_plan* p, const cplx* in, cplx* out, int dir, int64_t 
                        double scale, cudaStream_t st);
 bool line_length_supported(int n);
 bool fused_available(int nx, int ny, int nxo, int ncol);
+bool fused128_available(int nx, int ny, int nxo, int ncol, int band_limited32);
 int fused_cta_count(int n, int nxo, int ncol);
 
 // grid_kernels.cu
