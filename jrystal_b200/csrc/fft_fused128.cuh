@@ -360,6 +360,7 @@ __global__ void __launch_bounds__(F128::NT, 1) k_yx128_vmul(FusedArgs a) {
     }
     const int py = cur.plane & 1;
     cplx* ybuf = ybuf0 + par * ysz;
+    cplx* yother = ybuf0 + (par ^ 1) * ysz;
     // x stage: the two x parities of a line side by side (half slots 2 s and 2 s + 1)
 #pragma unroll
     for (int r = 0; r < 2; ++r) {
@@ -370,6 +371,7 @@ __global__ void __launch_bounds__(F128::NT, 1) k_yx128_vmul(FusedArgs a) {
         const unsigned row = t.pk[m] >> 16;
         va[0][m] = row != 0 ? ybuf[(int)row - 1 + yp] : czero();
       }
+      slot128_barrier(slot);  // both x parities hold their inputs
       if (px) phase128<+1>(va[0], t.c);
       FI::template stageA_store<NB>(va, ex, t.tj);
       hs_barrier(t.hs);
@@ -383,25 +385,14 @@ __global__ void __launch_bounds__(F128::NT, 1) k_yx128_vmul(FusedArgs a) {
       cplx vc[1][8];
       FF::template stageB_load<NB, true>(vc, ex, tw, t.tj);
       if (px) phase128<-1>(vc[0], t.c);
-      // both parities have read their inputs once the odd half slot passes this barrier
-      slot128_barrier(slot);
-      if (!px) {
+      // x parity 0 goes back in place (safe: the slot-wide barrier above ordered it after the odd
+      // half slot's input loads), parity 1 into the other Y buffer, which is idle right now; the
+      // y-forward stage adds the two when it loads
+      cplx* dsty = px ? yother : ybuf;
 #pragma unroll
-        for (int m = 0; m < 8; ++m) {
-          const unsigned row = t.pk[m] >> 16;
-          if (row != 0) ybuf[(int)row - 1 + yp] = vc[0][m];
-        }
-      }
-      slot128_barrier(slot);
-      if (px) {
-#pragma unroll
-        for (int m = 0; m < 8; ++m) {
-          const unsigned row = t.pk[m] >> 16;
-          if (row != 0) {
-            const cplx o = ybuf[(int)row - 1 + yp];
-            ybuf[(int)row - 1 + yp] = cadd(o, vc[0][m]);
-          }
-        }
+      for (int m = 0; m < 8; ++m) {
+        const unsigned row = t.pk[m] >> 16;
+        if (row != 0) dsty[(int)row - 1 + yp] = vc[0][m];
       }
     }
     __syncthreads();
@@ -410,9 +401,11 @@ __global__ void __launch_bounds__(F128::NT, 1) k_yx128_vmul(FusedArgs a) {
       const int xo = t.hs * NB + t.lane;
       const bool ok = xo < a.m.nxo;
       const cplx* in = ybuf + (ok ? xo : 0) * F128::SX;
+      const cplx* in1 = yother + (ok ? xo : 0) * F128::SX;
       cplx va[1][8];
 #pragma unroll
-      for (int m = 0; m < 8; ++m) va[0][m] = ok ? in[t.tj + 8 * m] : czero();
+      for (int m = 0; m < 8; ++m)
+        va[0][m] = ok ? cadd(in[t.tj + 8 * m], in1[t.tj + 8 * m]) : czero();
       FF::template stageA_store<NB>(va, ex, t.tj);
       hs_barrier(t.hs);
       cplx vb[1][8];

@@ -190,11 +190,14 @@ k_tri_inv_cols(const cplx* __restrict__ R, int nb, cplx* __restrict__ Rinv) {
 // grid: (1 + ceil((nb - p0 - 32) / 32), nsk), block 256
 constexpr int CP = 32;        // panel width == tile height
 constexpr int CP_LD = CP + 1;
-constexpr int CP_KC = 8;
-constexpr int CP_LK = CP_KC + 1;
+constexpr int CP_SMEM = 4 * CP * CP_LD * (int)sizeof(cplx);  // D, T, Ld, Lr
 __global__ void __launch_bounds__(256)
 k_chol_panel(cplx* __restrict__ S, cplx* __restrict__ Rt, int nb, int p0, int* __restrict__ fail_flag) {
-  __shared__ cplx D[CP * CP_LD], T[CP * CP_LD], Ld[CP * CP_LK], Lr[CP * CP_LK];
+  extern __shared__ __align__(16) unsigned char smem_raw_[];
+  cplx* D = reinterpret_cast<cplx*>(smem_raw_);
+  cplx* T = D + CP * CP_LD;
+  cplx* Ld = T + CP * CP_LD;
+  cplx* Lr = Ld + CP * CP_LD;
   const long long nn = (long long)nb * nb;
   S += blockIdx.y * nn;
   Rt += blockIdx.y * nn;
@@ -212,23 +215,36 @@ k_chol_panel(cplx* __restrict__ S, cplx* __restrict__ Rt, int nb, int p0, int* _
     accD[j] = (r < pw && c < pw) ? S[(long long)(p0 + r) * nb + p0 + c] : cmake(0.0, 0.0);
     accT[j] = (r < nr && c < pw) ? S[(long long)(r0 + r) * nb + p0 + c] : cmake(0.0, 0.0);
   }
-  for (int k0 = 0; k0 < p0; k0 += CP_KC) {  // p0 is a multiple of CP_KC
-    __syncthreads();
-    for (int e = tid; e < CP * CP_KC; e += 256) {
-      const int r = e / CP_KC, k = e % CP_KC;
-      Ld[r * CP_LK + k] = r < pw ? S[(long long)(p0 + r) * nb + k0 + k] : cmake(0.0, 0.0);
-      Lr[r * CP_LK + k] = r < nr ? S[(long long)(r0 + r) * nb + k0 + k] : cmake(0.0, 0.0);
+  // left-looking update with the finished columns k < p0, 32 at a time; the next slice is
+  // fetched into registers while the current one is multiplied
+  cplx pd[4], pr[4];
+  auto fetch = [&](int k0) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int r = rb + 8 * j;
+      pd[j] = r < pw ? S[(long long)(p0 + r) * nb + k0 + c] : cmake(0.0, 0.0);
+      pr[j] = r < nr ? S[(long long)(r0 + r) * nb + k0 + c] : cmake(0.0, 0.0);
     }
+  };
+  if (p0 > 0) fetch(0);
+  for (int k0 = 0; k0 < p0; k0 += CP) {  // p0 is a multiple of CP
     __syncthreads();
 #pragma unroll
-    for (int k = 0; k < CP_KC; ++k) {
-      const cplx lc = Ld[c * CP_LK + k];
+    for (int j = 0; j < 4; ++j) {
+      Ld[(rb + 8 * j) * CP_LD + c] = pd[j];
+      Lr[(rb + 8 * j) * CP_LD + c] = pr[j];
+    }
+    __syncthreads();
+    if (k0 + CP < p0) fetch(k0 + CP);
+#pragma unroll 8
+    for (int k = 0; k < CP; ++k) {
+      const cplx lc = Ld[c * CP_LD + k];
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         const int r = rb + 8 * j;
-        const cplx u = cmulc(Ld[r * CP_LK + k], lc);
+        const cplx u = cmulc(Ld[r * CP_LD + k], lc);
         accD[j].x -= u.x; accD[j].y -= u.y;
-        const cplx v = cmulc(Lr[r * CP_LK + k], lc);
+        const cplx v = cmulc(Lr[r * CP_LD + k], lc);
         accT[j].x -= v.x; accT[j].y -= v.y;
       }
     }
@@ -239,60 +255,25 @@ k_chol_panel(cplx* __restrict__ S, cplx* __restrict__ Rt, int nb, int p0, int* _
     T[(rb + 8 * j) * CP_LD + c] = accT[j];
   }
   __syncthreads();
-  // factor the diagonal block (lower triangle) in shared memory
+  // Unscaled right-looking elimination of the diagonal block and, in the same sweep, of the rows
+  // below it (one barrier per column): after step j column j of D and T is final up to the
+  // factor 1 / sqrt(d_j), d_j = D[j][j].
   for (int j = 0; j < pw; ++j) {
     const double djj = D[j * CP_LD + j].x;
-    if (!(djj > 0.0) && tid == 0 && tile == 0) atomicExch(fail_flag, 1);
-    const double d = sqrt(djj > 0.0 ? djj : 1.0);
-    const double inv = 1.0 / d;
-    __syncthreads();
-    if (tid >= j && tid < pw) {
-      const cplx v = D[tid * CP_LD + j];
-      D[tid * CP_LD + j] = tid == j ? cmake(d, 0.0) : cmake(v.x * inv, v.y * inv);
-    }
-    __syncthreads();
+    const double rinv = 1.0 / (djj > 0.0 ? djj : 1.0);
     if (c > j && c < pw) {
       const cplx lc = D[c * CP_LD + j];
+      const cplx lcs = cmake(lc.x * rinv, lc.y * rinv);
 #pragma unroll
       for (int jj = 0; jj < 4; ++jj) {
         const int r = rb + 8 * jj;
         if (r >= c && r < pw) {
-          const cplx v = cmulc(D[r * CP_LD + j], lc);
+          const cplx v = cmulc(D[r * CP_LD + j], lcs);
           D[r * CP_LD + c].x -= v.x;
           D[r * CP_LD + c].y -= v.y;
         }
-      }
-    }
-    __syncthreads();
-  }
-  if (tile == 0) {
-    // L (lower) back into S, R = L^H into Rt (zeros below its diagonal)
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int r = rb + 8 * j;
-      if (r < pw && c < pw) {
-        const cplx v = r >= c ? D[r * CP_LD + c] : cmake(0.0, 0.0);
-        S[(long long)(p0 + r) * nb + p0 + c] = v;
-        Rt[(long long)(p0 + c) * nb + p0 + r] = cconj(v);
-      }
-    }
-    return;
-  }
-  // rows below: X L11^H = T, column by column (right-looking inside the tile)
-  for (int j = 0; j < pw; ++j) {
-    const double inv = 1.0 / D[j * CP_LD + j].x;
-    if (tid < nr) {
-      const cplx v = T[tid * CP_LD + j];
-      T[tid * CP_LD + j] = cmake(v.x * inv, v.y * inv);
-    }
-    __syncthreads();
-    if (c > j && c < pw) {
-      const cplx lc = D[c * CP_LD + j];
-#pragma unroll
-      for (int jj = 0; jj < 4; ++jj) {
-        const int r = rb + 8 * jj;
         if (r < nr) {
-          const cplx v = cmulc(T[r * CP_LD + j], lc);
+          const cplx v = cmulc(T[r * CP_LD + j], lcs);
           T[r * CP_LD + c].x -= v.x;
           T[r * CP_LD + c].y -= v.y;
         }
@@ -300,11 +281,29 @@ k_chol_panel(cplx* __restrict__ S, cplx* __restrict__ Rt, int nb, int p0, int* _
     }
     __syncthreads();
   }
+  const double dcc = c < pw ? D[c * CP_LD + c].x : 1.0;
+  if (!(dcc > 0.0) && tile == 0 && rb == 0) atomicExch(fail_flag, 1);
+  const double sc = 1.0 / sqrt(dcc > 0.0 ? dcc : 1.0);
+  if (tile == 0) {
+    // L (lower) back into S, R = L^H into Rt (zeros below its diagonal)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int r = rb + 8 * j;
+      if (r < pw && c < pw) {
+        cplx v = cmake(0.0, 0.0);
+        if (r > c) v = cmake(D[r * CP_LD + c].x * sc, D[r * CP_LD + c].y * sc);
+        if (r == c) v = cmake(dcc > 0.0 ? sqrt(dcc) : 1.0, 0.0);
+        S[(long long)(p0 + r) * nb + p0 + c] = v;
+        Rt[(long long)(p0 + c) * nb + p0 + r] = cconj(v);
+      }
+    }
+    return;
+  }
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
     const int r = rb + 8 * j;
     if (r < nr && c < pw) {
-      const cplx v = T[r * CP_LD + c];
+      const cplx v = cmake(T[r * CP_LD + c].x * sc, T[r * CP_LD + c].y * sc);
       S[(long long)(r0 + r) * nb + p0 + c] = v;
       Rt[(long long)(p0 + c) * nb + r0 + r] = cconj(v);
       Rt[(long long)(r0 + r) * nb + p0 + c] = cmake(0.0, 0.0);
@@ -625,7 +624,9 @@ static int chol_and_inverse(jrb_plan* p, int nsk, cplx* S, cplx* Rt, cplx* Rit, 
     for (int p0 = 0; p0 < nb; p0 += CP) {
       const int below = std::max(0, nb - p0 - CP);
       dim3 grid(1 + (below + CP - 1) / CP, nsk);
-      k_chol_panel<<<grid, 256, 0, st>>>(S, Rt, nb, p0, fail);
+      static int once = opt_in_smem(k_chol_panel, CP_SMEM);
+      if (once) return once;
+      k_chol_panel<<<grid, 256, CP_SMEM, st>>>(S, Rt, nb, p0, fail);
       JRB_CHECK_LAUNCH("k_chol_panel");
     }
     return tri_inverse(Rt, nb, nsk, Rit, st);
