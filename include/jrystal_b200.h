@@ -74,6 +74,11 @@ int64_t jrb_plan_workspace_bytes(const jrb_plan* plan);
 int jrb_set_atoms(jrb_plan* plan, const double* positions_host, const double* charges_host,
                   int32_t natoms, jrb_stream stream);
 
+/* Replaces the plan's k-points (same count nk) by rebuilding the |G+k|^2 table on the device: the
+ * band-structure driver walks a k-path with one plan (calc/calc_band_structure_all_electrons.py:
+ * 115-182 re-traces `update` per k-point instead).  kpts_host: [nk][3] Cartesian, 1/Bohr. */
+int jrb_set_kpoints(jrb_plan* plan, const double* kpts_host, jrb_stream stream);
+
 /* unitary_module.unitary_matrix (jrystal/_src/unitary_module.py:66-81): Q R = w_re + i w_im per
  * (spin, k).  Cholesky-QR2 on FP64 tensor cores; gauge: diag(R) real POSITIVE (LAPACK's
  * Householder Q differs by a sign per column; energies, density and gradients are invariant).
@@ -200,6 +205,17 @@ int jrb_eval_finish(jrb_plan* plan, const double* occ, const double* rho, const 
 int jrb_energy_grad_host(jrb_plan* plan, const double* w_re_host, const double* w_im_host,
                          const double* occ_host, int32_t xc_id, double* energies_host,
                          double* g_re_host, double* g_im_host, double* rho_host);
+
+/* optax.adam update of one parameter array on the device: the optimiser of the energy-mode driver
+ * (calc/calc_ground_state_energy_all_electrons.py:175-181, opt_utils.py:153-168; default
+ * lr 0.01, b1 0.9, b2 0.99, eps 1e-8, config.py).  `state` is 4 device doubles, zero-initialised by
+ * the caller: step count and the two bias corrections, advanced ONCE per optimisation step by
+ * jrb_adam_tick and read by every jrb_adam_apply of that step -- no host value changes between
+ * steps, so begin + finish + tick + apply can be captured in one CUDA graph and replayed.
+ * No plan needed; arrays 16-byte aligned; m, v zero-initialised by the caller. */
+int jrb_adam_tick(double* state, double b1, double b2, jrb_stream stream);
+int jrb_adam_apply(int64_t n, double* param, const double* grad, double* m, double* v, double lr,
+                   double b1, double b2, double eps, const double* state, jrb_stream stream);
 
 const char* jrb_last_error(void);
 int jrb_version(void);

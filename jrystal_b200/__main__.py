@@ -1,0 +1,40 @@
+"""`python -m jrystal_b200 -m energy|band -c config.yaml`: the reference's command line
+(`jrystal -m energy|band -c config.yaml`, jrystal/main.py) on the B200 drivers."""
+import argparse
+import sys
+
+import numpy as np
+
+from . import calc
+from .config import get_config
+
+
+def main(argv=None):
+  ap = argparse.ArgumentParser(prog='jrystal_b200')
+  ap.add_argument('-m', '--mode', choices=['energy', 'band'], default='energy')
+  ap.add_argument('-c', '--config', default=None, help='config.yaml (reference keys)')
+  args = ap.parse_args(argv)
+  config = get_config(args.config)
+  log = print if config.verbose else None
+  if args.mode == 'energy':
+    out = calc.energy(config, log=log)
+    print(f'Hartree Energy: {out.energies["hartree"]:.4f} Ha')
+    print(f'External Energy: {out.energies["external"]:.4f} Ha')
+    print(f'XC Energy: {out.energies["xc"]:.4f} Ha')
+    print(f'Kinetic Energy: {out.energies["kinetic"]:.4f} Ha')
+    print(f'Nuclear repulsion Energy: {out.energies["ewald"]:.4f} Ha')
+    print(f'Total Energy: {out.total_energy:.4f} Ha')
+    print(f'{"Converged" if out.converged else "Did not converge"} after {out.steps} steps, '
+          f'{out.seconds_per_step * 1e3:.3f} ms/step')
+    if config.save_dir:
+      np.save(f'{config.save_dir}/density.npy', out.density.cpu().numpy())
+  else:
+    out = calc.band(config, log=log)
+    name = ''.join(out.ground_state.crystal.symbols) + '_band_structure.npy'
+    np.save(name, out.eigenvalues)
+    print(f'saved {name}: eigenvalues {out.eigenvalues.shape} (spin, k, band)')
+  return 0
+
+
+if __name__ == '__main__':
+  sys.exit(main())

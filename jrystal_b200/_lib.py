@@ -29,6 +29,7 @@ SYMBOLS = {
   'jrb_plan_num_g': (_I64, [_P]),
   'jrb_plan_workspace_bytes': (_I64, [_P]),
   'jrb_set_atoms': (ctypes.c_int, [_P, _P, _P, _I32, _P]),
+  'jrb_set_kpoints': (ctypes.c_int, [_P, _P, _P]),
   'jrb_qr_fwd': (ctypes.c_int, [_P, _P, _P, _P, _P, _P]),
   'jrb_qr_bwd': (ctypes.c_int, [_P, _P, _P, _P, _P, _P, _P]),
   'jrb_plan_create_rows': (ctypes.c_int, [_I64, _I32, _I32, _I32, _I32, ctypes.POINTER(_P)]),
@@ -52,6 +53,9 @@ SYMBOLS = {
   'jrb_eval_begin': (ctypes.c_int, [_P, _P, _P, _P, _P, _P, _P]),
   'jrb_eval_finish': (ctypes.c_int, [_P, _P, _P, _P, _I32, _P, _P, _P, _P, _P]),
   'jrb_energy_grad_host': (ctypes.c_int, [_P, _P, _P, _P, _I32, _P, _P, _P, _P]),
+  'jrb_adam_tick': (ctypes.c_int, [_P, ctypes.c_double, ctypes.c_double, _P]),
+  'jrb_adam_apply': (ctypes.c_int, [_I64, _P, _P, _P, _P, ctypes.c_double, ctypes.c_double,
+                                    ctypes.c_double, ctypes.c_double, _P, _P]),
   'jrb_last_error': (ctypes.c_char_p, []),
   'jrb_version': (ctypes.c_int, []),
   'jrb_launch_count': (_I64, []),

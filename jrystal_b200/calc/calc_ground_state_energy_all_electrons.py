@@ -1,0 +1,141 @@
+"""Energy-mode driver: direct minimisation of the all-electron total energy over the plane-wave
+parameters, the caller of the hot path (jrystal/calc/calc_ground_state_energy_all_electrons.py:63-249).
+
+Per step the reference does jax.value_and_grad(free_energy) + optax.adam inside one jitted
+`update`; here a step is jrb_eval_begin -> (all-reduce of rho, E_kin over the k mesh) ->
+jrb_eval_finish -> jrb_adam_tick/apply, all asynchronous on one stream and allocation free, so on a
+single GPU the whole step is captured once in a CUDA graph and replayed (launch latency is what
+bounds the small configurations).  Like the reference the host reads the total energy every step
+for the convergence window.
+
+Occupations are the parameter-free schemes ('uniform', 'gamma'); with them the entropy term of the
+free energy is a constant and the temperature schedule does not enter the gradient."""
+import dataclasses
+import time
+from math import ceil
+from typing import List, Optional
+
+import numpy as np
+import torch
+
+from .. import occupation, parallel
+from ..config import JrystalConfigDict, get_config
+from ..plan import Plan
+from .convergence import create_convergence_checker
+from .opt_utils import (create_crystal, create_freq_mask, create_grids, create_optimizer,
+                        get_ewald_coulomb_repulsion)
+
+
+@dataclasses.dataclass
+class GroundStateEnergyOutput:
+  """Mirrors the reference's output container (lines 49-60) plus what the band driver needs."""
+  config: JrystalConfigDict
+  crystal: object
+  params_pw: dict
+  occupation: torch.Tensor
+  density: torch.Tensor            # (spin, x, y, z), all-reduced
+  total_energy: float              # electronic + Ewald
+  energies: dict                   # kinetic, external, hartree, xc, ewald, entropy
+  total_energy_history: List[float]
+  converged: bool
+  steps: int
+  seconds_per_step: float
+
+
+def temperature_scheduler(config):
+  """optax.exponential_decay(100, epoch // 2, smearing / 100, end_value=smearing) (lines 190-199)."""
+  if config.smearing > 0.:
+    half = max(config.epoch // 2, 1)
+    rate = config.smearing / 100.
+
+    def sched(i):
+      return max(100. * rate ** (i / half), config.smearing)
+    return sched
+  return lambda i: 0.
+
+
+def calc(config: Optional[JrystalConfigDict] = None, plan: Optional[Plan] = None,
+         use_cuda_graph: bool = True, log=None) -> GroundStateEnergyOutput:
+  config = config or get_config()
+  if config.use_pseudopotential:
+    raise NotImplementedError('pseudopotential drivers are outside the B200 hot path (DESIGN.md)')
+  crystal = create_crystal(config)
+  _, _, k_vec = create_grids(config, crystal)
+  freq_mask = create_freq_mask(config, crystal)
+  num_kpts = k_vec.shape[0]
+  num_bands = ceil(crystal.num_electron / 2) + config.empty_bands
+  world, rank = parallel._world()
+  use_k_mesh = bool(config.parallel_over_k_mesh) and world > 1
+  k0, k1 = parallel.shard_kpoints(num_kpts, world, rank) if use_k_mesh else (0, num_kpts)
+  ew = get_ewald_coulomb_repulsion(config, crystal)
+
+  occ_full = occupation.param_init(None, num_bands, crystal.num_electron, num_kpts, crystal.spin,
+                                   config.occupation, config.spin_restricted)
+  entropy = occupation.fermi_dirac_entropy(occ_full, config.eps)
+  if not config.spin_restricted:
+    raise NotImplementedError('spin-unrestricted energy mode is not wired into the driver yet')
+  if plan is None:
+    plan = Plan(crystal.cell_vectors, freq_mask, k_vec[k0:k1], num_bands)
+  plan.set_atoms(crystal.positions, crystal.charges)
+  dev = plan.tdev
+  # parameters: the same global stream on every rank, each keeps its k block
+  rng = np.random.default_rng(config.seed)
+  shape = (1, num_kpts, plan.ng, num_bands)
+  w_re = torch.from_numpy(np.ascontiguousarray(rng.random(shape)[:, k0:k1])).to(dev)
+  w_im = torch.from_numpy(np.ascontiguousarray(rng.random(shape)[:, k0:k1])).to(dev)
+  occ = torch.from_numpy(np.ascontiguousarray(occ_full[:, k0:k1])).to(dev)
+  optimizer = create_optimizer(config, [w_re, w_im])
+  rho = torch.empty((1, plan.nx, plan.ny, plan.nz), dtype=torch.float64, device=dev)
+  e_kin = torch.empty(1, dtype=torch.float64, device=dev)
+  out = (torch.empty(4, dtype=torch.float64, device=dev), torch.empty_like(w_re),
+         torch.empty_like(w_im))
+
+  def step():
+    plan.eval_begin(w_re, w_im, occ, rho, e_kin)
+    if use_k_mesh:
+      parallel.allreduce_density(rho, e_kin)
+    plan.eval_finish(occ, rho, e_kin, config.xc, out=out)
+    optimizer.step([out[1], out[2]])
+
+  graph = None
+  step()  # warm-up outside the capture (one-time attribute calls); counts as step 0
+  first_energy = float(out[0].sum().item())
+  if use_cuda_graph and not use_k_mesh:
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+      step()
+    # the capture does not execute: parameters are those after step 0
+
+  checker = create_convergence_checker(config)
+  sched = temperature_scheduler(config)
+  history = [first_energy]
+  converged = checker.check(first_energy)
+  t0 = time.perf_counter()
+  steps = 1
+  for i in range(1, config.epoch):
+    if converged:
+      break
+    graph.replay() if graph is not None else step()
+    etot = float(out[0].sum().item())  # value BEFORE this step's update, as value_and_grad returns
+    history.append(etot)
+    steps += 1
+    converged = checker.check(etot)
+    if log is not None and (i % 50 == 0 or converged):
+      temp = sched(i)
+      log(f'step {i}: Loss {etot - temp * entropy:.6f} | Energy {etot + ew:.6f} | '
+          f'Entropy {entropy:.4f} | T {temp:.2E}')
+  torch.cuda.synchronize()
+  dt = (time.perf_counter() - t0) / max(steps - 1, 1)
+  plan.check_status()
+  # final energies at the final parameters (lines 223-247 of the reference)
+  plan.eval_begin(w_re, w_im, occ, rho, e_kin)
+  if use_k_mesh:
+    parallel.allreduce_density(rho, e_kin)
+  plan.eval_finish(occ, rho, e_kin, config.xc, out=out)
+  en = out[0].cpu().numpy()
+  energies = dict(kinetic=float(en[0]), external=float(en[1]), hartree=float(en[2]),
+                  xc=float(en[3]), ewald=float(ew), entropy=float(entropy))
+  return GroundStateEnergyOutput(
+    config=config, crystal=crystal, params_pw={'w_re': w_re, 'w_im': w_im}, occupation=occ,
+    density=rho.clone(), total_energy=float(en.sum() + ew), energies=energies,
+    total_energy_history=history, converged=bool(converged), steps=steps, seconds_per_step=dt)

@@ -1,0 +1,49 @@
+"""Set-up helpers of the drivers, same names as jrystal/calc/opt_utils.py (crystal, grids, masks,
+optimiser, Ewald constant), on numpy + the device Adam."""
+import numpy as np
+
+from .. import grid
+from ..crystal import Crystal
+from ..ewald import ewald_coulomb_repulsion
+from ..optim import Adam
+
+
+def create_crystal(config) -> Crystal:
+  # opt_utils.py:62-86: a file path wins over a built-in name
+  path = config.get('crystal_file_path_path')
+  if path:
+    return Crystal.create_from_file(path, spin=config.get('spin'))
+  return Crystal.create_builtin(config.crystal, spin=config.get('spin'))
+
+
+def create_freq_mask(config, crystal=None) -> np.ndarray:
+  crystal = crystal or create_crystal(config)
+  gs = grid.proper_grid_size(config.grid_sizes)
+  if config.freq_mask_method == 'spherical':
+    return grid.spherical_mask(crystal.cell_vectors, gs, config.cutoff_energy)
+  if config.freq_mask_method == 'cubic':
+    return grid.cubic_mask(gs)
+  raise ValueError(f'freq_mask_method "{config.freq_mask_method}" is not supported')
+
+
+def create_grids(config, crystal=None):
+  crystal = crystal or create_crystal(config)
+  gs = grid.proper_grid_size(config.grid_sizes)
+  ks = grid.proper_grid_size(config.k_grid_sizes)
+  return (grid.g_vectors(crystal.cell_vectors, gs), grid.r_vectors(crystal.cell_vectors, gs),
+          grid.k_vectors(crystal.cell_vectors, ks))
+
+
+def create_optimizer(config, params) -> Adam:
+  if config.optimizer != 'adam':
+    raise NotImplementedError(f'optimizer "{config.optimizer}" is not implemented (adam only)')
+  if config.get('scheduler'):
+    raise NotImplementedError('Scheduler is not implemented yet.')  # as in the reference
+  args = dict(config.optimizer_args)
+  return Adam(params, learning_rate=args.pop('learning_rate'), **args)
+
+
+def get_ewald_coulomb_repulsion(config, crystal=None) -> float:
+  crystal = crystal or create_crystal(config)
+  return ewald_coulomb_repulsion(crystal.positions, crystal.charges, crystal.cell_vectors,
+                                 ewald_eta=config.ewald_args.get('ewald_eta'))

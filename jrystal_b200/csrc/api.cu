@@ -41,6 +41,13 @@ extern "C" int jrb_set_atoms(jrb_plan* p, const double* pos_h, const double* chg
   return launch_set_atoms(p, pos_h, chg_h, na, S(st));
 }
 
+extern "C" int jrb_set_kpoints(jrb_plan* p, const double* kpts_h, jrb_stream st) {
+  int rc = enter(p);
+  if (rc) return rc;
+  REQUIRE(kpts_h, "null array");
+  return launch_set_kpoints(p, kpts_h, S(st));
+}
+
 extern "C" int jrb_qr_fwd(jrb_plan* p, const double* w_re, const double* w_im, double* q,
                           double* r, jrb_stream st) {
   int rc = enter(p, false);

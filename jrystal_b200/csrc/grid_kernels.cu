@@ -398,6 +398,33 @@ int launch_weighted_sum(jrb_plan* p, const double* a, const double* w, int64_t n
   return 0;
 }
 
+// gk2[g] = |G_g + k|^2 on the sphere for one k-point (same arithmetic order as the host table of
+// jrb_plan_create: G from integer frequencies, then the sum of squares over x, y, z)
+__global__ void k_gk2(GridGeom geo, const int32_t* __restrict__ gidx, long long ng, double kx,
+                      double ky, double kz, double* __restrict__ gk2) {
+  const long long g = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (g >= ng) return;
+  double gx, gy, gz;
+  g_of(geo, gidx[g], gx, gy, gz);
+  const double vx = gx + kx, vy = gy + ky, vz = gz + kz;
+  double s = 0.0;
+  s += vx * vx;
+  s += vy * vy;
+  s += vz * vz;
+  gk2[g] = s;
+}
+
+int launch_set_kpoints(jrb_plan* p, const double* kpts_h, cudaStream_t st) {
+  const GridGeom g = geom_of(p);
+  for (int k = 0; k < p->nk; ++k) {
+    k_gk2<<<(unsigned)((p->ng + 255) / 256), 256, 0, st>>>(
+      g, p->d_gidx, p->ng, kpts_h[3 * k], kpts_h[3 * k + 1], kpts_h[3 * k + 2],
+      p->d_gk2 + (long long)k * p->ng);
+    JRB_CHECK_LAUNCH("k_gk2");
+  }
+  return 0;
+}
+
 // focc[group][lane] = occ[sk][b0 + lane] / Omega, zero padded
 __global__ void k_focc(const double* __restrict__ occ, int nb, int ngpk, int total_groups,
                        double inv_vol, double* __restrict__ focc) {

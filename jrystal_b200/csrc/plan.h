@@ -120,6 +120,7 @@ int launch_weighted_sum(jrb_plan* p, const double* a, const double* w, int64_t n
 int launch_expand(jrb_plan* p, const cplx* q, cplx* dense, cudaStream_t st);
 int launch_squeeze(jrb_plan* p, const cplx* dense, cplx* q, cudaStream_t st);
 int launch_focc(jrb_plan* p, const double* occ, cudaStream_t st);
+int launch_set_kpoints(jrb_plan* p, const double* kpts_h, cudaStream_t st);
 
 // qr.cu
 int qr_gram_partial_mats(const jrb_plan* p);

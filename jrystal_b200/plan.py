@@ -92,6 +92,18 @@ class Plan:
                                       pos.shape[0], _stream()))
     self._atoms = True
 
+  def set_kpoints(self, kpts):
+    """Same number of k-points, new vectors (band-structure walk along a k-path)."""
+    k = np.ascontiguousarray(np.asarray(kpts, dtype=np.float64).reshape(-1, 3))
+    if k.shape[0] != self.nk:
+      raise ValueError(f'expected {self.nk} k-points, got {k.shape[0]}')
+    _lib.check(self.lib.jrb_set_kpoints(self._h, k.ctypes.data, _stream()))
+    self.kpts = k
+
+  def check_status(self):
+    """Synchronise and raise if an asynchronous call failed numerically (Cholesky breakdown)."""
+    _lib.check(self.lib.jrb_check_status(self._h, _stream()))
+
   # -- orthonormalisation -------------------------------------------------------------
   def qr_fwd(self, w_re, w_im, out=None):
     self._chk(w_re, self.sphere_shape, torch.float64, 'w_re')

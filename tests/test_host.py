@@ -148,3 +148,57 @@ def test_use_plan_context():
     assert p == 'sentinel' and context.current_plan() == 'sentinel'
   with pytest.raises(RuntimeError):
     context.current_plan()
+
+
+def test_convergence_checker_is_the_reference_rule():
+  """std of the last `window` values below the threshold (jrystal/calc/convergence.py:13-35)."""
+  from jrystal_b200.calc.convergence import ConvergenceChecker
+  c = ConvergenceChecker(window_size=3, threshold=1e-2)
+  assert [c.check(v) for v in (1.0, 0.5, 0.4, 0.399, 0.3985, 0.398)] == \
+      [False, False, False, False, True, True]
+  c.reset()
+  assert c.history == []
+
+
+def test_ewald_madelung_constant_and_eta_independence():
+  """Simple-cubic lattice of unit charges in a neutralising background: E = xi / (2 L),
+  xi = -2.837297479 (known answer); the converged sums do not depend on eta."""
+  from jrystal_b200.ewald import ewald_coulomb_repulsion
+  ref = -2.837297479 / 2
+  for eta in (None, 0.6, 2.5):
+    assert abs(ewald_coulomb_repulsion([[0, 0, 0]], [1.0], np.eye(3), eta) - ref) < 1e-9
+  cell, pos, chg = structures.load('diamond')
+  e1 = ewald_coulomb_repulsion(pos, chg, cell, 0.1)
+  e2 = ewald_coulomb_repulsion(pos, chg, cell, 0.35)
+  assert abs(e1 - e2) < 1e-10 * abs(e1)
+  # translation invariance
+  e3 = ewald_coulomb_repulsion(pos + 0.37, chg, cell)
+  assert abs(e1 - e3) < 1e-10 * abs(e1)
+
+
+def test_k_path_and_config_defaults():
+  from jrystal_b200 import k_path
+  from jrystal_b200.config import get_config
+  cell, _, _ = structures.load('diamond')
+  assert k_path.lattice_type(cell) == 'fcc'
+  frac = k_path.get_k_path(cell, 'GXL', 7, fractional=True)
+  np.testing.assert_allclose(frac[0], [0, 0, 0])
+  assert any(np.allclose(f, [0.5, 0, 0.5]) for f in frac)       # X is on a sample
+  np.testing.assert_allclose(frac[-1], [0.5, 0.5, 0.5])
+  cart = k_path.get_k_path(cell, 'GXL', 7)
+  np.testing.assert_allclose(cart, frac @ (2 * np.pi * np.linalg.inv(cell).T), atol=1e-14)
+  with pytest.raises(ValueError):
+    k_path.get_k_path(cell, 'GQ', 5)
+  cfg = get_config(epoch=10)
+  assert cfg.optimizer_args['b2'] == 0.99 and cfg.epoch == 10 and cfg.convergence_window_size == 20
+  assert cfg.band_structure_empty_bands == 8
+
+
+def test_temperature_schedule_matches_optax_exponential_decay():
+  from jrystal_b200.calc.calc_ground_state_energy_all_electrons import temperature_scheduler
+  from jrystal_b200.config import get_config
+  s = temperature_scheduler(get_config(epoch=100, smearing=0.001))
+  assert s(0) == 100.0
+  assert abs(s(50) - 0.001) < 1e-12 and s(99) == 0.001      # init * rate^(i / (epoch // 2)), floored
+  assert abs(s(25) - 100.0 * (0.001 / 100.0) ** 0.5) < 1e-12
+  assert temperature_scheduler(get_config(smearing=0.0))(10) == 0.0
