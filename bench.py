@@ -409,16 +409,42 @@ def run_b200(args):
   g_out = (torch.empty_like(w_re), torch.empty_like(w_im))
   plan.qr_fwd(w_re, w_im, out=(q, r))
   plan.density(q, occ, out=rho2)
-  _, veff = plan.grid_potential(rho2, 'lda_x', False)
+  gp_out = plan.grid_potential(rho2, 'lda_x', False)
+  veff = gp_out[1]
   plan.hpsi(q, veff, out=hq)
   plan.qr_bwd(q, r, hq, out=g_out)
   reps = 3
   phases['qr_fwd'] = timed(lambda: plan.qr_fwd(w_re, w_im, out=(q, r)), reps) / reps
   phases['density'] = timed(lambda: plan.density(q, occ, out=rho2), reps) / reps
-  phases['grid_potential'] = timed(lambda: plan.grid_potential(rho2, 'lda_x', False), reps) / reps
+  phases['grid_potential'] = timed(
+    lambda: plan.grid_potential(rho2, 'lda_x', False, out=gp_out), reps) / reps
   phases['hpsi'] = timed(lambda: plan.hpsi(q, veff, out=hq), reps) / reps
   phases['qr_bwd'] = timed(lambda: plan.qr_bwd(q, r, hq, out=g_out), reps) / reps
-  del q, r, hq, rho2, veff, g_out
+  del q, r, hq, rho2, veff, g_out, gp_out
+
+  # ---- the caller of the path: one optimisation step of the energy-mode driver (evaluation +
+  # device Adam), eager and replayed as a CUDA graph; informational
+  driver = None
+  if world == 1:
+    from jrystal_b200.optim import Adam
+    pw_re, pw_im = w_re.clone(), w_im.clone()
+    opt = Adam([pw_re, pw_im])
+
+    def opt_step():
+      plan.eval_begin(pw_re, pw_im, occ, rho, e_kin)
+      plan.eval_finish(occ, rho, e_kin, 'lda_x', out=out)
+      opt.step([out[1], out[2]])
+
+    opt_step()
+    eager_ms = timed(opt_step, reps) / reps
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+      opt_step()
+    graph.replay()
+    graph_ms = timed(graph.replay, reps) / reps
+    driver = {'eager_steps_per_s': 1e3 / eager_ms, 'graph_steps_per_s': 1e3 / graph_ms,
+              'what': 'jrb_eval_begin + jrb_eval_finish + jrb_adam_tick/apply per step'}
+    del pw_re, pw_im, opt, graph
 
   # ---- roofline (a dense 3-D transform is charged one read + one write of its box,
   # sphere data its true size), per GPU -------------------------------------------------------
@@ -473,7 +499,7 @@ def run_b200(args):
       'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': h2d,
               'd2h_bytes_per_step': d2h, 'path': e2e_path},
       'gpu_launches': launches, 'roofline': roofline, 'clocks': clk.summary(),
-      'phases_ms': phases, 'energies_ha': energies,
+      'phases_ms': phases, 'driver_step': driver, 'energies_ha': energies,
       'workspace_mib': plan.workspace_bytes / 2**20,
     }
     if world == 1 and not args.no_cpu:

@@ -157,14 +157,17 @@ class Plan:
     _lib.check(self.lib.jrb_kinetic(self._h, _ptr(q), _ptr(t), _stream()))
     return t
 
-  def grid_potential(self, rho, xc: str = 'lda_x', kohn_sham: bool = False):
+  def grid_potential(self, rho, xc: str = 'lda_x', kohn_sham: bool = False, out=None):
     if not self._atoms:
       raise RuntimeError('call set_atoms(positions, charges) first')
     self._chk(rho, (self.ns, self.nx, self.ny, self.nz), torch.float64, 'density')
     if xc not in _lib.XC_IDS:
       raise NotImplementedError(f'xc "{xc}" is not implemented (LDA only: {list(_lib.XC_IDS)})')
-    en = self._new((3,), torch.float64)
-    veff = self._new((self.ns, self.nx, self.ny, self.nz), torch.float64)
+    if out is None:
+      en = self._new((3,), torch.float64)
+      veff = self._new((self.ns, self.nx, self.ny, self.nz), torch.float64)
+    else:
+      en, veff = out
     _lib.check(self.lib.jrb_grid_potential(self._h, _ptr(rho), _lib.XC_IDS[xc],
                                            int(bool(kohn_sham)), _ptr(en), _ptr(veff), _stream()))
     return en, veff
