@@ -42,6 +42,16 @@ WORKLOADS = {
 METRIC = 'energy+grad evals/sec'
 UNIT = 'eval/s'
 
+# stdout carries exactly ONE line (the JSON): libraries that print to stdout (NCCL's version banner,
+# torchrun notices) are routed to stderr for the whole run
+_REAL_STDOUT = os.dup(1)
+os.dup2(2, 1)
+
+
+def emit(line: dict) -> None:
+  sys.stdout.flush()
+  os.write(_REAL_STDOUT, (json.dumps(line) + '\n').encode())
+
 
 def build_workload(name):
   from jrystal_b200 import grid, occupation
@@ -179,7 +189,7 @@ def run_reference(args):
     'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
     'gpu_launches': 0,
   }
-  print(json.dumps(line), flush=True)
+  emit(line)
 
 
 def run_b200_rows(args, wl, world, rank, local_rank):
@@ -285,7 +295,7 @@ def run_b200_rows(args, wl, world, rank, local_rank):
                    'orbitals_per_gpu': m_local},
       'clocks': clk.summary(), 'energies_ha': energies,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
   dist.destroy_process_group()
 
 
@@ -510,7 +520,7 @@ def run_b200(args):
         'value': v, 'unit': UNIT, 'cores': cores, 'kind': 'port',
         'sample': f'{nks} of {nk} k-points x {nb} bands ({t:.2f} s), scaled by {nk / nks:g}; '
                   'oracle port (torch FP64 autograd)'}
-    print(json.dumps(line), flush=True)
+    emit(line)
   if world > 1:
     dist.destroy_process_group()
 
