@@ -224,7 +224,11 @@ extern "C" int jrb_eval_begin(jrb_plan* p, const double* w_re, const double* w_i
   REQUIRE(w_re && w_im && occ && rho && e_kin, "null array");
   JRB_CUDA(cudaMemsetAsync(p->d_scal + 32, 0, sizeof(double), S(st)));  // Cholesky failure flag
   if ((rc = launch_qr_fwd(p, w_re, w_im, p->d_q, p->d_r, S(st)))) return rc;
-  if ((rc = launch_density(p, p->d_q, occ, rho, S(st)))) return rc;
+  p->keep_write = 1;
+  rc = launch_density(p, p->d_q, occ, rho, S(st));
+  p->keep_write = 0;
+  p->keep_filled = rc == 0;
+  if (rc) return rc;
   if ((rc = launch_kinetic(p, p->d_q, p->d_tkb, S(st)))) return rc;
   return launch_weighted_sum(p, p->d_tkb, occ, (int64_t)p->ns * p->nk * p->nb, e_kin, S(st));
 }
@@ -246,7 +250,11 @@ extern "C" int jrb_eval_finish(jrb_plan* p, const double* occ, const double* rho
   double* grid_e = p->d_scal;            // E_H, E_ext, E_xc
   double* veff = p->d_veff;
   if ((rc = launch_grid_potential(p, rho, xc_id, 0, 7, grid_e, veff, S(st)))) return rc;
-  if ((rc = launch_hpsi(p, p->d_q, veff, p->d_hq, S(st)))) return rc;
+  p->keep_read = p->keep_filled;
+  rc = launch_hpsi(p, p->d_q, veff, p->d_hq, S(st));
+  p->keep_read = 0;
+  p->keep_filled = 0;  // the fused H-apply works in place on the kept columns
+  if (rc) return rc;
   if (g_occ) {
     if ((rc = launch_band_expect(p, p->d_q, p->d_hq, g_occ, S(st)))) return rc;
   }
@@ -330,7 +338,10 @@ extern "C" int jrb_energy_grad_host(jrb_plan* p, const double* w_re_h, const dou
       const int k0 = k_of(c), k1 = k_of(c + 1);
       JRB_CUDA(cudaStreamWaitEvent(st, p->ev_in[c], 0));
       if ((rc = launch_qr_fwd_range(p, k0, k1 - k0, p->d_wre, p->d_wim, p->d_q, p->d_r, st))) return rc;
-      if ((rc = launch_density_krange(p, p->d_q, rho, k0, k1, st))) return rc;
+      p->keep_write = 1;
+      rc = launch_density_krange(p, p->d_q, rho, k0, k1, st);
+      p->keep_write = 0;
+      if (rc) return rc;
       if ((rc = launch_kinetic_range(p, k0, k1 - k0, p->d_q, p->d_tkb, st))) return rc;
     }
     if ((rc = launch_weighted_sum(p, p->d_tkb, p->d_occ, (int64_t)p->nk * p->nb, e_kin, st))) return rc;
@@ -340,7 +351,10 @@ extern "C" int jrb_energy_grad_host(jrb_plan* p, const double* w_re_h, const dou
     for (int c = 0; c < nch; ++c) {
       const int k0 = k_of(c), k1 = k_of(c + 1);
       const size_t off = (size_t)k0 * per_k, n = (size_t)(k1 - k0) * per_k;
-      if ((rc = launch_hpsi_krange(p, p->d_q, p->d_veff, p->d_hq, k0, k1, st))) return rc;
+      p->keep_read = 1;
+      rc = launch_hpsi_krange(p, p->d_q, p->d_veff, p->d_hq, k0, k1, st);
+      p->keep_read = 0;
+      if (rc) return rc;
       if ((rc = launch_qr_bwd_range(p, k0, k1 - k0, p->d_q, p->d_r, p->d_hq, p->d_occ, p->d_gre,
                                     p->d_gim, st)))
         return rc;

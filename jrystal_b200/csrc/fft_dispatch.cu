@@ -150,6 +150,7 @@ static int density_groups(jrb_plan* p, const cplx* q, double* rho_spin, int s, i
     a.ngroups = std::min(p->batch_groups, gb - g0);
     a.rho = rho_spin;
     a.tw = p->d_tw_z;
+    if (p->keep_write && p->d_a_keep) a.wa = p->d_a_keep + (long long)a.g0 * p->a_group_elems;
     if ((rc = run_pass(PASS_Z_INV_SCATTER, p->nz, a, st))) return rc;
     if (p->fused == 2) {
       FusedArgs f = fused_args(p, a);
@@ -202,7 +203,11 @@ static int hpsi_groups(jrb_plan* p, const cplx* q, const double* veff_spin, cplx
     a.ngroups = std::min(p->batch_groups, gb - g0);
     a.veff = veff_spin;
     a.tw = p->d_tw_z;
-    if ((rc = run_pass(PASS_Z_INV_SCATTER, p->nz, a, st))) return rc;
+    if (p->keep_read && p->d_a_keep) {
+      a.wa = p->d_a_keep + (long long)a.g0 * p->a_group_elems;  // columns of the density sweep
+    } else {
+      if ((rc = run_pass(PASS_Z_INV_SCATTER, p->nz, a, st))) return rc;
+    }
     if (p->fused == 2) {
       FusedArgs f = fused_args(p, a);
       if ((rc = fused128_launch(1, f, p->fused_ctas, st))) return rc;

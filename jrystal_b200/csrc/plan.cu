@@ -111,7 +111,7 @@ extern "C" int jrb_plan_destroy(jrb_plan* p) {
   if (!p) return 0;
   cudaSetDevice(p->device);
   void* ptrs[] = {p->d_zmap, p->d_ycol, p->d_xmap, p->d_gidx, p->d_gk2, p->d_tw_x, p->d_tw_y,
-                  p->d_tw_z, p->d_tw_half, p->d_ws_a, p->d_ws_b, p->d_rho_part, p->d_seg_z, p->d_focc, p->d_grid, p->d_vext,
+                  p->d_tw_z, p->d_tw_half, p->d_a_keep, p->d_ws_a, p->d_ws_b, p->d_rho_part, p->d_seg_z, p->d_focc, p->d_grid, p->d_vext,
                   p->d_partials, p->d_veff, p->d_q, p->d_hq, p->d_tmp, p->d_r, p->d_rinv, p->d_small, p->d_gpart,
                   p->d_tkb, p->d_eps, p->d_sphere_part, p->d_scal, p->d_wre, p->d_wim, p->d_gre, p->d_gim,
                   p->d_occ, p->d_rho, p->d_en};
@@ -346,6 +346,13 @@ extern "C" int jrb_plan_create(const jrb_plan_desc* d, jrb_plan** out) {
   const int nplanes = p->fused == 2 ? 2 * nz : nz;
   p->fused_segmax = p->fused ? (nplanes + p->fused_ctas - 1) / p->fused_ctas + 2 : 0;
   p->a_copy_elems = (long long)(a_per_group * bg);
+  p->a_group_elems = (long long)a_per_group;
+  {
+    double cap_mb = 8192.0;
+    if (const char* env = std::getenv("JRB_KEEP_A_MB")) cap_mb = std::atof(env);
+    const double need_mb = (double)total_groups * a_per_group * sizeof(cplx) / (1024.0 * 1024.0);
+    if (p->fused && need_mb <= cap_mb) TRY(dev_alloc(&p->d_a_keep, a_per_group * total_groups, &tot));
+  }
   TRY(dev_alloc(&p->d_ws_a, a_per_group * bg * (p->fused == 2 ? 3 : 1), &tot));
   TRY(dev_alloc(&p->d_ws_b, p->fused ? 1 : b_per_group * bg, &tot));
   TRY(dev_alloc(&p->d_rho_part,

@@ -58,6 +58,12 @@ struct jrb_plan {
   // pencil work space
   jrb::cplx* d_ws_a;  // [batch][ncol][nz][NB] (three copies when fused == 2)
   long long a_copy_elems;  // elements of one copy
+  // z-transformed columns of EVERY band group, kept from the density sweep of jrb_eval_begin for
+  // the H-apply of jrb_eval_finish (saves the second scatter + z pass); null when it would exceed
+  // the budget (JRB_KEEP_A_MB, default 8192) or the passes are not fused
+  jrb::cplx* d_a_keep;
+  long long a_group_elems;
+  int keep_write, keep_read, keep_filled;
   jrb::cplx* d_ws_b;  // [batch][nxo][ny][nz][NB]
   double* d_focc;     // [ns*nk*ngroups_per_k][NB] occupation / Omega, zero padded
   int fused;          // 1: y and x passes fused per z-plane (fft_fused.cuh); B slab unused;

@@ -16,6 +16,7 @@
 // (leading dimensions == 4 mod 16 doubles make every fragment load bank-conflict free).
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 
 #include "plan.h"
 #include "qr_gemm.cuh"
@@ -588,7 +589,14 @@ int launch_hamiltonian_matrix(jrb_plan* p, const cplx* q, const cplx* hq, cplx* 
 
 // Above this size the per-matrix recurrences are spread over several CTAs (more launches, far
 // less latency); below it one CTA per (spin,k) with batch parallelism is the better shape.
-constexpr int LARGE_NB = 96;
+static int large_nb_threshold() {
+  static int v = [] {
+    if (const char* env = std::getenv("JRB_LARGE_NB")) return std::atoi(env);
+    return 96;
+  }();
+  return v;
+}
+#define LARGE_NB large_nb_threshold()
 
 // Rinv = R^-1 (upper triangular)
 static int tri_inverse(const cplx* R, int nb, int nsk, cplx* Rinv, cudaStream_t st) {
