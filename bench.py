@@ -82,52 +82,67 @@ def synthetic_params(ng, nk, nb, k0, k1):
 
 
 class ClockSampler:
-  """nvidia-smi clocks / throttle reasons during the timed region."""
-  Q = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,'
-       'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
-       'clocks_event_reasons.sw_power_cap')
+  """SM clock and throttle reasons of one GPU during the timed region, through NVML (a few
+  microseconds per sample; spawning nvidia-smi from every rank perturbs the run it measures)."""
+  BAD = {'hw_slowdown': 0x8, 'hw_thermal_slowdown': 0x40, 'sw_thermal_slowdown': 0x20,
+         'sw_power_cap': 0x4}
 
-  def __init__(self, index):
-    self.index = index
-    self.samples = []
+  def __init__(self, index, enabled=True):
+    self.samples, self.reasons = [], set()
+    self.max_mhz = None
     self._stop = threading.Event()
-    self._t = threading.Thread(target=self._run, daemon=True)
+    self._t = None
+    self._h = None
+    if not enabled:
+      return
+    try:
+      import pynvml
+      pynvml.nvmlInit()
+      vis = os.environ.get('CUDA_VISIBLE_DEVICES')
+      phys = int(vis.split(',')[index]) if vis and vis.split(',')[index].isdigit() else index
+      self._nv = pynvml
+      self._h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+      self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self._h, pynvml.NVML_CLOCK_SM))
+      self._t = threading.Thread(target=self._run, daemon=True)
+    except Exception:
+      self._h = None
+
+  def _sample(self):
+    nv = self._nv
+    self.samples.append(float(nv.nvmlDeviceGetClockInfo(self._h, nv.NVML_CLOCK_SM)))
+    mask = int(nv.nvmlDeviceGetCurrentClocksEventReasons(self._h)) if hasattr(
+      nv, 'nvmlDeviceGetCurrentClocksEventReasons') else int(
+        nv.nvmlDeviceGetCurrentClocksThrottleReasons(self._h))
+    for name, bit in self.BAD.items():
+      if mask & bit:
+        self.reasons.add(name)
 
   def _run(self):
     while not self._stop.is_set():
       try:
-        out = subprocess.run(
-          ['nvidia-smi', f'--query-gpu={self.Q}', '--format=csv,noheader,nounits', '-i',
-           str(self.index)], capture_output=True, text=True, timeout=5).stdout.strip()
-        if out:
-          self.samples.append([x.strip() for x in out.split(',')])
+        self._sample()
       except Exception:
         pass
-      self._stop.wait(0.02)
+      self._stop.wait(0.01)
 
   def __enter__(self):
-    self._t.start()
+    if self._t is not None:
+      try:
+        self._sample()
+      except Exception:
+        pass
+      self._t.start()
     return self
 
   def __exit__(self, *a):
     self._stop.set()
-    self._t.join(timeout=6)
+    if self._t is not None:
+      self._t.join(timeout=2)
 
   def summary(self):
-    sm, mx, reasons = [], [], set()
-    names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
-    for s in self.samples:
-      try:
-        sm.append(float(s[0]))
-        mx.append(float(s[1]))
-        for n, v in zip(names, s[3:7]):
-          if v.lower().startswith('active'):
-            reasons.add(n)
-      except Exception:
-        continue
-    return {'sm_mhz': float(np.median(sm)) if sm else None,
-            'sm_max_mhz': float(max(mx)) if mx else None, 'reasons': sorted(reasons),
-            'samples': len(sm)}
+    return {'sm_mhz': float(np.median(self.samples)) if self.samples else None,
+            'sm_max_mhz': self.max_mhz, 'reasons': sorted(self.reasons),
+            'samples': len(self.samples), 'source': 'nvml' if self._h is not None else 'unavailable'}
 
 
 def measured_peak():
@@ -237,7 +252,7 @@ def run_b200_rows(args, wl, world, rank, local_rank):
     step()
   barrier()
   launches0 = lib.jrb_launch_count()
-  with ClockSampler(local_rank) as clk:
+  with ClockSampler(local_rank, enabled=(rank == 0)) as clk:
     total_ms = timed(step, args.steps)
   launches = int(lib.jrb_launch_count() - launches0)
   ms_per_step = total_ms / args.steps
@@ -331,14 +346,13 @@ def run_b200(args):
   w_re = torch.from_numpy(w_re_h).cuda()
   w_im = torch.from_numpy(w_im_h).cuda()
   occ = torch.from_numpy(occ_h).cuda()
-  rho = torch.empty((1,) + tuple(wl['grid']), dtype=torch.float64, device='cuda')
-  e_kin = torch.empty(1, dtype=torch.float64, device='cuda')
+  dbuf, rho, e_kin = parallel.density_buffers((1,) + tuple(wl['grid']), 'cuda')
   out = (torch.empty(4, dtype=torch.float64, device='cuda'), torch.empty_like(w_re),
          torch.empty_like(w_im))
 
   def step():
     plan.eval_begin(w_re, w_im, occ, rho, e_kin)
-    parallel.allreduce_density(rho, e_kin)
+    parallel.allreduce_density(rho, e_kin, dbuf)
     plan.eval_finish(occ, rho, e_kin, 'lda_x', out=out)
 
   def barrier():
@@ -385,7 +399,7 @@ def run_b200(args):
     step()
   barrier()
   launches0 = lib.jrb_launch_count()
-  with ClockSampler(local_rank) as clk:
+  with ClockSampler(local_rank, enabled=(rank == 0)) as clk:
     total_ms = (timed_flushed if flush_l2 else timed)(step, args.steps)
   launches = int(lib.jrb_launch_count() - launches0)
   ms_per_step = total_ms / args.steps

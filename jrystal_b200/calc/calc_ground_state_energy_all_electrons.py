@@ -85,15 +85,14 @@ def calc(config: Optional[JrystalConfigDict] = None, plan: Optional[Plan] = None
   w_im = torch.from_numpy(np.ascontiguousarray(rng.random(shape)[:, k0:k1])).to(dev)
   occ = torch.from_numpy(np.ascontiguousarray(occ_full[:, k0:k1])).to(dev)
   optimizer = create_optimizer(config, [w_re, w_im])
-  rho = torch.empty((1, plan.nx, plan.ny, plan.nz), dtype=torch.float64, device=dev)
-  e_kin = torch.empty(1, dtype=torch.float64, device=dev)
+  dbuf, rho, e_kin = parallel.density_buffers((1, plan.nx, plan.ny, plan.nz), dev)
   out = (torch.empty(4, dtype=torch.float64, device=dev), torch.empty_like(w_re),
          torch.empty_like(w_im))
 
   def step():
     plan.eval_begin(w_re, w_im, occ, rho, e_kin)
     if use_k_mesh:
-      parallel.allreduce_density(rho, e_kin)
+      parallel.allreduce_density(rho, e_kin, dbuf)
     plan.eval_finish(occ, rho, e_kin, config.xc, out=out)
     optimizer.step([out[1], out[2]])
 
@@ -130,7 +129,7 @@ def calc(config: Optional[JrystalConfigDict] = None, plan: Optional[Plan] = None
   # final energies at the final parameters (lines 223-247 of the reference)
   plan.eval_begin(w_re, w_im, occ, rho, e_kin)
   if use_k_mesh:
-    parallel.allreduce_density(rho, e_kin)
+    parallel.allreduce_density(rho, e_kin, dbuf)
   plan.eval_finish(occ, rho, e_kin, config.xc, out=out)
   en = out[0].cpu().numpy()
   energies = dict(kinetic=float(en[0]), external=float(en[1]), hartree=float(en[2]),

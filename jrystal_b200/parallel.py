@@ -12,6 +12,12 @@ import torch
 import torch.distributed as dist
 
 
+def _world(group=None) -> Tuple[int, int]:
+  if dist.is_available() and dist.is_initialized():
+    return dist.get_world_size(group), dist.get_rank(group)
+  return 1, 0
+
+
 def shard_kpoints(num_k: int, world_size: int, rank: int) -> Tuple[int, int]:
   """Contiguous k-range [start, stop) of `rank`.  Like the reference (spmd/uniform.py:22-24)
   this needs num_k % world_size == 0."""
@@ -33,23 +39,30 @@ def shard_bands(num_bands: int, world_size: int, rank: int) -> Tuple[int, int]:
   return start, start + base + (1 if rank < extra else 0)
 
 
-def allreduce_density(rho: torch.Tensor, e_kin: torch.Tensor) -> None:
+def density_buffers(shape, device):
+  """(buf, rho, e_kin): the partial density and the partial kinetic energy as views of ONE flat
+  buffer, so that a single all-reduce carries both (one collective latency per evaluation)."""
+  n = int(np.prod(shape))
+  buf = torch.empty(n + 1, dtype=torch.float64, device=device)
+  return buf, buf[:n].view(*shape), buf[n:]
+
+
+def allreduce_density(rho: torch.Tensor, e_kin: torch.Tensor, buf: Optional[torch.Tensor] = None,
+                      group=None) -> None:
   """In-place SUM over ranks of the partial density and kinetic energy (no-op when
-  torch.distributed is not initialised).  NCCL on GPUs, gloo in the CPU tests."""
-  if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
-    dist.all_reduce(rho, op=dist.ReduceOp.SUM)
-    dist.all_reduce(e_kin, op=dist.ReduceOp.SUM)
+  torch.distributed is not initialised).  NCCL on GPUs, gloo in the CPU tests.  With `buf` (from
+  density_buffers) one collective reduces both."""
+  if _world(group)[0] > 1:
+    if buf is not None:
+      dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=group)
+    else:
+      dist.all_reduce(rho, op=dist.ReduceOp.SUM, group=group)
+      dist.all_reduce(e_kin, op=dist.ReduceOp.SUM, group=group)
 
 
 def shard_rows(num_g: int, world_size: int, rank: int) -> Tuple[int, int]:
   """Contiguous block of sphere rows g of `rank` (row-sharded orthonormalisation)."""
   return shard_bands(num_g, world_size, rank)
-
-
-def _world(group=None) -> Tuple[int, int]:
-  if dist.is_available() and dist.is_initialized():
-    return dist.get_world_size(group), dist.get_rank(group)
-  return 1, 0
 
 
 def allreduce_sum(*tensors: torch.Tensor, group=None) -> None:
@@ -150,9 +163,10 @@ class RowShardedEvaluator:
       q_rows, _ = rp.apply(w_re_rows, w_im_rows, pass_, s)
     q_band = rows_to_bands(q_rows, self.row_blocks, self.band_blocks, self.group)
     occ_band = occ[:, :, self.b0:self.b1].contiguous()
-    rho = bp.density(q_band, occ_band)
-    e_kin = (bp.kinetic(q_band) * occ_band).sum().reshape(1)
-    allreduce_density(rho, e_kin) if self.group is None else allreduce_sum(rho, e_kin, group=self.group)
+    buf, rho, e_kin = density_buffers((1, bp.nx, bp.ny, bp.nz), bp.tdev)
+    bp.density(q_band, occ_band, out=rho)
+    e_kin.copy_((bp.kinetic(q_band) * occ_band).sum().reshape(1))
+    allreduce_density(rho, e_kin, buf, group=self.group)
     en, veff = bp.grid_potential(rho, xc, False)
     hq_band = bp.hpsi(q_band, veff)
     hq_rows = bands_to_rows(hq_band, self.row_blocks, self.band_blocks, self.group)
