@@ -339,6 +339,10 @@ def run_b200(args):
   k0, k1 = parallel.shard_kpoints(nk, world, rank)
   b0, b1 = 0, nb
   sharding = f'k{world}' if world > 1 else 'none'
+  if args.emulate_ranks > 1 and world == 1:
+    # tuning aid, NOT a bench line: the per-rank workload of an N-GPU k-sharded run on one GPU
+    k0, k1 = parallel.shard_kpoints(nk, args.emulate_ranks, 0)
+    sharding = f'EMULATED rank 0 of k{args.emulate_ranks} (no collectives; not a benchmark value)'
   plan = jb.Plan(c.cell_vectors, wl['mask'], wl['kpts'][k0:k1], nb, device=local_rank)
   plan.set_atoms(c.positions, c.charges)
   w_re_h, w_im_h = synthetic_params(ng, nk, nb, k0, k1)
@@ -569,6 +573,8 @@ def main():
   ap.add_argument('--config', default='C2', choices=list(WORKLOADS))
   ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
   ap.add_argument('--no-cpu', action='store_true', help='skip the cpu_baseline leg')
+  ap.add_argument('--emulate-ranks', type=int, default=1,
+                  help='tuning aid: run only the k-points rank 0 of an N-GPU run would own')
   args = ap.parse_args()
   if args.impl == 'reference':
     run_reference(args)

@@ -597,10 +597,19 @@ static int large_nb_threshold() {
   return v;
 }
 #define LARGE_NB large_nb_threshold()
+// One CTA per matrix only pays when there are enough matrices to fill the GPU: with few (spin,k)
+// items (a k-sharded rank of an 8-GPU run holds 8) the multi-CTA kernels win from 33 bands on.
+static bool multi_cta_small(int nb, int nsk) {
+  static int few = [] {
+    if (const char* env = std::getenv("JRB_MULTI_CTA_NSK")) return std::atoi(env);
+    return 16;
+  }();
+  return nb > LARGE_NB || (nb > 32 && nsk <= few);
+}
 
 // Rinv = R^-1 (upper triangular)
 static int tri_inverse(const cplx* R, int nb, int nsk, cplx* Rinv, cudaStream_t st) {
-  if (nb > LARGE_NB) {
+  if (multi_cta_small(nb, nsk)) {
     const int nblk = (nb + CP - 1) / CP;
     k_tri_inv_diag<<<dim3(nblk, nsk), 32, 0, st>>>(R, nb, Rinv);
     JRB_CHECK_LAUNCH("k_tri_inv_diag");
@@ -628,7 +637,7 @@ static int reduce_gram(jrb_plan* p, int nsk, int nchunks, cplx* S, cudaStream_t 
 static int chol_and_inverse(jrb_plan* p, int nsk, cplx* S, cplx* Rt, cplx* Rit, cudaStream_t st) {
   const int nb = p->nb;
   int* fail = reinterpret_cast<int*>(p->d_scal + 32);
-  if (nb > LARGE_NB) {
+  if (multi_cta_small(nb, nsk)) {
     for (int p0 = 0; p0 < nb; p0 += CP) {
       const int below = std::max(0, nb - p0 - CP);
       dim3 grid(1 + (below + CP - 1) / CP, nsk);

@@ -273,6 +273,29 @@ def test_rows_plan_rejects_grid_calls(cuda_device):
     check(_check)
 
 
+def test_mid_band_count_few_kpoints_qr(cuda_device):
+  """33..96 bands with few k-points take the multi-CTA panel Cholesky (two panels, the second one
+  partial) and the blocked triangular inverse."""
+  s = make_system('si', 16, [1, 1, 2], 30, 'spherical')
+  nb = 40
+  rng = np.random.default_rng(4)
+  w_re = rng.random((1, 2, s.num_g, nb))
+  w_im = rng.random((1, 2, s.num_g, nb))
+  plan = make_plan(s, nb)
+  q, r = plan.qr_fwd(to_dev(w_re), to_dev(w_im))
+  gq = rng.standard_normal(w_re.shape) + 1j * rng.standard_normal(w_re.shape)
+  g_re, g_im = plan.qr_bwd(q, r, to_dev(gq))
+  for k in range(2):
+    qn, rn = q.cpu().numpy()[0, k], r.cpu().numpy()[0, k]
+    w = (w_re + 1j * w_im)[0, k]
+    assert np.abs(qn.conj().T @ qn - np.eye(nb)).max() < 1e-12
+    assert relerr(qn @ rn, w) < 1e-12
+    assert np.abs(np.tril(rn, -1)).max() == 0.0
+    gw = analytic.qr_backward(qn, rn, gq[0, k])
+    assert relerr(g_re[0, k].cpu().numpy(), 2 * gw.real) < 1e-10
+    assert relerr(g_im[0, k].cpu().numpy(), 2 * gw.imag) < 1e-10
+
+
 def test_errors(cuda_device):
   import jrystal_b200 as jb
   from jrystal_b200._lib import JrbError
