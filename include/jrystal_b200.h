@@ -74,6 +74,14 @@ int64_t jrb_plan_workspace_bytes(const jrb_plan* plan);
 int jrb_set_atoms(jrb_plan* plan, const double* positions_host, const double* charges_host,
                   int32_t natoms, jrb_stream stream);
 
+/* Sets the reciprocal-space external potential V(G) directly (device, complex (nx, ny, nz), the
+ * convention of potential.external_reciprocal: E = Re sum_G conj(V) rho_hat * Omega / N^2,
+ * v(r) = ifftn(V)).  Besides replacing jrb_set_atoms this is the LOCAL part of a norm-conserving
+ * pseudopotential: pseudopotential/local.py:164-187 (energy_local = reciprocal_braket(V_loc, rho_hat),
+ * hamiltonian_local = <psi| ifftn(V_loc) |psi>) contracts exactly like the all-electron external
+ * term, with V_loc(G) precomputed on the host from the UPF data. */
+int jrb_set_external_potential(jrb_plan* plan, const double* vhat, jrb_stream stream);
+
 /* Replaces the plan's k-points (same count nk) by rebuilding the |G+k|^2 table on the device: the
  * band-structure driver walks a k-path with one plan (calc/calc_band_structure_all_electrons.py:
  * 115-182 re-traces `update` per k-point instead).  kpts_host: [nk][3] Cartesian, 1/Bohr. */

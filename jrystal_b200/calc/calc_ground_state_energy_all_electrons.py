@@ -8,8 +8,11 @@ single GPU the whole step is captured once in a CUDA graph and replayed (launch 
 bounds the small configurations).  Like the reference the host reads the total energy every step
 for the convergence window.
 
-Occupations are the parameter-free schemes ('uniform', 'gamma'); with them the entropy term of the
-free energy is a constant and the temperature schedule does not enter the gradient."""
+Occupations: the parameter-free schemes ('uniform', 'gamma'), for which the entropy term of the
+free energy is a constant, and the trainable ones ('simplex-projector', 'idempotent'): there the
+evaluation also returns dE/d occupation, which is chained through the (tiny, torch autograd)
+occupation map together with -T dS/d occupation under the reference's annealing schedule; those
+steps are not graph-captured."""
 import dataclasses
 import time
 from math import ceil
@@ -69,44 +72,83 @@ def calc(config: Optional[JrystalConfigDict] = None, plan: Optional[Plan] = None
   k0, k1 = parallel.shard_kpoints(num_kpts, world, rank) if use_k_mesh else (0, num_kpts)
   ew = get_ewald_coulomb_repulsion(config, crystal)
 
-  occ_full = occupation.param_init(None, num_bands, crystal.num_electron, num_kpts, crystal.spin,
-                                   config.occupation, config.spin_restricted)
-  entropy = occupation.fermi_dirac_entropy(occ_full, config.eps)
+  method = config.occupation
+  trainable = occupation.trainable(method)
   if not config.spin_restricted:
     raise NotImplementedError('spin-unrestricted energy mode is not wired into the driver yet')
   if plan is None:
     plan = Plan(crystal.cell_vectors, freq_mask, k_vec[k0:k1], num_bands)
   plan.set_atoms(crystal.positions, crystal.charges)
   dev = plan.tdev
-  # parameters: the same global stream on every rank, each keeps its k block
   rng = np.random.default_rng(config.seed)
+  params_occ = occupation.param_init(rng, num_bands, crystal.num_electron, num_kpts, crystal.spin,
+                                     method, config.spin_restricted)
+
+  def get_occupation():
+    """(spin, kpt, band) on the device; a torch graph for the trainable schemes (lines 109-117)."""
+    o = occupation.occupation(params_occ, num_kpts, crystal.num_electron, crystal.spin, method,
+                              config.spin_restricted)
+    return o if trainable else torch.from_numpy(np.ascontiguousarray(o)).to(dev)
+
+  occ_t = get_occupation()
+  entropy = float(occupation.fermi_dirac_entropy_torch(occ_t.detach(), config.eps))
+  # parameters: the same global stream on every rank, each keeps its k block
   shape = (1, num_kpts, plan.ng, num_bands)
   w_re = torch.from_numpy(np.ascontiguousarray(rng.random(shape)[:, k0:k1])).to(dev)
   w_im = torch.from_numpy(np.ascontiguousarray(rng.random(shape)[:, k0:k1])).to(dev)
-  occ = torch.from_numpy(np.ascontiguousarray(occ_full[:, k0:k1])).to(dev)
+  occ = occ_t.detach()[:, k0:k1].contiguous()
   optimizer = create_optimizer(config, [w_re, w_im])
+  occ_leaves, opt_occ = [], None
+  if trainable:
+    seen = set()
+    for v in params_occ.values():
+      for leaf in (v.values() if isinstance(v, dict) else [v]):
+        if id(leaf) not in seen:
+          seen.add(id(leaf))
+          occ_leaves.append(leaf)
+    opt_occ = create_optimizer(config, [leaf.detach() for leaf in occ_leaves])
+    # the optimiser updates the storage the leaves view
+    for leaf, p in zip(occ_leaves, opt_occ.params):
+      assert p.data_ptr() == leaf.data_ptr()
   dbuf, rho, e_kin = parallel.density_buffers((1, plan.nx, plan.ny, plan.nz), dev)
   out = (torch.empty(4, dtype=torch.float64, device=dev), torch.empty_like(w_re),
          torch.empty_like(w_im))
+  sched = temperature_scheduler(config)
+  state = {'i': 0, 'entropy': entropy}
 
   def step():
+    if trainable:
+      o = get_occupation()
+      occ.copy_(o.detach()[:, k0:k1])
     plan.eval_begin(w_re, w_im, occ, rho, e_kin)
     if use_k_mesh:
       parallel.allreduce_density(rho, e_kin, dbuf)
-    plan.eval_finish(occ, rho, e_kin, config.xc, out=out)
+    _, _, _, g_occ = plan.eval_finish(occ, rho, e_kin, config.xc, want_occ_grad=trainable, out=out)
     optimizer.step([out[1], out[2]])
+    if trainable:
+      # d(free energy)/d(occupation parameters): dE/d occ from the evaluation, chained through the
+      # occupation map; minus T dS/d(parameters) (lines 139-147: free = total - temp * entropy)
+      if use_k_mesh:
+        parts = [torch.empty_like(g_occ) for _ in range(world)]
+        torch.distributed.all_gather(parts, g_occ.contiguous())
+        g_occ = torch.cat(parts, dim=1)
+      s_t = occupation.fermi_dirac_entropy_torch(o, config.eps)
+      surrogate = (g_occ.detach() * o).sum() - sched(state['i']) * s_t
+      grads = torch.autograd.grad(surrogate, occ_leaves)
+      opt_occ.step([g.contiguous() for g in grads])
+      state['entropy'] = float(s_t.detach())
+    state['i'] += 1
 
   graph = None
   step()  # warm-up outside the capture (one-time attribute calls); counts as step 0
   first_energy = float(out[0].sum().item())
-  if use_cuda_graph and not use_k_mesh:
+  if use_cuda_graph and not use_k_mesh and not trainable:
     graph = torch.cuda.CUDAGraph()
     with torch.cuda.graph(graph):
       step()
     # the capture does not execute: parameters are those after step 0
 
   checker = create_convergence_checker(config)
-  sched = temperature_scheduler(config)
   history = [first_energy]
   converged = checker.check(first_energy)
   t0 = time.perf_counter()
@@ -121,19 +163,23 @@ def calc(config: Optional[JrystalConfigDict] = None, plan: Optional[Plan] = None
     converged = checker.check(etot)
     if log is not None and (i % 50 == 0 or converged):
       temp = sched(i)
-      log(f'step {i}: Loss {etot - temp * entropy:.6f} | Energy {etot + ew:.6f} | '
-          f'Entropy {entropy:.4f} | T {temp:.2E}')
+      log(f'step {i}: Loss {etot - temp * state["entropy"]:.6f} | Energy {etot + ew:.6f} | '
+          f'Entropy {state["entropy"]:.4f} | T {temp:.2E}')
   torch.cuda.synchronize()
   dt = (time.perf_counter() - t0) / max(steps - 1, 1)
   plan.check_status()
   # final energies at the final parameters (lines 223-247 of the reference)
+  if trainable:
+    occ_t = get_occupation().detach()
+    occ.copy_(occ_t[:, k0:k1])
+    state['entropy'] = float(occupation.fermi_dirac_entropy_torch(occ_t, config.eps))
   plan.eval_begin(w_re, w_im, occ, rho, e_kin)
   if use_k_mesh:
     parallel.allreduce_density(rho, e_kin, dbuf)
   plan.eval_finish(occ, rho, e_kin, config.xc, out=out)
   en = out[0].cpu().numpy()
   energies = dict(kinetic=float(en[0]), external=float(en[1]), hartree=float(en[2]),
-                  xc=float(en[3]), ewald=float(ew), entropy=float(entropy))
+                  xc=float(en[3]), ewald=float(ew), entropy=float(state['entropy']))
   return GroundStateEnergyOutput(
     config=config, crystal=crystal, params_pw={'w_re': w_re, 'w_im': w_im}, occupation=occ,
     density=rho.clone(), total_energy=float(en.sum() + ew), energies=energies,

@@ -41,6 +41,16 @@ extern "C" int jrb_set_atoms(jrb_plan* p, const double* pos_h, const double* chg
   return launch_set_atoms(p, pos_h, chg_h, na, S(st));
 }
 
+extern "C" int jrb_set_external_potential(jrb_plan* p, const double* vhat, jrb_stream st) {
+  int rc = enter(p);
+  if (rc) return rc;
+  REQUIRE(vhat, "null array");
+  JRB_CUDA(cudaMemcpyAsync(p->d_vext, vhat, sizeof(cplx) * (size_t)p->ngrid, cudaMemcpyDeviceToDevice,
+                           S(st)));
+  if (p->natoms <= 0) p->natoms = 1;  // "an external potential is set"
+  return 0;
+}
+
 extern "C" int jrb_set_kpoints(jrb_plan* p, const double* kpts_h, jrb_stream st) {
   int rc = enter(p);
   if (rc) return rc;

@@ -92,6 +92,13 @@ class Plan:
                                       pos.shape[0], _stream()))
     self._atoms = True
 
+  def set_external_potential(self, vhat):
+    """V(G) of the external / local pseudopotential term, complex128 CUDA tensor (nx, ny, nz) in
+    the convention of potential.external_reciprocal (potential.py:153-166)."""
+    self._chk(vhat, (self.nx, self.ny, self.nz), torch.complex128, 'vhat')
+    _lib.check(self.lib.jrb_set_external_potential(self._h, _ptr(vhat), _stream()))
+    self._atoms = True
+
   def set_kpoints(self, kpts):
     """Same number of k-points, new vectors (band-structure walk along a k-path)."""
     k = np.ascontiguousarray(np.asarray(kpts, dtype=np.float64).reshape(-1, 3))

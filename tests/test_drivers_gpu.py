@@ -70,6 +70,53 @@ def test_energy_driver_follows_the_oracle_trajectory(cuda_device, graph):
   assert out.total_energy_history[-1] < out.total_energy_history[0]
 
 
+@pytest.mark.parametrize('method', ['simplex-projector', 'idempotent'])
+def test_energy_driver_with_trainable_occupations(cuda_device, method):
+  """Free-energy minimisation over plane-wave AND occupation parameters (the reference's default
+  occupation scheme): 8 steps against the oracle (evaluation + literal occupation map + entropy,
+  torch autograd) with the same Adam and temperature schedule."""
+  from jrystal_b200 import calc
+  from jrystal_b200.calc.calc_ground_state_energy_all_electrons import temperature_scheduler
+  cfg = _config(epoch=8, occupation=method, smearing=0.01)
+  out = calc.energy(cfg)
+  c = out.crystal
+  s = rp.System(c.cell_vectors, c.positions, c.charges, [12, 12, 12], k_grid_sizes=[1, 1, 2],
+                cutoff_energy=10, mask_method='spherical')
+  nb = int(np.ceil(c.num_electron / 2)) + 2
+  ne = int(c.num_electron)
+  rng = np.random.default_rng(cfg.seed)
+  if method == 'simplex-projector':
+    n = nb * s.num_k
+    v = ((np.arange(n) - n // 2) * 0.1).reshape(s.num_k, nb)
+    leaves = [torch.tensor(v.copy(), requires_grad=True), torch.tensor(v.copy(), requires_grad=True)]
+    occ_fn = lambda: rp.occupation_simplex_projector(leaves[0], leaves[1], ne)
+  else:
+    w = rng.random((nb * s.num_k, (ne // 2) * s.num_k))
+    leaves = [torch.tensor(w, requires_grad=True)]
+    occ_fn = lambda: rp.occupation_idempotent(leaves[0], leaves[0], s.num_k)
+  shape = (1, s.num_k, s.num_g, nb)
+  w_re, w_im = rng.random(shape), rng.random(shape)
+  st = [np.zeros(shape) for _ in range(4)]
+  st_occ = [(np.zeros(l.shape), np.zeros(l.shape)) for l in leaves]
+  sched = temperature_scheduler(cfg)
+  for t in range(1, cfg.epoch + 1):
+    o = occ_fn()
+    ref = rp.energy_and_grad(s, w_re, w_im, o.detach().numpy(), occ_grad=True)
+    assert abs(out.total_energy_history[t - 1] - ref['e_tot']) < 1e-10 * abs(ref['e_tot']), t
+    sur = (torch.from_numpy(ref['g_occ']) * o).sum() - sched(t - 1) * rp.entropy_fermi_dirac(o, cfg.eps)
+    grads = torch.autograd.grad(sur, leaves)
+    _adam_numpy(w_re, ref['g_re'], st[0], st[1], t)
+    _adam_numpy(w_im, ref['g_im'], st[2], st[3], t)
+    for l, g, (m, v) in zip(leaves, grads, st_occ):
+      p = l.detach().numpy().copy()
+      _adam_numpy(p, g.numpy(), m, v, t)
+      with torch.no_grad():
+        l.copy_(torch.from_numpy(p))
+  o = occ_fn().detach()
+  assert relerr(out.occupation.cpu().numpy(), o.numpy()) < 1e-9
+  assert abs(float(out.occupation.sum()) - ne) < 1e-9
+
+
 def test_energy_driver_converges_and_stops(cuda_device):
   from jrystal_b200 import calc
   cfg = _config(epoch=400, convergence_window_size=5, convergence_condition=5e-2)

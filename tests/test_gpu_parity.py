@@ -273,6 +273,29 @@ def test_rows_plan_rejects_grid_calls(cuda_device):
     check(_check)
 
 
+def test_external_potential_from_the_caller(cuda_device):
+  """jrb_set_external_potential with the oracle's V_ext(G) reproduces jrb_set_atoms; a scaled
+  V(G) scales E_ext (the local-pseudopotential use: any V_loc(G) the host prepares)."""
+  s, plan, w_re, w_im, occ = _setup('diamond_16')
+  q = rp.unitary_matrix(torch.from_numpy(w_re), torch.from_numpy(w_im))
+  rho = rp.density_grid(rp.expand_coefficient(q, s.mask), s.vol, torch.from_numpy(occ))
+  rho_d = rho.cuda().contiguous()
+  en0, v0 = plan.grid_potential(rho_d, 'lda_x', False)
+  vhat = rp.external_reciprocal(s.positions, s.charges, s.g_vec, s.vol)
+  import jrystal_b200 as jb
+  plan2 = jb.Plan(s.cell, s.mask, s.kpts, CASES['diamond_16']['nb'])
+  with pytest.raises(RuntimeError):
+    plan2.grid_potential(rho_d)
+  plan2.set_external_potential(torch.as_tensor(vhat).to(torch.complex128).cuda().contiguous())
+  en1, v1 = plan2.grid_potential(rho_d, 'lda_x', False)
+  assert relerr(en1.cpu().numpy(), en0.cpu().numpy()) < 1e-12
+  assert relerr(v1.cpu().numpy(), v0.cpu().numpy()) < 1e-12
+  plan2.set_external_potential(0.5 * torch.as_tensor(vhat).to(torch.complex128).cuda().contiguous())
+  en2, _ = plan2.grid_potential(rho_d, 'lda_x', False)
+  assert abs(en2[1].item() - 0.5 * en0[1].item()) < 1e-12 * abs(en0[1].item())
+  assert abs(en2[0].item() - en0[0].item()) < 1e-12 * abs(en0[0].item())
+
+
 def test_mid_band_count_few_kpoints_qr(cuda_device):
   """33..96 bands with few k-points take the multi-CTA panel Cholesky (two panels, the second one
   partial) and the blocked triangular inverse."""

@@ -202,3 +202,42 @@ def test_temperature_schedule_matches_optax_exponential_decay():
   assert abs(s(50) - 0.001) < 1e-12 and s(99) == 0.001      # init * rate^(i / (epoch // 2)), floored
   assert abs(s(25) - 100.0 * (0.001 / 100.0) ** 0.5) < 1e-12
   assert temperature_scheduler(get_config(smearing=0.0))(10) == 0.0
+
+
+def test_trainable_occupations_match_the_literal_restatement():
+  """jrystal_b200.occupation (sort/cumsum projection, autograd) against the step-by-step
+  restatement of the reference's `proj` / simplex_projector / idempotent in the oracle, and the
+  constraints they must satisfy (occupation.py:299-366, 55-80)."""
+  from jrystal_b200 import occupation as occ
+  g = torch.Generator().manual_seed(3)
+  for n, m in [(12, 5), (40, 17), (7, 6), (9, 1), (16, 8)]:
+    x = torch.rand(n, dtype=torch.float64, generator=g)
+    a = occ._capped_simplex(x, float(m))
+    b = rp.occupation_proj(x, float(m))
+    assert float((a - b).abs().max()) < 1e-14
+    assert abs(float(a.sum()) - m) < 1e-12 and float(a.min()) >= 0 and float(a.max()) <= 1
+    # projecting a feasible point changes nothing
+    assert float((occ._capped_simplex(a, float(m)) - a).abs().max()) < 1e-14
+  nk, nb, ne = 3, 6, 8
+  p = {k: v.detach().cpu().requires_grad_(True) for k, v in occ.simplex_projector_init(nb, nk).items()}
+  o = occ.simplex_projector(p, ne)
+  ref = rp.occupation_simplex_projector(p['param_up'].detach(), p['param_down'].detach(), ne)
+  assert o.shape == (1, nk, nb) and float((o.detach() - ref).abs().max()) < 1e-14
+  assert abs(float(o.sum()) - ne) < 1e-12
+  # autograd through the projection against central differences
+  w = torch.rand(1, nk, nb, dtype=torch.float64, generator=g)
+  gu, = torch.autograd.grad((o * w).sum(), [p['param_up']])
+  i, j, h = 1, 2, 1e-6
+  vals = []
+  for sgn in (+1, -1):
+    q = {k: v.detach().clone() for k, v in p.items()}
+    q['param_up'][i, j] += sgn * h
+    vals.append(float((occ.simplex_projector(q, ne) * w).sum()))
+  assert abs(gu[i, j].item() - (vals[0] - vals[1]) / (2 * h)) < 1e-6
+  # idempotent: diag of a rank-(ne/2 nk) projector, trace fixed
+  ip = occ.idempotent_param_init(5, nb, ne, nk)
+  ip = {k: {'w_re': v['w_re'].detach().cpu()} for k, v in ip.items()}
+  oi = occ.idempotent(ip, nk)
+  refi = rp.occupation_idempotent(ip['param_up']['w_re'], ip['param_down']['w_re'], nk)
+  assert float((oi - refi).abs().max()) < 1e-13 and abs(float(oi.sum()) - ne) < 1e-10
+  assert float(oi.min()) >= 0 and float(oi.max()) <= 2.0 / nk + 1e-12
