@@ -74,6 +74,13 @@ int64_t jrb_plan_workspace_bytes(const jrb_plan* plan);
 int jrb_set_atoms(jrb_plan* plan, const double* positions_host, const double* charges_host,
                   int32_t natoms, jrb_stream stream);
 
+/* Position cotangent of energy.external (energy.py:121-135 through potential.external_reciprocal,
+ * potential.py:153-166) for the atoms of the last jrb_set_atoms: grad[a][c] = dE_ext / dR_a,c, what
+ * jax.grad w.r.t. `position` gives the reference (docs/tutorial/differentiation.rst:128-147);
+ * forces are minus this minus the Ewald part.  rho: (ns, nx, ny, nz); grad: device, [natoms][3]. */
+int jrb_external_position_gradient(jrb_plan* plan, const double* rho, double* grad,
+                                   jrb_stream stream);
+
 /* Sets the reciprocal-space external potential V(G) directly (device, complex (nx, ny, nz), the
  * convention of potential.external_reciprocal: E = Re sum_G conj(V) rho_hat * Omega / N^2,
  * v(r) = ifftn(V)).  Besides replacing jrb_set_atoms this is the LOCAL part of a norm-conserving

@@ -41,6 +41,14 @@ extern "C" int jrb_set_atoms(jrb_plan* p, const double* pos_h, const double* chg
   return launch_set_atoms(p, pos_h, chg_h, na, S(st));
 }
 
+extern "C" int jrb_external_position_gradient(jrb_plan* p, const double* rho, double* grad,
+                                              jrb_stream st) {
+  int rc = enter(p);
+  if (rc) return rc;
+  REQUIRE(rho && grad, "null array");
+  return launch_external_position_gradient(p, rho, grad, S(st));
+}
+
 extern "C" int jrb_set_external_potential(jrb_plan* p, const double* vhat, jrb_stream st) {
   int rc = enter(p);
   if (rc) return rc;
@@ -48,6 +56,7 @@ extern "C" int jrb_set_external_potential(jrb_plan* p, const double* vhat, jrb_s
   JRB_CUDA(cudaMemcpyAsync(p->d_vext, vhat, sizeof(cplx) * (size_t)p->ngrid, cudaMemcpyDeviceToDevice,
                            S(st)));
   if (p->natoms <= 0) p->natoms = 1;  // "an external potential is set"
+  p->atoms_on_device = 0;             // no point charges behind it
   return 0;
 }
 

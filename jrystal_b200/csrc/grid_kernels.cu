@@ -100,18 +100,89 @@ int launch_set_atoms(jrb_plan* p, const double* pos_h, const double* chg_h, int 
     set_error("jrb_set_atoms: need natoms > 0 and non-null positions/charges");
     return JRB_EINVAL;
   }
-  double *dpos = nullptr, *dchg = nullptr;
-  JRB_CUDA(cudaMalloc(&dpos, sizeof(double) * 3 * na));
-  JRB_CUDA(cudaMalloc(&dchg, sizeof(double) * na));
-  JRB_CUDA(cudaMemcpyAsync(dpos, pos_h, sizeof(double) * 3 * na, cudaMemcpyHostToDevice, st));
-  JRB_CUDA(cudaMemcpyAsync(dchg, chg_h, sizeof(double) * na, cudaMemcpyHostToDevice, st));
+  if (p->d_pos) cudaFree(p->d_pos);
+  if (p->d_chg) cudaFree(p->d_chg);
+  if (p->d_atom_part) cudaFree(p->d_atom_part);
+  p->d_pos = p->d_chg = p->d_atom_part = nullptr;
+  p->atoms_on_device = 0;
+  JRB_CUDA(cudaMalloc(&p->d_pos, sizeof(double) * 3 * na));
+  JRB_CUDA(cudaMalloc(&p->d_chg, sizeof(double) * na));
+  JRB_CUDA(cudaMalloc(&p->d_atom_part, sizeof(double) * 3 * 64 * na));
+  JRB_CUDA(cudaMemcpyAsync(p->d_pos, pos_h, sizeof(double) * 3 * na, cudaMemcpyHostToDevice, st));
+  JRB_CUDA(cudaMemcpyAsync(p->d_chg, chg_h, sizeof(double) * na, cudaMemcpyHostToDevice, st));
   const int blocks = (int)std::min<long long>((p->ngrid + 255) / 256, 148 * 8);
-  k_vext<<<blocks, 256, 0, st>>>(geom_of(p), dpos, dchg, na, p->d_vext);
+  k_vext<<<blocks, 256, 0, st>>>(geom_of(p), p->d_pos, p->d_chg, na, p->d_vext);
   JRB_CHECK_LAUNCH("k_vext");
-  JRB_CUDA(cudaStreamSynchronize(st));
-  cudaFree(dpos);
-  cudaFree(dchg);
+  JRB_CUDA(cudaStreamSynchronize(st));  // the host arrays may go away after the call
   p->natoms = na;
+  p->atoms_on_device = 1;
+  return 0;
+}
+
+// dE_ext / dR_a = (4 pi Z_a / N) sum_G G Im(exp(+i G.R_a) rho_hat(G)) / (|G|^2 + 1e-10), G != 0:
+// the position cotangent of energy.external (energy.py:121-135 through potential.py:153-166; the
+// reference gets it from jax.grad, docs/tutorial/differentiation.rst:128-147).
+// grid: (64, natoms), block 256; partials [atom][block][3], summed in block order (deterministic)
+__global__ void __launch_bounds__(RED_THREADS)
+k_ext_pos_grad(GridGeom g, const cplx* __restrict__ rho_hat, const double* __restrict__ pos,
+               const double* __restrict__ chg, double* __restrict__ part) {
+  const int a = blockIdx.y;
+  const double rx = pos[3 * a], ry = pos[3 * a + 1], rz = pos[3 * a + 2];
+  double acc[3] = {0.0, 0.0, 0.0};
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < g.n;
+       i += (long long)gridDim.x * blockDim.x) {
+    if (i == 0) continue;
+    double gx, gy, gz;
+    g_of(g, i, gx, gy, gz);
+    double sn, cs;
+    sincos(gx * rx + gy * ry + gz * rz, &sn, &cs);
+    const cplx r = rho_hat[i];
+    const double w = (cs * r.y + sn * r.x) / (gx * gx + gy * gy + gz * gz + 1e-10);
+    acc[0] += gx * w;
+    acc[1] += gy * w;
+    acc[2] += gz * w;
+  }
+  const double f = 4.0 * M_PI * chg[a] / (double)g.n;
+  double out[3];
+  block_sum<3>(acc, out);
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int c = 0; c < 3; ++c) part[((long long)a * gridDim.x + blockIdx.x) * 3 + c] = out[c] * f;
+  }
+}
+
+__global__ void k_ext_pos_grad_reduce(const double* __restrict__ part, int nblocks, int n3,
+                                      double* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;  // atom * 3 + component
+  if (i >= n3) return;
+  const int a = i / 3, c = i % 3;
+  double s = 0.0;
+  for (int b = 0; b < nblocks; ++b) s += part[((long long)a * nblocks + b) * 3 + c];
+  out[i] = s;
+}
+
+__global__ void k_rho_to_complex(const double* __restrict__ rho, int ns, long long n,
+                                 cplx* __restrict__ grid);
+
+int launch_external_position_gradient(jrb_plan* p, const double* rho, double* grad,
+                                      cudaStream_t st) {
+  if (!p->atoms_on_device) {
+    set_error("jrb_external_position_gradient: call jrb_set_atoms first");
+    return JRB_EINVAL;
+  }
+  const GridGeom g = geom_of(p);
+  const int blocks = (int)std::min<long long>((p->ngrid + RED_THREADS - 1) / RED_THREADS,
+                                              (long long)p->n_partial_blocks);
+  k_rho_to_complex<<<blocks, RED_THREADS, 0, st>>>(rho, p->ns, p->ngrid, p->d_grid);
+  JRB_CHECK_LAUNCH("k_rho_to_complex");
+  int rc = launch_fft3d_dense(p, p->d_grid, p->d_grid, JRB_FFT_FORWARD, 1, 1.0, st);
+  if (rc) return rc;
+  k_ext_pos_grad<<<dim3(64, p->natoms), RED_THREADS, 0, st>>>(g, p->d_grid, p->d_pos, p->d_chg,
+                                                              p->d_atom_part);
+  JRB_CHECK_LAUNCH("k_ext_pos_grad");
+  k_ext_pos_grad_reduce<<<(3 * p->natoms + 127) / 128, 128, 0, st>>>(p->d_atom_part, 64,
+                                                                   3 * p->natoms, grad);
+  JRB_CHECK_LAUNCH("k_ext_pos_grad_reduce");
   return 0;
 }
 

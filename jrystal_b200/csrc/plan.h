@@ -82,6 +82,9 @@ struct jrb_plan {
   double* d_veff;         // [ns][ngrid] effective potential of the fused evaluation
   int n_partial_blocks;
   int natoms;
+  double *d_pos, *d_chg;   // atoms of the last jrb_set_atoms (position gradient of E_ext)
+  double* d_atom_part;     // [natoms][64][3] block partials of that gradient
+  int atoms_on_device;
   // evaluation work space (Q, R, R^-1, HQ, W-sized temp)
   jrb::cplx *d_q, *d_hq, *d_tmp;
   jrb::cplx *d_r, *d_rinv, *d_small;  // [ns*nk][nb][nb] each (d_small: 5 of them)
@@ -127,6 +130,7 @@ int launch_expand(jrb_plan* p, const cplx* q, cplx* dense, cudaStream_t st);
 int launch_squeeze(jrb_plan* p, const cplx* dense, cplx* q, cudaStream_t st);
 int launch_focc(jrb_plan* p, const double* occ, cudaStream_t st);
 int launch_set_kpoints(jrb_plan* p, const double* kpts_h, cudaStream_t st);
+int launch_external_position_gradient(jrb_plan* p, const double* rho, double* grad, cudaStream_t st);
 
 // qr.cu
 int qr_gram_partial_mats(const jrb_plan* p);

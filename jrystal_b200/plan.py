@@ -91,6 +91,16 @@ class Plan:
     _lib.check(self.lib.jrb_set_atoms(self._h, pos.ctypes.data, chg.ctypes.data,
                                       pos.shape[0], _stream()))
     self._atoms = True
+    self._natoms = int(pos.shape[0])
+
+  def external_position_gradient(self, rho):
+    """dE_ext / d position, (natoms, 3), for the atoms of set_atoms."""
+    self._chk(rho, (self.ns, self.nx, self.ny, self.nz), torch.float64, 'density')
+    if not getattr(self, '_natoms', 0):
+      raise RuntimeError('call set_atoms(positions, charges) first')
+    g = self._new((self._natoms, 3), torch.float64)
+    _lib.check(self.lib.jrb_external_position_gradient(self._h, _ptr(rho), _ptr(g), _stream()))
+    return g
 
   def set_external_potential(self, vhat):
     """V(G) of the external / local pseudopotential term, complex128 CUDA tensor (nx, ny, nz) in
@@ -98,6 +108,7 @@ class Plan:
     self._chk(vhat, (self.nx, self.ny, self.nz), torch.complex128, 'vhat')
     _lib.check(self.lib.jrb_set_external_potential(self._h, _ptr(vhat), _stream()))
     self._atoms = True
+    self._natoms = 0
 
   def set_kpoints(self, kpts):
     """Same number of k-points, new vectors (band-structure walk along a k-path)."""

@@ -273,6 +273,28 @@ def test_rows_plan_rejects_grid_calls(cuda_device):
     check(_check)
 
 
+def test_external_position_gradient(cuda_device):
+  """dE_ext/dR from the kernel against central differences of the oracle's energy.external."""
+  s, plan, w_re, w_im, occ = _setup('diamond_16')
+  q = rp.unitary_matrix(torch.from_numpy(w_re), torch.from_numpy(w_im))
+  rho = rp.density_grid(rp.expand_coefficient(q, s.mask), s.vol, torch.from_numpy(occ))
+  rho_g = torch.fft.fftn(rho, dim=(-3, -2, -1))
+  g = plan.external_position_gradient(rho.cuda().contiguous()).cpu().numpy()
+  assert g.shape == (len(s.charges), 3)
+  h = 1e-5
+  for a, c in [(0, 0), (1, 2), (0, 1)]:
+    e = []
+    for sgn in (+1, -1):
+      pos = s.positions.copy()
+      pos[a, c] += sgn * h
+      e.append(rp.energy_external(rho_g, pos, s.charges, s.g_vec, s.vol).item())
+    fd = (e[0] - e[1]) / (2 * h)
+    assert abs(g[a, c] - fd) < 1e-6 * max(1.0, abs(fd)), (a, c, g[a, c], fd)
+  # translation invariance of the density-potential system is broken only by rho: sum_a grad_a
+  # equals minus the force on the electrons; at least it must be finite and real
+  assert np.isfinite(g).all()
+
+
 def test_external_potential_from_the_caller(cuda_device):
   """jrb_set_external_potential with the oracle's V_ext(G) reproduces jrb_set_atoms; a scaled
   V(G) scales E_ext (the local-pseudopotential use: any V_loc(G) the host prepares)."""
