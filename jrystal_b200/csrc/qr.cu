@@ -237,16 +237,28 @@ k_chol_panel(cplx* __restrict__ S, cplx* __restrict__ Rt, int nb, int p0, int* _
     }
     __syncthreads();
     if (k0 + CP < p0) fetch(k0 + CP);
+    if (tile == 0) {  // the diagonal tile has no rows below (whole-CTA branch)
 #pragma unroll 8
-    for (int k = 0; k < CP; ++k) {
-      const cplx lc = Ld[c * CP_LD + k];
+      for (int k = 0; k < CP; ++k) {
+        const cplx lc = Ld[c * CP_LD + k];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const int r = rb + 8 * j;
-        const cplx u = cmulc(Ld[r * CP_LD + k], lc);
-        accD[j].x -= u.x; accD[j].y -= u.y;
-        const cplx v = cmulc(Lr[r * CP_LD + k], lc);
-        accT[j].x -= v.x; accT[j].y -= v.y;
+        for (int j = 0; j < 4; ++j) {
+          const cplx u = cmulc(Ld[(rb + 8 * j) * CP_LD + k], lc);
+          accD[j].x -= u.x; accD[j].y -= u.y;
+        }
+      }
+    } else {
+#pragma unroll 8
+      for (int k = 0; k < CP; ++k) {
+        const cplx lc = Ld[c * CP_LD + k];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int r = rb + 8 * j;
+          const cplx u = cmulc(Ld[r * CP_LD + k], lc);
+          accD[j].x -= u.x; accD[j].y -= u.y;
+          const cplx v = cmulc(Lr[r * CP_LD + k], lc);
+          accT[j].x -= v.x; accT[j].y -= v.y;
+        }
       }
     }
   }
