@@ -74,6 +74,20 @@ int64_t jrb_plan_workspace_bytes(const jrb_plan* plan);
 int jrb_set_atoms(jrb_plan* plan, const double* positions_host, const double* charges_host,
                   int32_t natoms, jrb_stream stream);
 
+/* Non-local part of a norm-conserving pseudopotential (pseudopotential/nloc.py:143-158, 217-236):
+ * phi = potential_nl_psi_reciprocal restricted to the cut-off sphere, device complex
+ * (nk, nproj, ng), p = (beta, m) flattened, sqrt(D) already folded in as the reference does
+ * (nloc.py:60-141).  Once set (nproj > 0; nproj == 0 removes it; allocates, set-up time):
+ *   - jrb_hpsi adds  Phi^H (Phi q) / vol  (hamiltonian_nonlocal applied to q), so
+ *     jrb_band_expect / jrb_hamiltonian_matrix and the gradients of jrb_eval_finish include it;
+ *   - jrb_eval_begin adds E_nl = sum f |Phi q|^2 / vol (energy_nonlocal) to its e_kin output,
+ *     which then is "kinetic + non-local" in energies[0];
+ *   - jrb_nonlocal_energy returns E_nl alone (device double).
+ * With projectors set jrb_energy_grad_host runs its unchunked (non-pipelined) variant. */
+int jrb_set_nonlocal(jrb_plan* plan, const double* phi, int32_t nproj, jrb_stream stream);
+int jrb_nonlocal_energy(jrb_plan* plan, const double* q, const double* occ, double* e_nl,
+                        jrb_stream stream);
+
 /* Position cotangent of energy.external (energy.py:121-135 through potential.external_reciprocal,
  * potential.py:153-166) for the atoms of the last jrb_set_atoms: grad[a][c] = dE_ext / dR_a,c, what
  * jax.grad w.r.t. `position` gives the reference (docs/tutorial/differentiation.rst:128-147);

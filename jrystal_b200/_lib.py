@@ -31,6 +31,8 @@ SYMBOLS = {
   'jrb_set_atoms': (ctypes.c_int, [_P, _P, _P, _I32, _P]),
   'jrb_set_external_potential': (ctypes.c_int, [_P, _P, _P]),
   'jrb_external_position_gradient': (ctypes.c_int, [_P, _P, _P, _P]),
+  'jrb_set_nonlocal': (ctypes.c_int, [_P, _P, _I32, _P]),
+  'jrb_nonlocal_energy': (ctypes.c_int, [_P, _P, _P, _P, _P]),
   'jrb_set_kpoints': (ctypes.c_int, [_P, _P, _P]),
   'jrb_qr_fwd': (ctypes.c_int, [_P, _P, _P, _P, _P, _P]),
   'jrb_qr_bwd': (ctypes.c_int, [_P, _P, _P, _P, _P, _P, _P]),

@@ -41,6 +41,38 @@ extern "C" int jrb_set_atoms(jrb_plan* p, const double* pos_h, const double* chg
   return launch_set_atoms(p, pos_h, chg_h, na, S(st));
 }
 
+extern "C" int jrb_set_nonlocal(jrb_plan* p, const double* phi, int32_t nproj, jrb_stream st) {
+  int rc = enter(p);
+  if (rc) return rc;
+  REQUIRE(nproj >= 0 && (nproj == 0 || phi), "bad projector table");
+  for (cplx** q : {&p->d_nl_phi, &p->d_nl_p, &p->d_nl_part}) {
+    if (*q) cudaFree(*q);
+    *q = nullptr;
+  }
+  p->nproj = 0;
+  if (nproj == 0) return 0;
+  const size_t nphi = (size_t)p->nk * nproj * p->ng;
+  const size_t np = (size_t)p->ns * p->nk * nproj * p->nb;
+  JRB_CUDA(cudaMalloc(&p->d_nl_phi, nphi * sizeof(cplx)));
+  JRB_CUDA(cudaMalloc(&p->d_nl_p, np * sizeof(cplx)));
+  JRB_CUDA(cudaMalloc(&p->d_nl_part, 16 * np * sizeof(cplx)));
+  JRB_CUDA(cudaMemcpyAsync(p->d_nl_phi, phi, nphi * sizeof(cplx), cudaMemcpyDeviceToDevice, S(st)));
+  p->nproj = nproj;
+  p->ws_bytes += (int64_t)((nphi + 17 * np) * sizeof(cplx));
+  return 0;
+}
+
+extern "C" int jrb_nonlocal_energy(jrb_plan* p, const double* q, const double* occ, double* e_nl,
+                                   jrb_stream st) {
+  int rc = enter(p);
+  if (rc) return rc;
+  REQUIRE(q && occ && e_nl, "null array");
+  REQUIRE(p->nproj > 0, "call jrb_set_nonlocal first");
+  JRB_CUDA(cudaMemsetAsync(e_nl, 0, sizeof(double), S(st)));
+  if ((rc = launch_nonlocal_project(p, 0, p->ns * p->nk, C(q), S(st)))) return rc;
+  return launch_nonlocal_energy(p, occ, e_nl, S(st));
+}
+
 extern "C" int jrb_external_position_gradient(jrb_plan* p, const double* rho, double* grad,
                                               jrb_stream st) {
   int rc = enter(p);
@@ -249,7 +281,13 @@ extern "C" int jrb_eval_begin(jrb_plan* p, const double* w_re, const double* w_i
   p->keep_filled = rc == 0;
   if (rc) return rc;
   if ((rc = launch_kinetic(p, p->d_q, p->d_tkb, S(st)))) return rc;
-  return launch_weighted_sum(p, p->d_tkb, occ, (int64_t)p->ns * p->nk * p->nb, e_kin, S(st));
+  if ((rc = launch_weighted_sum(p, p->d_tkb, occ, (int64_t)p->ns * p->nk * p->nb, e_kin, S(st))))
+    return rc;
+  if (p->nproj > 0) {  // e_kin carries the sphere-local one-electron terms: kinetic + non-local
+    if ((rc = launch_nonlocal_project(p, 0, p->ns * p->nk, p->d_q, S(st)))) return rc;
+    if ((rc = launch_nonlocal_energy(p, occ, e_kin, S(st)))) return rc;
+  }
+  return 0;
 }
 
 __global__ void k_pack_energies(const double* e_kin, const double* grid_e, double* out) {
@@ -306,6 +344,7 @@ static int ensure_host_buffers(jrb_plan* p) {
 
 // k-point chunks of the host path: copies of chunk c+1 overlap the kernels of chunk c
 static int host_chunks(const jrb_plan* p) {
+  if (p->nproj > 0) return 1;  // the chunked pipeline does not carry the non-local energy term
   // chunking pays once a chunk carries tens of MB (measured on B200, C2: 1 chunk 24.8, 4 chunks
   // 35.3, 8 chunks 33.6, 16 chunks 27.3 eval/s end to end); tiny problems stay in one piece
   const double bytes = 16.0 * p->nk * (double)p->ng * p->nb;  // w_re + w_im

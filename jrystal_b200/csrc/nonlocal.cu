@@ -1,0 +1,181 @@
+// Non-local pseudopotential term on the cut-off sphere.
+//
+// Reference: hamiltonian_nonlocal / energy_nonlocal (jrystal/pseudopotential/nloc.py:143-158,
+// 217-236) contract the coefficients with potential_nl_psi_reciprocal Phi[k, beta, m, x, y, z]
+// (= 4 pi sqrt(D) Y_lm beta(|G+k|) exp(-i (G+k).R) i^l, nloc.py:60-141) over the WHOLE FFT box:
+//     F[s,k,b,p] = sum_G c[s,k,b,G] Phi[k,p,G]          (no conjugation, p = (beta, m) flattened)
+//     H_nl[b1,b2] = sum_p conj(F[b1,p]) F[b2,p] / vol,   E_nl = sum_skb f_skb H_nl[b,b]
+// c is zero outside the sphere, so only Phi on the sphere matters: the caller hands over
+// Phi[k][p][g] (nk x nproj x ng complex, 1.3 GB at C4 instead of 68 GB of dense projectors).  Then
+//     P[s,k,p,b] = sum_g Phi[k,p,g] Q[s,k,g,b]            (k_nl_project, split over row chunks)
+//     E_nl       = sum f_b |P[p,b]|^2 / vol               (k_nl_energy)
+//     HQ[g,b]   += sum_p conj(Phi[k,p,g]) P[p,b] / vol    (k_nl_apply)  = dE_nl/dQ* per unit f
+// First version: FP64 FMA kernels with shared-memory tiles (the products are ng x nproj x nb per
+// (spin,k): small next to the FFT work); a DMMA version belongs with rectangular Gram/apply tiles.
+#include <algorithm>
+
+#include "plan.h"
+
+namespace jrb {
+
+constexpr int NL_TP = 16;   // projectors per tile
+constexpr int NL_TB = 32;   // bands per tile
+constexpr int NL_TG = 32;   // sphere rows per smem slice
+constexpr int NL_CHUNKS = 16;
+
+// partial[chunk][sk][p][b] = sum_{g in chunk} Phi[k][p][g] Q[sk][g][b]
+// grid: (ceil(nproj/16) * ceil(nb/32), nsk, NL_CHUNKS), block (32, 16): thread (b, p)
+__global__ void __launch_bounds__(512)
+k_nl_project(const cplx* __restrict__ phi, const cplx* __restrict__ q, long long ng, int nb,
+             int nproj, int nk, int sk0, cplx* __restrict__ partial) {
+  __shared__ cplx sphi[NL_TP][NL_TG + 1];
+  __shared__ cplx sq[NL_TG][NL_TB + 1];
+  const int nbt = (nb + NL_TB - 1) / NL_TB;
+  const int p0 = (blockIdx.x / nbt) * NL_TP, b0 = (blockIdx.x % nbt) * NL_TB;
+  const int sk = blockIdx.y, k = (sk0 + sk) % nk;  // q / partial are indexed from sk0
+  const long long rows = (ng + gridDim.z - 1) / gridDim.z;
+  const long long g_lo = blockIdx.z * rows, g_hi = min(ng, g_lo + rows);
+  const int tb = threadIdx.x, tp = threadIdx.y;
+  const int tid = tp * 32 + tb;
+  cplx acc = cmake(0.0, 0.0);
+  for (long long g0 = g_lo; g0 < g_hi; g0 += NL_TG) {
+    {  // Phi tile: 16 x 32 elements, g fastest in memory
+      const int pp = tid / NL_TG, gg = tid % NL_TG;
+      const bool ok = p0 + pp < nproj && g0 + gg < g_hi;
+      sphi[pp][gg] = ok ? phi[((long long)k * nproj + p0 + pp) * ng + g0 + gg] : cmake(0.0, 0.0);
+    }
+    for (int e = tid; e < NL_TG * NL_TB; e += 512) {  // Q tile: 32 x 32, b fastest
+      const int gg = e / NL_TB, bb = e % NL_TB;
+      const bool ok = g0 + gg < g_hi && b0 + bb < nb;
+      sq[gg][bb] = ok ? q[((long long)sk * ng + g0 + gg) * nb + b0 + bb] : cmake(0.0, 0.0);
+    }
+    __syncthreads();
+#pragma unroll 8
+    for (int gg = 0; gg < NL_TG; ++gg) {
+      const cplx v = cmul(sphi[tp][gg], sq[gg][tb]);
+      acc.x += v.x; acc.y += v.y;
+    }
+    __syncthreads();
+  }
+  if (p0 + tp < nproj && b0 + tb < nb)
+    partial[(((long long)blockIdx.z * gridDim.y + sk) * nproj + p0 + tp) * nb + b0 + tb] = acc;
+}
+
+// P = sum of the chunk partials (fixed order).  grid: (ceil(nsk*nproj*nb / 256))
+__global__ void k_nl_reduce(const cplx* __restrict__ partial, int nchunks, long long n,
+                            cplx* __restrict__ P) {
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  cplx s = cmake(0.0, 0.0);
+  for (int c = 0; c < nchunks; ++c) {
+    const cplx v = partial[c * n + i];
+    s.x += v.x; s.y += v.y;
+  }
+  P[i] = s;
+}
+
+// e_out[0] += sum_{sk,p,b} occ[sk][b] |P|^2 / vol   (one CTA, fixed order)
+__global__ void __launch_bounds__(256)
+k_nl_energy(const cplx* __restrict__ P, const double* __restrict__ occ, int nsk, int nproj, int nb,
+            double inv_vol, double* __restrict__ e_out) {
+  __shared__ double sh[256];
+  double acc = 0.0;
+  const long long n = (long long)nsk * nproj * nb;
+  for (long long i = threadIdx.x; i < n; i += 256) {
+    const int b = (int)(i % nb);
+    const int sk = (int)(i / ((long long)nproj * nb));
+    const cplx v = P[i];
+    acc += occ[(long long)sk * nb + b] * (v.x * v.x + v.y * v.y);
+  }
+  sh[threadIdx.x] = acc;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) e_out[0] += sh[0] * inv_vol;
+}
+
+// hq[sk][g][b] += sum_p conj(Phi[k][p][g]) P[sk][p][b] / vol
+// grid: (ceil(ng/32), ceil(nb/32), nsk), block (32, 8): thread (b, g-sub), 4 rows each
+__global__ void __launch_bounds__(256)
+k_nl_apply(const cplx* __restrict__ phi, const cplx* __restrict__ P, long long ng, int nb,
+           int nproj, int nk, int sk0, double inv_vol, cplx* __restrict__ hq) {
+  __shared__ cplx sphi[NL_TP][NL_TG + 1];
+  __shared__ cplx sp[NL_TP][NL_TB + 1];
+  const long long g0 = (long long)blockIdx.x * NL_TG;
+  const int b0 = blockIdx.y * NL_TB;
+  const int sk = blockIdx.z, k = (sk0 + sk) % nk;  // P / hq are indexed from sk0
+  const int tb = threadIdx.x, ty = threadIdx.y;
+  const int tid = ty * 32 + tb;
+  cplx acc[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) acc[j] = cmake(0.0, 0.0);
+  for (int p0 = 0; p0 < nproj; p0 += NL_TP) {
+    for (int e = tid; e < NL_TP * NL_TG; e += 256) {
+      const int pp = e / NL_TG, gg = e % NL_TG;
+      const bool ok = p0 + pp < nproj && g0 + gg < ng;
+      sphi[pp][gg] = ok ? phi[((long long)k * nproj + p0 + pp) * ng + g0 + gg] : cmake(0.0, 0.0);
+    }
+    for (int e = tid; e < NL_TP * NL_TB; e += 256) {
+      const int pp = e / NL_TB, bb = e % NL_TB;
+      const bool ok = p0 + pp < nproj && b0 + bb < nb;
+      sp[pp][bb] = ok ? P[((long long)sk * nproj + p0 + pp) * nb + b0 + bb] : cmake(0.0, 0.0);
+    }
+    __syncthreads();
+#pragma unroll
+    for (int pp = 0; pp < NL_TP; ++pp) {
+      const cplx pv = sp[pp][tb];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const cplx f = sphi[pp][ty + 8 * j];
+        acc[j].x += f.x * pv.x + f.y * pv.y;   // conj(f) * pv
+        acc[j].y += f.x * pv.y - f.y * pv.x;
+      }
+    }
+    __syncthreads();
+  }
+  if (b0 + tb < nb) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const long long g = g0 + ty + 8 * j;
+      if (g < ng) {
+        cplx* o = hq + ((long long)sk * ng + g) * nb + b0 + tb;
+        const cplx h = *o;
+        *o = cmake(h.x + acc[j].x * inv_vol, h.y + acc[j].y * inv_vol);
+      }
+    }
+  }
+}
+
+// P of the (spin,k) range [sk0, sk0 + nsk) into p->d_nl_p (indexed from sk0)
+int launch_nonlocal_project(jrb_plan* p, int sk0, int nsk, const cplx* q, cudaStream_t st) {
+  const int nbt = (p->nb + NL_TB - 1) / NL_TB, npt = (p->nproj + NL_TP - 1) / NL_TP;
+  dim3 grid(npt * nbt, nsk, NL_CHUNKS), block(32, 16);
+  k_nl_project<<<grid, block, 0, st>>>(p->d_nl_phi, q + (long long)sk0 * p->ng * p->nb, p->ng, p->nb,
+                                      p->nproj, p->nk, sk0, p->d_nl_part);
+  JRB_CHECK_LAUNCH("k_nl_project");
+  const long long n = (long long)nsk * p->nproj * p->nb;
+  k_nl_reduce<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(p->d_nl_part, NL_CHUNKS, n,
+                                                          p->d_nl_p + (long long)sk0 * p->nproj * p->nb);
+  JRB_CHECK_LAUNCH("k_nl_reduce");
+  return 0;
+}
+
+int launch_nonlocal_energy(jrb_plan* p, const double* occ, double* e_inout, cudaStream_t st) {
+  k_nl_energy<<<1, 256, 0, st>>>(p->d_nl_p, occ, p->ns * p->nk, p->nproj, p->nb, 1.0 / p->vol,
+                                 e_inout);
+  JRB_CHECK_LAUNCH("k_nl_energy");
+  return 0;
+}
+
+int launch_nonlocal_apply(jrb_plan* p, int sk0, int nsk, cplx* hq, cudaStream_t st) {
+  dim3 grid((unsigned)((p->ng + NL_TG - 1) / NL_TG), (p->nb + NL_TB - 1) / NL_TB, nsk), block(32, 8);
+  k_nl_apply<<<grid, block, 0, st>>>(p->d_nl_phi, p->d_nl_p + (long long)sk0 * p->nproj * p->nb,
+                                     p->ng, p->nb, p->nproj, p->nk, sk0, 1.0 / p->vol,
+                                     hq + (long long)sk0 * p->ng * p->nb);
+  JRB_CHECK_LAUNCH("k_nl_apply");
+  return 0;
+}
+
+}  // namespace jrb

@@ -85,6 +85,11 @@ struct jrb_plan {
   double *d_pos, *d_chg;   // atoms of the last jrb_set_atoms (position gradient of E_ext)
   double* d_atom_part;     // [natoms][64][3] block partials of that gradient
   int atoms_on_device;
+  // non-local pseudopotential projectors on the sphere (nonlocal.cu); nproj == 0: none
+  int nproj;
+  jrb::cplx* d_nl_phi;   // [nk][nproj][ng]
+  jrb::cplx* d_nl_p;     // [ns*nk][nproj][nb]  P = Phi Q
+  jrb::cplx* d_nl_part;  // [16 chunks][ns*nk][nproj][nb]
   // evaluation work space (Q, R, R^-1, HQ, W-sized temp)
   jrb::cplx *d_q, *d_hq, *d_tmp;
   jrb::cplx *d_r, *d_rinv, *d_small;  // [ns*nk][nb][nb] each (d_small: 5 of them)
@@ -130,6 +135,9 @@ int launch_expand(jrb_plan* p, const cplx* q, cplx* dense, cudaStream_t st);
 int launch_squeeze(jrb_plan* p, const cplx* dense, cplx* q, cudaStream_t st);
 int launch_focc(jrb_plan* p, const double* occ, cudaStream_t st);
 int launch_set_kpoints(jrb_plan* p, const double* kpts_h, cudaStream_t st);
+int launch_nonlocal_project(jrb_plan* p, int sk0, int nsk, const cplx* q, cudaStream_t st);
+int launch_nonlocal_energy(jrb_plan* p, const double* occ, double* e_inout, cudaStream_t st);
+int launch_nonlocal_apply(jrb_plan* p, int sk0, int nsk, cplx* hq, cudaStream_t st);
 int launch_external_position_gradient(jrb_plan* p, const double* rho, double* grad, cudaStream_t st);
 
 // qr.cu

@@ -93,6 +93,26 @@ class Plan:
     self._atoms = True
     self._natoms = int(pos.shape[0])
 
+  def set_nonlocal(self, phi):
+    """Projectors of the non-local pseudopotential on the sphere: complex128 CUDA tensor
+    (nk, nproj, ng) = potential_nl_psi_reciprocal[..., mask] (nloc.py:60-141); None removes them."""
+    if phi is None:
+      _lib.check(self.lib.jrb_set_nonlocal(self._h, None, 0, _stream()))
+      self.nproj = 0
+      return
+    if phi.ndim != 3 or phi.shape[0] != self.nk or phi.shape[2] != self.ng:
+      raise ValueError(f'phi must have shape (nk={self.nk}, nproj, ng={self.ng}), got {tuple(phi.shape)}')
+    self._chk(phi, tuple(phi.shape), torch.complex128, 'phi')
+    _lib.check(self.lib.jrb_set_nonlocal(self._h, _ptr(phi), int(phi.shape[1]), _stream()))
+    self.nproj = int(phi.shape[1])
+
+  def nonlocal_energy(self, q, occ):
+    self._chk(q, self.sphere_shape, torch.complex128, 'q')
+    self._chk(occ, (self.ns, self.nk, self.nb), torch.float64, 'occupation')
+    e = self._new((1,), torch.float64)
+    _lib.check(self.lib.jrb_nonlocal_energy(self._h, _ptr(q), _ptr(occ), _ptr(e), _stream()))
+    return e
+
   def external_position_gradient(self, rho):
     """dE_ext / d position, (natoms, 3), for the atoms of set_atoms."""
     self._chk(rho, (self.ns, self.nx, self.ny, self.nz), torch.float64, 'density')

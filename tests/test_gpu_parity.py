@@ -299,6 +299,42 @@ def test_spin_polarised_energy_and_grad(cuda_device, case):
   assert relerr(g_occ.cpu().numpy(), ref['g_occ']) < G_TOL
 
 
+@pytest.mark.parametrize('case,nproj', [('diamond_16', 5), ('si_32', 18), ('diamond_789_cubic', 3)])
+def test_nonlocal_pseudopotential_term(cuda_device, case, nproj):
+  """energy_nonlocal / hamiltonian_nonlocal (pseudopotential/nloc.py:143-158, 217-236) with
+  synthetic projectors on the sphere: E_nl, the total energy (kinetic slot = kinetic + non-local),
+  the gradients and dE/d occ against the oracle contracting over the whole box."""
+  s, plan, w_re, w_im, occ = _setup(case)
+  rng = np.random.default_rng(17)
+  phi = 0.3 * (rng.standard_normal((s.num_k, nproj, s.num_g)) +
+               1j * rng.standard_normal((s.num_k, nproj, s.num_g)))
+  dense = np.zeros((s.num_k, nproj) + tuple(s.mask.shape), dtype=np.complex128)
+  dense[:, :, s.mask] = phi
+  ref = rp.energy_and_grad(s, w_re, w_im, occ, occ_grad=True, nonlocal_phi=dense)
+  plan.set_nonlocal(to_dev(phi))
+  occ_d = to_dev(occ)
+  rho, e_kin = plan.eval_begin(to_dev(w_re), to_dev(w_im), occ_d)
+  en, g_re, g_im, g_occ = plan.eval_finish(occ_d, rho, e_kin, 'lda_x', want_occ_grad=True)
+  en = en.cpu().numpy()
+  assert abs(en[0] - (ref['e_kin'] + ref['e_nl'])) < E_TOL * abs(ref['e_kin'] + ref['e_nl'])
+  assert abs(en.sum() - ref['e_tot']) / abs(ref['e_tot']) < E_TOL
+  assert relerr(g_re.cpu().numpy(), ref['g_re']) < G_TOL
+  assert relerr(g_im.cpu().numpy(), ref['g_im']) < G_TOL
+  assert relerr(g_occ.cpu().numpy(), ref['g_occ']) < G_TOL
+  q, _ = plan.qr_fwd(to_dev(w_re), to_dev(w_im))
+  e_nl = plan.nonlocal_energy(q, occ_d).item()
+  assert abs(e_nl - ref['e_nl']) < 1e-11 * abs(ref['e_nl'])
+  # host path (falls back to the unchunked variant) and removal of the projectors
+  en_h, g_re_h, _, _ = plan.energy_grad_host(w_re, w_im, occ)
+  assert abs(en_h.sum() - ref['e_tot']) / abs(ref['e_tot']) < E_TOL
+  assert relerr(g_re_h, ref['g_re']) < G_TOL
+  plan.set_nonlocal(None)
+  ref0 = rp.energy_and_grad(s, w_re, w_im, occ)
+  rho, e_kin = plan.eval_begin(to_dev(w_re), to_dev(w_im), occ_d)
+  en0, *_ = plan.eval_finish(occ_d, rho, e_kin, 'lda_x')
+  assert abs(en0.sum().item() - ref0['e_tot']) / abs(ref0['e_tot']) < E_TOL
+
+
 def test_external_position_gradient(cuda_device):
   """dE_ext/dR from the kernel against central differences of the oracle's energy.external."""
   s, plan, w_re, w_im, occ = _setup('diamond_16')
