@@ -38,6 +38,14 @@ WORKLOADS = {
               empty=16, text='C3a: diamond-64 supercell, 128^3, 40 Ha, Gamma, 208 bands'),
   'C3b': dict(crystal='diamond8', repeat=(2, 2, 2), grid=128, cutoff=40.0, kgrid=(2, 2, 2),
               empty=16, text='C3b: diamond-64 supercell, 128^3, 40 Ha, 2x2x2 k, 208 bands'),
+  # BASELINE config 4.  The Sr/Ti UPF files are not shipped with the reference, so the
+  # pseudopotential DATA are synthetic: valence point charges 10/12/6 for the local
+  # part, 18 random projectors per atom for the non-local part.  The arithmetic and the shapes
+  # (40 valence electrons, 30 bands, 90 projectors, 216 k-points) are those of the real run.
+  'C4': dict(crystal='srtio3', repeat=None, grid=64, cutoff=40.0, kgrid=(6, 6, 6), empty=10,
+             valence=[10, 12, 6, 6, 6], nproj_per_atom=18,
+             text='C4: SrTiO3 norm-conserving (synthetic PP data), 64^3, 40 Ha, 6x6x6 k, 30 bands, '
+                  '90 projectors'),
 }
 METRIC = 'energy+grad evals/sec'
 UNIT = 'eval/s'
@@ -61,10 +69,26 @@ def build_workload(name):
   gs = grid.proper_grid_size(w['grid'])
   mask = grid.spherical_mask(crystal.cell_vectors, gs, w['cutoff'])
   kpts = grid.k_vectors(crystal.cell_vectors, grid.proper_grid_size(w['kgrid']))
+  if 'valence' in w:  # pseudopotential run: the ions carry their valence charge
+    crystal.charges = np.asarray(w['valence'])
+    crystal.spin = 0
   nb = int(np.ceil(crystal.num_electron / 2)) + w['empty']
   occ = occupation.uniform(kpts.shape[0], crystal.num_electron, crystal.spin, nb)
+  nproj = w.get('nproj_per_atom', 0) * crystal.num_atom
   return dict(crystal=crystal, grid=[int(g) for g in gs], mask=mask, kpts=kpts, nb=nb, occ=occ,
-              ng=int(mask.sum()), text=w['text'])
+              ng=int(mask.sum()), text=w['text'], nproj=nproj)
+
+
+def synthetic_projectors(ng, nk, nproj, k0, k1, device):
+  """Random complex projector table (nk_local, nproj, ng), the same global stream on every rank."""
+  import torch
+  rng = np.random.default_rng(321)
+  out = np.empty((k1 - k0, nproj, ng), dtype=np.complex128)
+  for k in range(nk):
+    blk = 0.1 * (rng.standard_normal((nproj, ng)) + 1j * rng.standard_normal((nproj, ng)))
+    if k0 <= k < k1:
+      out[k - k0] = blk
+  return torch.from_numpy(out).to(device)
 
 
 def synthetic_params(ng, nk, nb, k0, k1):
@@ -171,10 +195,16 @@ def cpu_sample_eval(wl, nk_sample, steps, warmup):
   s.num_g = wl['ng']
   w_re, w_im = synthetic_params(wl['ng'], nk, wl['nb'], 0, nk_sample)
   occ = wl['occ'][:, :nk_sample]
+  dense_phi = None
+  if wl['nproj']:
+    # the reference contracts dense (kpt, proj, x, y, z) projectors over the whole box (nloc.py:143-158)
+    phi = synthetic_projectors(wl['ng'], nk, wl['nproj'], 0, nk_sample, 'cpu').numpy()
+    dense_phi = np.zeros((nk_sample, wl['nproj']) + tuple(wl['grid']), dtype=np.complex128)
+    dense_phi[:, :, wl['mask']] = phi
   times = []
   for i in range(warmup + steps):
     t0 = time.perf_counter()
-    rp.energy_and_grad(s, w_re, w_im, occ)
+    rp.energy_and_grad(s, w_re, w_im, occ, nonlocal_phi=dense_phi)
     dt = time.perf_counter() - t0
     if i >= warmup:
       times.append(dt)
@@ -188,7 +218,7 @@ def run_reference(args):
     return
   wl = build_workload(args.config)
   nk = wl['kpts'].shape[0]
-  nk_sample = {'C1': 8, 'C2': 8, 'C3a': 1, 'C3b': 1}[args.config]
+  nk_sample = {'C1': 8, 'C2': 8, 'C3a': 1, 'C3b': 1, 'C4': 8}[args.config]
   steps = max(1, min(args.steps, 3))
   value, t, cores, nks = cpu_sample_eval(wl, nk_sample, steps, min(args.warmup, 1))
   sample = (f'{nks} of {nk} k-points x {wl["nb"]} bands at {wl["grid"]} per step, time scaled '
@@ -345,6 +375,8 @@ def run_b200(args):
     sharding = f'EMULATED rank 0 of k{args.emulate_ranks} (no collectives; not a benchmark value)'
   plan = jb.Plan(c.cell_vectors, wl['mask'], wl['kpts'][k0:k1], nb, device=local_rank)
   plan.set_atoms(c.positions, c.charges)
+  if wl['nproj']:
+    plan.set_nonlocal(synthetic_projectors(ng, nk, wl['nproj'], k0, k1, 'cuda'))
   w_re_h, w_im_h = synthetic_params(ng, nk, nb, k0, k1)
   occ_h = np.ascontiguousarray(wl['occ'][:, k0:k1])
   w_re = torch.from_numpy(w_re_h).cuda()
@@ -554,7 +586,7 @@ def run_b200(args):
     }
     if world == 1 and not args.no_cpu:
       # bounded sample: ~10-20 s of CPU work
-      nks = {'C1': 8, 'C2': 8, 'C3a': 1, 'C3b': 1}[args.config]
+      nks = {'C1': 8, 'C2': 8, 'C3a': 1, 'C3b': 1, 'C4': 8}[args.config]
       v, t, cores, nks = cpu_sample_eval(wl, nks, 2 if args.config != 'C1' else 20, 1)
       line['cpu_baseline'] = {
         'value': v, 'unit': UNIT, 'cores': cores, 'kind': 'port',

@@ -40,6 +40,9 @@ BUILTIN = {
   'si8': (np.eye(3) * _A_SI, ['Si'] * 8,
           np.round(_DIAMOND_BASIS * _A_SI, 8)),
   'diamond8': (np.eye(3) * _A_C, ['C'] * 8, _DIAMOND_BASIS * _A_C),
+  # cubic perovskite, a = 3.899 A (geometry/srtio3.xyz of the reference)
+  'srtio3': (np.eye(3) * 3.899, ['Sr', 'Ti', 'O', 'O', 'O'],
+             np.array([[0.5, 0.5, 0.5], [0, 0, 0], [0.5, 0, 0], [0, 0.5, 0], [0, 0, 0.5]]) * 3.899),
   'al_primitive': (np.array([[0.0, 2.02475, 2.02475], [2.02475, 2.02475, 0.0],
                              [2.02475, 0.0, 2.02475]]), ['Al'], np.zeros((1, 3))),
 }

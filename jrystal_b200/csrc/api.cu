@@ -69,6 +69,7 @@ extern "C" int jrb_nonlocal_energy(jrb_plan* p, const double* q, const double* o
   REQUIRE(q && occ && e_nl, "null array");
   REQUIRE(p->nproj > 0, "call jrb_set_nonlocal first");
   JRB_CUDA(cudaMemsetAsync(e_nl, 0, sizeof(double), S(st)));
+  p->nl_p_valid = 0;
   if ((rc = launch_nonlocal_project(p, 0, p->ns * p->nk, C(q), S(st)))) return rc;
   return launch_nonlocal_energy(p, occ, e_nl, S(st));
 }
@@ -237,6 +238,7 @@ extern "C" int jrb_hpsi(jrb_plan* p, const double* q, const double* veff, double
   if (rc) return rc;
   REQUIRE(q && veff && hq, "null array");
   REQUIRE(q != hq, "hq must not alias q");
+  p->nl_p_valid = 0;
   return launch_hpsi(p, C(q), veff, C(hq), S(st));
 }
 
@@ -284,8 +286,10 @@ extern "C" int jrb_eval_begin(jrb_plan* p, const double* w_re, const double* w_i
   if ((rc = launch_weighted_sum(p, p->d_tkb, occ, (int64_t)p->ns * p->nk * p->nb, e_kin, S(st))))
     return rc;
   if (p->nproj > 0) {  // e_kin carries the sphere-local one-electron terms: kinetic + non-local
+    p->nl_p_valid = 0;
     if ((rc = launch_nonlocal_project(p, 0, p->ns * p->nk, p->d_q, S(st)))) return rc;
     if ((rc = launch_nonlocal_energy(p, occ, e_kin, S(st)))) return rc;
+    p->nl_p_valid = 1;  // the H-apply of jrb_eval_finish reuses P
   }
   return 0;
 }
@@ -311,6 +315,7 @@ extern "C" int jrb_eval_finish(jrb_plan* p, const double* occ, const double* rho
   rc = launch_hpsi(p, p->d_q, veff, p->d_hq, S(st));
   p->keep_read = 0;
   p->keep_filled = 0;  // the fused H-apply works in place on the kept columns
+  p->nl_p_valid = 0;
   if (rc) return rc;
   if (g_occ) {
     if ((rc = launch_band_expect(p, p->d_q, p->d_hq, g_occ, S(st)))) return rc;

@@ -231,7 +231,8 @@ static int hpsi_groups(jrb_plan* p, const cplx* q, const double* veff_spin, cplx
     // non-local pseudopotential: hq += Phi^H (Phi q) / vol on the (spin,k) items of [ga, gb)
     const int sk_lo = s * p->nk + ga / p->ngroups_per_k;
     const int sk_hi = s * p->nk + (gb + p->ngroups_per_k - 1) / p->ngroups_per_k;
-    if ((rc = launch_nonlocal_project(p, sk_lo, sk_hi - sk_lo, q, st))) return rc;
+    if (!(p->nl_p_valid && q == p->d_q))
+      if ((rc = launch_nonlocal_project(p, sk_lo, sk_hi - sk_lo, q, st))) return rc;
     if ((rc = launch_nonlocal_apply(p, sk_lo, sk_hi - sk_lo, hq, st))) return rc;
   }
   return 0;

@@ -24,27 +24,33 @@ constexpr int NL_TG = 32;   // sphere rows per smem slice
 constexpr int NL_CHUNKS = 16;
 
 // partial[chunk][sk][p][b] = sum_{g in chunk} Phi[k][p][g] Q[sk][g][b]
-// grid: (ceil(nproj/16) * ceil(nb/32), nsk, NL_CHUNKS), block (32, 16): thread (b, p)
-__global__ void __launch_bounds__(512)
+// CTA tile 32 projectors x 32 bands, thread (tx, ty) of (16, 16) owns the 2 x 2 outputs
+// (ty, ty + 16) x (tx, tx + 16): 4 shared-memory loads per 4 complex FMAs.
+// grid: (ceil(nproj/32) * ceil(nb/32), nsk, NL_CHUNKS), block (16, 16)
+__global__ void __launch_bounds__(256)
 k_nl_project(const cplx* __restrict__ phi, const cplx* __restrict__ q, long long ng, int nb,
              int nproj, int nk, int sk0, cplx* __restrict__ partial) {
-  __shared__ cplx sphi[NL_TP][NL_TG + 1];
+  __shared__ cplx sphi[2 * NL_TP][NL_TG + 1];
   __shared__ cplx sq[NL_TG][NL_TB + 1];
   const int nbt = (nb + NL_TB - 1) / NL_TB;
-  const int p0 = (blockIdx.x / nbt) * NL_TP, b0 = (blockIdx.x % nbt) * NL_TB;
+  const int p0 = (blockIdx.x / nbt) * 2 * NL_TP, b0 = (blockIdx.x % nbt) * NL_TB;
   const int sk = blockIdx.y, k = (sk0 + sk) % nk;  // q / partial are indexed from sk0
   const long long rows = (ng + gridDim.z - 1) / gridDim.z;
   const long long g_lo = blockIdx.z * rows, g_hi = min(ng, g_lo + rows);
-  const int tb = threadIdx.x, tp = threadIdx.y;
-  const int tid = tp * 32 + tb;
-  cplx acc = cmake(0.0, 0.0);
+  const int tx = threadIdx.x, ty = threadIdx.y;
+  const int tid = ty * 16 + tx;
+  cplx acc[2][2];
+#pragma unroll
+  for (int i = 0; i < 2; ++i)
+#pragma unroll
+    for (int j = 0; j < 2; ++j) acc[i][j] = cmake(0.0, 0.0);
   for (long long g0 = g_lo; g0 < g_hi; g0 += NL_TG) {
-    {  // Phi tile: 16 x 32 elements, g fastest in memory
-      const int pp = tid / NL_TG, gg = tid % NL_TG;
+    for (int e = tid; e < 2 * NL_TP * NL_TG; e += 256) {  // Phi tile: 32 x 32, g fastest in memory
+      const int pp = e / NL_TG, gg = e % NL_TG;
       const bool ok = p0 + pp < nproj && g0 + gg < g_hi;
       sphi[pp][gg] = ok ? phi[((long long)k * nproj + p0 + pp) * ng + g0 + gg] : cmake(0.0, 0.0);
     }
-    for (int e = tid; e < NL_TG * NL_TB; e += 512) {  // Q tile: 32 x 32, b fastest
+    for (int e = tid; e < NL_TG * NL_TB; e += 256) {  // Q tile: 32 x 32, b fastest
       const int gg = e / NL_TB, bb = e % NL_TB;
       const bool ok = g0 + gg < g_hi && b0 + bb < nb;
       sq[gg][bb] = ok ? q[((long long)sk * ng + g0 + gg) * nb + b0 + bb] : cmake(0.0, 0.0);
@@ -52,13 +58,24 @@ k_nl_project(const cplx* __restrict__ phi, const cplx* __restrict__ q, long long
     __syncthreads();
 #pragma unroll 8
     for (int gg = 0; gg < NL_TG; ++gg) {
-      const cplx v = cmul(sphi[tp][gg], sq[gg][tb]);
-      acc.x += v.x; acc.y += v.y;
+      const cplx f0 = sphi[ty][gg], f1 = sphi[ty + 16][gg];
+      const cplx q0 = sq[gg][tx], q1 = sq[gg][tx + 16];
+      cplx v;
+      v = cmul(f0, q0); acc[0][0].x += v.x; acc[0][0].y += v.y;
+      v = cmul(f0, q1); acc[0][1].x += v.x; acc[0][1].y += v.y;
+      v = cmul(f1, q0); acc[1][0].x += v.x; acc[1][0].y += v.y;
+      v = cmul(f1, q1); acc[1][1].x += v.x; acc[1][1].y += v.y;
     }
     __syncthreads();
   }
-  if (p0 + tp < nproj && b0 + tb < nb)
-    partial[(((long long)blockIdx.z * gridDim.y + sk) * nproj + p0 + tp) * nb + b0 + tb] = acc;
+#pragma unroll
+  for (int i = 0; i < 2; ++i)
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const int pp = p0 + ty + 16 * i, bb = b0 + tx + 16 * j;
+      if (pp < nproj && bb < nb)
+        partial[(((long long)blockIdx.z * gridDim.y + sk) * nproj + pp) * nb + bb] = acc[i][j];
+    }
 }
 
 // P = sum of the chunk partials (fixed order).  grid: (ceil(nsk*nproj*nb / 256))
@@ -74,14 +91,15 @@ __global__ void k_nl_reduce(const cplx* __restrict__ partial, int nchunks, long 
   P[i] = s;
 }
 
-// e_out[0] += sum_{sk,p,b} occ[sk][b] |P|^2 / vol   (one CTA, fixed order)
+// part[blk] = sum over a slice of (sk, p, b) of occ[sk][b] |P|^2; then one CTA adds the slices in
+// order: e_out[0] += sum / vol (deterministic)
 __global__ void __launch_bounds__(256)
 k_nl_energy(const cplx* __restrict__ P, const double* __restrict__ occ, int nsk, int nproj, int nb,
-            double inv_vol, double* __restrict__ e_out) {
+            double* __restrict__ part) {
   __shared__ double sh[256];
   double acc = 0.0;
   const long long n = (long long)nsk * nproj * nb;
-  for (long long i = threadIdx.x; i < n; i += 256) {
+  for (long long i = blockIdx.x * 256LL + threadIdx.x; i < n; i += (long long)gridDim.x * 256) {
     const int b = (int)(i % nb);
     const int sk = (int)(i / ((long long)nproj * nb));
     const cplx v = P[i];
@@ -93,7 +111,13 @@ k_nl_energy(const cplx* __restrict__ P, const double* __restrict__ occ, int nsk,
     if (threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
     __syncthreads();
   }
-  if (threadIdx.x == 0) e_out[0] += sh[0] * inv_vol;
+  if (threadIdx.x == 0) part[blockIdx.x] = sh[0];
+}
+__global__ void k_nl_energy_final(const double* __restrict__ part, int n, double inv_vol,
+                                  double* __restrict__ e_out) {
+  double s = 0.0;
+  for (int i = 0; i < n; ++i) s += part[i];
+  e_out[0] += s * inv_vol;
 }
 
 // hq[sk][g][b] += sum_p conj(Phi[k][p][g]) P[sk][p][b] / vol
@@ -150,8 +174,8 @@ k_nl_apply(const cplx* __restrict__ phi, const cplx* __restrict__ P, long long n
 
 // P of the (spin,k) range [sk0, sk0 + nsk) into p->d_nl_p (indexed from sk0)
 int launch_nonlocal_project(jrb_plan* p, int sk0, int nsk, const cplx* q, cudaStream_t st) {
-  const int nbt = (p->nb + NL_TB - 1) / NL_TB, npt = (p->nproj + NL_TP - 1) / NL_TP;
-  dim3 grid(npt * nbt, nsk, NL_CHUNKS), block(32, 16);
+  const int nbt = (p->nb + NL_TB - 1) / NL_TB, npt = (p->nproj + 2 * NL_TP - 1) / (2 * NL_TP);
+  dim3 grid(npt * nbt, nsk, NL_CHUNKS), block(16, 16);
   k_nl_project<<<grid, block, 0, st>>>(p->d_nl_phi, q + (long long)sk0 * p->ng * p->nb, p->ng, p->nb,
                                       p->nproj, p->nk, sk0, p->d_nl_part);
   JRB_CHECK_LAUNCH("k_nl_project");
@@ -163,9 +187,13 @@ int launch_nonlocal_project(jrb_plan* p, int sk0, int nsk, const cplx* q, cudaSt
 }
 
 int launch_nonlocal_energy(jrb_plan* p, const double* occ, double* e_inout, cudaStream_t st) {
-  k_nl_energy<<<1, 256, 0, st>>>(p->d_nl_p, occ, p->ns * p->nk, p->nproj, p->nb, 1.0 / p->vol,
-                                 e_inout);
+  // partial sums live at the head of the (by now consumed) chunk buffer of the projection
+  double* part = reinterpret_cast<double*>(p->d_nl_part);
+  const int blocks = 148;
+  k_nl_energy<<<blocks, 256, 0, st>>>(p->d_nl_p, occ, p->ns * p->nk, p->nproj, p->nb, part);
   JRB_CHECK_LAUNCH("k_nl_energy");
+  k_nl_energy_final<<<1, 1, 0, st>>>(part, blocks, 1.0 / p->vol, e_inout);
+  JRB_CHECK_LAUNCH("k_nl_energy_final");
   return 0;
 }
 

@@ -90,6 +90,7 @@ struct jrb_plan {
   jrb::cplx* d_nl_phi;   // [nk][nproj][ng]
   jrb::cplx* d_nl_p;     // [ns*nk][nproj][nb]  P = Phi Q
   jrb::cplx* d_nl_part;  // [16 chunks][ns*nk][nproj][nb]
+  int nl_p_valid;        // d_nl_p holds Phi Q of the plan's own Q (jrb_eval_begin -> jrb_eval_finish)
   // evaluation work space (Q, R, R^-1, HQ, W-sized temp)
   jrb::cplx *d_q, *d_hq, *d_tmp;
   jrb::cplx *d_r, *d_rinv, *d_small;  // [ns*nk][nb][nb] each (d_small: 5 of them)
