@@ -344,6 +344,12 @@ def run_b200_rows(args, wl, world, rank, local_rank):
   dist.destroy_process_group()
 
 
+def parse_orbital_grid(text):
+  if text in ('auto', 'full'):
+    return text
+  return tuple(int(v) for v in text.split(','))
+
+
 def run_b200(args):
   import torch
   import torch.distributed as dist
@@ -373,7 +379,8 @@ def run_b200(args):
     # tuning aid, NOT a bench line: the per-rank workload of an N-GPU k-sharded run on one GPU
     k0, k1 = parallel.shard_kpoints(nk, args.emulate_ranks, 0)
     sharding = f'EMULATED rank 0 of k{args.emulate_ranks} (no collectives; not a benchmark value)'
-  plan = jb.Plan(c.cell_vectors, wl['mask'], wl['kpts'][k0:k1], nb, device=local_rank)
+  plan = jb.Plan(c.cell_vectors, wl['mask'], wl['kpts'][k0:k1], nb, device=local_rank,
+                 orbital_grid=parse_orbital_grid(args.orbital_grid))
   plan.set_atoms(c.positions, c.charges)
   if wl['nproj']:
     plan.set_nonlocal(synthetic_projectors(ng, nk, wl['nproj'], k0, k1, 'cuda'))
@@ -573,6 +580,10 @@ def run_b200(args):
       'scaling': 'strong', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
       'config': {'workload': wl['text'], 'orbitals': nk * nb, 'ng': ng, 'grid': wl['grid'],
                  'sharding': sharding, 'xc': 'lda_x',
+                 'orbital_grid': list(plan.orbital_grid),
+                 'orbital_grid_note': 'box of the per-orbital FFTs (alias-free, n >= 4 gmax + 1 = '
+                                      f'{list(plan.min_orbital_grid)}); rho, potentials and all '
+                                      'results live on `grid`',
                  'l2': f'inputs larger than L2 ({2 * nw * 8 / 2**20:.0f} MiB of parameters per '
                        'GPU); no flush' if 2 * nw * 8 > 126 * 2**20 else
                        'working set fits L2: L2 flushed between timed steps (256 MiB rewrite), '
@@ -605,6 +616,8 @@ def main():
   ap.add_argument('--config', default='C2', choices=list(WORKLOADS))
   ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
   ap.add_argument('--no-cpu', action='store_true', help='skip the cpu_baseline leg')
+  ap.add_argument('--orbital-grid', default=os.environ.get('JRB_ORBITAL_GRID', 'full'),
+                  help="box of the per-orbital FFTs: 'full' (the reference's), 'auto' or nx,ny,nz")
   ap.add_argument('--emulate-ranks', type=int, default=1,
                   help='tuning aid: run only the k-points rank 0 of an N-GPU run would own')
   args = ap.parse_args()

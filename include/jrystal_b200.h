@@ -69,6 +69,22 @@ int64_t jrb_plan_num_g(const jrb_plan* plan);
 /* bytes of device work space owned by the plan */
 int64_t jrb_plan_workspace_bytes(const jrb_plan* plan);
 
+/* Orbital grid.  The reference transforms every orbital on the same (nx, ny, nz) box it uses for
+ * the density and the potentials (pw.wave_grid, jrystal/_src/pw.py:208-211; utils.expand_coefficient,
+ * utils.py:277-281).  psi only carries the frequencies of the cut-off sphere, |f_c| <= gmax_c, so
+ * |psi|^2 and the sphere part of v_eff*psi involve |f_c| <= 2 gmax_c and any box with
+ * n_c >= 4 gmax_c + 1 transforms them without aliasing: after this call the per-orbital passes
+ * (jrb_density, jrb_hpsi, jrb_eval_begin/finish, jrb_energy_grad_host) run on (nxw, nyw, nzw);
+ * rho is brought to the plan's grid by Fourier interpolation and v_eff to the orbital grid by
+ * Fourier truncation, so every result is the reference's to rounding (tests/test_gpu_parity.py::
+ * test_orbital_grid*).  Everything else (grids in the arguments, XC, Hartree, jrb_fft3d,
+ * jrb_wave_grid) keeps the plan's own grid.  Fails with JRB_EINVAL if an axis violates
+ * 4 gmax + 1 <= n_w <= n, JRB_EUNSUPPORTED without a compiled line length.  Allocates (set-up). */
+int jrb_plan_set_orbital_grid(jrb_plan* plan, int32_t nxw, int32_t nyw, int32_t nzw);
+/* dims[3] = the box the per-orbital passes currently run on / the smallest alias-free box */
+int jrb_plan_orbital_grid(const jrb_plan* plan, int32_t* dims);
+int jrb_plan_min_orbital_grid(const jrb_plan* plan, int32_t* dims);
+
 /* Pre-computes V_ext(G) once: potential.external_reciprocal (jrystal/_src/potential.py:
  * 153-166), which the reference re-evaluates every step although it is parameter free. */
 int jrb_set_atoms(jrb_plan* plan, const double* positions_host, const double* charges_host,

@@ -10,6 +10,10 @@ LIB_PATH = os.path.join(_HERE, 'csrc', 'libjrystal_b200.so')
 
 XC_IDS = {'lda_x': 1, 'lda_x+lda_c_pw': 2}
 FFT_FORWARD, FFT_INVERSE = -1, 1
+# axis lengths with compiled pencil passes; FUSED: also the fused y+x plane kernels (nx == ny)
+LINE_LENGTHS = (7, 8, 9, 12, 16, 24, 32, 40, 45, 48, 49, 50, 54, 56, 60, 64, 72, 80, 81, 90, 96,
+                100, 112, 128)
+FUSED_LENGTHS = (7, 8, 9, 12, 16, 24, 32, 48, 49, 64, 72, 81, 96, 128)
 
 
 class PlanDesc(ctypes.Structure):
@@ -28,6 +32,9 @@ SYMBOLS = {
   'jrb_plan_destroy': (ctypes.c_int, [_P]),
   'jrb_plan_num_g': (_I64, [_P]),
   'jrb_plan_workspace_bytes': (_I64, [_P]),
+  'jrb_plan_set_orbital_grid': (ctypes.c_int, [_P, _I32, _I32, _I32]),
+  'jrb_plan_orbital_grid': (ctypes.c_int, [_P, _P]),
+  'jrb_plan_min_orbital_grid': (ctypes.c_int, [_P, _P]),
   'jrb_set_atoms': (ctypes.c_int, [_P, _P, _P, _I32, _P]),
   'jrb_set_external_potential': (ctypes.c_int, [_P, _P, _P]),
   'jrb_external_position_gradient': (ctypes.c_int, [_P, _P, _P, _P]),

@@ -396,7 +396,7 @@ extern "C" int jrb_energy_grad_host(jrb_plan* p, const double* w_re_h, const dou
     }
     if ((rc = launch_focc(p, p->d_occ, st))) return rc;
     JRB_CUDA(cudaMemsetAsync(p->d_scal + 32, 0, sizeof(double), st));  // Cholesky failure flag
-    JRB_CUDA(cudaMemsetAsync(rho, 0, sizeof(double) * (size_t)p->ngrid, st));
+    if ((rc = launch_density_begin(p, rho, st))) return rc;
     for (int c = 0; c < nch; ++c) {
       const int k0 = k_of(c), k1 = k_of(c + 1);
       JRB_CUDA(cudaStreamWaitEvent(st, p->ev_in[c], 0));
@@ -407,10 +407,12 @@ extern "C" int jrb_energy_grad_host(jrb_plan* p, const double* w_re_h, const dou
       if (rc) return rc;
       if ((rc = launch_kinetic_range(p, k0, k1 - k0, p->d_q, p->d_tkb, st))) return rc;
     }
+    if ((rc = launch_density_end(p, rho, st))) return rc;
     if ((rc = launch_weighted_sum(p, p->d_tkb, p->d_occ, (int64_t)p->nk * p->nb, e_kin, st))) return rc;
     // backward: D2H of chunk c (copy stream) under H-apply + QR adjoint of chunk c+1
     double* grid_e = p->d_scal;
     if ((rc = launch_grid_potential(p, rho, xc_id, 0, 7, grid_e, p->d_veff, st))) return rc;
+    if ((rc = launch_hpsi_prepare(p, p->d_veff, st))) return rc;
     for (int c = 0; c < nch; ++c) {
       const int k0 = k_of(c), k1 = k_of(c + 1);
       const size_t off = (size_t)k0 * per_k, n = (size_t)(k1 - k0) * per_k;

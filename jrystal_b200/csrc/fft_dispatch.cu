@@ -15,6 +15,8 @@ static int run_pass(PassKind kind, int n, const PassArgs& a, cudaStream_t st) {
   if (rc == 1) rc = pass_group1(kind, n, a, st);
   if (rc == 1) rc = pass_group2(kind, n, a, st);
   if (rc == 1) rc = pass_group3(kind, n, a, st);
+  if (rc == 1) rc = pass_group4(kind, n, a, st);
+  if (rc == 1) rc = pass_group5(kind, n, a, st);
   if (rc == 1) {
     set_error("no compiled pencil pass for axis length " + std::to_string(n));
     return JRB_EUNSUPPORTED;
@@ -27,6 +29,8 @@ static int run_dense(int n, const DenseArgs& a, int dir, long long batch, cudaSt
   if (rc == 1) rc = dense_group1(n, a, dir, batch, st);
   if (rc == 1) rc = dense_group2(n, a, dir, batch, st);
   if (rc == 1) rc = dense_group3(n, a, dir, batch, st);
+  if (rc == 1) rc = dense_group4(n, a, dir, batch, st);
+  if (rc == 1) rc = dense_group5(n, a, dir, batch, st);
   if (rc == 1) {
     set_error("no compiled dense line FFT for axis length " + std::to_string(n));
     return JRB_EUNSUPPORTED;
@@ -142,6 +146,12 @@ static PassArgs base_args(jrb_plan* p) {
 static int density_groups(jrb_plan* p, const cplx* q, double* rho_spin, int s, int ga, int gb,
                           cudaStream_t st) {
   int rc = 0;
+  if (p->wf) {  // the orbital grid's plan runs the passes, into its own density
+    p->wf->keep_write = p->keep_write;
+    rc = density_groups(p->wf, q, p->wf->d_rho_w + (size_t)s * p->wf->ngrid, s, ga, gb, st);
+    p->wf->keep_write = 0;
+    return rc;
+  }
   const int per_spin = p->nk * p->ngroups_per_k;
   for (int g0 = ga; g0 < gb; g0 += p->batch_groups) {
     PassArgs a = base_args(p);
@@ -175,15 +185,63 @@ static int density_groups(jrb_plan* p, const cplx* q, double* rho_spin, int s, i
   return 0;
 }
 
+int launch_density_begin(jrb_plan* p, double* rho, cudaStream_t st) {
+  if (p->wf) {
+    JRB_CUDA(cudaMemsetAsync(p->wf->d_rho_w, 0, sizeof(double) * (size_t)p->ns * p->wf->ngrid, st));
+  } else {
+    JRB_CUDA(cudaMemsetAsync(rho, 0, sizeof(double) * (size_t)p->ns * p->ngrid, st));
+  }
+  return 0;
+}
+
+// Orbital grid -> the plan's grid: rho is band limited to 2 gmax, which both boxes hold, so the
+// Fourier interpolation reproduces the reference's rho(r_j) on the plan's grid exactly.
+int launch_density_end(jrb_plan* p, double* rho, cudaStream_t st) {
+  jrb_plan* w = p->wf;
+  if (!w) return 0;
+  int rc = 0;
+  for (int s = 0; s < p->ns; ++s) {
+    if ((rc = launch_real_to_complex(w->d_rho_w + (size_t)s * w->ngrid, w->ngrid, w->d_grid, st)))
+      return rc;
+    if ((rc = launch_fft3d_dense(w, w->d_grid, w->d_grid, JRB_FFT_FORWARD, 1, 1.0, st))) return rc;
+    if ((rc = launch_resample(w->d_grid, w->nx, w->ny, w->nz, p->d_grid, p->nx, p->ny, p->nz,
+                              1.0 / (double)w->ngrid, st)))
+      return rc;
+    if ((rc = launch_fft3d_dense(p, p->d_grid, p->d_grid, JRB_FFT_INVERSE, 1, 1.0, st))) return rc;
+    if ((rc = launch_complex_to_real(p->d_grid, p->ngrid, rho + (size_t)s * p->ngrid, st))) return rc;
+  }
+  return 0;
+}
+
+// v_eff on the plan's grid -> the orbital grid: only the Fourier components |f| <= 2 gmax of the
+// potential reach the sphere part of v_eff psi, so truncating to the orbital box changes nothing
+// the Hamiltonian apply returns.
+int launch_hpsi_prepare(jrb_plan* p, const double* veff, cudaStream_t st) {
+  jrb_plan* w = p->wf;
+  if (!w) return 0;
+  int rc = 0;
+  for (int s = 0; s < p->ns; ++s) {
+    if ((rc = launch_real_to_complex(veff + (size_t)s * p->ngrid, p->ngrid, p->d_grid, st))) return rc;
+    if ((rc = launch_fft3d_dense(p, p->d_grid, p->d_grid, JRB_FFT_FORWARD, 1, 1.0, st))) return rc;
+    if ((rc = launch_resample(p->d_grid, p->nx, p->ny, p->nz, w->d_grid, w->nx, w->ny, w->nz,
+                              1.0 / (double)p->ngrid, st)))
+      return rc;
+    if ((rc = launch_fft3d_dense(w, w->d_grid, w->d_grid, JRB_FFT_INVERSE, 1, 1.0, st))) return rc;
+    if ((rc = launch_complex_to_real(w->d_grid, w->ngrid, w->d_veff + (size_t)s * w->ngrid, st)))
+      return rc;
+  }
+  return 0;
+}
+
 // rho[s] = sum_{k,b} occ |psi|^2  (jrb_density).
 int launch_density(jrb_plan* p, const cplx* q, const double* occ, double* rho, cudaStream_t st) {
   int rc = launch_focc(p, occ, st);
   if (rc) return rc;
-  JRB_CUDA(cudaMemsetAsync(rho, 0, sizeof(double) * (size_t)p->ns * p->ngrid, st));
+  if ((rc = launch_density_begin(p, rho, st))) return rc;
   const int per_spin = p->nk * p->ngroups_per_k;
   for (int s = 0; s < p->ns; ++s)
     if ((rc = density_groups(p, q, rho + (size_t)s * p->ngrid, s, 0, per_spin, st))) return rc;
-  return 0;
+  return launch_density_end(p, rho, st);
 }
 
 // the k-points [k0, k1) of spin 0 only, accumulated into rho (no memset, no focc refresh)
@@ -191,11 +249,19 @@ int launch_density_krange(jrb_plan* p, const cplx* q, double* rho, int k0, int k
   return density_groups(p, q, rho, 0, k0 * p->ngroups_per_k, k1 * p->ngroups_per_k, st);
 }
 
+// veff_spin: on the grid of the plan that runs the passes (launch_hpsi_prepare for a child)
 static int hpsi_groups(jrb_plan* p, const cplx* q, const double* veff_spin, cplx* hq, int s, int ga,
                        int gb, cudaStream_t st) {
   int rc = 0;
+  if (p->wf) {
+    jrb_plan* w = p->wf;
+    w->keep_read = p->keep_read;
+    rc = hpsi_groups(w, q, w->d_veff + (size_t)s * w->ngrid, hq, s, ga, gb, st);
+    w->keep_read = 0;
+    if (rc) return rc;
+  }
   const int per_spin = p->nk * p->ngroups_per_k;
-  for (int g0 = ga; g0 < gb; g0 += p->batch_groups) {
+  for (int g0 = ga; g0 < gb && !p->wf; g0 += p->batch_groups) {
     PassArgs a = base_args(p);
     a.q = q;
     a.hq = hq;
@@ -240,7 +306,8 @@ static int hpsi_groups(jrb_plan* p, const cplx* q, const double* veff_spin, cplx
 
 // hq = 1/2|G+k|^2 q + (sqrt(Omega)/N) fftn(veff psi)|mask   (jrb_hpsi)
 int launch_hpsi(jrb_plan* p, const cplx* q, const double* veff, cplx* hq, cudaStream_t st) {
-  int rc = 0;
+  int rc = launch_hpsi_prepare(p, veff, st);
+  if (rc) return rc;
   const int per_spin = p->nk * p->ngroups_per_k;
   for (int s = 0; s < p->ns; ++s)
     if ((rc = hpsi_groups(p, q, veff + (size_t)s * p->ngrid, hq, s, 0, per_spin, st))) return rc;

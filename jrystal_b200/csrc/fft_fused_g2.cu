@@ -1,7 +1,7 @@
 // Instantiations of the fused y+x kernels (fft_fused.cuh) for one group of axis lengths.
 #include "fft_fused.cuh"
 
-#define JRB_SIZES(X) X(72) X(96)
+#define JRB_SIZES(X) X(72) X(81) X(96)
 
 namespace jrb {
 

@@ -57,6 +57,7 @@ JRB_LINE_PLAN(36, 6, 6, 6)
 JRB_LINE_PLAN(40, 4, 10, 2)
 JRB_LINE_PLAN(45, 3, 15, 3)
 JRB_LINE_PLAN(48, 4, 12, 4)
+JRB_LINE_PLAN(49, 7, 7, 7)
 JRB_LINE_PLAN(50, 5, 10, 5)
 JRB_LINE_PLAN(54, 6, 9, 3)
 JRB_LINE_PLAN(56, 4, 14, 2)

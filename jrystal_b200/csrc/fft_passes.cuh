@@ -94,7 +94,9 @@ __device__ __forceinline__ cplx czero() { return cmake(0.0, 0.0); }
 // The z passes are latency bound gathers/scatters: 4 resident CTAs (64 registers) instead of 3
 // where that costs no real spilling (checked with -Xptxas -v).
 constexpr bool vmul_two_buffers(int n) { return n <= 96; }
-constexpr int z_min_blocks(int n) { return n == 64 ? 4 : (n > 96 ? 2 : 1); }
+constexpr int z_min_blocks(int n) {
+  return (n == 64 || n == 49) ? 4 : (n == 81 || n == 100) ? 3 : (n > 96 ? 2 : 1);
+}
 // Long lines (16 elements per thread): cap the registers at 128 so that two CTAs are resident
 // (one CTA of 8 warps per SM left every 128-point pass latency bound at 12 % occupancy).
 constexpr int long_min_blocks(int n) { return n > 96 ? 2 : 1; }
@@ -607,9 +609,13 @@ int pass_group0(PassKind kind, int n, const PassArgs& a, cudaStream_t st);
 int pass_group1(PassKind kind, int n, const PassArgs& a, cudaStream_t st);
 int pass_group2(PassKind kind, int n, const PassArgs& a, cudaStream_t st);
 int pass_group3(PassKind kind, int n, const PassArgs& a, cudaStream_t st);
+int pass_group4(PassKind kind, int n, const PassArgs& a, cudaStream_t st);
+int pass_group5(PassKind kind, int n, const PassArgs& a, cudaStream_t st);
 int dense_group0(int n, const DenseArgs& a, int dir, long long batch, cudaStream_t st);
 int dense_group1(int n, const DenseArgs& a, int dir, long long batch, cudaStream_t st);
 int dense_group2(int n, const DenseArgs& a, int dir, long long batch, cudaStream_t st);
 int dense_group3(int n, const DenseArgs& a, int dir, long long batch, cudaStream_t st);
+int dense_group4(int n, const DenseArgs& a, int dir, long long batch, cudaStream_t st);
+int dense_group5(int n, const DenseArgs& a, int dir, long long batch, cudaStream_t st);
 
 }  // namespace jrb

@@ -357,6 +357,57 @@ __global__ void k_real_to_complex(const double* __restrict__ in, long long n, cp
     out[i] = cmake(in[i], 0.0);
 }
 
+int launch_real_to_complex(const double* in, long long n, cplx* out, cudaStream_t st) {
+  const int blocks = (int)std::min<long long>((n + 255) / 256, 148 * 8);
+  k_real_to_complex<<<blocks, 256, 0, st>>>(in, n, out);
+  JRB_CHECK_LAUNCH("k_real_to_complex");
+  return 0;
+}
+
+__global__ void k_complex_to_real(const cplx* __restrict__ in, long long n, double* __restrict__ out) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
+       i += (long long)gridDim.x * blockDim.x)
+    out[i] = in[i].x;
+}
+
+int launch_complex_to_real(const cplx* in, long long n, double* out, cudaStream_t st) {
+  const int blocks = (int)std::min<long long>((n + 255) / 256, 148 * 8);
+  k_complex_to_real<<<blocks, 256, 0, st>>>(in, n, out);
+  JRB_CHECK_LAUNCH("k_complex_to_real");
+  return 0;
+}
+
+// Fourier resampling between two FFT boxes: dst(f) = scale * src(f) for the frequencies both boxes
+// represent symmetrically (2|f_c| < min(n_src, n_dst) on every axis: an even box's unpaired Nyquist
+// bin is dropped so real fields stay real), zero elsewhere.  One thread per dst element.
+__global__ void k_resample(const cplx* __restrict__ src, int sx, int sy, int sz,
+                           cplx* __restrict__ dst, int dx, int dy, int dz, double scale) {
+  const long long n = (long long)dx * dy * dz;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int z = (int)(i % dz), y = (int)((i / dz) % dy), x = (int)(i / ((long long)dz * dy));
+    const int fx = fftfreq_int(x, dx), fy = fftfreq_int(y, dy), fz = fftfreq_int(z, dz);
+    const int mx = min(sx, dx), my = min(sy, dy), mz = min(sz, dz);
+    cplx v = cmake(0.0, 0.0);
+    if (2 * abs(fx) < mx && 2 * abs(fy) < my && 2 * abs(fz) < mz) {
+      const int px = fx >= 0 ? fx : fx + sx, py = fy >= 0 ? fy : fy + sy,
+                pz = fz >= 0 ? fz : fz + sz;
+      const cplx t = src[((long long)px * sy + py) * sz + pz];
+      v = cmake(t.x * scale, t.y * scale);
+    }
+    dst[i] = v;
+  }
+}
+
+int launch_resample(const cplx* src, int sx, int sy, int sz, cplx* dst, int dx, int dy, int dz,
+                    double scale, cudaStream_t st) {
+  const long long n = (long long)dx * dy * dz;
+  const int blocks = (int)std::min<long long>((n + 255) / 256, 148 * 8);
+  k_resample<<<blocks, 256, 0, st>>>(src, sx, sy, sz, dst, dx, dy, dz, scale);
+  JRB_CHECK_LAUNCH("k_resample");
+  return 0;
+}
+
 int launch_density_reciprocal(jrb_plan* p, const double* rho, cplx* rho_hat, cudaStream_t st) {
   const long long n = (long long)p->ns * p->ngrid;
   const int blocks = (int)std::min<long long>((n + 255) / 256, 148 * 8);
@@ -493,6 +544,8 @@ int launch_set_kpoints(jrb_plan* p, const double* kpts_h, cudaStream_t st) {
       p->d_gk2 + (long long)k * p->ng);
     JRB_CHECK_LAUNCH("k_gk2");
   }
+  if (p->h_kpts) std::copy(kpts_h, kpts_h + 3 * (size_t)p->nk, p->h_kpts);
+  if (p->wf) return launch_set_kpoints(p->wf, kpts_h, st);  // its z pass adds 1/2|G+k|^2 q
   return 0;
 }
 
@@ -511,6 +564,7 @@ int launch_focc(jrb_plan* p, const double* occ, cudaStream_t st) {
   k_focc<<<(total * NB + 255) / 256, 256, 0, st>>>(occ, p->nb, p->ngroups_per_k, total,
                                                   1.0 / p->vol, p->d_focc);
   JRB_CHECK_LAUNCH("k_focc");
+  if (p->wf) return launch_focc(p->wf, occ, st);  // the plan that runs the density sweep
   return 0;
 }
 

@@ -2,6 +2,7 @@
 // Host-side restatement of what the reference's drivers prepare before the loop
 // (jrystal/calc/calc_ground_state_energy_all_electrons.py:93-106 via grid.g_vectors,
 // jrystal/_src/grid.py:93-149, and the C-order mask enumeration of utils.py:279-281).
+#include <algorithm>
 #include <atomic>
 #include <cmath>
 #include <cstdio>
@@ -35,6 +36,9 @@ bool line_length_supported(int n) {
   switch (n) {
     case 7: case 8: case 9: case 12: case 16: case 24: case 32: case 48: case 64: case 72:
     case 96: case 128:
+    // pencil passes and dense lines only (no fused y+x kernels): lengths an orbital grid can take
+    case 40: case 45: case 49: case 50: case 54: case 56: case 60: case 80: case 81: case 90:
+    case 100: case 112:
       return true;
     default:
       return false;
@@ -110,6 +114,11 @@ extern "C" int64_t jrb_plan_workspace_bytes(const jrb_plan* p) { return p ? p->w
 extern "C" int jrb_plan_destroy(jrb_plan* p) {
   if (!p) return 0;
   cudaSetDevice(p->device);
+  if (p->wf) jrb_plan_destroy(p->wf);
+  p->wf = nullptr;
+  if (p->d_rho_w) cudaFree(p->d_rho_w);
+  delete[] p->h_freq;
+  delete[] p->h_kpts;
   void* ptrs[] = {p->d_zmap, p->d_ycol, p->d_xmap, p->d_gidx, p->d_gk2, p->d_tw_x, p->d_tw_y,
                   p->d_tw_z, p->d_tw_half, p->d_a_keep, p->d_pos, p->d_chg, p->d_atom_part, p->d_nl_phi, p->d_nl_p, p->d_nl_part, p->d_ws_a, p->d_ws_b, p->d_rho_part, p->d_seg_z, p->d_focc, p->d_grid, p->d_vext,
                   p->d_partials, p->d_veff, p->d_q, p->d_hq, p->d_tmp, p->d_r, p->d_rinv, p->d_small, p->d_gpart,
@@ -175,7 +184,13 @@ extern "C" int jrb_plan_create_rows(int64_t nrows, int32_t ns, int32_t nk, int32
   return 0;
 }
 
+static int plan_create_impl(const jrb_plan_desc* d, bool orbital_only, jrb_plan** out);
+
 extern "C" int jrb_plan_create(const jrb_plan_desc* d, jrb_plan** out) {
+  return plan_create_impl(d, false, out);
+}
+
+static int plan_create_impl(const jrb_plan_desc* d, bool orbital_only, jrb_plan** out) {
   if (!d || !out || !d->mask || !d->kpts || !d->cell) {
     set_error("jrb_plan_create: null argument");
     return JRB_EINVAL;
@@ -189,7 +204,8 @@ extern "C" int jrb_plan_create(const jrb_plan_desc* d, jrb_plan** out) {
   for (int i = 0; i < 3; ++i) {
     if (!line_length_supported(dims[i])) {
       set_error("jrb_plan_create: FFT length " + std::to_string(dims[i]) +
-                " has no compiled line plan (supported: 7 8 9 12 16 24 32 48 64 72 96 128)");
+                " has no compiled line plan (supported: 7 8 9 12 16 24 32 40 45 48 49 50 54 56 60 "
+                "64 72 80 81 90 96 100 112 128)");
       return JRB_EUNSUPPORTED;
     }
   }
@@ -206,6 +222,7 @@ extern "C" int jrb_plan_create(const jrb_plan_desc* d, jrb_plan** out) {
   p->nx = d->nx; p->ny = d->ny; p->nz = d->nz;
   p->ns = d->ns; p->nk = d->nk; p->nb = d->nb;
   p->device = d->device;
+  p->orbital_only = orbital_only ? 1 : 0;
   p->ngrid = (int64_t)d->nx * d->ny * d->nz;
   p->ngroups_per_k = (d->nb + NB - 1) / NB;
   std::memcpy(p->cell, d->cell, sizeof(double) * 9);
@@ -269,6 +286,18 @@ extern "C" int jrb_plan_create(const jrb_plan_desc* d, jrb_plan** out) {
     return JRB_EINVAL;
   }
   p->ng = ng;
+  p->h_freq = new int32_t[(size_t)ng * 3];
+  p->h_kpts = new double[(size_t)p->nk * 3];
+  std::memcpy(p->h_kpts, d->kpts, sizeof(double) * 3 * (size_t)p->nk);
+  for (int64_t g = 0; g < ng; ++g) {
+    const int lin = gidx[g];
+    const int f[3] = {fftfreq_int(lin / (nz * ny), nx), fftfreq_int((lin / nz) % ny, ny),
+                      fftfreq_int(lin % nz, nz)};
+    for (int c = 0; c < 3; ++c) {
+      p->h_freq[g * 3 + c] = f[c];
+      p->gmax[c] = std::max(p->gmax[c], std::abs(f[c]));
+    }
+  }
   // --- |G+k|^2 on the sphere --------------------------------------------------------
   std::vector<double> gk2((size_t)p->nk * ng);
   {
@@ -368,15 +397,18 @@ extern "C" int jrb_plan_create(const jrb_plan_desc* d, jrb_plan** out) {
   p->n_partial_blocks = 1024;
   TRY(dev_alloc(&p->d_partials, (size_t)p->n_partial_blocks * 4, &tot));
   // --- evaluation work space --------------------------------------------------------
-  const size_t nsphere = (size_t)p->ns * p->nk * ng * p->nb;
-  const size_t nsmall = (size_t)p->ns * p->nk * p->nb * p->nb;
+  // (a child plan on the orbital grid only runs the pencil passes: no sphere-sized buffers)
+  const size_t nsphere = orbital_only ? 1 : (size_t)p->ns * p->nk * ng * p->nb;
+  const size_t nsmall = orbital_only ? 1 : (size_t)p->ns * p->nk * p->nb * p->nb;
+  if (orbital_only) TRY(dev_alloc(&p->d_rho_w, (size_t)p->ns * p->ngrid, &tot));
   TRY(dev_alloc(&p->d_q, nsphere, &tot));
   TRY(dev_alloc(&p->d_hq, nsphere, &tot));
   TRY(dev_alloc(&p->d_tmp, nsphere, &tot));
   TRY(dev_alloc(&p->d_r, nsmall, &tot));
   TRY(dev_alloc(&p->d_rinv, nsmall, &tot));
   TRY(dev_alloc(&p->d_small, nsmall * 5, &tot));
-  TRY(dev_alloc(&p->d_gpart, (size_t)p->nb * p->nb * (size_t)qr_gram_partial_mats(p), &tot));
+  TRY(dev_alloc(&p->d_gpart,
+                orbital_only ? 1 : (size_t)p->nb * p->nb * (size_t)qr_gram_partial_mats(p), &tot));
   TRY(dev_alloc(&p->d_tkb, (size_t)p->ns * p->nk * p->nb, &tot));
   TRY(dev_alloc(&p->d_eps, (size_t)p->ns * p->nk * p->nb, &tot));
   TRY(dev_alloc(&p->d_sphere_part, ((size_t)8 * p->ns * p->nk + 640) * p->nb, &tot));
@@ -386,5 +418,102 @@ extern "C" int jrb_plan_create(const jrb_plan_desc* d, jrb_plan** out) {
 #undef TRY
   p->ws_bytes = tot;
   *out = p;
+  return 0;
+}
+
+// Orbital grid: every per-orbital transform (density sweep, Hamiltonian apply) runs on a smaller
+// box (nxw, nyw, nzw) while rho, the potentials and the dense API keep the plan's grid.  Exact, not
+// an approximation: psi carries frequencies |f_c| <= gmax_c, so |psi|^2 and the part of v_eff psi
+// that lands on the sphere only involve |f_c| <= 2 gmax_c, which a box with n_c >= 4 gmax_c + 1
+// represents without aliasing (the usual coarse wave-function grid of plane-wave codes; SURVEY.md
+// 8d notes that every shipped configuration over-satisfies it).  rho moves to the plan's grid by
+// Fourier interpolation, v_eff to the orbital grid by Fourier truncation (four single-grid FFTs
+// per evaluation).  Allocates: set-up time only.
+extern "C" int jrb_plan_set_orbital_grid(jrb_plan* p, int32_t nxw, int32_t nyw, int32_t nzw) {
+  if (!p || p->ngrid == 0 || p->orbital_only) {
+    set_error("jrb_plan_set_orbital_grid: needs a full plan");
+    return JRB_EINVAL;
+  }
+  JRB_CUDA(cudaSetDevice(p->device));
+  JRB_CUDA(cudaDeviceSynchronize());
+  if (p->wf) {
+    p->ws_bytes -= p->wf->ws_bytes;
+    jrb_plan_destroy(p->wf);
+    p->wf = nullptr;
+  }
+  const int nw[3] = {nxw, nyw, nzw}, n[3] = {p->nx, p->ny, p->nz};
+  if (nxw == p->nx && nyw == p->ny && nzw == p->nz) {
+    if (!p->d_ws_a) {
+      set_error("jrb_plan_set_orbital_grid: the plan's own pencil work space was released by an "
+                "earlier call; create a new plan to go back to the full grid");
+      return JRB_EINVAL;
+    }
+    return 0;
+  }
+  for (int c = 0; c < 3; ++c) {
+    if (nw[c] > n[c] || nw[c] < 4 * p->gmax[c] + 1) {
+      set_error("jrb_plan_set_orbital_grid: axis " + std::to_string(c) + " needs 4*gmax+1 = " +
+                std::to_string(4 * p->gmax[c] + 1) + " <= n_w <= " + std::to_string(n[c]) +
+                ", got " + std::to_string(nw[c]));
+      return JRB_EINVAL;
+    }
+  }
+  std::vector<uint8_t> mask((size_t)nxw * nyw * nzw, 0);
+  for (int64_t g = 0; g < p->ng; ++g) {
+    int idx[3];
+    for (int c = 0; c < 3; ++c) {
+      const int f = p->h_freq[g * 3 + c];
+      idx[c] = f >= 0 ? f : f + nw[c];
+    }
+    mask[((size_t)idx[0] * nyw + idx[1]) * nzw + idx[2]] = 1;
+  }
+  jrb_plan_desc d{};
+  d.nx = nxw; d.ny = nyw; d.nz = nzw;
+  d.ns = p->ns; d.nk = p->nk; d.nb = p->nb;
+  d.mask = mask.data();
+  d.kpts = p->h_kpts;
+  d.cell = p->cell;
+  d.device = p->device;
+  d.batch_groups = 0;
+  jrb_plan* w = nullptr;
+  int rc = plan_create_impl(&d, true, &w);
+  if (rc) return rc;
+  // the compact order must be the plan's own (both enumerate non-negative then negative
+  // frequencies in C order)
+  bool same = w->ng == p->ng;
+  for (int64_t i = 0; same && i < p->ng * 3; ++i) same = w->h_freq[i] == p->h_freq[i];
+  if (!same) {
+    jrb_plan_destroy(w);
+    set_error("jrb_plan_set_orbital_grid: internal error, sphere enumeration differs");
+    return JRB_EINVAL;
+  }
+  // this plan delegates its pencil passes from now on: release its own pencil work space
+  {
+    const long long total_groups = (long long)p->ns * p->nk * p->ngroups_per_k;
+    if (p->d_a_keep) p->ws_bytes -= total_groups * p->a_group_elems * (long long)sizeof(cplx);
+    if (p->d_ws_a) p->ws_bytes -= p->a_copy_elems * (p->fused == 2 ? 3 : 1) * (long long)sizeof(cplx);
+  }
+  for (cplx** q : {&p->d_a_keep, &p->d_ws_a, &p->d_ws_b}) {
+    if (*q) cudaFree(*q);
+    *q = nullptr;
+  }
+  if (p->d_rho_part) cudaFree(p->d_rho_part);
+  p->d_rho_part = nullptr;
+  p->wf = w;
+  p->ws_bytes += w->ws_bytes;
+  return 0;
+}
+
+extern "C" int jrb_plan_orbital_grid(const jrb_plan* p, int32_t* dims) {
+  if (!p || !dims) return JRB_EINVAL;
+  const jrb_plan* o = p->wf ? p->wf : p;
+  dims[0] = o->nx; dims[1] = o->ny; dims[2] = o->nz;
+  return 0;
+}
+
+/* smallest alias-free orbital box per axis: 4 gmax + 1 */
+extern "C" int jrb_plan_min_orbital_grid(const jrb_plan* p, int32_t* dims) {
+  if (!p || !dims || p->ngrid == 0) return JRB_EINVAL;
+  for (int c = 0; c < 3; ++c) dims[c] = 4 * p->gmax[c] + 1;
   return 0;
 }

@@ -103,6 +103,17 @@ struct jrb_plan {
   // host staging for jrb_energy_grad_host
   double *d_wre, *d_wim, *d_gre, *d_gim, *d_occ, *d_rho, *d_en;
   int64_t ws_bytes;
+  // Orbital grid (jrb_plan_set_orbital_grid): a child plan on a smaller, alias-free FFT box that
+  // runs every per-orbital transform; this plan keeps the reference's grid for rho, the
+  // potentials and the dense API.  Null: orbitals are transformed on the plan's own grid.
+  jrb_plan* wf;
+  int orbital_only;     // this plan IS such a child (no evaluation work space)
+  double* d_rho_w;      // child: [ns][ngrid] density on the orbital grid
+  int veff_w_valid;     // child: d_veff holds the resampled potential of the running evaluation
+  // host copies for the child's construction and jrb_set_kpoints
+  int32_t* h_freq;      // [ng][3] integer frequencies of the kept plane waves, compact order
+  double* h_kpts;       // [nk][3]
+  int gmax[3];          // largest |frequency| per axis on the sphere
 };
 
 namespace jrb {
@@ -117,6 +128,17 @@ int launch_kinetic_range(jrb_plan* p, int sk0, int nsk, const cplx* q, double* t
                          cudaStream_t st);
 int launch_fft3d_dense(jrb_plan* p, const cplx* in, cplx* out, int dir, int64_t batch,
                        double scale, cudaStream_t st);
+// density accumulation protocol of the k-chunked host path (and of launch_density itself):
+// begin (zero) -> launch_density_krange ... -> end (orbital grid -> the plan's grid)
+int launch_density_begin(jrb_plan* p, double* rho, cudaStream_t st);
+int launch_density_end(jrb_plan* p, double* rho, cudaStream_t st);
+// veff on the plan's grid -> what launch_hpsi_krange needs (resampled onto the orbital grid)
+int launch_hpsi_prepare(jrb_plan* p, const double* veff, cudaStream_t st);
+// grid_kernels.cu: Fourier resampling between two boxes (dst bins without a partner are zero)
+int launch_resample(const cplx* src, int sx, int sy, int sz, cplx* dst, int dx, int dy, int dz,
+                    double scale, cudaStream_t st);
+int launch_real_to_complex(const double* in, long long n, cplx* out, cudaStream_t st);
+int launch_complex_to_real(const cplx* in, long long n, double* out, cudaStream_t st);
 bool line_length_supported(int n);
 bool fused_available(int nx, int ny, int nxo, int ncol);
 bool fused128_available(int nx, int ny, int nxo, int ncol, int band_limited32);

@@ -24,7 +24,7 @@ def _stream():
 class Plan:
 
   def __init__(self, cell_vectors, freq_mask, kpts, num_bands: int, num_spin: int = 1,
-               device: Optional[int] = None, batch_groups: int = 0):
+               device: Optional[int] = None, batch_groups: int = 0, orbital_grid=None):
     if not torch.cuda.is_available():
       raise RuntimeError('jrystal_b200 needs a CUDA device (there is no CPU fallback)')
     self.lib = _lib.load()
@@ -50,6 +50,39 @@ class Plan:
     self.ng = int(self.lib.jrb_plan_num_g(self._h))
     self.tdev = torch.device('cuda', self.device)
     self._atoms = False
+    self.orbital_grid = (self.nx, self.ny, self.nz)
+    if orbital_grid is not None:
+      self.set_orbital_grid(orbital_grid)
+
+  # -- orbital grid -----------------------------------------------------------------
+  @property
+  def min_orbital_grid(self):
+    """Smallest alias-free box per axis, 4 gmax + 1."""
+    dims = (ctypes.c_int32 * 3)()
+    _lib.check(self.lib.jrb_plan_min_orbital_grid(self._h, dims))
+    return tuple(int(v) for v in dims)
+
+  def auto_orbital_grid(self):
+    """The box `orbital_grid='auto'` picks: z (the axis the fused y+x plane kernels loop over)
+    shrinks to the smallest compiled length >= 4 gmax + 1; x and y keep the plan's lengths (the
+    fused kernels are tuned for 64 and 128)."""
+    need = self.min_orbital_grid
+    full = (self.nx, self.ny, self.nz)
+    nz = min([n for n in _lib.LINE_LENGTHS if need[2] <= n <= full[2]] or [full[2]])
+    return (full[0], full[1], nz)
+
+  def set_orbital_grid(self, dims):
+    """Run the per-orbital transforms on a smaller alias-free box (jrb_plan_set_orbital_grid);
+    'auto' = auto_orbital_grid(), 'full' / None = the plan's grid."""
+    if dims is None or dims == 'full':
+      dims = (self.nx, self.ny, self.nz)
+    elif dims == 'auto':
+      dims = self.auto_orbital_grid()
+    dims = tuple(int(v) for v in dims)
+    if len(dims) != 3:
+      raise ValueError('orbital_grid must be three axis lengths, "auto" or "full"')
+    _lib.check(self.lib.jrb_plan_set_orbital_grid(self._h, *dims))
+    self.orbital_grid = dims
 
   def __del__(self):
     h = getattr(self, '_h', None)
