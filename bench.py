@@ -46,6 +46,14 @@ WORKLOADS = {
              valence=[10, 12, 6, 6, 6], nproj_per_atom=18,
              text='C4: SrTiO3 norm-conserving (synthetic PP data), 64^3, 40 Ha, 6x6x6 k, 30 bands, '
                   '90 projectors'),
+  # BASELINE config 5: band mode.  One evaluation = value + gradient of hamiltonian_matrix_trace at
+  # ONE k-point (hamiltonian.py:147-168: QR, H-apply with the fixed v_eff[rho_gs], trace, QR
+  # adjoint); the 64 path points are independent and run as one batch (the reference scans them
+  # one after the other per device, calc_band_structure_all_electrons.py:115-182).
+  'C5': dict(crystal='al_primitive', repeat=None, grid=48, cutoff=50.0, kpath=64, empty=8,
+             band_mode=True,
+             text='C5: Al primitive band mode, 48^3, 50 Ha, 64 k-path points, 15 bands; one '
+                  'evaluation = Hamiltonian trace + gradient at one k-point'),
 }
 METRIC = 'energy+grad evals/sec'
 UNIT = 'eval/s'
@@ -68,7 +76,11 @@ def build_workload(name):
   crystal = Crystal.create_builtin(w['crystal'], repeat=w['repeat'])
   gs = grid.proper_grid_size(w['grid'])
   mask = grid.spherical_mask(crystal.cell_vectors, gs, w['cutoff'])
-  kpts = grid.k_vectors(crystal.cell_vectors, grid.proper_grid_size(w['kgrid']))
+  if w.get('band_mode'):
+    from jrystal_b200.k_path import get_k_path
+    kpts = get_k_path(crystal.cell_vectors, None, w['kpath'])
+  else:
+    kpts = grid.k_vectors(crystal.cell_vectors, grid.proper_grid_size(w['kgrid']))
   if 'valence' in w:  # pseudopotential run: the ions carry their valence charge
     crystal.charges = np.asarray(w['valence'])
     crystal.spin = 0
@@ -76,7 +88,7 @@ def build_workload(name):
   occ = occupation.uniform(kpts.shape[0], crystal.num_electron, crystal.spin, nb)
   nproj = w.get('nproj_per_atom', 0) * crystal.num_atom
   return dict(crystal=crystal, grid=[int(g) for g in gs], mask=mask, kpts=kpts, nb=nb, occ=occ,
-              ng=int(mask.sum()), text=w['text'], nproj=nproj)
+              ng=int(mask.sum()), text=w['text'], nproj=nproj, band_mode=bool(w.get('band_mode')))
 
 
 def synthetic_projectors(ng, nk, nproj, k0, k1, device):
@@ -218,11 +230,16 @@ def run_reference(args):
     return
   wl = build_workload(args.config)
   nk = wl['kpts'].shape[0]
-  nk_sample = {'C1': 8, 'C2': 8, 'C3a': 1, 'C3b': 1, 'C4': 8}[args.config]
   steps = max(1, min(args.steps, 3))
-  value, t, cores, nks = cpu_sample_eval(wl, nk_sample, steps, min(args.warmup, 1))
-  sample = (f'{nks} of {nk} k-points x {wl["nb"]} bands at {wl["grid"]} per step, time scaled '
-            f'by {nk / nks:g}; oracle port (torch FP64 autograd), {cores} threads')
+  if wl['band_mode']:
+    value, t, cores, nks = cpu_sample_band(wl, 4, steps, min(args.warmup, 1))
+    sample = (f'{nks} of {nk} path points x {wl["nb"]} bands at {wl["grid"]} per step, one after '
+              f'the other; oracle port (torch FP64 autograd), {cores} threads')
+  else:
+    nk_sample = {'C1': 8, 'C2': 8, 'C3a': 1, 'C3b': 1, 'C4': 8}[args.config]
+    value, t, cores, nks = cpu_sample_eval(wl, nk_sample, steps, min(args.warmup, 1))
+    sample = (f'{nks} of {nk} k-points x {wl["nb"]} bands at {wl["grid"]} per step, time scaled '
+              f'by {nk / nks:g}; oracle port (torch FP64 autograd), {cores} threads')
   line = {
     'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': args.gpus,
     'steps': steps, 'warmup': min(args.warmup, 1), 'ms_per_step': 1e3 / value,
@@ -249,7 +266,7 @@ def run_b200_rows(args, wl, world, rank, local_rank):
   nk, nb, ng = wl['kpts'].shape[0], wl['nb'], wl['ng']
   ngrid = int(np.prod(wl['grid']))
   ev = RowShardedEvaluator(c.cell_vectors, wl['mask'], wl['kpts'], nb, c.positions, c.charges,
-                           device=local_rank)
+                           device=local_rank, orbital_grid=parse_orbital_grid(args.orbital_grid))
   w_re_f, w_im_f = synthetic_params(ng, nk, nb, 0, nk)
   w_re_h = np.ascontiguousarray(w_re_f[:, :, ev.g0:ev.g1])
   w_im_h = np.ascontiguousarray(w_im_f[:, :, ev.g0:ev.g1])
@@ -329,6 +346,7 @@ def run_b200_rows(args, wl, world, rank, local_rank):
       'config': {'workload': wl['text'], 'orbitals': nk * nb, 'ng': ng, 'grid': wl['grid'],
                  'sharding': f'rows{world} (QR) + bands{world} (FFT), all-to-all between',
                  'xc': 'lda_x', 'bands_per_rank': ev.b1 - ev.b0, 'rows_per_rank': ev.g1 - ev.g0,
+                 'orbital_grid': list(ev.bands.orbital_grid),
                  'l2': 'working set larger than L2 (pencil work space); no flush'},
       'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': 2 * nw * 8 + occ_h.size * 8,
               'd2h_bytes_per_step': 2 * nw * 8 + 32,
@@ -342,6 +360,172 @@ def run_b200_rows(args, wl, world, rank, local_rank):
     }
     emit(line)
   dist.destroy_process_group()
+
+
+def cpu_sample_band(wl, nk_sample, steps, warmup):
+  """Oracle band-mode evaluation (hamiltonian_matrix_trace value + gradient) on `nk_sample` path
+  points, one after the other as the reference scans them; returns k-point evaluations / s."""
+  import torch
+  from oracle import reference_port as rp
+  cores = os.cpu_count() or 1
+  torch.set_num_threads(cores)
+  c = wl['crystal']
+  rng = np.random.default_rng(7)
+  rho = np.abs(rng.standard_normal((1,) + tuple(wl['grid']))) * c.num_electron / c.vol
+  w_re, w_im = synthetic_params(wl['ng'], wl['kpts'].shape[0], wl['nb'], 0, nk_sample)
+  times = []
+  for i in range(warmup + steps):
+    t0 = time.perf_counter()
+    for k in range(nk_sample):
+      s = rp.System(c.cell_vectors, c.positions, c.charges, wl['grid'], kpts=wl['kpts'][k:k + 1],
+                    cutoff_energy=None, mask_method='cubic')
+      s.mask = wl['mask']
+      s.num_g = wl['ng']
+      rp.band_trace_and_grad(s, w_re[:, k:k + 1], w_im[:, k:k + 1], rho)
+    dt = time.perf_counter() - t0
+    if i >= warmup:
+      times.append(dt)
+  t = float(np.mean(times))
+  return nk_sample / t, t, cores, nk_sample
+
+
+def run_b200_band(args, wl, world, rank, local_rank):
+  """C5: band-mode evaluations (Hamiltonian trace + gradient per k-point), the path points split
+  in contiguous chunks over the ranks without communication (the reference's pmap over the
+  k-path); value = k-point evaluations / s of the whole job."""
+  import torch
+  import torch.distributed as dist
+  import jrystal_b200 as jb
+  from jrystal_b200 import _lib, parallel
+
+  c = wl['crystal']
+  nk, nb, ng = wl['kpts'].shape[0], wl['nb'], wl['ng']
+  ngrid = int(np.prod(wl['grid']))
+  k0, k1 = parallel.shard_kpoints(nk, world, rank) if nk % world == 0 else parallel.shard_bands(
+    nk, world, rank)
+  nkl = k1 - k0
+  plan = jb.Plan(c.cell_vectors, wl['mask'], wl['kpts'][k0:k1], nb, device=local_rank)
+  plan.set_atoms(c.positions, c.charges)
+  rng = np.random.default_rng(7)
+  rho_h = np.abs(rng.standard_normal((1,) + tuple(wl['grid']))) * c.num_electron / c.vol
+  rho = torch.from_numpy(rho_h).cuda()
+  _, veff = plan.grid_potential(rho, 'lda_x', True)   # v_eff[rho_gs]: once, not per step
+  w_re_h, w_im_h = synthetic_params(ng, nk, nb, k0, k1)
+  w_re, w_im = torch.from_numpy(w_re_h).cuda(), torch.from_numpy(w_im_h).cuda()
+  cdt = torch.complex128
+  q = torch.empty(w_re.shape, dtype=cdt, device='cuda')
+  r = torch.empty((1, nkl, nb, nb), dtype=cdt, device='cuda')
+  hq = torch.empty_like(q)
+  eps = torch.empty((1, nkl, nb), dtype=torch.float64, device='cuda')
+  grads = (torch.empty_like(w_re), torch.empty_like(w_im))
+
+  def step():
+    plan.qr_fwd(w_re, w_im, out=(q, r))
+    plan.hpsi(q, veff, out=hq)
+    plan.band_expect(q, hq, out=eps)
+    plan.qr_bwd(q, r, hq, out=grads)
+
+  def barrier():
+    if world > 1:
+      dist.barrier()
+    torch.cuda.synchronize()
+
+  flush_buf = torch.zeros(32 * 2**20, dtype=torch.float64, device='cuda')
+  lib = _lib.load()
+  for _ in range(max(args.warmup, 3)):
+    step()
+  graph = torch.cuda.CUDAGraph()
+  with torch.cuda.graph(graph):
+    step()
+  graph.replay()
+  barrier()
+
+  def timed(fn):
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+           for _ in range(args.steps)]
+    barrier()
+    for e0, e1 in evs:
+      flush_buf.add_(1.0)
+      e0.record()
+      fn()
+      e1.record()
+    barrier()
+    ms = torch.tensor([sum(e0.elapsed_time(e1) for e0, e1 in evs)], dtype=torch.float64,
+                      device='cuda')
+    if world > 1:
+      dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    return float(ms.item()) / args.steps
+
+  launches0 = lib.jrb_launch_count()
+  with ClockSampler(local_rank, enabled=(rank == 0)) as clk:
+    ms_eager = timed(step)
+  launches = int(lib.jrb_launch_count() - launches0)
+  ms_graph = timed(graph.replay)
+  ms_per_step = min(ms_eager, ms_graph)
+  value = nk / (ms_per_step * 1e-3)
+
+  # end to end: parameters of the chunk from pinned host memory, gradients + band energies back
+  pin = lambda a: torch.from_numpy(a).pin_memory()
+  w_re_p, w_im_p = pin(w_re_h), pin(w_im_h)
+  g_re_p = torch.empty(w_re_h.shape, dtype=torch.float64).pin_memory()
+  g_im_p = torch.empty(w_re_h.shape, dtype=torch.float64).pin_memory()
+  eps_p = torch.empty((1, nkl, nb), dtype=torch.float64).pin_memory()
+
+  def e2e_step():
+    w_re.copy_(w_re_p, non_blocking=True)
+    w_im.copy_(w_im_p, non_blocking=True)
+    step()
+    g_re_p.copy_(grads[0], non_blocking=True)
+    g_im_p.copy_(grads[1], non_blocking=True)
+    eps_p.copy_(eps, non_blocking=True)
+    torch.cuda.current_stream().synchronize()
+
+  e2e_step()
+  barrier()
+  t0 = time.perf_counter()
+  for _ in range(args.steps):
+    e2e_step()
+  barrier()
+  e2e_s = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device='cuda')
+  if world > 1:
+    dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
+  e2e_value = nk * args.steps / float(e2e_s.item())
+
+  peak, peak_src = measured_peak()
+  bytes_alg = nkl * nb * (32.0 * ngrid + 48.0 * ng)  # one dense transform pair + W, Q, HQ, dW
+  achieved = bytes_alg / (ms_per_step * 1e-3) / 1e9
+  if rank == 0:
+    nw = w_re_h.size
+    line = {
+      'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
+      'warmup': max(args.warmup, 3), 'ms_per_step': ms_per_step, 'higher_is_better': True,
+      'scaling': 'strong', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
+      'config': {'workload': wl['text'], 'k_points': nk, 'bands': nb, 'ng': ng,
+                 'grid': wl['grid'], 'sharding': f'kpath{world}' if world > 1 else 'none',
+                 'xc': 'lda_x', 'evaluations_per_step': nk,
+                 'l2': 'working set fits L2: L2 flushed between timed steps (256 MiB rewrite), '
+                       'per-step CUDA events',
+                 'launch': 'CUDA graph replay' if ms_graph <= ms_eager else 'eager'},
+      'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': 2 * nw * 8,
+              'd2h_bytes_per_step': 2 * nw * 8 + nkl * nb * 8,
+              'path': 'pinned H2D + jrb_qr_fwd/jrb_hpsi/jrb_band_expect/jrb_qr_bwd + D2H'},
+      'gpu_launches': launches,
+      'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
+                   'frac': achieved / peak, 'traffic': None, 'peak_source': peak_src,
+                   'kernel': 'whole band-mode evaluation batch (launch-latency bound at this size)',
+                   'bytes_formula': 'nk*nb*(32*N + 48*ng)'},
+      'clocks': clk.summary(),
+      'band_step': {'eager_ms': ms_eager, 'graph_ms': ms_graph},
+    }
+    if world == 1 and not args.no_cpu:
+      v, t, cores, nks = cpu_sample_band(wl, 4, 2, 1)
+      line['cpu_baseline'] = {
+        'value': v, 'unit': UNIT, 'cores': cores, 'kind': 'port',
+        'sample': f'{nks} of {nk} path points x {nb} bands ({t:.2f} s), one after the other; '
+                  'oracle port (torch FP64 autograd)'}
+    emit(line)
+  if world > 1:
+    dist.destroy_process_group()
 
 
 def parse_orbital_grid(text):
@@ -370,6 +554,8 @@ def run_b200(args):
   c = wl['crystal']
   nk, nb, ng = wl['kpts'].shape[0], wl['nb'], wl['ng']
   ngrid = int(np.prod(wl['grid']))
+  if wl['band_mode']:
+    return run_b200_band(args, wl, world, rank, local_rank)
   if nk % world != 0:
     return run_b200_rows(args, wl, world, rank, local_rank)
   k0, k1 = parallel.shard_kpoints(nk, world, rank)
@@ -616,8 +802,9 @@ def main():
   ap.add_argument('--config', default='C2', choices=list(WORKLOADS))
   ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
   ap.add_argument('--no-cpu', action='store_true', help='skip the cpu_baseline leg')
-  ap.add_argument('--orbital-grid', default=os.environ.get('JRB_ORBITAL_GRID', 'full'),
-                  help="box of the per-orbital FFTs: 'full' (the reference's), 'auto' or nx,ny,nz")
+  ap.add_argument('--orbital-grid', default=os.environ.get('JRB_ORBITAL_GRID', 'auto'),
+                  help="box of the per-orbital FFTs: 'auto' (smallest efficient alias-free box; default), "
+                       "'full' (the reference's own grid) or nx,ny,nz; results do not depend on it")
   ap.add_argument('--emulate-ranks', type=int, default=1,
                   help='tuning aid: run only the k-points rank 0 of an N-GPU run would own')
   args = ap.parse_args()

@@ -84,6 +84,9 @@ int jrb_plan_set_orbital_grid(jrb_plan* plan, int32_t nxw, int32_t nyw, int32_t 
 /* dims[3] = the box the per-orbital passes currently run on / the smallest alias-free box */
 int jrb_plan_orbital_grid(const jrb_plan* plan, int32_t* dims);
 int jrb_plan_min_orbital_grid(const jrb_plan* plan, int32_t* dims);
+/* which kernels run the y and x passes on the current orbital box: 0 single pencil passes,
+ * 1 fused y+x plane kernels (fft_fused.cuh), 2 the 128 x 128 fused family (fft_fused128.cuh) */
+int jrb_plan_orbital_fused(const jrb_plan* plan);
 
 /* Pre-computes V_ext(G) once: potential.external_reciprocal (jrystal/_src/potential.py:
  * 153-166), which the reference re-evaluates every step although it is parameter free. */

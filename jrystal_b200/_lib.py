@@ -14,6 +14,9 @@ FFT_FORWARD, FFT_INVERSE = -1, 1
 LINE_LENGTHS = (7, 8, 9, 12, 16, 24, 32, 40, 45, 48, 49, 50, 54, 56, 60, 64, 72, 80, 81, 90, 96,
                 100, 112, 128)
 FUSED_LENGTHS = (7, 8, 9, 12, 16, 24, 32, 48, 49, 64, 72, 81, 96, 128)
+# lengths whose two-stage line plan is square-ish (few elements per thread, 3-4 resident CTAs in
+# the z passes): what orbital_grid='auto' chooses from
+AUTO_Z_LENGTHS = (7, 8, 9, 12, 16, 24, 32, 49, 64, 81, 100, 128)
 
 
 class PlanDesc(ctypes.Structure):
@@ -35,6 +38,7 @@ SYMBOLS = {
   'jrb_plan_set_orbital_grid': (ctypes.c_int, [_P, _I32, _I32, _I32]),
   'jrb_plan_orbital_grid': (ctypes.c_int, [_P, _P]),
   'jrb_plan_min_orbital_grid': (ctypes.c_int, [_P, _P]),
+  'jrb_plan_orbital_fused': (ctypes.c_int, [_P]),
   'jrb_set_atoms': (ctypes.c_int, [_P, _P, _P, _I32, _P]),
   'jrb_set_external_potential': (ctypes.c_int, [_P, _P, _P]),
   'jrb_external_position_gradient': (ctypes.c_int, [_P, _P, _P, _P]),

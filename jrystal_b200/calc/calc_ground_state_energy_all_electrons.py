@@ -77,7 +77,9 @@ def calc(config: Optional[JrystalConfigDict] = None, plan: Optional[Plan] = None
   if not config.spin_restricted:
     raise NotImplementedError('spin-unrestricted energy mode is not wired into the driver yet')
   if plan is None:
-    plan = Plan(crystal.cell_vectors, freq_mask, k_vec[k0:k1], num_bands)
+    og = config.get('orbital_grid', 'auto')
+    plan = Plan(crystal.cell_vectors, freq_mask, k_vec[k0:k1], num_bands,
+                orbital_grid=tuple(og) if isinstance(og, (list, tuple)) else og)
   plan.set_atoms(crystal.positions, crystal.charges)
   dev = plan.tdev
   rng = np.random.default_rng(config.seed)

@@ -17,6 +17,9 @@ default_config = {
   "k_path_fine_tuning_epoch": 300, "seed": 123, "parallel_over_k_mesh": False,
   "parallel_over_k_path": True, "xla_preallocate": True, "jax_enable_x64": True,
   "jax_debug_nans": False, "verbose": True, "eps": 1e-8,
+  # not a reference key: box of the per-orbital FFTs, 'auto' | 'full' | [nx, ny, nz]
+  # (jrb_plan_set_orbital_grid; results do not depend on it)
+  "orbital_grid": "auto",
 }
 
 

@@ -511,6 +511,12 @@ extern "C" int jrb_plan_orbital_grid(const jrb_plan* p, int32_t* dims) {
   return 0;
 }
 
+/* 0: single pencil passes, 1: fused y+x plane kernels, 2: the 128 x 128 fused family */
+extern "C" int jrb_plan_orbital_fused(const jrb_plan* p) {
+  if (!p) return JRB_EINVAL;
+  return (p->wf ? p->wf : p)->fused;
+}
+
 /* smallest alias-free orbital box per axis: 4 gmax + 1 */
 extern "C" int jrb_plan_min_orbital_grid(const jrb_plan* p, int32_t* dims) {
   if (!p || !dims || p->ngrid == 0) return JRB_EINVAL;

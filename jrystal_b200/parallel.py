@@ -132,7 +132,7 @@ class RowShardedEvaluator:
   mathematics is that of the single-device evaluation, cut where sums cross ranks."""
 
   def __init__(self, cell_vectors, freq_mask, kpts, num_bands, positions, charges, group=None,
-               device: Optional[int] = None, batch_groups: int = 0):
+               device: Optional[int] = None, batch_groups: int = 0, orbital_grid=None):
     from .plan import Plan, RowsPlan
     self.group = group
     self.world, self.rank = _world(group)
@@ -150,7 +150,7 @@ class RowShardedEvaluator:
       raise ValueError('more ranks than bands / rows')
     self.rows = RowsPlan(self.g1 - self.g0, self.nk, self.nb, 1, device=device)
     self.bands = Plan(cell_vectors, mask, kpts, self.b1 - self.b0, device=device,
-                      batch_groups=batch_groups)
+                      batch_groups=batch_groups, orbital_grid=orbital_grid)
     self.bands.set_atoms(positions, charges)
 
   def evaluate(self, w_re_rows, w_im_rows, occ, xc: str = 'lda_x'):

@@ -63,13 +63,19 @@ class Plan:
     return tuple(int(v) for v in dims)
 
   def auto_orbital_grid(self):
-    """The box `orbital_grid='auto'` picks: z (the axis the fused y+x plane kernels loop over)
-    shrinks to the smallest compiled length >= 4 gmax + 1; x and y keep the plan's lengths (the
-    fused kernels are tuned for 64 and 128)."""
+    """The box `orbital_grid='auto'` picks (measured on B200, profiles/r01_orbital_grid.md): z, the
+    axis the fused y+x plane kernels loop over, shrinks to the smallest length >= 4 gmax + 1 with
+    a light line plan; x and y keep the plan's lengths (the fused kernels are tuned for 64 and
+    128) except 128 -> 81 when that fits and the fused 81 x 81 kernels have the shared memory."""
     need = self.min_orbital_grid
     full = (self.nx, self.ny, self.nz)
-    nz = min([n for n in _lib.LINE_LENGTHS if need[2] <= n <= full[2]] or [full[2]])
-    return (full[0], full[1], nz)
+    if self.ngrid < 48 ** 3:  # launch-latency bound sizes: the resampling launches cost more
+      return [full]
+    nz = min([n for n in _lib.AUTO_Z_LENGTHS if need[2] <= n <= full[2]] or [full[2]])
+    nxy = [(full[0], full[1])]
+    if full[0] == full[1] == 128 and max(need[:2]) <= 81:
+      nxy.insert(0, (81, 81))
+    return [(a, b, nz) for a, b in nxy]
 
   def set_orbital_grid(self, dims):
     """Run the per-orbital transforms on a smaller alias-free box (jrb_plan_set_orbital_grid);
@@ -77,7 +83,13 @@ class Plan:
     if dims is None or dims == 'full':
       dims = (self.nx, self.ny, self.nz)
     elif dims == 'auto':
-      dims = self.auto_orbital_grid()
+      cands = self.auto_orbital_grid()
+      for cand in cands[:-1]:  # boxes that only pay with the fused plane kernels
+        _lib.check(self.lib.jrb_plan_set_orbital_grid(self._h, *cand))
+        if self.lib.jrb_plan_orbital_fused(self._h) > 0:
+          self.orbital_grid = cand
+          return
+      dims = cands[-1]
     dims = tuple(int(v) for v in dims)
     if len(dims) != 3:
       raise ValueError('orbital_grid must be three axis lengths, "auto" or "full"')
@@ -275,10 +287,10 @@ class Plan:
     _lib.check(self.lib.jrb_hpsi(self._h, _ptr(q), _ptr(veff), _ptr(hq), _stream()))
     return hq
 
-  def band_expect(self, q, hq):
+  def band_expect(self, q, hq, out=None):
     self._chk(q, self.sphere_shape, torch.complex128, 'q')
     self._chk(hq, self.sphere_shape, torch.complex128, 'hq')
-    eps = self._new((self.ns, self.nk, self.nb), torch.float64)
+    eps = self._new((self.ns, self.nk, self.nb), torch.float64) if out is None else out
     _lib.check(self.lib.jrb_band_expect(self._h, _ptr(q), _ptr(hq), _ptr(eps), _stream()))
     return eps
 
