@@ -41,6 +41,12 @@ extern "C" {
  * reference are summed; the ids below are the combinations the kernels implement. */
 #define JRB_XC_LDA_X 1
 #define JRB_XC_LDA_X_C_PW 2 /* "lda_x+lda_c_pw" */
+/* GGA branch (xc.py:67-112: sigma = |ifftn(i G fftn(rho))|^2, eps(rho, sigma)); unpolarised.
+ * The potential is the exact discrete derivative of E_xc = (Omega/N) sum rho eps (what jax.grad
+ * gives the reference in energy mode); band mode (kohn_sham) uses the same potential instead of
+ * xc.py:127-219, whose gradient term calls a 1-D fft on a 3-D field. */
+#define JRB_XC_GGA_X_PBE 3 /* "gga_x_pbe" */
+#define JRB_XC_GGA_PBE 4   /* "gga_x_pbe+gga_c_pbe" (the reference's config.yaml default) */
 
 #define JRB_FFT_FORWARD (-1) /* jnp.fft.fftn  : exp(-i...)            (fftn_sharding)  */
 #define JRB_FFT_INVERSE (+1) /* jnp.fft.ifftn : exp(+i...) and 1/N    (ifftn_sharding) */

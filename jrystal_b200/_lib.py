@@ -8,7 +8,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, 'csrc', 'libjrystal_b200.so')
 
-XC_IDS = {'lda_x': 1, 'lda_x+lda_c_pw': 2}
+XC_IDS = {'lda_x': 1, 'lda_x+lda_c_pw': 2, 'gga_x_pbe': 3, 'gga_x_pbe+gga_c_pbe': 4}
 FFT_FORWARD, FFT_INVERSE = -1, 1
 # axis lengths with compiled pencil passes; FUSED: also the fused y+x plane kernels (nx == ny)
 LINE_LENGTHS = (7, 8, 9, 12, 16, 24, 32, 40, 45, 48, 49, 50, 54, 56, 60, 64, 72, 80, 81, 90, 96,

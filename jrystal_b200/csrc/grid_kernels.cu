@@ -256,11 +256,140 @@ __device__ __forceinline__ void lda_eps(int xc_id, double n, double& eps, double
   }
 }
 
+
+// ---------------------------------------------------------------------------------------
+// GGA (PBE exchange and correlation, unpolarised).  The reference evaluates
+// eps_xc(rho, sigma) per grid point with sigma = sum_j |d_j|^2, d_j = ifftn(i G_j fftn(rho))
+// (xc.py:67-112, 242-253) and lets jax.grad differentiate E_xc = (Omega/N) sum rho eps through
+// both arguments.  Here the same energy is accumulated and its exact discrete derivative is
+// formed by hand:  dE/d rho(r) = de/d rho - 2 Re ifftn( sum_j i G_j fftn( de/d sigma * d_j ) )
+// with e = rho eps (the adjoint of D_j = ifftn i G_j fftn on the FFT grid is u -> -conj(D_j conj u),
+// Nyquist bins included, so the result matches autograd to rounding).  de/d rho and de/d sigma
+// come from forward-mode duals of the closed-form eps(rho, sigma).
+struct Dual {  // value, d/d rho, d/d sigma
+  double v, r, s;
+};
+__device__ __forceinline__ Dual dmk(double v, double r = 0.0, double s = 0.0) {
+  Dual d;
+  d.v = v; d.r = r; d.s = s;
+  return d;
+}
+__device__ __forceinline__ Dual operator+(Dual a, Dual b) { return dmk(a.v + b.v, a.r + b.r, a.s + b.s); }
+__device__ __forceinline__ Dual operator-(Dual a, Dual b) { return dmk(a.v - b.v, a.r - b.r, a.s - b.s); }
+__device__ __forceinline__ Dual operator*(Dual a, Dual b) {
+  return dmk(a.v * b.v, a.r * b.v + a.v * b.r, a.s * b.v + a.v * b.s);
+}
+__device__ __forceinline__ Dual operator*(double c, Dual a) { return dmk(c * a.v, c * a.r, c * a.s); }
+__device__ __forceinline__ Dual operator+(double c, Dual a) { return dmk(c + a.v, a.r, a.s); }
+__device__ __forceinline__ Dual operator/(Dual a, Dual b) {
+  const double q = a.v / b.v, ib = 1.0 / b.v;
+  return dmk(q, (a.r - q * b.r) * ib, (a.s - q * b.s) * ib);
+}
+__device__ __forceinline__ Dual dchain(Dual a, double f, double df) { return dmk(f, df * a.r, df * a.s); }
+__device__ __forceinline__ Dual dsqrt(Dual a) { const double f = sqrt(a.v); return dchain(a, f, 0.5 / f); }
+__device__ __forceinline__ Dual dcbrt(Dual a) { const double f = cbrt(a.v); return dchain(a, f, f / (3.0 * a.v)); }
+__device__ __forceinline__ Dual dlog1p(Dual a) { return dchain(a, log1p(a.v), 1.0 / (1.0 + a.v)); }
+__device__ __forceinline__ Dual dexpm1(Dual a) { const double f = expm1(a.v); return dchain(a, f, f + 1.0); }
+
+// eps_xc(rho, sigma) of gga_x_pbe (+ gga_c_pbe) as LibXC defines them (jax_xc 0.0.8 translates
+// LibXC's maple sources; not vendored -> parity unpinned)
+__device__ __forceinline__ Dual pbe_eps(int xc_id, double rho, double sigma) {
+  const Dual n = dmk(rho, 1.0, 0.0), sg = dmk(sigma, 0.0, 1.0);
+  Dual eps = dmk(0.0);
+  const Dual n13 = dcbrt(n);
+  if (rho > 1e-15) {  // gga_x_pbe dens_threshold
+    const double kappa = 0.8040, mu = 0.2195149727645171;
+    const double cx = -0.73855876638202240588;                 // -3/4 (3/pi)^(1/3)
+    const double c_s2 = 1.0 / (4.0 * 9.5707800006273513);     // 1 / (4 (3 pi^2)^(2/3))
+    const Dual n83 = (n * n) * (n13 * n13);
+    const Dual s2 = c_s2 * (sg / n83);
+    const Dual fx = (1.0 + kappa) + (-kappa * kappa) * (dmk(1.0) / (kappa + mu * s2));
+    eps = eps + (cx * n13) * fx;
+  }
+  if (xc_id == JRB_XC_GGA_PBE && rho > 1e-12) {  // gga_c_pbe dens_threshold
+    // PW92 with LibXC's pw_mod parameters (what gga_c_pbe includes), zeta = 0
+    const double A = 0.0310907, a1 = 0.21370, b1 = 7.5957, b2 = 3.5876, b3 = 1.6382, b4 = 0.49294;
+    const double beta = 0.06672455060314922, gamma = 0.031090690869654895;  // (1 - ln 2) / pi^2
+    const Dual rs = 0.62035049089940001667 * (dmk(1.0) / n13);  // (3 / (4 pi))^(1/3) n^(-1/3)
+    const Dual sr = dsqrt(rs);
+    const Dual q = (2.0 * A) * (b1 * sr + b2 * rs + b3 * (rs * sr) + b4 * (rs * rs));
+    const Dual ec = (-2.0 * A) * ((1.0 + a1 * rs) * dlog1p(dmk(1.0) / q));
+    // t^2 = sigma / (4 ks^2 n^2), ks^2 = 4 kF / pi, kF = (3 pi^2 n)^(1/3)
+    const double c_t2 = M_PI / (16.0 * 3.0936677262801360);  // pi / (16 (3 pi^2)^(1/3))
+    const Dual t2 = c_t2 * (sg / ((n * n) * n13));
+    const Dual aa = (beta / gamma) * (dmk(1.0) / dexpm1((-1.0 / gamma) * ec));
+    const Dual f1 = t2 + aa * (t2 * t2);
+    const Dual f2 = (beta / gamma) * (f1 / (1.0 + aa * f1));
+    eps = eps + ec + gamma * dlog1p(f2);
+  }
+  return eps;
+}
+
+// w_j(G) = i G_j rho_hat(G) / N  (the 1/N of ifftn folded in)
+__global__ void k_gga_grad(GridGeom g, const cplx* __restrict__ rho_hat, cplx* __restrict__ w0,
+                           cplx* __restrict__ w1, cplx* __restrict__ w2) {
+  const double inv_n = 1.0 / (double)g.n;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < g.n;
+       i += (long long)gridDim.x * blockDim.x) {
+    double gx, gy, gz;
+    g_of(g, i, gx, gy, gz);
+    const cplx r = rho_hat[i];
+    const double a = -r.y * inv_n, b = r.x * inv_n;  // i * rho_hat / N
+    w0[i] = cmake(gx * a, gx * b);
+    w1[i] = cmake(gy * a, gy * b);
+    w2[i] = cmake(gz * a, gz * b);
+  }
+}
+
+// per grid point: sigma, eps, derivatives; vxc_loc = de/d rho (or eps), w_j <- de/d sigma * d_j
+__global__ void __launch_bounds__(RED_THREADS)
+k_gga_local(GridGeom g, const double* __restrict__ rho, int xc_id, int kohn_sham, int as_eps,
+            cplx* __restrict__ w0, cplx* __restrict__ w1, cplx* __restrict__ w2,
+            double* __restrict__ vxc_loc, double* __restrict__ partials) {
+  double acc[1] = {0.0};
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < g.n;
+       i += (long long)gridDim.x * blockDim.x) {
+    const double n = rho[i];
+    const cplx d0 = w0[i], d1 = w1[i], d2 = w2[i];
+    const double sigma = d0.x * d0.x + d0.y * d0.y + d1.x * d1.x + d1.y * d1.y + d2.x * d2.x +
+                         d2.y * d2.y;
+    const Dual e = pbe_eps(xc_id, n, sigma);
+    const double vrho = e.v + n * e.r, vsig = n * e.s;  // derivatives of n * eps
+    vxc_loc[i] = as_eps ? e.v : vrho;
+    const double f = as_eps ? 0.0 : vsig;
+    w0[i] = cmake(f * d0.x, f * d0.y);
+    w1[i] = cmake(f * d1.x, f * d1.y);
+    w2[i] = cmake(f * d2.x, f * d2.y);
+    // E_xc: rho eps; band mode integrates the potential (energy.py:204-211 with kohn_sham):
+    // sum rho v_xc = sum (rho de/d rho + 2 sigma de/d sigma)
+    acc[0] += kohn_sham ? (vrho * n + 2.0 * vsig * sigma) : e.v * n;
+  }
+  double out[1];
+  block_sum<1>(acc, out);
+  if (threadIdx.x == 0) partials[blockIdx.x * 4 + 2] = out[0] * g.vol / (double)g.n;
+}
+
+// grid(G) += -2 i sum_j G_j fftn(de/d sigma d_j)(G)
+__global__ void k_gga_add(GridGeom g, const cplx* __restrict__ w0, const cplx* __restrict__ w1,
+                          const cplx* __restrict__ w2, cplx* __restrict__ grid) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < g.n;
+       i += (long long)gridDim.x * blockDim.x) {
+    double gx, gy, gz;
+    g_of(g, i, gx, gy, gz);
+    const cplx a = w0[i], b = w1[i], c = w2[i];
+    const double re = gx * a.x + gy * b.x + gz * c.x, im = gx * a.y + gy * b.y + gz * c.y;
+    cplx v = grid[i];
+    v.x += 2.0 * im;
+    v.y -= 2.0 * re;
+    grid[i] = v;
+  }
+}
+
 // v_HE(r) (complex, already / N) + xc -> veff[s], E_xc partial sums.
 __global__ void __launch_bounds__(RED_THREADS)
 k_veff_xc(GridGeom g, const cplx* __restrict__ grid, const double* __restrict__ rho, int ns,
-          int xc_id, int kohn_sham, int parts, double* __restrict__ veff,
-          double* __restrict__ partials) {
+          int xc_id, int kohn_sham, int parts, const double* __restrict__ vxc_pre,
+          double* __restrict__ veff, double* __restrict__ partials) {
   // parts bit 2 = add the xc term; bit 3 = reference semantics: eps_xc unless kohn_sham
   // (xc.py:247-250), otherwise the functional derivative v_xc = eps + rho eps'
   const double xs = (parts & 4) ? 1.0 : 0.0;
@@ -269,7 +398,9 @@ k_veff_xc(GridGeom g, const cplx* __restrict__ grid, const double* __restrict__ 
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < g.n;
        i += (long long)gridDim.x * blockDim.x) {
     const double vhe = grid[i].x;
-    if (ns == 1) {
+    if (vxc_pre) {  // GGA: the local part comes from k_gga_local, the gradient part is in vhe
+      veff[i] = vhe + xs * vxc_pre[i];
+    } else if (ns == 1) {
       const double n = rho[i];
       double e, de;
       lda_eps(xc_id, n, e, de);
@@ -300,7 +431,7 @@ k_veff_xc(GridGeom g, const cplx* __restrict__ grid, const double* __restrict__ 
   }
   double out[1];
   block_sum<1>(acc, out);
-  if (threadIdx.x == 0) partials[blockIdx.x * 4 + 2] = out[0] * g.vol / (double)g.n;
+  if (threadIdx.x == 0 && !vxc_pre) partials[blockIdx.x * 4 + 2] = out[0] * g.vol / (double)g.n;
 }
 
 __global__ void k_reduce_partials(const double* __restrict__ partials, int nblocks, int ncomp,
@@ -316,12 +447,14 @@ __global__ void k_reduce_partials(const double* __restrict__ partials, int nbloc
 
 int launch_grid_potential(jrb_plan* p, const double* rho, int xc_id, int kohn_sham, int parts,
                           double* energies, double* veff, cudaStream_t st) {
-  if (xc_id != JRB_XC_LDA_X && xc_id != JRB_XC_LDA_X_C_PW) {
-    set_error("jrb_grid_potential: unsupported xc id (LDA only: lda_x, lda_x+lda_c_pw)");
+  const bool gga = xc_id == JRB_XC_GGA_X_PBE || xc_id == JRB_XC_GGA_PBE;
+  if (xc_id != JRB_XC_LDA_X && xc_id != JRB_XC_LDA_X_C_PW && !gga) {
+    set_error("jrb_grid_potential: unsupported xc id (lda_x, lda_x+lda_c_pw, gga_x_pbe, "
+              "gga_x_pbe+gga_c_pbe)");
     return JRB_EUNSUPPORTED;
   }
   if (p->ns == 2 && xc_id != JRB_XC_LDA_X) {
-    set_error("jrb_grid_potential: spin-polarised correlation is not implemented");
+    set_error("jrb_grid_potential: spin-polarised correlation / GGA is not implemented");
     return JRB_EUNSUPPORTED;
   }
   if (p->natoms <= 0) {
@@ -335,13 +468,31 @@ int launch_grid_potential(jrb_plan* p, const double* rho, int xc_id, int kohn_sh
   JRB_CHECK_LAUNCH("k_rho_to_complex");
   int rc = launch_fft3d_dense(p, p->d_grid, p->d_grid, JRB_FFT_FORWARD, 1, 1.0, st);
   if (rc) return rc;
+  const bool gga_on = gga && (parts & 4);
+  const bool as_eps = (parts & 8) && !kohn_sham;
+  cplx* w[3] = {p->d_gga, p->d_gga + p->ngrid, p->d_gga + 2 * p->ngrid};
+  if (gga_on) {
+    // gradient of rho from rho_hat (still in d_grid), then the local GGA sweep
+    k_gga_grad<<<blocks, RED_THREADS, 0, st>>>(g, p->d_grid, w[0], w[1], w[2]);
+    JRB_CHECK_LAUNCH("k_gga_grad");
+    if ((rc = launch_fft3d_dense(p, w[0], w[0], JRB_FFT_INVERSE, 3, 1.0, st))) return rc;
+    k_gga_local<<<blocks, RED_THREADS, 0, st>>>(g, rho, xc_id, kohn_sham, as_eps ? 1 : 0, w[0], w[1],
+                                               w[2], p->d_vxc, p->d_partials);
+    JRB_CHECK_LAUNCH("k_gga_local");
+    if (!as_eps)
+      if ((rc = launch_fft3d_dense(p, w[0], w[0], JRB_FFT_FORWARD, 3, 1.0, st))) return rc;
+  }
   k_hartree_ext<<<blocks, RED_THREADS, 0, st>>>(g, p->d_grid, p->d_vext, kohn_sham, parts,
                                                p->d_partials);
   JRB_CHECK_LAUNCH("k_hartree_ext");
+  if (gga_on && !as_eps) {
+    k_gga_add<<<blocks, RED_THREADS, 0, st>>>(g, w[0], w[1], w[2], p->d_grid);
+    JRB_CHECK_LAUNCH("k_gga_add");
+  }
   rc = launch_fft3d_dense(p, p->d_grid, p->d_grid, JRB_FFT_INVERSE, 1, 1.0 / (double)p->ngrid, st);
   if (rc) return rc;
-  k_veff_xc<<<blocks, RED_THREADS, 0, st>>>(g, p->d_grid, rho, p->ns, xc_id, kohn_sham, parts, veff,
-                                           p->d_partials);
+  k_veff_xc<<<blocks, RED_THREADS, 0, st>>>(g, p->d_grid, rho, p->ns, xc_id, kohn_sham, parts,
+                                           gga ? p->d_vxc : nullptr, veff, p->d_partials);
   JRB_CHECK_LAUNCH("k_veff_xc");
   if (energies) {
     k_reduce_partials<<<1, 96, 0, st>>>(p->d_partials, blocks, 3, energies);

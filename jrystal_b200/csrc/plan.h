@@ -80,6 +80,8 @@ struct jrb_plan {
   jrb::cplx* d_vext;      // [ngrid] V_ext(G) incl. the reference's -N/Omega factor
   double* d_partials;     // block partial sums for the grid reductions
   double* d_veff;         // [ns][ngrid] effective potential of the fused evaluation
+  jrb::cplx* d_gga;       // [3][ngrid] gradient components of rho (GGA); null on an orbital-grid child
+  double* d_vxc;          // [ngrid] local part of the GGA potential
   int n_partial_blocks;
   int natoms;
   double *d_pos, *d_chg;   // atoms of the last jrb_set_atoms (position gradient of E_ext)

@@ -245,7 +245,7 @@ class Plan:
       raise RuntimeError('call set_atoms(positions, charges) first')
     self._chk(rho, (self.ns, self.nx, self.ny, self.nz), torch.float64, 'density')
     if xc not in _lib.XC_IDS:
-      raise NotImplementedError(f'xc "{xc}" is not implemented (LDA only: {list(_lib.XC_IDS)})')
+      raise NotImplementedError(f'xc "{xc}" is not implemented (implemented: {list(_lib.XC_IDS)})')
     if out is None:
       en = self._new((3,), torch.float64)
       veff = self._new((self.ns, self.nx, self.ny, self.nz), torch.float64)
@@ -262,7 +262,7 @@ class Plan:
       raise RuntimeError('call set_atoms(positions, charges) first')
     self._chk(rho, (self.ns, self.nx, self.ny, self.nz), torch.float64, 'density')
     if xc not in _lib.XC_IDS:
-      raise NotImplementedError(f'xc "{xc}" is not implemented (LDA only: {list(_lib.XC_IDS)})')
+      raise NotImplementedError(f'xc "{xc}" is not implemented (implemented: {list(_lib.XC_IDS)})')
     v = self._new((self.ns, self.nx, self.ny, self.nz), torch.float64)
     _lib.check(self.lib.jrb_potential(self._h, _ptr(rho), _lib.XC_IDS[xc], int(bool(kohn_sham)),
                                       int(parts), _ptr(v), _stream()))
@@ -332,7 +332,7 @@ class Plan:
     if not self._atoms:
       raise RuntimeError('call set_atoms(positions, charges) first')
     if xc not in _lib.XC_IDS:
-      raise NotImplementedError(f'xc "{xc}" is not implemented (LDA only: {list(_lib.XC_IDS)})')
+      raise NotImplementedError(f'xc "{xc}" is not implemented (implemented: {list(_lib.XC_IDS)})')
     if out is None:
       energies = self._new((4,), torch.float64)
       g_re = self._new(self.sphere_shape, torch.float64)

@@ -164,3 +164,40 @@ def test_occupation_and_entropy():
   f = torch.tensor([[[2.0, 1.0]]], dtype=torch.float64)
   expect = -(2 * np.log(2 + 1e-8) + 0 * np.log(1e-8) + 1 * np.log(1 + 1e-8) + 1 * np.log(1 + 1e-8))
   assert abs(rp.entropy_fermi_dirac(f).item() - expect) < 1e-12
+
+
+def test_pbe_known_values():
+  """Pins of the GGA restatement (the arithmetic lives in jax_xc / LibXC, not vendored): the
+  published enhancement factor F_x(s) = 1 + kappa - kappa / (1 + mu s^2 / kappa) (Perdew, Burke,
+  Ernzerhof 1996, eq. 14), the uniform-gas limits (sigma = 0: PBE x -> LDA x, PBE c -> PW92), and
+  the PW92 correlation energy at r_s = 2 (-0.0448 Ha, Perdew-Wang 1992 table I)."""
+  rho = torch.tensor([0.3, 1e-3, 2.5], dtype=torch.float64)
+  zero = torch.zeros_like(rho)
+  assert torch.allclose(rp._eps_gga_x_pbe(rho, zero), rp._eps_lda_x(rho), rtol=1e-14)
+  ec0 = rp._eps_gga_c_pbe(rho, zero)
+  pw = rp._eps_lda_c_pw(rho)  # PW92 with the 1992 parameter digits: differs from pw_mod by ~1e-6
+  assert torch.allclose(ec0, pw, rtol=2e-5)
+  kf = (3 * np.pi**2 * rho)**(1 / 3)
+  for s_ in (0.5, 1.0, 2.0):
+    sigma = (2 * kf * rho * s_)**2
+    fx = rp._eps_gga_x_pbe(rho, sigma) / rp._eps_lda_x(rho)
+    want = 1 + 0.804 - 0.804 / (1 + 0.2195149727645171 * s_**2 / 0.804)
+    assert torch.allclose(fx, torch.full_like(fx, want), rtol=1e-13)
+  rs2 = torch.tensor([3.0 / (4 * np.pi * 2.0**3)], dtype=torch.float64)
+  assert abs(rp._eps_gga_c_pbe(rs2, torch.zeros(1, dtype=torch.float64)).item() + 0.0448) < 1e-4
+  # gradient correction H >= 0 and -> -eps_c^PW for t -> infinity (correlation vanishes)
+  big = rp._eps_gga_c_pbe(rho, torch.full_like(rho, 1e12))
+  assert torch.all(big.abs() < 1e-3 * ec0.abs())
+
+
+def test_gga_energy_gradient_finite_difference():
+  s = rp.System.from_name('diamond', 9, [1, 1, 1], 8.0)
+  p = rp.param_init(3, 4, s.num_k, s.mask)
+  occ = rp.occupation_uniform(s.num_k, s.num_electrons, num_bands=4).numpy()
+  xc = 'gga_x_pbe+gga_c_pbe'
+  ref = rp.energy_and_grad(s, p['w_re'], p['w_im'], occ, xc=xc)
+  d = np.random.default_rng(1).standard_normal(p['w_re'].shape)
+  h = 1e-5
+  ep = rp.energy_and_grad(s, p['w_re'] + h * d, p['w_im'], occ, xc=xc)['e_tot']
+  em = rp.energy_and_grad(s, p['w_re'] - h * d, p['w_im'], occ, xc=xc)['e_tot']
+  assert abs((ep - em) / (2 * h) - (ref['g_re'] * d).sum()) < 1e-6 * abs((ref['g_re'] * d).sum())
