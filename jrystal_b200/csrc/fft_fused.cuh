@@ -49,6 +49,10 @@ struct FusedArgs {
 #define JRB_SPARSE_M(m) ((m) < 2 || (m) >= 6)
 
 constexpr int fused_slots(int tpl) {
+  // 81-point lines (9 threads each): 6 slots = 432 threads.  The slots of this length are not
+  // whole warps, so the exchanges use CTA-wide barriers either way; six slots cover the 5 line
+  // groups of the y stage in one round and the 11 of the x stage in two (four slots: 2 + 3 rounds)
+  if (tpl == 9) return 6;
   int s = 256 / (NB * tpl);
   if (s < 1) s = 1;
   while ((NB * tpl * s) % 32 != 0) ++s;
