@@ -724,9 +724,11 @@ def run_b200(args):
   # sphere data its true size), per GPU -------------------------------------------------------
   m_local = (k1 - k0) * (b1 - b0)
   peak, peak_src = measured_peak()
-  # dominant kernel group: the H-apply sweep k_z_inv_scatter + k_yx_vmul + k_z_fwd_gather
-  # (k_yx_vmul alone is ~45 % of the step, profiles/); it performs the backward dense transform
-  # of every orbital and reads Q / writes HQ on the sphere
+  # dominant kernel group: the H-apply sweep k_yx_vmul + k_z_fwd_gather on the z-transformed
+  # columns kept from the density sweep (k_yx_vmul alone is ~37 % of the step, profiles/); it
+  # performs the backward dense transform of every orbital and reads Q / writes HQ on the sphere.
+  # The algorithmic bytes are the contract figure of SURVEY 8d on the reference's own grid N,
+  # whatever box the orbitals are transformed on (config.orbital_grid).
   happly_bytes = m_local * (32.0 * ngrid + 32.0 * ng)
   happly_achieved = happly_bytes / (phases['hpsi'] * 1e-3) / 1e9
   bytes_alg = 64.0 * m_local * (ngrid + ng)
@@ -744,14 +746,15 @@ def run_b200(args):
   roofline = {
     'bound': 'hbm', 'achieved': happly_achieved, 'peak': peak, 'unit': 'GB/s',
     'frac': happly_achieved / peak, 'traffic': traffic, 'peak_source': peak_src,
-    'kernel': 'H-apply sweep (k_z_inv_scatter + k_yx_vmul + k_z_fwd_gather; k_yx_vmul is the '
+    'kernel': 'H-apply sweep (k_yx_vmul + k_z_fwd_gather on the kept z columns; k_yx_vmul is the '
               'dominant kernel)',
     'bytes_per_launch': happly_bytes,
     'bytes_formula': 'M*(32*N + 32*ng): one dense transform (read+write of the box) per orbital '
                      '+ Q read + HQ write, SURVEY 8d',
     'ms_per_launch': phases['hpsi'],
-    'note': 'the sweep keeps psi(r) in shared memory, so it is bound by FP64 issue + the smem '
-            'exchange (see DESIGN.md), measured DRAM traffic is far below the algorithmic bytes',
+    'note': 'the sweep keeps psi(r) in shared memory and runs on the alias-free orbital box, so '
+            'it is bound by FP64 issue + the smem exchange (see DESIGN.md); measured DRAM traffic '
+            'is far below the algorithmic bytes of the reference grid',
     'whole_evaluation': {'achieved': whole_achieved, 'frac': whole_achieved / peak,
                          'bytes': '64*M*(N+ng)'},
     'fft_density_path': {'ms': fft_ms, 'achieved': fft_bytes / (fft_ms * 1e-3) / 1e9,

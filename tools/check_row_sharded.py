@@ -33,7 +33,7 @@ plan.set_atoms(s.positions, s.charges)
 occ_d = dev(occ)
 rho, e_kin = plan.eval_begin(dev(w_re), dev(w_im), occ_d)
 en, g_re, g_im, _ = plan.eval_finish(occ_d, rho, e_kin, 'lda_x')
-ev = RowShardedEvaluator(s.cell, s.mask, s.kpts, nb, s.positions, s.charges)
+ev = RowShardedEvaluator(s.cell, s.mask, s.kpts, nb, s.positions, s.charges, orbital_grid='auto')
 g0, g1 = ev.g0, ev.g1
 en2, g_re2, g_im2, rho2 = ev.evaluate(dev(w_re[:, :, g0:g1]), dev(w_im[:, :, g0:g1]), occ_d)
 ev.rows.check_status()
