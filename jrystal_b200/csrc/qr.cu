@@ -58,7 +58,9 @@ k_gram_reduce(const cplx* __restrict__ partial, int nchunks, int nb, cplx* __res
 // On exit the lower triangle of S holds L and Rt = L^H (upper triangular, zeros below).
 // dynamic smem: panel [nb][PB + 1] + stage [nb][KC + 1] complex
 __global__ void __launch_bounds__(CHOL_T)
-k_chol_blocked(cplx* __restrict__ S, cplx* __restrict__ Rt, int nb, int* __restrict__ fail_flag) {
+k_chol_blocked(cplx* __restrict__ S, cplx* __restrict__ Rt, int nb, int* __restrict__ fail_flag,
+               const int* __restrict__ skip) {
+  if (skip && skip[blockIdx.x]) return;  // factor already written by k_near_identity
   extern __shared__ __align__(16) unsigned char smem_raw_[];
   cplx* P = reinterpret_cast<cplx*>(smem_raw_);     // [rows][PB + 1]
   cplx* T = P + (size_t)nb * (CHOL_PB + 1);         // [rows][KC + 1]
@@ -141,7 +143,9 @@ k_chol_blocked(cplx* __restrict__ S, cplx* __restrict__ Rt, int nb, int* __restr
 // inverse (columns are independent), back substitution with the column kept in shared memory.
 // grid: (ceil(nb / 8), nsk), block 256; dynamic smem: 8 * nb complex
 __global__ void __launch_bounds__(256)
-k_tri_inv_cols(const cplx* __restrict__ R, int nb, cplx* __restrict__ Rinv) {
+k_tri_inv_cols(const cplx* __restrict__ R, int nb, cplx* __restrict__ Rinv,
+               const int* __restrict__ skip) {
+  if (skip && skip[blockIdx.y]) return;
   extern __shared__ __align__(16) unsigned char smem_raw_[];
   const long long nn = (long long)nb * nb;
   R += blockIdx.y * nn;
@@ -193,7 +197,9 @@ constexpr int CP = 32;        // panel width == tile height
 constexpr int CP_LD = CP + 1;
 constexpr int CP_SMEM = 4 * CP * CP_LD * (int)sizeof(cplx);  // D, T, Ld, Lr
 __global__ void __launch_bounds__(256)
-k_chol_panel(cplx* __restrict__ S, cplx* __restrict__ Rt, int nb, int p0, int* __restrict__ fail_flag) {
+k_chol_panel(cplx* __restrict__ S, cplx* __restrict__ Rt, int nb, int p0, int* __restrict__ fail_flag,
+             const int* __restrict__ skip) {
+  if (skip && skip[blockIdx.y]) return;
   extern __shared__ __align__(16) unsigned char smem_raw_[];
   cplx* D = reinterpret_cast<cplx*>(smem_raw_);
   cplx* T = D + CP * CP_LD;
@@ -327,7 +333,9 @@ k_chol_panel(cplx* __restrict__ S, cplx* __restrict__ Rt, int nb, int p0, int* _
 // Blocked inverse of an upper-triangular R, step 1: the 32 x 32 diagonal blocks (one thread per
 // column, the block staged in shared memory).   grid: (ceil(nb / 32), nsk), block 32
 __global__ void __launch_bounds__(32)
-k_tri_inv_diag(const cplx* __restrict__ R, int nb, cplx* __restrict__ Rinv) {
+k_tri_inv_diag(const cplx* __restrict__ R, int nb, cplx* __restrict__ Rinv,
+               const int* __restrict__ skip) {
+  if (skip && skip[blockIdx.y]) return;
   __shared__ cplx U[CP * CP_LD], X[CP * CP_LD];
   const long long nn = (long long)nb * nb;
   R += blockIdx.y * nn;
@@ -366,7 +374,9 @@ k_tri_inv_diag(const cplx* __restrict__ R, int nb, cplx* __restrict__ Rinv) {
 // grid: (4 * ceil(nb / 32), nsk), block 256 = 32 rows x 8 columns;
 // dynamic smem: (ceil(nb / 32) * 32) x 8 complex (the CTA's columns of X)
 __global__ void __launch_bounds__(256)
-k_tri_inv_offdiag(const cplx* __restrict__ R, int nb, cplx* __restrict__ Rinv) {
+k_tri_inv_offdiag(const cplx* __restrict__ R, int nb, cplx* __restrict__ Rinv,
+                  const int* __restrict__ skip) {
+  if (skip && skip[blockIdx.y]) return;
   extern __shared__ __align__(16) unsigned char smem_raw_[];
   cplx* Xc = reinterpret_cast<cplx*>(smem_raw_);  // [rows][8]
   __shared__ cplx A[CP * CP_LD], Y[CP * 8];
@@ -415,6 +425,57 @@ k_tri_inv_offdiag(const cplx* __restrict__ R, int nb, cplx* __restrict__ Rinv) {
     }
     Xc[(I * CP + r) * 8 + c] = out;
     if (col_ok) Rinv[(long long)(I * CP + r) * nb + col] = out;
+  }
+}
+
+
+// Second Cholesky-QR pass: S = Q1^H Q1 = I + E with |E| ~ kappa(W)^2 eps.  For |E|_max < tol the
+// factor is written in closed form, R = I + U, R^-1 = I - U + U^2 - ... with U = up(E) + diag(E)/2:
+// R^H R = I + E + U^H U, so the neglected terms are O(nb |E|^2) < 1e-17 for tol = 1e-10, below
+// the rounding of the factorisation it replaces (one launch instead of the 9 of the panel
+// Cholesky + blocked inverse at nb = 208).  skip[sk] tells the regular kernels to stand down.
+// grid: (nsk), block 256
+__global__ void __launch_bounds__(256)
+k_near_identity(const cplx* __restrict__ S, int nb, double tol, cplx* __restrict__ Rt,
+                cplx* __restrict__ Rit, int* __restrict__ skip) {
+  __shared__ double red[8];
+  __shared__ int ok;
+  const long long nn = (long long)nb * nb;
+  S += blockIdx.x * nn;
+  Rt += blockIdx.x * nn;
+  Rit += blockIdx.x * nn;
+  double m = 0.0;
+  for (long long e = threadIdx.x; e < nn; e += 256) {
+    const int i = (int)(e / nb), j = (int)(e % nb);
+    const cplx v = S[e];
+    m = fmax(m, fmax(fabs(v.x - (i == j ? 1.0 : 0.0)), fabs(v.y)));
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int w = 0; w < 8; ++w) t = fmax(t, red[w]);
+    ok = (t < tol) ? 1 : 0;   // NaN compares false: the regular path reports it
+    skip[blockIdx.x] = ok;
+  }
+  __syncthreads();
+  if (!ok) return;
+  for (long long e = threadIdx.x; e < nn; e += 256) {
+    const int i = (int)(e / nb), j = (int)(e % nb);
+    cplx r = cmake(0.0, 0.0), ri = cmake(0.0, 0.0);
+    if (j > i) {
+      const cplx u = S[e];
+      r = u;
+      ri = cmake(-u.x, -u.y);
+    } else if (j == i) {
+      const double u = 0.5 * (S[e].x - 1.0);
+      r = cmake(1.0 + u, 0.0);
+      ri = cmake(1.0 - u + u * u, 0.0);
+    }
+    Rt[e] = r;
+    Rit[e] = ri;
   }
 }
 
@@ -620,19 +681,21 @@ static bool multi_cta_small(int nb, int nsk) {
 }
 
 // Rinv = R^-1 (upper triangular)
-static int tri_inverse(const cplx* R, int nb, int nsk, cplx* Rinv, cudaStream_t st) {
+static int tri_inverse(const cplx* R, int nb, int nsk, cplx* Rinv, cudaStream_t st,
+                       const int* skip = nullptr) {
   if (multi_cta_small(nb, nsk)) {
     const int nblk = (nb + CP - 1) / CP;
-    k_tri_inv_diag<<<dim3(nblk, nsk), 32, 0, st>>>(R, nb, Rinv);
+    k_tri_inv_diag<<<dim3(nblk, nsk), 32, 0, st>>>(R, nb, Rinv, skip);
     JRB_CHECK_LAUNCH("k_tri_inv_diag");
     static int once = opt_in_smem(k_tri_inv_offdiag, 160 * 1024);
     if (once) return once;
-    k_tri_inv_offdiag<<<dim3(4 * nblk, nsk), 256, nblk * CP * 8 * (int)sizeof(cplx), st>>>(R, nb, Rinv);
+    k_tri_inv_offdiag<<<dim3(4 * nblk, nsk), 256, nblk * CP * 8 * (int)sizeof(cplx), st>>>(R, nb, Rinv,
+                                                                                    skip);
     JRB_CHECK_LAUNCH("k_tri_inv_offdiag");
     return 0;
   }
   dim3 igrid((nb + 7) / 8, nsk);
-  k_tri_inv_cols<<<igrid, 256, 8 * nb * (int)sizeof(cplx), st>>>(R, nb, Rinv);
+  k_tri_inv_cols<<<igrid, 256, 8 * nb * (int)sizeof(cplx), st>>>(R, nb, Rinv, skip);
   JRB_CHECK_LAUNCH("k_tri_inv_cols");
   return 0;
 }
@@ -646,7 +709,8 @@ static int reduce_gram(jrb_plan* p, int nsk, int nchunks, cplx* S, cudaStream_t 
 }
 
 // S (Hermitian, destroyed) -> Rt = chol(S)^H, Rit = Rt^-1
-static int chol_and_inverse(jrb_plan* p, int nsk, cplx* S, cplx* Rt, cplx* Rit, cudaStream_t st) {
+static int chol_and_inverse(jrb_plan* p, int nsk, cplx* S, cplx* Rt, cplx* Rit, cudaStream_t st,
+                            const int* skip = nullptr) {
   const int nb = p->nb;
   int* fail = reinterpret_cast<int*>(p->d_scal + 32);
   if (multi_cta_small(nb, nsk)) {
@@ -655,10 +719,10 @@ static int chol_and_inverse(jrb_plan* p, int nsk, cplx* S, cplx* Rt, cplx* Rit, 
       dim3 grid(1 + (below + CP - 1) / CP, nsk);
       static int once = opt_in_smem(k_chol_panel, CP_SMEM);
       if (once) return once;
-      k_chol_panel<<<grid, 256, CP_SMEM, st>>>(S, Rt, nb, p0, fail);
+      k_chol_panel<<<grid, 256, CP_SMEM, st>>>(S, Rt, nb, p0, fail, skip);
       JRB_CHECK_LAUNCH("k_chol_panel");
     }
-    return tri_inverse(Rt, nb, nsk, Rit, st);
+    return tri_inverse(Rt, nb, nsk, Rit, st, skip);
   }
   const int smem = nb * (CHOL_PB + 1 + CHOL_KC + 1) * (int)sizeof(cplx);
   static int once = opt_in_smem(k_chol_blocked, 200 * 1024);
@@ -667,9 +731,9 @@ static int chol_and_inverse(jrb_plan* p, int nsk, cplx* S, cplx* Rt, cplx* Rit, 
     set_error("Cholesky panel does not fit shared memory (too many bands)");
     return JRB_EUNSUPPORTED;
   }
-  k_chol_blocked<<<nsk, CHOL_T, smem, st>>>(S, Rt, nb, fail);
+  k_chol_blocked<<<nsk, CHOL_T, smem, st>>>(S, Rt, nb, fail, skip);
   JRB_CHECK_LAUNCH("k_chol_blocked");
-  return tri_inverse(Rt, nb, nsk, Rit, st);
+  return tri_inverse(Rt, nb, nsk, Rit, st, skip);
 }
 
 // Cholesky-QR2 of the (spin,k) range [sk0, sk0 + nsk), in phases so that a row-sharded caller can
@@ -720,7 +784,15 @@ int launch_qr_apply_phase(jrb_plan* p, int sk0, int nsk, const double* w_re, con
                         reinterpret_cast<double*>(q.tmp), nullptr, st);
   }
   TallMat Q1{reinterpret_cast<const double*>(q.tmp), nullptr, nb};
-  if ((rc = chol_and_inverse(p, nsk, S, q.Rt, q.Rit, st))) return rc;
+  const char* no_shortcut = std::getenv("JRB_NO_QR_SHORTCUT");
+  const bool shortcut = !(no_shortcut && std::atoi(no_shortcut) != 0);
+  const int* skip = nullptr;
+  if (shortcut) {
+    k_near_identity<<<nsk, 256, 0, st>>>(S, nb, 1e-10, q.Rt, q.Rit, p->d_skip + sk0);
+    JRB_CHECK_LAUNCH("k_near_identity");
+    skip = p->d_skip + sk0;
+  }
+  if ((rc = chol_and_inverse(p, nsk, S, q.Rt, q.Rit, st, skip))) return rc;
   const long long nn = (long long)nb * nb;
   dim3 egrid((unsigned)((nn + SMALL_T - 1) / SMALL_T), nsk);
   k_tri_compose<<<egrid, SMALL_T, 0, st>>>(q.Rt, q.Rit, q.R1, q.R1inv, nb, r + q.moff, q.rinv);

@@ -417,3 +417,34 @@ def test_errors(cuda_device):
   with pytest.raises(ValueError):
     plan.density(torch.zeros((1, 1, 3, 4), dtype=torch.complex128, device='cuda'),
                  torch.zeros((1, 1, 4), dtype=torch.float64, device='cuda'))
+
+
+@pytest.mark.parametrize('shortcut', ['on', 'off'])
+@pytest.mark.parametrize('kind', ['random', 'near_dependent'])
+@pytest.mark.parametrize('case', ['si_32', 'si8_32_nb130'])
+def test_qr_second_pass_paths(cuda_device, case, kind, shortcut, monkeypatch):
+  """Second Cholesky-QR pass: the closed-form factor of I + E (|E| < 1e-10: well-conditioned
+  parameters) and the regular factorisation (nearly dependent columns push |E| above the
+  threshold; JRB_NO_QR_SHORTCUT=1 forces it) must both give W = Q R with orthonormal Q."""
+  monkeypatch.setenv('JRB_NO_QR_SHORTCUT', '1' if shortcut == 'off' else '0')
+  s, plan, w_re, w_im, occ = _setup(case)
+  if kind == 'near_dependent':
+    rng = np.random.default_rng(9)
+    w_re = w_re.copy()
+    w_im = w_im.copy()
+    w_re[..., 1] = w_re[..., 0] + 3e-5 * rng.standard_normal(w_re[..., 0].shape)
+    w_im[..., 1] = w_im[..., 0] + 3e-5 * rng.standard_normal(w_im[..., 0].shape)
+  q, r = plan.qr_fwd(to_dev(w_re), to_dev(w_im))
+  plan.check_status()
+  q = q.cpu()
+  r = r.cpu()
+  w = torch.from_numpy(w_re + 1j * w_im)
+  nb = w.shape[-1]
+  eye = torch.eye(nb, dtype=torch.complex128)
+  orth = (q.conj().transpose(-1, -2) @ q - eye).abs().max().item()
+  rec = ((q @ r) - w).abs().max().item() / w.abs().max().item()
+  assert orth < 5e-13, orth
+  # the composed R = R2 R1 of a matrix with kappa ~ 1e5 carries eps * kappa-sized relative errors
+  assert rec < (1e-13 if kind == 'random' else 1e-11), rec
+  assert (torch.diagonal(r, dim1=-2, dim2=-1).real > 0).all()
+  assert torch.tril(r, -1).abs().max().item() == 0.0
