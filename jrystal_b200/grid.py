@@ -93,3 +93,40 @@ def estimate_max_cutoff_energy(cell_vectors, mask):
   """grid.py:328-349."""
   g = g_vectors(cell_vectors, mask.shape)
   return float(np.max(np.linalg.norm(g, axis=-1)**2 / 2 * mask))
+
+
+# axis lengths whose two-stage line plan is square-ish (few elements per thread, 3-4 resident CTAs
+# in the z passes); measured on B200, profiles/r01_orbital_grid.md
+ORBITAL_Z_LENGTHS = (7, 8, 9, 12, 16, 24, 32, 49, 64, 81, 100, 128)
+
+
+def min_orbital_grid(freq_mask) -> tuple:
+  """Smallest alias-free box of the per-orbital FFTs, 4 gmax + 1 per axis: psi carries the
+  frequencies of the mask (|f| <= gmax), |psi|^2 and the sphere part of v_eff psi twice that."""
+  mask = np.asarray(freq_mask).astype(bool)
+  out = []
+  for ax in range(3):
+    n = mask.shape[ax]
+    idx = np.nonzero(mask.any(axis=tuple(a for a in range(3) if a != ax)))[0]
+    f = np.where(idx < (n + 1) // 2, idx, idx - n)
+    out.append(4 * int(np.abs(f).max()) + 1)
+  return tuple(out)
+
+
+def orbital_grid_candidates(full, need) -> list:
+  """Boxes `orbital_grid='auto'` tries, best first; the last one never depends on the fused plane
+  kernels being available.  z (the axis the fused y+x kernels loop over) shrinks to the smallest
+  light line length >= need; x and y keep the grid's lengths except 128 -> 81 (fused 81 x 81
+  kernels); grids below 48^3 are launch-latency bound and left alone."""
+  full = tuple(int(v) for v in full)
+  need = tuple(int(v) for v in need)
+  if any(m > n for m, n in zip(need, full)):
+    raise ValueError(f'the grid {full} aliases: it needs at least {need}')
+  if full[0] * full[1] * full[2] < 48**3:
+    return [full]
+  nz = min([n for n in ORBITAL_Z_LENGTHS if need[2] <= n <= full[2]] or [full[2]])
+  out = []
+  if full[0] == full[1] == 128 and max(need[:2]) <= 81:
+    out.append((81, 81, nz))
+  out.append((full[0], full[1], nz))
+  return out

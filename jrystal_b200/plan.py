@@ -67,15 +67,8 @@ class Plan:
     axis the fused y+x plane kernels loop over, shrinks to the smallest length >= 4 gmax + 1 with
     a light line plan; x and y keep the plan's lengths (the fused kernels are tuned for 64 and
     128) except 128 -> 81 when that fits and the fused 81 x 81 kernels have the shared memory."""
-    need = self.min_orbital_grid
-    full = (self.nx, self.ny, self.nz)
-    if self.ngrid < 48 ** 3:  # launch-latency bound sizes: the resampling launches cost more
-      return [full]
-    nz = min([n for n in _lib.AUTO_Z_LENGTHS if need[2] <= n <= full[2]] or [full[2]])
-    nxy = [(full[0], full[1])]
-    if full[0] == full[1] == 128 and max(need[:2]) <= 81:
-      nxy.insert(0, (81, 81))
-    return [(a, b, nz) for a, b in nxy]
+    from .grid import orbital_grid_candidates
+    return orbital_grid_candidates((self.nx, self.ny, self.nz), self.min_orbital_grid)
 
   def set_orbital_grid(self, dims):
     """Run the per-orbital transforms on a smaller alias-free box (jrb_plan_set_orbital_grid);

@@ -241,3 +241,27 @@ def test_trainable_occupations_match_the_literal_restatement():
   refi = rp.occupation_idempotent(ip['param_up']['w_re'], ip['param_down']['w_re'], nk)
   assert float((oi - refi).abs().max()) < 1e-13 and abs(float(oi.sum()) - ne) < 1e-10
   assert float(oi.min()) >= 0 and float(oi.max()) <= 2.0 / nk + 1e-12
+
+
+def test_orbital_grid_selection():
+  """Host logic of orbital_grid='auto' (no GPU): alias-free minimum from the mask and the boxes
+  tried, for the benchmark geometries."""
+  from jrystal_b200 import grid
+  from jrystal_b200.crystal import Crystal
+  si8 = Crystal.create_builtin('si8')
+  mask = grid.spherical_mask(si8.cell_vectors, [64, 64, 64], 30.0)
+  need = grid.min_orbital_grid(mask)
+  assert need == (49, 49, 49)
+  assert grid.orbital_grid_candidates((64, 64, 64), need) == [(64, 64, 49)]
+  # diamond-64 at 40 Ha on 128^3: 4 * 19 + 1 = 77 -> fused 81^3 first, z-only fallback
+  assert grid.orbital_grid_candidates((128, 128, 128), (77, 77, 77)) == [(81, 81, 81), (128, 128, 81)]
+  assert grid.orbital_grid_candidates((128, 128, 128), (85, 85, 85)) == [(128, 128, 100)]
+  assert grid.orbital_grid_candidates((128, 128, 128), (105, 105, 105)) == [(128, 128, 128)]
+  # small grids are left alone; a grid that aliases is an error
+  assert grid.orbital_grid_candidates((32, 32, 32), (21, 21, 21)) == [(32, 32, 32)]
+  with pytest.raises(ValueError):
+    grid.orbital_grid_candidates((48, 48, 48), (49, 49, 49))
+  # anisotropic mask: per-axis minimum
+  m = np.zeros((16, 24, 32), dtype=bool)
+  m[0, 0, 0] = m[2, 0, 0] = m[-1, 3, 0] = m[0, -5, 7] = True
+  assert grid.min_orbital_grid(m) == (9, 21, 29)
