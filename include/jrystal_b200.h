@@ -84,8 +84,10 @@ int64_t jrb_plan_workspace_bytes(const jrb_plan* plan);
  * rho is brought to the plan's grid by Fourier interpolation and v_eff to the orbital grid by
  * Fourier truncation, so every result is the reference's to rounding (tests/test_gpu_parity.py::
  * test_orbital_grid*).  Everything else (grids in the arguments, XC, Hartree, jrb_fft3d,
- * jrb_wave_grid) keeps the plan's own grid.  Fails with JRB_EINVAL if an axis violates
- * 4 gmax + 1 <= n_w <= n, JRB_EUNSUPPORTED without a compiled line length.  Allocates (set-up). */
+ * jrb_wave_grid) keeps the plan's own grid.  Fails with JRB_EINVAL if a RESIZED axis violates
+ * 4 gmax + 1 <= n_w < n (an axis left at n is always accepted: where the caller's own grid is too
+ * coarse it aliases exactly as the reference does), JRB_EUNSUPPORTED without a compiled line
+ * length.  Allocates (set-up). */
 int jrb_plan_set_orbital_grid(jrb_plan* plan, int32_t nxw, int32_t nyw, int32_t nzw);
 /* dims[3] = the box the per-orbital passes currently run on / the smallest alias-free box */
 int jrb_plan_orbital_grid(const jrb_plan* plan, int32_t* dims);

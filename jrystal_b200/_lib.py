@@ -14,9 +14,6 @@ FFT_FORWARD, FFT_INVERSE = -1, 1
 LINE_LENGTHS = (7, 8, 9, 12, 16, 24, 32, 40, 45, 48, 49, 50, 54, 56, 60, 64, 72, 80, 81, 90, 96,
                 100, 112, 128)
 FUSED_LENGTHS = (7, 8, 9, 12, 16, 24, 32, 48, 49, 64, 72, 81, 96, 128)
-# lengths whose two-stage line plan is square-ish (few elements per thread, 3-4 resident CTAs in
-# the z passes): what orbital_grid='auto' chooses from
-AUTO_Z_LENGTHS = (7, 8, 9, 12, 16, 24, 32, 49, 64, 81, 100, 128)
 
 
 class PlanDesc(ctypes.Structure):

@@ -537,12 +537,17 @@ __global__ void k_resample(const cplx* __restrict__ src, int sx, int sy, int sz,
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
        i += (long long)gridDim.x * blockDim.x) {
     const int z = (int)(i % dz), y = (int)((i / dz) % dy), x = (int)(i / ((long long)dz * dy));
+    // an axis both boxes share is copied bin by bin (Nyquist included: a grid the caller chose too
+    // coarse aliases there exactly as the reference does); a resized axis keeps 2|f| < min(n)
     const int fx = fftfreq_int(x, dx), fy = fftfreq_int(y, dy), fz = fftfreq_int(z, dz);
     const int mx = min(sx, dx), my = min(sy, dy), mz = min(sz, dz);
+    const bool okx = sx == dx || 2 * abs(fx) < mx, oky = sy == dy || 2 * abs(fy) < my,
+               okz = sz == dz || 2 * abs(fz) < mz;
     cplx v = cmake(0.0, 0.0);
-    if (2 * abs(fx) < mx && 2 * abs(fy) < my && 2 * abs(fz) < mz) {
-      const int px = fx >= 0 ? fx : fx + sx, py = fy >= 0 ? fy : fy + sy,
-                pz = fz >= 0 ? fz : fz + sz;
+    if (okx && oky && okz) {
+      const int px = sx == dx ? x : (fx >= 0 ? fx : fx + sx);
+      const int py = sy == dy ? y : (fy >= 0 ? fy : fy + sy);
+      const int pz = sz == dz ? z : (fz >= 0 ? fz : fz + sz);
       const cplx t = src[((long long)px * sy + py) * sz + pz];
       v = cmake(t.x * scale, t.y * scale);
     }

@@ -455,7 +455,8 @@ extern "C" int jrb_plan_set_orbital_grid(jrb_plan* p, int32_t nxw, int32_t nyw, 
     return 0;
   }
   for (int c = 0; c < 3; ++c) {
-    if (nw[c] > n[c] || nw[c] < 4 * p->gmax[c] + 1) {
+    // an unchanged axis is always allowed (if the caller's grid aliases there, so does the reference)
+    if (nw[c] != n[c] && (nw[c] > n[c] || nw[c] < 4 * p->gmax[c] + 1)) {
       set_error("jrb_plan_set_orbital_grid: axis " + std::to_string(c) + " needs 4*gmax+1 = " +
                 std::to_string(4 * p->gmax[c] + 1) + " <= n_w <= " + std::to_string(n[c]) +
                 ", got " + std::to_string(nw[c]));

@@ -136,13 +136,17 @@ k_gram(TallMat A, TallMat B, int same, long long ng, int nb, long long sk_stride
   }
   const int lofs = lc * QLDB + lr;
 
-  // panel elements of this thread: e = tid + 256 q -> (row e / 72, col e % 72), fixed per thread
+  // panel elements of this thread: e = tid + 256 q -> (row e / pw, col e % pw), fixed per thread.
+  // pw = the panel columns any block of this CTA reads (whole 8-column blocks): with few bands
+  // (nb = 15 ... 32) a 72-wide panel would be 55-80 % zero-fill copies, and the copy instructions,
+  // not the DMMAs, bound the stage (measured: the same 4.4 us per 16-row stage at nb = 30 and 66).
   constexpr int GLOADS = (QK * QT + QTHREADS - 1) / QTHREADS;
+  const int pw = 8 * max(nbi, nbj);
   int lrc[GLOADS];
 #pragma unroll
   for (int q = 0; q < GLOADS; ++q) {
     const int e = threadIdx.x + QTHREADS * q;
-    lrc[q] = e < QK * QT ? (e / QT) | ((e % QT) << 8) : -1;
+    lrc[q] = e < QK * pw ? (e / pw) | ((e % pw) << 8) : -1;
   }
   auto load_stage = [&](int step, int stage) {
     const long long g0 = g_begin + (long long)step * QK;

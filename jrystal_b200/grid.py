@@ -120,8 +120,8 @@ def orbital_grid_candidates(full, need) -> list:
   kernels); grids below 48^3 are launch-latency bound and left alone."""
   full = tuple(int(v) for v in full)
   need = tuple(int(v) for v in need)
-  if any(m > n for m, n in zip(need, full)):
-    raise ValueError(f'the grid {full} aliases: it needs at least {need}')
+  # an axis the caller's own grid under-resolves (need > n) is left as it is: the reference
+  # aliases there and so does this library; the other axes can still shrink exactly
   if full[0] * full[1] * full[2] < 48**3:
     return [full]
   nz = min([n for n in ORBITAL_Z_LENGTHS if need[2] <= n <= full[2]] or [full[2]])

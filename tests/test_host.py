@@ -257,10 +257,11 @@ def test_orbital_grid_selection():
   assert grid.orbital_grid_candidates((128, 128, 128), (77, 77, 77)) == [(81, 81, 81), (128, 128, 81)]
   assert grid.orbital_grid_candidates((128, 128, 128), (85, 85, 85)) == [(128, 128, 100)]
   assert grid.orbital_grid_candidates((128, 128, 128), (105, 105, 105)) == [(128, 128, 128)]
-  # small grids are left alone; a grid that aliases is an error
+  # small grids are left alone; an axis the caller's grid under-resolves stays as it is
   assert grid.orbital_grid_candidates((32, 32, 32), (21, 21, 21)) == [(32, 32, 32)]
-  with pytest.raises(ValueError):
-    grid.orbital_grid_candidates((48, 48, 48), (49, 49, 49))
+  assert grid.orbital_grid_candidates((12, 12, 12), (13, 13, 13)) == [(12, 12, 12)]
+  assert grid.orbital_grid_candidates((48, 48, 48), (49, 49, 49)) == [(48, 48, 48)]
+  assert grid.orbital_grid_candidates((48, 48, 64), (49, 49, 49)) == [(48, 48, 49)]
   # anisotropic mask: per-axis minimum
   m = np.zeros((16, 24, 32), dtype=bool)
   m[0, 0, 0] = m[2, 0, 0] = m[-1, 3, 0] = m[0, -5, 7] = True
