@@ -8,7 +8,7 @@ pins against the reference's own test identities and crystal goldens first.  Eac
 the seeded inputs' recipe (structure, grid, k-grid, mask, seed) and the outputs
 (E_kin, E_ext, E_har, E_xc, rho, dE/dw_re, dE/dw_im, dE/docc, band trace data).
 
-  python tests/golden/make_golden.py        # rewrites the .npz files (deterministic)
+  python tests/golden/make_golden.py [case ...]   # rewrites the .npz files (deterministic)
 """
 import os
 import sys
@@ -28,6 +28,9 @@ CASES = {
                          cutoff=20.0, nb=10, seed=7, xc='lda_x'),
   'si_24x32x48_pw': dict(name='si', grid=[24, 32, 48], kgrid=[1, 1, 1], mask='spherical',
                          cutoff=8.0, nb=9, seed=11, xc='lda_x+lda_c_pw'),
+  # the GGA branch (xc.py:67-112), the reference's config.yaml default functional
+  'diamond_12_pbe': dict(name='diamond', grid=[12, 12, 12], kgrid=[1, 1, 2], mask='spherical',
+                         cutoff=10.0, nb=6, seed=5, xc='gga_x_pbe+gga_c_pbe'),
 }
 
 
@@ -40,7 +43,10 @@ def inputs(c):
 
 
 def main():
+  only = sys.argv[1:]
   for key, c in CASES.items():
+    if only and key not in only:
+      continue
     s, w_re, w_im, occ = inputs(c)
     ref = rp.energy_and_grad(s, w_re, w_im, occ, xc=c['xc'], occ_grad=True)
     band = rp.band_trace_and_grad(s, w_re, w_im, ref['density'], xc=c['xc'])
