@@ -31,8 +31,6 @@ void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 long long launch_count() { return g_launches.load(std::memory_order_relaxed); }
 
 bool line_length_supported(int n) {
-  PassArgs dummy{};
-  (void)dummy;
   switch (n) {
     case 7: case 8: case 9: case 12: case 16: case 24: case 32: case 48: case 64: case 72:
     case 96: case 128:
