@@ -598,7 +598,16 @@ static int run_gram(jrb_plan* p, int nsk, TallMat A, TallMat B, bool same, cplx*
   const long long sks = p->ng * p->nb;
   const int panels = (same && tiles == 1) ? 1 : 2;
   const int smem = panels * ST * QK * QLDB * (int)sizeof(cplx);
-  if (tiles == 1) {
+  if (tiles == 1 && p->nb <= 32) {
+    // few bands: 10 blocks at most (2 per warp), narrow panels, six-stage ring
+    constexpr int STS = 6;
+    const int ldb = 8 * ((p->nb + 7) / 8) + 2;
+    const int smem_s = panels * STS * QK * ldb * (int)sizeof(cplx);
+    static int once = opt_in_smem(k_gram<STS, 2, 0>, 2 * STS * QK * 34 * (int)sizeof(cplx));
+    if (once) return once;
+    k_gram<STS, 2, 0><<<grid, QTHREADS, smem_s, st>>>(A, B, same ? 1 : 0, p->ng, p->nb, sks, tiles,
+                                                     rows, partial);
+  } else if (tiles == 1) {
     static int once = opt_in_smem(k_gram<ST, QSLOT_DIAG>, 2 * ST * QK * QLDB * (int)sizeof(cplx));
     if (once) return once;
     k_gram<ST, QSLOT_DIAG><<<grid, QTHREADS, smem, st>>>(A, B, same ? 1 : 0, p->ng, p->nb, sks,

@@ -86,8 +86,11 @@ struct TallMat {
 // partial[chunk][sk][i][j] = sum_{g in chunk} conj(A[g][i]) B[g][j]   for 8x8 blocks bi <= bj
 // (entries below the block diagonal are NOT written; consumers mirror / ignore them).
 // grid: (ntiles (ntiles + 1) / 2 upper super-tiles, nchunks, nsk)
-// dynamic smem: STAGES * 2 panels [QK][QLDB]
-template <int STAGES, int MAXSLOT>
+// dynamic smem: STAGES * 2 panels [QK][ldb]
+// LDB_T: panel leading dimension; 0 = narrow panels sized at run time (ldb = pw + 2, still == 2 mod
+// 8), used with a deeper ring for nb <= 32 where a 16-row stage carries too few DMMAs to hide the
+// load latency behind a 3-stage ring.
+template <int STAGES, int MAXSLOT, int LDB_T = QLDB>
 __global__ void __launch_bounds__(QTHREADS, (MAXSLOT <= 6 ? 2 : 1))
 k_gram(TallMat A, TallMat B, int same, long long ng, int nb, long long sk_stride, int ntiles,
        long long rows_per_chunk, cplx* __restrict__ partial) {
@@ -102,7 +105,6 @@ k_gram(TallMat A, TallMat B, int same, long long ng, int nb, long long sk_stride
   const int tj = ti + rem;
   const bool diag = ti == tj;
   const bool one_panel = same && diag;
-  cplx* sB = one_panel ? sA : sA + STAGES * QK * QLDB;
 
   const int chunk = blockIdx.y, sk = blockIdx.z, nsk = gridDim.z;
   const long long g_begin = (long long)chunk * rows_per_chunk;
@@ -134,7 +136,9 @@ k_gram(TallMat A, TallMat B, int same, long long ng, int nb, long long sk_stride
     }
     blk[s] = bi < nbi ? (8 * bi) | ((8 * bj) << 16) : -1;
   }
-  const int lofs = lc * QLDB + lr;
+  const int ldb = LDB_T ? LDB_T : 8 * max(nbi, nbj) + 2;
+  cplx* sB = one_panel ? sA : sA + STAGES * QK * ldb;
+  const int lofs = lc * ldb + lr;
 
   // panel elements of this thread: e = tid + 256 q -> (row e / pw, col e % pw), fixed per thread.
   // pw = the panel columns any block of this CTA reads (whole 8-column blocks): with few bands
@@ -155,9 +159,9 @@ k_gram(TallMat A, TallMat B, int same, long long ng, int nb, long long sk_stride
       if (lrc[q] >= 0) {
         const int r = lrc[q] & 0xff, c = lrc[q] >> 8;
         const long long g = g0 + r;
-        a.fetch(&sA[(stage * QK + r) * QLDB + c], g, i0 + c, g < g_end && c < wi_cols);
+        a.fetch(&sA[(stage * QK + r) * ldb + c], g, i0 + c, g < g_end && c < wi_cols);
         if (!one_panel)
-          bm.fetch(&sB[(stage * QK + r) * QLDB + c], g, j0 + c, g < g_end && c < wj_cols);
+          bm.fetch(&sB[(stage * QK + r) * ldb + c], g, j0 + c, g < g_end && c < wj_cols);
       }
     }
   };
@@ -176,8 +180,8 @@ k_gram(TallMat A, TallMat B, int same, long long ng, int nb, long long sk_stride
     __syncthreads();
     if (it + STAGES - 1 < nsteps) load_stage(it + STAGES - 1, (it + STAGES - 1) % STAGES);
     cp_async_commit();
-    const cplx* pa = sA + (it % STAGES) * QK * QLDB;
-    const cplx* pb = sB + (it % STAGES) * QK * QLDB;
+    const cplx* pa = sA + (it % STAGES) * QK * ldb;
+    const cplx* pb = sB + (it % STAGES) * QK * ldb;
 #pragma unroll
     for (int k4 = 0; k4 < QK / 4; ++k4) {
       // slots in groups of QGRP: all first products, then all second products, so that the two
@@ -189,8 +193,8 @@ k_gram(TallMat A, TallMat B, int same, long long ng, int nb, long long sk_stride
         for (int q = 0; q < QGRP; ++q) {
           const int s = s0 + q;
           if (s < MAXSLOT && blk[s] >= 0) {
-            fa[q] = pa[k4 * 4 * QLDB + lofs + (blk[s] & 0xffff)];  // A frag (row i, col k)
-            fb[q] = pb[k4 * 4 * QLDB + lofs + (blk[s] >> 16)];     // B frag (row k, col j)
+            fa[q] = pa[k4 * 4 * ldb + lofs + (blk[s] & 0xffff)];  // A frag (row i, col k)
+            fb[q] = pb[k4 * 4 * ldb + lofs + (blk[s] >> 16)];     // B frag (row k, col j)
           }
         }
         // conj(a) b = (ar br + ai bi) + i (ar bi - ai br)
