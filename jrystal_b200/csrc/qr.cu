@@ -554,7 +554,7 @@ static int gram_chunks(const jrb_plan* p, int tiles, int nsk) {
   // CTAs = upper super-tile pairs x chunks x (spin,k); two CTAs are resident per SM.  Pick the
   // chunk count (>= 256 rows each) whose last wave is fullest, preferring >= 2 waves.
   const int per_chunk = nsk * (tiles * (tiles + 1) / 2);
-  const int slots = 2 * 148;
+  const int slots = (tiles == 1 && p->nb <= 32 ? 3 : 2) * 148;  // resident CTAs of the variant used
   const int max_chunks = (int)std::max<int64_t>(1, std::min<int64_t>(128, p->ng / 256));
   int best = 1;
   double best_score = -1.0;

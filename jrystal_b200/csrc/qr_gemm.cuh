@@ -91,7 +91,7 @@ struct TallMat {
 // 8), used with a deeper ring for nb <= 32 where a 16-row stage carries too few DMMAs to hide the
 // load latency behind a 3-stage ring.
 template <int STAGES, int MAXSLOT, int LDB_T = QLDB>
-__global__ void __launch_bounds__(QTHREADS, (MAXSLOT <= 6 ? 2 : 1))
+__global__ void __launch_bounds__(QTHREADS, (MAXSLOT <= 2 ? 3 : (MAXSLOT <= 6 ? 2 : 1)))
 k_gram(TallMat A, TallMat B, int same, long long ng, int nb, long long sk_stride, int ntiles,
        long long rows_per_chunk, cplx* __restrict__ partial) {
   extern __shared__ __align__(16) unsigned char smem_raw_[];
@@ -144,7 +144,8 @@ k_gram(TallMat A, TallMat B, int same, long long ng, int nb, long long sk_stride
   // pw = the panel columns any block of this CTA reads (whole 8-column blocks): with few bands
   // (nb = 15 ... 32) a 72-wide panel would be 55-80 % zero-fill copies, and the copy instructions,
   // not the DMMAs, bound the stage (measured: the same 4.4 us per 16-row stage at nb = 30 and 66).
-  constexpr int GLOADS = (QK * QT + QTHREADS - 1) / QTHREADS;
+  constexpr int PWMAX = LDB_T ? QT : 32;  // the run-time-narrow variant serves nb <= 32 only
+  constexpr int GLOADS = (QK * PWMAX + QTHREADS - 1) / QTHREADS;
   const int pw = 8 * max(nbi, nbj);
   int lrc[GLOADS];
 #pragma unroll
@@ -294,8 +295,10 @@ struct ApplyDispatch {
   }
 };
 
+// few bands (NCB <= 4): the k-loop is 2-4 steps, the kernel streams rows; three resident CTAs
+// (84 registers) overlap more row tiles
 template <int MODE, int NCB, int STAGES, bool SPLIT>
-__global__ void __launch_bounds__(QTHREADS, 2)
+__global__ void __launch_bounds__(QTHREADS, (NCB <= 4 ? 3 : 2))
 k_apply(const double* __restrict__ in1_re, const double* __restrict__ in1_im,
         const cplx* __restrict__ T1, int tri1, const cplx* __restrict__ in2,
         const cplx* __restrict__ T2, int tri2, int nterms, long long ng, int nb,

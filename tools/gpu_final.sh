@@ -10,6 +10,7 @@ import json
 d=json.load(open('gpurun_out/bench_final_default.json'))
 print(d['config']['workload'], round(d['value'],2),'eval/s e2e',round(d['e2e']['value'],2),'frac',round(d['roofline']['frac'],3),'cpu',d.get('cpu_baseline'),'clocks',d['clocks'])
 PY
+[ -n "$SKIP_NCU" ] && exit 0
 # ncu --set full of the fused 81 x 81 plane kernels (C3a), two launches
 timeout 600 ncu --set full --clock-control none --import-source on -k "regex:k_yx" --launch-skip 2 --launch-count 2 -f -o gpurun_out/prof_C3a_f81 \
     python tools/profile_eval.py --config C3a --evals 2 > gpurun_out/prof_C3a_f81.log 2>&1
