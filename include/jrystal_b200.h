@@ -221,6 +221,12 @@ int jrb_wave_grid(jrb_plan* plan, const double* q, double* psi, jrb_stream strea
  * This is the reverse pass of the energy w.r.t. Q (dE/dQ* = occ * hq) and the forward+reverse
  * pass of hamiltonian.hamiltonian_matrix_trace (jrystal/_src/hamiltonian.py:147-168). */
 int jrb_hpsi(jrb_plan* plan, const double* q, const double* veff, double* hq, jrb_stream stream);
+/* Band mode keeps v_eff[rho_gs] fixed over thousands of steps (the reference recomputes it inside
+ * every step, hamiltonian.py:147-156): jrb_hpsi_prepare copies it into plan work space (and
+ * resamples it onto the orbital grid once); jrb_hpsi with veff == NULL then applies the prepared
+ * potential.  Any call that passes its own veff, and jrb_eval_finish / jrb_energy_grad_host,
+ * replace the prepared potential. */
+int jrb_hpsi_prepare(jrb_plan* plan, const double* veff, jrb_stream stream);
 
 /* eps[s,k,b] = Re sum_G conj(q) hq: diagonal of braket.expectation(real)+(kinetic)
  * (jrystal/_src/braket.py:189-206) = dE/d occ[s,k,b]. */

@@ -11,7 +11,7 @@ LIB_PATH = os.path.join(_HERE, 'csrc', 'libjrystal_b200.so')
 XC_IDS = {'lda_x': 1, 'lda_x+lda_c_pw': 2, 'gga_x_pbe': 3, 'gga_x_pbe+gga_c_pbe': 4}
 FFT_FORWARD, FFT_INVERSE = -1, 1
 # axis lengths with compiled pencil passes; FUSED: also the fused y+x plane kernels (nx == ny)
-LINE_LENGTHS = (7, 8, 9, 12, 16, 24, 32, 40, 45, 48, 49, 50, 54, 56, 60, 64, 72, 80, 81, 90, 96,
+LINE_LENGTHS = (7, 8, 9, 12, 16, 24, 32, 36, 40, 45, 48, 49, 50, 54, 56, 60, 64, 72, 80, 81, 90, 96,
                 100, 112, 128)
 FUSED_LENGTHS = (7, 8, 9, 12, 16, 24, 32, 48, 49, 64, 72, 81, 96, 128)
 
@@ -59,6 +59,7 @@ SYMBOLS = {
   'jrb_density_reciprocal': (ctypes.c_int, [_P, _P, _P, _P]),
   'jrb_wave_grid': (ctypes.c_int, [_P, _P, _P, _P]),
   'jrb_hpsi': (ctypes.c_int, [_P, _P, _P, _P, _P]),
+  'jrb_hpsi_prepare': (ctypes.c_int, [_P, _P, _P]),
   'jrb_band_expect': (ctypes.c_int, [_P, _P, _P, _P, _P]),
   'jrb_hamiltonian_matrix': (ctypes.c_int, [_P, _P, _P, _P, _P]),
   'jrb_fft3d': (ctypes.c_int, [_P, _P, _P, _I32, _I64, _P]),

@@ -5,7 +5,8 @@ the diagonalisation of the nb x nb subspace matrix H_ij (hamiltonian.py:171-240)
 
 What differs from the reference, and why:
   * v_eff[rho_gs] is computed ONCE (the reference recomputes it inside every step although the
-    ground-state density is constant, hamiltonian.py:147-156);
+    ground-state density is constant, hamiltonian.py:147-156) and handed to the plan with
+    jrb_hpsi_prepare, which also resamples it onto the orbital grid once;
   * H_ij comes from one H-apply + one FP64 tensor-core Gram (jrb_hpsi + jrb_hamiltonian_matrix)
     instead of nb Hessian-vector products (hessian.py:21-55);
   * one plan walks the path (jrb_set_kpoints), warm-starting every k-point from its predecessor
@@ -57,10 +58,13 @@ def calc(config: Optional[JrystalConfigDict] = None, ground_state=None, k_path=N
     world, rank = 1, 0
   lo, hi = parallel.shard_bands(k_path.shape[0], world, rank)  # contiguous chunk of the path
   num_bands = ceil(crystal.num_electron / 2) + config.band_structure_empty_bands
-  plan = Plan(crystal.cell_vectors, freq_mask, k_path[lo:lo + 1], num_bands)
+  og = config.get('orbital_grid', 'auto')
+  plan = Plan(crystal.cell_vectors, freq_mask, k_path[lo:lo + 1], num_bands,
+              orbital_grid=tuple(og) if isinstance(og, (list, tuple)) else og)
   plan.set_atoms(crystal.positions, crystal.charges)
   dev = plan.tdev
   veff = plan.potential(rho_gs.to(dev).contiguous(), config.xc, True, 7)
+  plan.prepare_potential(veff)  # fixed over the whole scan: copied / resampled once
   rng = np.random.default_rng(config.seed)
   shape = (1, 1, plan.ng, num_bands)
   w_re = torch.from_numpy(rng.random(shape)).to(dev)
@@ -74,7 +78,7 @@ def calc(config: Optional[JrystalConfigDict] = None, ground_state=None, k_path=N
 
   def update():
     plan.qr_fwd(w_re, w_im, out=(q, r))
-    plan.hpsi(q, veff, out=hq)
+    plan.hpsi(q, None, out=hq)
     plan.qr_bwd(q, r, hq, out=grads)
     opt.step(grads)
 
@@ -86,7 +90,7 @@ def calc(config: Optional[JrystalConfigDict] = None, ground_state=None, k_path=N
     for _ in range(int(epochs)):
       update()
     plan.qr_fwd(w_re, w_im, out=(q, r))
-    plan.hpsi(q, veff, out=hq)
+    plan.hpsi(q, None, out=hq)
     h = plan.overlap(q, hq)[0, 0].cpu().numpy()
     eig[0, i - lo] = np.linalg.eigvalsh(0.5 * (h + h.conj().T))
     if log is not None:

@@ -232,12 +232,26 @@ extern "C" int jrb_wave_grid(jrb_plan* p, const double* q, double* psi, jrb_stre
                             1.0 / std::sqrt(p->vol), S(st));
 }
 
+extern "C" int jrb_hpsi_prepare(jrb_plan* p, const double* veff, jrb_stream st) {
+  int rc = enter(p);
+  if (rc) return rc;
+  REQUIRE(veff, "null array");
+  if (veff != p->d_veff)
+    JRB_CUDA(cudaMemcpyAsync(p->d_veff, veff, sizeof(double) * (size_t)p->ns * p->ngrid,
+                             cudaMemcpyDeviceToDevice, S(st)));
+  if ((rc = launch_hpsi_prepare(p, p->d_veff, S(st)))) return rc;
+  p->veff_prepared = 1;
+  return 0;
+}
+
 extern "C" int jrb_hpsi(jrb_plan* p, const double* q, const double* veff, double* hq,
                         jrb_stream st) {
   int rc = enter(p);
   if (rc) return rc;
-  REQUIRE(q && veff && hq, "null array");
+  REQUIRE(q && hq, "null array");
   REQUIRE(q != hq, "hq must not alias q");
+  REQUIRE(veff || p->veff_prepared, "veff is null and no potential was prepared (jrb_hpsi_prepare)");
+  if (veff) p->veff_prepared = 0;  // the work space now holds this call's potential
   p->nl_p_valid = 0;
   return launch_hpsi(p, C(q), veff, C(hq), S(st));
 }
@@ -310,6 +324,7 @@ extern "C" int jrb_eval_finish(jrb_plan* p, const double* occ, const double* rho
   REQUIRE(occ && rho && e_kin && energies && g_re && g_im, "null array");
   double* grid_e = p->d_scal;            // E_H, E_ext, E_xc
   double* veff = p->d_veff;
+  p->veff_prepared = 0;                  // d_veff is overwritten by this evaluation's potential
   if ((rc = launch_grid_potential(p, rho, xc_id, 0, 7, grid_e, veff, S(st)))) return rc;
   p->keep_read = p->keep_filled;
   rc = launch_hpsi(p, p->d_q, veff, p->d_hq, S(st));
@@ -411,6 +426,7 @@ extern "C" int jrb_energy_grad_host(jrb_plan* p, const double* w_re_h, const dou
     if ((rc = launch_weighted_sum(p, p->d_tkb, p->d_occ, (int64_t)p->nk * p->nb, e_kin, st))) return rc;
     // backward: D2H of chunk c (copy stream) under H-apply + QR adjoint of chunk c+1
     double* grid_e = p->d_scal;
+    p->veff_prepared = 0;
     if ((rc = launch_grid_potential(p, rho, xc_id, 0, 7, grid_e, p->d_veff, st))) return rc;
     if ((rc = launch_hpsi_prepare(p, p->d_veff, st))) return rc;
     for (int c = 0; c < nch; ++c) {

@@ -305,9 +305,15 @@ static int hpsi_groups(jrb_plan* p, const cplx* q, const double* veff_spin, cplx
 }
 
 // hq = 1/2|G+k|^2 q + (sqrt(Omega)/N) fftn(veff psi)|mask   (jrb_hpsi)
+// veff == nullptr: the potential of the last jrb_hpsi_prepare (band mode: v_eff[rho_gs] is fixed over
+// thousands of steps, so it is copied / resampled once instead of on every call)
 int launch_hpsi(jrb_plan* p, const cplx* q, const double* veff, cplx* hq, cudaStream_t st) {
-  int rc = launch_hpsi_prepare(p, veff, st);
-  if (rc) return rc;
+  int rc = 0;
+  if (veff == nullptr) {
+    veff = p->d_veff;
+  } else if ((rc = launch_hpsi_prepare(p, veff, st))) {
+    return rc;
+  }
   const int per_spin = p->nk * p->ngroups_per_k;
   for (int s = 0; s < p->ns; ++s)
     if ((rc = hpsi_groups(p, q, veff + (size_t)s * p->ngrid, hq, s, 0, per_spin, st))) return rc;

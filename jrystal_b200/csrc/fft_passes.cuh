@@ -95,7 +95,7 @@ __device__ __forceinline__ cplx czero() { return cmake(0.0, 0.0); }
 // where that costs no real spilling (checked with -Xptxas -v).
 constexpr bool vmul_two_buffers(int n) { return n <= 96; }
 constexpr int z_min_blocks(int n) {
-  return (n == 64 || n == 49) ? 4 : (n == 81 || n == 100) ? 3 : (n > 96 ? 2 : 1);
+  return (n == 64 || n == 49 || n == 36) ? 4 : (n == 81 || n == 100) ? 3 : (n > 96 ? 2 : 1);
 }
 // Long lines (16 elements per thread): cap the registers at 128 so that two CTAs are resident
 // (one CTA of 8 warps per SM left every 128-point pass latency bound at 12 % occupancy).

@@ -2,7 +2,7 @@
 // translation units so nvcc can build them in parallel).
 #include "fft_passes.cuh"
 
-#define JRB_SIZES(X) X(40) X(45) X(49) X(50) X(54) X(56) X(60)
+#define JRB_SIZES(X) X(36) X(40) X(45) X(49) X(50) X(54) X(56) X(60)
 
 namespace jrb {
 

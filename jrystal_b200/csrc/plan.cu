@@ -35,7 +35,7 @@ bool line_length_supported(int n) {
     case 7: case 8: case 9: case 12: case 16: case 24: case 32: case 48: case 64: case 72:
     case 96: case 128:
     // pencil passes and dense lines only (no fused y+x kernels): lengths an orbital grid can take
-    case 40: case 45: case 49: case 50: case 54: case 56: case 60: case 80: case 81: case 90:
+    case 36: case 40: case 45: case 49: case 50: case 54: case 56: case 60: case 80: case 81: case 90:
     case 100: case 112:
       return true;
     default:
@@ -203,7 +203,7 @@ static int plan_create_impl(const jrb_plan_desc* d, bool orbital_only, jrb_plan*
   for (int i = 0; i < 3; ++i) {
     if (!line_length_supported(dims[i])) {
       set_error("jrb_plan_create: FFT length " + std::to_string(dims[i]) +
-                " has no compiled line plan (supported: 7 8 9 12 16 24 32 40 45 48 49 50 54 56 60 "
+                " has no compiled line plan (supported: 7 8 9 12 16 24 32 36 40 45 48 49 50 54 56 60 "
                 "64 72 80 81 90 96 100 112 128)");
       return JRB_EUNSUPPORTED;
     }

@@ -112,7 +112,7 @@ struct jrb_plan {
   jrb_plan* wf;
   int orbital_only;     // this plan IS such a child (no evaluation work space)
   double* d_rho_w;      // child: [ns][ngrid] density on the orbital grid
-  int veff_w_valid;     // child: d_veff holds the resampled potential of the running evaluation
+  int veff_prepared;    // jrb_hpsi_prepare: d_veff (and the child's) hold the caller's fixed potential
   // host copies for the child's construction and jrb_set_kpoints
   int32_t* h_freq;      // [ng][3] integer frequencies of the kept plane waves, compact order
   double* h_kpts;       // [nk][3]

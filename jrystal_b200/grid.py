@@ -97,7 +97,7 @@ def estimate_max_cutoff_energy(cell_vectors, mask):
 
 # axis lengths whose two-stage line plan is square-ish (few elements per thread, 3-4 resident CTAs
 # in the z passes); measured on B200, profiles/r01_orbital_grid.md
-ORBITAL_Z_LENGTHS = (7, 8, 9, 12, 16, 24, 32, 49, 64, 81, 100, 128)
+ORBITAL_Z_LENGTHS = (7, 8, 9, 12, 16, 24, 32, 36, 49, 64, 81, 100, 128)
 
 
 def min_orbital_grid(freq_mask) -> tuple:

@@ -273,9 +273,17 @@ class Plan:
     _lib.check(self.lib.jrb_wave_grid(self._h, _ptr(q), _ptr(out), _stream()))
     return out
 
-  def hpsi(self, q, veff, out=None):
-    self._chk(q, self.sphere_shape, torch.complex128, 'q')
+  def prepare_potential(self, veff):
+    """Fix the potential of the following hpsi(q, None) calls (jrb_hpsi_prepare): copied into plan
+    work space and resampled onto the orbital grid once."""
     self._chk(veff, (self.ns, self.nx, self.ny, self.nz), torch.float64, 'veff')
+    _lib.check(self.lib.jrb_hpsi_prepare(self._h, _ptr(veff), _stream()))
+
+  def hpsi(self, q, veff, out=None):
+    """veff=None applies the potential of the last prepare_potential()."""
+    self._chk(q, self.sphere_shape, torch.complex128, 'q')
+    if veff is not None:
+      self._chk(veff, (self.ns, self.nx, self.ny, self.nz), torch.float64, 'veff')
     hq = self._new(self.sphere_shape, torch.complex128) if out is None else out
     _lib.check(self.lib.jrb_hpsi(self._h, _ptr(q), _ptr(veff), _ptr(hq), _stream()))
     return hq

@@ -122,6 +122,39 @@ def test_band_mode_on_orbital_grid(cuda_device, box):
     g_re, g_im = plan.qr_bwd(qd, r, hq)
     assert relerr(g_re.cpu().numpy(), ref['g_re']) < G_TOL
     assert relerr(g_im.cpu().numpy(), ref['g_im']) < G_TOL
+    # the prepared potential (jrb_hpsi_prepare + veff = NULL) gives the same H-apply
+    plan.prepare_potential(veff)
+    veff.zero_()   # the plan must not read the caller's buffer any more
+    hq2 = plan.hpsi(qd, None)
+    assert (hq2 - hq).abs().max().item() <= 1e-14 * hq.abs().max().item()
+
+
+def test_prepared_potential_rules(cuda_device):
+  """veff = NULL without a prepared potential is an error; an explicit veff or an evaluation
+  replaces the prepared one; works on a plan without an orbital grid too (48^3 -> z = 36 with)."""
+  from jrystal_b200._lib import JrbError
+  s = make_system('si', 48, [1, 1, 2], 15, 'spherical')
+  nb = 9
+  w_re, w_im, occ = make_inputs(s, nb, jitter=0.1)
+  for og in (None, 'auto'):
+    plan = make_plan(s, nb, orbital_grid=og)
+    if og == 'auto':
+      assert plan.orbital_grid[:2] == (48, 48) and plan.orbital_grid[2] < 48, plan.orbital_grid
+    q, r = plan.qr_fwd(to_dev(w_re), to_dev(w_im))
+    with pytest.raises(JrbError):
+      plan.hpsi(q, None)
+    rho = plan.density(q, to_dev(occ))
+    _, veff = plan.grid_potential(rho, 'lda_x', True)
+    ref = plan.hpsi(q, veff).clone()
+    with pytest.raises(JrbError):   # an explicit veff does not leave a prepared potential behind
+      plan.hpsi(q, None)
+    plan.prepare_potential(veff)
+    assert (plan.hpsi(q, None) - ref).abs().max().item() <= 1e-14 * ref.abs().max().item()
+    occ_d = to_dev(occ)
+    rho2, e_kin = plan.eval_begin(to_dev(w_re), to_dev(w_im), occ_d)
+    plan.eval_finish(occ_d, rho2, e_kin, 'lda_x')
+    with pytest.raises(JrbError):   # the evaluation overwrote the plan's potential
+      plan.hpsi(q, None)
 
 
 def test_spin_polarised_on_orbital_grid(cuda_device):
