@@ -59,9 +59,16 @@ METRIC = 'energy+grad evals/sec'
 UNIT = 'eval/s'
 
 # stdout carries exactly ONE line (the JSON): libraries that print to stdout (NCCL's version banner,
-# torchrun notices) are routed to stderr for the whole run
-_REAL_STDOUT = os.dup(1)
-os.dup2(2, 1)
+# torchrun notices) are routed to stderr for the whole run -- done in main(), so that importing
+# this module (tests, tools) leaves the importer's stdout alone
+_REAL_STDOUT = 1
+
+
+def _route_stdout_to_stderr():
+  global _REAL_STDOUT
+  sys.stdout.flush()
+  _REAL_STDOUT = os.dup(1)
+  os.dup2(2, 1)
 
 
 def emit(line: dict) -> None:
@@ -814,6 +821,7 @@ def main():
   ap.add_argument('--emulate-ranks', type=int, default=1,
                   help='tuning aid: run only the k-points rank 0 of an N-GPU run would own')
   args = ap.parse_args()
+  _route_stdout_to_stderr()
   if args.impl == 'reference':
     run_reference(args)
   else:
