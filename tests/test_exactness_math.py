@@ -1,9 +1,14 @@
-"""The mathematics behind jrb_plan_set_orbital_grid, checked on the CPU with numpy FFTs only
-(no CUDA, no product code): transforming the orbitals on any box with n >= 4 gmax + 1 and moving
-rho / v_eff between the boxes by Fourier interpolation / truncation reproduces what the
-reference computes on its own grid (pw.wave_grid + density_grid, jrystal/_src/pw.py:208-284; the
-sphere part of fftn(v_eff psi), the backward pass) to rounding -- including the case where the
-caller's grid itself is too coarse on some axes and only the other axis shrinks."""
+"""Mathematics behind two exact shortcuts of the product, checked on the CPU with numpy only (no CUDA,
+no product kernels).
+
+ORBITAL GRID (jrb_plan_set_orbital_grid): transforming the orbitals on any box with
+n >= 4 gmax + 1 and moving rho / v_eff between the boxes by Fourier interpolation / truncation
+reproduces what the reference computes on its own grid (pw.wave_grid + density_grid,
+jrystal/_src/pw.py:208-284; the sphere part of fftn(v_eff psi), the backward pass) to rounding --
+including the case where the caller's grid itself is too coarse on some axes and only the other
+axis shrinks; one point below the bound aliases.
+
+SECOND CHOLESKY-QR PASS (k_near_identity): the closed-form factor of I + E."""
 import numpy as np
 import pytest
 
@@ -104,3 +109,22 @@ def test_a_box_below_the_bound_aliases():
   rho_b = (np.abs(np.fft.ifftn(_scatter(c, fr, box), axes=(1, 2, 3)) * n_box)**2).sum(0)
   rho_up = np.fft.ifftn(_resample(np.fft.fftn(rho_b) / n_box, (24, 24, 24))).real * n_full
   assert np.abs(rho_up - rho_f).max() > 1e-6 * np.abs(rho_f).max()
+
+
+@pytest.mark.parametrize('nb,scale', [(66, 1e-12), (208, 9e-11)])
+def test_closed_form_second_pass_cholesky(nb, scale):
+  """k_near_identity (qr.cu): for S = I + E, max|E| < 1e-10, R = I + up(E) + diag(E)/2 and
+  R^-1 = I - U (+ u^2 on the diagonal) differ from the true Cholesky factor and its inverse by
+  O(nb |E|^2), far below the rounding of the factorisation they replace."""
+  rng = np.random.default_rng(nb)
+  a = rng.standard_normal((nb, nb)) + 1j * rng.standard_normal((nb, nb))
+  e = (a + a.conj().T) * (scale / np.abs(a + a.conj().T).max())
+  s = np.eye(nb) + e
+  u = np.triu(e, 1) + np.diag(np.diag(e).real / 2)
+  r = np.eye(nb) + u
+  d = np.diag(u).real
+  rinv = np.eye(nb) - u + np.diag(d * d)
+  r_true = np.linalg.cholesky(s).conj().T
+  assert np.abs(r - r_true).max() < 4 * nb * scale**2 + 4e-16
+  assert np.abs(r.conj().T @ r - s).max() < 4 * nb * scale**2 + 4e-16
+  assert np.abs(rinv @ r_true - np.eye(nb)).max() < 4 * nb * scale**2 + 4e-16
