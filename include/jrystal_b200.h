@@ -82,8 +82,8 @@ int64_t jrb_plan_workspace_bytes(const jrb_plan* plan);
  * n_c >= 4 gmax_c + 1 transforms them without aliasing: after this call the per-orbital passes
  * (jrb_density, jrb_hpsi, jrb_eval_begin/finish, jrb_energy_grad_host) run on (nxw, nyw, nzw);
  * rho is brought to the plan's grid by Fourier interpolation and v_eff to the orbital grid by
- * Fourier truncation, so every result is the reference's to rounding (tests/test_gpu_parity.py::
- * test_orbital_grid*).  Everything else (grids in the arguments, XC, Hartree, jrb_fft3d,
+ * Fourier truncation, so every result is the reference's to rounding (tests/test_orbital_grid_gpu.py,
+ * tests/test_exactness_math.py).  Everything else (grids in the arguments, XC, Hartree, jrb_fft3d,
  * jrb_wave_grid) keeps the plan's own grid.  Fails with JRB_EINVAL if a RESIZED axis violates
  * 4 gmax + 1 <= n_w < n (an axis left at n is always accepted: where the caller's own grid is too
  * coarse it aliases exactly as the reference does), JRB_EUNSUPPORTED without a compiled line
