@@ -78,7 +78,8 @@ class Plan:
     elif dims == 'auto':
       cands = self.auto_orbital_grid()
       for cand in cands[:-1]:  # boxes that only pay with the fused plane kernels
-        _lib.check(self.lib.jrb_plan_set_orbital_grid(self._h, *cand))
+        if self.lib.jrb_plan_set_orbital_grid(self._h, *cand) != 0:
+          continue  # e.g. no memory for this box: the next candidate is smaller in work space
         if self.lib.jrb_plan_orbital_fused(self._h) > 0:
           self.orbital_grid = cand
           return
