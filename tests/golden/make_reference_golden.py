@@ -1,0 +1,229 @@
+#!/usr/bin/env python
+"""Golden vectors produced by the REFERENCE'S OWN SOURCE (not by the oracle restatement).
+
+jax is not installable in this container, so the reference cannot run as shipped; but its forward
+path is plain array code, and `tests/golden/numpy_jax_standin.py` lets the files under
+/root/reference/jrystal execute over numpy (see that file for what is stood in and why it is
+faithful).  This script calls the reference functions VERBATIM on the seeded inputs of the
+existing golden recipes (tests/golden/make_golden.py: same structure / grid / k-grid / mask /
+seed) and stores their outputs in tests/golden/reference_<case>.npz:
+
+  jrystal/_src/grid.py        g_vectors, r_vectors, k_vectors, spherical_mask / cubic_mask
+  jrystal/_src/utils.py       volume
+  jrystal/_src/pw.py          coeff (QR + expand), wave_grid, density_grid, density_grid_reciprocal
+  jrystal/_src/energy.py      kinetic, hartree, external, nuclear_repulsion
+  jrystal/_src/potential.py   hartree_reciprocal, external_reciprocal
+  jrystal/_src/kinetic.py     kinetic_operator
+  jrystal/_src/braket.py      expectation (kinetic mode, diagonal)
+  jrystal/_src/occupation.py  uniform, gamma
+  jrystal/_src/entropy.py     fermi_dirac
+
+and, for the norm-conserving rows (tests/golden/reference_si_normcons.npz), from the shipped
+pseudopotential/normconserving/Si.pz-vbc.UPF:
+
+  jrystal/pseudopotential/load.py       parse_upf
+  jrystal/pseudopotential/dataclass.py  NormConservingPseudopotential.create
+  jrystal/pseudopotential/beta.py       beta_sbt_grid
+  jrystal/pseudopotential/local.py      potential_local_reciprocal, energy_local
+  jrystal/pseudopotential/nloc.py       potential_nonlocal_psi_reciprocal, hamiltonian_nonlocal,
+                                        energy_nonlocal
+  jrystal/pseudopotential/spherical.py  batch_sph_harm_real, cartesian_to_spherical
+
+NOT covered (needs jax_xc / automatic differentiation): every XC value and every gradient.
+
+  python tests/golden/make_reference_golden.py      # needs /root/reference; deterministic
+
+The fixtures travel to the GPU box; /root/reference does not (and is never read by a test).
+"""
+import os
+import sys
+import types
+import warnings
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, HERE)
+sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+warnings.filterwarnings('ignore', category=SyntaxWarning)
+
+import numpy_jax_standin as standin  # noqa: E402
+from make_golden import CASES  # noqa: E402  (recipes only; the oracle is not called here)
+from oracle import structures  # noqa: E402  (geometry literals, each citing its .xyz file)
+
+ref = standin.ref
+A = lambda x: np.ascontiguousarray(np.asarray(x))
+SAMPLE_STRIDE = (2, 3, 5)  # grids above 8192 points are stored as strided samples + sums
+
+
+def G(x):
+  """A field on the FFT grid: whole for small grids, a strided sample otherwise (the test takes
+  the same sample; the *_sum entries cover the rest)."""
+  x = A(x)
+  if x.shape[-3] * x.shape[-2] * x.shape[-1] <= 8192:
+    return x
+  return A(x[..., ::SAMPLE_STRIDE[0], ::SAMPLE_STRIDE[1], ::SAMPLE_STRIDE[2]])
+
+
+def seeded_params(seed, nb, nk, ng):
+  """The parameter recipe of the golden cases (oracle.reference_port.param_init: numpy
+  default_rng(seed), U[0,1), shape (1, nk, ng, nb)); restated so this script does not call the
+  oracle."""
+  rng = np.random.default_rng(seed)
+  shape = (1, nk, ng, nb)
+  return rng.random(shape), rng.random(shape)
+
+
+def core_case(key, c):
+  grid_m, utils, pw, energy = ref('_src.grid'), ref('_src.utils'), ref('_src.pw'), ref('_src.energy')
+  potential, kinetic, braket = ref('_src.potential'), ref('_src.kinetic'), ref('_src.braket')
+  occupation, entropy = ref('_src.occupation'), ref('_src.entropy')
+
+  cell, pos, chg = structures.load(c['name'], None)
+  gs = [int(g) for g in grid_m.proper_grid_size(c['grid'])]
+  ks = [int(g) for g in grid_m.proper_grid_size(c['kgrid'])]
+  vol = float(utils.volume(cell))
+  g_vec = grid_m.g_vectors(cell, gs)
+  r_vec = grid_m.r_vectors(cell, gs)
+  kpts = grid_m.k_vectors(cell, ks)
+  if c['mask'] == 'spherical':
+    mask = grid_m.spherical_mask(cell, gs, c['cutoff'])
+  else:
+    mask = grid_m.cubic_mask(gs)
+  mask = np.asarray(mask)
+  nk, ng, nb = kpts.shape[0], int(mask.sum()), c['nb']
+  w_re, w_im = seeded_params(c['seed'], nb, nk, ng)
+  ne = int(round(float(np.sum(chg))))
+  occ = A(occupation.uniform(nk, ne, num_bands=nb))
+  occ = occ * (1.0 + 0.1 * np.random.default_rng(c['seed'] + 1).random(occ.shape))
+
+  coeff = pw.coeff({'w_re': w_re, 'w_im': w_im}, mask)
+  psi = pw.wave_grid(coeff, vol)
+  rho = pw.density_grid(coeff, vol, occ)
+  rho_g = pw.density_grid_reciprocal(coeff, vol, occ)
+  e_kin = energy.kinetic(g_vec, kpts, coeff, occ)
+  e_har = energy.hartree(rho_g, g_vec, vol)
+  e_har_ks = energy.hartree(rho_g, g_vec, vol, kohn_sham=True)
+  e_ext = energy.external(rho_g, pos, chg, g_vec, vol)
+  e_nuc = energy.nuclear_repulsion(pos, chg, cell, g_vec, vol, 0.1, 2e4)
+  v_har = potential.hartree_reciprocal(rho_g, g_vec)
+  v_ext = potential.external_reciprocal(pos, chg, g_vec, vol)
+  t_k = kinetic.kinetic_operator(g_vec, kpts)
+  kin_band = braket.expectation(coeff, t_k, vol, diagonal=True, mode='kinetic')
+  ent_in = np.random.default_rng(c['seed'] + 2).random(occ.shape) * 2.0 / nk  # occupations in (0, 2/nk)
+  out = dict(
+    vol=np.array(vol), grid=np.array(gs), kpts=A(kpts), mask=mask,
+    g_vec_sum=np.array(np.abs(A(g_vec)).sum()), g_vec_corner=A(g_vec)[1, 2, 3],
+    r_vec_corner=A(r_vec)[1, 2, 3], occ=occ,
+    w_re_sum=np.array(w_re.sum()), w_im_sum=np.array(w_im.sum()),
+    # Q on the sphere, (ns, nk, ng, nb): the reference's compact layout
+    q=A(np.swapaxes(A(coeff)[..., mask], -1, -2)),
+    psi_band0=G(A(psi)[0, 0, 0]), density=G(rho), density_reciprocal=G(rho_g),
+    density_sum=np.array(A(rho).sum()), density_abs2_sum=np.array((A(rho) ** 2).sum()),
+    e_kin=np.array(float(e_kin)), e_har=np.array(float(e_har)),
+    e_har_kohn_sham=np.array(float(e_har_ks)), e_ext=np.array(float(e_ext)),
+    e_nuc=np.array(float(e_nuc)), v_har_reciprocal=G(v_har), v_ext_reciprocal=G(v_ext),
+    v_har_abs_sum=np.array(np.abs(A(v_har)).sum()), v_ext_abs_sum=np.array(np.abs(A(v_ext)).sum()),
+    kinetic_per_band=A(kin_band),
+    occ_uniform=A(occupation.uniform(nk, ne, num_bands=nb)),
+    occ_gamma=A(occupation.gamma(nk, ne, num_bands=nb)),
+    entropy_input=ent_in, entropy_fermi_dirac=np.array(float(entropy.fermi_dirac(ent_in))),
+  )
+  path = os.path.join(HERE, f'reference_{key}.npz')
+  np.savez_compressed(path, **out)
+  print(f'{key}: E_kin {float(e_kin):.12f} E_H {float(e_har):.12f} E_ext {float(e_ext):.12f} '
+        f'E_nuc {float(e_nuc):.12f} -> {os.path.basename(path)}')
+
+
+NORMCONS = dict(name='si', grid=[12, 12, 12], kgrid=[1, 1, 2], cutoff=6.0, nb=6, seed=21)
+
+
+def normcons_case():
+  """Si2 with the shipped Si.pz-vbc.UPF: the reference's pseudopotential set-up and its
+  local / non-local energy terms, executed verbatim."""
+  c = NORMCONS
+  grid_m, utils, pw = ref('_src.grid'), ref('_src.utils'), ref('_src.pw')
+  occupation = ref('_src.occupation')
+  load, dc = ref('pseudopotential.load'), ref('pseudopotential.dataclass')
+  beta, local, nloc = ref('pseudopotential.beta'), ref('pseudopotential.local'), ref('pseudopotential.nloc')
+  sph = ref('pseudopotential.spherical')
+
+  cell, pos, _ = structures.load(c['name'], None)
+  upf_dir = os.path.join(standin.REFERENCE_ROOT, 'pseudopotential', 'normconserving') + '/'
+  upf = load.parse_upf(load.find_upf(upf_dir, 'Si'))
+  crystal = types.SimpleNamespace(positions=pos, charges=np.array([14, 14]), symbols=['Si', 'Si'])
+  pp = dc.NormConservingPseudopotential.create(crystal, upf_dir)
+
+  gs = [int(g) for g in grid_m.proper_grid_size(c['grid'])]
+  vol = float(utils.volume(cell))
+  g_vec = grid_m.g_vectors(cell, gs)
+  kpts = grid_m.k_vectors(cell, c['kgrid'])
+  mask = np.asarray(grid_m.spherical_mask(cell, gs, c['cutoff']))
+  nk, ng, nb = kpts.shape[0], int(mask.sum()), c['nb']
+  w_re, w_im = seeded_params(c['seed'], nb, nk, ng)
+  ne = int(sum(pp.valence_charges))
+  occ = A(occupation.uniform(nk, ne, num_bands=nb))
+  coeff = pw.coeff({'w_re': w_re, 'w_im': w_im}, mask)
+  rho_g = pw.density_grid_reciprocal(coeff, vol, occ)
+
+  v_loc = local.potential_local_reciprocal(
+    pos, g_vec, pp.r_grid, pp.local_potential_grid, pp.local_potential_charge, vol)
+  e_loc = local.energy_local(rho_g, v_loc, vol)
+  beta_gk = beta.beta_sbt_grid(pp.r_grid, pp.nonlocal_beta_grid, pp.nonlocal_angular_momentum,
+                               g_vec, kpts)
+  phi = nloc.potential_nonlocal_psi_reciprocal(
+    pos, g_vec, kpts, pp.r_grid, pp.nonlocal_beta_grid, pp.nonlocal_angular_momentum,
+    pp.nonlocal_d_matrix, beta_gk)          # (kpt, beta, m, x, y, z)
+  h_nl = nloc.hamiltonian_nonlocal(coeff, phi, vol)
+  e_nl = nloc.energy_nonlocal(coeff, phi, vol, occ)
+
+  # spherical harmonics on a fixed set of directions
+  dirs = np.random.default_rng(3).normal(size=(7, 3))
+  sp = A(sph.cartesian_to_spherical(dirs))
+  ylm = {f'ylm_real_l{l}': A(sph.batch_sph_harm_real(l, sp[:, 1], sp[:, 2])) for l in range(3)}
+
+  phi = A(phi)
+  out = dict(
+    vol=np.array(vol), grid=np.array(gs), kpts=A(kpts), mask=mask, occ=occ,
+    w_re_sum=np.array(w_re.sum()), w_im_sum=np.array(w_im.sum()),
+    # parse_upf / NormConservingPseudopotential.create
+    upf_header_keys=np.array(sorted(upf['PP_HEADER'].keys())),
+    upf_z_valence=np.array(float(upf['PP_HEADER']['z_valence'])),
+    upf_mesh_size=np.array(int(upf['PP_HEADER']['mesh_size'])),
+    upf_r=np.array(upf['PP_MESH']['PP_R']), upf_rab=np.array(upf['PP_MESH']['PP_RAB']),
+    upf_local=np.array(upf['PP_LOCAL']),
+    upf_beta=np.array([b['values'] for b in upf['PP_NONLOCAL']['PP_BETA']]),
+    upf_beta_l=np.array([int(b['angular_momentum']) for b in upf['PP_NONLOCAL']['PP_BETA']]),
+    upf_dij=np.array(upf['PP_NONLOCAL']['PP_DIJ']),
+    pp_valence_charges=np.array(pp.valence_charges), pp_r_grid=A(pp.r_grid[0]),
+    pp_local_potential_grid=A(pp.local_potential_grid[0]),
+    pp_nonlocal_beta_grid=A(pp.nonlocal_beta_grid[0]),
+    pp_nonlocal_d_matrix=A(pp.nonlocal_d_matrix[0]),
+    pp_nonlocal_angular_momentum=A(pp.nonlocal_angular_momentum[0]),
+    # potentials and energies
+    v_loc_reciprocal=A(v_loc), e_loc=np.array(float(np.real(e_loc))),
+    beta_gk_atom0=A(beta_gk[0]),
+    phi_shape=np.array(phi.shape), phi_on_sphere=A(phi[..., mask]),
+    phi_abs_sum_off_sphere=np.array(np.abs(phi[..., ~mask]).sum()),
+    phi_abs_sum=np.array(np.abs(phi).sum()),
+    h_nonlocal=A(h_nl), e_nonlocal=np.array(float(np.real(e_nl))),
+    directions=dirs, directions_spherical=sp, **ylm,
+  )
+  path = os.path.join(HERE, 'reference_si_normcons.npz')
+  np.savez_compressed(path, **out)
+  print(f'si_normcons: E_loc {float(np.real(e_loc)):.12f} E_nl {float(np.real(e_nl)):.12f} '
+        f'phi {phi.shape} -> {os.path.basename(path)}')
+
+
+def main():
+  only = sys.argv[1:]
+  for key, c in CASES.items():
+    if only and key not in only:
+      continue
+    core_case(key, c)
+  if not only or 'si_normcons' in only:
+    normcons_case()
+
+
+if __name__ == '__main__':
+  main()
