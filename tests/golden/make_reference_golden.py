@@ -14,8 +14,8 @@ seed) and stores their outputs in tests/golden/reference_<case>.npz:
   jrystal/_src/energy.py      kinetic, hartree, external, nuclear_repulsion
   jrystal/_src/potential.py   hartree_reciprocal, external_reciprocal
   jrystal/_src/kinetic.py     kinetic_operator
-  jrystal/_src/braket.py      expectation (kinetic mode, diagonal)
-  jrystal/_src/occupation.py  uniform, gamma
+  jrystal/_src/braket.py      expectation (kinetic mode diagonal; real mode diagonal and full)
+  jrystal/_src/occupation.py  uniform, gamma, simplex_projector(_init), proj, idempotent
   jrystal/_src/entropy.py     fermi_dirac
 
 and, for the norm-conserving rows (tests/golden/reference_si_normcons.npz), from the shipped
@@ -111,7 +111,13 @@ def core_case(key, c):
   t_k = kinetic.kinetic_operator(g_vec, kpts)
   kin_band = braket.expectation(coeff, t_k, vol, diagonal=True, mode='kinetic')
   ent_in = np.random.default_rng(c['seed'] + 2).random(occ.shape) * 2.0 / nk  # occupations in (0, 2/nk)
+  # <psi_i| v |psi_j> in real space for a seeded real potential (braket.py:167-207), the
+  # contraction band mode is built on; v is regenerated by the test from the same seed
+  v_r = np.random.default_rng(c['seed'] + 3).standard_normal(tuple(gs))
+  v_diag = braket.expectation(psi, v_r, vol, diagonal=True, mode='real')
+  v_full = braket.expectation(psi, v_r, vol, diagonal=False, mode='real')
   out = dict(
+    expect_v_diag=A(v_diag), expect_v_full=A(v_full),
     vol=np.array(vol), grid=np.array(gs), kpts=A(kpts), mask=mask,
     g_vec_sum=np.array(np.abs(A(g_vec)).sum()), g_vec_corner=A(g_vec)[1, 2, 3],
     r_vec_corner=A(r_vec)[1, 2, 3], occ=occ,
@@ -215,6 +221,33 @@ def normcons_case():
         f'phi {phi.shape} -> {os.path.basename(path)}')
 
 
+def occupation_case():
+  """occupation.py: simplex_projector (+ its init), idempotent, on seeded parameters."""
+  occupation = ref('_src.occupation')
+  nk, nb, ne = 3, 7, 8
+  rng = np.random.default_rng(17)
+  logits_up, logits_dn = rng.normal(size=(nk, nb)) * 2, rng.normal(size=(nk, nb)) * 2
+  params = {'param_up': logits_up, 'param_down': logits_dn}
+  w_up = rng.random((nb * nk, (ne + 2) // 2 * nk))
+  w_dn = rng.random((nb * nk, (ne - 2) // 2 * nk))
+  idem = {'param_up': {'w_re': w_up}, 'param_down': {'w_re': w_dn}}
+  init = occupation.simplex_projector_init(nb, nk)
+  out = dict(
+    nk=np.array(nk), nb=np.array(nb), ne=np.array(ne), logits_up=logits_up, logits_down=logits_dn,
+    w_up=w_up, w_down=w_dn,
+    simplex_restricted=A(occupation.simplex_projector(params, ne)),
+    simplex_spin2=A(occupation.simplex_projector(params, ne, spin=2, spin_restricted=False)),
+    simplex_init_up=A(init['param_up']), simplex_init_down=A(init['param_down']),
+    simplex_from_init=A(occupation.simplex_projector(init, ne)),
+    idempotent_unrestricted=A(occupation.idempotent(idem, nk, spin_restricted=False)),
+    idempotent_restricted=A(occupation.idempotent({'param_up': {'w_re': w_up},
+                                                   'param_down': {'w_re': w_up}}, nk)),
+  )
+  np.savez_compressed(os.path.join(HERE, 'reference_occupation.npz'), **out)
+  print('occupation: sums', out['simplex_restricted'].sum(), out['idempotent_unrestricted'].sum(),
+        '-> reference_occupation.npz')
+
+
 def main():
   only = sys.argv[1:]
   for key, c in CASES.items():
@@ -223,6 +256,9 @@ def main():
     core_case(key, c)
   if not only or 'si_normcons' in only:
     normcons_case()
+  if not only or 'occupation' in only:
+    with np.errstate(divide='ignore', invalid='ignore'):  # proj() divides by n - arange(n) - 1
+      occupation_case()
 
 
 if __name__ == '__main__':

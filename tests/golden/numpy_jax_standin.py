@@ -97,6 +97,9 @@ class _AtIdx:
     np.add.at(out, self.idx, v)
     return out
 
+  def get(self):
+    return np.asarray(self.a)[self.idx].view(Arr) if np.ndim(np.asarray(self.a)[self.idx]) else np.asarray(self.a)[self.idx]
+
   def multiply(self, v):
     out = np.array(self.a, copy=True).view(Arr)
     out[self.idx] = out[self.idx] * v

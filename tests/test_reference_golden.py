@@ -92,6 +92,13 @@ def test_oracle_matches_reference_source(key):
   kin = rp.expectation(cg, t_k, s.vol, diagonal=True, mode='kinetic')
   assert relerr(np.asarray(kin), g['kinetic_per_band']) < 1e-12
 
+  # <psi_i|v|psi_j> for a seeded real potential (the contraction of band mode)
+  v_r = torch.from_numpy(np.random.default_rng(c['seed'] + 3).standard_normal(tuple(s.grid_sizes)))
+  assert relerr(np.asarray(rp.expectation(psi, v_r, s.vol, diagonal=True, mode='real')),
+                g['expect_v_diag']) < 1e-12
+  assert relerr(np.asarray(rp.expectation(psi, v_r, s.vol, diagonal=False, mode='real')),
+                g['expect_v_full']) < 1e-12
+
   ne = s.num_electrons
   np.testing.assert_allclose(rp.occupation_uniform(s.num_k, ne, num_bands=c['nb']).numpy(),
                              g['occ_uniform'], rtol=1e-15)
@@ -143,6 +150,39 @@ def test_host_modules_match_reference_source(key):
   assert abs(e_nuc - float(g['e_nuc'])) < 1e-6 * abs(float(g['e_nuc']))
 
 
+def test_occupation_maps_match_reference_source():
+  """simplex_projector / proj / idempotent (occupation.py:55-80, 281-366): oracle restatement and
+  the host module the energy driver differentiates through, against the reference's outputs."""
+  from jrystal_b200 import occupation
+  g = np.load(os.path.join(HERE, 'golden', 'reference_occupation.npz'))
+  nk, nb, ne = int(g['nk']), int(g['nb']), int(g['ne'])
+  t = torch.from_numpy
+  up, dn = t(g['logits_up']), t(g['logits_down'])
+  for impl in ('oracle', 'host'):
+    if impl == 'oracle':
+      r = rp.occupation_simplex_projector(up, dn, ne)
+      u = rp.occupation_simplex_projector(up, dn, ne, spin=2, spin_restricted=False)
+      i_u = rp.occupation_idempotent(t(g['w_up']), t(g['w_down']), nk, spin_restricted=False)
+      i_r = rp.occupation_idempotent(t(g['w_up']), t(g['w_up']), nk)
+    else:
+      p = {'param_up': up, 'param_down': dn}
+      r = occupation.simplex_projector(p, ne)
+      u = occupation.simplex_projector(p, ne, spin=2, spin_restricted=False)
+      i_u = occupation.idempotent({'param_up': {'w_re': t(g['w_up'])},
+                                   'param_down': {'w_re': t(g['w_down'])}}, nk, spin_restricted=False)
+      i_r = occupation.idempotent({'param_up': {'w_re': t(g['w_up'])},
+                                   'param_down': {'w_re': t(g['w_up'])}}, nk)
+    assert relerr(r.detach().numpy(), g['simplex_restricted']) < 1e-13, impl
+    assert relerr(u.detach().numpy(), g['simplex_spin2']) < 1e-13, impl
+    assert relerr(i_u.detach().numpy(), g['idempotent_unrestricted']) < 1e-12, impl
+    assert relerr(i_r.detach().numpy(), g['idempotent_restricted']) < 1e-12, impl
+  init = occupation.simplex_projector_init(nb, nk)
+  np.testing.assert_allclose(init['param_up'].detach().cpu().numpy(), g['simplex_init_up'], rtol=1e-15)
+  np.testing.assert_allclose(init['param_down'].detach().cpu().numpy(), g['simplex_init_down'], rtol=1e-15)
+  cpu_init = {k: v.detach().cpu() for k, v in init.items()}
+  assert relerr(occupation.simplex_projector(cpu_init, ne).numpy(), g['simplex_from_init']) < 1e-13
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize('key', list(mg.CASES))
 def test_cuda_matches_reference_source(cuda_device, key):
@@ -169,3 +209,14 @@ def test_cuda_matches_reference_source(cuda_device, key):
   assert _close(rho.sum(), g['density_sum'], 1e-10)
   eps_kin = plan.kinetic(qd).cpu().numpy()        # <c|T|c> per orbital (braket.py:167-207)
   assert relerr(eps_kin, g['kinetic_per_band']) < 1e-10
+  # band mode: <q_i|T + v|q_j> with the seeded real potential of the reference run
+  v_r = np.random.default_rng(c['seed'] + 3).standard_normal(tuple(s.grid_sizes))
+  hq = plan.hpsi(qd, to_dev(v_r[None]))
+  eps = plan.band_expect(qd, hq).cpu().numpy()
+  assert relerr(eps, g['kinetic_per_band'] + np.real(g['expect_v_diag'])) < 1e-10
+  h = plan.overlap(qd, hq).cpu().numpy()
+  t_k = np.asarray(rp.kinetic_operator(s.g_vec, s.kpts))[:, s.mask]          # (nk, ng)
+  t_full = np.einsum('skgi,kg,skgj->skij', np.conj(q), t_k, q)
+  sg = sign[:, :, 0, :]                                                       # (ns, nk, nb)
+  v_full = g['expect_v_full'] * sg[..., :, None] * sg[..., None, :]
+  assert relerr(h, t_full + v_full) < 1e-10
