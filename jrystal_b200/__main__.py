@@ -19,7 +19,11 @@ def main(argv=None):
   if args.mode == 'energy':
     out = calc.energy(config, log=log)
     print(f'Hartree Energy: {out.energies["hartree"]:.4f} Ha')
-    print(f'External Energy: {out.energies["external"]:.4f} Ha')
+    if 'external_local' in out.energies:
+      print(f'External (local) Energy: {out.energies["external_local"]:.4f} Ha')
+      print(f'External (nonlocal) Energy: {out.energies["external_nonlocal"]:.4f} Ha')
+    else:
+      print(f'External Energy: {out.energies["external"]:.4f} Ha')
     print(f'XC Energy: {out.energies["xc"]:.4f} Ha')
     print(f'Kinetic Energy: {out.energies["kinetic"]:.4f} Ha')
     print(f'Nuclear repulsion Energy: {out.energies["ewald"]:.4f} Ha')

@@ -26,7 +26,7 @@ from ..k_path import get_k_path
 from ..optim import Adam
 from ..plan import Plan
 from .calc_ground_state_energy_all_electrons import calc as energy_calc
-from .opt_utils import create_crystal, create_freq_mask
+from .opt_utils import create_crystal, create_freq_mask, create_grids, create_pseudopotential
 
 
 @dataclasses.dataclass
@@ -39,8 +39,14 @@ class BandStructureOutput:
 
 def calc(config: Optional[JrystalConfigDict] = None, ground_state=None, k_path=None,
          log=None) -> BandStructureOutput:
+  """With `use_pseudopotential: true` this is the norm-conserving band driver
+  (calc_band_structure_normcons.py:66-299 of the reference): the fixed potential is
+  v_H[rho_gs] + v_xc[rho_gs] + V_loc, the projectors <beta|G+k> are rebuilt on the sphere for every
+  k-point of the path (radial transforms on the grid of the WHOLE path, as the reference's
+  pre_calc_beta_sbt does) and join the H-apply and H_ij."""
   config = config or get_config()
   crystal = create_crystal(config)
+  pseudopot = create_pseudopotential(config, crystal) if config.use_pseudopotential else None
   freq_mask = create_freq_mask(config, crystal)
   if k_path is None:
     if config.get('k_path_file'):
@@ -57,11 +63,20 @@ def calc(config: Optional[JrystalConfigDict] = None, ground_state=None, k_path=N
   if not config.parallel_over_k_path:
     world, rank = 1, 0
   lo, hi = parallel.shard_bands(k_path.shape[0], world, rank)  # contiguous chunk of the path
-  num_bands = ceil(crystal.num_electron / 2) + config.band_structure_empty_bands
+  num_electron = pseudopot.num_valence_electrons if pseudopot is not None else crystal.num_electron
+  num_bands = ceil(num_electron / 2) + config.band_structure_empty_bands
   og = config.get('orbital_grid', 'auto')
   plan = Plan(crystal.cell_vectors, freq_mask, k_path[lo:lo + 1], num_bands,
               orbital_grid=tuple(og) if isinstance(og, (list, tuple)) else og)
-  plan.set_atoms(crystal.positions, crystal.charges)
+  if pseudopot is not None:
+    from ..pseudopotential import normcons
+    from ..pseudopotential.beta import max_radius
+    g_vec, _, _ = create_grids(config, crystal)
+    kmax = max_radius(g_vec, k_path)
+    normcons.attach(plan, pseudopot, g_vec, kpts=k_path[lo:lo + 1], positions=crystal.positions,
+                    kmax=kmax)
+  else:
+    plan.set_atoms(crystal.positions, crystal.charges)
   dev = plan.tdev
   veff = plan.potential(rho_gs.to(dev).contiguous(), config.xc, True, 7)
   plan.prepare_potential(veff)  # fixed over the whole scan: copied / resampled once
@@ -85,6 +100,9 @@ def calc(config: Optional[JrystalConfigDict] = None, ground_state=None, k_path=N
   eig = np.zeros((1, hi - lo, num_bands))
   for i in range(lo, hi):
     plan.set_kpoints(k_path[i:i + 1])
+    if pseudopot is not None and i > lo:
+      normcons.set_projectors(plan, normcons.projectors(
+        plan, pseudopot, g_vec, k_path[i:i + 1], crystal.positions, kmax))
     epochs = config.band_structure_epoch if i == lo else (
       config.k_path_fine_tuning_epoch if config.k_path_fine_tuning else config.band_structure_epoch)
     for _ in range(int(epochs)):

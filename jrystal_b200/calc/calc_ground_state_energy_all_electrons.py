@@ -59,14 +59,27 @@ def temperature_scheduler(config):
 
 def calc(config: Optional[JrystalConfigDict] = None, plan: Optional[Plan] = None,
          use_cuda_graph: bool = True, log=None) -> GroundStateEnergyOutput:
+  """All-electron energy mode; a config with `use_pseudopotential: true` (the shipped config.yaml)
+  goes to the norm-conserving driver, as `jrystal -m energy` dispatches."""
   config = config or get_config()
   if config.use_pseudopotential:
-    raise NotImplementedError('pseudopotential drivers are outside the B200 hot path (DESIGN.md)')
+    from . import calc_ground_state_energy_normcons
+    return calc_ground_state_energy_normcons.calc(config, plan, use_cuda_graph, log)
+  return minimise(config, plan, use_cuda_graph, log)
+
+
+def minimise(config: JrystalConfigDict, plan: Optional[Plan] = None, use_cuda_graph: bool = True,
+             log=None, pseudopot=None) -> GroundStateEnergyOutput:
+  """The optimisation loop shared by the all-electron and the norm-conserving drivers.  With
+  `pseudopot` (a NormConservingPseudopotential) the electron count is the valence charge, the
+  external term is the local pseudopotential and the non-local term joins the kinetic slot
+  (calc_ground_state_energy_normcons.py:84-192 of the reference)."""
   crystal = create_crystal(config)
-  _, _, k_vec = create_grids(config, crystal)
+  g_vec, _, k_vec = create_grids(config, crystal)
   freq_mask = create_freq_mask(config, crystal)
   num_kpts = k_vec.shape[0]
-  num_bands = ceil(crystal.num_electron / 2) + config.empty_bands
+  num_electron = pseudopot.num_valence_electrons if pseudopot is not None else crystal.num_electron
+  num_bands = ceil(num_electron / 2) + config.empty_bands
   world, rank = parallel._world()
   use_k_mesh = bool(config.parallel_over_k_mesh) and world > 1
   k0, k1 = parallel.shard_kpoints(num_kpts, world, rank) if use_k_mesh else (0, num_kpts)
@@ -80,15 +93,19 @@ def calc(config: Optional[JrystalConfigDict] = None, plan: Optional[Plan] = None
     og = config.get('orbital_grid', 'auto')
     plan = Plan(crystal.cell_vectors, freq_mask, k_vec[k0:k1], num_bands,
                 orbital_grid=tuple(og) if isinstance(og, (list, tuple)) else og)
-  plan.set_atoms(crystal.positions, crystal.charges)
+  if pseudopot is not None:
+    from ..pseudopotential import normcons
+    normcons.attach(plan, pseudopot, g_vec, kpts=k_vec[k0:k1], positions=crystal.positions)
+  else:
+    plan.set_atoms(crystal.positions, crystal.charges)
   dev = plan.tdev
   rng = np.random.default_rng(config.seed)
-  params_occ = occupation.param_init(rng, num_bands, crystal.num_electron, num_kpts, crystal.spin,
+  params_occ = occupation.param_init(rng, num_bands, num_electron, num_kpts, crystal.spin,
                                      method, config.spin_restricted)
 
   def get_occupation():
     """(spin, kpt, band) on the device; a torch graph for the trainable schemes (lines 109-117)."""
-    o = occupation.occupation(params_occ, num_kpts, crystal.num_electron, crystal.spin, method,
+    o = occupation.occupation(params_occ, num_kpts, num_electron, crystal.spin, method,
                               config.spin_restricted)
     return o if trainable else torch.from_numpy(np.ascontiguousarray(o)).to(dev)
 
@@ -182,6 +199,16 @@ def calc(config: Optional[JrystalConfigDict] = None, plan: Optional[Plan] = None
   en = out[0].cpu().numpy()
   energies = dict(kinetic=float(en[0]), external=float(en[1]), hartree=float(en[2]),
                   xc=float(en[3]), ewald=float(ew), entropy=float(state['entropy']))
+  if pseudopot is not None:
+    # split the kinetic slot (kinetic + non-local) and name the terms as the reference logs them
+    e_nl = torch.zeros(1, dtype=torch.float64, device=dev)
+    if getattr(plan, 'nproj', 0):
+      q, _ = plan.qr_fwd(w_re, w_im)
+      e_nl = plan.nonlocal_energy(q, occ)
+      if use_k_mesh:
+        parallel.allreduce_sum(e_nl)
+    energies.update(kinetic=float(en[0]) - float(e_nl), external_local=float(en[1]),
+                    external_nonlocal=float(e_nl))
   return GroundStateEnergyOutput(
     config=config, crystal=crystal, params_pw={'w_re': w_re, 'w_im': w_im}, occupation=occ,
     density=rho.clone(), total_energy=float(en.sum() + ew), energies=energies,

@@ -26,6 +26,19 @@ def create_freq_mask(config, crystal=None) -> np.ndarray:
   raise ValueError(f'freq_mask_method "{config.freq_mask_method}" is not supported')
 
 
+def create_pseudopotential(config, crystal=None):
+  """opt_utils.py:116-139: the container for `pseudopotential_type` ('nc' family only; ultrasoft
+  is not on the B200 path) from the UPF files in `pseudopotential_file_dir` (required here: the
+  reference's default points into its own checkout, and no UPF files ship with jrystal_b200)."""
+  from ..pseudopotential import NormConservingPseudopotential
+  assert config.use_pseudopotential
+  kind = config.get('pseudopotential_type', 'nc')
+  if kind not in ('normcons', 'normconserving', 'nc'):
+    raise ValueError(f'Pseudopotential type {kind} is not supported.')
+  crystal = crystal or create_crystal(config)
+  return NormConservingPseudopotential.create(crystal, config.get('pseudopotential_file_dir'))
+
+
 def create_grids(config, crystal=None):
   crystal = crystal or create_crystal(config)
   gs = grid.proper_grid_size(config.grid_sizes)

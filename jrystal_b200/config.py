@@ -6,7 +6,8 @@ import yaml
 
 default_config = {
   "crystal": "diamond", "crystal_file_path_path": None, "save_dir": None, "spin": 0,
-  "xc": "lda_x", "use_pseudopotential": False, "pseudopotential_file_dir": None,
+  "xc": "lda_x", "use_pseudopotential": False, "pseudopotential_type": "nc",
+  "pseudopotential_file_dir": None,
   "freq_mask_method": "spherical", "cutoff_energy": 100, "grid_sizes": 64, "k_grid_sizes": 3,
   "occupation": "uniform", "smearing": 0.001, "empty_bands": 8, "spin_restricted": True,
   "ewald_args": {'ewald_eta': 0.1, 'ewald_cutoff': 2e4}, "epoch": 5000, "optimizer": "adam",

@@ -1,0 +1,89 @@
+"""Projectors of the non-local (Kleinman-Bylander) part on the cut-off SPHERE, ready for
+`Plan.set_nonlocal` (jrb_set_nonlocal), and host-side twins of the reference's contractions.
+
+Reference: jrystal/pseudopotential/nloc.py:43-141 builds, for the whole box,
+  Phi[k, (a, b1), m, G] = 4 pi i^{l_b1} e^{-i (G+k).R_a} sum_b2 S_a[b1, b2] Y_{l_b2, m}(G+k) beta_b2(|G+k|)
+with S_a = eigvec * sqrt(eigval) of the atom's D matrix, Y the REAL harmonics of spherical.py and
+beta the transforms of beta.py; energy: F = sum_G c_G Phi_G, E_nl = sum f |F|^2 / Omega
+(nloc.py:143-158, 217-236).  The (kpt, beta, m, x, y, z) array is 68 GB at BASELINE config 4; the
+coefficients vanish outside the sphere, so only Phi[..., mask] ever contributes: (kpt, proj, g),
+1.5 GB there.  Rows that are identically zero (the m-padding of l < l_max) are dropped.
+
+Reference behaviour kept on purpose: |F|^2 is weighted by |eigval| (the sign of a negative D_ii is
+lost through conj(sqrt(eigval)) * sqrt(eigval)), and i^{l} is indexed by the OUTPUT projector b1;
+both are exact for the shipped pseudopotentials (diagonal positive D)."""
+from typing import List, Optional, Sequence
+
+import numpy as np
+
+from .beta import beta_sbt_sphere, max_radius
+from .spherical import batch_sph_harm_real, cartesian_to_spherical
+
+
+def sphere_vectors(g_vector_grid, kpts, freq_mask) -> np.ndarray:
+  """G + k on the sphere, (kpt, g, 3), g in the C-order enumeration of the mask (the compact index
+  of the coefficients, utils.py:279-281)."""
+  g = np.asarray(g_vector_grid, dtype=np.float64)[np.asarray(freq_mask, dtype=bool)]
+  return g[None] + np.asarray(kpts, dtype=np.float64).reshape(-1, 1, 3)
+
+
+def potential_nonlocal_psi_sphere(position, g_vector_grid, kpts, freq_mask, r_grid,
+                                  nonlocal_beta_grid, nonlocal_angular_momentum, nonlocal_d_matrix,
+                                  drop_zero_rows: bool = True,
+                                  kmax: Optional[float] = None) -> np.ndarray:
+  """<beta_i | G + k> on the sphere: complex128 (kpt, proj, g), proj = (atom, beta, m) flattened in
+  the reference's order (atoms concatenated along beta, m fastest).
+  `kmax`: upper end of the radial-transform grid; default max |G + k| over the box and `kpts`, what
+  the reference uses when it transforms these k-points in one call.  The band driver passes the
+  maximum over its whole k-path (the reference transforms the path at once,
+  calc_band_structure_normcons.py:118-123) while building the projectors one k-point at a time."""
+  pos = np.asarray(position, dtype=np.float64).reshape(-1, 3)
+  gk = sphere_vectors(g_vector_grid, kpts, freq_mask)                 # (k, g, 3)
+  kmax = max_radius(g_vector_grid, kpts) if kmax is None else float(kmax)
+  sph = cartesian_to_spherical(gk)
+  radius = np.sqrt((gk * gk).sum(-1))
+  l_max = int(max(int(np.max(l)) for l in nonlocal_angular_momentum))
+  nm = 2 * l_max + 1
+  # real harmonics for every l, m padded to 2 l_max + 1: (l, k, g, m)
+  y_lm = np.zeros((l_max + 1,) + radius.shape + (nm,))
+  for l in range(l_max + 1):
+    y_lm[l, ..., :2 * l + 1] = batch_sph_harm_real(l, sph[..., 1], sph[..., 2])
+  radial = {}
+  blocks: List[np.ndarray] = []
+  for a in range(pos.shape[0]):
+    ls = np.asarray(nonlocal_angular_momentum[a]).astype(int)
+    d = np.asarray(nonlocal_d_matrix[a], dtype=np.float64)
+    key = (id(r_grid[a]), id(nonlocal_beta_grid[a]), tuple(ls))
+    if key not in radial:  # atoms of one species share the radial transform
+      radial[key] = beta_sbt_sphere(r_grid[a], nonlocal_beta_grid[a], ls, radius, kmax)  # (k, b, g)
+    beta = radial[key]
+    eigval, eigvec = np.linalg.eigh(d)
+    s = eigvec * np.sqrt(eigval + 0j)                                 # (b1, b2)
+    yb = y_lm[ls] * np.swapaxes(beta, 0, 1)[..., None]               # (b2, k, g, m)
+    out = np.einsum('ab,bkgm->kamg', s, yb)                          # (k, b1, m, g)
+    phase = np.exp(-1j * (gk @ pos[a]))                               # (k, g)
+    out = out * phase[:, None, None, :] * ((1j) ** ls)[None, :, None, None] * (4 * np.pi)
+    blocks.append(out.reshape(out.shape[0], -1, out.shape[-1]))
+  phi = np.concatenate(blocks, axis=1)
+  if drop_zero_rows:
+    # structural zeros only (m >= 2 l + 1 for every projector feeding the row), so that the row
+    # count does not depend on the k-points
+    keep = np.concatenate([
+      ((np.abs(np.linalg.eigh(np.asarray(d, dtype=np.float64))[1]) > 0)
+       @ (np.arange(nm)[None, :] < 2 * np.asarray(l).astype(int)[:, None] + 1)).reshape(-1) > 0
+      for d, l in zip(nonlocal_d_matrix, nonlocal_angular_momentum)])
+    phi = phi[:, keep]
+  return np.ascontiguousarray(phi)
+
+
+def hamiltonian_nonlocal(coeff_sphere, phi_sphere, vol: float) -> np.ndarray:
+  """Host twin of nloc.py:143-158 on the sphere: coeff (spin, kpt, g, band) (the compact layout of
+  the parameters), phi (kpt, proj, g) -> (spin, kpt, band, band)."""
+  f = np.einsum('skgb,kpg->skbp', np.asarray(coeff_sphere), np.asarray(phi_sphere))
+  return np.einsum('skap,skbp->skab', np.conj(f), f) / vol
+
+
+def energy_nonlocal(coeff_sphere, phi_sphere, vol: float, occupation) -> float:
+  """Host twin of nloc.py:217-236."""
+  h = hamiltonian_nonlocal(coeff_sphere, phi_sphere, vol)
+  return float(np.real(np.sum(np.diagonal(h, axis1=-2, axis2=-1) * np.asarray(occupation))))
