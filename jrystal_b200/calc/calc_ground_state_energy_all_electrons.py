@@ -161,7 +161,7 @@ def minimise(config: JrystalConfigDict, plan: Optional[Plan] = None, use_cuda_gr
   graph = None
   step()  # warm-up outside the capture (one-time attribute calls); counts as step 0
   first_energy = float(out[0].sum().item())
-  if use_cuda_graph and not use_k_mesh and not trainable:
+  if use_cuda_graph and dev.type == 'cuda' and not use_k_mesh and not trainable:
     graph = torch.cuda.CUDAGraph()
     with torch.cuda.graph(graph):
       step()
