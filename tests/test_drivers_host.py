@@ -31,3 +31,117 @@ def test_energy_driver_converges_and_stops(emulated):
 
 def test_band_driver_eigenvalues_are_variational_and_close(emulated):
   gpu_tests.test_band_driver_eigenvalues_are_variational_and_close(emulated)
+
+
+# ---------------------------------------------------------------------------------------------
+# N > 1: the k-mesh layout of the energy drivers on two gloo ranks (one k-point each)
+# ---------------------------------------------------------------------------------------------
+
+def _kmesh_config(upf_dir, normcons):
+  from jrystal_b200.config import get_config
+  kw = dict(crystal='si', grid_sizes=12, k_grid_sizes=[1, 1, 2], cutoff_energy=6.0, empty_bands=2,
+            epoch=4, verbose=False, orbital_grid='full', convergence_condition=1e-12, seed=3,
+            smearing=0.01)
+  if normcons:
+    kw.update(use_pseudopotential=True, pseudopotential_file_dir=upf_dir,
+              occupation='simplex-projector')
+  else:
+    kw.update(crystal='diamond', cutoff_energy=10, occupation='uniform')
+  return get_config(**kw)
+
+
+def _patch_plain():
+  import torch
+  torch.set_num_threads(2)  # two ranks share the box with the test runner
+  from jrystal_b200.calc import (calc_band_structure_all_electrons as band,
+                                 calc_ground_state_energy_all_electrons as energy, opt_utils)
+  energy.Plan = band.Plan = emulated_plan.EmulatedPlan
+  band.Adam = opt_utils.Adam = emulated_plan.EmulatedAdam
+  torch.cuda.synchronize = lambda *a, **k: None
+
+
+def _rank_kmesh(rank, world, port, upf_dir, out_dir):
+  import os
+  import numpy as np
+  import torch.distributed as dist
+  from jrystal_b200 import calc
+  os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
+  dist.init_process_group('gloo', rank=rank, world_size=world)
+  try:
+    _patch_plain()
+    for normcons in (False, True):
+      cfg = _kmesh_config(upf_dir, normcons)
+      cfg.parallel_over_k_mesh = True
+      out = calc.energy(cfg)
+      assert tuple(out.params_pw['w_re'].shape)[1] == 1       # this rank's k-point only
+      np.save(os.path.join(out_dir, f'hist{int(normcons)}_{rank}.npy'),
+              np.array(out.total_energy_history + [out.total_energy]
+                       + [out.energies[k] for k in sorted(out.energies)]))
+      np.save(os.path.join(out_dir, f'rho{int(normcons)}_{rank}.npy'), out.density.numpy())
+  finally:
+    dist.destroy_process_group()
+
+
+def test_gloo_world2_energy_drivers_on_a_k_mesh(emulated, tmp_path):
+  """parallel_over_k_mesh on 2 ranks == 1 rank: parameters / occupations sharded by k-point, rho and
+  E_kin all-reduced between eval_begin and eval_finish, dE/d occ gathered for the occupation
+  update, E_nl all-reduced for the final split (all-electron + uniform occupations; norm-conserving
+  + simplex-projector occupations)."""
+  import os
+  import numpy as np
+  import torch.multiprocessing as mp
+  from jrystal_b200 import calc
+  from tests.test_pseudopotential import golden, write_upf
+  upf_dir = str(tmp_path / 'upf')
+  os.makedirs(upf_dir)
+  write_upf(os.path.join(upf_dir, 'Si.pz-vbc.UPF'), golden())
+  port = 33500 + (os.getpid() % 2000)
+  mp.spawn(_rank_kmesh, args=(2, port, upf_dir, str(tmp_path)), nprocs=2, join=True)
+  for normcons in (False, True):
+    one = calc.energy(_kmesh_config(upf_dir, normcons))
+    want = np.array(one.total_energy_history + [one.total_energy]
+                    + [one.energies[k] for k in sorted(one.energies)])
+    for rank in range(2):
+      got = np.load(tmp_path / f'hist{int(normcons)}_{rank}.npy')
+      np.testing.assert_allclose(got, want, rtol=1e-10, atol=1e-12)
+      np.testing.assert_allclose(np.load(tmp_path / f'rho{int(normcons)}_{rank}.npy'),
+                                 one.density.numpy(), rtol=1e-9, atol=1e-12)
+
+
+def _band_config():
+  return gpu_tests._config(epoch=3, band_structure_empty_bands=2, band_structure_epoch=1500,
+                           k_path_fine_tuning_epoch=600, num_kpoints=2, k_path_special_points='GX',
+                           optimizer_args={'learning_rate': 0.02, 'b1': 0.9, 'b2': 0.99})
+
+
+def _rank_kpath(rank, world, port, out_dir):
+  import os
+  import numpy as np
+  import torch.distributed as dist
+  from jrystal_b200 import calc
+  os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
+  dist.init_process_group('gloo', rank=rank, world_size=world)
+  try:
+    _patch_plain()
+    out = calc.band(_band_config())
+    np.save(os.path.join(out_dir, f'eig{rank}.npy'), out.eigenvalues)
+  finally:
+    dist.destroy_process_group()
+
+
+def test_gloo_world2_band_driver_splits_the_k_path(emulated, tmp_path):
+  """parallel_over_k_path: each rank walks its contiguous chunk of the path without communication
+  (the reference's pmap), the eigenvalues are gathered at the end; every rank holds the whole band
+  structure and it agrees with the one-rank walk at the convergence level of the minimisation."""
+  import os
+  import numpy as np
+  import torch.multiprocessing as mp
+  from jrystal_b200 import calc
+  port = 35500 + (os.getpid() % 2000)
+  mp.spawn(_rank_kpath, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+  e0, e1 = np.load(tmp_path / 'eig0.npy'), np.load(tmp_path / 'eig1.npy')
+  np.testing.assert_array_equal(e0, e1)
+  one = calc.band(_band_config()).eigenvalues
+  assert e0.shape == one.shape
+  np.testing.assert_allclose(e0[0, 0], one[0, 0], rtol=0, atol=1e-10)   # same first k-point, same walk
+  assert np.abs(e0 - one).max() < 2e-3                                   # second: cold vs warm start
