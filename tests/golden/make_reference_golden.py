@@ -17,6 +17,7 @@ seed) and stores their outputs in tests/golden/reference_<case>.npz:
   jrystal/_src/braket.py      expectation (kinetic mode diagonal; real mode diagonal and full)
   jrystal/_src/occupation.py  uniform, gamma, simplex_projector(_init), proj, idempotent
   jrystal/_src/entropy.py     fermi_dirac
+  jrystal/_src/xc.py          sigma_r_fn (the functional-free part of the GGA branch)
 
 and, for the norm-conserving rows (tests/golden/reference_si_normcons.npz), from the shipped
 pseudopotential/normconserving/Si.pz-vbc.UPF:
@@ -78,6 +79,7 @@ def core_case(key, c):
   grid_m, utils, pw, energy = ref('_src.grid'), ref('_src.utils'), ref('_src.pw'), ref('_src.energy')
   potential, kinetic, braket = ref('_src.potential'), ref('_src.kinetic'), ref('_src.braket')
   occupation, entropy = ref('_src.occupation'), ref('_src.entropy')
+  xc_m = ref('_src.xc')  # imports with jax_xc stubbed; only the functional-free sigma_r_fn is called
 
   cell, pos, chg = structures.load(c['name'], None)
   gs = [int(g) for g in grid_m.proper_grid_size(c['grid'])]
@@ -118,6 +120,7 @@ def core_case(key, c):
   v_full = braket.expectation(psi, v_r, vol, diagonal=False, mode='real')
   out = dict(
     expect_v_diag=A(v_diag), expect_v_full=A(v_full),
+    sigma_r=G(xc_m.sigma_r_fn(rho, g_vec)),  # |grad rho|^2 of the GGA branch (xc.py:94-112)
     vol=np.array(vol), grid=np.array(gs), kpts=A(kpts), mask=mask,
     g_vec_sum=np.array(np.abs(A(g_vec)).sum()), g_vec_corner=A(g_vec)[1, 2, 3],
     r_vec_corner=A(r_vec)[1, 2, 3], occ=occ,

@@ -99,6 +99,9 @@ def test_oracle_matches_reference_source(key):
   assert relerr(np.asarray(rp.expectation(psi, v_r, s.vol, diagonal=False, mode='real')),
                 g['expect_v_full']) < 1e-12
 
+  # |grad rho|^2 as the GGA branch forms it (complex absolute square on the FFT grid)
+  assert relerr(_grid_sample(np.asarray(rp.sigma_r_fn(rho, s.g_vec))), g['sigma_r']) < 1e-11
+
   ne = s.num_electrons
   np.testing.assert_allclose(rp.occupation_uniform(s.num_k, ne, num_bands=c['nb']).numpy(),
                              g['occ_uniform'], rtol=1e-15)
