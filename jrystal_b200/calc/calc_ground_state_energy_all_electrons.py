@@ -87,12 +87,15 @@ def minimise(config: JrystalConfigDict, plan: Optional[Plan] = None, use_cuda_gr
 
   method = config.occupation
   trainable = occupation.trainable(method)
-  if not config.spin_restricted:
-    raise NotImplementedError('spin-unrestricted energy mode is not wired into the driver yet')
+  # spin_restricted: false -> two spin channels (pw.py:88-91), per-spin densities and potentials;
+  # the device implements the spin-scaled exchange only and refuses other functionals loudly
+  num_spin = 1 if config.spin_restricted else 2
   if plan is None:
     og = config.get('orbital_grid', 'auto')
-    plan = Plan(crystal.cell_vectors, freq_mask, k_vec[k0:k1], num_bands,
+    plan = Plan(crystal.cell_vectors, freq_mask, k_vec[k0:k1], num_bands, num_spin=num_spin,
                 orbital_grid=tuple(og) if isinstance(og, (list, tuple)) else og)
+  elif plan.ns != num_spin:
+    raise ValueError(f'the plan has {plan.ns} spin channel(s), spin_restricted={config.spin_restricted}')
   if pseudopot is not None:
     from ..pseudopotential import normcons
     normcons.attach(plan, pseudopot, g_vec, kpts=k_vec[k0:k1], positions=crystal.positions)
@@ -112,7 +115,7 @@ def minimise(config: JrystalConfigDict, plan: Optional[Plan] = None, use_cuda_gr
   occ_t = get_occupation()
   entropy = float(occupation.fermi_dirac_entropy_torch(occ_t.detach(), config.eps))
   # parameters: the same global stream on every rank, each keeps its k block
-  shape = (1, num_kpts, plan.ng, num_bands)
+  shape = (num_spin, num_kpts, plan.ng, num_bands)
   w_re = torch.from_numpy(np.ascontiguousarray(rng.random(shape)[:, k0:k1])).to(dev)
   w_im = torch.from_numpy(np.ascontiguousarray(rng.random(shape)[:, k0:k1])).to(dev)
   occ = occ_t.detach()[:, k0:k1].contiguous()
@@ -129,7 +132,7 @@ def minimise(config: JrystalConfigDict, plan: Optional[Plan] = None, use_cuda_gr
     # the optimiser updates the storage the leaves view
     for leaf, p in zip(occ_leaves, opt_occ.params):
       assert p.data_ptr() == leaf.data_ptr()
-  dbuf, rho, e_kin = parallel.density_buffers((1, plan.nx, plan.ny, plan.nz), dev)
+  dbuf, rho, e_kin = parallel.density_buffers((num_spin, plan.nx, plan.ny, plan.nz), dev)
   out = (torch.empty(4, dtype=torch.float64, device=dev), torch.empty_like(w_re),
          torch.empty_like(w_im))
   sched = temperature_scheduler(config)

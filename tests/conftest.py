@@ -12,6 +12,20 @@ def pytest_configure(config):
   config.addinivalue_line('markers', 'gpu: needs a CUDA device (run on the B200 box)')
 
 
+# GPU tests written after this round's GPU budget was spent: their bodies are verified on the CPU
+# stand-in only.  They are ordered after the hardware-verified suite so that `pytest -x` cannot
+# hide it behind a first failure among them.  Drop a file from this list once it has passed on a B200.
+NOT_YET_RUN_ON_HARDWARE = ['test_reference_golden.py', 'test_pseudopotential.py',
+                           'test_drivers_host.py']
+
+
+def pytest_collection_modifyitems(config, items):
+  def rank(item):
+    name = item.fspath.basename
+    return NOT_YET_RUN_ON_HARDWARE.index(name) + 1 if name in NOT_YET_RUN_ON_HARDWARE else 0
+  items.sort(key=rank)  # stable: keeps the collection order inside each group
+
+
 @pytest.fixture(scope='session')
 def cuda_device():
   import torch
@@ -19,3 +33,27 @@ def cuda_device():
     pytest.skip('no CUDA device')
   torch.cuda.set_device(0)
   return 0
+
+
+# Dual-backend tests: the same body on the product ('cuda', marked gpu: jrystal_b200.Plan through
+# the C ABI) and on the oracle-backed CPU stand-in ('emulated', tests/emulated_plan.py), which
+# checks the host logic of the drivers and the test's own arithmetic without a GPU.
+BACKENDS = [pytest.param('cuda', marks=pytest.mark.gpu), 'emulated']
+
+
+@pytest.fixture
+def backend(request, monkeypatch):
+  """(kind, Plan class, to-device function); parametrize indirectly with BACKENDS."""
+  import numpy as np
+  import torch
+  kind = request.param
+  if kind == 'cuda':
+    if not torch.cuda.is_available():
+      pytest.skip('no CUDA device')
+    torch.cuda.set_device(0)
+    import jrystal_b200 as jb
+    from tests.common import to_dev
+    return kind, jb.Plan, to_dev
+  from tests import emulated_plan
+  emulated_plan.patch_drivers(monkeypatch)
+  return kind, emulated_plan.EmulatedPlan, lambda a: torch.from_numpy(np.ascontiguousarray(a))

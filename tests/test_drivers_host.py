@@ -145,3 +145,43 @@ def test_gloo_world2_band_driver_splits_the_k_path(emulated, tmp_path):
   assert e0.shape == one.shape
   np.testing.assert_allclose(e0[0, 0], one[0, 0], rtol=0, atol=1e-10)   # same first k-point, same walk
   assert np.abs(e0 - one).max() < 2e-3                                   # second: cold vs warm start
+
+
+# ---------------------------------------------------------------------------------------------
+# spin-unrestricted energy mode (spin_restricted: false), both backends
+# ---------------------------------------------------------------------------------------------
+
+from tests.conftest import BACKENDS  # noqa: E402
+
+
+@pytest.mark.parametrize('backend', BACKENDS, indirect=True)
+def test_spin_unrestricted_energy_driver(backend):
+  """Two spin channels through the energy-mode loop (pw.py:88-91 ns = 2, spin-scaled lda_x,
+  xc.py:54-64): 5 Adam steps == the oracle's value_and_grad + the same Adam; per-spin density."""
+  import numpy as np
+  from oracle import reference_port as rp
+  from jrystal_b200 import calc
+  from tests.common import relerr
+  kind = backend[0]
+  cfg = gpu_tests._config(epoch=5, spin_restricted=False, empty_bands=3, orbital_grid='full')
+  out = calc.energy(cfg, use_cuda_graph=(kind == 'cuda'))
+  c = out.crystal
+  s = rp.System(c.cell_vectors, c.positions, c.charges, [12, 12, 12], k_grid_sizes=[1, 1, 2],
+                cutoff_energy=10, mask_method='spherical')
+  nb = int(np.ceil(c.num_electron / 2)) + 3
+  shape = (2, s.num_k, s.num_g, nb)
+  assert tuple(out.params_pw['w_re'].shape) == shape and out.density.shape[0] == 2
+  rng = np.random.default_rng(cfg.seed)
+  w_re, w_im = rng.random(shape), rng.random(shape)
+  occ = rp.occupation_uniform(s.num_k, s.num_electrons, spin=c.spin, num_bands=nb,
+                              spin_restricted=False).numpy()
+  assert relerr(out.occupation.cpu().numpy(), occ) < 1e-14
+  st = [np.zeros(shape) for _ in range(4)]
+  for t in range(1, cfg.epoch + 1):
+    ref = rp.energy_and_grad(s, w_re, w_im, occ)
+    assert abs(out.total_energy_history[t - 1] - ref['e_tot']) < 1e-10 * abs(ref['e_tot']), t
+    gpu_tests._adam_numpy(w_re, ref['g_re'], st[0], st[1], t)
+    gpu_tests._adam_numpy(w_im, ref['g_im'], st[2], st[3], t)
+  ref = rp.energy_and_grad(s, w_re, w_im, occ)
+  assert abs(out.total_energy - out.energies['ewald'] - ref['e_tot']) < 1e-10 * abs(ref['e_tot'])
+  assert relerr(out.density.cpu().numpy(), ref['density']) < 1e-8
