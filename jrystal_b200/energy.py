@@ -56,6 +56,16 @@ def kinetic(g_vector_grid, kpts, coeff_grid, occupation=None):
   return torch.sum(t * _pw._occ(c.plan, occupation))
 
 
+def nuclear_repulsion(position, charge, cell_vectors, g_vector_grid, vol, ewald_eta: float,
+                      ewald_cutoff: float):
+  """jrystal/_src/energy.py:214-243: Ewald energy of the point charges with the reference's own
+  truncation (translations up to `ewald_cutoff`, the G grid as given).  Host numpy."""
+  from .ewald import ewald_coulomb_repulsion
+  from .grid import translation_vectors
+  return ewald_coulomb_repulsion(position, charge, g_vector_grid, vol, ewald_eta,
+                                 translation_vectors(cell_vectors, ewald_cutoff))
+
+
 def xc_energy(density_grid, g_vector_grid, vol, xc_type: str = 'lda_x', kohn_sham: bool = False):
   """jrystal/_src/energy.py:185-211 (LDA functionals)."""
   del g_vector_grid

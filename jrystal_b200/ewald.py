@@ -25,8 +25,50 @@ def _shells(vectors, rmax):
   return n @ vectors
 
 
-def ewald_coulomb_repulsion(positions, charges, cell_vectors, ewald_eta: float = None,
-                            tol: float = 1e-14) -> float:
+def ewald_coulomb_repulsion(positions, charges, g_vector_grid, vol=None, ewald_eta=None,
+                            ewald_grid=None, tol: float = 1e-14) -> float:
+  """Two call forms.
+  Reference form (jrystal/_src/ewald.py:21-86): (positions, charges, g_vector_grid (x, y, z, 3), vol,
+  ewald_eta, ewald_grid (num, 3) from grid.translation_vectors) -> the sums truncated at exactly
+  those two grids, as the reference computes them.
+  Converged form: (positions, charges, cell_vectors (3, 3), ewald_eta=None, tol=...) -> lattice
+  sums run until the neglected terms are below `tol`; what the drivers use."""
+  third = np.asarray(g_vector_grid, dtype=np.float64)
+  if third.ndim == 4:
+    if vol is None or ewald_eta is None or ewald_grid is None:
+      raise TypeError('reference form needs vol, ewald_eta and ewald_grid')
+    return _ewald_on_given_grids(positions, charges, third, float(vol), float(ewald_eta), ewald_grid)
+  if third.shape != (3, 3):
+    raise ValueError('third argument: g_vector_grid (x, y, z, 3) or cell_vectors (3, 3)')
+  if ewald_grid is not None:
+    raise TypeError('ewald_grid belongs to the reference form (g_vector_grid as third argument)')
+  eta = vol if (vol is not None and ewald_eta is None) else ewald_eta  # positional eta after the cell
+  return ewald_converged(positions, charges, third, eta, tol)
+
+
+def _ewald_on_given_grids(positions, charges, g_vector_grid, vol, eta, ewald_grid) -> float:
+  """The reference's truncation: real-space sum over the given translations (a term with
+  |tau - T| <= 1e-9 is dropped), reciprocal sum over the given G grid without G = 0."""
+  pos = np.asarray(positions, dtype=np.float64).reshape(-1, 3)
+  z = np.asarray(charges, dtype=np.float64).reshape(-1)
+  t = np.asarray(ewald_grid, dtype=np.float64).reshape(-1, 3)
+  g = g_vector_grid.reshape(-1, 3)[1:]                           # C order: element 0 is G = 0
+  g2 = np.sum(g * g, axis=1)
+  tau = pos[None, :, :] - pos[:, None, :]                        # tau[i, j] = R_j - R_i
+  real = np.zeros(tau.shape[:2])
+  for i in range(pos.shape[0]):                                   # bounded memory: na x nt per row
+    d = np.sqrt(np.sum((tau[i][:, None, :] - t[None]) ** 2, axis=-1) + 1e-20)
+    d = np.where(d <= 1e-9, 1e20, d)
+    real[i] = np.sum(erfc(eta * d) / d, axis=1)
+  w = np.exp(-g2 / (4 * eta * eta)) / g2
+  recip = np.einsum('g,ijg->ij', w, np.cos(np.einsum('ijd,gd->ijg', tau, g))) * 4 * np.pi / vol
+  pair = 0.5 * z @ (real + recip) @ z
+  single = -np.sum(z * z) * eta / math.sqrt(math.pi) - np.sum(z) ** 2 * math.pi / (eta * eta * vol * 2)
+  return float(pair + single)
+
+
+def ewald_converged(positions, charges, cell_vectors, ewald_eta: float = None,
+                    tol: float = 1e-14) -> float:
   pos = np.asarray(positions, dtype=np.float64).reshape(-1, 3)
   z = np.asarray(charges, dtype=np.float64).reshape(-1)
   a = np.asarray(cell_vectors, dtype=np.float64).reshape(3, 3)

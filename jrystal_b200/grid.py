@@ -59,6 +59,60 @@ def r_vectors(cell_vectors, grid_sizes):
   return _frequency_grid(cell_vectors, grid_sizes, True)
 
 
+def translation_vectors(cell_vectors, cutoff=1e4):
+  """Real-space translations of the reference's Ewald sum (grid.py:213-236): the r-vector lattice
+  of n^3 cells, n = ceil(cutoff / |a1 + a2 + a3|^2), flattened to (n^3, 3)."""
+  a = np.asarray(cell_vectors, dtype=np.float64)
+  n = int(np.ceil(cutoff / np.linalg.norm(a.sum(axis=0)) ** 2))
+  return _frequency_grid(a, [n] * a.shape[0], False).reshape(-1, a.shape[0])
+
+
+def g2cell_vectors(g_vector_grid):
+  """Cell vectors back from a G grid: least squares of G against the integer frequencies
+  (grid.py:428-448)."""
+  g = np.asarray(g_vector_grid, dtype=np.float64)
+  a = g_vectors(np.eye(3), g.shape[:-1]).reshape(-1, 3)
+  return np.linalg.inv(np.linalg.solve(a.T @ a, a.T @ g.reshape(-1, 3)))
+
+
+def r2cell_vectors(r_vector_grid):
+  """Cell vectors back from an r grid (grid.py:451-470)."""
+  r = np.asarray(r_vector_grid, dtype=np.float64)
+  d = r_vectors(np.eye(3), r.shape[:-1]).reshape(-1, 3)
+  return np.linalg.solve(d.T @ d, d.T @ r.reshape(-1, 3))
+
+
+def g2r_vector_grid(g_vector_grid, cell_vectors=None):
+  """grid.py:377-401."""
+  g = np.asarray(g_vector_grid)
+  cell = g2cell_vectors(g) if cell_vectors is None else cell_vectors
+  return r_vectors(cell, g.shape[:-1])
+
+
+def r2g_vector_grid(r_vector_grid, cell_vectors=None):
+  """grid.py:404-425."""
+  r = np.asarray(r_vector_grid)
+  cell = r2cell_vectors(r) if cell_vectors is None else cell_vectors
+  return g_vectors(cell, r.shape[:-1])
+
+
+def grid_vector_radius(grid_vector):
+  """|v| at every grid point (grid.py:352-374)."""
+  v = np.asarray(grid_vector, dtype=np.float64)
+  return np.sqrt(np.sum(v * v, axis=-1))
+
+
+def half_frequency_shape(grid_sizes):
+  """Shape of the block of frequencies |f| <= ((n - 1) // 2) // 2 per axis: what cubic_mask keeps
+  (grid.py:57-69)."""
+  out = []
+  for n in (int(v) for v in grid_sizes):
+    half = ((n - 1) // 2) // 2
+    lower = -((n - 1) // 2) // 2        # floor division of the negative bound, as the reference
+    out.append((half + 1) + (-lower))
+  return tuple(out)
+
+
 def monkhorst_pack(grid_sizes):
   sizes = [int(s) for s in grid_sizes]
   idx = np.stack(np.meshgrid(*[np.arange(s) for s in sizes], indexing='ij'), axis=-1)

@@ -60,6 +60,12 @@ def _capped_simplex(x, total: float):
   return 1.0 - push_down(1.0 - x, n - total)
 
 
+def proj(x, sum):  # noqa: A002 (the reference's argument name)
+  """jrystal/_src/occupation.py:295-338 under its own name: projection of x (1-D torch tensor in
+  [0, 1]) onto {0 <= y <= 1, sum(y) = sum}."""
+  return _capped_simplex(x, float(sum))
+
+
 def simplex_projector_init(num_bands: int, num_kpts: int) -> dict:
   """jrystal/_src/occupation.py:281-296: logits (arange(n) - n // 2) * 0.1, both spins alike."""
   import torch
@@ -123,7 +129,7 @@ def idempotent(params: dict, num_kpts: int, spin_restricted: bool = True):
 
 
 def param_init(key, num_bands: int, num_electrons: int, num_kpts: int, spin: int = 0,
-               method: str = "uniform", spin_restricted: bool = True):
+               method: str = "simplex-projector", spin_restricted: bool = True):
   """jrystal/_src/occupation.py:240-258.  Parameter-free methods return the occupations as a numpy
   array; the trainable ones a dict of torch leaves (requires_grad) on the current device."""
   if method == "uniform":
@@ -138,7 +144,7 @@ def param_init(key, num_bands: int, num_electrons: int, num_kpts: int, spin: int
 
 
 def occupation(params, num_kpts: int, num_electrons: Optional[int] = None, spin: int = 0,
-               method: str = "uniform", spin_restricted: bool = True):
+               method: str = "simplex-projector", spin_restricted: bool = True):
   """jrystal/_src/occupation.py:261-278."""
   if method in ("uniform", "gamma"):
     return params

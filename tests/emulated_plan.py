@@ -128,6 +128,14 @@ class EmulatedPlan:
       v = v + rp.xc_density(rho, kohn_sham, xc, self.g_vec)
     return v.contiguous()
 
+  def fft3d(self, x, inverse, out=None):
+    assert x.dtype == C128 and tuple(x.shape[-3:]) == (self.nx, self.ny, self.nz)
+    y = (torch.fft.ifftn if inverse else torch.fft.fftn)(x, dim=(-3, -2, -1))
+    if out is not None:
+      out.copy_(y)
+      return out
+    return y
+
   def prepare_potential(self, veff):
     self._prepared = veff.clone()
 

@@ -235,6 +235,7 @@ def occupation_case():
   w_dn = rng.random((nb * nk, (ne - 2) // 2 * nk))
   idem = {'param_up': {'w_re': w_up}, 'param_down': {'w_re': w_dn}}
   init = occupation.simplex_projector_init(nb, nk)
+  proj_x = np.random.default_rng(8).random(11)
   out = dict(
     nk=np.array(nk), nb=np.array(nb), ne=np.array(ne), logits_up=logits_up, logits_down=logits_dn,
     w_up=w_up, w_down=w_dn,
@@ -242,6 +243,8 @@ def occupation_case():
     simplex_spin2=A(occupation.simplex_projector(params, ne, spin=2, spin_restricted=False)),
     simplex_init_up=A(init['param_up']), simplex_init_down=A(init['param_down']),
     simplex_from_init=A(occupation.simplex_projector(init, ne)),
+    proj_input=proj_x, proj_down=A(occupation.proj(proj_x, 3.0)),   # sum(x) > 3: push down
+    proj_up=A(occupation.proj(proj_x * 0.3, 6.0)),                   # sum(0.3 x) < 6: push up
     idempotent_unrestricted=A(occupation.idempotent(idem, nk, spin_restricted=False)),
     idempotent_restricted=A(occupation.idempotent({'param_up': {'w_re': w_up},
                                                    'param_down': {'w_re': w_up}}, nk)),
@@ -249,6 +252,59 @@ def occupation_case():
   np.savez_compressed(os.path.join(HERE, 'reference_occupation.npz'), **out)
   print('occupation: sums', out['simplex_restricted'].sum(), out['idempotent_unrestricted'].sum(),
         '-> reference_occupation.npz')
+
+
+API_MODULES = {  # jrystal_b200 module -> reference module it mirrors
+  'pw': '_src.pw', 'grid': '_src.grid', 'energy': '_src.energy', 'potential': '_src.potential',
+  'kinetic': '_src.kinetic', 'hamiltonian': '_src.hamiltonian', 'occupation': '_src.occupation',
+  'ewald': '_src.ewald', 'pseudopotential.load': 'pseudopotential.load',
+  'pseudopotential.local': 'pseudopotential.local', 'pseudopotential.beta': 'pseudopotential.beta',
+  'pseudopotential.nloc': 'pseudopotential.nloc',
+  'pseudopotential.spherical': 'pseudopotential.spherical',
+}
+
+
+def api_signatures():
+  """Parameter names, order and defaults of every public function of the reference modules the
+  host package mirrors (inspect.signature over the modules as imported here) ->
+  tests/golden/reference_api_signatures.json; tests/test_reference_golden.py holds
+  jrystal_b200's functions of the same name to them (the drop-in claim of the Python API)."""
+  import inspect
+  import json
+  out = {}
+  for ours, theirs in API_MODULES.items():
+    mod = ref(theirs)
+    out[ours] = {
+      name: [[p.name, None if p.default is inspect.Parameter.empty else repr(p.default)]
+             for p in inspect.signature(fn).parameters.values()]
+      for name, fn in inspect.getmembers(mod, inspect.isfunction)
+      if not name.startswith('_') and fn.__module__ == mod.__name__}
+  with open(os.path.join(HERE, 'reference_api_signatures.json'), 'w') as f:
+    json.dump(out, f, indent=1, sort_keys=True)
+  print('api signatures:', sum(len(v) for v in out.values()), 'functions ->',
+        'reference_api_signatures.json')
+
+
+def grid_helpers_case():
+  """grid.py set-up helpers and the Ewald sum on given grids, on the Si2 cell."""
+  grid_m, ewald = ref('_src.grid'), ref('_src.ewald')
+  cell, pos, chg = structures.load('si', None)
+  gs = [8, 9, 10]
+  g, r = grid_m.g_vectors(cell, gs), grid_m.r_vectors(cell, gs)
+  tv = grid_m.translation_vectors(cell, 3e3)
+  vol = float(abs(np.linalg.det(cell)))
+  out = dict(
+    grid=np.array(gs), translation_cutoff=np.array(3e3), translation_vectors=A(tv),
+    g2cell=A(grid_m.g2cell_vectors(g)), r2cell=A(grid_m.r2cell_vectors(r)),
+    g2r_corner=A(grid_m.g2r_vector_grid(g))[1, 2, 3], r2g_corner=A(grid_m.r2g_vector_grid(r))[1, 2, 3],
+    radius_corner=A(grid_m.grid_vector_radius(g))[1, 2, 3],
+    half_frequency_shapes=np.array([grid_m.half_frequency_shape(n) for n in
+                                    ([7, 8, 9], [12, 12, 12], [16, 5, 6], [1, 2, 3])]),
+    ewald_eta=np.array(0.25),
+    ewald=np.array(float(ewald.ewald_coulomb_repulsion(pos, chg, g, vol, 0.25, tv))),
+  )
+  np.savez_compressed(os.path.join(HERE, 'reference_grid_helpers.npz'), **out)
+  print('grid helpers: ewald', float(out['ewald']), '-> reference_grid_helpers.npz')
 
 
 def main():
@@ -259,6 +315,10 @@ def main():
     core_case(key, c)
   if not only or 'si_normcons' in only:
     normcons_case()
+  if not only or 'api' in only:
+    api_signatures()
+  if not only or 'grid_helpers' in only:
+    grid_helpers_case()
   if not only or 'occupation' in only:
     with np.errstate(divide='ignore', invalid='ignore'):  # proj() divides by n - arange(n) - 1
       occupation_case()

@@ -186,6 +186,144 @@ def test_occupation_maps_match_reference_source():
   assert relerr(occupation.simplex_projector(cpu_init, ne).numpy(), g['simplex_from_init']) < 1e-13
 
 
+def test_grid_helpers_ewald_and_reciprocal_potentials_match_reference_source():
+  """Set-up helpers of grid.py, the Ewald sum on the reference's own truncation grids
+  (ewald.py:21-86, energy.nuclear_repulsion) and the stand-alone G-space potentials
+  (potential.hartree_reciprocal / external_reciprocal) of the host package."""
+  from jrystal_b200 import energy, ewald, grid, occupation, potential
+  from oracle import structures
+  g = np.load(os.path.join(HERE, 'golden', 'reference_grid_helpers.npz'))
+  cell, pos, chg = structures.load('si', None)
+  gs = [int(v) for v in g['grid']]
+  gv, rv = grid.g_vectors(cell, gs), grid.r_vectors(cell, gs)
+  tv = grid.translation_vectors(cell, float(g['translation_cutoff']))
+  np.testing.assert_allclose(tv, g['translation_vectors'], rtol=1e-14, atol=1e-12)
+  np.testing.assert_allclose(grid.g2cell_vectors(gv), g['g2cell'], rtol=1e-11, atol=1e-12)
+  np.testing.assert_allclose(grid.g2cell_vectors(gv), cell, rtol=1e-11, atol=1e-12)
+  np.testing.assert_allclose(grid.r2cell_vectors(rv), g['r2cell'], rtol=1e-11, atol=1e-12)
+  np.testing.assert_allclose(grid.g2r_vector_grid(gv)[1, 2, 3], g['g2r_corner'], rtol=1e-11, atol=1e-12)
+  np.testing.assert_allclose(grid.r2g_vector_grid(rv)[1, 2, 3], g['r2g_corner'], rtol=1e-11, atol=1e-12)
+  np.testing.assert_allclose(grid.grid_vector_radius(gv)[1, 2, 3], g['radius_corner'], rtol=1e-15)
+  shapes = [grid.half_frequency_shape(n) for n in ([7, 8, 9], [12, 12, 12], [16, 5, 6], [1, 2, 3])]
+  np.testing.assert_array_equal(np.array(shapes), g['half_frequency_shapes'])
+  vol = float(abs(np.linalg.det(cell)))
+  e = ewald.ewald_coulomb_repulsion(pos, chg, gv, vol, float(g['ewald_eta']), tv)
+  assert _close(e, g['ewald'], 1e-13)
+  assert _close(energy.nuclear_repulsion(pos, chg, cell, gv, vol, float(g['ewald_eta']),
+                                         float(g['translation_cutoff'])), g['ewald'], 1e-13)
+  with pytest.raises(TypeError):
+    ewald.ewald_coulomb_repulsion(pos, chg, gv)                     # reference form needs the grids
+  assert _close(ewald.ewald_coulomb_repulsion(pos, chg, cell), g['ewald'], 1e-7)   # converged form
+  # per-case goldens: nuclear repulsion with the config defaults, V_H(G), V_ext(G)
+  for key, c in mg.CASES.items():
+    r = _ref(key)
+    s, w_re, w_im, occ = mg.inputs(c)
+    if key == 'diamond_16_sph':
+      assert _close(energy.nuclear_repulsion(s.positions, s.charges, s.cell, s.g_vec, s.vol, 0.1, 2e4),
+                    r['e_nuc'], 1e-12)
+    v_ext = potential.external_reciprocal(s.positions, s.charges, s.g_vec, s.vol)
+    assert relerr(_grid_sample(v_ext), r['v_ext_reciprocal']) < 1e-12
+    q = rp.unitary_matrix(torch.from_numpy(w_re), torch.from_numpy(w_im))
+    rho_g = rp.density_grid_reciprocal(rp.expand_coefficient(q, s.mask), s.vol, torch.from_numpy(occ))
+    for arr in (rho_g, rho_g.numpy()):                               # torch tensor and numpy array
+      v_h = np.asarray(potential.hartree_reciprocal(arr, s.g_vec))
+      assert relerr(_grid_sample(v_h), r['v_har_reciprocal']) < 1e-12
+    v_ks = np.asarray(potential.hartree_reciprocal(rho_g, s.g_vec, kohn_sham=True))
+    assert relerr(v_ks, 2 * np.asarray(potential.hartree_reciprocal(rho_g, s.g_vec))) < 1e-15
+  o = np.load(os.path.join(HERE, 'golden', 'reference_occupation.npz'))
+  x = torch.from_numpy(o['proj_input'])
+  assert relerr(occupation.proj(x, 3.0).numpy(), o['proj_down']) < 1e-13
+  assert relerr(occupation.proj(0.3 * x, 6.0).numpy(), o['proj_up']) < 1e-13
+  assert relerr(rp.occupation_proj(x, 3.0).numpy(), o['proj_down']) < 1e-13
+  assert relerr(rp.occupation_proj(0.3 * x, 6.0).numpy(), o['proj_up']) < 1e-13
+
+
+# names the host package mirrors with a DIFFERENT contract, and why (anything else must match the
+# reference's parameter list: same names, same order, same defaults; extra trailing keyword
+# parameters with defaults are allowed)
+API_DEVIATIONS = {
+  'grid.monkhorst_pack': 'ase\'s function in the reference (not part of its API); ours names the argument grid_sizes',
+  'ewald.ewald_coulomb_repulsion': 'accepts the reference form AND a converged (cell_vectors) form; vol / eta / grid therefore default to None',
+  'pseudopotential.load.parse_pp_info': 'internal helper, same dict out',
+  'pseudopotential.load.parse_pp_nonlocal': 'internal helper, same dict out',
+  'pseudopotential.beta.sbt_numerical': 'kmax is required here (None is a bug in the reference: linspace to None); delta_r override not offered',
+  'pseudopotential.nloc.energy_nonlocal': 'sphere layout: coefficients (s, k, g, b) and projectors (k, proj, g) instead of the dense box',
+  'pseudopotential.nloc.hamiltonian_nonlocal': 'sphere layout, as above',
+}
+
+
+def test_python_api_signatures_match_reference_source():
+  """Drop-in check of the host API: every public function of jrystal_b200 that carries a
+  reference function's name takes the reference's parameters (names, order, defaults), read from
+  the reference modules themselves (tests/golden/reference_api_signatures.json)."""
+  import importlib
+  import inspect
+  import json
+  with open(os.path.join(HERE, 'golden', 'reference_api_signatures.json')) as f:
+    ref_api = json.load(f)
+  checked = 0
+  for mod_name, funcs in ref_api.items():
+    mod = importlib.import_module('jrystal_b200.' + mod_name)
+    for name, ref_params in funcs.items():
+      fn = getattr(mod, name, None)
+      if fn is None or not inspect.isfunction(fn) or f'{mod_name}.{name}' in API_DEVIATIONS:
+        continue
+      ours = [[p.name, None if p.default is inspect.Parameter.empty else repr(p.default)]
+              for p in inspect.signature(fn).parameters.values()]
+      head, extra = ours[:len(ref_params)], ours[len(ref_params):]
+      for (on, od), (rn, rd) in zip(head, ref_params):
+        assert on == rn, f'{mod_name}.{name}: parameter {on!r} vs reference {rn!r}'
+        assert od == rd or rd is None, f'{mod_name}.{name}({on}): default {od} vs reference {rd}'
+      assert len(head) == len(ref_params), f'{mod_name}.{name}: missing parameters {ref_params[len(head):]}'
+      assert all(d is not None for _, d in extra), f'{mod_name}.{name}: extra required parameters {extra}'
+      checked += 1
+  assert checked >= 40, checked
+  # the core of the hot path's API must all be there
+  for mod_name, names in {'pw': ['param_init', 'coeff', 'wave_grid', 'density_grid', 'density_grid_reciprocal'],
+                          'energy': ['hartree', 'external', 'kinetic', 'xc_energy', 'total_energy', 'nuclear_repulsion'],
+                          'potential': ['hartree_reciprocal', 'hartree', 'external_reciprocal', 'external', 'effective'],
+                          'grid': ['g_vectors', 'r_vectors', 'k_vectors', 'spherical_mask', 'cubic_mask',
+                                   'proper_grid_size', 'translation_vectors', 'estimate_max_cutoff_energy'],
+                          'hamiltonian': ['hamiltonian_matrix_trace', 'hamiltonian_matrix'],
+                          'occupation': ['uniform', 'gamma', 'idempotent', 'simplex_projector', 'proj',
+                                         'param_init', 'occupation', 'idempotent_param_init',
+                                         'simplex_projector_init'],
+                          'kinetic': ['kinetic_operator']}.items():
+    mod = importlib.import_module('jrystal_b200.' + mod_name)
+    for n in names:
+      assert n in ref_api[mod_name] and callable(getattr(mod, n, None)), f'{mod_name}.{n}'
+
+
+from tests.conftest import BACKENDS  # noqa: E402
+
+
+@pytest.mark.parametrize('backend', BACKENDS, indirect=True)
+def test_potential_module_real_space_potentials(backend):
+  """potential.hartree(density_grid_reciprocal, g_vector_grid, kohn_sham) and potential.external
+  (potential.py:80-118, 169-200) on the current plan against ifftn of the reference's V_H(G) /
+  V_ext(G) (real parts)."""
+  import jrystal_b200 as jb
+  kind, Plan, dev = backend
+  key = 'diamond_16_sph'                 # 16^3 = 4096 points: the fixture holds the whole grids
+  c, g = mg.CASES[key], _ref(key)
+  s, w_re, w_im, occ = mg.inputs(c)
+  plan = Plan(s.cell, s.mask, s.kpts, c['nb'])
+  plan.set_atoms(s.positions, s.charges)
+  rho_g = dev(g['density_reciprocal'])
+  with jb.use_plan(plan):
+    v_h = jb.potential.hartree(rho_g, s.g_vec)
+    v_h_ks = jb.potential.hartree(rho_g, s.g_vec, kohn_sham=True)
+    v_e = jb.potential.external(s.positions, s.charges, s.g_vec, s.vol)
+    with pytest.raises(ValueError):
+      jb.potential.hartree(rho_g[0], s.g_vec)
+  ref_h = np.fft.ifftn(g['v_har_reciprocal']).real
+  ref_e = np.fft.ifftn(g['v_ext_reciprocal']).real
+  assert tuple(v_h.shape) == tuple(s.grid_sizes)
+  assert relerr(v_h.cpu().numpy(), ref_h) < 1e-10
+  assert relerr(v_h_ks.cpu().numpy(), 2 * ref_h) < 1e-10
+  assert relerr(v_e.cpu().numpy(), ref_e) < 1e-10
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize('key', list(mg.CASES))
 def test_cuda_matches_reference_source(cuda_device, key):
