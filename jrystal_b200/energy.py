@@ -97,3 +97,19 @@ def total_energy(coefficient, position, charge, g_vector_grid, kpts, vol, occupa
   e_kin = torch.sum(plan.kinetic(c.q) * occ)
   parts = (e_kin, en[1], en[0], en[2])
   return parts if split else e_kin + en[1] + en[0] + en[2]
+
+
+def band_energy(coefficient, position, charge, g_vector_grid, kpts, vol, occupation,
+                kohn_sham: bool = False, xc_type: str = 'lda_x'):
+  """jrystal/_src/energy.py:310-372: eps[s, k, b] = <psi_b| T + v_eff[rho] |psi_b> with rho the
+  occupation-weighted density of the same coefficients.  One density sweep, one fused potential
+  sweep, one H-apply and the per-band reduction (jrb_density, jrb_potential, jrb_hpsi,
+  jrb_band_expect) instead of the reference's dense per-band densities."""
+  del g_vector_grid, kpts
+  c = _pw._as_coeff(coefficient)
+  plan = _plan_with_atoms(position, charge)
+  if c.plan is not plan:
+    raise ValueError('coefficients belong to a different plan')
+  rho = _pw.density_grid(c, vol, occupation)
+  v = plan.potential(rho, xc_type, kohn_sham, 7)
+  return plan.band_expect(c.q, plan.hpsi(c.q, v))

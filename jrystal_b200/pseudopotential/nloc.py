@@ -76,6 +76,29 @@ def potential_nonlocal_psi_sphere(position, g_vector_grid, kpts, freq_mask, r_gr
   return np.ascontiguousarray(phi)
 
 
+def potential_nonlocal_psi_reciprocal(position, g_vector_grid, kpts, r_grid, nonlocal_beta_grid,
+                                      nonlocal_angular_momentum, nonlocal_d_matrix, beta_gk=None,
+                                      fourier_transform_method: str = 'sbt', concat: bool = True):
+  """Dense drop-in for the reference's function of this name (nloc.py:43-141): the whole
+  (kpt, beta, m, x, y, z) array, for callers that want it; the drivers never build it.
+  `beta_gk` (a precomputed transform) is accepted and ignored: the transform is recomputed on the
+  same radial grid.  concat=False returns the per-atom list."""
+  del beta_gk
+  if fourier_transform_method != 'sbt':
+    raise ValueError("only the reference's default method 'sbt' is implemented")
+  g = np.asarray(g_vector_grid)
+  full = np.ones(g.shape[:-1], dtype=bool)
+  nm = 2 * int(max(int(np.max(l)) for l in nonlocal_angular_momentum)) + 1
+  rows = potential_nonlocal_psi_sphere(position, g, kpts, full, r_grid, nonlocal_beta_grid,
+                                       nonlocal_angular_momentum, nonlocal_d_matrix,
+                                       drop_zero_rows=False)
+  dense = rows.reshape(rows.shape[0], -1, nm, *g.shape[:-1])
+  if concat:
+    return dense
+  edges = np.cumsum([0] + [len(l) for l in nonlocal_angular_momentum])
+  return [dense[:, a:b] for a, b in zip(edges[:-1], edges[1:])]
+
+
 def hamiltonian_nonlocal(coeff_sphere, phi_sphere, vol: float) -> np.ndarray:
   """Host twin of nloc.py:143-158 on the sphere: coeff (spin, kpt, g, band) (the compact layout of
   the parameters), phi (kpt, proj, g) -> (spin, kpt, band, band)."""

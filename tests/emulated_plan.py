@@ -128,6 +128,21 @@ class EmulatedPlan:
       v = v + rp.xc_density(rho, kohn_sham, xc, self.g_vec)
     return v.contiguous()
 
+  def expand(self, q):
+    return self._box(q)
+
+  def squeeze(self, c):
+    return c[..., torch.from_numpy(self._m)].transpose(-1, -2).contiguous()
+
+  def wave_grid(self, q):
+    return rp.wave_grid(self._box(q), self.vol)
+
+  def density(self, q, occ):
+    return rp.density_grid(self._box(q), self.vol, occ)
+
+  def density_reciprocal(self, rho):
+    return torch.fft.fftn(rho, dim=(-3, -2, -1))
+
   def fft3d(self, x, inverse, out=None):
     assert x.dtype == C128 and tuple(x.shape[-3:]) == (self.nx, self.ny, self.nz)
     y = (torch.fft.ifftn if inverse else torch.fft.fftn)(x, dim=(-3, -2, -1))

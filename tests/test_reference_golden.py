@@ -324,6 +324,28 @@ def test_potential_module_real_space_potentials(backend):
   assert relerr(v_e.cpu().numpy(), ref_e) < 1e-10
 
 
+@pytest.mark.parametrize('backend', BACKENDS, indirect=True)
+@pytest.mark.parametrize('kohn_sham', [False, True])
+def test_energy_band_energy(backend, kohn_sham):
+  """energy.band_energy (energy.py:310-372) against the oracle's per-band <psi|T + v_eff|psi>."""
+  import jrystal_b200 as jb
+  kind, Plan, dev = backend
+  c = mg.CASES['diamond_12_pbe']
+  s, w_re, w_im, occ = mg.inputs(c)
+  plan = Plan(s.cell, s.mask, s.kpts, c['nb'])
+  with jb.use_plan(plan):
+    coeff = jb.pw.coeff({'w_re': dev(w_re), 'w_im': dev(w_im)}, s.mask)
+    eps = jb.energy.band_energy(coeff, s.positions, s.charges, s.g_vec, s.kpts, s.vol, dev(occ),
+                                kohn_sham=kohn_sham, xc_type='lda_x')
+  q = rp.unitary_matrix(torch.from_numpy(w_re), torch.from_numpy(w_im))
+  cg = rp.expand_coefficient(q, s.mask)
+  rho = rp.density_grid(cg, s.vol, torch.from_numpy(occ))
+  ref = rp.hamiltonian_matrix_trace(cg, s.positions, s.charges, rho, s.g_vec, s.kpts, s.vol,
+                                    'lda_x', kohn_sham=kohn_sham, per_band=True).numpy()
+  assert tuple(eps.shape) == (1, s.num_k, c['nb'])
+  assert relerr(eps.cpu().numpy(), ref) < 1e-10
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize('key', list(mg.CASES))
 def test_cuda_matches_reference_source(cuda_device, key):
