@@ -36,3 +36,19 @@ def test_plan_desc_layout_matches_header():
   import ctypes
   # int32 x6, 3 pointers, int32 x2 (with natural alignment)
   assert ctypes.sizeof(_lib.PlanDesc) == 6 * 4 + 3 * 8 + 2 * 4
+
+
+def test_documents_name_only_declared_entry_points():
+  """INTEGRATION.md / DESIGN.md / README.md may only name C entry points the header declares
+  (planned ones are listed here explicitly)."""
+  planned = {'jrb_comm_create',   # DESIGN.md section 9: peer all-reduce set-up, on a branch
+             'jrb_xla_ffi'}       # name of the XLA-FFI shim library in INTEGRATION.md
+  declared = set(_declared())
+  text = open(os.path.join(ROOT, 'include', 'jrystal_b200.h')).read()
+  types = set(re.findall(r'\b(jrb_[a-z0-9_]+)\b', text)) - declared   # typedefs / structs / enums
+  for doc in ('INTEGRATION.md', 'DESIGN.md', 'README.md'):
+    body = open(os.path.join(ROOT, doc)).read()
+    for name in set(re.findall(r'\b(jrb_[a-z0-9_]+)\b', body)):
+      base = name.rstrip('_')
+      assert (name in declared or name in types or name in planned
+              or any(d.startswith(base) for d in declared)), f'{doc} names {name}, not in the header'
