@@ -185,3 +185,36 @@ def test_spin_unrestricted_energy_driver(backend):
   ref = rp.energy_and_grad(s, w_re, w_im, occ)
   assert abs(out.total_energy - out.energies['ewald'] - ref['e_tot']) < 1e-10 * abs(ref['e_tot'])
   assert relerr(out.density.cpu().numpy(), ref['density']) < 1e-8
+
+
+def test_command_line_with_the_shipped_config_keys(emulated, tmp_path, capsys):
+  """`python -m jrystal_b200 -m energy -c config.yaml` with the keys of the reference's shipped
+  config.yaml (GGA-PBE, simplex-projector occupations, norm-conserving pseudopotentials), scaled
+  down to a 12^3 grid; the pseudopotential directory is the one thing a user must point somewhere."""
+  import os
+  import yaml
+  from jrystal_b200.__main__ import main
+  from tests.test_pseudopotential import golden, write_upf
+  upf_dir = str(tmp_path / 'upf')
+  os.makedirs(upf_dir)
+  write_upf(os.path.join(upf_dir, 'Si.pz-vbc.UPF'), golden())
+  cfg = {
+    'crystal': 'si', 'crystal_file_path_path': None, 'spin': 0, 'save_dir': str(tmp_path),
+    'xc': 'gga_x_pbe+gga_c_pbe', 'use_pseudopotential': True, 'pseudopotential_type': 'nc',
+    'pseudopotential_file_dir': upf_dir, 'freq_mask_method': 'spherical', 'cutoff_energy': 6,
+    'grid_sizes': 12, 'k_grid_sizes': [1, 1, 1], 'occupation': 'simplex-projector',
+    'smearing': 0.001, 'empty_bands': 2, 'spin_restricted': True,
+    'ewald_args': {'ewald_eta': 0.1, 'ewald_cutoff': 2.0e4}, 'epoch': 6, 'optimizer': 'adam',
+    'optimizer_args': {'learning_rate': 0.01, 'b1': 0.9, 'b2': 0.99}, 'scheduler': None,
+    'convergence_window_size': 20, 'convergence_condition': 1e-4, 'seed': 123, 'verbose': True,
+    'orbital_grid': 'full',
+  }
+  path = tmp_path / 'config.yaml'
+  path.write_text(yaml.safe_dump(cfg))
+  assert main(['-m', 'energy', '-c', str(path)]) == 0
+  out = capsys.readouterr().out
+  for line in ('Hartree Energy:', 'External (local) Energy:', 'External (nonlocal) Energy:',
+               'XC Energy:', 'Kinetic Energy:', 'Nuclear repulsion Energy:', 'Total Energy:',
+               'Did not converge after 6 steps'):
+    assert line in out, line
+  assert (tmp_path / 'density.npy').exists()
