@@ -45,11 +45,17 @@ extern "C" int jrb_set_nonlocal(jrb_plan* p, const double* phi, int32_t nproj, j
   int rc = enter(p);
   if (rc) return rc;
   REQUIRE(nproj >= 0 && (nproj == 0 || phi), "bad projector table");
+  if (p->nproj > 0) {  // give back what the previous table was charged (the band driver sets one per k-point)
+    const size_t old_phi = (size_t)p->nk * p->nproj * p->ng;
+    const size_t old_p = (size_t)p->ns * p->nk * p->nproj * p->nb;
+    p->ws_bytes -= (int64_t)((old_phi + 17 * old_p) * sizeof(cplx));
+  }
   for (cplx** q : {&p->d_nl_phi, &p->d_nl_p, &p->d_nl_part}) {
     if (*q) cudaFree(*q);
     *q = nullptr;
   }
   p->nproj = 0;
+  p->nl_p_valid = 0;
   if (nproj == 0) return 0;
   const size_t nphi = (size_t)p->nk * nproj * p->ng;
   const size_t np = (size_t)p->ns * p->nk * nproj * p->nb;
