@@ -79,7 +79,7 @@ int main() {
   int bad = 0;
 #define T(n) bad += one<n>();
   T(2) T(3) T(4) T(5) T(6) T(7) T(8) T(9) T(10) T(12) T(14) T(15) T(16) T(18) T(20) T(24) T(25) T(27) T(28)
-  T(30) T(32) T(36) T(40) T(45) T(48) T(50) T(54) T(56) T(60) T(64) T(72) T(80) T(81) T(90) T(96) T(100)
+  T(30) T(32) T(36) T(40) T(45) T(48) T(49) T(50) T(54) T(56) T(60) T(64) T(72) T(80) T(81) T(90) T(96) T(100)
   T(108) T(112) T(120) T(128) T(144) T(160) T(192) T(256)
   std::printf(bad ? "FAIL\n" : "OK\n");
   return bad;
