@@ -9,6 +9,7 @@
 #include <vector>
 
 #include "plan.h"
+#include "xc_functionals.cuh"
 
 namespace jrb {
 
@@ -230,99 +231,6 @@ k_hartree_ext(GridGeom g, cplx* __restrict__ grid, const cplx* __restrict__ vext
     partials[blockIdx.x * 4 + 0] = out[0] * w * (kohn_sham ? 1.0 : 0.5);
     partials[blockIdx.x * 4 + 1] = out[1] * w;
   }
-}
-
-// LDA energy density per particle and its derivative for the unpolarised gas.
-__device__ __forceinline__ void lda_eps(int xc_id, double n, double& eps, double& deps) {
-  const double thr = 1e-15;  // LibXC dens_threshold
-  eps = 0.0;
-  deps = 0.0;
-  if (!(n > thr)) return;
-  const double cx = -0.73855876638202240588;  // -3/4 (3/pi)^(1/3)
-  const double c13 = cbrt(n);
-  eps = cx * c13;
-  deps = eps / (3.0 * n);
-  if (xc_id == JRB_XC_LDA_X_C_PW) {
-    const double A = 0.031091, a1 = 0.21370, b1 = 7.5957, b2 = 3.5876, b3 = 1.6382, b4 = 0.49294;
-    const double rs = cbrt(3.0 / (4.0 * M_PI * n));
-    const double sr = sqrt(rs);
-    const double Q = 2.0 * A * (b1 * sr + b2 * rs + b3 * rs * sr + b4 * rs * rs);
-    const double dQ = 2.0 * A * (0.5 * b1 / sr + b2 + 1.5 * b3 * sr + 2.0 * b4 * rs);
-    const double L = log1p(1.0 / Q);
-    const double ec = -2.0 * A * (1.0 + a1 * rs) * L;
-    const double dec_drs = -2.0 * A * a1 * L + 2.0 * A * (1.0 + a1 * rs) * dQ / (Q * Q + Q);
-    eps += ec;
-    deps += dec_drs * (-rs / (3.0 * n));
-  }
-}
-
-
-// ---------------------------------------------------------------------------------------
-// GGA (PBE exchange and correlation, unpolarised).  The reference evaluates
-// eps_xc(rho, sigma) per grid point with sigma = sum_j |d_j|^2, d_j = ifftn(i G_j fftn(rho))
-// (xc.py:67-112, 242-253) and lets jax.grad differentiate E_xc = (Omega/N) sum rho eps through
-// both arguments.  Here the same energy is accumulated and its exact discrete derivative is
-// formed by hand:  dE/d rho(r) = de/d rho - 2 Re ifftn( sum_j i G_j fftn( de/d sigma * d_j ) )
-// with e = rho eps (the adjoint of D_j = ifftn i G_j fftn on the FFT grid is u -> -conj(D_j conj u),
-// Nyquist bins included, so the result matches autograd to rounding).  de/d rho and de/d sigma
-// come from forward-mode duals of the closed-form eps(rho, sigma).
-struct Dual {  // value, d/d rho, d/d sigma
-  double v, r, s;
-};
-__device__ __forceinline__ Dual dmk(double v, double r = 0.0, double s = 0.0) {
-  Dual d;
-  d.v = v; d.r = r; d.s = s;
-  return d;
-}
-__device__ __forceinline__ Dual operator+(Dual a, Dual b) { return dmk(a.v + b.v, a.r + b.r, a.s + b.s); }
-__device__ __forceinline__ Dual operator-(Dual a, Dual b) { return dmk(a.v - b.v, a.r - b.r, a.s - b.s); }
-__device__ __forceinline__ Dual operator*(Dual a, Dual b) {
-  return dmk(a.v * b.v, a.r * b.v + a.v * b.r, a.s * b.v + a.v * b.s);
-}
-__device__ __forceinline__ Dual operator*(double c, Dual a) { return dmk(c * a.v, c * a.r, c * a.s); }
-__device__ __forceinline__ Dual operator+(double c, Dual a) { return dmk(c + a.v, a.r, a.s); }
-__device__ __forceinline__ Dual operator/(Dual a, Dual b) {
-  const double q = a.v / b.v, ib = 1.0 / b.v;
-  return dmk(q, (a.r - q * b.r) * ib, (a.s - q * b.s) * ib);
-}
-__device__ __forceinline__ Dual dchain(Dual a, double f, double df) { return dmk(f, df * a.r, df * a.s); }
-__device__ __forceinline__ Dual dsqrt(Dual a) { const double f = sqrt(a.v); return dchain(a, f, 0.5 / f); }
-__device__ __forceinline__ Dual dcbrt(Dual a) { const double f = cbrt(a.v); return dchain(a, f, f / (3.0 * a.v)); }
-__device__ __forceinline__ Dual dlog1p(Dual a) { return dchain(a, log1p(a.v), 1.0 / (1.0 + a.v)); }
-__device__ __forceinline__ Dual dexpm1(Dual a) { const double f = expm1(a.v); return dchain(a, f, f + 1.0); }
-
-// eps_xc(rho, sigma) of gga_x_pbe (+ gga_c_pbe) as LibXC defines them (jax_xc 0.0.8 translates
-// LibXC's maple sources; not vendored -> parity unpinned)
-__device__ __forceinline__ Dual pbe_eps(int xc_id, double rho, double sigma) {
-  const Dual n = dmk(rho, 1.0, 0.0), sg = dmk(sigma, 0.0, 1.0);
-  Dual eps = dmk(0.0);
-  const Dual n13 = dcbrt(n);
-  if (rho > 1e-15) {  // gga_x_pbe dens_threshold
-    const double kappa = 0.8040, mu = 0.2195149727645171;
-    const double cx = -0.73855876638202240588;                 // -3/4 (3/pi)^(1/3)
-    const double c_s2 = 1.0 / (4.0 * 9.5707800006273513);     // 1 / (4 (3 pi^2)^(2/3))
-    const Dual n83 = (n * n) * (n13 * n13);
-    const Dual s2 = c_s2 * (sg / n83);
-    const Dual fx = (1.0 + kappa) + (-kappa * kappa) * (dmk(1.0) / (kappa + mu * s2));
-    eps = eps + (cx * n13) * fx;
-  }
-  if (xc_id == JRB_XC_GGA_PBE && rho > 1e-12) {  // gga_c_pbe dens_threshold
-    // PW92 with LibXC's pw_mod parameters (what gga_c_pbe includes), zeta = 0
-    const double A = 0.0310907, a1 = 0.21370, b1 = 7.5957, b2 = 3.5876, b3 = 1.6382, b4 = 0.49294;
-    const double beta = 0.06672455060314922, gamma = 0.031090690869654895;  // (1 - ln 2) / pi^2
-    const Dual rs = 0.62035049089940001667 * (dmk(1.0) / n13);  // (3 / (4 pi))^(1/3) n^(-1/3)
-    const Dual sr = dsqrt(rs);
-    const Dual q = (2.0 * A) * (b1 * sr + b2 * rs + b3 * (rs * sr) + b4 * (rs * rs));
-    const Dual ec = (-2.0 * A) * ((1.0 + a1 * rs) * dlog1p(dmk(1.0) / q));
-    // t^2 = sigma / (4 ks^2 n^2), ks^2 = 4 kF / pi, kF = (3 pi^2 n)^(1/3)
-    const double c_t2 = M_PI / (16.0 * 3.0936677262801360);  // pi / (16 (3 pi^2)^(1/3))
-    const Dual t2 = c_t2 * (sg / ((n * n) * n13));
-    const Dual aa = (beta / gamma) * (dmk(1.0) / dexpm1((-1.0 / gamma) * ec));
-    const Dual f1 = t2 + aa * (t2 * t2);
-    const Dual f2 = (beta / gamma) * (f1 / (1.0 + aa * f1));
-    eps = eps + ec + gamma * dlog1p(f2);
-  }
-  return eps;
 }
 
 // w_j(G) = i G_j rho_hat(G) / N  (the 1/N of ifftn folded in)
