@@ -102,7 +102,10 @@ def total_energy(coefficient, position, charge, g_vector_grid, kpts, vol, occupa
 def band_energy(coefficient, position, charge, g_vector_grid, kpts, vol, occupation,
                 kohn_sham: bool = False, xc_type: str = 'lda_x'):
   """jrystal/_src/energy.py:310-372: eps[s, k, b] = <psi_b| T + v_eff[rho] |psi_b> with rho the
-  occupation-weighted density of the same coefficients.  One density sweep, one fused potential
+  occupation-weighted density of the same coefficients (the formula of the reference's docstring;
+  the reference's own body raises in braket.real_braket, energy.py:361, on the per-band density
+  against the (spin, x, y, z) potential, so there is no reference vector for it: the oracle's
+  per-band Hamiltonian trace is the checker).  One density sweep, one fused potential
   sweep, one H-apply and the per-band reduction (jrb_density, jrb_potential, jrb_hpsi,
   jrb_band_expect) instead of the reference's dense per-band densities."""
   del g_vector_grid, kpts

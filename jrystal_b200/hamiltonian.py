@@ -25,17 +25,20 @@ def _apply(band_coefficient, positions, charges, effictive_density_grid, xc, koh
 def hamiltonian_matrix_trace(band_coefficient, positions, charges, effictive_density_grid,
                              g_vector_grid, kpts, vol, xc: str = 'lda_x', kohn_sham: bool = True,
                              keep_kpts_axis: bool = False, keep_spin_axis: bool = False):
-  """Sum_i <psi_i| T + v_eff |psi_i> per (spin, kpt), summed unless the keep_* flags say
-  otherwise (jrystal/_src/hamiltonian.py:105-168)."""
+  """Sum_i <psi_i| T + v_eff |psi_i> (jrystal/_src/hamiltonian.py:105-168).
+  keep_kpts_axis=False: the scalar the band-mode loss uses (summed over spin, kpt, band), as the
+  reference.  keep_kpts_axis=True: shape [spin, kpt], what the reference's docstring promises; its
+  code sums axes (1, 2) there and returns [spin] (hamiltonian.py:165-166) -- `.sum(1)` of this
+  result.  keep_spin_axis (not a reference argument) only matters with keep_kpts_axis=False:
+  True keeps [spin]."""
   del g_vector_grid, kpts, vol
   c, plan, hq = _apply(band_coefficient, positions, charges, effictive_density_grid, xc, kohn_sham)
   eps = plan.band_expect(c.q, hq)          # (ns, nk, nb)
-  out = eps.sum(dim=-1)
-  if not keep_kpts_axis:
-    out = out.sum(dim=1)
-  if not keep_spin_axis:
-    out = out.sum(dim=0)
-  return out
+  out = eps.sum(dim=-1)                    # (ns, nk)
+  if keep_kpts_axis:
+    return out
+  out = out.sum(dim=1)
+  return out if keep_spin_axis else out.sum(dim=0)
 
 
 def hamiltonian_matrix(band_coefficient, positions, charges, effictive_density_grid,

@@ -151,6 +151,21 @@ class EmulatedPlan:
       return out
     return y
 
+  def grid_potential(self, rho, xc='lda_x', kohn_sham=False, out=None):
+    """(E_H, E_ext, E_xc) of a density and v_eff = the potential the backward pass applies
+    (dE/d rho: Hartree not halved, v_xc the functional derivative)."""
+    assert self._atoms
+    rho_g = torch.fft.fftn(rho, dim=(-3, -2, -1))
+    en = torch.stack([rp.energy_hartree(rho_g, self.g_vec, self.vol, kohn_sham),
+                      rp.reciprocal_braket(self.v_ext, rho_g, self.vol),
+                      rp.energy_xc(rho, self.vol, xc, kohn_sham=kohn_sham, g_vector_grid=self.g_vec)])
+    veff = self.potential(rho, xc, True, 7)
+    if out is not None:
+      out[0].copy_(en)
+      out[1].copy_(veff)
+      return out
+    return en, veff
+
   def prepare_potential(self, veff):
     self._prepared = veff.clone()
 

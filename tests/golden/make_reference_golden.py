@@ -254,6 +254,84 @@ def occupation_case():
         '-> reference_occupation.npz')
 
 
+# ---- LDA formulas handed to the reference in place of jax_xc (OUR restatement of LibXC's lda_x
+# and lda_c_pw, the same closed forms as oracle/reference_port.py:_eps_lda_x/_eps_lda_c_pw, written
+# for numpy and analytic in rho so that the complex-step derivative of the stand-in applies).
+_LDA_X = -0.75 * (3.0 / np.pi) ** (1.0 / 3.0)
+
+
+def _stub_lda_x(p, rho):
+  return np.where(np.real(rho) > 1e-15, _LDA_X * np.asarray(rho) ** (1.0 / 3.0), 0.0)
+
+
+def _stub_lda_c_pw(p, rho):
+  a, a1, b1, b2, b3, b4 = 0.031091, 0.21370, 7.5957, 3.5876, 1.6382, 0.49294
+  rho = np.asarray(rho)
+  safe = np.where(np.real(rho) > 1e-15, rho, 1e-15)
+  rs = (3.0 / (4.0 * np.pi * safe)) ** (1.0 / 3.0)
+  den = 2 * a * (b1 * rs ** 0.5 + b2 * rs + b3 * rs ** 1.5 + b4 * rs ** 2)
+  return np.where(np.real(rho) > 1e-15, -2 * a * (1 + a1 * rs) * np.log(1 + 1 / den), 0.0)
+
+
+def xc_assembly_case(key, c):
+  """Everything the reference builds AROUND the functional, executed verbatim with the two LDA
+  formulas above registered as jax_xc.impl.lda_x / lda_c_pw: xc.xc_density (both kohn_sham
+  flags; vxc_lda = eps + rho d eps / d rho with jax.grad per grid point), energy.xc_energy,
+  potential.effective (split and summed), energy.total_energy,
+  hamiltonian.hamiltonian_matrix_trace.  The functional FORMULA stays unpinned (jax_xc absent);
+  these vectors pin its calling convention, the kohn_sham semantics, the normalisations and the
+  assembly of the band-mode loss."""
+  standin.provide_functional('lda_x', _stub_lda_x)
+  standin.provide_functional('lda_c_pw', _stub_lda_c_pw)
+  grid_m, utils, pw, energy = ref('_src.grid'), ref('_src.utils'), ref('_src.pw'), ref('_src.energy')
+  potential, hamiltonian, xc_m = ref('_src.potential'), ref('_src.hamiltonian'), ref('_src.xc')
+  occupation = ref('_src.occupation')
+  cell, pos, chg = structures.load(c['name'], None)
+  gs = [int(g) for g in grid_m.proper_grid_size(c['grid'])]
+  vol = float(utils.volume(cell))
+  g_vec = grid_m.g_vectors(cell, gs)
+  kpts = grid_m.k_vectors(cell, [int(g) for g in grid_m.proper_grid_size(c['kgrid'])])
+  mask = np.asarray(grid_m.spherical_mask(cell, gs, c['cutoff']) if c['mask'] == 'spherical'
+                    else grid_m.cubic_mask(gs))
+  nk, ng, nb = kpts.shape[0], int(mask.sum()), c['nb']
+  w_re, w_im = seeded_params(c['seed'], nb, nk, ng)
+  ne = int(round(float(np.sum(chg))))
+  occ = A(occupation.uniform(nk, ne, num_bands=nb))
+  occ = occ * (1.0 + 0.1 * np.random.default_rng(c['seed'] + 1).random(occ.shape))
+  coeff = pw.coeff({'w_re': w_re, 'w_im': w_im}, mask)
+  rho = pw.density_grid(coeff, vol, occ)
+  out = dict(w_re_sum=np.array(w_re.sum()), occ=occ)
+  for xc in ('lda_x', 'lda_x+lda_c_pw'):
+    tag = xc.replace('+', '_')
+    out[f'{tag}_eps'] = G(xc_m.xc_density(rho, g_vec, False, xc))
+    out[f'{tag}_vxc'] = G(xc_m.xc_density(rho, g_vec, True, xc))
+    out[f'{tag}_e_xc'] = np.array(float(energy.xc_energy(rho, g_vec, vol, xc, False)))
+    out[f'{tag}_e_xc_kohn_sham'] = np.array(float(energy.xc_energy(rho, g_vec, vol, xc, True)))
+    for ks in (False, True):
+      v_h, v_e, v_x = potential.effective(rho, pos, chg, g_vec, vol, split=True, xc_type=xc,
+                                          kohn_sham=ks)
+      v_sum = potential.effective(rho, pos, chg, g_vec, vol, split=False, xc_type=xc, kohn_sham=ks)
+      # real parts (what every consumer keeps, hamiltonian.py:164); the imaginary part is the
+      # Nyquist residue of an even grid
+      out[f'{tag}_veff_ks{int(ks)}'] = G(np.real(A(v_sum)))
+      out[f'{tag}_veff_imag_max_ks{int(ks)}'] = np.array(np.abs(np.imag(A(v_sum))).max())
+      out[f'{tag}_veff_parts_ks{int(ks)}'] = np.stack(
+        [G(np.real(np.broadcast_to(A(v), A(v_sum).shape))) for v in (v_h, v_e, v_x)])
+      out[f'{tag}_total_energy_ks{int(ks)}'] = np.array(
+        [float(np.real(e)) for e in energy.total_energy(coeff, pos, chg, g_vec, kpts, vol, occ,
+                                                         kohn_sham=ks, xc=xc, split=True)])
+      # energy.band_energy is not callable as shipped (energy.py:361: real_braket rejects the
+      # (s, k, b, x, y, z) density against the (s, x, y, z) potential), so it has no golden
+    out[f'{tag}_hamiltonian_trace'] = np.array(float(np.real(hamiltonian.hamiltonian_matrix_trace(
+      coeff, pos, chg, rho, g_vec, kpts, vol, xc=xc, kohn_sham=True))))
+    out[f'{tag}_hamiltonian_trace_per_k'] = A(hamiltonian.hamiltonian_matrix_trace(
+      coeff, pos, chg, rho, g_vec, kpts, vol, xc=xc, kohn_sham=True, keep_kpts_axis=True))
+  path = os.path.join(HERE, f'reference_xc_assembly_{key}.npz')
+  np.savez_compressed(path, **out)
+  print(f'xc assembly {key}: E_xc(lda_x) {float(out["lda_x_e_xc"]):.12f} trace '
+        f'{float(out["lda_x_hamiltonian_trace"]):.12f} -> {os.path.basename(path)}')
+
+
 API_MODULES = {  # jrystal_b200 module -> reference module it mirrors
   'pw': '_src.pw', 'grid': '_src.grid', 'energy': '_src.energy', 'potential': '_src.potential',
   'kinetic': '_src.kinetic', 'hamiltonian': '_src.hamiltonian', 'occupation': '_src.occupation',
@@ -315,6 +393,9 @@ def main():
     core_case(key, c)
   if not only or 'si_normcons' in only:
     normcons_case()
+  for key in ('diamond_789_cubic', 'diamond_16_sph'):
+    if not only or 'xc_assembly' in only or f'xc_assembly_{key}' in only:
+      xc_assembly_case(key, CASES[key])
   if not only or 'api' in only:
     api_signatures()
   if not only or 'grid_helpers' in only:

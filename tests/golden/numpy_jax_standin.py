@@ -27,7 +27,8 @@ What the stand-in provides, and why each is faithful:
     (interpax mirrors scipy's signature and not-a-knot default).
   * jax_xc is NOT stood in for: anything that evaluates an XC functional stays outside the
     reference goldens (XC arithmetic parity unpinned).
-No automatic differentiation: jax.grad / jacfwd raise.  Gradients are pinned through finite
+No automatic differentiation: jacfwd / value_and_grad / vjp raise; jax.grad is a complex-step
+derivative for scalar analytic functions only (the per-point d(exc)/d(rho) of xc.py:118).  Gradients are pinned through finite
 differences of the pinned energies (tests/test_oracle.py).
 """
 import dataclasses
@@ -175,6 +176,25 @@ def _vmap(fun, in_axes=0, out_axes=0, **_unused):
   return mapped
 
 
+def _complex_step_grad(fun, argnums=0, **_unused):
+  """jax.grad for a REAL ANALYTIC scalar function of a scalar: Im f(x + i h) / h, exact to rounding
+  (no subtraction).  Enough for the one use on the LDA forward path (xc.py:118:
+  jax.vmap(jax.grad(exc)) over the grid points); anything else must not rely on it."""
+  h = 1e-40
+
+  def g(*args):
+    x = np.asarray(args[argnums])
+    if x.ndim != 0:
+      raise NotImplementedError('complex-step grad stand-in: scalar argument only')
+    shifted = list(args)
+    shifted[argnums] = (x.astype(np.complex128) + 1j * h).view(Arr)
+    y = np.asarray(fun(*shifted))
+    if y.size != 1:
+      raise NotImplementedError('complex-step grad stand-in: scalar function only')
+    return (np.imag(y).reshape(()) / h).view(Arr)
+  return g
+
+
 def _no_autodiff(*_a, **_k):
   raise NotImplementedError('the numpy stand-in has no automatic differentiation')
 
@@ -267,7 +287,7 @@ def install():
   _module('jax', _is_numpy_standin=True, numpy=jnp, lax=lax, sharding=sharding, scipy=jscipy,
           random=random, extend=extend, _src=src, interpreters=interp, nn=nn,
           Array=np.ndarray, vmap=_vmap, jit=lambda f=None, **k: (f if f is not None else (lambda g: g)),
-          grad=_no_autodiff, value_and_grad=_no_autodiff, jacfwd=_no_autodiff,
+          grad=_complex_step_grad, value_and_grad=_no_autodiff, jacfwd=_no_autodiff,
           jacrev=_no_autodiff, hessian=_no_autodiff, jvp=_no_autodiff, vjp=_no_autodiff,
           tree_map=lambda f, t: f(t), device_count=lambda: 1, devices=lambda: [None],
           config=types.SimpleNamespace(update=lambda *a, **k: None))
@@ -304,9 +324,11 @@ def load_reference(root=REFERENCE_ROOT):
   sbt_pkg = bare('jrystal.sbt', f'{base}/sbt')
   # sharding decorator of the FFT primitives: identity on values
   _module('jrystal._src.spmd.custom_sharding', custom_sharding_by_mesh=lambda f: f)
-  # the functional library is not available: importing xc.py must fail loudly if it is USED
-  _module('jax_xc.utils', get_p=_no_autodiff)
-  _module('jax_xc', utils=sys.modules['jax_xc.utils'], impl=None)
+  # the functional library is not available: importing xc.py works, USING a functional fails
+  # loudly unless the caller registers a formula with provide_functional()
+  _module('jax_xc.utils', get_p=lambda name, polarized: None)
+  _module('jax_xc.impl')
+  _module('jax_xc', utils=sys.modules['jax_xc.utils'], impl=sys.modules['jax_xc.impl'])
   # a Crystal type for annotations only (the real one needs ase + chex)
   _module('jrystal._src.crystal', Crystal=type('Crystal', (), {}))
   # what jrystal/sbt/__init__.py exports
@@ -319,6 +341,15 @@ def load_reference(root=REFERENCE_ROOT):
     sbt_pkg.sbt = sbt_pkg.batch_sbt = None
   del spmd
   return pkg
+
+
+def provide_functional(name, unpol):
+  """Register `jax_xc.impl.<name>.unpol(p, rho) -> eps_xc per particle` (jax_xc's calling
+  convention, xc.py:25-27, 57-63).  The FORMULA is the caller's (jax_xc is absent): goldens made
+  with it pin the reference's assembly AROUND the functional, not the functional."""
+  load_reference()
+  mod = _module(f'jax_xc.impl.{name}', unpol=unpol)
+  setattr(sys.modules['jax_xc.impl'], name, mod)
 
 
 def ref(module):
