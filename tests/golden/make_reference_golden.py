@@ -273,6 +273,61 @@ def _stub_lda_c_pw(p, rho):
   return np.where(np.real(rho) > 1e-15, -2 * a * (1 + a1 * rs) * np.log(1 + 1 / den), 0.0)
 
 
+def _stub_gga_x_pbe(p, rho, sigma):
+  kappa, mu = 0.8040, 0.2195149727645171
+  safe = np.where(rho > 1e-15, rho, 1e-15)
+  s2 = sigma / (4.0 * (3.0 * np.pi ** 2) ** (2.0 / 3.0) * safe ** (8.0 / 3.0))
+  fx = 1.0 + kappa - kappa ** 2 / (kappa + mu * s2)
+  return np.where(rho > 1e-15, _LDA_X * safe ** (1.0 / 3.0) * fx, 0.0)
+
+
+def _stub_gga_c_pbe(p, rho, sigma):
+  a, a1, b1, b2, b3, b4 = 0.0310907, 0.21370, 7.5957, 3.5876, 1.6382, 0.49294
+  beta, gamma = 0.06672455060314922, (1.0 - np.log(2.0)) / np.pi ** 2
+  safe = np.where(rho > 1e-12, rho, 1e-12)
+  rs = (3.0 / (4.0 * np.pi * safe)) ** (1.0 / 3.0)
+  den = 2 * a * (b1 * rs ** 0.5 + b2 * rs + b3 * rs ** 1.5 + b4 * rs ** 2)
+  ec = -2 * a * (1 + a1 * rs) * np.log1p(1 / den)
+  kf = (3.0 * np.pi ** 2 * safe) ** (1.0 / 3.0)
+  t2 = sigma * np.pi / (16.0 * kf * safe ** 2)
+  aa = (beta / gamma) / np.expm1(-ec / gamma)
+  f1 = t2 + aa * t2 ** 2
+  return np.where(rho > 1e-12, ec + gamma * np.log1p((beta / gamma) * f1 / (1 + aa * f1)), 0.0)
+
+
+def gga_assembly_case():
+  """GGA energy branch (kohn_sham=False): xc.sigma_r_fn + the per-point call of the functional +
+  energy.xc_energy / total_energy, verbatim, with our PBE closed forms standing in for jax_xc."""
+  standin.provide_functional('gga_x_pbe', _stub_gga_x_pbe)
+  standin.provide_functional('gga_c_pbe', _stub_gga_c_pbe)
+  key = 'diamond_12_pbe'
+  c = CASES[key]
+  grid_m, utils, pw, energy = ref('_src.grid'), ref('_src.utils'), ref('_src.pw'), ref('_src.energy')
+  xc_m, occupation = ref('_src.xc'), ref('_src.occupation')
+  cell, pos, chg = structures.load(c['name'], None)
+  gs = [int(g) for g in grid_m.proper_grid_size(c['grid'])]
+  vol = float(utils.volume(cell))
+  g_vec = grid_m.g_vectors(cell, gs)
+  kpts = grid_m.k_vectors(cell, [int(g) for g in grid_m.proper_grid_size(c['kgrid'])])
+  mask = np.asarray(grid_m.spherical_mask(cell, gs, c['cutoff']))
+  nk, ng, nb = kpts.shape[0], int(mask.sum()), c['nb']
+  w_re, w_im = seeded_params(c['seed'], nb, nk, ng)
+  occ = A(occupation.uniform(nk, int(round(float(np.sum(chg)))), num_bands=nb))
+  occ = occ * (1.0 + 0.1 * np.random.default_rng(c['seed'] + 1).random(occ.shape))
+  coeff = pw.coeff({'w_re': w_re, 'w_im': w_im}, mask)
+  rho = pw.density_grid(coeff, vol, occ)
+  out = dict(w_re_sum=np.array(w_re.sum()), occ=occ)
+  for xc in ('gga_x_pbe', 'gga_x_pbe+gga_c_pbe'):
+    tag = xc.replace('+', '_')
+    out[f'{tag}_eps'] = G(xc_m.xc_density(rho, g_vec, False, xc))
+    out[f'{tag}_e_xc'] = np.array(float(energy.xc_energy(rho, g_vec, vol, xc, False)))
+    out[f'{tag}_total_energy'] = np.array(
+      [float(np.real(e)) for e in energy.total_energy(coeff, pos, chg, g_vec, kpts, vol, occ,
+                                                       kohn_sham=False, xc=xc, split=True)])
+  np.savez_compressed(os.path.join(HERE, f'reference_xc_assembly_{key}.npz'), **out)
+  print(f'gga assembly {key}: E_xc(pbe) {float(out["gga_x_pbe_gga_c_pbe_e_xc"]):.12f}')
+
+
 def xc_assembly_case(key, c):
   """Everything the reference builds AROUND the functional, executed verbatim with the two LDA
   formulas above registered as jax_xc.impl.lda_x / lda_c_pw: xc.xc_density (both kohn_sham
@@ -396,6 +451,8 @@ def main():
   for key in ('diamond_789_cubic', 'diamond_16_sph'):
     if not only or 'xc_assembly' in only or f'xc_assembly_{key}' in only:
       xc_assembly_case(key, CASES[key])
+  if not only or 'gga_assembly' in only:
+    gga_assembly_case()
   if not only or 'api' in only:
     api_signatures()
   if not only or 'grid_helpers' in only:

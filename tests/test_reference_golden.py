@@ -342,6 +342,27 @@ def test_oracle_matches_reference_assembly_around_the_functional(key):
     assert relerr(np.asarray(per_k), np.real(g[f'{tag}_hamiltonian_trace_per_k'])) < 1e-12
 
 
+def test_oracle_matches_reference_gga_energy_assembly():
+  """GGA, kohn_sham=False: the reference's xc.xc_density (sigma_r_fn + per-point functional call),
+  energy.xc_energy and energy.total_energy with our PBE closed forms standing in for jax_xc; also
+  the oracle-made fixture the GPU tests consume carries the same four energies."""
+  key = 'diamond_12_pbe'
+  c, g = mg.CASES[key], _xc_ref(key)
+  s, w_re, w_im, occ = mg.inputs(c)
+  assert float(g['w_re_sum']) == w_re.sum()
+  o = torch.from_numpy(occ)
+  cg = rp.coeff(torch.from_numpy(w_re), torch.from_numpy(w_im), s.mask)
+  rho = rp.density_grid(cg, s.vol, o)
+  for xc in ('gga_x_pbe', 'gga_x_pbe+gga_c_pbe'):
+    tag = xc.replace('+', '_')
+    assert relerr(_grid_sample(rp.xc_density(rho, False, xc, s.g_vec).numpy()), g[f'{tag}_eps']) < 1e-11
+    assert _close(rp.energy_xc(rho, s.vol, xc, kohn_sham=False, g_vector_grid=s.g_vec), g[f'{tag}_e_xc'], 1e-12)
+    e = rp.total_energy(cg, s.positions, s.charges, s.g_vec, s.kpts, s.vol, o, xc=xc, split=True)
+    np.testing.assert_allclose([float(x) for x in e], g[f'{tag}_total_energy'], rtol=1e-11)
+  fixture = np.load(os.path.join(HERE, 'golden', key + '.npz'))
+  np.testing.assert_allclose(fixture['energies'], g['gga_x_pbe_gga_c_pbe_total_energy'], rtol=1e-11)
+
+
 @pytest.mark.parametrize('backend', BACKENDS, indirect=True)
 @pytest.mark.parametrize('key', XC_ASSEMBLY_CASES)
 def test_potentials_and_band_mode_loss_match_reference_assembly(backend, key):
