@@ -14,6 +14,27 @@ from scipy.interpolate import CubicSpline
 from .beta import max_radius, sbt_numerical
 
 
+def _atomic_form_factors(g, r_grid, local_potential_grid, local_potential_charge):
+  """u_a(G) = 4 pi [SBT_0{V_a + Z_a / r}(|G|) - Z_a / |G|^2], u_a(0) = 0: one real (x, y, z) array per
+  atom; atoms of one species share it."""
+  g_radius = np.sqrt((g * g).sum(-1))
+  kmax = max_radius(g)
+  g2 = g_radius ** 2
+  g2[0, 0, 0] = 1e20                      # the reference's 1e10 ** 2 guard; the bin is zeroed below
+  radial, out = {}, []
+  for r, v_r, z in zip(r_grid, local_potential_grid, local_potential_charge):
+    r, v_r = np.asarray(r), np.asarray(v_r)
+    key = (r.shape[0], float(z), float(r[0]), float(r[-1]), float(v_r[0]), float(v_r.sum()))
+    if key not in radial:
+      kk, f_k = sbt_numerical(r, (v_r + z / r)[None], 0, kmax)
+      short = 4 * np.pi * CubicSpline(kk, f_k[0])(g_radius)     # V + Z/r: short ranged
+      atom = short - 4 * np.pi * z / g2                          # minus the Coulomb tail
+      atom[0, 0, 0] = 0.0
+      radial[key] = atom
+    out.append(radial[key])
+  return out
+
+
 def potential_local_reciprocal(positions, g_vector_grid, r_grid, local_potential_grid,
                                local_potential_charge, vol: float,
                                fourier_transform_method: str = 'sbt') -> np.ndarray:
@@ -23,23 +44,29 @@ def potential_local_reciprocal(positions, g_vector_grid, r_grid, local_potential
                      "Only 'sbt' (the reference's default) is implemented.")
   g = np.asarray(g_vector_grid, dtype=np.float64)
   pos = np.asarray(positions, dtype=np.float64).reshape(-1, 3)
-  g_radius = np.sqrt((g * g).sum(-1))
-  kmax = max_radius(g)
-  g2 = g_radius ** 2
-  g2[0, 0, 0] = 1e20                      # the reference's 1e10 ** 2 guard; the bin is zeroed below
   v_g = np.zeros(g.shape[:-1], dtype=np.complex128)
-  radial = {}
+  u = _atomic_form_factors(g, r_grid, local_potential_grid, local_potential_charge)
   for a in range(pos.shape[0]):
-    r, v_r, z = np.asarray(r_grid[a]), np.asarray(local_potential_grid[a]), local_potential_charge[a]
-    key = (r.shape[0], float(z), float(r[0]), float(r[-1]), float(v_r[0]), float(v_r.sum()))
-    if key not in radial:
-      kk, f_k = sbt_numerical(r, (v_r + z / r)[None], 0, kmax)
-      short = 4 * np.pi * CubicSpline(kk, f_k[0])(g_radius)     # V + Z/r: short ranged
-      atom = short - 4 * np.pi * z / g2                          # minus the Coulomb tail
-      atom[0, 0, 0] = 0.0
-      radial[key] = atom
-    v_g += radial[key] * np.exp(-1j * (g @ pos[a]))
-  return v_g * (g_radius.size / vol)
+    v_g += u[a] * np.exp(-1j * (g @ pos[a]))
+  return v_g * (v_g.size / vol)
+
+
+def energy_local_position_gradient(reciprocal_density_grid, positions, g_vector_grid, r_grid,
+                                   local_potential_grid, local_potential_charge) -> np.ndarray:
+  """dE_loc / dR_a, (atom, 3): what jax.grad of energy_local gives the reference through the
+  structure factor of local.py:120-126.  E_loc = Re sum_G conj(V_loc) rho_hat Omega / N^2 and
+  V_loc = (N / Omega) sum_a u_a(G) e^{-i G.R_a}  =>  dE/dR_a = Re sum_G i G u_a e^{+i G.R_a} rho_hat / N."""
+  g = np.asarray(g_vector_grid, dtype=np.float64)
+  pos = np.asarray(positions, dtype=np.float64).reshape(-1, 3)
+  rho = np.asarray(reciprocal_density_grid)
+  if rho.ndim == 4:
+    rho = rho.sum(0)
+  u = _atomic_form_factors(g, r_grid, local_potential_grid, local_potential_charge)
+  out = np.zeros((pos.shape[0], 3))
+  for a in range(pos.shape[0]):
+    w = u[a] * np.exp(1j * (g @ pos[a])) * rho
+    out[a] = np.real(1j * np.einsum('xyzd,xyz->d', g, w)) / rho.size
+  return out
 
 
 def energy_local(reciprocal_density_grid, potential_local_grid_reciprocal, vol: float) -> float:

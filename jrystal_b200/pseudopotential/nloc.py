@@ -27,6 +27,21 @@ def sphere_vectors(g_vector_grid, kpts, freq_mask) -> np.ndarray:
   return g[None] + np.asarray(kpts, dtype=np.float64).reshape(-1, 1, 3)
 
 
+def projector_rows(nonlocal_angular_momentum, nonlocal_d_matrix):
+  """(keep, atom): for the (atom, beta, m) rows in the reference's order, which rows are not
+  structurally zero (m < 2 l + 1 for a projector that feeds the row) and the atom each row
+  belongs to.  Independent of the k-points, so the row count of a plan never changes."""
+  nm = 2 * int(max(int(np.max(l)) for l in nonlocal_angular_momentum)) + 1
+  keep, atom = [], []
+  for a, (d, l) in enumerate(zip(nonlocal_d_matrix, nonlocal_angular_momentum)):
+    mixes = np.abs(np.linalg.eigh(np.asarray(d, dtype=np.float64))[1]) > 0       # (b1, b2)
+    has_m = np.arange(nm)[None, :] < 2 * np.asarray(l).astype(int)[:, None] + 1  # (b2, m)
+    rows = (mixes.astype(int) @ has_m.astype(int)).reshape(-1) > 0
+    keep.append(rows)
+    atom.append(np.full(rows.shape, a))
+  return np.concatenate(keep), np.concatenate(atom)
+
+
 def potential_nonlocal_psi_sphere(position, g_vector_grid, kpts, freq_mask, r_grid,
                                   nonlocal_beta_grid, nonlocal_angular_momentum, nonlocal_d_matrix,
                                   drop_zero_rows: bool = True,
@@ -66,13 +81,7 @@ def potential_nonlocal_psi_sphere(position, g_vector_grid, kpts, freq_mask, r_gr
     blocks.append(out.reshape(out.shape[0], -1, out.shape[-1]))
   phi = np.concatenate(blocks, axis=1)
   if drop_zero_rows:
-    # structural zeros only (m >= 2 l + 1 for every projector feeding the row), so that the row
-    # count does not depend on the k-points
-    keep = np.concatenate([
-      ((np.abs(np.linalg.eigh(np.asarray(d, dtype=np.float64))[1]) > 0)
-       @ (np.arange(nm)[None, :] < 2 * np.asarray(l).astype(int)[:, None] + 1)).reshape(-1) > 0
-      for d, l in zip(nonlocal_d_matrix, nonlocal_angular_momentum)])
-    phi = phi[:, keep]
+    phi = phi[:, projector_rows(nonlocal_angular_momentum, nonlocal_d_matrix)[0]]
   return np.ascontiguousarray(phi)
 
 
@@ -110,3 +119,20 @@ def energy_nonlocal(coeff_sphere, phi_sphere, vol: float, occupation) -> float:
   """Host twin of nloc.py:217-236."""
   h = hamiltonian_nonlocal(coeff_sphere, phi_sphere, vol)
   return float(np.real(np.sum(np.diagonal(h, axis1=-2, axis2=-1) * np.asarray(occupation))))
+
+
+def energy_nonlocal_position_gradient(coeff_sphere, phi_sphere, row_atom, gk_sphere, vol: float,
+                                      occupation, num_atom: int) -> np.ndarray:
+  """dE_nl / dR_a, (atom, 3): the position cotangent jax.grad gives the reference through the
+  structure factor e^{-i (G+k).R_a} of nloc.py:122-129.  With F_p = sum_g c_g Phi_pg:
+  dE_nl/dR_a = (2 / Omega) sum_skb f sum_{p in a} Re( conj(F_p) sum_g c_g Phi_pg (-i (G+k)_g) ).
+  coeff_sphere (s, k, g, b); phi_sphere (k, proj, g); row_atom (proj,) from projector_rows (kept
+  rows); gk_sphere (k, g, 3) from sphere_vectors."""
+  c = np.asarray(coeff_sphere)
+  phi = np.asarray(phi_sphere)
+  f = np.einsum('skgb,kpg->skbp', c, phi)
+  df = np.einsum('skgb,kpg,kgd->skbpd', c, phi, -1j * np.asarray(gk_sphere))
+  per_row = 2.0 / vol * np.real(np.einsum('skb,skbp,skbpd->pd', np.asarray(occupation), np.conj(f), df))
+  out = np.zeros((num_atom, 3))
+  np.add.at(out, np.asarray(row_atom), per_row)
+  return out
