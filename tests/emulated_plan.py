@@ -137,8 +137,12 @@ class EmulatedPlan:
   def wave_grid(self, q):
     return rp.wave_grid(self._box(q), self.vol)
 
-  def density(self, q, occ):
-    return rp.density_grid(self._box(q), self.vol, occ)
+  def density(self, q, occ, out=None):
+    rho = rp.density_grid(self._box(q), self.vol, occ)
+    if out is not None:
+      out.copy_(rho)
+      return out
+    return rho
 
   def density_reciprocal(self, rho):
     return torch.fft.fftn(rho, dim=(-3, -2, -1))
@@ -231,6 +235,50 @@ class EmulatedPlan:
     out[1].copy_(grads[0])
     out[2].copy_(grads[1])
     return out[0], out[1], out[2], (grads[2].detach() if want_occ_grad else None)
+
+
+class EmulatedRowsPlan:
+  """CPU stand-in for jrystal_b200.plan.RowsPlan (jrb_qr_rows_*): the split-phase Cholesky-QR2 and
+  its adjoint on a block of sphere rows; the caller all-reduces the small matrices between the
+  phases (parallel.RowShardedEvaluator)."""
+
+  def __init__(self, nrows, num_k, num_bands, num_spin=1, device=None):
+    self.ns, self.nk, self.nb, self.ng = int(num_spin), int(num_k), int(num_bands), int(nrows)
+    self.tdev = torch.device('cpu')
+    self._r1 = self._q1 = self._r = None
+
+  @staticmethod
+  def _chol_upper(s):
+    return torch.linalg.cholesky(s).conj().transpose(-1, -2)      # S = R^H R
+
+  def gram(self, w_re, w_im, pass_, out=None):
+    x = (w_re + 1j * w_im) if pass_ == 0 else self._q1
+    return torch.einsum('skgi,skgj->skij', x.conj(), x)
+
+  def apply(self, w_re, w_im, pass_, s, q=None, r=None):
+    if pass_ == 0:
+      self._r1 = self._chol_upper(s)
+      self._q1 = (w_re + 1j * w_im) @ torch.linalg.inv(self._r1)
+      return None, None
+    r2 = self._chol_upper(s)
+    self._r = r2 @ self._r1
+    return self._q1 @ torch.linalg.inv(r2), self._r
+
+  def bwd_gram(self, q, gq, out=None):
+    return torch.einsum('skgi,skgj->skij', q.conj(), gq)
+
+  def bwd_apply(self, q, gq, occ, m, out=None):
+    f = occ[:, :, None, :].to(gq.dtype)
+    g = gq * f                                                   # dE/dQ* = HQ diag(f)
+    mf = m * f                                                   # Q^H G summed over ALL rows
+    up = torch.triu(mf, 1)
+    x = -(up + up.conj().transpose(-1, -2)
+          + torch.diag_embed(torch.diagonal(mf, dim1=-2, dim2=-1).real.to(mf.dtype)))
+    gw = (g + q @ x) @ torch.linalg.inv(self._r).conj().transpose(-1, -2)
+    return (2 * gw.real).contiguous(), (2 * gw.imag).contiguous()
+
+  def check_status(self):
+    pass
 
 
 class EmulatedAdam:

@@ -218,3 +218,66 @@ def test_command_line_with_the_shipped_config_keys(emulated, tmp_path, capsys):
                'Did not converge after 6 steps'):
     assert line in out, line
   assert (tmp_path / 'density.npy').exists()
+
+
+# ---------------------------------------------------------------------------------------------
+# N > 1, fewer k-points than ranks: the row/band-sharded evaluation (Gamma-only supercells, C3a)
+# ---------------------------------------------------------------------------------------------
+
+def _rank_row_sharded(rank, world, port, out_dir):
+  import os
+  import numpy as np
+  import torch
+  import torch.distributed as dist
+  import jrystal_b200.plan as plan_mod
+  from jrystal_b200 import parallel
+  from oracle import reference_port as rp
+  os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
+  dist.init_process_group('gloo', rank=rank, world_size=world)
+  try:
+    torch.set_num_threads(2)
+    plan_mod.Plan, plan_mod.RowsPlan = emulated_plan.EmulatedPlan, emulated_plan.EmulatedRowsPlan
+    s = rp.System.from_name('diamond', [12, 12, 12], [1, 1, 1], 10.0)     # Gamma only
+    nb = 7                                                                 # odd: uneven band blocks
+    p = rp.param_init(3, nb, s.num_k, s.mask)
+    occ = rp.occupation_uniform(s.num_k, s.num_electrons, num_bands=nb).numpy()
+    occ = occ * (1.0 + 0.1 * np.random.default_rng(4).random(occ.shape))
+    ev = parallel.RowShardedEvaluator(s.cell, s.mask, s.kpts, nb, s.positions, s.charges)
+    w_re = torch.from_numpy(np.ascontiguousarray(p['w_re'][:, :, ev.g0:ev.g1]))
+    w_im = torch.from_numpy(np.ascontiguousarray(p['w_im'][:, :, ev.g0:ev.g1]))
+    en, g_re, g_im, rho = ev.evaluate(w_re, w_im, torch.from_numpy(occ), 'lda_x')
+    np.savez(os.path.join(out_dir, f'rows{rank}.npz'), en=en.numpy(), g_re=g_re.numpy(),
+             g_im=g_im.numpy(), rho=rho.numpy(), g0=ev.g0, g1=ev.g1, b0=ev.b0, b1=ev.b1)
+  finally:
+    dist.destroy_process_group()
+
+
+def test_gloo_world2_row_band_sharded_evaluation(tmp_path):
+  """parallel.RowShardedEvaluator on 2 ranks (rows of the parameters for the QR, bands for the
+  FFT work, two all-to-alls, Gram / rho / E_kin all-reduces) == the oracle's single evaluation:
+  energies, density and the row blocks of both gradients."""
+  import os
+  import numpy as np
+  import torch.multiprocessing as mp
+  from oracle import reference_port as rp
+  port = 37500 + (os.getpid() % 2000)
+  mp.spawn(_rank_row_sharded, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+  s = rp.System.from_name('diamond', [12, 12, 12], [1, 1, 1], 10.0)
+  nb = 7
+  p = rp.param_init(3, nb, s.num_k, s.mask)
+  occ = rp.occupation_uniform(s.num_k, s.num_electrons, num_bands=nb).numpy()
+  occ = occ * (1.0 + 0.1 * np.random.default_rng(4).random(occ.shape))
+  ref = rp.energy_and_grad(s, p['w_re'], p['w_im'], occ)
+  rows = 0
+  for rank in range(2):
+    d = np.load(tmp_path / f'rows{rank}.npz')
+    g0, g1 = int(d['g0']), int(d['g1'])
+    rows += g1 - g0
+    np.testing.assert_allclose(d['en'], [ref['e_kin'], ref['e_ext'], ref['e_har'], ref['e_xc']],
+                               rtol=1e-10)
+    assert np.abs(d['rho'] - ref['density']).max() < 1e-10 * np.abs(ref['density']).max()
+    scale = np.abs(ref['g_re']).max()
+    assert np.abs(d['g_re'] - ref['g_re'][:, :, g0:g1]).max() < 1e-9 * scale
+    assert np.abs(d['g_im'] - ref['g_im'][:, :, g0:g1]).max() < 1e-9 * scale
+    assert int(d['b1']) - int(d['b0']) in (3, 4)
+  assert rows == s.num_g
