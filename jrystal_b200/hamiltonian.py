@@ -3,8 +3,6 @@
 `hamiltonian_matrix_trace` is the band-mode loss (hamiltonian.py:105-168); `hamiltonian_matrix`
 (171-240, nb Hessian-vector products through AD in the reference) is evaluated analytically as
 C^H (T C + FFT(v IFFT C)) from ONE H-apply."""
-import torch
-
 from . import pw as _pw
 from .energy import _plan_with_atoms
 

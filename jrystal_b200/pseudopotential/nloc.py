@@ -12,7 +12,7 @@ coefficients vanish outside the sphere, so only Phi[..., mask] ever contributes:
 Reference behaviour kept on purpose: |F|^2 is weighted by |eigval| (the sign of a negative D_ii is
 lost through conj(sqrt(eigval)) * sqrt(eigval)), and i^{l} is indexed by the OUTPUT projector b1;
 both are exact for the shipped pseudopotentials (diagonal positive D)."""
-from typing import List, Optional, Sequence
+from typing import List, Optional
 
 import numpy as np
 

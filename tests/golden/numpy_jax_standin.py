@@ -33,7 +33,6 @@ differences of the pinned energies (tests/test_oracle.py).
 """
 import dataclasses
 import importlib
-import itertools
 import sys
 import types
 

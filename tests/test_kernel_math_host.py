@@ -46,7 +46,6 @@ def test_device_xc_functionals_on_the_host(tmp_path):
   eps_xc and the derivatives the fused grid kernels use, the GGA ones by forward-mode duals)
   compiled for the host, against the oracle's functionals differentiated by torch autograd, from
   the density thresholds up to 900 electrons / bohr^3."""
-  import numpy as np
   import torch
   from oracle import reference_port as rp
   lines = _build_and_run('test_xc_functionals', tmp_path)
