@@ -17,15 +17,20 @@ from scipy.special import spherical_jn
 K_MIN = 1e-4  # sbt_numerical.py:45
 
 
-def sbt_numerical(r_grid, f_grid, l, kmax: float) -> Tuple[np.ndarray, np.ndarray]:
-  """(k grid (2 nr,), F (nf, 2 nr)); l is one int or one int per row of f_grid."""
+def sbt_numerical(r_grid, f_grid, l, kmax: float, delta_r=None) -> Tuple[np.ndarray, np.ndarray]:
+  """(k grid (2 nr,), F (nf, 2 nr)); l is one int or one int per row of f_grid.  `delta_r`
+  overrides the quadrature weights (e.g. the UPF's PP_RAB, as the reference's sbt_test does);
+  default: forward differences of r with the last point dropped."""
   r = np.asarray(r_grid, dtype=np.float64)
   f = np.atleast_2d(np.asarray(f_grid, dtype=np.float64))
   ls = [int(l)] * f.shape[0] if np.ndim(l) == 0 else [int(v) for v in l]
   if len(ls) != f.shape[0]:
     raise ValueError('The length of l must be the same as the batch dimension of f_grid')
-  dr = np.zeros_like(r)
-  dr[:-1] = r[1:] - r[:-1]
+  if delta_r is None:
+    dr = np.zeros_like(r)
+    dr[:-1] = r[1:] - r[:-1]
+  else:
+    dr = np.asarray(delta_r, dtype=np.float64)
   k = np.linspace(K_MIN, kmax, 2 * r.shape[0])
   kr = k[:, None] * r[None, :]
   w = r * r * dr

@@ -191,8 +191,13 @@ def normcons_case():
   sp = A(sph.cartesian_to_spherical(dirs))
   ylm = {f'ylm_real_l{l}': A(sph.batch_sph_harm_real(l, sp[:, 1], sp[:, 2])) for l in range(3)}
 
+  # sbt_numerical with the UPF's own quadrature weights (the call of jrystal/sbt/sbt_test.py:57-63)
+  sbt_num = ref('sbt.sbt_numerical')
+  kk, bk = sbt_num.sbt(pp.r_grid[0], pp.nonlocal_beta_grid[0], l=list(pp.nonlocal_angular_momentum[0]),
+                       kmax=100, delta_r=pp.r_ab[0])
   phi = A(phi)
   out = dict(
+    pp_r_ab=A(pp.r_ab[0]), sbt_rab_k=A(kk)[::37], sbt_rab_beta=A(bk)[:, ::37],
     vol=np.array(vol), grid=np.array(gs), kpts=A(kpts), mask=mask, occ=occ,
     w_re_sum=np.array(w_re.sum()), w_im_sum=np.array(w_im.sum()),
     # parse_upf / NormConservingPseudopotential.create

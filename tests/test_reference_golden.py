@@ -246,7 +246,7 @@ API_DEVIATIONS = {
   'ewald.ewald_coulomb_repulsion': 'accepts the reference form AND a converged (cell_vectors) form; vol / eta / grid therefore default to None',
   'pseudopotential.load.parse_pp_info': 'internal helper, same dict out',
   'pseudopotential.load.parse_pp_nonlocal': 'internal helper, same dict out',
-  'pseudopotential.beta.sbt_numerical': 'kmax is required here (None is a bug in the reference: linspace to None); delta_r override not offered',
+  'pseudopotential.beta.sbt_numerical': 'kmax is required here (the reference\'s default None makes linspace fail)',
   'pseudopotential.nloc.energy_nonlocal': 'sphere layout: coefficients (s, k, g, b) and projectors (k, proj, g) instead of the dense box',
   'pseudopotential.nloc.hamiltonian_nonlocal': 'sphere layout, as above',
 }
