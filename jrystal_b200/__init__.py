@@ -6,10 +6,10 @@ include/jrystal_b200.h.  No CPU fallback: compute calls need the built
 jrystal_b200/csrc/libjrystal_b200.so and a CUDA device.
 """
 from . import _lib  # noqa: F401
-from . import crystal, energy, grid, hamiltonian, kinetic, occupation, potential, pw  # noqa: F401
+from . import autograd, crystal, energy, grid, hamiltonian, kinetic, occupation, potential, pw  # noqa: F401
 from .context import current_plan, use_plan  # noqa: F401
 from .crystal import Crystal  # noqa: F401
 from .plan import Plan  # noqa: F401
 
 __all__ = ['Plan', 'Crystal', 'use_plan', 'current_plan', 'pw', 'grid', 'energy', 'potential',
-           'kinetic', 'hamiltonian', 'occupation', 'crystal']
+           'kinetic', 'hamiltonian', 'occupation', 'crystal', 'autograd']

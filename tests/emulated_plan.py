@@ -212,21 +212,22 @@ class EmulatedPlan:
     come from the TOTAL density, the kinetic slot reports the TOTAL `e_kin`, and the gradients
     are those of this plan's own orbitals in the total potential (what jrb_eval_finish does)."""
     assert self._atoms
-    wr = self._w[0].clone().requires_grad_(True)
-    wi = self._w[1].clone().requires_grad_(True)
-    oc = occ.clone().requires_grad_(True)
-    q = rp.unitary_matrix(wr, wi)
-    c = self._box(q)
-    own = rp.density_grid(c, self.vol, oc)
-    dens = own + (rho - own.detach())               # other ranks' share enters as a constant
-    dens_g = torch.fft.fftn(dens, dim=(-3, -2, -1))
-    e0 = (self.kinetic(q) * oc).sum()
-    if self.nproj:
-      e0 = e0 + self.nonlocal_energy(q, oc)[0]
-    e1 = rp.reciprocal_braket(self.v_ext, dens_g, self.vol)
-    e2 = rp.energy_hartree(dens_g, self.g_vec, self.vol)
-    e3 = rp.energy_xc(dens, self.vol, xc, kohn_sham=False, g_vector_grid=self.g_vec)
-    grads = torch.autograd.grad(e0 + e1 + e2 + e3, [wr, wi, oc])
+    with torch.enable_grad():  # callable from inside a torch.autograd.Function forward
+      wr = self._w[0].clone().requires_grad_(True)
+      wi = self._w[1].clone().requires_grad_(True)
+      oc = occ.clone().requires_grad_(True)
+      q = rp.unitary_matrix(wr, wi)
+      c = self._box(q)
+      own = rp.density_grid(c, self.vol, oc)
+      dens = own + (rho - own.detach())               # other ranks' share enters as a constant
+      dens_g = torch.fft.fftn(dens, dim=(-3, -2, -1))
+      e0 = (self.kinetic(q) * oc).sum()
+      if self.nproj:
+        e0 = e0 + self.nonlocal_energy(q, oc)[0]
+      e1 = rp.reciprocal_braket(self.v_ext, dens_g, self.vol)
+      e2 = rp.energy_hartree(dens_g, self.g_vec, self.vol)
+      e3 = rp.energy_xc(dens, self.vol, xc, kohn_sham=False, g_vector_grid=self.g_vec)
+      grads = torch.autograd.grad(e0 + e1 + e2 + e3, [wr, wi, oc])
     en = torch.stack([e_kin.reshape(()).to(e1.dtype), e1, e2, e3]).detach()
     if out is None:
       out = (torch.empty(4, dtype=torch.float64), torch.empty(self.sphere_shape, dtype=torch.float64),
