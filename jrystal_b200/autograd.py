@@ -89,3 +89,66 @@ def hamiltonian_trace(param_pw, veff: Optional[torch.Tensor] = None, plan=None,
     w_re, w_im = param_pw
   tr, eps = _HamiltonianTrace.apply(w_re, w_im, plan, veff)
   return (tr, eps) if per_band else tr
+
+
+# ---------------------------------------------------------------------------------------------
+# Fine-grained pieces: the reference's own call sequence (pw.coeff -> energy.total_energy) under
+# torch.autograd.  Gradients of complex tensors follow torch's convention: for a real loss L the
+# gradient of z = x + i y is dL/dx + i dL/dy = 2 dL/dz*.
+# ---------------------------------------------------------------------------------------------
+
+class _OrthonormalCoefficients(torch.autograd.Function):
+  """pw.coeff: Q of the QR of w_re + i w_im (jrb_qr_fwd); backward = the closed-form QR adjoint
+  (jrb_qr_bwd), which maps dE/dQ* to (dE/dw_re, dE/dw_im)."""
+
+  @staticmethod
+  def forward(ctx, w_re, w_im, plan):
+    q, r = plan.qr_fwd(w_re.contiguous(), w_im.contiguous())
+    ctx.plan = plan
+    ctx.save_for_backward(q, r)
+    ctx.mark_non_differentiable(r)
+    return q, r
+
+  @staticmethod
+  def backward(ctx, grad_q, _grad_r):
+    q, r = ctx.saved_tensors
+    g_re, g_im = ctx.plan.qr_bwd(q, r, (0.5 * grad_q).contiguous())   # torch grad = 2 dL/dQ*
+    return g_re, g_im, None
+
+
+def orthonormal_coefficients(w_re, w_im, plan):
+  return _OrthonormalCoefficients.apply(w_re, w_im, plan)
+
+
+class _EnergyOfCoefficients(torch.autograd.Function):
+  """E_kin + E_ext + E_har + E_xc of orthonormal coefficients Q and occupations f (jrb_density,
+  jrb_kinetic, jrb_grid_potential); backward: dE/dQ* = f H Q (one jrb_hpsi with
+  v_eff = dE/d rho) and dE/df = <q|H|q> (jrb_band_expect)."""
+
+  @staticmethod
+  def forward(ctx, q, occ, plan, xc):
+    q, occ = q.contiguous(), occ.contiguous()
+    rho = plan.density(q, occ)
+    t = plan.kinetic(q)
+    en, veff = plan.grid_potential(rho, xc, False)
+    e_kin = (t * occ).sum()
+    if getattr(plan, 'nproj', 0):
+      e_kin = e_kin + plan.nonlocal_energy(q, occ)[0]
+    energies = torch.stack([e_kin, en[1], en[0], en[2]])
+    ctx.plan = plan
+    ctx.save_for_backward(q, occ, veff)
+    ctx.mark_non_differentiable(energies, rho)
+    return energies.sum(), energies, rho
+
+  @staticmethod
+  def backward(ctx, ct, _ct_energies, _ct_rho):
+    q, occ, veff = ctx.saved_tensors
+    hq = ctx.plan.hpsi(q, veff)
+    g_occ = ctx.plan.band_expect(q, hq)
+    g_q = 2.0 * hq * occ[:, :, None, :].to(hq.dtype)
+    return ct * g_q, ct * g_occ, None, None
+
+
+def energy_of_coefficients(q, occupation, plan, xc: str = 'lda_x'):
+  """(E, energies[4] detached, rho detached) for Q (ns, nk, ng, nb) complex and f (ns, nk, nb)."""
+  return _EnergyOfCoefficients.apply(q, occupation, plan, xc)

@@ -92,6 +92,15 @@ def total_energy(coefficient, position, charge, g_vector_grid, kpts, vol, occupa
   if occupation is None:
     occupation = torch.ones((plan.ns, plan.nk, plan.nb), dtype=torch.float64, device=plan.tdev)
   occ = _pw._occ(plan, occupation)
+  if torch.is_grad_enabled() and (c.q.requires_grad or occ.requires_grad):
+    # the reference differentiates this very call (jax.value_and_grad of the tutorial / driver
+    # closure): under torch.autograd the SUM is differentiable in the coefficients and the
+    # occupations (custom backward = one H-apply); the split terms come back detached
+    if kohn_sham:
+      raise NotImplementedError('total_energy(kohn_sham=True) is not differentiable here')
+    from .autograd import energy_of_coefficients
+    e, energies, _ = energy_of_coefficients(c.q, occ, plan, xc)
+    return tuple(energies) if split else e
   rho = plan.density(c.q, occ)
   en, _ = plan.grid_potential(rho, xc, kohn_sham)
   e_kin = torch.sum(plan.kinetic(c.q) * occ)

@@ -63,7 +63,13 @@ def coeff(pw_param: Union[dict, tuple, list], freq_mask, sharding=None) -> Coeff
     w_re, w_im = pw_param['w_re'], pw_param['w_im']
   else:
     w_re, w_im = pw_param
-  q, r = plan.qr_fwd(w_re, w_im)
+  if torch.is_grad_enabled() and (getattr(w_re, 'requires_grad', False)
+                                  or getattr(w_im, 'requires_grad', False)):
+    # under torch.autograd the handle carries a differentiable Q (backward = the QR adjoint)
+    from .autograd import orthonormal_coefficients
+    q, r = orthonormal_coefficients(w_re, w_im, plan)
+  else:
+    q, r = plan.qr_fwd(w_re, w_im)
   return Coefficients(plan, q, r)
 
 

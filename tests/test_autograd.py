@@ -74,3 +74,41 @@ def test_hamiltonian_trace_is_differentiable(backend):
   plan.prepare_potential(veff)
   tr2 = jb.autograd.hamiltonian_trace({'w_re': w_re, 'w_im': w_im}, None, plan=plan)
   assert abs(float(tr2) - float(tr)) < 1e-12 * abs(float(tr))
+
+
+@pytest.mark.parametrize('backend', BACKENDS, indirect=True)
+def test_reference_call_sequence_under_autograd(backend):
+  """The tutorial's closure, call for call (docs/examples/dft100lines.rst: occupation.idempotent ->
+  pw.coeff -> energy.total_energy), differentiated by torch.autograd through the fine-grained
+  custom backwards (QR adjoint; H-apply) == the fused evaluation == the oracle."""
+  import jrystal_b200 as jb
+  kind, Plan, dev = backend
+  s, nb, p = _case()
+  ne = s.num_electrons
+  w_occ = np.random.default_rng(2).random((nb * s.num_k, (ne // 2) * s.num_k))
+  plan = Plan(s.cell, s.mask, s.kpts, nb)
+  w_re = dev(p['w_re']).requires_grad_(True)
+  w_im = dev(p['w_im']).requires_grad_(True)
+  leaf = dev(w_occ).requires_grad_(True)
+  with jb.use_plan(plan):
+    occ = jb.occupation.idempotent({'param_up': {'w_re': leaf}, 'param_down': {'w_re': leaf}}, s.num_k)
+    coeff = jb.pw.coeff({'w_re': w_re, 'w_im': w_im}, s.mask)
+    assert coeff.q.requires_grad
+    e = jb.energy.total_energy(coeff, s.positions, s.charges, s.g_vec, s.kpts, s.vol, occ, xc='lda_x')
+    g_re, g_im, g_leaf = torch.autograd.grad(e, [w_re, w_im, leaf])
+    parts = jb.energy.total_energy(coeff, s.positions, s.charges, s.g_vec, s.kpts, s.vol, occ,
+                                   xc='lda_x', split=True)
+    with torch.no_grad():   # outside autograd nothing changes: plain values
+      e_plain = jb.energy.total_energy(jb.pw.coeff({'w_re': w_re, 'w_im': w_im}, s.mask), s.positions,
+                                       s.charges, s.g_vec, s.kpts, s.vol, occ.detach())
+  o_leaf = torch.from_numpy(w_occ).requires_grad_(True)
+  o_occ = rp.occupation_idempotent(o_leaf, o_leaf, s.num_k)
+  ref = rp.energy_and_grad(s, p['w_re'], p['w_im'], o_occ.detach().numpy(), occ_grad=True)
+  (o_g_leaf,) = torch.autograd.grad((torch.from_numpy(ref['g_occ']) * o_occ).sum(), o_leaf)
+  assert abs(e.item() - ref['e_tot']) < 1e-10 * abs(ref['e_tot'])
+  assert abs(float(e_plain) - ref['e_tot']) < 1e-10 * abs(ref['e_tot'])
+  for got, key in zip(parts, ['e_kin', 'e_ext', 'e_har', 'e_xc']):
+    assert not got.requires_grad and abs(float(got) - ref[key]) < 1e-10 * abs(ref[key])
+  assert relerr(g_re.cpu().numpy(), ref['g_re']) < 1e-8
+  assert relerr(g_im.cpu().numpy(), ref['g_im']) < 1e-8
+  assert relerr(g_leaf.cpu().numpy(), o_g_leaf.numpy()) < 1e-8
