@@ -152,3 +152,24 @@ class _EnergyOfCoefficients(torch.autograd.Function):
 def energy_of_coefficients(q, occupation, plan, xc: str = 'lda_x'):
   """(E, energies[4] detached, rho detached) for Q (ns, nk, ng, nb) complex and f (ns, nk, nb)."""
   return _EnergyOfCoefficients.apply(q, occupation, plan, xc)
+
+
+class _BandExpectation(torch.autograd.Function):
+  """eps[s, k, b] = <q_b| T + v (+ V_nl) |q_b> for a FIXED potential (jrb_hpsi + jrb_band_expect);
+  H is Hermitian, so d(sum ct eps)/dQ* = ct H Q."""
+
+  @staticmethod
+  def forward(ctx, q, plan, veff):
+    q = q.contiguous()
+    hq = plan.hpsi(q, veff)
+    ctx.save_for_backward(hq)
+    return plan.band_expect(q, hq)
+
+  @staticmethod
+  def backward(ctx, ct):
+    (hq,) = ctx.saved_tensors
+    return 2.0 * hq * ct[:, :, None, :].to(hq.dtype), None, None
+
+
+def band_expectation(q, plan, veff):
+  return _BandExpectation.apply(q, plan, veff)

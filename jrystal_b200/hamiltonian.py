@@ -3,6 +3,8 @@
 `hamiltonian_matrix_trace` is the band-mode loss (hamiltonian.py:105-168); `hamiltonian_matrix`
 (171-240, nb Hessian-vector products through AD in the reference) is evaluated analytically as
 C^H (T C + FFT(v IFFT C)) from ONE H-apply."""
+import torch
+
 from . import pw as _pw
 from .energy import _plan_with_atoms
 
@@ -30,8 +32,17 @@ def hamiltonian_matrix_trace(band_coefficient, positions, charges, effictive_den
   result.  keep_spin_axis (not a reference argument) only matters with keep_kpts_axis=False:
   True keeps [spin]."""
   del g_vector_grid, kpts, vol
-  c, plan, hq = _apply(band_coefficient, positions, charges, effictive_density_grid, xc, kohn_sham)
-  eps = plan.band_expect(c.q, hq)          # (ns, nk, nb)
+  c = _pw._as_coeff(band_coefficient)
+  if torch.is_grad_enabled() and c.q.requires_grad:
+    # the band-mode loss under torch.autograd (calc_band_structure_all_electrons.py:139-152
+    # differentiates this call): the potential of the given density is a constant
+    from .autograd import band_expectation
+    plan = _plan_with_atoms(positions, charges)
+    rho = effictive_density_grid if effictive_density_grid.ndim == 4 else effictive_density_grid[None]
+    eps = band_expectation(c.q, plan, plan.potential(rho.detach().contiguous(), xc, kohn_sham, 7))
+  else:
+    c, plan, hq = _apply(c, positions, charges, effictive_density_grid, xc, kohn_sham)
+    eps = plan.band_expect(c.q, hq)        # (ns, nk, nb)
   out = eps.sum(dim=-1)                    # (ns, nk)
   if keep_kpts_axis:
     return out

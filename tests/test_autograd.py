@@ -112,3 +112,27 @@ def test_reference_call_sequence_under_autograd(backend):
   assert relerr(g_re.cpu().numpy(), ref['g_re']) < 1e-8
   assert relerr(g_im.cpu().numpy(), ref['g_im']) < 1e-8
   assert relerr(g_leaf.cpu().numpy(), o_g_leaf.numpy()) < 1e-8
+
+
+@pytest.mark.parametrize('backend', BACKENDS, indirect=True)
+def test_band_mode_loss_call_under_autograd(backend):
+  """hamiltonian.hamiltonian_matrix_trace(pw.coeff(params), ..., density) differentiated by
+  torch.autograd, the call the reference's band driver differentiates."""
+  import jrystal_b200 as jb
+  kind, Plan, dev = backend
+  s, nb, p = _case()
+  occ = rp.occupation_uniform(s.num_k, s.num_electrons, num_bands=nb)
+  q = rp.unitary_matrix(torch.from_numpy(p['w_re']), torch.from_numpy(p['w_im']))
+  rho = rp.density_grid(rp.expand_coefficient(q, s.mask), s.vol, occ)
+  plan = Plan(s.cell, s.mask, s.kpts, nb)
+  w_re = dev(p['w_re']).requires_grad_(True)
+  w_im = dev(p['w_im']).requires_grad_(True)
+  with jb.use_plan(plan):
+    coeff = jb.pw.coeff({'w_re': w_re, 'w_im': w_im}, s.mask)
+    tr = jb.hamiltonian.hamiltonian_matrix_trace(coeff, s.positions, s.charges, dev(rho.numpy()),
+                                                 s.g_vec, s.kpts, s.vol, xc='lda_x', kohn_sham=True)
+    g_re, g_im = torch.autograd.grad(tr, [w_re, w_im])
+  ref = rp.band_trace_and_grad(s, p['w_re'], p['w_im'], rho.numpy(), 'lda_x')
+  assert abs(tr.item() - ref['trace']) < 1e-10 * abs(ref['trace'])
+  assert relerr(g_re.cpu().numpy(), ref['g_re']) < 1e-8
+  assert relerr(g_im.cpu().numpy(), ref['g_im']) < 1e-8
