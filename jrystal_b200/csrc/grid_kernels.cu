@@ -307,7 +307,7 @@ k_veff_xc(GridGeom g, const cplx* __restrict__ grid, const double* __restrict__ 
        i += (long long)gridDim.x * blockDim.x) {
     const double vhe = grid[i].x;
     if (vxc_pre) {  // GGA: the local part comes from k_gga_local, the gradient part is in vhe
-      veff[i] = vhe + xs * vxc_pre[i];
+      veff[i] = (parts & 4) ? vhe + vxc_pre[i] : vhe;  // without the xc part vxc_pre is stale: not even read
     } else if (ns == 1) {
       const double n = rho[i];
       double e, de;
