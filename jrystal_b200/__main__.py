@@ -6,6 +6,7 @@ import sys
 import numpy as np
 
 from . import calc
+from .calc import ground_state_io
 from .config import get_config
 
 
@@ -13,6 +14,9 @@ def main(argv=None):
   ap = argparse.ArgumentParser(prog='jrystal_b200')
   ap.add_argument('-m', '--mode', choices=['energy', 'band'], default='energy')
   ap.add_argument('-c', '--config', default=None, help='config.yaml (reference keys)')
+  ap.add_argument('-l', '--load', default=None,
+                  help='band mode: ground_state.npz (or its directory) written by the energy mode '
+                       'into save_dir, instead of minimising the energy again (main.py:31-38)')
   args = ap.parse_args(argv)
   config = get_config(args.config)
   log = print if config.verbose else None
@@ -32,8 +36,10 @@ def main(argv=None):
           f'{out.seconds_per_step * 1e3:.3f} ms/step')
     if config.save_dir:
       np.save(f'{config.save_dir}/density.npy', out.density.cpu().numpy())
+      print(f'saved {ground_state_io.save(out, config.save_dir)}')
   else:
-    out = calc.band(config, log=log)
+    ground_state = ground_state_io.load(args.load, config) if args.load else None
+    out = calc.band(config, ground_state=ground_state, log=log)
     name = ''.join(out.ground_state.crystal.symbols) + '_band_structure.npy'
     np.save(name, out.eigenvalues)
     print(f'saved {name}: eigenvalues {out.eigenvalues.shape} (spin, k, band)')

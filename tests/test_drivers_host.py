@@ -220,6 +220,49 @@ def test_command_line_with_the_shipped_config_keys(emulated, tmp_path, capsys):
   assert (tmp_path / 'density.npy').exists()
 
 
+def test_command_line_band_mode_loads_the_saved_ground_state(emulated, tmp_path, capsys, monkeypatch):
+  """`-m energy` with save_dir writes ground_state.npz; `-m band -l` takes the density from it
+  instead of minimising again (the reference declares -l / save_dir, main.py:31-38, config.py:64,
+  without wiring them) and gives the eigenvalues of the in-process flow; a file made for another
+  grid is refused."""
+  import numpy as np
+  import yaml
+  from jrystal_b200 import calc
+  from jrystal_b200.__main__ import main
+  from jrystal_b200.calc import calc_band_structure_all_electrons as band_mod
+  from jrystal_b200.calc import ground_state_io
+  from jrystal_b200.config import get_config
+  cfg = dict(crystal='diamond', grid_sizes=12, k_grid_sizes=[1, 1, 2], cutoff_energy=10, empty_bands=2,
+             epoch=6, occupation='uniform', xc='lda_x', verbose=False, orbital_grid='full',
+             convergence_condition=1e-12, save_dir=str(tmp_path), band_structure_empty_bands=2,
+             num_kpoints=2, k_path_special_points='GX', band_structure_epoch=30,
+             k_path_fine_tuning_epoch=10)
+  path = tmp_path / 'config.yaml'
+  path.write_text(yaml.safe_dump(cfg))
+  monkeypatch.chdir(tmp_path)                       # the band mode writes its .npy into the cwd
+  assert main(['-m', 'energy', '-c', str(path)]) == 0
+  assert (tmp_path / ground_state_io.FILE_NAME).exists()
+  config = get_config(str(path))
+  gs = ground_state_io.load(str(tmp_path), config)
+  assert gs.steps == 6 and len(gs.total_energy_history) == 6
+  assert tuple(gs.density.shape) == (1, 12, 12, 12)
+  np.testing.assert_array_equal(gs.density.numpy(), np.load(tmp_path / 'density.npy'))
+  assert abs(sum(gs.energies[k] for k in ('kinetic', 'external', 'hartree', 'xc', 'ewald'))
+             - gs.total_energy) < 1e-12 * abs(gs.total_energy)
+  expected = calc.band(config, ground_state=gs).eigenvalues
+
+  def no_energy_run(*a, **k):
+    raise AssertionError('the band mode minimised the energy again although -l was given')
+  monkeypatch.setattr(band_mod, 'energy_calc', no_energy_run)
+  assert main(['-m', 'band', '-c', str(path), '-l', str(tmp_path / ground_state_io.FILE_NAME)]) == 0
+  assert 'CC_band_structure.npy' in capsys.readouterr().out
+  np.testing.assert_allclose(np.load(tmp_path / 'CC_band_structure.npy'), expected, rtol=0, atol=1e-12)
+  with pytest.raises(ValueError):
+    ground_state_io.load(str(tmp_path), get_config(str(path), grid_sizes=16))
+  with pytest.raises(ValueError):
+    ground_state_io.load(str(tmp_path), get_config(str(path), xc='lda_x+lda_c_pw'))
+
+
 # ---------------------------------------------------------------------------------------------
 # N > 1, fewer k-points than ranks: the row/band-sharded evaluation (Gamma-only supercells, C3a)
 # ---------------------------------------------------------------------------------------------
