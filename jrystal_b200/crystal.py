@@ -121,6 +121,10 @@ class Crystal:
 
   @staticmethod
   def create_builtin(name: str, repeat=None, spin: Optional[int] = None):
+    if name not in BUILTIN:
+      raise ValueError(f'crystal "{name}" is not built in (built in: {sorted(BUILTIN)}); point '
+                       'crystal_file_path_path at its extended-xyz file (the reference ships its '
+                       'structures as geometry/<name>.xyz)')
     lattice, symbols, pos = BUILTIN[name]
     lattice = np.asarray(lattice, dtype=np.float64)
     pos = np.asarray(pos, dtype=np.float64)

@@ -194,6 +194,47 @@ def test_k_path_and_config_defaults():
   assert cfg.band_structure_empty_bands == 8
 
 
+def test_k_path_tables_of_the_other_shipped_lattices():
+  """BCC primitive (li), hexagonal (mg, graphene, zns_w), tetragonal (li_slab), orthorhombic cells:
+  lattice detection and the special points at their textbook Cartesian places."""
+  from jrystal_b200 import k_path
+  from jrystal_b200.crystal import Crystal
+  tp = 2 * np.pi
+  a = 3.51
+  bcc = a / 2 * np.array([[-1.0, 1, 1], [1, -1, 1], [1, 1, -1]])
+  assert k_path.lattice_type(bcc) == 'bcc'
+  pts = k_path.get_k_path(bcc, 'GHNGPH', 41)
+  for want in ([0, 1, 0], [0.5, 0.5, 0], [0.5, 0.5, 0.5]):            # H, N, P in units of 2 pi / a
+    assert any(np.allclose(p, np.array(want) * tp / a, atol=1e-12) for p in pts), want
+  a, c = 3.20302773, 5.126691
+  hexc = np.array([[a, 0, 0], [-a / 2, a * np.sqrt(3) / 2, 0], [0, 0, c]])
+  assert k_path.lattice_type(hexc) == 'hex'
+  pts = k_path.get_k_path(hexc, 'GMKGALHA', 61)
+  norms = np.linalg.norm(pts, axis=1)
+  assert any(abs(n - tp / a / np.sqrt(3)) < 1e-12 for n in norms)      # |M| = 2 pi / (sqrt(3) a)
+  assert any(abs(n - 2 * tp / (3 * a)) < 1e-12 for n in norms)         # |K| = 4 pi / (3 a)
+  assert any(np.allclose(p, [0, 0, tp / (2 * c)], atol=1e-12) for p in pts)   # A
+  # K is a zone corner: equidistant from Gamma and the two nearest reciprocal lattice points
+  b = tp * np.linalg.inv(hexc).T
+  k = (b[0] + b[1]) / 3
+  assert abs(np.linalg.norm(k) - np.linalg.norm(k - b[0])) < 1e-12
+  assert abs(np.linalg.norm(k) - np.linalg.norm(k - b[1])) < 1e-12
+  tet = np.diag([3.285, 3.285, 21.14])
+  assert k_path.lattice_type(tet) == 'tet'
+  f = k_path.get_k_path(tet, None, 50, fractional=True)                # default path GXMGZRAZ
+  np.testing.assert_allclose(f[0], [0, 0, 0])
+  np.testing.assert_allclose(f[-1], [0, 0, 0.5])
+  assert any(np.allclose(x, [0.5, 0.5, 0.5]) for x in f)
+  assert k_path.lattice_type(np.diag([3.0, 4.0, 5.0])) == 'orc'
+  assert k_path.lattice_type(np.diag([4.2906] * 3)) == 'cubic'
+  for bad in (np.array([[a, 0, 0], [a / 2, a * np.sqrt(3) / 2, 0], [0, 0, c]]),   # 60 degree setting
+              np.array([[3.0, 0, 0], [0.4, 4.0, 0], [0, 0, 5.0]])):               # monoclinic
+    with pytest.raises(NotImplementedError):
+      k_path.lattice_type(bad)
+  with pytest.raises(ValueError, match='crystal_file_path_path'):
+    Crystal.create_builtin('graphene')
+
+
 def test_temperature_schedule_matches_optax_exponential_decay():
   from jrystal_b200.calc.calc_ground_state_energy_all_electrons import temperature_scheduler
   from jrystal_b200.config import get_config
