@@ -16,7 +16,7 @@ def pytest_configure(config):
 # stand-in only.  They are ordered after the hardware-verified suite so that `pytest -x` cannot
 # hide it behind a first failure among them.  Drop a file from this list once it has passed on a B200.
 NOT_YET_RUN_ON_HARDWARE = ['test_reference_golden.py', 'test_autograd.py',
-                           'test_pseudopotential.py', 'test_drivers_host.py']
+                           'test_pseudopotential.py', 'test_drivers_host.py', 'test_utils_api.py']
 
 
 def pytest_collection_modifyitems(config, items):

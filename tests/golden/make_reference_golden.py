@@ -399,6 +399,7 @@ API_MODULES = {  # jrystal_b200 module -> reference module it mirrors
   'pseudopotential.local': 'pseudopotential.local', 'pseudopotential.beta': 'pseudopotential.beta',
   'pseudopotential.nloc': 'pseudopotential.nloc',
   'pseudopotential.spherical': 'pseudopotential.spherical',
+  'utils': '_src.utils', 'entropy': '_src.entropy',
 }
 
 

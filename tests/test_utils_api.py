@@ -1,0 +1,85 @@
+"""jrystal_b200.utils / entropy / the calc and package namespaces under the reference's names
+(jrystal/utils/__init__.py, jrystal/entropy.py, jrystal/calc/__init__.py, jrystal/__init__.py)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import reference_port as rp
+from tests.common import relerr
+from tests.conftest import BACKENDS
+
+
+def test_namespaces_carry_the_reference_names():
+  import jrystal_b200 as jb
+  for name in ('calc', 'config', 'crystal', 'energy', 'entropy', 'ewald', 'grid', 'hamiltonian',
+               'occupation', 'potential', 'pseudopotential', 'pw', 'utils', 'Crystal', 'get_pkg_path'):
+    assert hasattr(jb, name), name
+  for name in ('energy_all_electrons', 'band_all_electrons', 'energy_normcons', 'band_normcons'):
+    assert callable(getattr(jb.calc, name)), name
+  assert jb.calc.energy_all_electrons is jb.calc.energy
+  import os
+  assert os.path.isdir(os.path.join(jb.get_pkg_path(), 'jrystal_b200'))
+
+
+def test_safe_real_and_entropy():
+  from jrystal_b200 import entropy, utils
+  assert utils.safe_real(np.array([1.0 + 1e-10j]))[0] == 1.0
+  assert utils.safe_real(torch.tensor([2.0 + 1e-10j], dtype=torch.complex128))[0] == 2.0
+  x = np.array([1.0, 2.0])
+  assert utils.safe_real(x) is not None and not np.iscomplexobj(utils.safe_real(x))
+  for bad in (np.array([1.0 + 1.0j]), torch.tensor([1.0 + 1.0j])):
+    with pytest.raises(ValueError):
+      utils.safe_real(bad)
+  with pytest.raises(ValueError):
+    utils.check_spin_number(8, 1)
+  utils.check_spin_number(13, 1)
+  assert utils.fft_factor(11) == 12 and abs(utils.volume(np.diag([1.0, 2.0, 3.0])) - 6.0) < 1e-15
+  occ = np.random.default_rng(0).random((1, 3, 4)) / 3 * 2
+  s_np = entropy.fermi_dirac(occ)
+  t = torch.from_numpy(occ).requires_grad_(True)
+  s_t = entropy.fermi_dirac(t)
+  assert abs(float(s_t) - s_np) < 1e-14 * abs(s_np)
+  fmax = 2.0 / 3
+  want = -np.sum(occ * np.log(1e-8 + occ) + (fmax - occ) * np.log(1e-8 + fmax - occ))
+  assert abs(s_np - want) < 1e-14 * abs(want)
+  (g,) = torch.autograd.grad(s_t, t)                    # keeps its graph (the -T S term of the driver)
+  assert g.shape == t.shape and torch.isfinite(g).all()
+
+
+@pytest.mark.parametrize('backend', BACKENDS, indirect=True)
+def test_utils_on_the_current_plan(backend):
+  """expand_coefficient / squeeze_coefficient against the mask scatter they stand for
+  (utils.py:277-281, 303-308), wave_to_density(_reciprocal) of the dense psi(r) against
+  pw.density_grid(_reciprocal) and the oracle."""
+  import jrystal_b200 as jb
+  kind, Plan, dev = backend
+  s = rp.System.from_name('diamond', [8, 9, 12], [1, 1, 2], 8.0)
+  nb = 5
+  p = rp.param_init(4, nb, s.num_k, s.mask)
+  occ = rp.occupation_uniform(s.num_k, s.num_electrons, num_bands=nb).numpy()
+  occ = occ * (1.0 + 0.2 * np.random.default_rng(1).random(occ.shape))
+  plan = Plan(s.cell, s.mask, s.kpts, nb)
+  plan.set_atoms(s.positions, s.charges)
+  with jb.use_plan(plan):
+    coeff = jb.pw.coeff({'w_re': dev(p['w_re']), 'w_im': dev(p['w_im'])}, s.mask)
+    dense = jb.utils.expand_coefficient(coeff.q, s.mask)
+    q = coeff.q.cpu().numpy()
+    want = np.zeros((1, s.num_k, nb) + tuple(s.mask.shape), dtype=np.complex128)
+    want[..., s.mask] = np.swapaxes(q, -1, -2)
+    np.testing.assert_array_equal(dense.cpu().numpy(), want)
+    back = jb.utils.squeeze_coefficient(dense, s.mask)
+    np.testing.assert_array_equal(back.cpu().numpy(), q)
+    with pytest.raises(ValueError):
+      jb.utils.expand_coefficient(coeff.q, ~s.mask)
+    psi = jb.pw.wave_grid(coeff, s.vol)
+    rho = jb.utils.wave_to_density(psi, dev(occ))
+    rho_fused = jb.pw.density_grid(coeff, s.vol, dev(occ))
+    assert relerr(rho.cpu().numpy(), rho_fused.cpu().numpy()) < 1e-12
+    per_orbital = jb.utils.wave_to_density(psi)
+    assert tuple(per_orbital.shape) == tuple(psi.shape) and not per_orbital.is_complex()
+    rho_g = jb.utils.wave_to_density_reciprocal(psi, dev(occ))
+    assert relerr(rho_g.cpu().numpy(), jb.pw.density_grid_reciprocal(coeff, s.vol, dev(occ)).cpu().numpy()) < 1e-12
+    with pytest.raises(ValueError):
+      jb.utils.wave_to_density(psi, dev(occ)[:, :, :-1])
+  ref = rp.density_grid(rp.expand_coefficient(torch.from_numpy(q), s.mask), s.vol, torch.from_numpy(occ))
+  assert relerr(rho.cpu().numpy(), ref.numpy()) < 1e-10

@@ -6,7 +6,7 @@
 mkdir -p gpurun_out
 timeout 600 python -m pytest -q -m gpu \
   tests/test_reference_golden.py tests/test_autograd.py tests/test_pseudopotential.py \
-  tests/test_drivers_host.py \
+  tests/test_drivers_host.py tests/test_utils_api.py \
   2>&1 | tail -25 | tee gpurun_out/new_gpu_tests.log
 timeout 1500 python -m pytest tests -m gpu -x -q 2>&1 | tail -4 | tee gpurun_out/all_gpu_tests.log
 python bench.py --steps 5 --no-cpu > gpurun_out/bench_default.json 2> gpurun_out/bench_default.err
