@@ -7,7 +7,7 @@ jrystal_b200/csrc/libjrystal_b200.so and a CUDA device.
 """
 from . import _lib  # noqa: F401
 from . import (autograd, calc, config, crystal, energy, entropy, ewald, grid, hamiltonian,  # noqa: F401
-               kinetic, occupation, potential, pseudopotential, pw, utils)
+               kinetic, occupation, potential, pseudopotential, pw, sbt, utils)
 from .context import current_plan, use_plan  # noqa: F401
 from .crystal import Crystal  # noqa: F401
 from .plan import Plan  # noqa: F401
@@ -22,4 +22,4 @@ def get_pkg_path() -> str:
 
 __all__ = ['Plan', 'Crystal', 'use_plan', 'current_plan', 'pw', 'grid', 'energy', 'potential',
            'kinetic', 'hamiltonian', 'occupation', 'crystal', 'autograd', 'calc', 'config',
-           'entropy', 'ewald', 'pseudopotential', 'utils', 'get_pkg_path']
+           'entropy', 'ewald', 'pseudopotential', 'sbt', 'utils', 'get_pkg_path']

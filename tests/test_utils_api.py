@@ -12,11 +12,12 @@ from tests.conftest import BACKENDS
 def test_namespaces_carry_the_reference_names():
   import jrystal_b200 as jb
   for name in ('calc', 'config', 'crystal', 'energy', 'entropy', 'ewald', 'grid', 'hamiltonian',
-               'occupation', 'potential', 'pseudopotential', 'pw', 'utils', 'Crystal', 'get_pkg_path'):
+               'occupation', 'potential', 'pseudopotential', 'pw', 'sbt', 'utils', 'Crystal', 'get_pkg_path'):
     assert hasattr(jb, name), name
   for name in ('energy_all_electrons', 'band_all_electrons', 'energy_normcons', 'band_normcons'):
     assert callable(getattr(jb.calc, name)), name
   assert jb.calc.energy_all_electrons is jb.calc.energy
+  assert jb.sbt.sbt_numerical is jb.pseudopotential.beta.sbt_numerical
   import os
   assert os.path.isdir(os.path.join(jb.get_pkg_path(), 'jrystal_b200'))
 
