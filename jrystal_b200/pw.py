@@ -114,3 +114,62 @@ def _occ(plan, occupation):
 def _check_vol(plan, vol):
   if abs(float(vol) - plan.vol) > 1e-9 * plan.vol:
     raise ValueError(f'vol={vol} differs from the cell volume of the current plan ({plan.vol})')
+
+
+# -- point evaluations (pw.py:337-511 of the reference: diagnostics / test helpers) ---------------
+# Direct plane-wave sums over the cut-off sphere at ONE position r (the reference sums over the
+# whole zero-padded box); O(M ng) elementwise torch work on the device that holds the coefficients.
+
+def _point_sums(r, coeff, cell_vectors, g_vector_grid, want_gradient):
+  from .grid import g_vectors
+  c = _as_coeff(coeff)
+  p = c.plan
+  r = np.asarray(r.detach().cpu() if isinstance(r, torch.Tensor) else r, dtype=np.float64).reshape(-1)
+  if r.shape != (3,):
+    raise ValueError('r must have shape (3,)')
+  _check_vol(p, abs(np.linalg.det(np.asarray(cell_vectors, dtype=np.float64))))
+  if g_vector_grid is None:
+    g_vector_grid = g_vectors(cell_vectors, [p.nx, p.ny, p.nz])
+  g = np.asarray(g_vector_grid, dtype=np.float64)[p.mask.astype(bool)]            # (ng, 3)
+  q = c.q
+  phase = torch.from_numpy(np.exp(1j * (g @ r))).to(q.device)                     # (ng,)
+  a = torch.einsum('skgb,g->skb', q, phase)                                       # sqrt(vol) psi(r)
+  if not want_gradient:
+    return p, a, None
+  ig = torch.from_numpy(1j * g).to(q.device) * phase[:, None]                     # (ng, 3)
+  da = torch.einsum('skgb,gd->skbd', q, ig)                                       # sqrt(vol) grad psi
+  return p, a, 2.0 * (a.conj()[..., None] * da).real                              # grad |a|^2
+
+
+def wave_r(r, coeff, cell_vectors, g_vector_grid=None) -> torch.Tensor:
+  """jrystal/_src/pw.py:337-381: psi[s, k, b](r) = vol^-1/2 sum_G c_G exp(i G.r) (no Bloch phase,
+  as the reference)."""
+  p, a, _ = _point_sums(r, coeff, cell_vectors, g_vector_grid, False)
+  return a / np.sqrt(p.vol)
+
+
+def density_r(r, coeff, cell_vectors, g_vector_grid=None, occupation=None) -> torch.Tensor:
+  """jrystal/_src/pw.py:384-415: |psi(r)|^2 per orbital, or its occupation-weighted sum."""
+  p, a, _ = _point_sums(r, coeff, cell_vectors, g_vector_grid, False)
+  dens = (a.real * a.real + a.imag * a.imag) / p.vol
+  return dens if occupation is None else torch.sum(dens * _occ(p, occupation).to(dens.device))
+
+
+def nabla_density_r(r, coeff, cell_vectors, g_vector_grid=None, occupation=None) -> torch.Tensor:
+  """jrystal/_src/pw.py:418-447 (jax.grad of density_r there): d density_r / d r, shape (3,) with
+  occupations, (spin, kpt, band, 3) without."""
+  p, _, grad = _point_sums(r, coeff, cell_vectors, g_vector_grid, True)
+  grad = grad / p.vol
+  if occupation is None:
+    return grad
+  return torch.sum(grad * _occ(p, occupation).to(grad.device)[..., None], dim=(0, 1, 2))
+
+
+def nabla_density_grid(r, coeff, cell_vectors, g_vector_grid=None, occupation=None) -> torch.Tensor:
+  """jrystal/_src/pw.py:450-511, the closed-form twin of nabla_density_r with the reference's
+  normalisation: the occupation-weighted sum is divided by the volume, the per-orbital result
+  (spin, kpt, band, 3) is not."""
+  p, _, grad = _point_sums(r, coeff, cell_vectors, g_vector_grid, True)
+  if occupation is None:
+    return grad
+  return torch.sum(grad * _occ(p, occupation).to(grad.device)[..., None], dim=(0, 1, 2)) / p.vol

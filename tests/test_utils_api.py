@@ -84,3 +84,44 @@ def test_utils_on_the_current_plan(backend):
       jb.utils.wave_to_density(psi, dev(occ)[:, :, :-1])
   ref = rp.density_grid(rp.expand_coefficient(torch.from_numpy(q), s.mask), s.vol, torch.from_numpy(occ))
   assert relerr(rho.cpu().numpy(), ref.numpy()) < 1e-10
+
+
+@pytest.mark.parametrize('backend', BACKENDS, indirect=True)
+def test_point_evaluations_equal_the_fft_grids(backend):
+  """The reference's own T1 property (pw_test.py:36-49: wave_grid via FFT == the direct plane-wave
+  sum wave_r at the grid points, atol 1e-8) through the host API, plus density_r == density_grid at
+  the same points and nabla_density_r / nabla_density_grid against central differences."""
+  import jrystal_b200 as jb
+  kind, Plan, dev = backend
+  s = rp.System.from_name('diamond', [7, 8, 9], [1, 1, 1], None, mask_method='cubic')   # pw_test.py:33-34
+  nb = 4
+  p = rp.param_init(2, nb, s.num_k, s.mask)
+  occ = np.random.default_rng(3).random((1, s.num_k, nb))
+  plan = Plan(s.cell, s.mask, s.kpts, nb)
+  plan.set_atoms(s.positions, s.charges)
+  r_grid = jb.grid.r_vectors(s.cell, [7, 8, 9])
+  with jb.use_plan(plan):
+    coeff = jb.pw.coeff({'w_re': dev(p['w_re']), 'w_im': dev(p['w_im'])}, s.mask)
+    psi = jb.pw.wave_grid(coeff, s.vol).cpu().numpy()
+    rho = jb.pw.density_grid(coeff, s.vol, dev(occ)).cpu().numpy()
+    for idx in [(0, 0, 0), (3, 5, 2), (6, 7, 8)]:
+      r = r_grid[idx]
+      w = jb.pw.wave_r(r, coeff, s.cell).cpu().numpy()
+      np.testing.assert_allclose(w, psi[(slice(None),) * 3 + idx], atol=1e-8)
+      d = float(jb.pw.density_r(r, coeff, s.cell, s.g_vec, dev(occ)))
+      assert abs(d - rho[(0,) + idx]) < 1e-10 * abs(rho).max()
+    r0 = np.array([0.31, -0.47, 1.13])
+    g = jb.pw.nabla_density_r(r0, coeff, s.cell, None, dev(occ)).cpu().numpy()
+    h = 1e-5
+    fd = np.array([(float(jb.pw.density_r(r0 + h * e, coeff, s.cell, None, dev(occ)))
+                    - float(jb.pw.density_r(r0 - h * e, coeff, s.cell, None, dev(occ)))) / (2 * h)
+                   for e in np.eye(3)])
+    np.testing.assert_allclose(g, fd, rtol=1e-6, atol=1e-9)
+    g2 = jb.pw.nabla_density_grid(r0, coeff, s.cell, s.g_vec, dev(occ)).cpu().numpy()
+    np.testing.assert_allclose(g2, g, rtol=1e-12, atol=1e-14)
+    per = jb.pw.nabla_density_grid(r0, coeff, s.cell)
+    assert tuple(per.shape) == (1, s.num_k, nb, 3)
+    np.testing.assert_allclose((per.cpu().numpy() * occ[..., None]).sum((0, 1, 2)) / s.vol, g, rtol=1e-12)
+    assert tuple(jb.pw.density_r(r0, coeff, s.cell).shape) == (1, s.num_k, nb)
+    with pytest.raises(ValueError):
+      jb.pw.wave_r(np.zeros(2), coeff, s.cell)
