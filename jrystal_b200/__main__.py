@@ -1,6 +1,7 @@
 """`python -m jrystal_b200 -m energy|band -c config.yaml`: the reference's command line
 (`jrystal -m energy|band -c config.yaml`, jrystal/main.py) on the B200 drivers."""
 import argparse
+import os
 import sys
 
 import numpy as np
@@ -13,11 +14,15 @@ from .config import get_config
 def main(argv=None):
   ap = argparse.ArgumentParser(prog='jrystal_b200')
   ap.add_argument('-m', '--mode', choices=['energy', 'band'], default='energy')
-  ap.add_argument('-c', '--config', default=None, help='config.yaml (reference keys)')
+  ap.add_argument('-c', '--config', default=None,
+                  help='config file with the reference keys; default: ./config.yaml if it exists '
+                       '(the reference\'s default, main.py:24-29), else the built-in defaults')
   ap.add_argument('-l', '--load', default=None,
                   help='band mode: ground_state.npz (or its directory) written by the energy mode '
                        'into save_dir, instead of minimising the energy again (main.py:31-38)')
   args = ap.parse_args(argv)
+  if args.config is None and os.path.exists('config.yaml'):
+    args.config = 'config.yaml'
   config = get_config(args.config)
   log = print if config.verbose else None
   if args.mode == 'energy':

@@ -254,7 +254,8 @@ def test_command_line_band_mode_loads_the_saved_ground_state(emulated, tmp_path,
   def no_energy_run(*a, **k):
     raise AssertionError('the band mode minimised the energy again although -l was given')
   monkeypatch.setattr(band_mod, 'energy_calc', no_energy_run)
-  assert main(['-m', 'band', '-c', str(path), '-l', str(tmp_path / ground_state_io.FILE_NAME)]) == 0
+  # no -c: ./config.yaml of the working directory, the reference's default (main.py:24-29)
+  assert main(['-m', 'band', '-l', str(tmp_path / ground_state_io.FILE_NAME)]) == 0
   assert 'CC_band_structure.npy' in capsys.readouterr().out
   np.testing.assert_allclose(np.load(tmp_path / 'CC_band_structure.npy'), expected, rtol=0, atol=1e-12)
   with pytest.raises(ValueError):
