@@ -17,6 +17,7 @@ def _plan_with_atoms(position, charge):
   if cur != key:
     plan.set_atoms(pos, chg)
     plan._atom_key = key
+    plan._pseudopotential_key = None   # V_ext(G) of the plan is the all-electron table again
   return plan
 
 

@@ -78,3 +78,18 @@ def energy_local(reciprocal_density_grid, potential_local_grid_reciprocal, vol: 
   if rho.ndim == v.ndim + 1:
     rho = rho.sum(0)
   return float(np.real(np.sum(np.conj(v) * rho)) * vol / n / n)
+
+
+def hamiltonian_local(wave_grid, potential_local_grid_reciprocal, vol: float):
+  """jrystal/pseudopotential/local.py:134-161 on a dense psi(r) the caller holds (diagnostic; the
+  evaluation applies V_loc inside the H-apply): <psi_i| v_loc(r) |psi_j> vol / N with
+  v_loc(r) = ifftn(V_loc(G)), (spin, kpt, band, band).  torch tensor in -> torch tensor out."""
+  import torch
+  is_torch = isinstance(wave_grid, torch.Tensor)
+  w = wave_grid if is_torch else torch.from_numpy(np.asarray(wave_grid))
+  v = potential_local_grid_reciprocal
+  v = v if isinstance(v, torch.Tensor) else torch.from_numpy(np.asarray(v, dtype=np.complex128))
+  v_r = torch.fft.ifftn(v.to(w.device), dim=(-3, -2, -1))
+  n = w.shape[-3] * w.shape[-2] * w.shape[-1]
+  h = torch.einsum('skaxyz,xyz,skbxyz->skab', w.conj(), v_r.to(w.dtype), w) * (float(vol) / n)
+  return h if is_torch else h.numpy()

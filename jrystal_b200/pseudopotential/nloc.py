@@ -136,3 +136,63 @@ def energy_nonlocal_position_gradient(coeff_sphere, phi_sphere, row_atom, gk_sph
   out = np.zeros((num_atom, 3))
   np.add.at(out, np.asarray(row_atom), per_row)
   return out
+
+
+# -- the band-mode loss and subspace matrix of the norm-conserving drivers, on the current plan ----
+
+def _plan_with_pseudopotential(coefficient, potential_local_grid_reciprocal,
+                               potential_nl_psi_reciprocal):
+  """Hand V_loc(G) and the projectors to the plan the coefficients live on (once per distinct pair
+  of arrays; jrb_set_external_potential / jrb_set_nonlocal).  Projectors may come dense,
+  (kpt, proj, x, y, z) as the reference builds them, or on the sphere, (kpt, proj, g)."""
+  import torch
+  from .. import pw as _pw
+  c = _pw._as_coeff(coefficient)
+  plan = c.plan
+  host = lambda a: a.detach().cpu().numpy() if isinstance(a, torch.Tensor) else np.asarray(a)
+  v_loc = np.ascontiguousarray(host(potential_local_grid_reciprocal), dtype=np.complex128)
+  phi = host(potential_nl_psi_reciprocal)
+  if phi.ndim == 5:
+    phi = phi[:, :, plan.mask.astype(bool)]
+  phi = np.ascontiguousarray(phi, dtype=np.complex128)
+  key = (v_loc.tobytes(), phi.tobytes())
+  if getattr(plan, '_pseudopotential_key', None) != key:
+    plan.set_external_potential(torch.from_numpy(v_loc).to(c.q.device))
+    plan.set_nonlocal(torch.from_numpy(phi).to(c.q.device) if phi.shape[1] else None)
+    plan._pseudopotential_key = key
+    plan._atom_key = None      # energy._plan_with_atoms must re-send its all-electron table
+  return c, plan
+
+
+def _h_apply(coefficient, hamiltonian_density_grid, potential_local_grid_reciprocal,
+             potential_nl_psi_reciprocal, xc, kohn_sham):
+  c, plan = _plan_with_pseudopotential(coefficient, potential_local_grid_reciprocal,
+                                       potential_nl_psi_reciprocal)
+  rho = hamiltonian_density_grid
+  if rho.ndim == 3:
+    rho = rho[None]
+  v = plan.potential(rho.contiguous(), xc, kohn_sham, 7)    # v_H + V_loc + v_xc of the given density
+  return c, plan, plan.hpsi(c.q, v)                          # + T + V_nl
+
+
+def hamiltonian_matrix(coefficient, hamiltonian_density_grid, potential_local_grid_reciprocal,
+                       potential_nl_psi_reciprocal, g_vector_grid, kpts, vol, xc: str = 'lda_x',
+                       kohn_sham: bool = True):
+  """jrystal/pseudopotential/nloc.py:161-214: <psi_i| T + v_H[rho] + v_xc[rho] + V_loc + V_nl |psi_j>,
+  (spin, kpt, band, band), from ONE H-apply (jrb_potential, jrb_hpsi with the projectors on the
+  sphere) and one FP64 tensor-core Gram (jrb_hamiltonian_matrix) instead of four dense einsums."""
+  del g_vector_grid, kpts, vol
+  c, plan, hq = _h_apply(coefficient, hamiltonian_density_grid, potential_local_grid_reciprocal,
+                         potential_nl_psi_reciprocal, xc, kohn_sham)
+  return plan.overlap(c.q, hq)
+
+
+def hamiltonian_trace(coefficient, hamiltonian_density_grid, potential_local_grid_reciprocal,
+                      potential_nl_psi_reciprocal, g_vector_grid, kpts, vol, xc: str = 'lda_x',
+                      kohn_sham: bool = True):
+  """jrystal/pseudopotential/nloc.py:230-279: the band-mode loss of the norm-conserving driver,
+  sum over (spin, kpt, band) of the diagonal above with unit occupations (a device scalar)."""
+  del g_vector_grid, kpts, vol
+  c, plan, hq = _h_apply(coefficient, hamiltonian_density_grid, potential_local_grid_reciprocal,
+                         potential_nl_psi_reciprocal, xc, kohn_sham)
+  return plan.band_expect(c.q, hq).sum()
