@@ -301,6 +301,85 @@ class EmulatedAdam:
       p.sub_(self.lr * (m / (1 - self.b1 ** t)) / (torch.sqrt(v / (1 - self.b2 ** t)) + self.eps))
 
 
+# ---------------------------------------------------------------------------------------------
+# The argument contract of the real Plan (jrystal_b200/plan.py:_chk): torch tensors of the exact
+# shape and dtype, contiguous.  Enforced here too, so that a test body that would be refused on the
+# GPU (numpy array, wrong dtype, a strided view) already fails on the CPU stand-in.
+# ---------------------------------------------------------------------------------------------
+_F64 = torch.float64
+_SHAPES = {
+  'sphere': lambda p: p.sphere_shape,
+  'occ': lambda p: (p.ns, p.nk, p.nb),
+  'grid': lambda p: (p.ns, p.nx, p.ny, p.nz),
+  'grid3': lambda p: (p.nx, p.ny, p.nz),
+  'small': lambda p: (p.ns, p.nk, p.nb, p.nb),
+  'dense': lambda p: (p.ns, p.nk, p.nb, p.nx, p.ny, p.nz),
+}
+_CONTRACT = {  # method -> [(positional index, parameter name, shape key, dtype, may be None)]
+  'nonlocal_energy': [(0, 'q', 'sphere', C128, False), (1, 'occ', 'occ', _F64, False)],
+  'set_external_potential': [(0, 'vhat', 'grid3', C128, False)],
+  'set_nonlocal': [(0, 'phi', None, C128, True)],
+  'qr_fwd': [(0, 'w_re', 'sphere', _F64, False), (1, 'w_im', 'sphere', _F64, False)],
+  'qr_bwd': [(0, 'q', 'sphere', C128, False), (1, 'r', 'small', C128, False),
+             (2, 'gq', 'sphere', C128, False)],
+  'expand': [(0, 'q', 'sphere', C128, False)],
+  'squeeze': [(0, 'c', 'dense', C128, False)],
+  'density': [(0, 'q', 'sphere', C128, False), (1, 'occ', 'occ', _F64, False)],
+  'kinetic': [(0, 'q', 'sphere', C128, False)],
+  'grid_potential': [(0, 'rho', 'grid', _F64, False)],
+  'potential': [(0, 'rho', 'grid', _F64, False)],
+  'density_reciprocal': [(0, 'rho', 'grid', _F64, False)],
+  'wave_grid': [(0, 'q', 'sphere', C128, False)],
+  'prepare_potential': [(0, 'veff', 'grid', _F64, False)],
+  'hpsi': [(0, 'q', 'sphere', C128, False), (1, 'veff', 'grid', _F64, True)],
+  'band_expect': [(0, 'q', 'sphere', C128, False), (1, 'hq', 'sphere', C128, False)],
+  'overlap': [(0, 'q', 'sphere', C128, False), (1, 'hq', 'sphere', C128, False)],
+  'eval_begin': [(0, 'w_re', 'sphere', _F64, False), (1, 'w_im', 'sphere', _F64, False),
+                 (2, 'occ', 'occ', _F64, False)],
+  'fft3d': [(0, 'x', None, C128, False)],
+}
+
+
+def _check_argument(plan, method, name, t, shape_key, dtype, optional):
+  if t is None and optional:
+    return
+  if not isinstance(t, torch.Tensor):
+    raise TypeError(f'{method}: {name} must be a tensor (the real Plan takes CUDA tensors), got {type(t)}')
+  if shape_key is not None and tuple(t.shape) != tuple(_SHAPES[shape_key](plan)):
+    raise ValueError(f'{method}: {name} has shape {tuple(t.shape)}, expected '
+                     f'{tuple(_SHAPES[shape_key](plan))}')
+  if t.dtype != dtype:
+    raise TypeError(f'{method}: {name} has dtype {t.dtype}, expected {dtype}')
+  if not t.is_contiguous():
+    raise ValueError(f'{method}: {name} must be contiguous')
+
+
+def _with_contract(method, fn, spec):
+  import functools
+
+  @functools.wraps(fn)
+  def checked(self, *args, **kwargs):
+    if getattr(self, '_inside', 0):          # the stand-in calling its own methods: not a caller
+      return fn(self, *args, **kwargs)
+    for index, name, shape_key, dtype, optional in spec:
+      if index < len(args):
+        _check_argument(self, method, name, args[index], shape_key, dtype, optional)
+      elif name in kwargs:
+        _check_argument(self, method, name, kwargs[name], shape_key, dtype, optional)
+    self._inside = 1
+    try:
+      return fn(self, *args, **kwargs)
+    finally:
+      self._inside = 0
+  return checked
+
+
+for _method in [n for n, f in vars(EmulatedPlan).items() if callable(f) and not n.startswith('_')]:
+  # every public method marks "inside", the ones of the contract also check their arguments
+  setattr(EmulatedPlan, _method,
+          _with_contract(_method, getattr(EmulatedPlan, _method), _CONTRACT.get(_method, [])))
+
+
 def patch_drivers(monkeypatch):
   """Point the driver modules at the emulation (Plan, Adam) and make the CUDA-only calls no-ops."""
   from jrystal_b200.calc import (calc_band_structure_all_electrons as band,
