@@ -11,3 +11,9 @@ timeout 600 python -m pytest -q -m gpu \
 timeout 1500 python -m pytest tests -m gpu -x -q 2>&1 | tail -4 | tee gpurun_out/all_gpu_tests.log
 python bench.py --steps 5 --no-cpu > gpurun_out/bench_default.json 2> gpurun_out/bench_default.err
 tail -c 600 gpurun_out/bench_default.json
+# Then (separate calls; see DESIGN.md section 9 for what each one decides):
+#   tools/gpu.sh 900 bash tools/gpu_profile_orbital_grid.sh      # ncu --set full of one C2 evaluation: baseline of the round
+#   gpurun --gpus 2 -- bash tools/gpu_check_2gpu.sh              # row-sharded evaluation bit-for-bit, C2 / C3a at N = 2
+#   gpurun --gpus 8 -- 'python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 \
+#       --master-port 29511 bench.py --gpus 8 --steps 10 --warmup 3 > gpurun_out/bench_n8.json'   # the 80 % target
+#   JRB_HOST_CHUNKS=... / --emulate-ranks 8 are the single-GPU tuning aids for the e2e path and the per-rank share.
