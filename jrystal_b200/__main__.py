@@ -40,7 +40,8 @@ def main(argv=None):
     print(f'{"Converged" if out.converged else "Did not converge"} after {out.steps} steps, '
           f'{out.seconds_per_step * 1e3:.3f} ms/step')
     if config.save_dir:
-      np.save(f'{config.save_dir}/density.npy', out.density.cpu().numpy())
+      os.makedirs(config.save_dir, exist_ok=True)  # before the first write: a converged run is not lost
+      np.save(os.path.join(config.save_dir, 'density.npy'), out.density.cpu().numpy())
       print(f'saved {ground_state_io.save(out, config.save_dir)}')
   else:
     ground_state = ground_state_io.load(args.load, config) if args.load else None

@@ -25,6 +25,7 @@ from ..config import JrystalConfigDict, get_config
 from ..k_path import get_k_path
 from ..optim import Adam
 from ..plan import Plan
+from ..utils import check_spin_number
 from .calc_ground_state_energy_all_electrons import calc as energy_calc
 from .opt_utils import create_crystal, create_freq_mask, create_grids, create_pseudopotential
 
@@ -64,6 +65,7 @@ def calc(config: Optional[JrystalConfigDict] = None, ground_state=None, k_path=N
     world, rank = 1, 0
   lo, hi = parallel.shard_bands(k_path.shape[0], world, rank)  # contiguous chunk of the path
   num_electron = pseudopot.num_valence_electrons if pseudopot is not None else crystal.num_electron
+  check_spin_number(int(num_electron), crystal.spin)
   num_bands = ceil(num_electron / 2) + config.band_structure_empty_bands
   og = config.get('orbital_grid', 'auto')
   plan = Plan(crystal.cell_vectors, freq_mask, k_path[lo:lo + 1], num_bands,

@@ -24,6 +24,7 @@ import torch
 from .. import occupation, parallel
 from ..config import JrystalConfigDict, get_config
 from ..plan import Plan
+from ..utils import check_spin_number
 from .convergence import create_convergence_checker
 from .opt_utils import (create_crystal, create_freq_mask, create_grids, create_optimizer,
                         get_ewald_coulomb_repulsion)
@@ -43,6 +44,8 @@ class GroundStateEnergyOutput:
   converged: bool
   steps: int
   seconds_per_step: float
+  # rows [k0, k1) of the k-mesh that params_pw / occupation hold (a k-sharded run keeps its block)
+  k_range: Optional[tuple] = None
 
 
 def temperature_scheduler(config):
@@ -79,6 +82,8 @@ def minimise(config: JrystalConfigDict, plan: Optional[Plan] = None, use_cuda_gr
   freq_mask = create_freq_mask(config, crystal)
   num_kpts = k_vec.shape[0]
   num_electron = pseudopot.num_valence_electrons if pseudopot is not None else crystal.num_electron
+  # the count the occupations are built from: a parity mismatch would drop an electron silently
+  check_spin_number(int(num_electron), crystal.spin)
   num_bands = ceil(num_electron / 2) + config.empty_bands
   world, rank = parallel._world()
   use_k_mesh = bool(config.parallel_over_k_mesh) and world > 1
@@ -215,4 +220,5 @@ def minimise(config: JrystalConfigDict, plan: Optional[Plan] = None, use_cuda_gr
   return GroundStateEnergyOutput(
     config=config, crystal=crystal, params_pw={'w_re': w_re, 'w_im': w_im}, occupation=occ,
     density=rho.clone(), total_energy=float(en.sum() + ew), energies=energies,
-    total_energy_history=history, converged=bool(converged), steps=steps, seconds_per_step=dt)
+    total_energy_history=history, converged=bool(converged), steps=steps, seconds_per_step=dt,
+    k_range=(int(k0), int(k1)))

@@ -22,6 +22,23 @@ def _grid_sizes(config):
   return [int(g)] * 3 if np.isscalar(g) else [int(v) for v in g]
 
 
+def _k_grid_sizes(config):
+  g = config.k_grid_sizes
+  return [int(g)] * 3 if np.isscalar(g) else [int(v) for v in g]
+
+
+# settings the density depends on beyond cell / grid / functional: stored by `save`, compared by
+# `load` (a density from another cut-off or k-mesh must not be accepted silently)
+_SETTING_KEYS = ('cutoff_energy', 'freq_mask_method', 'spin_restricted', 'occupation', 'smearing',
+                 'spin', 'empty_bands')
+
+
+def _setting(config, key):
+  v = config.get(key)
+  return 'None' if v is None else str(float(v)) if isinstance(v, (int, float)) and not isinstance(
+    v, bool) else str(v)
+
+
 def save(out, path: str) -> str:
   """Write a GroundStateEnergyOutput; `path` is a directory (-> path/ground_state.npz) or a file."""
   if os.path.isdir(path) or not path.endswith('.npz'):
@@ -37,7 +54,13 @@ def save(out, path: str) -> str:
     crystal=np.str_(str(c.crystal)), xc=np.str_(str(c.xc)),
     use_pseudopotential=np.bool_(c.use_pseudopotential),
     grid_sizes=np.asarray(_grid_sizes(c), dtype=np.int64),
-    cell_vectors=np.asarray(out.crystal.cell_vectors, dtype=np.float64))
+    cell_vectors=np.asarray(out.crystal.cell_vectors, dtype=np.float64),
+    k_grid_sizes=np.asarray(_k_grid_sizes(c), dtype=np.int64),
+    # rows [k0, k1) of the k-mesh this file holds (a k-sharded run saves its own block)
+    k_range=np.asarray(getattr(out, 'k_range', None) or (0, out.occupation.shape[1]),
+                       dtype=np.int64))
+  for k in _SETTING_KEYS:
+    arrays['setting_' + k] = np.str_(_setting(c, k))
   for k in _ENERGY_KEYS:
     if k in out.energies:
       arrays['energy_' + k] = np.float64(out.energies[k])
@@ -63,6 +86,18 @@ def load(path: str, config):
         config.use_pseudopotential):
       raise ValueError(f'{path}: saved with xc={str(z["xc"])!r}, use_pseudopotential='
                        f'{bool(z["use_pseudopotential"])}; config differs')
+    if 'k_grid_sizes' in z.files and list(z['k_grid_sizes']) != _k_grid_sizes(config):
+      raise ValueError(f'{path}: saved with k-mesh {list(z["k_grid_sizes"])}, config has '
+                       f'{_k_grid_sizes(config)}')
+    for k in _SETTING_KEYS:
+      if 'setting_' + k in z.files and str(z['setting_' + k]) != _setting(config, k):
+        raise ValueError(f'{path}: saved with {k}={str(z["setting_" + k])}, config has '
+                         f'{_setting(config, k)}')
+    if 'k_range' in z.files:
+      nk_mesh = int(np.prod(_k_grid_sizes(config)))
+      if tuple(int(v) for v in z['k_range']) != (0, nk_mesh):
+        raise ValueError(f'{path}: holds k-points {tuple(z["k_range"])} of {nk_mesh} (the block of '
+                         'one rank of a k-sharded run); gather before loading')
     energies = {k: float(z['energy_' + k]) for k in _ENERGY_KEYS if 'energy_' + k in z.files}
     return GroundStateEnergyOutput(
       config=config, crystal=crystal,

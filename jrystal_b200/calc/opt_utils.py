@@ -6,14 +6,19 @@ from .. import grid
 from ..crystal import Crystal
 from ..ewald import ewald_coulomb_repulsion
 from ..optim import Adam
+from ..utils import check_spin_number
 
 
 def create_crystal(config) -> Crystal:
-  # opt_utils.py:62-86: a file path wins over a built-in name
-  path = config.get('crystal_file_path_path')
-  if path:
-    return Crystal.create_from_file(path, spin=config.get('spin'))
-  return Crystal.create_builtin(config.crystal, spin=config.get('spin'))
+  """opt_utils.py:105-114: a built-in `crystal` name wins over `crystal_file_path_path`, and the
+  spin number must have the parity of the electron count (check_spin_number raises ValueError
+  otherwise: with the default `spin: 0` an odd-electron cell would silently lose an electron)."""
+  if config.get('crystal') is not None:
+    crystal = Crystal.create_builtin(config.crystal, spin=config.get('spin'))
+  else:
+    crystal = Crystal.create_from_file(config.get('crystal_file_path_path'), spin=config.get('spin'))
+  check_spin_number(crystal.num_electron, crystal.spin)
+  return crystal
 
 
 def create_freq_mask(config, crystal=None) -> np.ndarray:
@@ -53,6 +58,10 @@ def create_optimizer(config, params) -> Adam:
   if config.get('scheduler'):
     raise NotImplementedError('Scheduler is not implemented yet.')  # as in the reference
   args = dict(config.optimizer_args)
+  # the reference forwards optimizer_args to optax.adam: keys it omits take optax's defaults
+  # (b1 0.9, b2 0.999), not the b2 = 0.99 of the shipped config
+  args.setdefault('b1', 0.9)
+  args.setdefault('b2', 0.999)
   return Adam(params, learning_rate=args.pop('learning_rate'), **args)
 
 

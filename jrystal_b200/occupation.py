@@ -55,6 +55,12 @@ def _capped_simplex(x, total: float):
     return torch.clamp(v - lam, min=0.0)
 
   n = x.numel()
+  # edges the sort/cumsum rule has no index for: an empty channel and a completely filled one
+  # (empty_bands = 0, or num_electrons == spin); the projection is the constant vertex
+  if total <= 0:
+    return x * 0.0
+  if total >= n:
+    return x * 0.0 + 1.0
   if float(x.detach().sum()) > total:
     return push_down(x, total)
   return 1.0 - push_down(1.0 - x, n - total)

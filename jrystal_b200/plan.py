@@ -17,8 +17,24 @@ def _ptr(t: Optional[torch.Tensor]):
   return None if t is None else ctypes.c_void_p(t.data_ptr())
 
 
-def _stream():
-  return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+def _stream(device=None):
+  """torch's current stream ON `device` (the plan's device, which need not be torch's current
+  one: the C side calls cudaSetDevice(plan.device) and the stream must belong to it)."""
+  return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def _check_tensor(t, shape, dtype, name, device):
+  if not isinstance(t, torch.Tensor) or not t.is_cuda:
+    raise TypeError(f'{name} must be a CUDA tensor')
+  if t.device.index != device:
+    raise ValueError(f'{name} is on {t.device}, plan is on cuda:{device}')
+  if tuple(t.shape) != tuple(shape):
+    raise ValueError(f'{name} has shape {tuple(t.shape)}, expected {tuple(shape)}')
+  if t.dtype != dtype:
+    raise TypeError(f'{name} has dtype {t.dtype}, expected {dtype}')
+  if not t.is_contiguous():
+    raise ValueError(f'{name} must be contiguous')
+  return t
 
 
 class Plan:
@@ -106,17 +122,31 @@ class Plan:
     return int(self.lib.jrb_plan_workspace_bytes(self._h))
 
   def _chk(self, t, shape, dtype, name):
-    if not isinstance(t, torch.Tensor) or not t.is_cuda:
-      raise TypeError(f'{name} must be a CUDA tensor')
-    if t.device.index != self.device:
-      raise ValueError(f'{name} is on {t.device}, plan is on cuda:{self.device}')
-    if tuple(t.shape) != tuple(shape):
-      raise ValueError(f'{name} has shape {tuple(t.shape)}, expected {tuple(shape)}')
-    if t.dtype != dtype:
-      raise TypeError(f'{name} has dtype {t.dtype}, expected {dtype}')
-    if not t.is_contiguous():
-      raise ValueError(f'{name} must be contiguous')
-    return t
+    return _check_tensor(t, shape, dtype, name, self.device)
+
+  def _out(self, out, specs):
+    """Caller-provided output tensors: every element is held to the same contract as the inputs
+    (a wrong shape / device / stride would be an out-of-bounds device write, not a Python error).
+    specs: (shape, dtype, name) per element; returns fresh tensors when out is None."""
+    if out is None:
+      return tuple(self._new(shape, dtype) for shape, dtype, _ in specs)
+    if isinstance(out, torch.Tensor):
+      out = (out,)
+    if len(out) != len(specs):
+      raise ValueError(f'out must hold {len(specs)} tensors ({[n for _, _, n in specs]})')
+    return tuple(self._chk(t, shape, dtype, 'out.' + name) for t, (shape, dtype, name) in zip(out, specs))
+
+  @property
+  def grid_shape(self):
+    return (self.ns, self.nx, self.ny, self.nz)
+
+  @property
+  def small_shape(self):
+    return (self.ns, self.nk, self.nb, self.nb)
+
+  @property
+  def band_shape(self):
+    return (self.ns, self.nk, self.nb)
 
   def _new(self, shape, dtype):
     return torch.empty(shape, dtype=dtype, device=self.tdev)
@@ -128,7 +158,7 @@ class Plan:
     if pos.shape[0] != chg.shape[0]:
       raise ValueError('positions and charges disagree on the number of atoms')
     _lib.check(self.lib.jrb_set_atoms(self._h, pos.ctypes.data, chg.ctypes.data,
-                                      pos.shape[0], _stream()))
+                                      pos.shape[0], _stream(self.device)))
     self._atoms = True
     self._natoms = int(pos.shape[0])
 
@@ -136,20 +166,20 @@ class Plan:
     """Projectors of the non-local pseudopotential on the sphere: complex128 CUDA tensor
     (nk, nproj, ng) = potential_nl_psi_reciprocal[..., mask] (nloc.py:60-141); None removes them."""
     if phi is None:
-      _lib.check(self.lib.jrb_set_nonlocal(self._h, None, 0, _stream()))
+      _lib.check(self.lib.jrb_set_nonlocal(self._h, None, 0, _stream(self.device)))
       self.nproj = 0
       return
     if phi.ndim != 3 or phi.shape[0] != self.nk or phi.shape[2] != self.ng:
       raise ValueError(f'phi must have shape (nk={self.nk}, nproj, ng={self.ng}), got {tuple(phi.shape)}')
     self._chk(phi, tuple(phi.shape), torch.complex128, 'phi')
-    _lib.check(self.lib.jrb_set_nonlocal(self._h, _ptr(phi), int(phi.shape[1]), _stream()))
+    _lib.check(self.lib.jrb_set_nonlocal(self._h, _ptr(phi), int(phi.shape[1]), _stream(self.device)))
     self.nproj = int(phi.shape[1])
 
   def nonlocal_energy(self, q, occ):
     self._chk(q, self.sphere_shape, torch.complex128, 'q')
     self._chk(occ, (self.ns, self.nk, self.nb), torch.float64, 'occupation')
     e = self._new((1,), torch.float64)
-    _lib.check(self.lib.jrb_nonlocal_energy(self._h, _ptr(q), _ptr(occ), _ptr(e), _stream()))
+    _lib.check(self.lib.jrb_nonlocal_energy(self._h, _ptr(q), _ptr(occ), _ptr(e), _stream(self.device)))
     return e
 
   def external_position_gradient(self, rho):
@@ -158,14 +188,14 @@ class Plan:
     if not getattr(self, '_natoms', 0):
       raise RuntimeError('call set_atoms(positions, charges) first')
     g = self._new((self._natoms, 3), torch.float64)
-    _lib.check(self.lib.jrb_external_position_gradient(self._h, _ptr(rho), _ptr(g), _stream()))
+    _lib.check(self.lib.jrb_external_position_gradient(self._h, _ptr(rho), _ptr(g), _stream(self.device)))
     return g
 
   def set_external_potential(self, vhat):
     """V(G) of the external / local pseudopotential term, complex128 CUDA tensor (nx, ny, nz) in
     the convention of potential.external_reciprocal (potential.py:153-166)."""
     self._chk(vhat, (self.nx, self.ny, self.nz), torch.complex128, 'vhat')
-    _lib.check(self.lib.jrb_set_external_potential(self._h, _ptr(vhat), _stream()))
+    _lib.check(self.lib.jrb_set_external_potential(self._h, _ptr(vhat), _stream(self.device)))
     self._atoms = True
     self._natoms = 0
 
@@ -174,64 +204,58 @@ class Plan:
     k = np.ascontiguousarray(np.asarray(kpts, dtype=np.float64).reshape(-1, 3))
     if k.shape[0] != self.nk:
       raise ValueError(f'expected {self.nk} k-points, got {k.shape[0]}')
-    _lib.check(self.lib.jrb_set_kpoints(self._h, k.ctypes.data, _stream()))
+    _lib.check(self.lib.jrb_set_kpoints(self._h, k.ctypes.data, _stream(self.device)))
     self.kpts = k
 
   def check_status(self):
     """Synchronise and raise if an asynchronous call failed numerically (Cholesky breakdown)."""
-    _lib.check(self.lib.jrb_check_status(self._h, _stream()))
+    _lib.check(self.lib.jrb_check_status(self._h, _stream(self.device)))
 
   # -- orthonormalisation -------------------------------------------------------------
   def qr_fwd(self, w_re, w_im, out=None):
     self._chk(w_re, self.sphere_shape, torch.float64, 'w_re')
     self._chk(w_im, self.sphere_shape, torch.float64, 'w_im')
-    if out is None:
-      q = self._new(self.sphere_shape, torch.complex128)
-      r = self._new((self.ns, self.nk, self.nb, self.nb), torch.complex128)
-    else:
-      q, r = out
-    _lib.check(self.lib.jrb_qr_fwd(self._h, _ptr(w_re), _ptr(w_im), _ptr(q), _ptr(r), _stream()))
+    q, r = self._out(out, [(self.sphere_shape, torch.complex128, 'q'),
+                           (self.small_shape, torch.complex128, 'r')])
+    _lib.check(self.lib.jrb_qr_fwd(self._h, _ptr(w_re), _ptr(w_im), _ptr(q), _ptr(r), _stream(self.device)))
     return q, r
 
   def qr_bwd(self, q, r, gq, out=None):
     self._chk(q, self.sphere_shape, torch.complex128, 'q')
     self._chk(r, (self.ns, self.nk, self.nb, self.nb), torch.complex128, 'r')
     self._chk(gq, self.sphere_shape, torch.complex128, 'gq')
-    if out is None:
-      g_re = self._new(self.sphere_shape, torch.float64)
-      g_im = self._new(self.sphere_shape, torch.float64)
-    else:
-      g_re, g_im = out
+    g_re, g_im = self._out(out, [(self.sphere_shape, torch.float64, 'g_re'),
+                                 (self.sphere_shape, torch.float64, 'g_im')])
     _lib.check(self.lib.jrb_qr_bwd(self._h, _ptr(q), _ptr(r), _ptr(gq), _ptr(g_re), _ptr(g_im),
-                                   _stream()))
+                                   _stream(self.device)))
     return g_re, g_im
 
   # -- sphere <-> box ---------------------------------------------------------------
   def expand(self, q):
     self._chk(q, self.sphere_shape, torch.complex128, 'q')
     out = self._new((self.ns, self.nk, self.nb, self.nx, self.ny, self.nz), torch.complex128)
-    _lib.check(self.lib.jrb_expand(self._h, _ptr(q), _ptr(out), _stream()))
+    _lib.check(self.lib.jrb_expand(self._h, _ptr(q), _ptr(out), _stream(self.device)))
     return out
 
   def squeeze(self, coeff_dense):
     self._chk(coeff_dense, (self.ns, self.nk, self.nb, self.nx, self.ny, self.nz),
               torch.complex128, 'coeff')
     q = self._new(self.sphere_shape, torch.complex128)
-    _lib.check(self.lib.jrb_squeeze(self._h, _ptr(coeff_dense), _ptr(q), _stream()))
+    _lib.check(self.lib.jrb_squeeze(self._h, _ptr(coeff_dense), _ptr(q), _stream(self.device)))
     return q
 
   # -- hot path pieces --------------------------------------------------------------
   def density(self, q, occ, out=None):
     self._chk(q, self.sphere_shape, torch.complex128, 'q')
     self._chk(occ, (self.ns, self.nk, self.nb), torch.float64, 'occupation')
-    rho = self._new((self.ns, self.nx, self.ny, self.nz), torch.float64) if out is None else out
-    _lib.check(self.lib.jrb_density(self._h, _ptr(q), _ptr(occ), _ptr(rho), _stream()))
+    rho, = self._out(out, [(self.grid_shape, torch.float64, 'rho')])
+    _lib.check(self.lib.jrb_density(self._h, _ptr(q), _ptr(occ), _ptr(rho), _stream(self.device)))
     return rho
 
   def kinetic(self, q):
     self._chk(q, self.sphere_shape, torch.complex128, 'q')
     t = self._new((self.ns, self.nk, self.nb), torch.float64)
-    _lib.check(self.lib.jrb_kinetic(self._h, _ptr(q), _ptr(t), _stream()))
+    _lib.check(self.lib.jrb_kinetic(self._h, _ptr(q), _ptr(t), _stream(self.device)))
     return t
 
   def grid_potential(self, rho, xc: str = 'lda_x', kohn_sham: bool = False, out=None):
@@ -240,13 +264,10 @@ class Plan:
     self._chk(rho, (self.ns, self.nx, self.ny, self.nz), torch.float64, 'density')
     if xc not in _lib.XC_IDS:
       raise NotImplementedError(f'xc "{xc}" is not implemented (implemented: {list(_lib.XC_IDS)})')
-    if out is None:
-      en = self._new((3,), torch.float64)
-      veff = self._new((self.ns, self.nx, self.ny, self.nz), torch.float64)
-    else:
-      en, veff = out
+    en, veff = self._out(out, [((3,), torch.float64, 'energies'),
+                               (self.grid_shape, torch.float64, 'veff')])
     _lib.check(self.lib.jrb_grid_potential(self._h, _ptr(rho), _lib.XC_IDS[xc],
-                                           int(bool(kohn_sham)), _ptr(en), _ptr(veff), _stream()))
+                                           int(bool(kohn_sham)), _ptr(en), _ptr(veff), _stream(self.device)))
     return en, veff
 
   def potential(self, rho, xc: str = 'lda_x', kohn_sham: bool = False, parts: int = 7):
@@ -259,41 +280,41 @@ class Plan:
       raise NotImplementedError(f'xc "{xc}" is not implemented (implemented: {list(_lib.XC_IDS)})')
     v = self._new((self.ns, self.nx, self.ny, self.nz), torch.float64)
     _lib.check(self.lib.jrb_potential(self._h, _ptr(rho), _lib.XC_IDS[xc], int(bool(kohn_sham)),
-                                      int(parts), _ptr(v), _stream()))
+                                      int(parts), _ptr(v), _stream(self.device)))
     return v
 
   def density_reciprocal(self, rho):
     self._chk(rho, (self.ns, self.nx, self.ny, self.nz), torch.float64, 'density')
     out = self._new((self.ns, self.nx, self.ny, self.nz), torch.complex128)
-    _lib.check(self.lib.jrb_density_reciprocal(self._h, _ptr(rho), _ptr(out), _stream()))
+    _lib.check(self.lib.jrb_density_reciprocal(self._h, _ptr(rho), _ptr(out), _stream(self.device)))
     return out
 
   def wave_grid(self, q):
     self._chk(q, self.sphere_shape, torch.complex128, 'q')
     out = self._new((self.ns, self.nk, self.nb, self.nx, self.ny, self.nz), torch.complex128)
-    _lib.check(self.lib.jrb_wave_grid(self._h, _ptr(q), _ptr(out), _stream()))
+    _lib.check(self.lib.jrb_wave_grid(self._h, _ptr(q), _ptr(out), _stream(self.device)))
     return out
 
   def prepare_potential(self, veff):
     """Fix the potential of the following hpsi(q, None) calls (jrb_hpsi_prepare): copied into plan
     work space and resampled onto the orbital grid once."""
     self._chk(veff, (self.ns, self.nx, self.ny, self.nz), torch.float64, 'veff')
-    _lib.check(self.lib.jrb_hpsi_prepare(self._h, _ptr(veff), _stream()))
+    _lib.check(self.lib.jrb_hpsi_prepare(self._h, _ptr(veff), _stream(self.device)))
 
   def hpsi(self, q, veff, out=None):
     """veff=None applies the potential of the last prepare_potential()."""
     self._chk(q, self.sphere_shape, torch.complex128, 'q')
     if veff is not None:
       self._chk(veff, (self.ns, self.nx, self.ny, self.nz), torch.float64, 'veff')
-    hq = self._new(self.sphere_shape, torch.complex128) if out is None else out
-    _lib.check(self.lib.jrb_hpsi(self._h, _ptr(q), _ptr(veff), _ptr(hq), _stream()))
+    hq, = self._out(out, [(self.sphere_shape, torch.complex128, 'hq')])
+    _lib.check(self.lib.jrb_hpsi(self._h, _ptr(q), _ptr(veff), _ptr(hq), _stream(self.device)))
     return hq
 
   def band_expect(self, q, hq, out=None):
     self._chk(q, self.sphere_shape, torch.complex128, 'q')
     self._chk(hq, self.sphere_shape, torch.complex128, 'hq')
-    eps = self._new((self.ns, self.nk, self.nb), torch.float64) if out is None else out
-    _lib.check(self.lib.jrb_band_expect(self._h, _ptr(q), _ptr(hq), _ptr(eps), _stream()))
+    eps, = self._out(out, [(self.band_shape, torch.float64, 'eps')])
+    _lib.check(self.lib.jrb_band_expect(self._h, _ptr(q), _ptr(hq), _ptr(eps), _stream(self.device)))
     return eps
 
   def overlap(self, q, hq):
@@ -301,7 +322,7 @@ class Plan:
     self._chk(q, self.sphere_shape, torch.complex128, 'q')
     self._chk(hq, self.sphere_shape, torch.complex128, 'hq')
     h = self._new((self.ns, self.nk, self.nb, self.nb), torch.complex128)
-    _lib.check(self.lib.jrb_hamiltonian_matrix(self._h, _ptr(q), _ptr(hq), _ptr(h), _stream()))
+    _lib.check(self.lib.jrb_hamiltonian_matrix(self._h, _ptr(q), _ptr(hq), _ptr(h), _stream(self.device)))
     return h
 
   def fft3d(self, x, inverse: bool, out=None):
@@ -311,11 +332,14 @@ class Plan:
       raise ValueError(f'Input must have at least 3 dimensions, got {x.ndim}')
     if tuple(x.shape[-3:]) != (self.nx, self.ny, self.nz):
       raise ValueError(f'last three axes {tuple(x.shape[-3:])} do not match the plan grid')
-    out = torch.empty_like(x) if out is None else out
+    out = torch.empty_like(x) if out is None else self._chk(out, tuple(x.shape), torch.complex128,
+                                                            'out')
+    if x.device.index != self.device:
+      raise ValueError(f'x is on {x.device}, plan is on cuda:{self.device}')
     batch = int(np.prod(x.shape[:-3])) if x.ndim > 3 else 1
     _lib.check(self.lib.jrb_fft3d(self._h, _ptr(x), _ptr(out),
                                   _lib.FFT_INVERSE if inverse else _lib.FFT_FORWARD, batch,
-                                  _stream()))
+                                  _stream(self.device)))
     return out
 
   # -- fused evaluation ---------------------------------------------------------------
@@ -323,10 +347,12 @@ class Plan:
     self._chk(w_re, self.sphere_shape, torch.float64, 'w_re')
     self._chk(w_im, self.sphere_shape, torch.float64, 'w_im')
     self._chk(occ, (self.ns, self.nk, self.nb), torch.float64, 'occupation')
-    rho = self._new((self.ns, self.nx, self.ny, self.nz), torch.float64) if rho is None else rho
-    e_kin = self._new((1,), torch.float64) if e_kin is None else e_kin
+    rho = self._new(self.grid_shape, torch.float64) if rho is None else self._chk(
+      rho, self.grid_shape, torch.float64, 'rho')
+    e_kin = self._new((1,), torch.float64) if e_kin is None else self._chk(
+      e_kin, (1,), torch.float64, 'e_kin')
     _lib.check(self.lib.jrb_eval_begin(self._h, _ptr(w_re), _ptr(w_im), _ptr(occ), _ptr(rho),
-                                       _ptr(e_kin), _stream()))
+                                       _ptr(e_kin), _stream(self.device)))
     return rho, e_kin
 
   def eval_finish(self, occ, rho, e_kin, xc: str = 'lda_x', want_occ_grad: bool = False,
@@ -335,16 +361,17 @@ class Plan:
       raise RuntimeError('call set_atoms(positions, charges) first')
     if xc not in _lib.XC_IDS:
       raise NotImplementedError(f'xc "{xc}" is not implemented (implemented: {list(_lib.XC_IDS)})')
-    if out is None:
-      energies = self._new((4,), torch.float64)
-      g_re = self._new(self.sphere_shape, torch.float64)
-      g_im = self._new(self.sphere_shape, torch.float64)
-    else:
-      energies, g_re, g_im = out
-    g_occ = self._new((self.ns, self.nk, self.nb), torch.float64) if want_occ_grad else None
+    # occ must be THIS plan's k-shard (ns, nk_local, nb), not the global occupation array
+    self._chk(occ, self.band_shape, torch.float64, 'occupation')
+    self._chk(rho, self.grid_shape, torch.float64, 'rho')
+    self._chk(e_kin, (1,), torch.float64, 'e_kin')
+    energies, g_re, g_im = self._out(out, [((4,), torch.float64, 'energies'),
+                                           (self.sphere_shape, torch.float64, 'g_re'),
+                                           (self.sphere_shape, torch.float64, 'g_im')])
+    g_occ = self._new(self.band_shape, torch.float64) if want_occ_grad else None
     _lib.check(self.lib.jrb_eval_finish(self._h, _ptr(occ), _ptr(rho), _ptr(e_kin),
                                         _lib.XC_IDS[xc], _ptr(energies), _ptr(g_re), _ptr(g_im),
-                                        _ptr(g_occ), _stream()))
+                                        _ptr(g_occ), _stream(self.device)))
     return energies, g_re, g_im, g_occ
 
   def energy_grad_host(self, w_re, w_im, occ, xc: str = 'lda_x', out=None, want_rho=False):
@@ -409,34 +436,67 @@ class RowsPlan:
   def _new(self, shape, dtype):
     return torch.empty(shape, dtype=dtype, device=self.tdev)
 
+  def _chk(self, t, shape, dtype, name):
+    return _check_tensor(t, shape, dtype, name, self.device)
+
+  def _rows_in(self, w_re, w_im, needed: bool):
+    # pass 1 reads the Q1 of pass 0 from plan work space and ignores w_re / w_im
+    if needed or w_re is not None:
+      self._chk(w_re, self.rows_shape, torch.float64, 'w_re')
+    if needed or w_im is not None:
+      self._chk(w_im, self.rows_shape, torch.float64, 'w_im')
+
   def gram(self, w_re, w_im, pass_: int, out=None):
-    s = self._new(self.small_shape, torch.complex128) if out is None else out
+    if pass_ not in (0, 1):
+      raise ValueError('pass_ must be 0 or 1')
+    self._rows_in(w_re, w_im, pass_ == 0)
+    s = self._new(self.small_shape, torch.complex128) if out is None else self._chk(
+      out, self.small_shape, torch.complex128, 'out')
     _lib.check(self.lib.jrb_qr_rows_gram(self._h, _ptr(w_re), _ptr(w_im), int(pass_), _ptr(s),
-                                         _stream()))
+                                         _stream(self.device)))
     return s
 
   def apply(self, w_re, w_im, pass_: int, s, q=None, r=None):
+    if pass_ not in (0, 1):
+      raise ValueError('pass_ must be 0 or 1')
+    self._rows_in(w_re, w_im, pass_ == 0)
+    self._chk(s, self.small_shape, torch.complex128, 's')
     if pass_ == 1:
       q = self._new(self.rows_shape, torch.complex128) if q is None else q
       r = self._new(self.small_shape, torch.complex128) if r is None else r
+    if q is not None:
+      self._chk(q, self.rows_shape, torch.complex128, 'q')
+    if r is not None:
+      self._chk(r, self.small_shape, torch.complex128, 'r')
     _lib.check(self.lib.jrb_qr_rows_apply(self._h, _ptr(w_re), _ptr(w_im), int(pass_), _ptr(s),
-                                          _ptr(q), _ptr(r), _stream()))
+                                          _ptr(q), _ptr(r), _stream(self.device)))
     return q, r
 
   def bwd_gram(self, q, gq, out=None):
-    m = self._new(self.small_shape, torch.complex128) if out is None else out
-    _lib.check(self.lib.jrb_qr_rows_bwd_gram(self._h, _ptr(q), _ptr(gq), _ptr(m), _stream()))
+    self._chk(q, self.rows_shape, torch.complex128, 'q')
+    self._chk(gq, self.rows_shape, torch.complex128, 'gq')
+    m = self._new(self.small_shape, torch.complex128) if out is None else self._chk(
+      out, self.small_shape, torch.complex128, 'out')
+    _lib.check(self.lib.jrb_qr_rows_bwd_gram(self._h, _ptr(q), _ptr(gq), _ptr(m),
+                                             _stream(self.device)))
     return m
 
   def bwd_apply(self, q, gq, occ, m, out=None):
+    self._chk(q, self.rows_shape, torch.complex128, 'q')
+    self._chk(gq, self.rows_shape, torch.complex128, 'gq')
+    if occ is not None:
+      self._chk(occ, (self.ns, self.nk, self.nb), torch.float64, 'occupation')
+    self._chk(m, self.small_shape, torch.complex128, 'm')
     if out is None:
       g_re = self._new(self.rows_shape, torch.float64)
       g_im = self._new(self.rows_shape, torch.float64)
     else:
       g_re, g_im = out
+      self._chk(g_re, self.rows_shape, torch.float64, 'out.g_re')
+      self._chk(g_im, self.rows_shape, torch.float64, 'out.g_im')
     _lib.check(self.lib.jrb_qr_rows_bwd_apply(self._h, _ptr(q), _ptr(gq), _ptr(occ), _ptr(m),
-                                              _ptr(g_re), _ptr(g_im), _stream()))
+                                              _ptr(g_re), _ptr(g_im), _stream(self.device)))
     return g_re, g_im
 
   def check_status(self):
-    _lib.check(self.lib.jrb_check_status(self._h, _stream()))
+    _lib.check(self.lib.jrb_check_status(self._h, _stream(self.device)))

@@ -86,9 +86,10 @@ def density_grid(coeff, vol: float, occupation: Optional[torch.Tensor] = None) -
   c = _as_coeff(coeff)
   _check_vol(c.plan, vol)
   if occupation is None:
-    raise NotImplementedError(
-      'density_grid without occupation returns M*N per-orbital densities; use '
-      'abs(wave_grid(coeff, vol))**2 for that diagnostic')
+    # pw.py:273-284: without occupation the reference returns the per-orbital densities
+    # |psi_skb(r)|^2, shape (spin, kpt, band, x, y, z) -- the dense diagnostic, M*N numbers
+    psi = torch.view_as_real(c.plan.wave_grid(c.q))
+    return psi[..., 0] ** 2 + psi[..., 1] ** 2
   p = c.plan
   occ = _occ(p, occupation)
   return p.density(c.q, occ)
@@ -97,7 +98,10 @@ def density_grid(coeff, vol: float, occupation: Optional[torch.Tensor] = None) -
 def density_grid_reciprocal(coeff, vol: float, occupation=None) -> torch.Tensor:
   """jrystal/_src/pw.py:287-334: fftn(density_grid)."""
   c = _as_coeff(coeff)
-  return c.plan.density_reciprocal(density_grid(c, vol, occupation))
+  dens = density_grid(c, vol, occupation)
+  if occupation is None:  # per-orbital: batched dense transform over (spin, kpt, band)
+    return c.plan.fft3d(torch.complex(dens, torch.zeros_like(dens)), inverse=False)
+  return c.plan.density_reciprocal(dens)
 
 
 def _occ(plan, occupation):

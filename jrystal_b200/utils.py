@@ -66,7 +66,11 @@ def wave_to_density(wave_grid, occupation=None):
 
 def wave_to_density_reciprocal(wave_grid, occupation=None):
   """utils.py:200-224: fftn of wave_to_density over the last three axes."""
-  return torch.fft.fftn(wave_to_density(wave_grid, occupation).to(torch.complex128), dim=(-3, -2, -1))
+  dens = wave_to_density(wave_grid, occupation)
+  plan = current_plan()
+  if not dens.is_cuda:
+    dens = dens.to(plan.tdev)
+  return plan.fft3d(torch.complex(dens, torch.zeros_like(dens)).contiguous(), inverse=False)
 
 
 def _check_mask(plan, mask):

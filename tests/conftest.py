@@ -12,20 +12,6 @@ def pytest_configure(config):
   config.addinivalue_line('markers', 'gpu: needs a CUDA device (run on the B200 box)')
 
 
-# GPU tests written after this round's GPU budget was spent: their bodies are verified on the CPU
-# stand-in only.  They are ordered after the hardware-verified suite so that `pytest -x` cannot
-# hide it behind a first failure among them.  Drop a file from this list once it has passed on a B200.
-NOT_YET_RUN_ON_HARDWARE = ['test_reference_golden.py', 'test_autograd.py',
-                           'test_pseudopotential.py', 'test_drivers_host.py', 'test_utils_api.py']
-
-
-def pytest_collection_modifyitems(config, items):
-  def rank(item):
-    name = item.fspath.basename
-    return NOT_YET_RUN_ON_HARDWARE.index(name) + 1 if name in NOT_YET_RUN_ON_HARDWARE else 0
-  items.sort(key=rank)  # stable: keeps the collection order inside each group
-
-
 @pytest.fixture(scope='session')
 def cuda_device():
   import torch

@@ -325,3 +325,44 @@ def test_gloo_world2_row_band_sharded_evaluation(tmp_path):
     assert np.abs(d['g_im'] - ref['g_im'][:, :, g0:g1]).max() < 1e-9 * scale
     assert int(d['b1']) - int(d['b0']) in (3, 4)
   assert rows == s.num_g
+
+
+def test_create_crystal_checks_the_spin_number_and_prefers_the_builtin_name(tmp_path):
+  """opt_utils.py:105-114 of the reference: check_spin_number on the created crystal (the default
+  `spin: 0` with the 13 electrons of al_primitive must raise, not drop an electron) and a built-in
+  `crystal` name wins over `crystal_file_path_path`."""
+  from jrystal_b200.calc.opt_utils import create_crystal, create_optimizer
+  from jrystal_b200.config import get_config
+  with pytest.raises(ValueError):
+    create_crystal(get_config(crystal='al_primitive', spin=0))
+  assert create_crystal(get_config(crystal='al_primitive', spin=1)).num_electron == 13
+  c = create_crystal(get_config(crystal='si', crystal_file_path_path=str(tmp_path / 'missing.xyz'), spin=0))
+  assert c.num_electron == 28
+
+
+def test_ground_state_file_rejects_other_settings(tmp_path):
+  """ground_state_io.load compares every setting the density depends on (cut-off, mask method,
+  k-mesh, occupation scheme, smearing, spin) and refuses the k-block of a sharded run."""
+  import torch
+  from jrystal_b200.calc import ground_state_io
+  from jrystal_b200.calc.calc_ground_state_energy_all_electrons import GroundStateEnergyOutput
+  from jrystal_b200.calc.opt_utils import create_crystal
+  from jrystal_b200.config import get_config
+  cfg = get_config(crystal='diamond', grid_sizes=8, k_grid_sizes=[1, 1, 2], cutoff_energy=10.0,
+                   save_dir=str(tmp_path))
+  out = GroundStateEnergyOutput(
+    config=cfg, crystal=create_crystal(cfg),
+    params_pw={'w_re': torch.zeros(1, 2, 5, 3), 'w_im': torch.zeros(1, 2, 5, 3)},
+    occupation=torch.zeros(1, 2, 3), density=torch.zeros(1, 8, 8, 8), total_energy=-1.0,
+    energies={'kinetic': 1.0}, total_energy_history=[-1.0], converged=True, steps=1,
+    seconds_per_step=0.0, k_range=(0, 2))
+  path = ground_state_io.save(out, str(tmp_path))
+  assert ground_state_io.load(path, cfg).total_energy == -1.0
+  for key, val in [('cutoff_energy', 12.0), ('k_grid_sizes', [1, 1, 1]), ('occupation', 'gamma'),
+                   ('freq_mask_method', 'cubic'), ('smearing', 0.01), ('spin_restricted', False)]:
+    with pytest.raises(ValueError):
+      ground_state_io.load(path, get_config(**{**dict(cfg), key: val}))
+  out.k_range = (0, 1)
+  path = ground_state_io.save(out, str(tmp_path / 'shard'))
+  with pytest.raises(ValueError):
+    ground_state_io.load(path, cfg)

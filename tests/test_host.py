@@ -259,6 +259,16 @@ def test_trainable_occupations_match_the_literal_restatement():
     assert abs(float(a.sum()) - m) < 1e-12 and float(a.min()) >= 0 and float(a.max()) <= 1
     # projecting a feasible point changes nothing
     assert float((occ._capped_simplex(a, float(m)) - a).abs().max()) < 1e-14
+  # edges without an index in the sort/cumsum rule: an empty channel and a completely filled one
+  # (simplex-projector with empty_bands = 0; num_electrons == spin)
+  x = torch.rand(6, dtype=torch.float64, generator=g)
+  assert float(occ._capped_simplex(x, 0.0).abs().max()) == 0.0
+  assert float((occ._capped_simplex(x, 6.0) - 1.0).abs().max()) == 0.0
+  full = occ.simplex_projector({k: v.detach().cpu() for k, v in occ.simplex_projector_init(4, 2).items()}, 8)
+  assert float((full - 2.0 / 2).abs().max()) == 0.0          # every band full, 2 / nk each
+  one = occ.simplex_projector({k: v.detach().cpu() for k, v in occ.simplex_projector_init(3, 1).items()},
+                              1, spin=1, spin_restricted=False)
+  assert float(one[1].abs().max()) == 0.0 and abs(float(one[0].sum()) - 1.0) < 1e-14
   nk, nb, ne = 3, 6, 8
   p = {k: v.detach().cpu().requires_grad_(True) for k, v in occ.simplex_projector_init(nb, nk).items()}
   o = occ.simplex_projector(p, ne)

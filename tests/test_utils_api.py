@@ -82,6 +82,14 @@ def test_utils_on_the_current_plan(backend):
     assert relerr(rho_g.cpu().numpy(), jb.pw.density_grid_reciprocal(coeff, s.vol, dev(occ)).cpu().numpy()) < 1e-12
     with pytest.raises(ValueError):
       jb.utils.wave_to_density(psi, dev(occ)[:, :, :-1])
+    # pw.py:273-284: without occupation density_grid returns the per-orbital densities
+    per = jb.pw.density_grid(coeff, s.vol)
+    assert tuple(per.shape) == tuple(psi.shape) and not per.is_complex()
+    assert relerr(per.cpu().numpy(), np.abs(psi.cpu().numpy()) ** 2) < 1e-13
+    assert relerr((per.cpu().numpy() * occ[..., None, None, None]).sum((1, 2)),
+                  rho_fused.cpu().numpy()) < 1e-12
+    per_g = jb.pw.density_grid_reciprocal(coeff, s.vol)
+    assert relerr(per_g.cpu().numpy(), np.fft.fftn(per.cpu().numpy(), axes=(-3, -2, -1))) < 1e-12
   ref = rp.density_grid(rp.expand_coefficient(torch.from_numpy(q), s.mask), s.vol, torch.from_numpy(occ))
   assert relerr(rho.cpu().numpy(), ref.numpy()) < 1e-10
 
