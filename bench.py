@@ -11,8 +11,11 @@ Inputs are synthetic (U[0,1) parameters from numpy default_rng(123), uniform occ
 Multi-GPU: one process per GPU (torchrun), k-points sharded over ranks, partial densities
 all-reduced with NCCL; total work is fixed => "strong" scaling.
 
-Prints ONE JSON line (rank 0).  `--impl reference` times the CPU restatement of the
-reference (oracle/, torch FP64, all host cores) on a bounded sample of the same workload.
+Prints ONE JSON line (rank 0).  The default run (no --config) measures C2, the configuration
+BASELINE.json's metric is quoted on, and appends the two diamond-64 configurations of the same
+metric (C3b, C3a) under the key "diamond64", so that the driver's 1/2/4/8-GPU runs carry both
+systems the metric names.  `--impl reference` times the CPU restatement of the reference
+(oracle/, torch FP64, all host cores): for C2 all 64 k-points, nothing extrapolated.
 """
 import argparse
 import json
@@ -198,6 +201,64 @@ def measured_peak():
   return 6650.0, 'fallback (B200_PROFILING.md)'
 
 
+# FP64 ceiling of one B200: DFMA and DMMA share one datapath, their times add (measured with
+# tools/fp64_dmma_dfma_mix.cu on this pool's B200s, profiles/r01_fp64_dmma_dfma_mix.txt:
+# DFMA alone 32.2-33.0, DMMA alone 36.8-37.0, mixed 35.1-35.5 TFLOP/s)
+FP64_PEAK_TFLOPS = 35.0
+FP64_PEAK_SOURCE = ('measured: tools/fp64_dmma_dfma_mix.cu, profiles/r01_fp64_dmma_dfma_mix.txt '
+                    '(DFMA + DMMA mixed on one datapath, 35.1-35.5 TFLOP/s)')
+
+
+def fp64_flops(mask, orbital_grid, num_orbitals, num_sk, ng, nb):
+  """FP64 flops of one evaluation as the kernels execute it, counted with the nominal
+  5 n log2 n per length-n line on the PRUNED passes of the orbital box (z passes on the occupied
+  (x, y) columns only, y passes on the occupied x planes only): per orbital 2 z passes (scatter
+  side of the density sweep, gather side of the H-apply; the H-apply reuses the z-transformed
+  columns), 3 y and 3 x passes (density; H-apply inverse and forward).  QR products: 8 ng nb^2 per
+  full complex tall-skinny product; Hermitian Gram, upper-triangle-only Gram and triangular
+  factors charged one half: 2 x 1/2 (Gram) + 2 x 1/2 (apply, triangular R^-1) forward,
+  1/2 (upper triangle of Q^H G) + 1/2 + 1 (two-term apply) backward = 4 products per (spin, k)."""
+  nxw, nyw, nzw = (int(v) for v in orbital_grid)
+  ncol = int(np.asarray(mask).any(axis=2).sum())
+  nxo = int(np.asarray(mask).any(axis=(1, 2)).sum())
+  line = lambda n: 5.0 * n * np.log2(n)
+  per_orbital = (2 * ncol * line(nzw) + 3 * nxo * nzw * line(nyw) + 3 * nyw * nzw * line(nxw))
+  fft = per_orbital * num_orbitals
+  qr = 4.0 * 8.0 * ng * nb * nb * num_sk
+  return fft, qr
+
+
+def kernels_stamp():
+  """sha256 over the CUDA sources the library is built from: profiles/traffic.json carries the
+  stamp of the sources its ncu capture was made with and is refused when they have changed."""
+  import hashlib
+  h = hashlib.sha256()
+  d = os.path.join(ROOT, 'jrystal_b200', 'csrc')
+  for name in sorted(os.listdir(d)):
+    if name.endswith(('.cu', '.cuh', '.h')):
+      h.update(name.encode())
+      h.update(open(os.path.join(d, name), 'rb').read())
+  return h.hexdigest()[:16]
+
+
+def measured_traffic(config, world):
+  """(bytes per evaluation of the H-apply sweep, note): dram__bytes_read + dram__bytes_write from
+  the ncu --set full capture committed as profiles/traffic.json (tools/capture_traffic.py writes
+  it from the capture of `bench.py --config C`), only if it was taken with these kernel sources."""
+  try:
+    prof = json.load(open(os.path.join(ROOT, 'profiles', 'traffic.json')))
+  except Exception as e:
+    return None, f'profiles/traffic.json unreadable: {e}'
+  ent = prof.get(config)
+  if not ent or world != 1:
+    return None, 'no capture for this configuration / GPU count'
+  stamp = kernels_stamp()
+  if ent.get('kernels_sha') != stamp:
+    return None, (f'capture refused: made with kernel sources {ent.get("kernels_sha")}, the '
+                  f'library is built from {stamp} (re-run tools/gpu_capture_traffic.sh)')
+  return ent['happly_dram_bytes_per_eval'], f'ncu capture {ent.get("source")} (kernels {stamp})'
+
+
 def cpu_sample_eval(wl, nk_sample, steps, warmup):
   """Oracle (CPU restatement of the reference dataflow) on `nk_sample` k-points of the
   workload, all host threads.  Returns (eval/s scaled to the full workload, seconds/sample)."""
@@ -231,6 +292,34 @@ def cpu_sample_eval(wl, nk_sample, steps, warmup):
   return 1.0 / (t * nk / nk_sample), t, cores, nk_sample
 
 
+GRADIENT_PIN = ('energies / density / Q pinned by the reference source executed over a numpy stand-in '
+                '(tests/golden/reference_*.npz); gradients have no reference-derived pin (no AD in '
+                'the stand-in): torch-autograd oracle + finite differences + oracle/analytic.py')
+
+
+def cpu_full_eval(wl, kblock):
+  """Oracle evaluation of the WHOLE workload on the host cores with bounded memory: the k-points
+  couple only through rho, so (1) rho and E_kin are accumulated over k-blocks, (2) the grid
+  energies and v = dE/drho come from the total rho, (3) the gradients of every k-block are
+  those of E_kin + <v, rho_block> -- reference_port.energy_and_grad_chunked run per k-block.
+  Returns (eval/s, seconds, cores, nk)."""
+  import torch
+  from oracle import reference_port as rp
+  cores = os.cpu_count() or 1
+  torch.set_num_threads(cores)
+  c = wl['crystal']
+  nk = wl['kpts'].shape[0]
+  s = rp.System(c.cell_vectors, c.positions, c.charges, wl['grid'], kpts=wl['kpts'],
+                cutoff_energy=None, mask_method='cubic')
+  s.mask = wl['mask']
+  s.num_g = wl['ng']
+  w_re, w_im = synthetic_params(wl['ng'], nk, wl['nb'], 0, nk)
+  t0 = time.perf_counter()
+  rp.energy_and_grad_kblocks(s, w_re, w_im, wl['occ'], kblock=kblock)
+  t = time.perf_counter() - t0
+  return 1.0 / t, t, cores, nk
+
+
 def run_reference(args):
   rank = int(os.environ.get('RANK', '0'))
   if rank != 0:
@@ -243,16 +332,27 @@ def run_reference(args):
     sample = (f'{nks} of {nk} path points x {wl["nb"]} bands at {wl["grid"]} per step, one after '
               f'the other; oracle port (torch FP64 autograd), {cores} threads')
   else:
-    nk_sample = {'C1': 8, 'C2': 8, 'C3a': 1, 'C3b': 1, 'C4': 8}[args.config]
-    value, t, cores, nks = cpu_sample_eval(wl, nk_sample, steps, min(args.warmup, 1))
-    sample = (f'{nks} of {nk} k-points x {wl["nb"]} bands at {wl["grid"]} per step, time scaled '
-              f'by {nk / nks:g}; oracle port (torch FP64 autograd), {cores} threads')
+    # C2 (the headline): every one of the 64 k-points, in k-blocks of 8 (the dense (k, band, x, y, z)
+    # tensor of all 64 would need 17.7 GB per copy) -- nothing extrapolated, one step = 25-30 s
+    nk_sample = {'C1': 8, 'C2': nk, 'C3a': 1, 'C3b': 1, 'C4': 8}[args.config]
+    if args.config == 'C2':
+      steps = 1
+      value, t, cores, nks = cpu_full_eval(wl, 8)
+      sample = (f'all {nk} k-points x {wl["nb"]} bands at {wl["grid"]}, one step of {t:.1f} s in '
+                f'k-blocks of 8 (density pass, grid potential, gradient pass); nothing scaled; '
+                f'oracle port (torch FP64 autograd), {cores} threads')
+    else:
+      value, t, cores, nks = cpu_sample_eval(wl, nk_sample, steps, min(args.warmup, 1))
+      sample = (f'{nks} of {nk} k-points x {wl["nb"]} bands at {wl["grid"]} per step, time scaled '
+                f'by {nk / nks:g}; oracle port (torch FP64 autograd), {cores} threads')
   line = {
     'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': args.gpus,
-    'steps': steps, 'warmup': min(args.warmup, 1), 'ms_per_step': 1e3 / value,
+    'steps': steps, 'warmup': 0 if args.config == 'C2' else min(args.warmup, 1),
+    'ms_per_step': 1e3 / value,
     'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None, 'dtype': 'f64',
     'data': 'synthetic',
-    'config': {'workload': wl['text'], 'note': 'CPU restatement of the reference (JAX absent)'},
+    'config': {'workload': wl['text'], 'note': 'CPU restatement of the reference (JAX absent)',
+               'gradient_pin': GRADIENT_PIN},
     'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': cores, 'kind': 'port',
                      'sample': sample},
     'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
@@ -261,9 +361,9 @@ def run_reference(args):
   emit(line)
 
 
-def run_b200_rows(args, wl, world, rank, local_rank):
+def run_b200_rows(args, wl, world, rank, local_rank, steps=None):
   """Fewer k-points than GPUs (C3a, Gamma only): rows of the parameters sharded for the QR, bands
-  for the FFTs (jrystal_b200.parallel.RowShardedEvaluator); strong scaling."""
+  for the FFTs (jrystal_b200.parallel.RowShardedEvaluator); strong scaling.  Returns the line."""
   import torch
   import torch.distributed as dist
   from jrystal_b200 import _lib
@@ -302,14 +402,15 @@ def run_b200_rows(args, wl, world, rank, local_rank):
     return float(ms.item())
 
   lib = _lib.load()
+  steps = steps or args.steps
   for _ in range(max(args.warmup, 3)):
     step()
   barrier()
   launches0 = lib.jrb_launch_count()
   with ClockSampler(local_rank, enabled=(rank == 0)) as clk:
-    total_ms = timed(step, args.steps)
+    total_ms = timed(step, steps)
   launches = int(lib.jrb_launch_count() - launches0)
-  ms_per_step = total_ms / args.steps
+  ms_per_step = total_ms / steps
   value = 1e3 / ms_per_step
   energies = result['out'][0].cpu().numpy().tolist()
 
@@ -330,7 +431,7 @@ def run_b200_rows(args, wl, world, rank, local_rank):
     g_im_p.copy_(g_im, non_blocking=True)
     torch.cuda.current_stream().synchronize()
 
-  e2e_steps = max(1, min(args.steps, 5))
+  e2e_steps = max(1, min(steps, 5))
   e2e_step()
   barrier()
   t0 = time.perf_counter()
@@ -345,13 +446,17 @@ def run_b200_rows(args, wl, world, rank, local_rank):
   m_local = nk * (ev.b1 - ev.b0)
   bytes_alg = 64.0 * nk * nb * (ngrid + ng) / world  # per GPU share of the whole evaluation
   whole_achieved = bytes_alg / (ms_per_step * 1e-3) / 1e9
+  fft_fl, qr_fl = fp64_flops(wl['mask'], ev.bands.orbital_grid, nk * nb, nk, ng, nb)
+  fp64_tf = (fft_fl + qr_fl) / world / (ms_per_step * 1e-3) / 1e12
+  line = None
   if rank == 0:
     line = {
-      'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
+      'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': steps,
       'warmup': max(args.warmup, 3), 'ms_per_step': ms_per_step, 'higher_is_better': True,
       'scaling': 'strong', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
       'config': {'workload': wl['text'], 'orbitals': nk * nb, 'ng': ng, 'grid': wl['grid'],
                  'sharding': f'rows{world} (QR) + bands{world} (FFT), all-to-all between',
+                 'reduce_path': ev.reduce_path,
                  'xc': 'lda_x', 'bands_per_rank': ev.b1 - ev.b0, 'rows_per_rank': ev.g1 - ev.g0,
                  'orbital_grid': list(ev.bands.orbital_grid),
                  'l2': 'working set larger than L2 (pencil work space); no flush'},
@@ -362,11 +467,15 @@ def run_b200_rows(args, wl, world, rank, local_rank):
       'roofline': {'bound': 'hbm', 'achieved': whole_achieved, 'peak': peak, 'unit': 'GB/s',
                    'frac': whole_achieved / peak, 'traffic': None, 'peak_source': peak_src,
                    'kernel': 'whole evaluation per GPU (64*M*(N+ng)/n_gpus algorithmic bytes)',
-                   'orbitals_per_gpu': m_local},
+                   'orbitals_per_gpu': m_local,
+                   'fp64': {'flops_per_eval': fft_fl + qr_fl, 'achieved': fp64_tf,
+                            'peak': FP64_PEAK_TFLOPS, 'unit': 'TFLOP/s',
+                            'frac': fp64_tf / FP64_PEAK_TFLOPS, 'peak_source': FP64_PEAK_SOURCE}},
       'clocks': clk.summary(), 'energies_ha': energies,
     }
-    emit(line)
-  dist.destroy_process_group()
+  del ev, w_re, w_im, occ, result
+  torch.cuda.empty_cache()
+  return line
 
 
 def cpu_sample_band(wl, nk_sample, steps, warmup):
@@ -533,9 +642,8 @@ def run_b200_band(args, wl, world, rank, local_rank):
         'value': v, 'unit': UNIT, 'cores': cores, 'kind': 'port',
         'sample': f'{nks} of {nk} path points x {nb} bands ({t:.2f} s), one after the other; '
                   'oracle port (torch FP64 autograd)'}
-    emit(line)
-  if world > 1:
-    dist.destroy_process_group()
+    return line
+  return None
 
 
 def parse_orbital_grid(text):
@@ -547,8 +655,6 @@ def parse_orbital_grid(text):
 def run_b200(args):
   import torch
   import torch.distributed as dist
-  import jrystal_b200 as jb
-  from jrystal_b200 import _lib, parallel
 
   world = int(os.environ.get('WORLD_SIZE', '1'))
   rank = int(os.environ.get('RANK', '0'))
@@ -559,25 +665,62 @@ def run_b200(args):
   torch.cuda.set_device(local_rank)
   if world > 1:
     dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
+  try:
+    # no --config: the headline configuration C2 in full, then the diamond-64 configurations of the
+    # same metric (BASELINE.json: "Si8, diamond64 at 1/2/4/8") as extra objects of the same line
+    name = args.config or 'C2'
+    line = measure(args, name, world, rank, local_rank, full=True)
+    if args.config is None and not args.emulate_ranks > 1:
+      extra = {}
+      for other in ('C3b', 'C3a'):
+        sub = measure(args, other, world, rank, local_rank, full=False,
+                      steps=max(3, min(args.steps, 10)))
+        if sub is not None:
+          extra[other] = sub
+      if line is not None:
+        line['diamond64'] = extra
+    if rank == 0 and line is not None:
+      emit(line)
+  finally:
+    if world > 1:
+      dist.destroy_process_group()
 
-  wl = build_workload(args.config)
-  c = wl['crystal']
-  nk, nb, ng = wl['kpts'].shape[0], wl['nb'], wl['ng']
-  ngrid = int(np.prod(wl['grid']))
+
+def measure(args, name, world, rank, local_rank, full=True, steps=None):
+  """One workload on this job's GPUs; returns the JSON object (rank 0) or None."""
+  wl = build_workload(name)
+  nk = wl['kpts'].shape[0]
   if wl['band_mode']:
     return run_b200_band(args, wl, world, rank, local_rank)
   if nk % world != 0:
-    return run_b200_rows(args, wl, world, rank, local_rank)
-  k0, k1 = parallel.shard_kpoints(nk, world, rank)
+    return run_b200_rows(args, wl, world, rank, local_rank, steps=steps)
+  return run_b200_kshard(args, name, wl, world, rank, local_rank, full, steps)
+
+
+def run_b200_kshard(args, name, wl, world, rank, local_rank, full, steps=None):
+  """Whole k-points per rank (the reference's k-mesh layout); world == 1 is the single-GPU run."""
+  import torch
+  import torch.distributed as dist
+  from jrystal_b200 import _lib, parallel
+
+  steps = steps or args.steps
+  c = wl['crystal']
+  nk, nb, ng = wl['kpts'].shape[0], wl['nb'], wl['ng']
+  ngrid = int(np.prod(wl['grid']))
   b0, b1 = 0, nb
+  kpts = wl['kpts']
   sharding = f'k{world}' if world > 1 else 'none'
-  if args.emulate_ranks > 1 and world == 1:
+  emulated = args.emulate_ranks > 1 and world == 1
+  if emulated:
     # tuning aid, NOT a bench line: the per-rank workload of an N-GPU k-sharded run on one GPU
-    k0, k1 = parallel.shard_kpoints(nk, args.emulate_ranks, 0)
+    e0, e1 = parallel.shard_kpoints(nk, args.emulate_ranks, 0)
+    kpts = kpts[e0:e1]
     sharding = f'EMULATED rank 0 of k{args.emulate_ranks} (no collectives; not a benchmark value)'
-  plan = jb.Plan(c.cell_vectors, wl['mask'], wl['kpts'][k0:k1], nb, device=local_rank,
-                 orbital_grid=parse_orbital_grid(args.orbital_grid))
-  plan.set_atoms(c.positions, c.charges)
+  ev = parallel.KShardedEvaluator(c.cell_vectors, wl['mask'], kpts, nb, c.positions, c.charges,
+                                  device=local_rank,
+                                  orbital_grid=parse_orbital_grid(args.orbital_grid))
+  plan = ev.plan
+  k0, k1 = ev.k0, ev.k1
   if wl['nproj']:
     plan.set_nonlocal(synthetic_projectors(ng, nk, wl['nproj'], k0, k1, 'cuda'))
   w_re_h, w_im_h = synthetic_params(ng, nk, nb, k0, k1)
@@ -585,25 +728,24 @@ def run_b200(args):
   w_re = torch.from_numpy(w_re_h).cuda()
   w_im = torch.from_numpy(w_im_h).cuda()
   occ = torch.from_numpy(occ_h).cuda()
-  dbuf, rho, e_kin = parallel.density_buffers((1,) + tuple(wl['grid']), 'cuda')
   out = (torch.empty(4, dtype=torch.float64, device='cuda'), torch.empty_like(w_re),
          torch.empty_like(w_im))
 
   def step():
-    plan.eval_begin(w_re, w_im, occ, rho, e_kin)
-    parallel.allreduce_density(rho, e_kin, dbuf)
-    plan.eval_finish(occ, rho, e_kin, 'lda_x', out=out)
+    # ONE call of the public API per evaluation: jrb_eval (QR, density sweep, the in-library
+    # all-reduce over NVLink peer memory when world > 1, grid potential, H-apply, QR adjoint)
+    ev.evaluate(w_re, w_im, occ, 'lda_x', out=out)
 
   def barrier():
     if world > 1:
       dist.barrier()
     torch.cuda.synchronize()
 
-  def timed(fn, steps):
+  def timed(fn, n):
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     ev0.record()
-    for _ in range(steps):
+    for _ in range(n):
       fn()
     ev1.record()
     barrier()
@@ -612,14 +754,15 @@ def run_b200(args):
       dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     return float(ms.item())
 
-  # working sets that fit the 126 MB L2 (C1): flush it between timed steps by rewriting a 256 MiB
-  # buffer, and time every step with its own event pair (the flush is outside the timed spans)
+  # working sets that fit the 126 MB L2 (C1; C2 on 8 GPUs): flush it between timed steps by
+  # rewriting a 256 MiB buffer, and time every step with its own event pair (the flush is outside
+  # the timed spans)
   flush_l2 = 2 * w_re_h.size * 8 < 126 * 2**20
   flush_buf = torch.zeros(32 * 2**20, dtype=torch.float64, device='cuda') if flush_l2 else None
 
-  def timed_flushed(fn, steps):
+  def timed_flushed(fn, n):
     evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
-           for _ in range(steps)]
+           for _ in range(n)]
     barrier()
     for e0, e1 in evs:
       flush_buf.add_(1.0)
@@ -636,12 +779,13 @@ def run_b200(args):
   lib = _lib.load()
   for _ in range(max(args.warmup, 3)):
     step()
+  plan.check_status()
   barrier()
   launches0 = lib.jrb_launch_count()
   with ClockSampler(local_rank, enabled=(rank == 0)) as clk:
-    total_ms = (timed_flushed if flush_l2 else timed)(step, args.steps)
+    total_ms = (timed_flushed if flush_l2 else timed)(step, steps)
   launches = int(lib.jrb_launch_count() - launches0)
-  ms_per_step = total_ms / args.steps
+  ms_per_step = total_ms / steps
   value = 1e3 / ms_per_step
   energies = out[0].cpu().numpy().tolist()
 
@@ -654,10 +798,13 @@ def run_b200(args):
   en_p = torch.empty(4, dtype=torch.float64).pin_memory()
   g_re_p = torch.empty(w_re_h.shape, dtype=torch.float64).pin_memory()
   g_im_p = torch.empty(w_re_h.shape, dtype=torch.float64).pin_memory()
-  if world == 1:
+  if ev.reduce_path != 'nccl':
+    # the reference-facing call with HOST buffers: k-chunked copies overlapped with the kernels,
+    # the density all-reduce (world > 1) inside the library
     def e2e_step():
       plan.energy_grad_host(w_re_p, w_im_p, occ_p, 'lda_x', out=(en_p, g_re_p, g_im_p))
-    e2e_path = 'jrb_energy_grad_host (C ABI, pinned host buffers)'
+    e2e_path = 'jrb_energy_grad_host (C ABI, pinned host buffers' + (
+      '; density all-reduce over NVLink peer memory inside)' if world > 1 else ')')
   else:
     def e2e_step():
       w_re.copy_(w_re_p, non_blocking=True)
@@ -669,7 +816,7 @@ def run_b200(args):
       g_im_p.copy_(out[2], non_blocking=True)
       torch.cuda.current_stream().synchronize()
     e2e_path = 'pinned H2D + jrb_eval_begin/NCCL all-reduce/jrb_eval_finish + D2H per rank'
-  e2e_steps = max(1, min(args.steps, 5))
+  e2e_steps = max(1, min(steps, 5))
   e2e_step()
   barrier()
   t0 = time.perf_counter()
@@ -680,6 +827,7 @@ def run_b200(args):
   if world > 1:
     dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
   e2e_value = e2e_steps / float(e2e_s.item())
+  e2e_energy = float(en_p.sum())
 
   # ---- phase split (outside the timed region; explains the number) ----------------------
   # CUDA events on torch's current stream = the stream every kernel of the phase is launched on;
@@ -689,7 +837,7 @@ def run_b200(args):
   q = torch.empty(w_re.shape, dtype=cdt, device='cuda')
   r = torch.empty((1, k1 - k0, nb, nb), dtype=cdt, device='cuda')
   hq = torch.empty_like(q)
-  rho2 = torch.empty_like(rho)
+  rho2 = torch.empty((1,) + tuple(wl['grid']), dtype=torch.float64, device='cuda')
   g_out = (torch.empty_like(w_re), torch.empty_like(w_im))
   plan.qr_fwd(w_re, w_im, out=(q, r))
   plan.density(q, occ, out=rho2)
@@ -704,19 +852,22 @@ def run_b200(args):
     lambda: plan.grid_potential(rho2, 'lda_x', False, out=gp_out), reps) / reps
   phases['hpsi'] = timed(lambda: plan.hpsi(q, veff, out=hq), reps) / reps
   phases['qr_bwd'] = timed(lambda: plan.qr_bwd(q, r, hq, out=g_out), reps) / reps
+  if world > 1 and ev.reduce_path == 'peer':
+    ebuf = torch.zeros(1, dtype=torch.float64, device='cuda')
+    phases['allreduce_rho'] = timed(lambda: plan.allreduce_rho(rho2, ebuf), 10) / 10
   del q, r, hq, rho2, veff, g_out, gp_out
 
   # ---- the caller of the path: one optimisation step of the energy-mode driver (evaluation +
   # device Adam), eager and replayed as a CUDA graph; informational
   driver = None
-  if world == 1:
+  if world == 1 and full:
     from jrystal_b200.optim import Adam
     pw_re, pw_im = w_re.clone(), w_im.clone()
     opt = Adam([pw_re, pw_im])
+    rho_d = torch.empty((1,) + tuple(wl['grid']), dtype=torch.float64, device='cuda')
 
     def opt_step():
-      plan.eval_begin(pw_re, pw_im, occ, rho, e_kin)
-      plan.eval_finish(occ, rho, e_kin, 'lda_x', out=out)
+      plan.eval(pw_re, pw_im, occ, 'lda_x', out=out, rho=rho_d)
       opt.step([out[1], out[2]])
 
     opt_step()
@@ -727,8 +878,8 @@ def run_b200(args):
     graph.replay()
     graph_ms = timed(graph.replay, reps) / reps
     driver = {'eager_steps_per_s': 1e3 / eager_ms, 'graph_steps_per_s': 1e3 / graph_ms,
-              'what': 'jrb_eval_begin + jrb_eval_finish + jrb_adam_tick/apply per step'}
-    del pw_re, pw_im, opt, graph
+              'what': 'jrb_eval + jrb_adam_tick/apply per step'}
+    del pw_re, pw_im, opt, graph, rho_d
 
   # ---- roofline (a dense 3-D transform is charged one read + one write of its box,
   # sphere data its true size), per GPU -------------------------------------------------------
@@ -745,26 +896,32 @@ def run_b200(args):
   whole_achieved = bytes_alg / (ms_per_step * 1e-3) / 1e9
   fft_ms = phases['density'] + phases['hpsi']
   fft_bytes = 64.0 * m_local * ngrid
-  traffic = None
-  try:
-    prof = json.load(open(os.path.join(ROOT, 'profiles', 'traffic.json')))
-    ent = prof.get(args.config)
-    if ent and world == 1:
-      traffic = ent['happly_dram_bytes_per_eval']
-  except Exception:
-    pass
+  traffic, traffic_note = measured_traffic(name, world)
+  # FP64 ceiling: what ncu says binds the path (the sweeps keep psi(r) in shared memory; DRAM runs
+  # at ~10 % of peak, the FP64 pipe at 45-60 %, the shared-memory pipe at 50-65 %)
+  fft_fl, qr_fl = fp64_flops(wl['mask'], plan.orbital_grid, m_local, k1 - k0, ng, nb)
+  fp64_tf = (fft_fl + qr_fl) / (ms_per_step * 1e-3) / 1e12
   roofline = {
-    'bound': 'hbm', 'achieved': happly_achieved, 'peak': peak, 'unit': 'GB/s',
-    'frac': happly_achieved / peak, 'traffic': traffic, 'peak_source': peak_src,
+    'bound': 'fp64', 'achieved': happly_achieved, 'peak': peak, 'unit': 'GB/s',
+    'frac': happly_achieved / peak, 'traffic': traffic, 'traffic_source': traffic_note,
+    'peak_source': peak_src,
+    'bound_note': 'ncu (profiles/): the dominant kernels are bound by FP64 issue + the shared-memory '
+                  'exchange of the line FFTs, not by HBM; achieved/peak/frac keep the HBM-convention '
+                  'contract figure of SURVEY 8d (algorithmic bytes of the reference grid), '
+                  'roofline.fp64 is the fraction of the bounding roof',
     'kernel': 'H-apply sweep (k_yx_vmul + k_z_fwd_gather on the kept z columns; k_yx_vmul is the '
               'dominant kernel)',
     'bytes_per_launch': happly_bytes,
     'bytes_formula': 'M*(32*N + 32*ng): one dense transform (read+write of the box) per orbital '
                      '+ Q read + HQ write, SURVEY 8d',
     'ms_per_launch': phases['hpsi'],
-    'note': 'the sweep keeps psi(r) in shared memory and runs on the alias-free orbital box, so '
-            'it is bound by FP64 issue + the smem exchange (see DESIGN.md); measured DRAM traffic '
-            'is far below the algorithmic bytes of the reference grid',
+    'fp64': {'flops_per_eval': fft_fl + qr_fl, 'fft_flops': fft_fl, 'qr_flops': qr_fl,
+             'achieved': fp64_tf, 'peak': FP64_PEAK_TFLOPS, 'unit': 'TFLOP/s',
+             'frac': fp64_tf / FP64_PEAK_TFLOPS, 'peak_source': FP64_PEAK_SOURCE,
+             'flops_formula': 'pruned line FFTs at 5 n log2 n (2 z + 3 y + 3 x passes per orbital on '
+                              'the orbital box) + 4 x 8 ng nb^2 per (spin, k) for the QR products '
+                              '(Hermitian / triangular halves not charged); whole evaluation over '
+                              'ms_per_step'},
     'whole_evaluation': {'achieved': whole_achieved, 'frac': whole_achieved / peak,
                          'bytes': '64*M*(N+ng)'},
     'fft_density_path': {'ms': fft_ms, 'achieved': fft_bytes / (fft_ms * 1e-3) / 1e9,
@@ -772,39 +929,42 @@ def run_b200(args):
                          'bytes': '64*M*N (two dense 3-D transforms per orbital)'},
   }
 
+  line = None
   if rank == 0:
     line = {
-      'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
+      'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': steps,
       'warmup': max(args.warmup, 3), 'ms_per_step': ms_per_step, 'higher_is_better': True,
       'scaling': 'strong', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
       'config': {'workload': wl['text'], 'orbitals': nk * nb, 'ng': ng, 'grid': wl['grid'],
-                 'sharding': sharding, 'xc': 'lda_x',
+                 'sharding': sharding, 'reduce_path': ev.reduce_path, 'xc': 'lda_x',
                  'orbital_grid': list(plan.orbital_grid),
                  'orbital_grid_note': 'box of the per-orbital FFTs (alias-free, n >= 4 gmax + 1 = '
                                       f'{list(plan.min_orbital_grid)}); rho, potentials and all '
                                       'results live on `grid`',
                  'l2': f'inputs larger than L2 ({2 * nw * 8 / 2**20:.0f} MiB of parameters per '
-                       'GPU); no flush' if 2 * nw * 8 > 126 * 2**20 else
+                       'GPU); no flush' if not flush_l2 else
                        'working set fits L2: L2 flushed between timed steps (256 MiB rewrite), '
                        'per-step CUDA events',
+                 'gradient_pin': GRADIENT_PIN,
                  'batch_groups': int(os.environ.get('JRB_BATCH_GROUPS', 0))},
       'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': h2d,
-              'd2h_bytes_per_step': d2h, 'path': e2e_path},
+              'd2h_bytes_per_step': d2h, 'path': e2e_path,
+              'energy_rel_diff_vs_device_path': abs(e2e_energy - sum(energies)) / abs(sum(energies))},
       'gpu_launches': launches, 'roofline': roofline, 'clocks': clk.summary(),
       'phases_ms': phases, 'driver_step': driver, 'energies_ha': energies,
       'workspace_mib': plan.workspace_bytes / 2**20,
     }
-    if world == 1 and not args.no_cpu:
+    if world == 1 and full and not args.no_cpu and not emulated:
       # bounded sample: ~10-20 s of CPU work
-      nks = {'C1': 8, 'C2': 8, 'C3a': 1, 'C3b': 1, 'C4': 8}[args.config]
-      v, t, cores, nks = cpu_sample_eval(wl, nks, 2 if args.config != 'C1' else 20, 1)
+      nks = {'C1': 8, 'C2': 8, 'C3a': 1, 'C3b': 1, 'C4': 8}[name]
+      v, t, cores, nks = cpu_sample_eval(wl, nks, 2 if name != 'C1' else 20, 1)
       line['cpu_baseline'] = {
         'value': v, 'unit': UNIT, 'cores': cores, 'kind': 'port',
         'sample': f'{nks} of {nk} k-points x {nb} bands ({t:.2f} s), scaled by {nk / nks:g}; '
-                  'oracle port (torch FP64 autograd)'}
-    emit(line)
-  if world > 1:
-    dist.destroy_process_group()
+                  'oracle port (torch FP64 autograd); `--impl reference` runs all k-points'}
+  del ev, plan, w_re, w_im, occ, out, w_re_p, w_im_p, g_re_p, g_im_p
+  torch.cuda.empty_cache()
+  return line
 
 
 def main():
@@ -812,7 +972,8 @@ def main():
   ap.add_argument('--gpus', type=int, default=1)
   ap.add_argument('--steps', type=int, default=10)
   ap.add_argument('--warmup', type=int, default=3)
-  ap.add_argument('--config', default='C2', choices=list(WORKLOADS))
+  ap.add_argument('--config', default=None, choices=list(WORKLOADS),
+                  help='one workload; default: C2 + the diamond-64 configurations C3b, C3a')
   ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
   ap.add_argument('--no-cpu', action='store_true', help='skip the cpu_baseline leg')
   ap.add_argument('--orbital-grid', default=os.environ.get('JRB_ORBITAL_GRID', 'auto'),
@@ -823,6 +984,7 @@ def main():
   args = ap.parse_args()
   _route_stdout_to_stderr()
   if args.impl == 'reference':
+    args.config = args.config or 'C2'
     run_reference(args)
   else:
     run_b200(args)

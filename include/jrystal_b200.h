@@ -261,9 +261,47 @@ int jrb_eval_finish(jrb_plan* plan, const double* occ, const double* rho, const 
                     int32_t xc_id, double* energies, double* g_re, double* g_im, double* g_occ,
                     jrb_stream stream);
 
+/* Multi-GPU (one process per GPU): a plan-owned communicator over NVLink / NVSwitch peer memory
+ * and the ONE collective of the path, the all-reduce of the partial densities.  The reference
+ * shards the k-mesh over devices (calc/calc_ground_state_energy_all_electrons.py:83-91,151-158,
+ * `nk % ndev == 0`, _src/spmd/uniform.py:22-24) and XLA inserts this all-reduce where
+ * einsum('skb...,skb->s...') contracts the sharded k axis (_src/pw.py:278).
+ *   set-up (allocates, synchronises; not on the hot path):
+ *     jrb_comm_create  : allocates this rank's symmetric region (capacity doubles per buffer;
+ *                        0 = enough for the plan's density + E_kin, or for the small matrices of a
+ *                        rows-only plan) and writes its CUDA IPC handle (jrb_comm_handle_bytes()
+ *                        bytes) to handle_out; the caller exchanges the handles of all ranks by
+ *                        any means (torch.distributed, MPI, a file);
+ *     jrb_comm_connect : handles = world x jrb_comm_handle_bytes() bytes in rank order; maps the
+ *                        peers' regions.  world == 1 needs no connect.
+ *   data path (asynchronous on the stream, no host round trip, CUDA-graph capturable; the same
+ *   call order on every rank; every rank ends with BIT-IDENTICAL sums, reduced in rank order):
+ *     jrb_allreduce     : in-place SUM over the ranks of buf[0..n) (device doubles);
+ *     jrb_allreduce_rho : the same for rho (ns, nx, ny, nz) and e_kin[1] (may be NULL) between
+ *                         jrb_eval_begin and jrb_eval_finish.
+ * A peer that never arrives raises an error that jrb_check_status reports (bounded spin). */
+int jrb_comm_handle_bytes(void);
+int jrb_comm_create(jrb_plan* plan, int32_t rank, int32_t world, int64_t capacity, void* handle_out);
+int jrb_comm_connect(jrb_plan* plan, const void* handles);
+int jrb_comm_world(const jrb_plan* plan); /* 1 without a connected communicator */
+int jrb_allreduce(jrb_plan* plan, double* buf, int64_t n, jrb_stream stream);
+int jrb_allreduce_rho(jrb_plan* plan, double* rho, double* e_kin, jrb_stream stream);
+
+/* jrb_eval_begin + the all-reduce + jrb_eval_finish in one call: with a connected communicator the
+ * partial density is reduced INSIDE, on the box the orbitals were transformed on (the orbital
+ * grid: 4x fewer bytes than the 128^3 grid of the diamond-64 configuration), before its Fourier
+ * interpolation onto the plan's grid; without one it is the single-GPU evaluation.  w_re, w_im,
+ * occ, g_re, g_im, g_occ (may be NULL): this rank's k-points; rho (ns, nx, ny, nz) and
+ * energies[4] = E_kin, E_ext, E_har, E_xc: the whole system's, identical on every rank. */
+int jrb_eval(jrb_plan* plan, const double* w_re, const double* w_im, const double* occ,
+             int32_t xc_id, double* energies, double* g_re, double* g_im, double* g_occ,
+             double* rho, jrb_stream stream);
+
 /* Same evaluation through HOST buffers (the reference-facing call a non-CUDA host makes):
- * copies w_re/w_im/occ in, runs begin+finish, copies energies[4], g_re, g_im (and rho_host if
- * non-NULL) back and synchronises.  Single GPU only. */
+ * copies w_re/w_im/occ in (k-point chunks, overlapped with the kernels), runs the evaluation,
+ * copies energies[4], g_re, g_im (and rho_host if non-NULL) back and synchronises.  With a
+ * connected communicator (jrb_comm_connect) every rank passes its own k-points and the partial
+ * densities are all-reduced inside, as in jrb_eval. */
 int jrb_energy_grad_host(jrb_plan* plan, const double* w_re_host, const double* w_im_host,
                          const double* occ_host, int32_t xc_id, double* energies_host,
                          double* g_re_host, double* g_im_host, double* rho_host);

@@ -65,6 +65,13 @@ SYMBOLS = {
   'jrb_fft3d': (ctypes.c_int, [_P, _P, _P, _I32, _I64, _P]),
   'jrb_eval_begin': (ctypes.c_int, [_P, _P, _P, _P, _P, _P, _P]),
   'jrb_eval_finish': (ctypes.c_int, [_P, _P, _P, _P, _I32, _P, _P, _P, _P, _P]),
+  'jrb_eval': (ctypes.c_int, [_P, _P, _P, _P, _I32, _P, _P, _P, _P, _P, _P]),
+  'jrb_comm_handle_bytes': (ctypes.c_int, []),
+  'jrb_comm_create': (ctypes.c_int, [_P, _I32, _I32, _I64, _P]),
+  'jrb_comm_connect': (ctypes.c_int, [_P, _P]),
+  'jrb_comm_world': (ctypes.c_int, [_P]),
+  'jrb_allreduce': (ctypes.c_int, [_P, _P, _I64, _P]),
+  'jrb_allreduce_rho': (ctypes.c_int, [_P, _P, _P, _P]),
   'jrb_energy_grad_host': (ctypes.c_int, [_P, _P, _P, _P, _I32, _P, _P, _P, _P]),
   'jrb_adam_tick': (ctypes.c_int, [_P, ctypes.c_double, ctypes.c_double, _P]),
   'jrb_adam_apply': (ctypes.c_int, [_I64, _P, _P, _P, _P, ctypes.c_double, ctypes.c_double,

@@ -170,6 +170,10 @@ extern "C" int jrb_check_status(jrb_plan* p, jrb_stream st) {
     set_error("Cholesky-QR: Gram matrix not positive definite (rank-deficient parameters)");
     return JRB_EINVAL;
   }
+  if (comm_error(p, S(st))) {
+    set_error("communicator: a peer rank did not arrive within JRB_COMM_TIMEOUT_S (all-reduce over peer memory)");
+    return JRB_ECUDA;
+  }
   return 0;
 }
 
@@ -290,28 +294,42 @@ extern "C" int jrb_fft3d(jrb_plan* p, const double* in, double* out, int32_t dir
   return launch_fft3d_dense(p, C(in), C(out), direction, batch, scale, S(st));
 }
 
+// QR, density sweep, kinetic (+ non-local) energy.  reduce: all-reduce the partial density over the
+// plan's communicator where it is smallest -- on the box the sweep ran on (the orbital grid),
+// before the Fourier interpolation onto the plan's grid -- together with e_kin.
+static int eval_begin_impl(jrb_plan* p, const double* w_re, const double* w_im, const double* occ,
+                           double* rho, double* e_kin, bool reduce, cudaStream_t st) {
+  int rc = 0;
+  JRB_CUDA(cudaMemsetAsync(p->d_scal + 32, 0, sizeof(double), st));  // Cholesky failure flag
+  if ((rc = launch_qr_fwd(p, w_re, w_im, p->d_q, p->d_r, st))) return rc;
+  p->keep_write = 1;
+  rc = launch_density_partial(p, p->d_q, occ, rho, st);
+  p->keep_write = 0;
+  p->keep_filled = rc == 0;
+  if (rc) return rc;
+  if ((rc = launch_kinetic(p, p->d_q, p->d_tkb, st))) return rc;
+  if ((rc = launch_weighted_sum(p, p->d_tkb, occ, (int64_t)p->ns * p->nk * p->nb, e_kin, st)))
+    return rc;
+  if (p->nproj > 0) {  // e_kin carries the sphere-local one-electron terms: kinetic + non-local
+    p->nl_p_valid = 0;
+    if ((rc = launch_nonlocal_project(p, 0, p->ns * p->nk, p->d_q, st))) return rc;
+    if ((rc = launch_nonlocal_energy(p, occ, e_kin, st))) return rc;
+    p->nl_p_valid = 1;  // the H-apply of jrb_eval_finish reuses P
+  }
+  if (reduce && comm_world(p) > 1) {
+    double* part = p->wf ? p->wf->d_rho_w : rho;
+    const long long n = (long long)p->ns * (p->wf ? p->wf->ngrid : p->ngrid);
+    if ((rc = launch_comm_allreduce(p, part, n, e_kin, 1, st))) return rc;
+  }
+  return launch_density_end(p, rho, st);
+}
+
 extern "C" int jrb_eval_begin(jrb_plan* p, const double* w_re, const double* w_im,
                               const double* occ, double* rho, double* e_kin, jrb_stream st) {
   int rc = enter(p);
   if (rc) return rc;
   REQUIRE(w_re && w_im && occ && rho && e_kin, "null array");
-  JRB_CUDA(cudaMemsetAsync(p->d_scal + 32, 0, sizeof(double), S(st)));  // Cholesky failure flag
-  if ((rc = launch_qr_fwd(p, w_re, w_im, p->d_q, p->d_r, S(st)))) return rc;
-  p->keep_write = 1;
-  rc = launch_density(p, p->d_q, occ, rho, S(st));
-  p->keep_write = 0;
-  p->keep_filled = rc == 0;
-  if (rc) return rc;
-  if ((rc = launch_kinetic(p, p->d_q, p->d_tkb, S(st)))) return rc;
-  if ((rc = launch_weighted_sum(p, p->d_tkb, occ, (int64_t)p->ns * p->nk * p->nb, e_kin, S(st))))
-    return rc;
-  if (p->nproj > 0) {  // e_kin carries the sphere-local one-electron terms: kinetic + non-local
-    p->nl_p_valid = 0;
-    if ((rc = launch_nonlocal_project(p, 0, p->ns * p->nk, p->d_q, S(st)))) return rc;
-    if ((rc = launch_nonlocal_energy(p, occ, e_kin, S(st)))) return rc;
-    p->nl_p_valid = 1;  // the H-apply of jrb_eval_finish reuses P
-  }
-  return 0;
+  return eval_begin_impl(p, w_re, w_im, occ, rho, e_kin, false, S(st));
 }
 
 __global__ void k_pack_energies(const double* e_kin, const double* grid_e, double* out) {
@@ -347,6 +365,17 @@ extern "C" int jrb_eval_finish(jrb_plan* p, const double* occ, const double* rho
   return 0;
 }
 
+extern "C" int jrb_eval(jrb_plan* p, const double* w_re, const double* w_im, const double* occ,
+                        int32_t xc_id, double* energies, double* g_re, double* g_im, double* g_occ,
+                        double* rho, jrb_stream st) {
+  int rc = enter(p);
+  if (rc) return rc;
+  REQUIRE(w_re && w_im && occ && energies && g_re && g_im && rho, "null array");
+  double* e_kin = p->d_scal + 40;
+  if ((rc = eval_begin_impl(p, w_re, w_im, occ, rho, e_kin, true, S(st)))) return rc;
+  return jrb_eval_finish(p, occ, rho, e_kin, xc_id, energies, g_re, g_im, g_occ, st);
+}
+
 static int ensure_host_buffers(jrb_plan* p) {
   if (p->d_wre) return 0;
   const size_t nw = (size_t)p->ns * p->nk * p->ng * p->nb;
@@ -373,8 +402,9 @@ static int host_chunks(const jrb_plan* p) {
   if (p->nproj > 0) return 1;  // the chunked pipeline does not carry the non-local energy term
   // chunking pays once a chunk carries tens of MB (measured on B200, C2: 1 chunk 24.8, 4 chunks
   // 35.3, 8 chunks 33.6, 16 chunks 27.3 eval/s end to end); tiny problems stay in one piece
+  // (a k-sharded rank of an 8-GPU C2 run holds 71 MB: two to four chunks still hide most of the copies)
   const double bytes = 16.0 * p->nk * (double)p->ng * p->nb;  // w_re + w_im
-  int n = p->ns == 1 ? (int)std::min(4.0, bytes / (64.0 * 1024 * 1024)) : 1;
+  int n = p->ns == 1 ? (int)std::min(4.0, bytes / (16.0 * 1024 * 1024)) : 1;
   if (const char* env = std::getenv("JRB_HOST_CHUNKS")) n = std::atoi(env);
   if (p->ns != 1) n = 1;
   return std::max(1, std::min(std::min(n, 16), p->nk));
@@ -398,7 +428,7 @@ extern "C" int jrb_energy_grad_host(jrb_plan* p, const double* w_re_h, const dou
     const size_t nw = (size_t)p->ns * p->nk * per_k * sizeof(double);
     JRB_CUDA(cudaMemcpyAsync(p->d_wre, w_re_h, nw, cudaMemcpyHostToDevice, st));
     JRB_CUDA(cudaMemcpyAsync(p->d_wim, w_im_h, nw, cudaMemcpyHostToDevice, st));
-    if ((rc = jrb_eval_begin(p, p->d_wre, p->d_wim, p->d_occ, rho, e_kin, st))) return rc;
+    if ((rc = eval_begin_impl(p, p->d_wre, p->d_wim, p->d_occ, rho, e_kin, true, st))) return rc;
     if ((rc = jrb_eval_finish(p, p->d_occ, rho, e_kin, xc_id, p->d_en, p->d_gre, p->d_gim, nullptr,
                               st)))
       return rc;
@@ -428,8 +458,13 @@ extern "C" int jrb_energy_grad_host(jrb_plan* p, const double* w_re_h, const dou
       if (rc) return rc;
       if ((rc = launch_kinetic_range(p, k0, k1 - k0, p->d_q, p->d_tkb, st))) return rc;
     }
-    if ((rc = launch_density_end(p, rho, st))) return rc;
     if ((rc = launch_weighted_sum(p, p->d_tkb, p->d_occ, (int64_t)p->nk * p->nb, e_kin, st))) return rc;
+    if (comm_world(p) > 1) {  // k-sharded ranks: the one collective, on the box the sweep ran on
+      double* part = p->wf ? p->wf->d_rho_w : rho;
+      const long long n = (long long)p->ns * (p->wf ? p->wf->ngrid : p->ngrid);
+      if ((rc = launch_comm_allreduce(p, part, n, e_kin, 1, st))) return rc;
+    }
+    if ((rc = launch_density_end(p, rho, st))) return rc;
     // backward: D2H of chunk c (copy stream) under H-apply + QR adjoint of chunk c+1
     double* grid_e = p->d_scal;
     p->veff_prepared = 0;

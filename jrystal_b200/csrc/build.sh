@@ -6,7 +6,7 @@ cd "$(dirname "$0")"
 JOBS=${JOBS:-8}
 NVCC=${NVCC:-nvcc}
 FLAGS="-std=c++17 -O3 -gencode arch=compute_100a,code=sm_100a -lineinfo -diag-suppress 128 -Xcompiler -fPIC -Xcompiler -O2"
-SRCS="plan.cu api.cu optim.cu nonlocal.cu fft_dispatch.cu grid_kernels.cu qr.cu fft_passes_g0.cu fft_passes_g1.cu fft_passes_g2.cu fft_passes_g3.cu fft_passes_g4.cu fft_passes_g5.cu fft_fused_g0.cu fft_fused_g1.cu fft_fused_g2.cu fft_fused_g3.cu"
+SRCS="plan.cu api.cu comm.cu optim.cu nonlocal.cu fft_dispatch.cu grid_kernels.cu qr.cu fft_passes_g0.cu fft_passes_g1.cu fft_passes_g2.cu fft_passes_g3.cu fft_passes_g4.cu fft_passes_g5.cu fft_fused_g0.cu fft_fused_g1.cu fft_fused_g2.cu fft_fused_g3.cu"
 mkdir -p build
 pids=()
 for s in $SRCS; do

@@ -234,13 +234,19 @@ int launch_hpsi_prepare(jrb_plan* p, const double* veff, cudaStream_t st) {
 }
 
 // rho[s] = sum_{k,b} occ |psi|^2  (jrb_density).
-int launch_density(jrb_plan* p, const cplx* q, const double* occ, double* rho, cudaStream_t st) {
+int launch_density_partial(jrb_plan* p, const cplx* q, const double* occ, double* rho, cudaStream_t st) {
   int rc = launch_focc(p, occ, st);
   if (rc) return rc;
   if ((rc = launch_density_begin(p, rho, st))) return rc;
   const int per_spin = p->nk * p->ngroups_per_k;
   for (int s = 0; s < p->ns; ++s)
     if ((rc = density_groups(p, q, rho + (size_t)s * p->ngrid, s, 0, per_spin, st))) return rc;
+  return 0;
+}
+
+int launch_density(jrb_plan* p, const cplx* q, const double* occ, double* rho, cudaStream_t st) {
+  int rc = launch_density_partial(p, q, occ, rho, st);
+  if (rc) return rc;
   return launch_density_end(p, rho, st);
 }
 

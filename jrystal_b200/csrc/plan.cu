@@ -114,6 +114,7 @@ extern "C" int jrb_plan_destroy(jrb_plan* p) {
   cudaSetDevice(p->device);
   if (p->wf) jrb_plan_destroy(p->wf);
   p->wf = nullptr;
+  comm_destroy(p);
   if (p->d_rho_w) cudaFree(p->d_rho_w);
   delete[] p->h_freq;
   delete[] p->h_kpts;

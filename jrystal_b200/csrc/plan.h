@@ -117,6 +117,8 @@ struct jrb_plan {
   int32_t* h_freq;      // [ng][3] integer frequencies of the kept plane waves, compact order
   double* h_kpts;       // [nk][3]
   int gmax[3];          // largest |frequency| per axis on the sphere
+  // communicator over NVLink peer memory (comm.cu: jrb_comm_create / jrb_comm_connect); null = none
+  void* comm;
 };
 
 namespace jrb {
@@ -165,6 +167,17 @@ int launch_nonlocal_project(jrb_plan* p, int sk0, int nsk, const cplx* q, cudaSt
 int launch_nonlocal_energy(jrb_plan* p, const double* occ, double* e_inout, cudaStream_t st);
 int launch_nonlocal_apply(jrb_plan* p, int sk0, int nsk, cplx* hq, cudaStream_t st);
 int launch_external_position_gradient(jrb_plan* p, const double* rho, double* grad, cudaStream_t st);
+
+// comm.cu: all-reduce over peer memory (in-place SUM over ranks of buf[0..n) and extra[0..m), m <= 8)
+int launch_comm_allreduce(jrb_plan* p, double* buf, long long n, double* extra, int m,
+                          cudaStream_t st);
+int comm_world(const jrb_plan* p);   // 1 without a connected communicator
+int comm_error(jrb_plan* p, cudaStream_t st);
+void comm_destroy(jrb_plan* p);
+// fft_dispatch.cu: occupation table + zero + every (spin, k, band group) swept into the density of
+// the grid the passes run on (the orbital box when there is one): launch_density without the
+// final resampling, so that a multi-GPU caller can all-reduce the smaller box in between
+int launch_density_partial(jrb_plan* p, const cplx* q, const double* occ, double* rho, cudaStream_t st);
 
 // qr.cu
 int qr_gram_partial_mats(const jrb_plan* p);

@@ -120,6 +120,47 @@ def bands_to_rows(x_bands: torch.Tensor, row_blocks: Sequence[Tuple[int, int]],
   return torch.cat(pieces, dim=3)
 
 
+class KShardedEvaluator:
+  """Energy+gradient evaluation with whole k-points per rank -- the reference's
+  `parallel_over_k_mesh` layout (calc/calc_ground_state_energy_all_electrons.py:83-91,151-158;
+  nk % world == 0, spmd/uniform.py:22-24).  The one collective, the all-reduce of the partial
+  density and E_kin, runs INSIDE the library over NVLink peer memory (jrb_eval with the plan's
+  communicator: reduced on the orbital grid, bit-identical on every rank); when peer memory
+  cannot be set up (or JRB_NO_PEER=1) it falls back to NCCL between jrb_eval_begin and
+  jrb_eval_finish.  `reduce_path` says which."""
+
+  def __init__(self, cell_vectors, freq_mask, kpts, num_bands, positions, charges, group=None,
+               device: Optional[int] = None, batch_groups: int = 0, orbital_grid=None):
+    from .plan import Plan
+    self.group = group
+    self.world, self.rank = _world(group)
+    kpts = np.asarray(kpts, dtype=np.float64).reshape(-1, 3)
+    self.k0, self.k1 = shard_kpoints(kpts.shape[0], self.world, self.rank)
+    self.plan = Plan(cell_vectors, freq_mask, kpts[self.k0:self.k1], num_bands, device=device,
+                     batch_groups=batch_groups, orbital_grid=orbital_grid)
+    self.plan.set_atoms(positions, charges)
+    self.reduce_path = 'none'
+    if self.world > 1:
+      self.reduce_path = 'peer' if self.plan.comm_init(group) else 'nccl'
+    p = self.plan
+    self._dbuf, self._rho, self._e_kin = density_buffers((p.ns, p.nx, p.ny, p.nz), p.tdev)
+
+  def evaluate(self, w_re, w_im, occ, xc: str = 'lda_x', out=None, want_occ_grad: bool = False):
+    """w_re, w_im: (ns, k-points of this rank, ng, nb); occ: (ns, k-points of this rank, nb).
+    Returns energies[4] (whole system), dE/dw_re, dE/dw_im (this rank's k-points), rho (whole)."""
+    p = self.plan
+    if self.reduce_path != 'nccl':
+      en, g_re, g_im, g_occ, rho = p.eval(w_re, w_im, occ, xc, want_occ_grad, out=out, rho=self._rho)
+    else:
+      p.eval_begin(w_re, w_im, occ, self._rho, self._e_kin)
+      allreduce_density(self._rho, self._e_kin, self._dbuf, group=self.group)
+      en, g_re, g_im, g_occ = p.eval_finish(occ, self._rho, self._e_kin, xc, want_occ_grad, out=out)
+      rho = self._rho
+    if want_occ_grad:
+      return en, g_re, g_im, rho, g_occ
+    return en, g_re, g_im, rho
+
+
 class RowShardedEvaluator:
   """Energy+gradient evaluation when there are fewer k-points than GPUs (Gamma-only supercells,
   BASELINE config C3a): every rank owns a contiguous block of sphere ROWS of the parameters for
@@ -152,6 +193,18 @@ class RowShardedEvaluator:
     self.bands = Plan(cell_vectors, mask, kpts, self.b1 - self.b0, device=device,
                       batch_groups=batch_groups, orbital_grid=orbital_grid)
     self.bands.set_atoms(positions, charges)
+    # peer-memory all-reduces of the library (bit-identical sums on every rank, which the
+    # replicated Cholesky relies on); NCCL when they cannot be set up
+    self.reduce_path = 'none'
+    if self.world > 1:
+      ok = self.rows.comm_init(group) and self.bands.comm_init(group)
+      self.reduce_path = 'peer' if ok else 'nccl'
+
+  def _sum_small(self, m):
+    if self.reduce_path == 'peer':
+      self.rows.allreduce(m)
+    else:
+      allreduce_sum(m, group=self.group)
 
   def evaluate(self, w_re_rows, w_im_rows, occ, xc: str = 'lda_x'):
     """w_re_rows, w_im_rows: (1, nk, rows of this rank, nb); occ: (1, nk, nb) full.
@@ -159,19 +212,22 @@ class RowShardedEvaluator:
     rp, bp = self.rows, self.bands
     for pass_ in (0, 1):
       s = rp.gram(w_re_rows, w_im_rows, pass_)
-      allreduce_sum(s, group=self.group)
+      self._sum_small(s)
       q_rows, _ = rp.apply(w_re_rows, w_im_rows, pass_, s)
     q_band = rows_to_bands(q_rows, self.row_blocks, self.band_blocks, self.group)
     occ_band = occ[:, :, self.b0:self.b1].contiguous()
     buf, rho, e_kin = density_buffers((1, bp.nx, bp.ny, bp.nz), bp.tdev)
     bp.density(q_band, occ_band, out=rho)
     e_kin.copy_((bp.kinetic(q_band) * occ_band).sum().reshape(1))
-    allreduce_density(rho, e_kin, buf, group=self.group)
+    if self.reduce_path == 'peer':
+      bp.allreduce_rho(rho, e_kin)
+    else:
+      allreduce_density(rho, e_kin, buf, group=self.group)
     en, veff = bp.grid_potential(rho, xc, False)
     hq_band = bp.hpsi(q_band, veff)
     hq_rows = bands_to_rows(hq_band, self.row_blocks, self.band_blocks, self.group)
     m = rp.bwd_gram(q_rows, hq_rows)
-    allreduce_sum(m, group=self.group)
+    self._sum_small(m)
     g_re, g_im = rp.bwd_apply(q_rows, hq_rows, occ, m)
     energies = torch.stack([e_kin[0], en[1], en[0], en[2]])
     return energies, g_re, g_im, rho

@@ -37,7 +37,55 @@ def _check_tensor(t, shape, dtype, name, device):
   return t
 
 
-class Plan:
+class _CommMixin:
+  """Plan-owned communicator over NVLink peer memory (jrb_comm_*; include/jrystal_b200.h)."""
+
+  comm_world = 1
+
+  def comm_init(self, group=None, capacity: int = 0) -> bool:
+    """Create this rank's symmetric region, exchange the CUDA IPC handles over torch.distributed
+    and map the peers.  Returns False (and leaves the plan without a communicator) when peer
+    memory cannot be set up -- callers then keep the NCCL all-reduce.  JRB_NO_PEER=1 disables it."""
+    import os
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()):
+      return False
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    if world == 1 or os.environ.get('JRB_NO_PEER', '0') not in ('', '0'):
+      return False
+    nbytes = int(self.lib.jrb_comm_handle_bytes())
+    mine = (ctypes.c_ubyte * nbytes)()
+    ok = self.lib.jrb_comm_create(self._h, rank, world, int(capacity), mine) == 0
+    send = torch.zeros(nbytes + 1, dtype=torch.uint8, device=self.tdev)
+    if ok:
+      send[:nbytes] = torch.frombuffer(bytearray(mine), dtype=torch.uint8).to(self.tdev)
+      send[nbytes] = 1
+    recv = torch.empty(world * (nbytes + 1), dtype=torch.uint8, device=self.tdev)
+    dist.all_gather_into_tensor(recv, send, group=group)
+    recv = recv.cpu().view(world, nbytes + 1)
+    ok = bool(recv[:, nbytes].all())
+    if ok:
+      handles = recv[:, :nbytes].contiguous().numpy().tobytes()
+      ok = self.lib.jrb_comm_connect(self._h, handles) == 0
+    flag = torch.tensor([1 if ok else 0], dtype=torch.int32, device=self.tdev)
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)   # all ranks or none
+    ok = bool(flag.item())
+    self.comm_world = world if ok else 1
+    self.comm_error = None if ok else _lib.load().jrb_last_error()
+    return ok
+
+  def allreduce(self, buf):
+    """In-place SUM over the ranks of a contiguous float64 / complex128 CUDA tensor."""
+    if not buf.is_cuda or not buf.is_contiguous() or buf.dtype not in (torch.float64, torch.complex128):
+      raise TypeError('allreduce needs a contiguous float64 / complex128 CUDA tensor')
+    if buf.device.index != self.device:
+      raise ValueError(f'buffer is on {buf.device}, plan is on cuda:{self.device}')
+    n = buf.numel() * (2 if buf.is_complex() else 1)
+    _lib.check(self.lib.jrb_allreduce(self._h, _ptr(buf), n, _stream(self.device)))
+    return buf
+
+
+class Plan(_CommMixin):
 
   def __init__(self, cell_vectors, freq_mask, kpts, num_bands: int, num_spin: int = 1,
                device: Optional[int] = None, batch_groups: int = 0, orbital_grid=None):
@@ -374,6 +422,35 @@ class Plan:
                                         _ptr(g_occ), _stream(self.device)))
     return energies, g_re, g_im, g_occ
 
+  def allreduce_rho(self, rho, e_kin=None):
+    """jrb_allreduce_rho: in-place SUM over the ranks of the partial density (+ E_kin)."""
+    self._chk(rho, self.grid_shape, torch.float64, 'rho')
+    if e_kin is not None:
+      self._chk(e_kin, (1,), torch.float64, 'e_kin')
+    _lib.check(self.lib.jrb_allreduce_rho(self._h, _ptr(rho), _ptr(e_kin), _stream(self.device)))
+
+  def eval(self, w_re, w_im, occ, xc: str = 'lda_x', want_occ_grad: bool = False, out=None,
+           rho=None):
+    """jrb_eval: the whole evaluation in one call; with a connected communicator the partial
+    density is all-reduced inside the library (on the orbital grid)."""
+    if not self._atoms:
+      raise RuntimeError('call set_atoms(positions, charges) first')
+    if xc not in _lib.XC_IDS:
+      raise NotImplementedError(f'xc "{xc}" is not implemented (implemented: {list(_lib.XC_IDS)})')
+    self._chk(w_re, self.sphere_shape, torch.float64, 'w_re')
+    self._chk(w_im, self.sphere_shape, torch.float64, 'w_im')
+    self._chk(occ, self.band_shape, torch.float64, 'occupation')
+    energies, g_re, g_im = self._out(out, [((4,), torch.float64, 'energies'),
+                                           (self.sphere_shape, torch.float64, 'g_re'),
+                                           (self.sphere_shape, torch.float64, 'g_im')])
+    rho = self._new(self.grid_shape, torch.float64) if rho is None else self._chk(
+      rho, self.grid_shape, torch.float64, 'rho')
+    g_occ = self._new(self.band_shape, torch.float64) if want_occ_grad else None
+    _lib.check(self.lib.jrb_eval(self._h, _ptr(w_re), _ptr(w_im), _ptr(occ), _lib.XC_IDS[xc],
+                                 _ptr(energies), _ptr(g_re), _ptr(g_im), _ptr(g_occ), _ptr(rho),
+                                 _stream(self.device)))
+    return energies, g_re, g_im, g_occ, rho
+
   def energy_grad_host(self, w_re, w_im, occ, xc: str = 'lda_x', out=None, want_rho=False):
     """Host (numpy / pinned torch CPU) buffers in and out through jrb_energy_grad_host."""
     if not self._atoms:
@@ -400,7 +477,7 @@ class Plan:
     return energies, g_re, g_im, rho
 
 
-class RowsPlan:
+class RowsPlan(_CommMixin):
   """QR-only plan over a block of `nrows` rows of the (ns, nk, ng, nb) coefficient matrices
   (jrb_plan_create_rows): the row-sharded half of the Gamma-only multi-GPU layout, SURVEY 8e.
   The split-phase methods also exist on nothing else; between `gram` and `apply` the caller

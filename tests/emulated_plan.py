@@ -39,6 +39,10 @@ class EmulatedPlan:
 
   sphere_shape = property(lambda self: (self.ns, self.nk, self.ng, self.nb))
 
+  def comm_init(self, group=None, capacity=0):
+    """No peer memory on the CPU: callers keep the torch.distributed all-reduce (gloo here)."""
+    return False
+
   # -- set-up ---------------------------------------------------------------------------------
   def set_atoms(self, positions, charges):
     self.v_ext = torch.as_tensor(rp.external_reciprocal(
@@ -247,6 +251,9 @@ class EmulatedRowsPlan:
     self.ns, self.nk, self.nb, self.ng = int(num_spin), int(num_k), int(num_bands), int(nrows)
     self.tdev = torch.device('cpu')
     self._r1 = self._q1 = self._r = None
+
+  def comm_init(self, group=None, capacity=0):
+    return False
 
   @staticmethod
   def _chol_upper(s):

@@ -327,6 +327,65 @@ def test_gloo_world2_row_band_sharded_evaluation(tmp_path):
   assert rows == s.num_g
 
 
+def _rank_k_sharded(rank, world, port, out_dir):
+  import os
+  import numpy as np
+  import torch
+  import torch.distributed as dist
+  import jrystal_b200.plan as plan_mod
+  from jrystal_b200 import parallel
+  from oracle import reference_port as rp
+  os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
+  dist.init_process_group('gloo', rank=rank, world_size=world)
+  try:
+    torch.set_num_threads(2)
+    plan_mod.Plan = emulated_plan.EmulatedPlan
+    s = rp.System.from_name('diamond', [12, 12, 12], [1, 2, 2], 10.0)     # 4 k-points, 2 per rank
+    nb = 6
+    p = rp.param_init(3, nb, s.num_k, s.mask)
+    occ = rp.occupation_uniform(s.num_k, s.num_electrons, num_bands=nb).numpy()
+    occ = occ * (1.0 + 0.1 * np.random.default_rng(4).random(occ.shape))
+    ev = parallel.KShardedEvaluator(s.cell, s.mask, s.kpts, nb, s.positions, s.charges)
+    assert ev.reduce_path == 'nccl'     # = torch.distributed (gloo here): no peer memory on the CPU
+    sl = slice(ev.k0, ev.k1)
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a))
+    en, g_re, g_im, rho = ev.evaluate(t(p['w_re'][:, sl]), t(p['w_im'][:, sl]), t(occ[:, sl]))
+    np.savez(os.path.join(out_dir, f'k{rank}.npz'), en=en.numpy(), g_re=g_re.numpy(),
+             g_im=g_im.numpy(), rho=rho.numpy(), k0=ev.k0, k1=ev.k1)
+  finally:
+    dist.destroy_process_group()
+
+
+def test_gloo_world2_k_sharded_evaluator(tmp_path):
+  """parallel.KShardedEvaluator on 2 ranks (whole k-points per rank, the reference's k-mesh layout,
+  calc_ground_state_energy_all_electrons.py:83-91; rho + E_kin all-reduced) == the oracle's single
+  evaluation: energies, density and each rank's k-block of both gradients."""
+  import os
+  import numpy as np
+  import torch.multiprocessing as mp
+  from oracle import reference_port as rp
+  port = 39500 + (os.getpid() % 2000)
+  mp.spawn(_rank_k_sharded, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+  s = rp.System.from_name('diamond', [12, 12, 12], [1, 2, 2], 10.0)
+  nb = 6
+  p = rp.param_init(3, nb, s.num_k, s.mask)
+  occ = rp.occupation_uniform(s.num_k, s.num_electrons, num_bands=nb).numpy()
+  occ = occ * (1.0 + 0.1 * np.random.default_rng(4).random(occ.shape))
+  ref = rp.energy_and_grad(s, p['w_re'], p['w_im'], occ)
+  seen = 0
+  for rank in range(2):
+    d = np.load(tmp_path / f'k{rank}.npz')
+    k0, k1 = int(d['k0']), int(d['k1'])
+    seen += k1 - k0
+    np.testing.assert_allclose(d['en'], [ref['e_kin'], ref['e_ext'], ref['e_har'], ref['e_xc']],
+                               rtol=1e-10)
+    assert np.abs(d['rho'] - ref['density']).max() < 1e-10 * np.abs(ref['density']).max()
+    scale = np.abs(ref['g_re']).max()
+    assert np.abs(d['g_re'] - ref['g_re'][:, k0:k1]).max() < 1e-9 * scale
+    assert np.abs(d['g_im'] - ref['g_im'][:, k0:k1]).max() < 1e-9 * scale
+  assert seen == s.num_k
+
+
 def test_create_crystal_checks_the_spin_number_and_prefers_the_builtin_name(tmp_path):
   """opt_utils.py:105-114 of the reference: check_spin_number on the created crystal (the default
   `spin: 0` with the 13 electrons of al_primitive must raise, not drop an electron) and a built-in

@@ -201,3 +201,23 @@ def test_gga_energy_gradient_finite_difference():
   ep = rp.energy_and_grad(s, p['w_re'] + h * d, p['w_im'], occ, xc=xc)['e_tot']
   em = rp.energy_and_grad(s, p['w_re'] - h * d, p['w_im'], occ, xc=xc)['e_tot']
   assert abs((ep - em) / (2 * h) - (ref['g_re'] * d).sum()) < 1e-6 * abs((ref['g_re'] * d).sum())
+
+
+def test_blocked_evaluation_equals_the_one_graph_evaluation():
+  """reference_port.energy_and_grad_blocked (k-blocks / band chunks with bounded memory; the
+  checker of the BASELINE-sized GPU tests and the full-workload CPU arm of bench.py) against
+  energy_and_grad, which runs the reference's loss through ONE autograd graph."""
+  s = rp.System.from_name('diamond', 16, [1, 2, 2], 20.0)
+  nb = 10
+  p = rp.param_init(123, nb, s.num_k, s.mask)
+  occ = rp.occupation_uniform(s.num_k, s.num_electrons, num_bands=nb).numpy()
+  occ = occ * (1 + 0.3 * np.random.default_rng(0).random(occ.shape))
+  for xc in ('lda_x', 'lda_x+lda_c_pw'):
+    a = rp.energy_and_grad(s, p['w_re'], p['w_im'], occ, xc=xc)
+    for b in (rp.energy_and_grad_chunked(s, p['w_re'], p['w_im'], occ, xc, band_chunk=3),
+              rp.energy_and_grad_kblocks(s, p['w_re'], p['w_im'], occ, xc, kblock=3),
+              rp.energy_and_grad_blocked(s, p['w_re'], p['w_im'], occ, xc, 2, 4)):
+      for k in ('e_kin', 'e_ext', 'e_har', 'e_xc', 'e_tot'):
+        assert abs(a[k] - b[k]) < 1e-13 * abs(a['e_tot']), k
+      for k in ('density', 'g_re', 'g_im'):
+        assert np.abs(a[k] - b[k]).max() < 1e-13 * np.abs(a[k]).max(), k
