@@ -503,6 +503,216 @@ k_tri_compose(const cplx* __restrict__ R2, const cplx* __restrict__ R2inv,
   rinv_out[off + e] = b;
 }
 
+// ---------------------------------------------------------------------------------------
+// One CTA per (spin, k), everything in shared memory: Cholesky factor, triangular inverse and (second
+// Cholesky-QR pass) the composition with the first pass, in ONE launch.  Replaces the chain
+// k_chol_blocked / k_chol_panel x3 + k_tri_inv_* x2 (+ k_near_identity + k_tri_compose): 5-10
+// dependent launches of 8-25 us each, a latency floor that does not shrink with the number of
+// k-points of a rank (8 per rank for Si8 on 8 GPUs).
+//   phase 1  S = L L^H, lower-triangle elements DISTRIBUTED OVER REGISTERS (element e -> thread
+//            e % FS_T, EPT per thread): unscaled right-looking elimination, one barrier per
+//            column; only the finished column j is published (double-buffered vector in shared
+//            memory), so a step costs two conflict-free loads and one complex FMA per live element
+//   phase 2  X = L^-1 row by row: X[i][j] = -(sum_{k=j}^{i-1} L[i][k] X[k][j]) / L[i][i]; four
+//            lanes per column split the k-sum; X is kept TRANSPOSED in the upper triangle of the
+//            same shared-memory matrix that holds L in its lower one (no write-after-read hazard:
+//            one barrier per row)
+//   PASS2    Q1^H Q1 = I + E: closed form for max|E| < tol (see k_near_identity), else phases 1-2;
+//            then r = R2 R1 and rinv = R1^-1 R2^-1 (upper triangular products) from the same
+//            shared-memory factors
+// Outputs (row major, zeros below the diagonal): Rt = L^H, Rit = Rt^-1; PASS2 also r, rinv.
+// grid: (nsk), block FS_T; dynamic smem: fs_smem_bytes(nb)
+constexpr int FS_T = 512;
+__host__ __device__ inline int fs_ld(int nb) { return nb | 1; }
+static int fs_smem_bytes(int nb) {
+  // matrix [nb][ld] + 2 column vectors + diagonal (double) + inverse diagonal (double)
+  return (nb * fs_ld(nb) + 2 * nb) * (int)sizeof(cplx) + 2 * nb * (int)sizeof(double);
+}
+
+template <int EPT, bool PASS2>
+__global__ void __launch_bounds__(FS_T)
+k_small_factor(const cplx* __restrict__ S, int nb, double tol, cplx* __restrict__ Rt,
+               cplx* __restrict__ Rit, const cplx* __restrict__ R1, const cplx* __restrict__ R1inv,
+               cplx* __restrict__ r_out, cplx* __restrict__ rinv_out, int* __restrict__ fail_flag) {
+  extern __shared__ __align__(16) unsigned char smem_raw_[];
+  const int ld = fs_ld(nb);
+  cplx* M = reinterpret_cast<cplx*>(smem_raw_);          // [nb][ld]: L below, X^T above the diagonal
+  cplx* col = M + (size_t)nb * ld;                       // [2][nb] published column
+  double* dvec = reinterpret_cast<double*>(col + 2 * nb);  // [nb] unscaled pivots, then L[i][i]
+  double* invd = dvec + nb;                              // [nb] 1 / L[i][i]
+  __shared__ double red[FS_T / 32];
+  __shared__ int near_id;
+  const long long nn = (long long)nb * nb;
+  const long long off = blockIdx.x * nn;
+  S += off;
+  const int tid = threadIdx.x;
+  const int ntri = nb * (nb + 1) / 2;
+
+  bool shortcut = false;
+  if (PASS2) {
+    double m = 0.0;
+    for (int e = tid; e < nb * nb; e += FS_T) {
+      const int i = e / nb, j = e - i * nb;
+      const cplx v = S[e];
+      m = fmax(m, fmax(fabs(v.x - (i == j ? 1.0 : 0.0)), fabs(v.y)));
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((tid & 31) == 0) red[tid >> 5] = m;
+    __syncthreads();
+    if (tid == 0) {
+      double t = 0.0;
+      for (int w = 0; w < FS_T / 32; ++w) t = fmax(t, red[w]);
+      near_id = (t < tol) ? 1 : 0;   // NaN compares false: the factorisation reports it
+    }
+    __syncthreads();
+    shortcut = near_id != 0;
+  }
+
+  if (shortcut) {
+    // R2 = I + U, R2^-1 = I - U (+ U^2 on the diagonal), U = up(E) + diag(E) / 2
+    for (int e = tid; e < nb * nb; e += FS_T) {
+      const int i = e / nb, j = e - i * nb;
+      const cplx v = S[e];
+      if (i > j) M[i * ld + j] = v;                      // L = R2^H: L[i][j] = conj(S[j][i]) = S[i][j]
+      else if (i < j) M[i * ld + j] = cmake(-v.x, v.y);  // X^T[i][j] = X[j][i] = conj(R2inv[i][j])
+      else {
+        const double u = 0.5 * (v.x - 1.0);
+        dvec[i] = 1.0 + u;
+        invd[i] = 1.0 - u + u * u;
+      }
+    }
+    __syncthreads();
+  } else {
+    // ---- phase 1: Cholesky, elements in registers --------------------------------------------
+    cplx v[EPT];
+    int rc[EPT];  // r | c << 16, -1 = none
+#pragma unroll
+    for (int q = 0; q < EPT; ++q) {
+      const int e = tid + FS_T * q;
+      rc[q] = -1;
+      v[q] = cmake(0.0, 0.0);
+      if (e < ntri) {
+        int r = (int)((sqrt(8.0 * e + 1.0) - 1.0) * 0.5);
+        while (r * (r + 1) / 2 > e) --r;
+        while ((r + 1) * (r + 2) / 2 <= e) ++r;
+        const int c = e - r * (r + 1) / 2;
+        rc[q] = r | (c << 16);
+        v[q] = S[(long long)r * nb + c];
+        if (c == 0) col[r] = v[q];
+        if (r == c) v[q].y = 0.0;
+        if (r == 0) dvec[0] = v[q].x;
+      }
+    }
+    for (int j = 0; j < nb - 1; ++j) {
+      __syncthreads();
+      const cplx* cj = col + (j & 1) * nb;
+      cplx* cn = col + ((j + 1) & 1) * nb;
+      const double djj = cj[j].x;
+      const double rinv = 1.0 / (djj > 0.0 ? djj : 1.0);
+#pragma unroll
+      for (int q = 0; q < EPT; ++q) {
+        const int r = rc[q] & 0xffff, c = rc[q] >> 16;
+        if (rc[q] >= 0 && c > j) {
+          const cplx a = cj[r], b = cj[c];
+          const cplx u = cmulc(a, cmake(b.x * rinv, b.y * rinv));
+          v[q].x -= u.x;
+          v[q].y -= u.y;
+          if (c == j + 1) {
+            if (r == c) {
+              v[q].y = 0.0;
+              dvec[c] = v[q].x;
+            }
+            cn[r] = v[q];
+          }
+        }
+      }
+    }
+    __syncthreads();
+    // pivots -> L: column c scaled by 1 / sqrt(d_c)
+#pragma unroll
+    for (int q = 0; q < EPT; ++q) {
+      if (rc[q] >= 0) {
+        const int r = rc[q] & 0xffff, c = rc[q] >> 16;
+        const double d = dvec[c];
+        if (r == c) {
+          if (!(d > 0.0)) atomicExch(fail_flag, 1);
+        } else {
+          const double sc = 1.0 / sqrt(d > 0.0 ? d : 1.0);
+          M[r * ld + c] = cmake(v[q].x * sc, v[q].y * sc);
+        }
+      }
+    }
+    __syncthreads();
+    if (tid < nb) {
+      const double d = dvec[tid];
+      const double l = sqrt(d > 0.0 ? d : 1.0);
+      dvec[tid] = l;
+      invd[tid] = 1.0 / l;
+    }
+    __syncthreads();
+    // ---- phase 2: X = L^-1, row by row; X[i][j] lives at M[j][i] --------------------------------
+    const int j = tid >> 2, l = tid & 3;
+    for (int i = 1; i < nb; ++i) {
+      double sx = 0.0, sy = 0.0;
+      if (j < i) {
+        const cplx* Li = M + i * ld;   // L[i][k], k < i
+        const cplx* Xj = M + j * ld;   // X[k][j] at M[j][k], k > j; X[j][j] = invd[j]
+        for (int k = j + l; k < i; k += 4) {
+          const cplx a = Li[k];
+          const cplx x = k == j ? cmake(invd[j], 0.0) : Xj[k];
+          sx += a.x * x.x - a.y * x.y;
+          sy += a.x * x.y + a.y * x.x;
+        }
+      }
+      sx += __shfl_xor_sync(0xffffffffu, sx, 1);
+      sy += __shfl_xor_sync(0xffffffffu, sy, 1);
+      sx += __shfl_xor_sync(0xffffffffu, sx, 2);
+      sy += __shfl_xor_sync(0xffffffffu, sy, 2);
+      if (j < i && l == 0) {
+        const double s = -invd[i];
+        M[j * ld + i] = cmake(sx * s, sy * s);
+      }
+      __syncthreads();
+    }
+  }
+
+  // ---- outputs: R2 = L^H: R[a][b] = conj(M[b][a]) (a < b), R[a][a] = dvec[a];
+  //      R^-1 = X^H: Rinv[a][b] = conj(X[b][a]) = conj(M[a][b]) (a < b), Rinv[a][a] = invd[a]
+  for (int e = tid; e < nb * nb; e += FS_T) {
+    const int a = e / nb, b = e - a * nb;
+    cplx r = cmake(0.0, 0.0), ri = cmake(0.0, 0.0);
+    if (a < b) {
+      r = cconj(M[b * ld + a]);
+      ri = cconj(M[a * ld + b]);
+    } else if (a == b) {
+      r = cmake(dvec[a], 0.0);
+      ri = cmake(invd[a], 0.0);
+    }
+    Rt[off + e] = r;
+    Rit[off + e] = ri;
+  }
+  if (PASS2) {
+    // r = R2 R1, rinv = R1^-1 R2^-1 (all upper triangular): k runs over [a, b]
+    for (int e = tid; e < nb * nb; e += FS_T) {
+      const int a = e / nb, b = e - a * nb;
+      cplx x = cmake(0.0, 0.0), y = cmake(0.0, 0.0);
+      if (b >= a) {
+        for (int k = a; k <= b; ++k) {
+          const cplx r2 = k == a ? cmake(dvec[a], 0.0) : cconj(M[k * ld + a]);
+          const cplx u = cmul(r2, R1[off + (long long)k * nb + b]);
+          x.x += u.x; x.y += u.y;
+          const cplx r2i = k == b ? cmake(invd[b], 0.0) : cconj(M[k * ld + b]);
+          const cplx w = cmul(R1inv[off + (long long)a * nb + k], r2i);
+          y.x += w.x; y.y += w.y;
+        }
+      }
+      r_out[off + e] = x;
+      rinv_out[off + e] = y;
+    }
+  }
+}
+
 // Adjoint, step 1: M = (sum partial) diag(f); X = -(up(M) + up(M)^H + diag Re M);
 // T1 = diag(f) Rinv^H.   grid: (ceil(nb^2 / 256), nsk)
 __global__ void __launch_bounds__(SMALL_T)
@@ -745,6 +955,34 @@ static int chol_and_inverse(jrb_plan* p, int nsk, cplx* S, cplx* Rt, cplx* Rit, 
   return tri_inverse(Rt, nb, nsk, Rit, st, skip);
 }
 
+// The one-launch shared-memory chain (k_small_factor) serves matrices whose lower triangle fits the
+// registers of one CTA and whose square fits shared memory.
+static int small_fused_ept(int nb) {
+  static int off = [] {
+    const char* env = std::getenv("JRB_NO_FUSED_SMALL");
+    return env ? std::atoi(env) : 0;
+  }();
+  if (off) return 0;
+  const int ntri = nb * (nb + 1) / 2;
+  if (fs_smem_bytes(nb) > 200 * 1024) return 0;
+  if (ntri <= 5 * FS_T) return 5;
+  if (ntri <= 14 * FS_T) return 14;
+  return 0;
+}
+
+template <int EPT, bool PASS2>
+static int run_small_factor(jrb_plan* p, int nsk, const cplx* S, double tol, cplx* Rt, cplx* Rit,
+                            const cplx* R1, const cplx* R1inv, cplx* r_out, cplx* rinv_out,
+                            cudaStream_t st) {
+  static int once = opt_in_smem(k_small_factor<EPT, PASS2>, 200 * 1024);
+  if (once) return once;
+  int* fail = reinterpret_cast<int*>(p->d_scal + 32);
+  k_small_factor<EPT, PASS2><<<nsk, FS_T, fs_smem_bytes(p->nb), st>>>(S, p->nb, tol, Rt, Rit, R1,
+                                                                     R1inv, r_out, rinv_out, fail);
+  JRB_CHECK_LAUNCH("k_small_factor");
+  return 0;
+}
+
 // Cholesky-QR2 of the (spin,k) range [sk0, sk0 + nsk), in phases so that a row-sharded caller can
 // all-reduce the Gram matrices in between (jrb_qr_rows_*): pass 0 works on W, pass 1 on Q1.
 struct QrSlots {
@@ -786,15 +1024,33 @@ int launch_qr_apply_phase(jrb_plan* p, int sk0, int nsk, const double* w_re, con
   const int nb = p->nb;
   int rc = 0;
   TallMat none{nullptr, nullptr, 0};
+  const int ept = small_fused_ept(nb);
   if (pass == 0) {
     TallMat W{w_re + q.soff, w_im + q.soff, nb};
-    if ((rc = chol_and_inverse(p, nsk, S, q.R1, q.R1inv, st))) return rc;
+    if (ept == 5)
+      rc = run_small_factor<5, false>(p, nsk, S, 0.0, q.R1, q.R1inv, nullptr, nullptr, nullptr, nullptr, st);
+    else if (ept == 14)
+      rc = run_small_factor<14, false>(p, nsk, S, 0.0, q.R1, q.R1inv, nullptr, nullptr, nullptr, nullptr, st);
+    else
+      rc = chol_and_inverse(p, nsk, S, q.R1, q.R1inv, st);
+    if (rc) return rc;
     return run_apply<0>(p, nsk, W, q.R1inv, TRI_UPPER, none, nullptr, TRI_FULL, 1,
                         reinterpret_cast<double*>(q.tmp), nullptr, st);
   }
   TallMat Q1{reinterpret_cast<const double*>(q.tmp), nullptr, nb};
   const char* no_shortcut = std::getenv("JRB_NO_QR_SHORTCUT");
   const bool shortcut = !(no_shortcut && std::atoi(no_shortcut) != 0);
+  if (ept) {
+    // one launch: closed form or factorisation, inverse, and the composition with the first pass
+    const double tol = shortcut ? 1e-10 : 0.0;
+    if (ept == 5)
+      rc = run_small_factor<5, true>(p, nsk, S, tol, q.Rt, q.Rit, q.R1, q.R1inv, r + q.moff, q.rinv, st);
+    else
+      rc = run_small_factor<14, true>(p, nsk, S, tol, q.Rt, q.Rit, q.R1, q.R1inv, r + q.moff, q.rinv, st);
+    if (rc) return rc;
+    return run_apply<0>(p, nsk, Q1, q.Rit, TRI_UPPER, none, nullptr, TRI_FULL, 1,
+                        reinterpret_cast<double*>(qout + q.soff), nullptr, st);
+  }
   const int* skip = nullptr;
   if (shortcut) {
     k_near_identity<<<nsk, 256, 0, st>>>(S, nb, 1e-10, q.Rt, q.Rit, p->d_skip + sk0);
