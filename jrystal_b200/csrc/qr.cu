@@ -16,7 +16,10 @@
 // (leading dimensions == 4 mod 16 doubles make every fragment load bank-conflict free).
 #include <algorithm>
 #include <cmath>
+#include <cstdio>
 #include <cstdlib>
+
+#include <cooperative_groups.h>
 
 #include "plan.h"
 #include "qr_gemm.cuh"
@@ -504,57 +507,151 @@ k_tri_compose(const cplx* __restrict__ R2, const cplx* __restrict__ R2inv,
 }
 
 // ---------------------------------------------------------------------------------------
-// One CTA per (spin, k), everything in shared memory: Cholesky factor, triangular inverse and (second
-// Cholesky-QR pass) the composition with the first pass, in ONE launch.  Replaces the chain
-// k_chol_blocked / k_chol_panel x3 + k_tri_inv_* x2 (+ k_near_identity + k_tri_compose): 5-10
-// dependent launches of 8-25 us each, a latency floor that does not shrink with the number of
-// k-points of a rank (8 per rank for Si8 on 8 GPUs).
-//   phase 1  S = L L^H, lower-triangle elements DISTRIBUTED OVER REGISTERS (element e -> thread
-//            e % FS_T, EPT per thread): unscaled right-looking elimination, one barrier per
-//            column; only the finished column j is published (double-buffered vector in shared
-//            memory), so a step costs two conflict-free loads and one complex FMA per live element
-//   phase 2  X = L^-1 row by row: X[i][j] = -(sum_{k=j}^{i-1} L[i][k] X[k][j]) / L[i][i]; four
-//            lanes per column split the k-sum; X is kept TRANSPOSED in the upper triangle of the
-//            same shared-memory matrix that holds L in its lower one (no write-after-read hazard:
-//            one barrier per row)
-//   PASS2    Q1^H Q1 = I + E: closed form for max|E| < tol (see k_near_identity), else phases 1-2;
-//            then r = R2 R1 and rinv = R1^-1 R2^-1 (upper triangular products) from the same
-//            shared-memory factors
-// Outputs (row major, zeros below the diagonal): Rt = L^H, Rit = Rt^-1; PASS2 also r, rinv.
-// grid: (nsk), block FS_T; dynamic smem: fs_smem_bytes(nb)
-constexpr int FS_T = 512;
-__host__ __device__ inline int fs_ld(int nb) { return nb | 1; }
-static int fs_smem_bytes(int nb) {
-  // matrix [nb][ld] + 2 column vectors + diagonal (double) + inverse diagonal (double)
-  return (nb * fs_ld(nb) + 2 * nb) * (int)sizeof(cplx) + 2 * nb * (int)sizeof(double);
+// Cholesky factor AND triangular inverse of one Hermitian nb x nb matrix per CTA (or per cluster of
+// 8 CTAs) in ONE launch and ONE sweep of nb - 1 steps.  Replaces the chains k_chol_blocked +
+// k_tri_inv_cols (one CTA per matrix) and k_chol_panel x7 + k_tri_inv_diag + k_tri_inv_offdiag
+// (nb = 208: 16 dependent launches, 0.6 ms of the 5.1 ms diamond-64 evaluation), whose latency
+// does not shrink with the number of k-points a rank holds.
+//
+// Measured on B200 (tools/lat_probe.cu: DFMA 10, LDS ~30, 512-thread barrier 44 cycles; a lone warp
+// issues one dependent instruction per ~4.5 cycles): a factorisation is bound by the chain of nb
+// pivots and by the instructions PER THREAD between two barriers, not by flops.  So:
+//   * S = L~ D L~^H by unscaled right-looking elimination with the lower-triangle slots (r, c)
+//     DISTRIBUTED OVER THE REGISTERS of all threads (slot e -> thread e mod T: the slots a step
+//     finishes are spread one per thread); L = L~ D^1/2.
+//   * the inverse rides on the same steps: W = L~^-1 is the same row operations applied to the
+//     identity, and slot (r, c) is needed for the factor only while j < c and for W only while
+//     c <= j < r -- so ONE register per slot serves both, one update per slot and step, no second
+//     phase:  L^-1 = D^-1/2 W.
+//   * one published vector per step makes the update uniform: U_j[i] = a_ij (i > j),
+//     U_j[j] = 1, U_j[i] = conj(W[j][i]) (i < j):   v(r, c) -= U_j[r] conj(U_j[c]) / d_j  for every
+//     slot with r > j, whatever it currently holds.  Finished slots keep being updated (their
+//     results were saved when they were published): no liveness branches, the slots of a thread
+//     interleave.  U lives in shared memory, two interleaved buffers (the parity is an immediate
+//     offset of the step unrolled by two); with a cluster every CTA holds a copy, written through
+//     distributed shared memory by the slot's owner, and the barrier is the cluster barrier.
+//   * 1 / d_j = rcp.approx + two Newton steps per thread, under the latency of its loads.
+// PASS2 (single CTA): Q1^H Q1 = I + E, closed form for max|E| < tol (see k_near_identity).
+// Outputs (row major, zeros below the diagonal): Rt = L^H, Rit = Rt^-1.
+// grid: (nsk * NCTA) in clusters of NCTA, block CF_T; dynamic smem: cf_smem_bytes(nb)
+namespace cg = cooperative_groups;
+constexpr int CF_T = 512;
+__device__ long long g_fs_clocks[8];      // JRB_FS_TIMING: phase boundaries of CTA 0 (tuning aid)
+static int cf_smem_bytes(int nb) {
+  return 2 * nb * (int)sizeof(cplx) + (nb + 2) * (int)sizeof(double);  // U[nb][2], pivots, piv[2]
 }
 
-template <int EPT, bool PASS2>
-__global__ void __launch_bounds__(FS_T)
-k_small_factor(const cplx* __restrict__ S, int nb, double tol, cplx* __restrict__ Rt,
-               cplx* __restrict__ Rit, const cplx* __restrict__ R1, const cplx* __restrict__ R1inv,
-               cplx* __restrict__ r_out, cplx* __restrict__ rinv_out, int* __restrict__ fail_flag) {
+__device__ __forceinline__ double fast_rcp(double d) {
+  double x;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(x) : "d"(d));
+  double t = fma(-d, x, 1.0);
+  x = fma(x, t, x);
+  t = fma(-d, x, 1.0);
+  return fma(x, t, x);
+}
+
+// store to the same shared-memory location of every CTA of the cluster (distributed shared
+// memory: mapa + st.shared::cluster on 32-bit shared addresses, emitted where the value is ready)
+template <int NCTA>
+__device__ __forceinline__ void cf_publish(cplx* local, cplx val) {
+  if constexpr (NCTA > 1) {
+    const unsigned a = (unsigned)__cvta_generic_to_shared(local);
+#pragma unroll
+    for (int k = 0; k < NCTA; ++k)
+      asm volatile(
+        "{ .reg .u32 ra; mapa.shared::cluster.u32 ra, %0, %1;\n"
+        "  st.shared::cluster.v2.f64 [ra], {%2, %3}; }\n" ::"r"(a), "r"(k), "d"(val.x), "d"(val.y)
+        : "memory");
+  } else {
+    *local = val;
+  }
+}
+template <int NCTA>
+__device__ __forceinline__ void cf_publish(double* local, double val) {
+  if constexpr (NCTA > 1) {
+    const unsigned a = (unsigned)__cvta_generic_to_shared(local);
+#pragma unroll
+    for (int k = 0; k < NCTA; ++k)
+      asm volatile(
+        "{ .reg .u32 ra; mapa.shared::cluster.u32 ra, %0, %1;\n"
+        "  st.shared::cluster.f64 [ra], %2; }\n" ::"r"(a), "r"(k), "d"(val)
+        : "memory");
+  } else {
+    *local = val;
+  }
+}
+
+// one step: U_j at parity PAR is complete; updates every slot and publishes U_{j+1} at PAR ^ 1.
+// ua / ub: byte offsets of U[er] / U[ec] (16 bytes per index) within one parity array of pitch
+// `pitch` bytes; a slot's finished factor and inverse entries stay in registers (af, wf).
+template <int EPT, int NCTA, int PAR>
+__device__ __forceinline__ void cf_step(int j, int nb, int pitch, cplx (&v)[EPT], cplx (&af)[EPT],
+                                        cplx (&wf)[EPT], const int (&ua)[EPT], const int (&ub)[EPT],
+                                        unsigned char* Ub, double* dvec) {
+  const double djj = dvec[nb + PAR];
+  const double rinv = fast_rcp(djj > 0.0 ? djj : 1.0);
+  const int jn = 16 * (j + 1);
+  const unsigned char* Uc = Ub + PAR * pitch;
+  unsigned char* Un = Ub + (PAR ^ 1) * pitch;
+#pragma unroll
+  for (int q = 0; q < EPT; ++q) {
+    const cplx a = *reinterpret_cast<const cplx*>(Uc + ua[q]);
+    const cplx b = *reinterpret_cast<const cplx*>(Uc + ub[q]);
+    const double ax = a.x * rinv, ay = a.y * rinv;
+    v[q].x -= ax * b.x + ay * b.y;     // (a rinv) conj(b)
+    v[q].y -= ay * b.x - ax * b.y;
+  }
+#pragma unroll
+  for (int q = 0; q < EPT; ++q) {
+    if (ub[q] == jn) {               // column j + 1 of the factor is final (r >= j + 1)
+      if (ua[q] == jn) {             // its pivot
+        cf_publish<NCTA>(dvec + j + 1, v[q].x);
+        cf_publish<NCTA>(dvec + nb + (PAR ^ 1), v[q].x);
+        cf_publish<NCTA>(reinterpret_cast<cplx*>(Un + jn), cmake(1.0, 0.0));
+      } else {
+        cf_publish<NCTA>(reinterpret_cast<cplx*>(Un + ua[q]), v[q]);
+        af[q] = v[q];                // a_rc, c = j + 1
+        v[q] = cmake(0.0, 0.0);      // the slot now accumulates W[r][c]
+      }
+    } else if (ua[q] == jn) {        // row j + 1 of W is final (c <= j)
+      wf[q] = v[q];                  // W[r][c], r = j + 1
+      cf_publish<NCTA>(reinterpret_cast<cplx*>(Un + ub[q]), cconj(v[q]));
+    }
+  }
+}
+
+template <int EPT, int NCTA, bool PASS2>
+__global__ void __launch_bounds__(CF_T, 1)
+k_factor_stream(const cplx* __restrict__ S, int nb, double tol, cplx* __restrict__ Rt,
+                cplx* __restrict__ Rit, int* __restrict__ fail_flag, const int* __restrict__ skip,
+                int timing) {
   extern __shared__ __align__(16) unsigned char smem_raw_[];
-  const int ld = fs_ld(nb);
-  cplx* M = reinterpret_cast<cplx*>(smem_raw_);          // [nb][ld]: L below, X^T above the diagonal
-  cplx* col = M + (size_t)nb * ld;                       // [2][nb] published column
-  double* dvec = reinterpret_cast<double*>(col + 2 * nb);  // [nb] unscaled pivots, then L[i][i]
-  double* invd = dvec + nb;                              // [nb] 1 / L[i][i]
-  __shared__ double red[FS_T / 32];
-  __shared__ int near_id;
+  cplx* U = reinterpret_cast<cplx*>(smem_raw_);               // [2][nb]: U_j by parity of j
+  double* dvec = reinterpret_cast<double*>(U + 2 * nb);       // [nb] pivots d_i, then [2] d_j by parity
+  const int pitch = nb * (int)sizeof(cplx);
+  const int mat = blockIdx.x / NCTA;
+  if (skip && skip[mat]) return;  // factor already written by k_near_identity (cluster-uniform)
   const long long nn = (long long)nb * nb;
-  const long long off = blockIdx.x * nn;
+  const long long off = mat * nn;
   S += off;
+  Rt += off;
+  Rit += off;
   const int tid = threadIdx.x;
   const int ntri = nb * (nb + 1) / 2;
+  auto tick = [&](int slot) {
+    if (timing && blockIdx.x == 0 && threadIdx.x == 0) g_fs_clocks[slot] = clock64();
+  };
+  tick(0);
 
-  bool shortcut = false;
   if (PASS2) {
+    static_assert(!PASS2 || NCTA == 1, "the fused second pass is a single-CTA variant");
+    __shared__ double red[CF_T / 32];
+    __shared__ int near_id;
     double m = 0.0;
-    for (int e = tid; e < nb * nb; e += FS_T) {
+    for (int e = tid; e < nb * nb; e += CF_T) {
       const int i = e / nb, j = e - i * nb;
-      const cplx v = S[e];
-      m = fmax(m, fmax(fabs(v.x - (i == j ? 1.0 : 0.0)), fabs(v.y)));
+      const cplx x = S[e];
+      m = fmax(m, fmax(fabs(x.x - (i == j ? 1.0 : 0.0)), fabs(x.y)));
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
@@ -562,154 +659,162 @@ k_small_factor(const cplx* __restrict__ S, int nb, double tol, cplx* __restrict_
     __syncthreads();
     if (tid == 0) {
       double t = 0.0;
-      for (int w = 0; w < FS_T / 32; ++w) t = fmax(t, red[w]);
+      for (int w = 0; w < CF_T / 32; ++w) t = fmax(t, red[w]);
       near_id = (t < tol) ? 1 : 0;   // NaN compares false: the factorisation reports it
     }
     __syncthreads();
-    shortcut = near_id != 0;
-  }
-
-  if (shortcut) {
-    // R2 = I + U, R2^-1 = I - U (+ U^2 on the diagonal), U = up(E) + diag(E) / 2
-    for (int e = tid; e < nb * nb; e += FS_T) {
-      const int i = e / nb, j = e - i * nb;
-      const cplx v = S[e];
-      if (i > j) M[i * ld + j] = v;                      // L = R2^H: L[i][j] = conj(S[j][i]) = S[i][j]
-      else if (i < j) M[i * ld + j] = cmake(-v.x, v.y);  // X^T[i][j] = X[j][i] = conj(R2inv[i][j])
-      else {
-        const double u = 0.5 * (v.x - 1.0);
-        dvec[i] = 1.0 + u;
-        invd[i] = 1.0 - u + u * u;
-      }
-    }
-    __syncthreads();
-  } else {
-    // ---- phase 1: Cholesky, elements in registers --------------------------------------------
-    cplx v[EPT];
-    int rc[EPT];  // r | c << 16, -1 = none
-#pragma unroll
-    for (int q = 0; q < EPT; ++q) {
-      const int e = tid + FS_T * q;
-      rc[q] = -1;
-      v[q] = cmake(0.0, 0.0);
-      if (e < ntri) {
-        int r = (int)((sqrt(8.0 * e + 1.0) - 1.0) * 0.5);
-        while (r * (r + 1) / 2 > e) --r;
-        while ((r + 1) * (r + 2) / 2 <= e) ++r;
-        const int c = e - r * (r + 1) / 2;
-        rc[q] = r | (c << 16);
-        v[q] = S[(long long)r * nb + c];
-        if (c == 0) col[r] = v[q];
-        if (r == c) v[q].y = 0.0;
-        if (r == 0) dvec[0] = v[q].x;
-      }
-    }
-    for (int j = 0; j < nb - 1; ++j) {
-      __syncthreads();
-      const cplx* cj = col + (j & 1) * nb;
-      cplx* cn = col + ((j + 1) & 1) * nb;
-      const double djj = cj[j].x;
-      const double rinv = 1.0 / (djj > 0.0 ? djj : 1.0);
-#pragma unroll
-      for (int q = 0; q < EPT; ++q) {
-        const int r = rc[q] & 0xffff, c = rc[q] >> 16;
-        if (rc[q] >= 0 && c > j) {
-          const cplx a = cj[r], b = cj[c];
-          const cplx u = cmulc(a, cmake(b.x * rinv, b.y * rinv));
-          v[q].x -= u.x;
-          v[q].y -= u.y;
-          if (c == j + 1) {
-            if (r == c) {
-              v[q].y = 0.0;
-              dvec[c] = v[q].x;
-            }
-            cn[r] = v[q];
-          }
+    if (near_id) {
+      // R2 = I + U, R2^-1 = I - U (+ U^2 on the diagonal), U = up(E) + diag(E) / 2
+      for (int e = tid; e < nb * nb; e += CF_T) {
+        const int i = e / nb, j = e - i * nb;
+        cplx r = cmake(0.0, 0.0), ri = cmake(0.0, 0.0);
+        if (j > i) {
+          const cplx u = S[e];
+          r = u;
+          ri = cmake(-u.x, -u.y);
+        } else if (j == i) {
+          const double u = 0.5 * (S[e].x - 1.0);
+          r = cmake(1.0 + u, 0.0);
+          ri = cmake(1.0 - u + u * u, 0.0);
         }
+        Rt[e] = r;
+        Rit[e] = ri;
       }
+      tick(1);
+      tick(2);
+      tick(3);
+      return;
     }
-    __syncthreads();
-    // pivots -> L: column c scaled by 1 / sqrt(d_c)
+  }
+  tick(1);
+
+  int rank = 0;
+  if constexpr (NCTA > 1) {
+    rank = (int)cg::this_cluster().block_rank();
+    cg::this_cluster().sync();  // every CTA of the cluster is running before remote stores
+  }
+  auto sync = [&]() {
+    if constexpr (NCTA > 1) cg::this_cluster().sync();
+    else __syncthreads();
+  };
+
+  // slots, row-major lower triangle e = r (r + 1) / 2 + c: a WARP owns 32 EPT consecutive slots (a
+  // few neighbouring rows, so it retires as a whole once its last row is done: rows finish top
+  // down), lane l its slots l, l + 32, ... (consecutive lanes read consecutive U entries)
+  const int gw = (rank * CF_T + tid) >> 5, lane = tid & 31;
+  unsigned char* Ub = smem_raw_;
+  cplx v[EPT], af[EPT], wf[EPT];
+  int ua[EPT], ub[EPT];
+  int rmax = 0;  // last row of this warp
 #pragma unroll
-    for (int q = 0; q < EPT; ++q) {
-      if (rc[q] >= 0) {
-        const int r = rc[q] & 0xffff, c = rc[q] >> 16;
-        const double d = dvec[c];
-        if (r == c) {
-          if (!(d > 0.0)) atomicExch(fail_flag, 1);
+  for (int q = 0; q < EPT; ++q) {
+    const int e = (gw * EPT + q) * 32 + lane;
+    // absent slots alias (0, 0), which publishes at set-up only (never equals j + 1)
+    ua[q] = 0;
+    ub[q] = 0;
+    v[q] = af[q] = wf[q] = cmake(0.0, 0.0);
+    if (e < ntri) {
+      int r = (int)((sqrt(8.0 * e + 1.0) - 1.0) * 0.5);
+      while (r * (r + 1) / 2 > e) --r;
+      while ((r + 1) * (r + 2) / 2 <= e) ++r;
+      const int c = e - r * (r + 1) / 2;
+      ua[q] = 16 * r;
+      ub[q] = 16 * c;
+      rmax = r;
+      v[q] = S[(long long)r * nb + c];
+      if (r == c) v[q].y = 0.0;
+      if (c == 0) {  // column 0 is final as it stands: U_0
+        if (r == 0) {
+          cf_publish<NCTA>(dvec, v[q].x);
+          cf_publish<NCTA>(dvec + nb, v[q].x);
+          cf_publish<NCTA>(U, cmake(1.0, 0.0));
         } else {
-          const double sc = 1.0 / sqrt(d > 0.0 ? d : 1.0);
-          M[r * ld + c] = cmake(v[q].x * sc, v[q].y * sc);
+          cf_publish<NCTA>(U + r, v[q]);
+          af[q] = v[q];
+          v[q] = cmake(0.0, 0.0);
         }
       }
-    }
-    __syncthreads();
-    if (tid < nb) {
-      const double d = dvec[tid];
-      const double l = sqrt(d > 0.0 ? d : 1.0);
-      dvec[tid] = l;
-      invd[tid] = 1.0 / l;
-    }
-    __syncthreads();
-    // ---- phase 2: X = L^-1, row by row; X[i][j] lives at M[j][i] --------------------------------
-    const int j = tid >> 2, l = tid & 3;
-    for (int i = 1; i < nb; ++i) {
-      double sx = 0.0, sy = 0.0;
-      if (j < i) {
-        const cplx* Li = M + i * ld;   // L[i][k], k < i
-        const cplx* Xj = M + j * ld;   // X[k][j] at M[j][k], k > j; X[j][j] = invd[j]
-        for (int k = j + l; k < i; k += 4) {
-          const cplx a = Li[k];
-          const cplx x = k == j ? cmake(invd[j], 0.0) : Xj[k];
-          sx += a.x * x.x - a.y * x.y;
-          sy += a.x * x.y + a.y * x.x;
-        }
-      }
-      sx += __shfl_xor_sync(0xffffffffu, sx, 1);
-      sy += __shfl_xor_sync(0xffffffffu, sy, 1);
-      sx += __shfl_xor_sync(0xffffffffu, sx, 2);
-      sy += __shfl_xor_sync(0xffffffffu, sy, 2);
-      if (j < i && l == 0) {
-        const double s = -invd[i];
-        M[j * ld + i] = cmake(sx * s, sy * s);
-      }
-      __syncthreads();
     }
   }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) rmax = max(rmax, __shfl_xor_sync(0xffffffffu, rmax, o));
+  sync();
+  for (int j = 0; j < nb - 1; j += 2) {
+    if (rmax > j) cf_step<EPT, NCTA, 0>(j, nb, pitch, v, af, wf, ua, ub, Ub, dvec);
+    sync();
+    if (j + 1 < nb - 1) {
+      if (rmax > j + 1) cf_step<EPT, NCTA, 1>(j + 1, nb, pitch, v, af, wf, ua, ub, Ub, dvec);
+      sync();
+    }
+  }
+  tick(2);
+  // L = L~ D^1/2, L^-1 = D^-1/2 W:  Rt[c][r] = conj(L[r][c]) = conj(a_rc) / sqrt(d_c),
+  // Rit[c][r] = conj(X[r][c]) = conj(W[r][c]) / sqrt(d_r)
+#pragma unroll
+  for (int q = 0; q < EPT; ++q) {
+    const int e = (gw * EPT + q) * 32 + lane;
+    if (e < ntri) {
+      const int r = ua[q] >> 4, c = ub[q] >> 4;
+      const double dc = dvec[c];
+      if (r == c) {
+        if (!(dc > 0.0)) atomicExch(fail_flag, 1);
+        const double l = sqrt(dc > 0.0 ? dc : 1.0);
+        Rt[(long long)r * nb + r] = cmake(l, 0.0);
+        Rit[(long long)r * nb + r] = cmake(1.0 / l, 0.0);
+      } else {
+        const double dr = dvec[r];
+        const double sc = rsqrt(dc > 0.0 ? dc : 1.0), sr = rsqrt(dr > 0.0 ? dr : 1.0);
+        Rt[(long long)c * nb + r] = cmake(af[q].x * sc, -af[q].y * sc);
+        Rit[(long long)c * nb + r] = cmake(wf[q].x * sr, -wf[q].y * sr);
+        Rt[(long long)r * nb + c] = cmake(0.0, 0.0);
+        Rit[(long long)r * nb + c] = cmake(0.0, 0.0);
+      }
+    }
+  }
+  tick(3);
+}
 
-  // ---- outputs: R2 = L^H: R[a][b] = conj(M[b][a]) (a < b), R[a][a] = dvec[a];
-  //      R^-1 = X^H: Rinv[a][b] = conj(X[b][a]) = conj(M[a][b]) (a < b), Rinv[a][a] = invd[a]
-  for (int e = tid; e < nb * nb; e += FS_T) {
-    const int a = e / nb, b = e - a * nb;
-    cplx r = cmake(0.0, 0.0), ri = cmake(0.0, 0.0);
-    if (a < b) {
-      r = cconj(M[b * ld + a]);
-      ri = cconj(M[a * ld + b]);
-    } else if (a == b) {
-      r = cmake(dvec[a], 0.0);
-      ri = cmake(invd[a], 0.0);
-    }
-    Rt[off + e] = r;
-    Rit[off + e] = ri;
+// Second Cholesky-QR pass: r = R2 R1, rinv = R1^-1 R2^-1 (all upper triangular, k over [a, b]); a CTA
+// owns 8 rows of one matrix: its rows of R2 and R1^-1 (the operands every lane of a row shares)
+// sit in shared memory, R1 and R2^-1 stream from L2 coalesced along the output columns.
+// grid: (ceil(nb / 8), nsk), block 256 = 8 rows x 32 column lanes; dynamic smem: 2 * 8 * nb complex
+__global__ void __launch_bounds__(256)
+k_compose_rows(const cplx* __restrict__ R2, const cplx* __restrict__ R2inv,
+               const cplx* __restrict__ R1, const cplx* __restrict__ R1inv, int nb,
+               cplx* __restrict__ r_out, cplx* __restrict__ rinv_out) {
+  extern __shared__ __align__(16) unsigned char smem_raw_[];
+  cplx* s2 = reinterpret_cast<cplx*>(smem_raw_);  // [8][nb] rows of R2
+  cplx* s1i = s2 + 8 * nb;                        // [8][nb] rows of R1^-1
+  const long long off = (long long)blockIdx.y * nb * nb;
+  const int a0 = blockIdx.x * 8;
+  for (int e = threadIdx.x; e < 8 * nb; e += 256) {
+    const int al = e / nb, k = e - al * nb;
+    const bool ok = a0 + al < nb;
+    s2[e] = ok ? R2[off + (long long)(a0 + al) * nb + k] : cmake(0.0, 0.0);
+    s1i[e] = ok ? R1inv[off + (long long)(a0 + al) * nb + k] : cmake(0.0, 0.0);
   }
-  if (PASS2) {
-    // r = R2 R1, rinv = R1^-1 R2^-1 (all upper triangular): k runs over [a, b]
-    for (int e = tid; e < nb * nb; e += FS_T) {
-      const int a = e / nb, b = e - a * nb;
-      cplx x = cmake(0.0, 0.0), y = cmake(0.0, 0.0);
-      if (b >= a) {
-        for (int k = a; k <= b; ++k) {
-          const cplx r2 = k == a ? cmake(dvec[a], 0.0) : cconj(M[k * ld + a]);
-          const cplx u = cmul(r2, R1[off + (long long)k * nb + b]);
-          x.x += u.x; x.y += u.y;
-          const cplx r2i = k == b ? cmake(invd[b], 0.0) : cconj(M[k * ld + b]);
-          const cplx w = cmul(R1inv[off + (long long)a * nb + k], r2i);
-          y.x += w.x; y.y += w.y;
-        }
+  __syncthreads();
+  const int al = threadIdx.x >> 5, lane = threadIdx.x & 31, a = a0 + al;
+  if (a >= nb) return;
+  const cplx* r2 = s2 + al * nb;
+  const cplx* r1i = s1i + al * nb;
+  for (int b = lane; b < nb; b += 32) {
+    double xx = 0.0, xy = 0.0, yx = 0.0, yy = 0.0;
+    if (b >= a) {
+      const cplx* c1 = R1 + off + b;      // R1[k][b] = c1[k nb]
+      const cplx* c2i = R2inv + off + b;  // R2inv[k][b]
+#pragma unroll 4
+      for (int k = a; k <= b; ++k) {
+        const cplx u = r2[k], w = c1[(long long)k * nb];
+        xx += u.x * w.x - u.y * w.y;
+        xy += u.x * w.y + u.y * w.x;
+        const cplx p = r1i[k], q = c2i[(long long)k * nb];
+        yx += p.x * q.x - p.y * q.y;
+        yy += p.x * q.y + p.y * q.x;
       }
-      r_out[off + e] = x;
-      rinv_out[off + e] = y;
     }
+    r_out[off + (long long)a * nb + b] = cmake(xx, xy);
+    rinv_out[off + (long long)a * nb + b] = cmake(yx, yy);
   }
 }
 
@@ -879,6 +984,86 @@ int launch_hamiltonian_matrix(jrb_plan* p, const cplx* q, const cplx* hq, cplx* 
   return 0;
 }
 
+// Configuration of k_factor_stream for nb bands: slots per thread and CTAs per matrix (0 = use
+// the multi-launch kernels).  One CTA while the lower triangle fits 6 registers-slots per thread
+// (nb <= 77), else a cluster of 8 (nb <= 221).
+struct CfConfig {
+  int ept, ncta;
+};
+static CfConfig cf_config(int nb) {
+  static int off = [] {
+    const char* env = std::getenv("JRB_NO_FUSED_SMALL");
+    return env ? std::atoi(env) : 0;
+  }();
+  const int ntri = nb * (nb + 1) / 2;
+  if (off) return {0, 0};
+  static int cluster = [] {
+    const char* env = std::getenv("JRB_FACTOR_CLUSTER");  // tuning aid: 8-CTA clusters for nb > 77
+    return env ? std::atoi(env) : 0;
+  }();
+  if (ntri <= 2 * CF_T) return {2, 1};
+  if (ntri <= 5 * CF_T) return {5, 1};
+  if (ntri <= 6 * CF_T) return {6, 1};
+  if (cluster && ntri <= 6 * CF_T * 8) return {6, 8};
+  return {0, 0};
+}
+
+template <int EPT, int NCTA, bool PASS2>
+static int run_factor_stream(jrb_plan* p, int nsk, const cplx* S, double tol, cplx* Rt, cplx* Rit,
+                             const int* skip, cudaStream_t st) {
+  int* fail = reinterpret_cast<int*>(p->d_scal + 32);
+  static int timing = std::getenv("JRB_FS_TIMING") ? std::atoi(std::getenv("JRB_FS_TIMING")) : 0;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(nsk * NCTA);
+  cfg.blockDim = dim3(CF_T);
+  cfg.dynamicSmemBytes = cf_smem_bytes(p->nb);
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = NCTA;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  const int nb = p->nb;
+  JRB_CUDA(cudaLaunchKernelEx(&cfg, k_factor_stream<EPT, NCTA, PASS2>, S, nb, tol, Rt, Rit, fail,
+                              skip, timing));
+  JRB_CHECK_LAUNCH("k_factor_stream");
+  if (timing) {
+    long long h[8];
+    cudaStreamSynchronize(st);
+    cudaMemcpyFromSymbol(h, g_fs_clocks, sizeof(h));
+    fprintf(stderr, "k_factor_stream<%d,%d,%d> nb %d cycles: scan %lld sweep %lld out %lld total %lld\n",
+            EPT, NCTA, (int)PASS2, nb, h[1] - h[0], h[2] - h[1], h[3] - h[2], h[3] - h[0]);
+  }
+  return 0;
+}
+
+// pass2: the single-CTA variants also test for the near-identity closed form (tol > 0)
+static int factor_stream(jrb_plan* p, CfConfig c, bool pass2, int nsk, const cplx* S, double tol,
+                         cplx* Rt, cplx* Rit, const int* skip, cudaStream_t st) {
+  if (c.ncta == 8) return run_factor_stream<6, 8, false>(p, nsk, S, 0.0, Rt, Rit, skip, st);
+  if (c.ept == 2)
+    return pass2 ? run_factor_stream<2, 1, true>(p, nsk, S, tol, Rt, Rit, skip, st)
+                 : run_factor_stream<2, 1, false>(p, nsk, S, 0.0, Rt, Rit, skip, st);
+  if (c.ept == 5)
+    return pass2 ? run_factor_stream<5, 1, true>(p, nsk, S, tol, Rt, Rit, skip, st)
+                 : run_factor_stream<5, 1, false>(p, nsk, S, 0.0, Rt, Rit, skip, st);
+  return pass2 ? run_factor_stream<6, 1, true>(p, nsk, S, tol, Rt, Rit, skip, st)
+               : run_factor_stream<6, 1, false>(p, nsk, S, 0.0, Rt, Rit, skip, st);
+}
+
+static int compose_rows(jrb_plan* p, int nsk, const cplx* R2, const cplx* R2inv, const cplx* R1,
+                        const cplx* R1inv, cplx* r_out, cplx* rinv_out, cudaStream_t st) {
+  const int nb = p->nb;
+  const int smem = 2 * 8 * nb * (int)sizeof(cplx);
+  static int once = opt_in_smem(k_compose_rows, 160 * 1024);
+  if (once) return once;
+  k_compose_rows<<<dim3((nb + 7) / 8, nsk), 256, smem, st>>>(R2, R2inv, R1, R1inv, nb, r_out, rinv_out);
+  JRB_CHECK_LAUNCH("k_compose_rows");
+  return 0;
+}
+
 // Above this size the per-matrix recurrences are spread over several CTAs (more launches, far
 // less latency); below it one CTA per (spin,k) with batch parallelism is the better shape.
 static int large_nb_threshold() {
@@ -932,6 +1117,8 @@ static int chol_and_inverse(jrb_plan* p, int nsk, cplx* S, cplx* Rt, cplx* Rit, 
                             const int* skip = nullptr) {
   const int nb = p->nb;
   int* fail = reinterpret_cast<int*>(p->d_scal + 32);
+  const CfConfig cf = cf_config(nb);
+  if (cf.ept) return factor_stream(p, cf, false, nsk, S, 0.0, Rt, Rit, skip, st);
   if (multi_cta_small(nb, nsk)) {
     for (int p0 = 0; p0 < nb; p0 += CP) {
       const int below = std::max(0, nb - p0 - CP);
@@ -953,34 +1140,6 @@ static int chol_and_inverse(jrb_plan* p, int nsk, cplx* S, cplx* Rt, cplx* Rit, 
   k_chol_blocked<<<nsk, CHOL_T, smem, st>>>(S, Rt, nb, fail, skip);
   JRB_CHECK_LAUNCH("k_chol_blocked");
   return tri_inverse(Rt, nb, nsk, Rit, st, skip);
-}
-
-// The one-launch shared-memory chain (k_small_factor) serves matrices whose lower triangle fits the
-// registers of one CTA and whose square fits shared memory.
-static int small_fused_ept(int nb) {
-  static int off = [] {
-    const char* env = std::getenv("JRB_NO_FUSED_SMALL");
-    return env ? std::atoi(env) : 0;
-  }();
-  if (off) return 0;
-  const int ntri = nb * (nb + 1) / 2;
-  if (fs_smem_bytes(nb) > 200 * 1024) return 0;
-  if (ntri <= 5 * FS_T) return 5;
-  if (ntri <= 14 * FS_T) return 14;
-  return 0;
-}
-
-template <int EPT, bool PASS2>
-static int run_small_factor(jrb_plan* p, int nsk, const cplx* S, double tol, cplx* Rt, cplx* Rit,
-                            const cplx* R1, const cplx* R1inv, cplx* r_out, cplx* rinv_out,
-                            cudaStream_t st) {
-  static int once = opt_in_smem(k_small_factor<EPT, PASS2>, 200 * 1024);
-  if (once) return once;
-  int* fail = reinterpret_cast<int*>(p->d_scal + 32);
-  k_small_factor<EPT, PASS2><<<nsk, FS_T, fs_smem_bytes(p->nb), st>>>(S, p->nb, tol, Rt, Rit, R1,
-                                                                     R1inv, r_out, rinv_out, fail);
-  JRB_CHECK_LAUNCH("k_small_factor");
-  return 0;
 }
 
 // Cholesky-QR2 of the (spin,k) range [sk0, sk0 + nsk), in phases so that a row-sharded caller can
@@ -1024,30 +1183,21 @@ int launch_qr_apply_phase(jrb_plan* p, int sk0, int nsk, const double* w_re, con
   const int nb = p->nb;
   int rc = 0;
   TallMat none{nullptr, nullptr, 0};
-  const int ept = small_fused_ept(nb);
+  const CfConfig cf = cf_config(nb);
   if (pass == 0) {
     TallMat W{w_re + q.soff, w_im + q.soff, nb};
-    if (ept == 5)
-      rc = run_small_factor<5, false>(p, nsk, S, 0.0, q.R1, q.R1inv, nullptr, nullptr, nullptr, nullptr, st);
-    else if (ept == 14)
-      rc = run_small_factor<14, false>(p, nsk, S, 0.0, q.R1, q.R1inv, nullptr, nullptr, nullptr, nullptr, st);
-    else
-      rc = chol_and_inverse(p, nsk, S, q.R1, q.R1inv, st);
-    if (rc) return rc;
+    if ((rc = chol_and_inverse(p, nsk, S, q.R1, q.R1inv, st))) return rc;
     return run_apply<0>(p, nsk, W, q.R1inv, TRI_UPPER, none, nullptr, TRI_FULL, 1,
                         reinterpret_cast<double*>(q.tmp), nullptr, st);
   }
   TallMat Q1{reinterpret_cast<const double*>(q.tmp), nullptr, nb};
   const char* no_shortcut = std::getenv("JRB_NO_QR_SHORTCUT");
   const bool shortcut = !(no_shortcut && std::atoi(no_shortcut) != 0);
-  if (ept) {
-    // one launch: closed form or factorisation, inverse, and the composition with the first pass
-    const double tol = shortcut ? 1e-10 : 0.0;
-    if (ept == 5)
-      rc = run_small_factor<5, true>(p, nsk, S, tol, q.Rt, q.Rit, q.R1, q.R1inv, r + q.moff, q.rinv, st);
-    else
-      rc = run_small_factor<14, true>(p, nsk, S, tol, q.Rt, q.Rit, q.R1, q.R1inv, r + q.moff, q.rinv, st);
-    if (rc) return rc;
+  if (cf.ncta == 1) {
+    // one launch: closed form or factorisation + inverse; then the composition with the first pass
+    if ((rc = factor_stream(p, cf, true, nsk, S, shortcut ? 1e-10 : 0.0, q.Rt, q.Rit, nullptr, st)))
+      return rc;
+    if ((rc = compose_rows(p, nsk, q.Rt, q.Rit, q.R1, q.R1inv, r + q.moff, q.rinv, st))) return rc;
     return run_apply<0>(p, nsk, Q1, q.Rit, TRI_UPPER, none, nullptr, TRI_FULL, 1,
                         reinterpret_cast<double*>(qout + q.soff), nullptr, st);
   }
