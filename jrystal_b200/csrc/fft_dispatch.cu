@@ -125,6 +125,20 @@ static FusedArgs fused_args(jrb_plan* p, const PassArgs& a) {
   f.band_limited = p->band_limited;
   if (const char* env = std::getenv("JRB_NO_SPARSE"))
     if (std::atoi(env) != 0) f.band_limited = 0;
+  // TMA staging: which tensor map covers a.wa, and the row (16 doubles = 8 bands) it starts at
+  f.tmap = nullptr;
+  f.row0 = 0;
+  if (p->d_tmaps) {
+    const char* maps = static_cast<const char*>(p->d_tmaps);
+    const long long keep_elems = (long long)p->ns * p->nk * p->ngroups_per_k * p->a_group_elems;
+    if (p->d_a_keep && a.wa >= p->d_a_keep && a.wa < p->d_a_keep + keep_elems) {
+      f.tmap = maps + 128;
+      f.row0 = (a.wa - p->d_a_keep) / NB;
+    } else if (a.wa >= p->d_ws_a && a.wa < p->d_ws_a + p->a_copy_elems) {
+      f.tmap = maps;
+      f.row0 = (a.wa - p->d_ws_a) / NB;
+    }
+  }
   return f;
 }
 

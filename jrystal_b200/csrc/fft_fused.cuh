@@ -4,8 +4,13 @@
 // columns, 2-5 % of the box).  Work item = (z-plane, band group); the CTAs are persistent and
 // split the z-major item list evenly (grid = resident CTA slots, so every SM is busy to the
 // end).  Band by band a CTA runs
-//   stage  : cp.async (LDGSTS) of the NEXT band's plane columns into a shared-memory staging
-//            buffer while the current band is being transformed (no exposed global latency)
+//   stage  : the NEXT band's plane columns arrive in a shared-memory staging buffer while the
+//            current band is being transformed (no exposed global latency): one elected thread
+//            issues TMA tensor copies (cp.async.bulk.tensor.2d: a box of {one band = 16 bytes,
+//            256 columns} of the 2-D view [rows = (group, z, column)][8 bands] of the column work
+//            space lands as 256 consecutive complex numbers, i.e. the band is de-interleaved on
+//            the way in) that complete on an mbarrier; the fallback (JRB_NO_TMA=1, or no tensor
+//            map) is one cp.async (LDGSTS) per column and thread
 //   y stage: y-transforms the occupied x planes into a shared-memory slab Y[xo][y]
 //   x stage: zero-pads the occupied x entries to nx, x-transforms every y line and
 //     k_yx_density : accumulates f |psi|^2 in registers (a thread owns the same (x, y) points
@@ -43,6 +48,10 @@ struct FusedArgs {
   int g0, ngroups;     // first global group id, number of groups in the batch
   double vscale;
   int band_limited;    // every occupied x and y index lies in [0, 2 RB) u [n - 2 RB, n)
+  // TMA staging: tensor map (in global memory) of the buffer `wa` points into, viewed as
+  // [rows of 8 bands][16 doubles], and the row of wa[0]; null = cp.async staging
+  const void* tmap;
+  long long row0;
 };
 
 // butterfly slots that can be non-zero for band-limited data (see dft_small.cuh)
@@ -72,7 +81,8 @@ struct FCfg {
   static constexpr int EXCH = SLOTS * N * NB;          // exchange buffers (complex)
   // shared memory (complex numbers): 2 Y slabs, exchange buffers, 2 staging buffers
   static JRB_HD int ybuf_elems(int nxo) { return nxo * SX; }
-  static JRB_HD int stage_elems(int ncol) { return (ncol + 7) / 8 * 8; }
+  // staging buffers hold whole TMA boxes of 256 columns (the tail box is filled past ncol)
+  static JRB_HD int stage_elems(int ncol) { return (ncol + 255) / 256 * 256; }
   static JRB_HD int smem_bytes(int nxo, int ncol) {
     return (2 * ybuf_elems(nxo) + EXCH + 2 * stage_elems(ncol)) * (int)sizeof(cplx);
   }
@@ -131,16 +141,80 @@ __device__ __forceinline__ cplx* band_plane(const FusedArgs& a, const BandPos& p
   return a.wa + (long long)(p.gl * a.m.nz + p.z) * (a.m.ncol * NB) + p.band;
 }
 
-// stage the plane columns of one band: stage[col] = A[gl][z][col][band]
+// ---- mbarrier + TMA (cp.async.bulk.tensor) helpers ---------------------------------------
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, int count) {
+  const unsigned b = (unsigned)__cvta_generic_to_shared(bar);
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(b), "r"(count));
+}
+__device__ __forceinline__ void mbar_fence_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(unsigned long long* bar, unsigned bytes) {
+  const unsigned b = (unsigned)__cvta_generic_to_shared(bar);
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(b), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
+  const unsigned b = (unsigned)__cvta_generic_to_shared(bar);
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(b) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+  const unsigned b = (unsigned)__cvta_generic_to_shared(bar);
+  asm volatile(
+    "{\n"
+    ".reg .pred p;\n"
+    "WAIT_%=:\n"
+    "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+    "@p bra DONE_%=;\n"
+    "bra WAIT_%=;\n"
+    "DONE_%=:\n"
+    "}\n" ::"r"(b),
+    "r"(parity)
+    : "memory");
+}
+// box {2 doubles, 256 rows} at (c0, c1) of the 2-D tensor -> 256 consecutive complex numbers
+__device__ __forceinline__ void tma_load_box(void* smem_dst, const void* tmap, int c0, int c1,
+                                             unsigned long long* bar) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  const unsigned b = (unsigned)__cvta_generic_to_shared(bar);
+  asm volatile(
+    "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, "
+    "{%2, %3}], [%4];\n" ::"r"(d),
+    "l"(tmap), "r"(c0), "r"(c1), "r"(b)
+    : "memory");
+}
+
+// stage the plane columns of one band: stage[col] = A[gl][z][col][band].  TMA: thread 0 arms the
+// buffer's mbarrier with the byte count and issues one box per 256 columns (nothing to stage:
+// a plain arrive, so that every stage is matched by exactly one completed phase).
 template <int NT>
 __device__ __forceinline__ void fused_stage(const FusedArgs& a, const BandPos& p, int w_end,
-                                            cplx* stage) {
+                                            cplx* stage, unsigned long long* bar) {
+  if (a.tmap) {
+    if (threadIdx.x == 0) {
+      if (p.w < w_end) {
+        const int nbox = (a.m.ncol + 255) >> 8;
+        mbar_arrive_expect_tx(bar, (unsigned)(nbox * 256 * sizeof(cplx)));
+        const int row = (int)(a.row0 + (long long)(p.gl * a.m.nz + p.z) * a.m.ncol);
+        for (int b = 0; b < nbox; ++b) tma_load_box(stage + 256 * b, a.tmap, 2 * p.band, row + 256 * b, bar);
+      } else {
+        mbar_arrive(bar);
+      }
+    }
+    return;
+  }
   if (p.w < w_end) {
     const cplx* src = band_plane(a, p);
     for (int c = threadIdx.x; c < a.m.ncol; c += NT)
       fused_cp_async16(stage + c, src + (long long)c * NB);
   }
   fused_cp_commit();
+}
+// the staged band of `bar`'s buffer has landed (TMA: phase `parity` of its mbarrier)
+__device__ __forceinline__ void fused_stage_wait(const FusedArgs& a, unsigned long long* bar,
+                                                 unsigned parity) {
+  if (a.tmap) mbar_wait(bar, parity);
+  else fused_cp_wait_all();
 }
 
 // y stage, inverse: staged columns of one band-plane -> Y[xo][y].  All threads call it.
@@ -212,17 +286,25 @@ __global__ void __launch_bounds__(FCfg<N>::NT, (FCfg<N>::NT <= 256 ? 2 : 1))
 k_yx_density(FusedArgs a) {
   using F = LineFFT<N, +1>;
   using C = FCfg<N>;
-  extern __shared__ __align__(16) unsigned char smem_raw_[];
-  cplx* ybuf0 = reinterpret_cast<cplx*>(smem_raw_);
+  extern __shared__ __align__(128) unsigned char smem_fused_[];
+  __shared__ __align__(8) unsigned long long sbar[2];
+  // staging buffers first: TMA destinations (whole 4 KB boxes from a 128-byte aligned base)
+  cplx* stage0 = reinterpret_cast<cplx*>(smem_fused_);
+  const int ssz = C::stage_elems(a.m.ncol);
+  cplx* ybuf0 = stage0 + 2 * ssz;
   const int ysz = C::ybuf_elems(a.m.nxo);
   cplx* exbase = ybuf0 + 2 * ysz;
-  cplx* stage0 = exbase + C::EXCH;
-  const int ssz = C::stage_elems(a.m.ncol);
   const int t = threadIdx.x;
   const int lane = t % NB;
   const int tj = (t / NB) % C::TPL;
   const int slot = t / C::SLOT_THREADS;
   cplx* ex = exbase + (size_t)slot * N * NB + lane;
+  if (a.tmap && t == 0) {
+    mbar_init(&sbar[0], 1);
+    mbar_init(&sbar[1], 1);
+    mbar_fence_init();
+  }
+  unsigned sph0 = 0, sph1 = 0;  // phase of each staging buffer's mbarrier
   cplx tw[F::CB][F::NTW];
   F::load_twiddles(tw, a.tw, tj);
 
@@ -274,12 +356,14 @@ k_yx_density(FusedArgs a) {
     ++seg;
   };
 
+  __syncthreads();  // mbarriers initialised
   if (cur.w < w_end) {
     // prologue: stage band 0, run its y stage, stage band 1
-    fused_stage<C::NT>(a, cur, w_end, stage0);
-    fused_cp_wait_all();
+    fused_stage<C::NT>(a, cur, w_end, stage0, &sbar[0]);
+    fused_stage_wait(a, &sbar[0], sph0);
+    sph0 ^= 1;
     __syncthreads();
-    fused_stage<C::NT>(a, band_next(a, cur, w_end, gmod0), w_end, stage0 + ssz);
+    fused_stage<C::NT>(a, band_next(a, cur, w_end, gmod0), w_end, stage0 + ssz, &sbar[1]);
     fused_y_inverse<N, ONE_ITER, SP>(a, stage0, ybuf0, ex, tw, pk, lane, tj, slot);
     int par = 0;  // parity of the current band: it lives in Y[par]
     int cur_z = cur.z;
@@ -287,11 +371,12 @@ k_yx_density(FusedArgs a) {
     while (cur.w < w_end) {
       // Y[par] complete (y stage of the current band by every slot); staged data of the next
       // band landed and visible; everybody is done with Y[par ^ 1] and stage[par]
-      fused_cp_wait_all();
+      if (par) { fused_stage_wait(a, &sbar[0], sph0); sph0 ^= 1; }
+      else { fused_stage_wait(a, &sbar[1], sph1); sph1 ^= 1; }
       __syncthreads();
       // band b+1 is staged in stage[par ^ 1]; prefetch band b+2 into stage[par]
       const BandPos nxt = band_next(a, cur, w_end, gmod0);
-      fused_stage<C::NT>(a, band_next(a, nxt, w_end, gmod0), w_end, stage0 + par * ssz);
+      fused_stage<C::NT>(a, band_next(a, nxt, w_end, gmod0), w_end, stage0 + par * ssz, &sbar[par]);
       if (cur.z != cur_z) {
         flush(cur_z);
         cur_z = cur.z;
@@ -334,7 +419,7 @@ k_yx_density(FusedArgs a) {
       cur = nxt;
       par ^= 1;
     }
-    fused_cp_wait_all();
+    if (!a.tmap) fused_cp_wait_all();
     flush(cur_z);
   }
   if (t == 0)
@@ -377,17 +462,24 @@ k_yx_vmul(FusedArgs a) {
   using FF = LineFFT<N, -1>;
   using C = FCfg<N>;
   static_assert(FI::CB == FF::CA && FI::RB == FF::RA, "register chaining contract");
-  extern __shared__ __align__(16) unsigned char smem_raw_[];
-  cplx* ybuf0 = reinterpret_cast<cplx*>(smem_raw_);
+  extern __shared__ __align__(128) unsigned char smem_fused_[];
+  __shared__ __align__(8) unsigned long long sbar[2];
+  cplx* stage0 = reinterpret_cast<cplx*>(smem_fused_);
+  const int ssz = C::stage_elems(a.m.ncol);
+  cplx* ybuf0 = stage0 + 2 * ssz;
   const int ysz = C::ybuf_elems(a.m.nxo);
   cplx* exbase = ybuf0 + 2 * ysz;
-  cplx* stage0 = exbase + C::EXCH;
-  const int ssz = C::stage_elems(a.m.ncol);
   const int t = threadIdx.x;
   const int lane = t % NB;
   const int tj = (t / NB) % C::TPL;
   const int slot = t / C::SLOT_THREADS;
   cplx* ex = exbase + (size_t)slot * N * NB + lane;
+  if (a.tmap && t == 0) {
+    mbar_init(&sbar[0], 1);
+    mbar_init(&sbar[1], 1);
+    mbar_fence_init();
+  }
+  unsigned sph0 = 0, sph1 = 0;
   const long long nyz = (long long)N * a.m.nz;
   // equal radices: the forward twiddles are the conjugates of the inverse ones -> one register set
   constexpr bool SHARE_TW = LinePlan<N>::r1 == LinePlan<N>::r2;
@@ -451,20 +543,23 @@ k_yx_vmul(FusedArgs a) {
   const int w_end = (int)((c + 1) * W / G);
   const int gmod0 = a.g0 % a.ngpk;
   BandPos cur = band_first(a, (int)(c * W / G));
+  __syncthreads();  // mbarriers initialised
   if (cur.w >= w_end) return;
-  fused_stage<C::NT>(a, cur, w_end, stage0);
-  fused_cp_wait_all();
+  fused_stage<C::NT>(a, cur, w_end, stage0, &sbar[0]);
+  fused_stage_wait(a, &sbar[0], sph0);
+  sph0 ^= 1;
   __syncthreads();
-  fused_stage<C::NT>(a, band_next(a, cur, w_end, gmod0), w_end, stage0 + ssz);
+  fused_stage<C::NT>(a, band_next(a, cur, w_end, gmod0), w_end, stage0 + ssz, &sbar[1]);
   fused_y_inverse<N, ONE_ITER, SP>(a, stage0, ybuf0, ex, twi, pk, lane, tj, slot);
   int par = 0;
   int cur_z = cur.z;
   load_v(cur_z);
   while (cur.w < w_end) {
-    fused_cp_wait_all();
+    if (par) { fused_stage_wait(a, &sbar[0], sph0); sph0 ^= 1; }
+    else { fused_stage_wait(a, &sbar[1], sph1); sph1 ^= 1; }
     __syncthreads();
     const BandPos nxt = band_next(a, cur, w_end, gmod0);
-    fused_stage<C::NT>(a, band_next(a, nxt, w_end, gmod0), w_end, stage0 + par * ssz);
+    fused_stage<C::NT>(a, band_next(a, nxt, w_end, gmod0), w_end, stage0 + par * ssz, &sbar[par]);
     if (cur.z != cur_z) {
       cur_z = cur.z;
       load_v(cur_z);
@@ -553,7 +648,7 @@ k_yx_vmul(FusedArgs a) {
     cur = nxt;
     par ^= 1;
   }
-  fused_cp_wait_all();
+  if (!a.tmap) fused_cp_wait_all();
 }
 
 // ---------------------------------------------------------------------------------------

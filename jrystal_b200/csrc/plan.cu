@@ -11,6 +11,8 @@
 #include <vector>
 
 #include "fft_passes.cuh"
+#include <cuda.h>
+
 #include "plan.h"
 
 namespace jrb {
@@ -109,6 +111,51 @@ extern "C" int64_t jrb_launch_count(void) { return jrb::launch_count(); }
 extern "C" int64_t jrb_plan_num_g(const jrb_plan* p) { return p ? p->ng : -1; }
 extern "C" int64_t jrb_plan_workspace_bytes(const jrb_plan* p) { return p ? p->ws_bytes : -1; }
 
+
+// ---- TMA tensor maps of the column work space ------------------------------------------------
+// The fused y+x kernels stage one band of one z-plane: the 16-byte entries [col][band] of the
+// plane's [ncol][8 bands] block.  As a 2-D FP64 tensor {16 doubles, rows} with a 128-byte row pitch
+// that is the box {2 doubles, 256 rows}, which cp.async.bulk.tensor.2d lands as 256 consecutive
+// complex numbers.  cuTensorMapEncodeTiled comes from the driver through the runtime's entry-point
+// query, so the library still links libcudart only.
+typedef CUresult (*jrb_encode_tiled_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                        const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                        const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                        CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static bool encode_column_map(void* base, unsigned long long rows, CUtensorMap* out) {
+  static jrb_encode_tiled_fn fn = [] {
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) != cudaSuccess ||
+        q != cudaDriverEntryPointSuccess)
+      f = nullptr;
+    return reinterpret_cast<jrb_encode_tiled_fn>(f);
+  }();
+  if (!fn || !base || rows == 0 || rows >= (1ull << 31)) return false;
+  const cuuint64_t dims[2] = {16, rows};
+  const cuuint64_t strides[1] = {128};  // bytes between rows
+  const cuuint32_t box[2] = {2, 256};
+  const cuuint32_t estr[2] = {1, 1};
+  return fn(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, base, dims, strides, box, estr,
+            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+// d_tmaps[0]: d_ws_a, d_tmaps[1]: d_a_keep (fused == 1 plans; JRB_NO_TMA=1 keeps cp.async)
+static int make_tensor_maps(jrb_plan* p, long long ws_rows, long long keep_rows) {
+  if (const char* env = std::getenv("JRB_NO_TMA"))
+    if (std::atoi(env) != 0) return 0;
+  if (p->fused != 1) return 0;
+  alignas(64) CUtensorMap maps[2];
+  std::memset(maps, 0, sizeof(maps));
+  if (!encode_column_map(p->d_ws_a, (unsigned long long)ws_rows, &maps[0])) return 0;
+  if (p->d_a_keep && !encode_column_map(p->d_a_keep, (unsigned long long)keep_rows, &maps[1])) return 0;
+  JRB_CUDA(cudaMalloc(&p->d_tmaps, sizeof(maps)));
+  JRB_CUDA(cudaMemcpy(p->d_tmaps, maps, sizeof(maps), cudaMemcpyHostToDevice));
+  return 0;
+}
+
 extern "C" int jrb_plan_destroy(jrb_plan* p) {
   if (!p) return 0;
   cudaSetDevice(p->device);
@@ -116,6 +163,7 @@ extern "C" int jrb_plan_destroy(jrb_plan* p) {
   p->wf = nullptr;
   comm_destroy(p);
   if (p->d_rho_w) cudaFree(p->d_rho_w);
+  if (p->d_tmaps) cudaFree(p->d_tmaps);
   delete[] p->h_freq;
   delete[] p->h_kpts;
   void* ptrs[] = {p->d_zmap, p->d_ycol, p->d_xmap, p->d_gidx, p->d_gk2, p->d_tw_x, p->d_tw_y,
@@ -383,6 +431,7 @@ static int plan_create_impl(const jrb_plan_desc* d, bool orbital_only, jrb_plan*
     if (p->fused && need_mb <= cap_mb) TRY(dev_alloc(&p->d_a_keep, a_per_group * total_groups, &tot));
   }
   TRY(dev_alloc(&p->d_ws_a, a_per_group * bg * (p->fused == 2 ? 3 : 1), &tot));
+  TRY(make_tensor_maps(p, (long long)bg * nz * ncol, (long long)total_groups * nz * ncol));
   TRY(dev_alloc(&p->d_ws_b, p->fused ? 1 : b_per_group * bg, &tot));
   TRY(dev_alloc(&p->d_rho_part,
                 p->fused ? (size_t)p->fused_ctas * p->fused_segmax * nx * ny / (p->fused == 2 ? 2 : 1) : 1,

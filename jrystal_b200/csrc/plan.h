@@ -70,6 +70,9 @@ struct jrb_plan {
                       // 2: the 128 x 128 variant (fft_fused128.cuh)
   int band_limited32; // occupied x and y indices all in [0, 32) u [n - 32, n)
   jrb::cplx* d_tw_half;  // exp(-2 pi i t / (nx / 2)) (fused == 2)
+  // TMA tensor maps (two CUtensorMap objects in device memory) of d_ws_a and d_a_keep viewed as
+  // [rows = (group, z, column)][8 bands x (re, im)] doubles; null: cp.async staging (plan.cu)
+  void* d_tmaps;
   int fused_ctas;     // persistent CTAs of the fused kernels (resident slots)
   int band_limited;   // occupied x and y indices all in [0, 16) u [n - 16, n) (sparse radix-8 butterflies)
   int fused_segmax;   // partial density planes per CTA (upper bound over batch sizes)
