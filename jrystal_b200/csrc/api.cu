@@ -298,7 +298,8 @@ extern "C" int jrb_fft3d(jrb_plan* p, const double* in, double* out, int32_t dir
 // plan's communicator where it is smallest -- on the box the sweep ran on (the orbital grid),
 // before the Fourier interpolation onto the plan's grid -- together with e_kin.
 static int eval_begin_impl(jrb_plan* p, const double* w_re, const double* w_im, const double* occ,
-                           double* rho, double* e_kin, bool reduce, cudaStream_t st) {
+                           double* rho, double* e_kin, bool reduce, bool keep_rhohat,
+                           cudaStream_t st) {
   int rc = 0;
   JRB_CUDA(cudaMemsetAsync(p->d_scal + 32, 0, sizeof(double), st));  // Cholesky failure flag
   if ((rc = launch_qr_fwd(p, w_re, w_im, p->d_q, p->d_r, st))) return rc;
@@ -321,7 +322,8 @@ static int eval_begin_impl(jrb_plan* p, const double* w_re, const double* w_im, 
     const long long n = (long long)p->ns * (p->wf ? p->wf->ngrid : p->ngrid);
     if ((rc = launch_comm_allreduce(p, part, n, e_kin, 1, st))) return rc;
   }
-  return launch_density_end(p, rho, st);
+  // keep_rhohat: the interpolation leaves fftn(rho) in p->d_grid for the grid part that follows
+  return keep_rhohat ? launch_density_end_hat(p, rho, st) : launch_density_end(p, rho, st);
 }
 
 extern "C" int jrb_eval_begin(jrb_plan* p, const double* w_re, const double* w_im,
@@ -329,7 +331,7 @@ extern "C" int jrb_eval_begin(jrb_plan* p, const double* w_re, const double* w_i
   int rc = enter(p);
   if (rc) return rc;
   REQUIRE(w_re && w_im && occ && rho && e_kin, "null array");
-  return eval_begin_impl(p, w_re, w_im, occ, rho, e_kin, false, S(st));
+  return eval_begin_impl(p, w_re, w_im, occ, rho, e_kin, false, false, S(st));
 }
 
 __global__ void k_pack_energies(const double* e_kin, const double* grid_e, double* out) {
@@ -340,16 +342,21 @@ __global__ void k_pack_energies(const double* e_kin, const double* grid_e, doubl
   out[3] = grid_e[2];
 }
 
-extern "C" int jrb_eval_finish(jrb_plan* p, const double* occ, const double* rho,
-                               const double* e_kin, int32_t xc_id, double* energies, double* g_re,
-                               double* g_im, double* g_occ, jrb_stream st) {
-  int rc = enter(p);
-  if (rc) return rc;
-  REQUIRE(occ && rho && e_kin && energies && g_re && g_im, "null array");
+// rhohat_ready: p->d_grid holds fftn(rho) (eval_begin_impl with keep_rhohat just ran)
+static int eval_finish_impl(jrb_plan* p, const double* occ, const double* rho, const double* e_kin,
+                            int32_t xc_id, double* energies, double* g_re, double* g_im,
+                            double* g_occ, bool rhohat_ready, jrb_stream st) {
+  int rc = 0;
   double* grid_e = p->d_scal;            // E_H, E_ext, E_xc
   double* veff = p->d_veff;
   p->veff_prepared = 0;                  // d_veff is overwritten by this evaluation's potential
-  if ((rc = launch_grid_potential(p, rho, xc_id, 0, 7, grid_e, veff, S(st)))) return rc;
+  if (grid_fused_ok(p, xc_id)) {
+    // energies + v_eff straight onto the orbital box (each field transformed once)
+    if ((rc = launch_grid_potential_orbital(p, rho, rhohat_ready, xc_id, grid_e, S(st)))) return rc;
+    veff = nullptr;                      // H-apply with the potential now in the orbital plan
+  } else if ((rc = launch_grid_potential(p, rho, xc_id, 0, 7, grid_e, veff, S(st)))) {
+    return rc;
+  }
   p->keep_read = p->keep_filled;
   rc = launch_hpsi(p, p->d_q, veff, p->d_hq, S(st));
   p->keep_read = 0;
@@ -365,6 +372,15 @@ extern "C" int jrb_eval_finish(jrb_plan* p, const double* occ, const double* rho
   return 0;
 }
 
+extern "C" int jrb_eval_finish(jrb_plan* p, const double* occ, const double* rho,
+                               const double* e_kin, int32_t xc_id, double* energies, double* g_re,
+                               double* g_im, double* g_occ, jrb_stream st) {
+  int rc = enter(p);
+  if (rc) return rc;
+  REQUIRE(occ && rho && e_kin && energies && g_re && g_im, "null array");
+  return eval_finish_impl(p, occ, rho, e_kin, xc_id, energies, g_re, g_im, g_occ, false, st);
+}
+
 extern "C" int jrb_eval(jrb_plan* p, const double* w_re, const double* w_im, const double* occ,
                         int32_t xc_id, double* energies, double* g_re, double* g_im, double* g_occ,
                         double* rho, jrb_stream st) {
@@ -372,8 +388,9 @@ extern "C" int jrb_eval(jrb_plan* p, const double* w_re, const double* w_im, con
   if (rc) return rc;
   REQUIRE(w_re && w_im && occ && energies && g_re && g_im && rho, "null array");
   double* e_kin = p->d_scal + 40;
-  if ((rc = eval_begin_impl(p, w_re, w_im, occ, rho, e_kin, true, S(st)))) return rc;
-  return jrb_eval_finish(p, occ, rho, e_kin, xc_id, energies, g_re, g_im, g_occ, st);
+  const bool hat = grid_fused_ok(p, xc_id);
+  if ((rc = eval_begin_impl(p, w_re, w_im, occ, rho, e_kin, true, hat, S(st)))) return rc;
+  return eval_finish_impl(p, occ, rho, e_kin, xc_id, energies, g_re, g_im, g_occ, hat, st);
 }
 
 static int ensure_host_buffers(jrb_plan* p) {
@@ -428,9 +445,10 @@ extern "C" int jrb_energy_grad_host(jrb_plan* p, const double* w_re_h, const dou
     const size_t nw = (size_t)p->ns * p->nk * per_k * sizeof(double);
     JRB_CUDA(cudaMemcpyAsync(p->d_wre, w_re_h, nw, cudaMemcpyHostToDevice, st));
     JRB_CUDA(cudaMemcpyAsync(p->d_wim, w_im_h, nw, cudaMemcpyHostToDevice, st));
-    if ((rc = eval_begin_impl(p, p->d_wre, p->d_wim, p->d_occ, rho, e_kin, true, st))) return rc;
-    if ((rc = jrb_eval_finish(p, p->d_occ, rho, e_kin, xc_id, p->d_en, p->d_gre, p->d_gim, nullptr,
-                              st)))
+    const bool hat = grid_fused_ok(p, xc_id);
+    if ((rc = eval_begin_impl(p, p->d_wre, p->d_wim, p->d_occ, rho, e_kin, true, hat, st))) return rc;
+    if ((rc = eval_finish_impl(p, p->d_occ, rho, e_kin, xc_id, p->d_en, p->d_gre, p->d_gim, nullptr,
+                               hat, st)))
       return rc;
     JRB_CUDA(cudaMemcpyAsync(g_re_h, p->d_gre, nw, cudaMemcpyDeviceToHost, st));
     JRB_CUDA(cudaMemcpyAsync(g_im_h, p->d_gim, nw, cudaMemcpyDeviceToHost, st));
@@ -464,12 +482,17 @@ extern "C" int jrb_energy_grad_host(jrb_plan* p, const double* w_re_h, const dou
       const long long n = (long long)p->ns * (p->wf ? p->wf->ngrid : p->ngrid);
       if ((rc = launch_comm_allreduce(p, part, n, e_kin, 1, st))) return rc;
     }
-    if ((rc = launch_density_end(p, rho, st))) return rc;
+    const bool hat = grid_fused_ok(p, xc_id);
+    if ((rc = hat ? launch_density_end_hat(p, rho, st) : launch_density_end(p, rho, st))) return rc;
     // backward: D2H of chunk c (copy stream) under H-apply + QR adjoint of chunk c+1
     double* grid_e = p->d_scal;
     p->veff_prepared = 0;
-    if ((rc = launch_grid_potential(p, rho, xc_id, 0, 7, grid_e, p->d_veff, st))) return rc;
-    if ((rc = launch_hpsi_prepare(p, p->d_veff, st))) return rc;
+    if (hat) {
+      if ((rc = launch_grid_potential_orbital(p, rho, true, xc_id, grid_e, st))) return rc;
+    } else {
+      if ((rc = launch_grid_potential(p, rho, xc_id, 0, 7, grid_e, p->d_veff, st))) return rc;
+      if ((rc = launch_hpsi_prepare(p, p->d_veff, st))) return rc;
+    }
     for (int c = 0; c < nch; ++c) {
       const int k0 = k_of(c), k1 = k_of(c + 1);
       const size_t off = (size_t)k0 * per_k, n = (size_t)(k1 - k0) * per_k;

@@ -439,8 +439,9 @@ int launch_complex_to_real(const cplx* in, long long n, double* out, cudaStream_
 // Fourier resampling between two FFT boxes: dst(f) = scale * src(f) for the frequencies both boxes
 // represent symmetrically (2|f_c| < min(n_src, n_dst) on every axis: an even box's unpaired Nyquist
 // bin is dropped so real fields stay real), zero elsewhere.  One thread per dst element.
-__global__ void k_resample(const cplx* __restrict__ src, int sx, int sy, int sz,
-                           cplx* __restrict__ dst, int dx, int dy, int dz, double scale) {
+__global__ void k_resample(const cplx* __restrict__ src, const cplx* __restrict__ src2, int sx,
+                           int sy, int sz, cplx* __restrict__ dst, int dx, int dy, int dz,
+                           double scale) {
   const long long n = (long long)dx * dy * dz;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
        i += (long long)gridDim.x * blockDim.x) {
@@ -456,7 +457,12 @@ __global__ void k_resample(const cplx* __restrict__ src, int sx, int sy, int sz,
       const int px = sx == dx ? x : (fx >= 0 ? fx : fx + sx);
       const int py = sy == dy ? y : (fy >= 0 ? fy : fy + sy);
       const int pz = sz == dz ? z : (fz >= 0 ? fz : fz + sz);
-      const cplx t = src[((long long)px * sy + py) * sz + pz];
+      const long long o = ((long long)px * sy + py) * sz + pz;
+      cplx t = src[o];
+      if (src2) {  // sum of two fields of the source box
+        const cplx u = src2[o];
+        t = cmake(t.x + u.x, t.y + u.y);
+      }
       v = cmake(t.x * scale, t.y * scale);
     }
     dst[i] = v;
@@ -467,8 +473,97 @@ int launch_resample(const cplx* src, int sx, int sy, int sz, cplx* dst, int dx, 
                     double scale, cudaStream_t st) {
   const long long n = (long long)dx * dy * dz;
   const int blocks = (int)std::min<long long>((n + 255) / 256, 148 * 8);
-  k_resample<<<blocks, 256, 0, st>>>(src, sx, sy, sz, dst, dx, dy, dz, scale);
+  k_resample<<<blocks, 256, 0, st>>>(src, nullptr, sx, sy, sz, dst, dx, dy, dz, scale);
   JRB_CHECK_LAUNCH("k_resample");
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------
+// The grid part of one evaluation when the orbitals live on their own box (LDA, one spin).  The
+// separate calls (launch_density_end -> launch_grid_potential -> launch_hpsi_prepare) transform
+// the same fields back and forth: rho goes to the plan's grid (inverse FFT) and is transformed
+// forward again for the Hartree term; v_H + v_ext goes to real space, gets v_xc added and is
+// transformed forward again to be truncated onto the orbital box.  Here each field is transformed
+// once: rho_hat comes from the interpolation itself, and v_H(G) + v_ext(G) joins fftn(v_xc) in
+// G space inside the truncating resample (linearity) -- 4 dense single-grid FFTs instead of 6
+// (plus the 2 on the orbital box) and 6 launches fewer.  This replicated work is what a rank of an
+// 8-GPU run cannot shrink.
+bool grid_fused_ok(const jrb_plan* p, int xc_id) {
+  static int off = [] {
+    const char* env = std::getenv("JRB_NO_GRID_FUSE");
+    return env ? std::atoi(env) : 0;
+  }();
+  return !off && p->wf && p->ns == 1 && p->natoms > 0 &&
+         (xc_id == JRB_XC_LDA_X || xc_id == JRB_XC_LDA_X_C_PW);
+}
+
+// rho on the orbital box -> rho on the plan's grid AND rho_hat = fftn(rho) left in p->d_grid
+int launch_density_end_hat(jrb_plan* p, double* rho, cudaStream_t st) {
+  jrb_plan* w = p->wf;
+  int rc = 0;
+  if ((rc = launch_real_to_complex(w->d_rho_w, w->ngrid, w->d_grid, st))) return rc;
+  if ((rc = launch_fft3d_dense(w, w->d_grid, w->d_grid, JRB_FFT_FORWARD, 1, 1.0, st))) return rc;
+  if ((rc = launch_resample(w->d_grid, w->nx, w->ny, w->nz, p->d_grid, p->nx, p->ny, p->nz,
+                            (double)p->ngrid / (double)w->ngrid, st)))
+    return rc;
+  cplx* tmp = p->d_gga + p->ngrid;  // out of place: rho_hat stays in d_grid
+  if ((rc = launch_fft3d_dense(p, p->d_grid, tmp, JRB_FFT_INVERSE, 1, 1.0 / (double)p->ngrid, st)))
+    return rc;
+  return launch_complex_to_real(tmp, p->ngrid, rho, st);
+}
+
+// complex(v_xc(r)) and the E_xc partial sums (LDA, one spin; v_xc = eps + rho eps')
+__global__ void __launch_bounds__(RED_THREADS)
+k_vxc_to_complex(GridGeom g, const double* __restrict__ rho, int xc_id, cplx* __restrict__ out,
+                 double* __restrict__ partials) {
+  double acc[1] = {0.0};
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < g.n;
+       i += (long long)gridDim.x * blockDim.x) {
+    const double n = rho[i];
+    double e, de;
+    lda_eps(xc_id, n, e, de);
+    out[i] = cmake(e + n * de, 0.0);
+    acc[0] += e * n;
+  }
+  double sum[1];
+  block_sum<1>(acc, sum);
+  if (threadIdx.x == 0) partials[blockIdx.x * 4 + 2] = sum[0] * g.vol / (double)g.n;
+}
+
+// energies[3] = E_H, E_ext, E_xc from rho (plan grid) and v_eff = dE/drho ON THE ORBITAL BOX
+// (p->wf->d_veff); rhohat_ready: p->d_grid already holds fftn(rho) (launch_density_end_hat)
+int launch_grid_potential_orbital(jrb_plan* p, const double* rho, bool rhohat_ready, int xc_id,
+                                  double* energies, cudaStream_t st) {
+  jrb_plan* w = p->wf;
+  const GridGeom g = geom_of(p);
+  const int blocks = (int)std::min<long long>((p->ngrid + RED_THREADS - 1) / RED_THREADS,
+                                              (long long)p->n_partial_blocks);
+  int rc = 0;
+  if (!rhohat_ready) {
+    k_rho_to_complex<<<blocks, RED_THREADS, 0, st>>>(rho, 1, p->ngrid, p->d_grid);
+    JRB_CHECK_LAUNCH("k_rho_to_complex");
+    if ((rc = launch_fft3d_dense(p, p->d_grid, p->d_grid, JRB_FFT_FORWARD, 1, 1.0, st))) return rc;
+  }
+  k_hartree_ext<<<blocks, RED_THREADS, 0, st>>>(g, p->d_grid, p->d_vext, 0, 3, p->d_partials);
+  JRB_CHECK_LAUNCH("k_hartree_ext");
+  cplx* vx = p->d_gga;
+  k_vxc_to_complex<<<blocks, RED_THREADS, 0, st>>>(g, rho, xc_id, vx, p->d_partials);
+  JRB_CHECK_LAUNCH("k_vxc_to_complex");
+  if ((rc = launch_fft3d_dense(p, vx, vx, JRB_FFT_FORWARD, 1, 1.0, st))) return rc;
+  // fftn(v_eff) = fftn(v_xc) + v_H(G) + v_ext(G), truncated onto the orbital box
+  {
+    const long long n = w->ngrid;
+    const int rb = (int)std::min<long long>((n + 255) / 256, 148 * 8);
+    k_resample<<<rb, 256, 0, st>>>(vx, p->d_grid, p->nx, p->ny, p->nz, w->d_grid, w->nx, w->ny, w->nz,
+                                   1.0 / (double)p->ngrid);
+    JRB_CHECK_LAUNCH("k_resample");
+  }
+  if ((rc = launch_fft3d_dense(w, w->d_grid, w->d_grid, JRB_FFT_INVERSE, 1, 1.0, st))) return rc;
+  if ((rc = launch_complex_to_real(w->d_grid, w->ngrid, w->d_veff, st))) return rc;
+  if (energies) {
+    k_reduce_partials<<<1, 96, 0, st>>>(p->d_partials, blocks, 3, energies);
+    JRB_CHECK_LAUNCH("k_reduce_partials");
+  }
   return 0;
 }
 

@@ -153,6 +153,11 @@ bool fused128_available(int nx, int ny, int nxo, int ncol, int band_limited32);
 int fused_cta_count(int n, int nxo, int ncol);
 
 // grid_kernels.cu
+// fused grid part of an evaluation (orbital box, LDA, one spin): see launch_grid_potential_orbital
+bool grid_fused_ok(const jrb_plan* p, int xc_id);
+int launch_density_end_hat(jrb_plan* p, double* rho, cudaStream_t st);
+int launch_grid_potential_orbital(jrb_plan* p, const double* rho, bool rhohat_ready, int xc_id,
+                                  double* energies, cudaStream_t st);
 int launch_set_atoms(jrb_plan* p, const double* pos_h, const double* chg_h, int na,
                      cudaStream_t st);
 int launch_grid_potential(jrb_plan* p, const double* rho, int xc_id, int kohn_sham, int parts,

@@ -81,3 +81,19 @@ def test_dense_contractions_use_the_fp64_tensor_instruction():
     out = subprocess.run(['cuobjdump', '-sass', obj], capture_output=True, text=True, check=True)
   assert out.stdout.count('DMMA') > 100
   assert 'LDGSTS' in out.stdout
+
+
+def test_fused_plane_kernels_stage_with_tma():
+  """The fused y+x plane kernels stage their band-planes with TMA tensor copies completed on an
+  mbarrier (north_star (1): transposes staged through TMA / shared memory): the shipped SASS holds
+  UTMALDG (cp.async.bulk.tensor) and SYNCS (mbarrier) instructions, and the cp.async fallback."""
+  objs = [os.path.join(os.path.dirname(_lib.LIB_PATH), 'build', f'fft_fused_g{i}.o') for i in range(3)]
+  if not all(os.path.exists(o) for o in objs):
+    pytest.skip('no per-object build tree')
+  tma = mbar = ldgsts = 0
+  for obj in objs:
+    out = subprocess.run(['cuobjdump', '-sass', obj], capture_output=True, text=True, check=True).stdout
+    tma += out.count('UTMALDG')
+    mbar += out.count('SYNCS')
+    ldgsts += out.count('LDGSTS')
+  assert tma > 0 and mbar > 0 and ldgsts > 0, (tma, mbar, ldgsts)
