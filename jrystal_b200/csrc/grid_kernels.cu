@@ -344,13 +344,19 @@ k_veff_xc(GridGeom g, const cplx* __restrict__ grid, const double* __restrict__ 
 
 __global__ void k_reduce_partials(const double* __restrict__ partials, int nblocks, int ncomp,
                                   double* __restrict__ out) {
-  // one warp per component, fixed order -> deterministic
-  const int c = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  if (c >= ncomp) return;
+  // one CTA of 256 threads per component: 8 warps, fixed order -> deterministic
+  __shared__ double red[8];
+  const int c = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   double s = 0.0;
-  for (int i = lane; i < nblocks; i += 32) s += partials[i * 4 + c];
+  for (int i = threadIdx.x; i < nblocks; i += 256) s += partials[i * 4 + c];
   s = warp_sum(s);
-  if (lane == 0) out[c] = s;
+  if (lane == 0) red[warp] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int w = 0; w < 8; ++w) t += red[w];
+    out[c] = t;
+  }
 }
 
 int launch_grid_potential(jrb_plan* p, const double* rho, int xc_id, int kohn_sham, int parts,
@@ -403,7 +409,7 @@ int launch_grid_potential(jrb_plan* p, const double* rho, int xc_id, int kohn_sh
                                            gga ? p->d_vxc : nullptr, veff, p->d_partials);
   JRB_CHECK_LAUNCH("k_veff_xc");
   if (energies) {
-    k_reduce_partials<<<1, 96, 0, st>>>(p->d_partials, blocks, 3, energies);
+    k_reduce_partials<<<3, 256, 0, st>>>(p->d_partials, blocks, 3, energies);
     JRB_CHECK_LAUNCH("k_reduce_partials");
   }
   return 0;
@@ -561,7 +567,7 @@ int launch_grid_potential_orbital(jrb_plan* p, const double* rho, bool rhohat_re
   if ((rc = launch_fft3d_dense(w, w->d_grid, w->d_grid, JRB_FFT_INVERSE, 1, 1.0, st))) return rc;
   if ((rc = launch_complex_to_real(w->d_grid, w->ngrid, w->d_veff, st))) return rc;
   if (energies) {
-    k_reduce_partials<<<1, 96, 0, st>>>(p->d_partials, blocks, 3, energies);
+    k_reduce_partials<<<3, 256, 0, st>>>(p->d_partials, blocks, 3, energies);
     JRB_CHECK_LAUNCH("k_reduce_partials");
   }
   return 0;

@@ -169,7 +169,7 @@ extern "C" int jrb_plan_destroy(jrb_plan* p) {
   void* ptrs[] = {p->d_zmap, p->d_ycol, p->d_xmap, p->d_gidx, p->d_gk2, p->d_tw_x, p->d_tw_y,
                   p->d_tw_z, p->d_tw_half, p->d_a_keep, p->d_pos, p->d_chg, p->d_atom_part, p->d_nl_phi, p->d_nl_p, p->d_nl_part, p->d_ws_a, p->d_ws_b, p->d_rho_part, p->d_seg_z, p->d_focc, p->d_grid, p->d_vext,
                   p->d_partials, p->d_veff, p->d_gga, p->d_vxc, p->d_q, p->d_hq, p->d_tmp, p->d_r, p->d_rinv, p->d_small, p->d_gpart,
-                  p->d_tkb, p->d_eps, p->d_sphere_part, p->d_scal, p->d_skip, p->d_wre, p->d_wim, p->d_gre, p->d_gim,
+                  p->d_tkb, p->d_eps, p->d_sphere_part, p->d_scal, p->d_skip, p->d_emax, p->d_wre, p->d_wim, p->d_gre, p->d_gim,
                   p->d_occ, p->d_rho, p->d_en};
   for (void* q : ptrs)
     if (q) cudaFree(q);
@@ -226,6 +226,7 @@ extern "C" int jrb_plan_create_rows(int64_t nrows, int32_t ns, int32_t nk, int32
   TRY(dev_alloc(&p->d_scal, 64, &tot));
   JRB_CUDA(cudaMemset(p->d_scal, 0, 64 * sizeof(double)));
   TRY(dev_alloc(&p->d_skip, (size_t)p->ns * p->nk, &tot));
+  TRY(dev_alloc(&p->d_emax, (size_t)p->ns * p->nk, &tot));
 #undef TRY
   p->ws_bytes = tot;
   *out = p;
@@ -466,6 +467,7 @@ static int plan_create_impl(const jrb_plan_desc* d, bool orbital_only, jrb_plan*
   TRY(dev_alloc(&p->d_scal, 64, &tot));
   JRB_CUDA(cudaMemset(p->d_scal, 0, 64 * sizeof(double)));
   TRY(dev_alloc(&p->d_skip, (size_t)p->ns * p->nk, &tot));
+  TRY(dev_alloc(&p->d_emax, (size_t)p->ns * p->nk, &tot));
   JRB_CUDA(cudaStreamCreateWithFlags(&p->own_stream, cudaStreamNonBlocking));
 #undef TRY
   p->ws_bytes = tot;

@@ -104,6 +104,7 @@ struct jrb_plan {
   double* d_sphere_part;              // [8 chunks][ns*nk*nb] partials of the sphere reductions
   double* d_scal;                     // small device scalars
   int* d_skip;                        // [ns*nk] second-pass Cholesky already written (k_near_identity)
+  double* d_emax;                     // [ns*nk] max|Q1^H Q1 - I| of the second pass (bit pattern)
   cudaStream_t own_stream, h2d_stream, d2h_stream;
   cudaEvent_t ev_in[16], ev_out[16];  // per k-chunk events of jrb_energy_grad_host
   // host staging for jrb_energy_grad_host

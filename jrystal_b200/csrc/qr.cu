@@ -201,7 +201,7 @@ constexpr int CP_LD = CP + 1;
 constexpr int CP_SMEM = 4 * CP * CP_LD * (int)sizeof(cplx);  // D, T, Ld, Lr
 __global__ void __launch_bounds__(256)
 k_chol_panel(cplx* __restrict__ S, cplx* __restrict__ Rt, int nb, int p0, int* __restrict__ fail_flag,
-             const int* __restrict__ skip) {
+             const int* __restrict__ skip, int right_looking) {
   if (skip && skip[blockIdx.y]) return;
   extern __shared__ __align__(16) unsigned char smem_raw_[];
   cplx* D = reinterpret_cast<cplx*>(smem_raw_);
@@ -236,8 +236,11 @@ k_chol_panel(cplx* __restrict__ S, cplx* __restrict__ Rt, int nb, int p0, int* _
       pr[j] = r < nr ? S[(long long)(r0 + r) * nb + k0 + c] : cmake(0.0, 0.0);
     }
   };
-  if (p0 > 0) fetch(0);
-  for (int k0 = 0; k0 < p0; k0 += CP) {  // p0 is a multiple of CP
+  // right-looking mode: the finished panels were already subtracted from the trailing matrix by
+  // k_trailing_update (many CTAs per panel instead of this CTA's serial slices)
+  const int kend = right_looking ? 0 : p0;
+  if (kend > 0) fetch(0);
+  for (int k0 = 0; k0 < kend; k0 += CP) {  // p0 is a multiple of CP
     __syncthreads();
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
@@ -245,7 +248,7 @@ k_chol_panel(cplx* __restrict__ S, cplx* __restrict__ Rt, int nb, int p0, int* _
       Lr[(rb + 8 * j) * CP_LD + c] = pr[j];
     }
     __syncthreads();
-    if (k0 + CP < p0) fetch(k0 + CP);
+    if (k0 + CP < kend) fetch(k0 + CP);
     if (tile == 0) {  // the diagonal tile has no rows below (whole-CTA branch)
 #pragma unroll 8
       for (int k = 0; k < CP; ++k) {
@@ -329,6 +332,55 @@ k_chol_panel(cplx* __restrict__ S, cplx* __restrict__ Rt, int nb, int p0, int* _
       S[(long long)(r0 + r) * nb + p0 + c] = v;
       Rt[(long long)(p0 + c) * nb + r0 + r] = cconj(v);
       Rt[(long long)(r0 + r) * nb + p0 + c] = cmake(0.0, 0.0);
+    }
+  }
+}
+
+// Right-looking companion of k_chol_panel: after panel p0 is factored (its L sits in the lower
+// part of S), the trailing matrix gets  S[i][j] -= sum_{k in panel} L[i][k] conj(L[j][k])  for
+// i >= j >= p0 + 32, one CTA per 32 x 32 lower tile -- the rank-32 update spread over up to 21 CTAs
+// instead of the serial left-looking slices inside each panel CTA (the 61 us per panel at nb = 208
+// were half this update).   grid: (nt (nt + 1) / 2, nsk), nt = ceil((nb - p0 - 32) / 32); block 256
+__global__ void __launch_bounds__(256)
+k_trailing_update(cplx* __restrict__ S, int nb, int p0, const int* __restrict__ skip) {
+  if (skip && skip[blockIdx.y]) return;
+  __shared__ cplx Li[CP * CP_LD], Lj[CP * CP_LD];
+  S += (long long)blockIdx.y * nb * nb;
+  int ti = 0, rem = blockIdx.x;  // lower tiles enumerated row by row: ti >= tj
+  while (rem > ti) {
+    rem -= ti + 1;
+    ++ti;
+  }
+  const int tj = rem;
+  const int base = p0 + CP, i0 = base + CP * ti, j0 = base + CP * tj;
+  const int pw = min(CP, nb - p0);
+  const int tid = threadIdx.x, c = tid & 31, rb = tid >> 5;
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const int r = rb + 8 * q;
+    Li[r * CP_LD + c] = (i0 + r < nb && c < pw) ? S[(long long)(i0 + r) * nb + p0 + c] : cmake(0.0, 0.0);
+    Lj[r * CP_LD + c] = (j0 + r < nb && c < pw) ? S[(long long)(j0 + r) * nb + p0 + c] : cmake(0.0, 0.0);
+  }
+  __syncthreads();
+  cplx acc[4];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) acc[q] = cmake(0.0, 0.0);
+#pragma unroll 8
+  for (int k = 0; k < CP; ++k) {
+    const cplx lc = Lj[c * CP_LD + k];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const cplx u = cmulc(Li[(rb + 8 * q) * CP_LD + k], lc);
+      acc[q].x += u.x;
+      acc[q].y += u.y;
+    }
+  }
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const int i = i0 + rb + 8 * q, j = j0 + c;
+    if (i < nb && j < nb && i >= j) {
+      cplx v = S[(long long)i * nb + j];
+      S[(long long)i * nb + j] = cmake(v.x - acc[q].x, v.y - acc[q].y);
     }
   }
 }
@@ -431,6 +483,116 @@ k_tri_inv_offdiag(const cplx* __restrict__ R, int nb, cplx* __restrict__ Rinv,
   }
 }
 
+
+// ---------------------------------------------------------------------------------------
+// Blocked inverse of an upper-triangular R by recursive doubling (large matrices, few of them):
+//   [[A, B], [0, C]]^-1 = [[A^-1, -A^-1 B C^-1], [0, C^-1]]
+// level 0 inverts the 32 x 32 diagonal blocks (k_tri_inv_diag256); level l joins neighbouring
+// groups of g = 2^(l-1) blocks: T = B C^-1, then X_B = -A^-1 T, every 32 x 32 tile of every group a
+// CTA of its own -- 1 + 2 ceil(log2 nblk) launches with no serial block walk inside a CTA
+// (k_tri_inv_offdiag: one CTA per 8 columns walking up to 6 block rows, 120 us at nb = 208).
+// T lives in the strictly upper part of the scratch matrix `Tm` (the Cholesky work matrix keeps L
+// in its lower part; its upper part is free).
+// grid: (ceil(nb / 32), nsk), block 256: thread (column j, part) of one diagonal block
+__global__ void __launch_bounds__(256)
+k_tri_inv_diag256(const cplx* __restrict__ R, int nb, cplx* __restrict__ Rinv,
+                  const int* __restrict__ skip) {
+  if (skip && skip[blockIdx.y]) return;
+  __shared__ cplx U[CP * CP_LD], X[CP * CP_LD], P[8 * CP];
+  const long long nn = (long long)nb * nb;
+  R += blockIdx.y * nn;
+  Rinv += blockIdx.y * nn;
+  const int b0 = blockIdx.x * CP, bw = min(CP, nb - b0);
+  const int tid = threadIdx.x, j = tid & 31, part = tid >> 5;
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const int i = part + 8 * q;
+    U[i * CP_LD + j] = (i < bw && j < bw) ? R[(long long)(b0 + i) * nb + b0 + j] : cmake(i == j ? 1.0 : 0.0, 0.0);
+    X[i * CP_LD + j] = cmake(0.0, 0.0);
+  }
+  __syncthreads();
+  // back substitution, rows bottom up: X[i][j] = (delta_ij - sum_{k = i+1}^{j} U[i][k] X[k][j]) / U[i][i]
+  for (int i = CP - 1; i >= 0; --i) {
+    double sx = 0.0, sy = 0.0;
+    if (j > i)
+      for (int k = i + 1 + part; k <= j; k += 8) {
+        const cplx v = cmul(U[i * CP_LD + k], X[k * CP_LD + j]);
+        sx += v.x;
+        sy += v.y;
+      }
+    P[part * CP + j] = cmake(sx, sy);
+    __syncthreads();
+    if (part == 0 && j >= i) {
+      double tx = j == i ? 1.0 : 0.0, ty = 0.0;
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        tx -= P[q * CP + j].x;
+        ty -= P[q * CP + j].y;
+      }
+      const cplx d = U[i * CP_LD + i];
+      const double n2 = d.x * d.x + d.y * d.y;
+      X[i * CP_LD + j] = cmake((tx * d.x + ty * d.y) / n2, (ty * d.x - tx * d.y) / n2);  // t / d
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const int i = part + 8 * q;
+    if (i < bw && j < bw) Rinv[(long long)(b0 + i) * nb + b0 + j] = X[i * CP_LD + j];
+  }
+}
+
+// One product of a doubling level, a 32 x 32 output tile per CTA.  Group G joins the block ranges
+// L = [2 g G, 2 g G + g) and Rr = [2 g G + g, min(2 g G + 2 g, nblk)).
+//   phase 0:  T[L][Rr]   =  R[L][Rr] X[Rr][Rr]        (k over Rr)
+//   phase 1:  X[L][Rr]   = -X[L][L]  T[L][Rr]         (k over L)
+// grid: (g * g, ngroups, nsk): tile (bi, bj) = (blockIdx.x / g, blockIdx.x % g) of the group
+__global__ void __launch_bounds__(256)
+k_tri_inv_level(const cplx* __restrict__ R, cplx* __restrict__ X, cplx* __restrict__ Tm, int nb,
+                int nblk, int g, int phase, const int* __restrict__ skip) {
+  if (skip && skip[blockIdx.z]) return;
+  __shared__ cplx As[CP * CP_LD], Bs[CP * CP_LD];
+  const long long off = (long long)blockIdx.z * nb * nb;
+  const int lo = 2 * g * blockIdx.y, mid = lo + g, hi = min(lo + 2 * g, nblk);
+  const int bi = lo + blockIdx.x / g, bj = mid + blockIdx.x % g;
+  if (mid >= nblk || bj >= hi) return;
+  const cplx* A = (phase == 0 ? R : X) + off;
+  const cplx* B = (phase == 0 ? X : Tm) + off;
+  cplx* C = (phase == 0 ? Tm : X) + off;
+  const int k_lo = phase == 0 ? mid : lo, k_hi = phase == 0 ? hi : mid;
+  const int tid = threadIdx.x, c = tid & 31, rb = tid >> 5;
+  const int i0 = bi * CP, j0 = bj * CP;
+  cplx acc[4];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) acc[q] = cmake(0.0, 0.0);
+  for (int K = k_lo; K < k_hi; ++K) {
+    const int k0 = K * CP;
+    __syncthreads();
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int r = rb + 8 * q;
+      As[r * CP_LD + c] = (i0 + r < nb && k0 + c < nb) ? A[(long long)(i0 + r) * nb + k0 + c] : cmake(0.0, 0.0);
+      Bs[r * CP_LD + c] = (k0 + r < nb && j0 + c < nb) ? B[(long long)(k0 + r) * nb + j0 + c] : cmake(0.0, 0.0);
+    }
+    __syncthreads();
+#pragma unroll 8
+    for (int k = 0; k < CP; ++k) {
+      const cplx b = Bs[k * CP_LD + c];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const cplx u = cmul(As[(rb + 8 * q) * CP_LD + k], b);
+        acc[q].x += u.x;
+        acc[q].y += u.y;
+      }
+    }
+  }
+  const double sgn = phase == 0 ? 1.0 : -1.0;
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const int i = i0 + rb + 8 * q, j = j0 + c;
+    if (i < nb && j < nb) C[(long long)i * nb + j] = cmake(sgn * acc[q].x, sgn * acc[q].y);
+  }
+}
 
 // Second Cholesky-QR pass: S = Q1^H Q1 = I + E with |E| ~ kappa(W)^2 eps.  For |E|_max < tol the
 // factor is written in closed form, R = I + U, R^-1 = I - U + U^2 - ... with U = up(E) + diag(E)/2:
@@ -865,6 +1027,117 @@ k_bwd_t2(const cplx* __restrict__ X, const cplx* __restrict__ rinv, int nb, cplx
 }
 
 // ---------------------------------------------------------------------------------------
+// nb x nb products of the small algebra as 32 x 32 tiles, one CTA each (large nb, few matrices: the
+// one-thread-per-element kernels k_tri_compose / k_bwd_t2 walk 200 strided L2 reads per thread).
+//   MODE 0: C = A B, A and B upper triangular (blocks K in [bi, bj]; C's lower blocks are zeroed)
+//   MODE 1: C = A B^H, B upper triangular (B^H[k][j] = conj(B[j][k]): blocks K >= bj)
+// blockIdx.z = which * nsk + sk: `which` selects the operand set (two products per launch).
+struct TileGemmOps {
+  const cplx* A[2];
+  const cplx* B[2];
+  cplx* C[2];
+};
+template <int MODE>
+__global__ void __launch_bounds__(256)
+k_tile_gemm(TileGemmOps ops, int nb, int nsk) {
+  __shared__ cplx As[CP * CP_LD], Bs[CP * CP_LD];
+  const int which = blockIdx.z / nsk, sk = blockIdx.z % nsk;
+  const long long off = (long long)sk * nb * nb;
+  const cplx* A = ops.A[which] + off;
+  const cplx* B = ops.B[which] + off;
+  cplx* C = ops.C[which] + off;
+  const int nblk = (nb + CP - 1) / CP;
+  const int bi = blockIdx.y, bj = blockIdx.x;
+  const int tid = threadIdx.x, c = tid & 31, rb = tid >> 5;
+  const int i0 = bi * CP, j0 = bj * CP;
+  cplx acc[4];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) acc[q] = cmake(0.0, 0.0);
+  const int k_lo = MODE == 0 ? bi : bj, k_hi = MODE == 0 ? bj + 1 : nblk;
+  for (int K = k_lo; K < k_hi; ++K) {
+    const int k0 = K * CP;
+    __syncthreads();
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int r = rb + 8 * q;
+      As[r * CP_LD + c] = (i0 + r < nb && k0 + c < nb) ? A[(long long)(i0 + r) * nb + k0 + c] : cmake(0.0, 0.0);
+      if (MODE == 0) {
+        Bs[r * CP_LD + c] = (k0 + r < nb && j0 + c < nb) ? B[(long long)(k0 + r) * nb + j0 + c] : cmake(0.0, 0.0);
+      } else {  // Bs[k][j] = conj(B[j0 + j][k0 + k]): read row-wise, store transposed
+        const cplx v = (j0 + r < nb && k0 + c < nb) ? B[(long long)(j0 + r) * nb + k0 + c] : cmake(0.0, 0.0);
+        Bs[c * CP_LD + r] = cconj(v);
+      }
+    }
+    __syncthreads();
+#pragma unroll 8
+    for (int k = 0; k < CP; ++k) {
+      const cplx b = Bs[k * CP_LD + c];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const cplx u = cmul(As[(rb + 8 * q) * CP_LD + k], b);
+        acc[q].x += u.x;
+        acc[q].y += u.y;
+      }
+    }
+  }
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const int i = i0 + rb + 8 * q, j = j0 + c;
+    if (i < nb && j < nb) C[(long long)i * nb + j] = acc[q];
+  }
+}
+
+// k_near_identity in two grid-wide kernels (one CTA scanning a 208 x 208 matrix took 143 us):
+// max|S - I| by blocks into emax[sk] (non-negative doubles order like their bit patterns), then
+// the closed form and the skip flag.   grid: (ceil(nb^2 / 256), nsk), block 256
+__global__ void __launch_bounds__(256)
+k_near_identity_max(const cplx* __restrict__ S, int nb, unsigned long long* __restrict__ emax) {
+  __shared__ double red[8];
+  const long long nn = (long long)nb * nb;
+  const long long e = (long long)blockIdx.x * 256 + threadIdx.x;
+  double m = 0.0;
+  if (e < nn) {
+    const int i = (int)(e / nb), j = (int)(e % nb);
+    const cplx v = S[blockIdx.y * nn + e];
+    m = fmax(fabs(v.x - (i == j ? 1.0 : 0.0)), fabs(v.y));
+    if (!(m == m)) m = 1e300;  // NaN: not near the identity
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int w = 0; w < 8; ++w) t = fmax(t, red[w]);
+    atomicMax(emax + blockIdx.y, (unsigned long long)__double_as_longlong(t));
+  }
+}
+__global__ void __launch_bounds__(256)
+k_near_identity_apply(const cplx* __restrict__ S, int nb, double tol,
+                      const unsigned long long* __restrict__ emax, cplx* __restrict__ Rt,
+                      cplx* __restrict__ Rit, int* __restrict__ skip) {
+  const bool ok = __longlong_as_double((long long)emax[blockIdx.y]) < tol;
+  if (blockIdx.x == 0 && threadIdx.x == 0) skip[blockIdx.y] = ok ? 1 : 0;
+  if (!ok) return;
+  const long long nn = (long long)nb * nb;
+  const long long e = (long long)blockIdx.x * 256 + threadIdx.x;
+  if (e >= nn) return;
+  const int i = (int)(e / nb), j = (int)(e % nb);
+  cplx r = cmake(0.0, 0.0), ri = cmake(0.0, 0.0);
+  const cplx u0 = S[blockIdx.y * nn + e];
+  if (j > i) {
+    r = u0;
+    ri = cmake(-u0.x, -u0.y);
+  } else if (j == i) {
+    const double u = 0.5 * (u0.x - 1.0);
+    r = cmake(1.0 + u, 0.0);
+    ri = cmake(1.0 - u + u * u, 0.0);
+  }
+  Rt[blockIdx.y * nn + e] = r;
+  Rit[blockIdx.y * nn + e] = ri;
+}
+
+// ---------------------------------------------------------------------------------------
 static int gram_chunks(const jrb_plan* p, int tiles, int nsk) {
   // CTAs = upper super-tile pairs x chunks x (spin,k); two CTAs are resident per SM.  Pick the
   // chunk count (>= 256 rows each) whose last wave is fullest, preferring >= 2 waves.
@@ -1064,6 +1337,12 @@ static int compose_rows(jrb_plan* p, int nsk, const cplx* R2, const cplx* R2inv,
   return 0;
 }
 
+__global__ void k_zero_unless_skipped(cplx* __restrict__ a, long long n, const int* __restrict__ skip) {
+  if (skip && skip[blockIdx.y]) return;
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) a[(long long)blockIdx.y * n + i] = cmake(0.0, 0.0);
+}
+
 // Above this size the per-matrix recurrences are spread over several CTAs (more launches, far
 // less latency); below it one CTA per (spin,k) with batch parallelism is the better shape.
 static int large_nb_threshold() {
@@ -1086,7 +1365,28 @@ static bool multi_cta_small(int nb, int nsk) {
 
 // Rinv = R^-1 (upper triangular)
 static int tri_inverse(const cplx* R, int nb, int nsk, cplx* Rinv, cudaStream_t st,
-                       const int* skip = nullptr) {
+                       const int* skip = nullptr, cplx* scratch = nullptr) {
+  static int no_doubling = std::getenv("JRB_NO_TRI_DOUBLING") ? std::atoi(std::getenv("JRB_NO_TRI_DOUBLING")) : 0;
+  if (multi_cta_small(nb, nsk) && scratch && !no_doubling) {
+    // recursive doubling over 32 x 32 blocks; `scratch`: nb x nb per matrix whose strictly upper
+    // part is free (the Cholesky work matrix).  Rinv is zeroed first unless the matrix is skipped
+    // (its factor and inverse were written by k_near_identity).
+    const int nblk = (nb + CP - 1) / CP;
+    k_zero_unless_skipped<<<dim3((unsigned)(((long long)nb * nb + 255) / 256), nsk), 256, 0, st>>>(
+      Rinv, (long long)nb * nb, skip);
+    JRB_CHECK_LAUNCH("k_zero_unless_skipped");
+    k_tri_inv_diag256<<<dim3(nblk, nsk), 256, 0, st>>>(R, nb, Rinv, skip);
+    JRB_CHECK_LAUNCH("k_tri_inv_diag256");
+    for (int g = 1; g < nblk; g *= 2) {
+      const int ngroups = (nblk + 2 * g - 1) / (2 * g);
+      for (int phase = 0; phase < 2; ++phase) {
+        k_tri_inv_level<<<dim3(g * g, ngroups, nsk), 256, 0, st>>>(R, Rinv, scratch, nb, nblk, g, phase,
+                                                                  skip);
+        JRB_CHECK_LAUNCH("k_tri_inv_level");
+      }
+    }
+    return 0;
+  }
   if (multi_cta_small(nb, nsk)) {
     const int nblk = (nb + CP - 1) / CP;
     k_tri_inv_diag<<<dim3(nblk, nsk), 32, 0, st>>>(R, nb, Rinv, skip);
@@ -1114,21 +1414,30 @@ static int reduce_gram(jrb_plan* p, int nsk, int nchunks, cplx* S, cudaStream_t 
 
 // S (Hermitian, destroyed) -> Rt = chol(S)^H, Rit = Rt^-1
 static int chol_and_inverse(jrb_plan* p, int nsk, cplx* S, cplx* Rt, cplx* Rit, cudaStream_t st,
-                            const int* skip = nullptr) {
+                            const int* skip = nullptr, bool prefer_single = false) {
   const int nb = p->nb;
   int* fail = reinterpret_cast<int*>(p->d_scal + 32);
   const CfConfig cf = cf_config(nb);
   if (cf.ept) return factor_stream(p, cf, false, nsk, S, 0.0, Rt, Rit, skip, st);
-  if (multi_cta_small(nb, nsk)) {
+  const int smem1 = nb * (CHOL_PB + 1 + CHOL_KC + 1) * (int)sizeof(cplx);
+  // prefer_single: the caller expects every matrix to be skipped (second pass behind the closed
+  // form): two launches of the one-CTA kernels instead of the 20+ of the multi-CTA ones
+  if (multi_cta_small(nb, nsk) && !(prefer_single && smem1 <= 200 * 1024)) {
     for (int p0 = 0; p0 < nb; p0 += CP) {
       const int below = std::max(0, nb - p0 - CP);
       dim3 grid(1 + (below + CP - 1) / CP, nsk);
       static int once = opt_in_smem(k_chol_panel, CP_SMEM);
       if (once) return once;
-      k_chol_panel<<<grid, 256, CP_SMEM, st>>>(S, Rt, nb, p0, fail, skip);
+      static int left = std::getenv("JRB_CHOL_LEFT") ? std::atoi(std::getenv("JRB_CHOL_LEFT")) : 0;
+      k_chol_panel<<<grid, 256, CP_SMEM, st>>>(S, Rt, nb, p0, fail, skip, left ? 0 : 1);
       JRB_CHECK_LAUNCH("k_chol_panel");
+      if (!left && below > 0) {
+        const int nt = (below + CP - 1) / CP;
+        k_trailing_update<<<dim3(nt * (nt + 1) / 2, nsk), 256, 0, st>>>(S, nb, p0, skip);
+        JRB_CHECK_LAUNCH("k_trailing_update");
+      }
     }
-    return tri_inverse(Rt, nb, nsk, Rit, st, skip);
+    return tri_inverse(Rt, nb, nsk, Rit, st, skip, S);  // S: L below, free above the diagonal
   }
   const int smem = nb * (CHOL_PB + 1 + CHOL_KC + 1) * (int)sizeof(cplx);
   static int once = opt_in_smem(k_chol_blocked, 200 * 1024);
@@ -1139,7 +1448,10 @@ static int chol_and_inverse(jrb_plan* p, int nsk, cplx* S, cplx* Rt, cplx* Rit, 
   }
   k_chol_blocked<<<nsk, CHOL_T, smem, st>>>(S, Rt, nb, fail, skip);
   JRB_CHECK_LAUNCH("k_chol_blocked");
-  return tri_inverse(Rt, nb, nsk, Rit, st, skip);
+  dim3 igrid((nb + 7) / 8, nsk);
+  k_tri_inv_cols<<<igrid, 256, 8 * nb * (int)sizeof(cplx), st>>>(Rt, nb, Rit, skip);
+  JRB_CHECK_LAUNCH("k_tri_inv_cols");
+  return 0;
 }
 
 // Cholesky-QR2 of the (spin,k) range [sk0, sk0 + nsk), in phases so that a row-sharded caller can
@@ -1202,16 +1514,29 @@ int launch_qr_apply_phase(jrb_plan* p, int sk0, int nsk, const double* w_re, con
                         reinterpret_cast<double*>(qout + q.soff), nullptr, st);
   }
   const int* skip = nullptr;
-  if (shortcut) {
-    k_near_identity<<<nsk, 256, 0, st>>>(S, nb, 1e-10, q.Rt, q.Rit, p->d_skip + sk0);
-    JRB_CHECK_LAUNCH("k_near_identity");
-    skip = p->d_skip + sk0;
-  }
-  if ((rc = chol_and_inverse(p, nsk, S, q.Rt, q.Rit, st, skip))) return rc;
   const long long nn = (long long)nb * nb;
   dim3 egrid((unsigned)((nn + SMALL_T - 1) / SMALL_T), nsk);
-  k_tri_compose<<<egrid, SMALL_T, 0, st>>>(q.Rt, q.Rit, q.R1, q.R1inv, nb, r + q.moff, q.rinv);
-  JRB_CHECK_LAUNCH("k_tri_compose");
+  if (shortcut) {
+    unsigned long long* emax = reinterpret_cast<unsigned long long*>(p->d_emax) + sk0;
+    JRB_CUDA(cudaMemsetAsync(emax, 0, sizeof(unsigned long long) * nsk, st));
+    k_near_identity_max<<<egrid, 256, 0, st>>>(S, nb, emax);
+    JRB_CHECK_LAUNCH("k_near_identity_max");
+    k_near_identity_apply<<<egrid, 256, 0, st>>>(S, nb, 1e-10, emax, q.Rt, q.Rit, p->d_skip + sk0);
+    JRB_CHECK_LAUNCH("k_near_identity_apply");
+    skip = p->d_skip + sk0;
+  }
+  // the regular factorisation stands down where the closed form applied; with a skip list the
+  // one-CTA kernels serve (2 launches that return at once instead of 22)
+  if ((rc = chol_and_inverse(p, nsk, S, q.Rt, q.Rit, st, skip, skip != nullptr))) return rc;
+  {
+    // r = R2 R1, rinv = R1^-1 R2^-1: both products as 32 x 32 tiles in one launch
+    TileGemmOps ops;
+    ops.A[0] = q.Rt;    ops.B[0] = q.R1;  ops.C[0] = r + q.moff;
+    ops.A[1] = q.R1inv; ops.B[1] = q.Rit; ops.C[1] = q.rinv;
+    const int nblk = (nb + CP - 1) / CP;
+    k_tile_gemm<0><<<dim3(nblk, nblk, 2 * nsk), 256, 0, st>>>(ops, nb, nsk);
+    JRB_CHECK_LAUNCH("k_tile_gemm");
+  }
   return run_apply<0>(p, nsk, Q1, q.Rit, TRI_UPPER, none, nullptr, TRI_FULL, 1,
                       reinterpret_cast<double*>(qout + q.soff), nullptr, st);
 }
@@ -1265,8 +1590,17 @@ int launch_qr_bwd_apply_phase(jrb_plan* p, int sk0, int nsk, const cplx* q, cons
   dim3 egrid((unsigned)((nn + SMALL_T - 1) / SMALL_T), nsk);
   k_bwd_x<<<egrid, SMALL_T, 0, st>>>(M, 1, nb, occ ? occ + (long long)sk0 * nb : nullptr, rinv, X, T1);
   JRB_CHECK_LAUNCH("k_bwd_x");
-  k_bwd_t2<<<egrid, SMALL_T, 0, st>>>(X, rinv, nb, T2);
-  JRB_CHECK_LAUNCH("k_bwd_t2");
+  if (nb > 96) {  // T2 = X Rinv^H as 32 x 32 tiles
+    TileGemmOps ops;
+    ops.A[0] = X; ops.B[0] = rinv; ops.C[0] = T2;
+    ops.A[1] = X; ops.B[1] = rinv; ops.C[1] = T2;
+    const int nblk = (nb + CP - 1) / CP;
+    k_tile_gemm<1><<<dim3(nblk, nblk, nsk), 256, 0, st>>>(ops, nb, nsk);
+    JRB_CHECK_LAUNCH("k_tile_gemm");
+  } else {
+    k_bwd_t2<<<egrid, SMALL_T, 0, st>>>(X, rinv, nb, T2);
+    JRB_CHECK_LAUNCH("k_bwd_t2");
+  }
   return run_apply<1>(p, nsk, G, T1, TRI_LOWER, Q, T2, TRI_FULL, 2, g_re + sl.soff, g_im + sl.soff, st);
 }
 
