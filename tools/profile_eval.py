@@ -25,7 +25,6 @@ w_re_h, w_im_h = bench.synthetic_params(wl['ng'], nk, wl['nb'], 0, nk)
 w_re, w_im = torch.from_numpy(w_re_h).cuda(), torch.from_numpy(w_im_h).cuda()
 occ = torch.from_numpy(wl['occ']).cuda()
 for _ in range(args.evals):
-  rho, e_kin = plan.eval_begin(w_re, w_im, occ)
-  en, g_re, g_im, _ = plan.eval_finish(occ, rho, e_kin, 'lda_x')
+  en, g_re, g_im, _, rho = plan.eval(w_re, w_im, occ, 'lda_x')
 torch.cuda.synchronize()
 print('energies', en.cpu().numpy())
