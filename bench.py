@@ -850,6 +850,25 @@ def run_b200_kshard(args, name, wl, world, rank, local_rank, full, steps=None):
     dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
   e2e_value = e2e_steps / float(e2e_s.item())
   e2e_energy = float(en_p.sum())
+  # what the host <-> device copies of one step cost with NO kernel in between (H2D then D2H of the
+  # same pinned buffers, all ranks at once): the floor the platform's PCIe / host memory puts
+  # under e2e, reported next to it
+  def copy_only():
+    w_re.copy_(w_re_p, non_blocking=True)
+    w_im.copy_(w_im_p, non_blocking=True)
+    g_re_p.copy_(out[1], non_blocking=True)
+    g_im_p.copy_(out[2], non_blocking=True)
+    torch.cuda.current_stream().synchronize()
+  copy_only()
+  barrier()
+  t0 = time.perf_counter()
+  for _ in range(3):
+    copy_only()
+  barrier()
+  copy_s = torch.tensor([(time.perf_counter() - t0) / 3], dtype=torch.float64, device='cuda')
+  if world > 1:
+    dist.all_reduce(copy_s, op=dist.ReduceOp.MAX)
+  copy_only_ms = float(copy_s.item()) * 1e3
 
   # ---- phase split (outside the timed region; explains the number) ----------------------
   # CUDA events on torch's current stream = the stream every kernel of the phase is launched on;
@@ -973,7 +992,10 @@ def run_b200_kshard(args, name, wl, world, rank, local_rank, full, steps=None):
                  'eager_ms': ms_eager, 'graph_ms': ms_graph,
                  'batch_groups': int(os.environ.get('JRB_BATCH_GROUPS', 0))},
       'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': h2d,
-              'd2h_bytes_per_step': d2h, 'path': e2e_path,
+              'd2h_bytes_per_step': d2h, 'path': e2e_path, 'ms_per_step': 1e3 / e2e_value,
+              'copies_alone_ms': copy_only_ms,
+              'copies_alone_note': 'the same H2D + D2H with no kernel in between, all ranks at once: '
+                                   'the PCIe / host-memory floor of this box under e2e',
               'energy_rel_diff_vs_device_path': abs(e2e_energy - sum(energies)) / abs(sum(energies))},
       'gpu_launches': launches, 'roofline': roofline, 'clocks': clk.summary(),
       'phases_ms': phases, 'driver_step': driver, 'energies_ha': energies,

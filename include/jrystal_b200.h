@@ -40,7 +40,7 @@ extern "C" {
 /* xc functionals (jrystal/_src/xc.py:242-253, LDA branch).  Names joined by '+' in the
  * reference are summed; the ids below are the combinations the kernels implement. */
 #define JRB_XC_LDA_X 1
-#define JRB_XC_LDA_X_C_PW 2 /* "lda_x+lda_c_pw" */
+#define JRB_XC_LDA_X_C_PW 2 /* "lda_x+lda_c_pw"; two spin channels: polarised PW92 (xc.py:60-61) */
 /* GGA branch (xc.py:67-112: sigma = |ifftn(i G fftn(rho))|^2, eps(rho, sigma)); unpolarised.
  * The potential is the exact discrete derivative of E_xc = (Omega/N) sum rho eps (what jax.grad
  * gives the reference in energy mode); band mode (kohn_sham) uses the same potential instead of

@@ -316,14 +316,13 @@ k_veff_xc(GridGeom g, const cplx* __restrict__ grid, const double* __restrict__ 
       veff[i] = vhe + xs * (as_eps ? e : vxc);
       acc[0] += (kohn_sham ? vxc : e) * n;
     } else {
-      // exchange only: eps = 1/2 [eps_x(2 rho_up) + eps_x(2 rho_dn)]  (xc.py:56-59)
+      // exchange: eps = 1/2 [eps_x(2 rho_up) + eps_x(2 rho_dn)]  (xc.py:56-59); correlation: the
+      // functional's spin-polarised form (xc.py:60-61)
       const double ru = rho[i], rd = rho[g.n + i];
-      double eu, deu, ed, ded;
-      lda_eps(JRB_XC_LDA_X, 2.0 * ru, eu, deu);
-      lda_eps(JRB_XC_LDA_X, 2.0 * rd, ed, ded);
-      const double e = 0.5 * (eu + ed);
+      double e, deu, ded;
+      lda_pol_eps(xc_id, ru, rd, e, deu, ded);
       const double n = ru + rd;
-      // d eps / d rho_s = eps_x'(2 rho_s)
+      // deu, ded = d eps / d rho_s
       if (kohn_sham) {
         // reference vxc_lda (xc.py:114-122): v_s = eps + rho_s d eps/d rho_s
         const double vu = e + ru * deu, vd = e + rd * ded;
@@ -367,8 +366,8 @@ int launch_grid_potential(jrb_plan* p, const double* rho, int xc_id, int kohn_sh
               "gga_x_pbe+gga_c_pbe)");
     return JRB_EUNSUPPORTED;
   }
-  if (p->ns == 2 && xc_id != JRB_XC_LDA_X) {
-    set_error("jrb_grid_potential: spin-polarised correlation / GGA is not implemented");
+  if (p->ns == 2 && gga) {
+    set_error("jrb_grid_potential: spin-polarised GGA is not implemented");
     return JRB_EUNSUPPORTED;
   }
   if (p->natoms <= 0) {

@@ -936,50 +936,6 @@ k_factor_stream(const cplx* __restrict__ S, int nb, double tol, cplx* __restrict
   tick(3);
 }
 
-// Second Cholesky-QR pass: r = R2 R1, rinv = R1^-1 R2^-1 (all upper triangular, k over [a, b]); a CTA
-// owns 8 rows of one matrix: its rows of R2 and R1^-1 (the operands every lane of a row shares)
-// sit in shared memory, R1 and R2^-1 stream from L2 coalesced along the output columns.
-// grid: (ceil(nb / 8), nsk), block 256 = 8 rows x 32 column lanes; dynamic smem: 2 * 8 * nb complex
-__global__ void __launch_bounds__(256)
-k_compose_rows(const cplx* __restrict__ R2, const cplx* __restrict__ R2inv,
-               const cplx* __restrict__ R1, const cplx* __restrict__ R1inv, int nb,
-               cplx* __restrict__ r_out, cplx* __restrict__ rinv_out) {
-  extern __shared__ __align__(16) unsigned char smem_raw_[];
-  cplx* s2 = reinterpret_cast<cplx*>(smem_raw_);  // [8][nb] rows of R2
-  cplx* s1i = s2 + 8 * nb;                        // [8][nb] rows of R1^-1
-  const long long off = (long long)blockIdx.y * nb * nb;
-  const int a0 = blockIdx.x * 8;
-  for (int e = threadIdx.x; e < 8 * nb; e += 256) {
-    const int al = e / nb, k = e - al * nb;
-    const bool ok = a0 + al < nb;
-    s2[e] = ok ? R2[off + (long long)(a0 + al) * nb + k] : cmake(0.0, 0.0);
-    s1i[e] = ok ? R1inv[off + (long long)(a0 + al) * nb + k] : cmake(0.0, 0.0);
-  }
-  __syncthreads();
-  const int al = threadIdx.x >> 5, lane = threadIdx.x & 31, a = a0 + al;
-  if (a >= nb) return;
-  const cplx* r2 = s2 + al * nb;
-  const cplx* r1i = s1i + al * nb;
-  for (int b = lane; b < nb; b += 32) {
-    double xx = 0.0, xy = 0.0, yx = 0.0, yy = 0.0;
-    if (b >= a) {
-      const cplx* c1 = R1 + off + b;      // R1[k][b] = c1[k nb]
-      const cplx* c2i = R2inv + off + b;  // R2inv[k][b]
-#pragma unroll 4
-      for (int k = a; k <= b; ++k) {
-        const cplx u = r2[k], w = c1[(long long)k * nb];
-        xx += u.x * w.x - u.y * w.y;
-        xy += u.x * w.y + u.y * w.x;
-        const cplx p = r1i[k], q = c2i[(long long)k * nb];
-        yx += p.x * q.x - p.y * q.y;
-        yy += p.x * q.y + p.y * q.x;
-      }
-    }
-    r_out[off + (long long)a * nb + b] = cmake(xx, xy);
-    rinv_out[off + (long long)a * nb + b] = cmake(yx, yy);
-  }
-}
-
 // Adjoint, step 1: M = (sum partial) diag(f); X = -(up(M) + up(M)^H + diag Re M);
 // T1 = diag(f) Rinv^H.   grid: (ceil(nb^2 / 256), nsk)
 __global__ void __launch_bounds__(SMALL_T)
@@ -1326,14 +1282,15 @@ static int factor_stream(jrb_plan* p, CfConfig c, bool pass2, int nsk, const cpl
                : run_factor_stream<6, 1, false>(p, nsk, S, 0.0, Rt, Rit, skip, st);
 }
 
-static int compose_rows(jrb_plan* p, int nsk, const cplx* R2, const cplx* R2inv, const cplx* R1,
-                        const cplx* R1inv, cplx* r_out, cplx* rinv_out, cudaStream_t st) {
-  const int nb = p->nb;
-  const int smem = 2 * 8 * nb * (int)sizeof(cplx);
-  static int once = opt_in_smem(k_compose_rows, 160 * 1024);
-  if (once) return once;
-  k_compose_rows<<<dim3((nb + 7) / 8, nsk), 256, smem, st>>>(R2, R2inv, R1, R1inv, nb, r_out, rinv_out);
-  JRB_CHECK_LAUNCH("k_compose_rows");
+// r = R2 R1, rinv = R1^-1 R2^-1 (all upper triangular): both products as 32 x 32 tiles, one launch
+static int compose_factors(jrb_plan* p, int nsk, const cplx* R2, const cplx* R2inv, const cplx* R1,
+                           const cplx* R1inv, cplx* r_out, cplx* rinv_out, cudaStream_t st) {
+  TileGemmOps ops;
+  ops.A[0] = R2;    ops.B[0] = R1;    ops.C[0] = r_out;
+  ops.A[1] = R1inv; ops.B[1] = R2inv; ops.C[1] = rinv_out;
+  const int nblk = (p->nb + CP - 1) / CP;
+  k_tile_gemm<0><<<dim3(nblk, nblk, 2 * nsk), 256, 0, st>>>(ops, p->nb, nsk);
+  JRB_CHECK_LAUNCH("k_tile_gemm");
   return 0;
 }
 
@@ -1509,7 +1466,7 @@ int launch_qr_apply_phase(jrb_plan* p, int sk0, int nsk, const double* w_re, con
     // one launch: closed form or factorisation + inverse; then the composition with the first pass
     if ((rc = factor_stream(p, cf, true, nsk, S, shortcut ? 1e-10 : 0.0, q.Rt, q.Rit, nullptr, st)))
       return rc;
-    if ((rc = compose_rows(p, nsk, q.Rt, q.Rit, q.R1, q.R1inv, r + q.moff, q.rinv, st))) return rc;
+    if ((rc = compose_factors(p, nsk, q.Rt, q.Rit, q.R1, q.R1inv, r + q.moff, q.rinv, st))) return rc;
     return run_apply<0>(p, nsk, Q1, q.Rit, TRI_UPPER, none, nullptr, TRI_FULL, 1,
                         reinterpret_cast<double*>(qout + q.soff), nullptr, st);
   }
@@ -1528,15 +1485,7 @@ int launch_qr_apply_phase(jrb_plan* p, int sk0, int nsk, const double* w_re, con
   // the regular factorisation stands down where the closed form applied; with a skip list the
   // one-CTA kernels serve (2 launches that return at once instead of 22)
   if ((rc = chol_and_inverse(p, nsk, S, q.Rt, q.Rit, st, skip, skip != nullptr))) return rc;
-  {
-    // r = R2 R1, rinv = R1^-1 R2^-1: both products as 32 x 32 tiles in one launch
-    TileGemmOps ops;
-    ops.A[0] = q.Rt;    ops.B[0] = q.R1;  ops.C[0] = r + q.moff;
-    ops.A[1] = q.R1inv; ops.B[1] = q.Rit; ops.C[1] = q.rinv;
-    const int nblk = (nb + CP - 1) / CP;
-    k_tile_gemm<0><<<dim3(nblk, nblk, 2 * nsk), 256, 0, st>>>(ops, nb, nsk);
-    JRB_CHECK_LAUNCH("k_tile_gemm");
-  }
+  if ((rc = compose_factors(p, nsk, q.Rt, q.Rit, q.R1, q.R1inv, r + q.moff, q.rinv, st))) return rc;
   return run_apply<0>(p, nsk, Q1, q.Rit, TRI_UPPER, none, nullptr, TRI_FULL, 1,
                       reinterpret_cast<double*>(qout + q.soff), nullptr, st);
 }

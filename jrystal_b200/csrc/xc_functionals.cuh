@@ -109,4 +109,47 @@ JRB_XC_FN Dual pbe_eps(int xc_id, double rho, double sigma) {
   return eps;
 }
 
+// x^(4/3) with its derivative, regular at x = 0 (fully polarised points)
+JRB_XC_FN Dual dpow43(Dual a) {
+  const double c = cbrt(a.v > 0.0 ? a.v : 0.0);
+  return dchain(a, a.v * c, (4.0 / 3.0) * c);
+}
+JRB_XC_FN Dual pw92_g(Dual rs, Dual sr, double a, double a1, double b1, double b2, double b3,
+                      double b4) {
+  const Dual q = (2.0 * a) * (b1 * sr + b2 * rs + b3 * (rs * sr) + b4 * (rs * rs));
+  return (-2.0 * a) * ((1.0 + a1 * rs) * dlog1p(dmk(1.0) / q));
+}
+
+// Two spin channels (xc.py:54-64): eps per particle and d eps / d rho_up, d eps / d rho_dn.
+//   exchange:    eps_x = 1/2 [eps_x(2 rho_up) + eps_x(2 rho_dn)]  (the reference's spin-scaling call)
+//   correlation: LibXC lda_c_pw, polarised (xc.py:60-61): PW92 with the spin interpolation
+//                g1 + zeta^4 f (g2 - g1 + g3 / f''(0)) - f g3 / f''(0); Dual slots r, s = d/d rho_up,
+//                d/d rho_dn
+JRB_XC_FN void lda_pol_eps(int xc_id, double ru, double rd, double& eps, double& deu, double& ded) {
+  double eu, ed;
+  lda_eps(JRB_XC_LDA_X, 2.0 * ru, eu, deu);
+  lda_eps(JRB_XC_LDA_X, 2.0 * rd, ed, ded);
+  eps = 0.5 * (eu + ed);
+  if (xc_id != JRB_XC_LDA_X_C_PW) return;
+  const double nt = ru + rd;
+  if (!(nt > 1e-15)) return;
+  const Dual up = dmk(ru, 1.0, 0.0), dn = dmk(rd, 0.0, 1.0);
+  const Dual n = up + dn;
+  const Dual rs = 0.62035049089940001667 * (dmk(1.0) / dcbrt(n));
+  const Dual sr = dsqrt(rs);
+  Dual zeta = (up - dn) / n;
+  if (zeta.v > 1.0) zeta = dmk(1.0);
+  if (zeta.v < -1.0) zeta = dmk(-1.0);
+  const Dual g1 = pw92_g(rs, sr, 0.031091, 0.21370, 7.5957, 3.5876, 1.6382, 0.49294);
+  const Dual g2 = pw92_g(rs, sr, 0.015545, 0.20548, 14.1189, 6.1977, 3.3662, 0.62517);
+  const Dual g3 = pw92_g(rs, sr, 0.016887, 0.11125, 10.357, 3.6231, 0.88026, 0.49671);
+  const double fz20 = 1.709921, fden = 1.0 / (2.5198420997897463295 - 2.0);  // 2^(4/3) - 2
+  const Dual f = fden * (-2.0 + (dpow43(1.0 + zeta) + dpow43(1.0 + (-1.0) * zeta)));
+  const Dual z2 = zeta * zeta, z4 = z2 * z2;
+  const Dual ec = g1 + (z4 * f) * ((g2 - g1) + (1.0 / fz20) * g3) - (1.0 / fz20) * (f * g3);
+  eps += ec.v;
+  deu += ec.r;
+  ded += ec.s;
+}
+
 }  // namespace jrb

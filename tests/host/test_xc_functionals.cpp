@@ -4,6 +4,7 @@
 // differentiated by torch autograd).  One line per point:
 //   lda <xc_id> <n> <eps> <deps/dn>
 //   gga <xc_id> <rho> <sigma> <eps> <deps/drho> <deps/dsigma>
+//   pol <xc_id> <rho_up> <rho_dn> <eps> <deps/drho_up> <deps/drho_dn>
 #include <cstdio>
 #include <initializer_list>
 #include "../../jrystal_b200/csrc/xc_functionals.cuh"
@@ -24,6 +25,17 @@ int main() {
         const double sigma = r * std::pow(n, 8.0 / 3.0) * 30.0;
         const jrb::Dual e = jrb::pbe_eps(id, n, sigma);
         std::printf("gga %d %.17g %.17g %.17g %.17g %.17g\n", id, n, sigma, e.v, e.r, e.s);
+      }
+  // two spin channels: from unpolarised (zeta = 0) over partial to full polarisation (zeta = +-1)
+  const double ntot[] = {1e-9, 1e-4, 0.02, 0.37, 4.2, 55.0};
+  const double zeta[] = {0.0, 0.1, -0.35, 0.8, 0.999, -1.0, 1.0};
+  for (int id : {JRB_XC_LDA_X, JRB_XC_LDA_X_C_PW})
+    for (double n : ntot)
+      for (double z : zeta) {
+        const double ru = 0.5 * n * (1.0 + z), rd = 0.5 * n * (1.0 - z);
+        double e, du, dd;
+        jrb::lda_pol_eps(id, ru, rd, e, du, dd);
+        std::printf("pol %d %.17g %.17g %.17g %.17g %.17g\n", id, ru, rd, e, du, dd);
       }
   return 0;
 }

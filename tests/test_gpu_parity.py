@@ -273,10 +273,12 @@ def test_rows_plan_rejects_grid_calls(cuda_device):
     check(_check)
 
 
+@pytest.mark.parametrize('xc', ['lda_x', 'lda_x+lda_c_pw'])
 @pytest.mark.parametrize('case', ['diamond_12', 'si8_64'])
-def test_spin_polarised_energy_and_grad(cuda_device, case):
+def test_spin_polarised_energy_and_grad(cuda_device, case, xc):
   """Two spin channels (spin_restricted=False, pw.py:88-91 ns = 2): spin-scaled LDA exchange
-  (xc.py:54-64), per-spin densities and potentials, gradients of both channels."""
+  (xc.py:54-59) and the functional's own polarised form for the correlation (xc.py:60-61, PW92
+  with the spin interpolation), per-spin densities and potentials, gradients of both channels."""
   import jrystal_b200 as jb
   c = CASES[case]
   s = make_system(c['name'], c['grid'], c['kgrid'], c['cutoff'], c['mask'])
@@ -285,12 +287,12 @@ def test_spin_polarised_energy_and_grad(cuda_device, case):
   occ = rp.occupation_uniform(s.num_k, s.num_electrons, spin=2, num_bands=nb,
                               spin_restricted=False).numpy()
   occ = occ * (1.0 + 0.1 * np.random.default_rng(5).random(occ.shape))
-  ref = rp.energy_and_grad(s, p['w_re'], p['w_im'], occ, occ_grad=True)
+  ref = rp.energy_and_grad(s, p['w_re'], p['w_im'], occ, xc=xc, occ_grad=True)
   plan = jb.Plan(s.cell, s.mask, s.kpts, nb, num_spin=2)
   plan.set_atoms(s.positions, s.charges)
   occ_d = to_dev(occ)
   rho, e_kin = plan.eval_begin(to_dev(p['w_re']), to_dev(p['w_im']), occ_d)
-  en, g_re, g_im, g_occ = plan.eval_finish(occ_d, rho, e_kin, 'lda_x', want_occ_grad=True)
+  en, g_re, g_im, g_occ = plan.eval_finish(occ_d, rho, e_kin, xc, want_occ_grad=True)
   en = en.cpu().numpy()
   assert abs(en.sum() - ref['e_tot']) / abs(ref['e_tot']) < E_TOL
   assert rho.shape[0] == 2 and relerr(rho.cpu().numpy(), ref['density']) < G_TOL

@@ -53,11 +53,29 @@ def test_device_xc_functionals_on_the_host(tmp_path):
   gga = {3: ['gga_x_pbe'], 4: ['gga_x_pbe', 'gga_c_pbe']}
   fns = {'lda_x': rp._eps_lda_x, 'lda_c_pw': rp._eps_lda_c_pw,
          'gga_x_pbe': rp._eps_gga_x_pbe, 'gga_c_pbe': rp._eps_gga_c_pbe}
-  n_lda = n_gga = 0
+  n_lda = n_gga = n_pol = 0
   for ln in lines:
     tok = ln.split()
     vals = [float(t) for t in tok[2:]]
     xc_id = int(tok[1])
+    if tok[0] == 'pol':
+      # two spin channels (xc.py:54-64): spin-scaled exchange + the polarised PW92 correlation
+      ru, rd, eps, d_up, d_dn = vals
+      rho = torch.tensor([[ru], [rd]], dtype=torch.float64, requires_grad=True)
+      parts = [rp._lda(f, rho) for f in lda[xc_id]]
+      e = sum(parts)
+      (g,) = torch.autograd.grad(e.sum(), rho, retain_graph=True)
+      scale = sum(torch.autograd.grad(p_.sum(), rho, retain_graph=True)[0].abs().max().item()
+                  for p_ in parts)
+      assert abs(eps - e.item()) <= 1e-12 * abs(e.item()), ln
+      # an empty channel: the exchange derivative of that channel is switched off below the
+      # threshold on both sides; (1 -+ zeta)^(1/3) has an infinite slope there, not compared
+      if ru > 1e-15:
+        assert abs(d_up - g[0].item()) <= 1e-9 * scale, ln
+      if rd > 1e-15:
+        assert abs(d_dn - g[1].item()) <= 1e-9 * scale, ln
+      n_pol += 1
+      continue
     if tok[0] == 'lda':
       n, eps, deps = vals
       x = torch.tensor([n], dtype=torch.float64, requires_grad=True)
@@ -89,4 +107,4 @@ def test_device_xc_functionals_on_the_host(tmp_path):
         assert abs(d_rho - dr.item()) <= 1e2 * tol * max(scale_r, 1e-300), ln
         assert abs(d_sigma - ds.item()) <= 1e2 * tol * max(scale_s, 1e-300), ln
       n_gga += 1
-  assert n_lda == 24 and n_gga == 132
+  assert n_lda == 24 and n_gga == 132 and n_pol == 84
