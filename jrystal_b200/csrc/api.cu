@@ -48,9 +48,9 @@ extern "C" int jrb_set_nonlocal(jrb_plan* p, const double* phi, int32_t nproj, j
   if (p->nproj > 0) {  // give back what the previous table was charged (the band driver sets one per k-point)
     const size_t old_phi = (size_t)p->nk * p->nproj * p->ng;
     const size_t old_p = (size_t)p->ns * p->nk * p->nproj * p->nb;
-    p->ws_bytes -= (int64_t)((old_phi + 17 * old_p) * sizeof(cplx));
+    p->ws_bytes -= (int64_t)((2 * old_phi + 18 * old_p) * sizeof(cplx));
   }
-  for (cplx** q : {&p->d_nl_phi, &p->d_nl_p, &p->d_nl_part}) {
+  for (cplx** q : {&p->d_nl_phi, &p->d_nl_p, &p->d_nl_part, &p->d_nl_phit, &p->d_nl_ps}) {
     if (*q) cudaFree(*q);
     *q = nullptr;
   }
@@ -62,10 +62,12 @@ extern "C" int jrb_set_nonlocal(jrb_plan* p, const double* phi, int32_t nproj, j
   JRB_CUDA(cudaMalloc(&p->d_nl_phi, nphi * sizeof(cplx)));
   JRB_CUDA(cudaMalloc(&p->d_nl_p, np * sizeof(cplx)));
   JRB_CUDA(cudaMalloc(&p->d_nl_part, 16 * np * sizeof(cplx)));
+  JRB_CUDA(cudaMalloc(&p->d_nl_phit, nphi * sizeof(cplx)));
+  JRB_CUDA(cudaMalloc(&p->d_nl_ps, np * sizeof(cplx)));
   JRB_CUDA(cudaMemcpyAsync(p->d_nl_phi, phi, nphi * sizeof(cplx), cudaMemcpyDeviceToDevice, S(st)));
   p->nproj = nproj;
-  p->ws_bytes += (int64_t)((nphi + 17 * np) * sizeof(cplx));
-  return 0;
+  p->ws_bytes += (int64_t)((2 * nphi + 18 * np) * sizeof(cplx));
+  return launch_nonlocal_transpose(p, S(st));  // conj(Phi)^T: the tall operand of the DMMA products
 }
 
 extern "C" int jrb_nonlocal_energy(jrb_plan* p, const double* q, const double* occ, double* e_nl,

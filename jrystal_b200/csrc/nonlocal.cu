@@ -10,9 +10,12 @@
 //     P[s,k,p,b] = sum_g Phi[k,p,g] Q[s,k,g,b]            (k_nl_project, split over row chunks)
 //     E_nl       = sum f_b |P[p,b]|^2 / vol               (k_nl_energy)
 //     HQ[g,b]   += sum_p conj(Phi[k,p,g]) P[p,b] / vol    (k_nl_apply)  = dE_nl/dQ* per unit f
-// First version: FP64 FMA kernels with shared-memory tiles (the products are ng x nproj x nb per
-// (spin,k): small next to the FFT work); a DMMA version belongs with rectangular Gram/apply tiles.
+// Both products run on the FP64 tensor cores (DMMA) through the rectangular forms of the QR
+// kernels (qr_gemm.cuh: k_gram with GramRect, k_apply with ApplyRect) on Phit = conj(Phi)^T, the
+// [ng][nproj] tall operand built once by jrb_set_nonlocal; the FP64-FMA tile kernels below are
+// kept as the reference path (JRB_NL_FMA=1).
 #include <algorithm>
+#include <cstdlib>
 
 #include "plan.h"
 
@@ -78,9 +81,9 @@ k_nl_project(const cplx* __restrict__ phi, const cplx* __restrict__ q, long long
     }
 }
 
-// P = sum of the chunk partials (fixed order).  grid: (ceil(nsk*nproj*nb / 256))
+// P = sum of the chunk partials (fixed order), Ps = P / vol.  grid: (ceil(nsk*nproj*nb / 256))
 __global__ void k_nl_reduce(const cplx* __restrict__ partial, int nchunks, long long n,
-                            cplx* __restrict__ P) {
+                            cplx* __restrict__ P, cplx* __restrict__ Ps, double inv_vol) {
   const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (i >= n) return;
   cplx s = cmake(0.0, 0.0);
@@ -89,6 +92,42 @@ __global__ void k_nl_reduce(const cplx* __restrict__ partial, int nchunks, long 
     s.x += v.x; s.y += v.y;
   }
   P[i] = s;
+  Ps[i] = cmake(s.x * inv_vol, s.y * inv_vol);
+}
+
+// Phit[k][g][p] = conj(Phi[k][p][g]) through a 32 x 32 shared-memory tile.
+// grid: (ceil(ng / 32), ceil(nproj / 32), nk), block (32, 8)
+__global__ void __launch_bounds__(256)
+k_nl_transpose(const cplx* __restrict__ phi, long long ng, int nproj, cplx* __restrict__ phit) {
+  __shared__ cplx tile[32][33];
+  const long long g0 = (long long)blockIdx.x * 32;
+  const int p0 = blockIdx.y * 32, k = blockIdx.z;
+  for (int j = threadIdx.y; j < 32; j += 8) {
+    const long long g = g0 + threadIdx.x;
+    const int pp = p0 + j;
+    tile[j][threadIdx.x] = (g < ng && pp < nproj) ? phi[((long long)k * nproj + pp) * ng + g] : cmake(0.0, 0.0);
+  }
+  __syncthreads();
+  for (int j = threadIdx.y; j < 32; j += 8) {
+    const long long g = g0 + j;
+    const int pp = p0 + threadIdx.x;
+    if (g < ng && pp < nproj) phit[((long long)k * ng + g) * nproj + pp] = cconj(tile[threadIdx.x][j]);
+  }
+}
+
+int launch_nonlocal_transpose(jrb_plan* p, cudaStream_t st) {
+  dim3 grid((unsigned)((p->ng + 31) / 32), (p->nproj + 31) / 32, p->nk), block(32, 8);
+  k_nl_transpose<<<grid, block, 0, st>>>(p->d_nl_phi, p->ng, p->nproj, p->d_nl_phit);
+  JRB_CHECK_LAUNCH("k_nl_transpose");
+  return 0;
+}
+
+static bool nl_use_fma() {
+  static int v = [] {
+    const char* env = std::getenv("JRB_NL_FMA");
+    return env ? std::atoi(env) : 0;
+  }();
+  return v != 0;
 }
 
 // part[blk] = sum over a slice of (sk, p, b) of occ[sk][b] |P|^2; then one CTA adds the slices in
@@ -174,14 +213,27 @@ k_nl_apply(const cplx* __restrict__ phi, const cplx* __restrict__ P, long long n
 
 // P of the (spin,k) range [sk0, sk0 + nsk) into p->d_nl_p (indexed from sk0)
 int launch_nonlocal_project(jrb_plan* p, int sk0, int nsk, const cplx* q, cudaStream_t st) {
-  const int nbt = (p->nb + NL_TB - 1) / NL_TB, npt = (p->nproj + 2 * NL_TP - 1) / (2 * NL_TP);
-  dim3 grid(npt * nbt, nsk, NL_CHUNKS), block(16, 16);
-  k_nl_project<<<grid, block, 0, st>>>(p->d_nl_phi, q + (long long)sk0 * p->ng * p->nb, p->ng, p->nb,
-                                      p->nproj, p->nk, sk0, p->d_nl_part);
-  JRB_CHECK_LAUNCH("k_nl_project");
+  int nchunks = NL_CHUNKS;
+  if (nl_use_fma()) {
+    const int nbt = (p->nb + NL_TB - 1) / NL_TB, npt = (p->nproj + 2 * NL_TP - 1) / (2 * NL_TP);
+    dim3 grid(npt * nbt, nsk, NL_CHUNKS), block(16, 16);
+    k_nl_project<<<grid, block, 0, st>>>(p->d_nl_phi, q + (long long)sk0 * p->ng * p->nb, p->ng, p->nb,
+                                        p->nproj, p->nk, sk0, p->d_nl_part);
+    JRB_CHECK_LAUNCH("k_nl_project");
+  } else {
+    // P = Phi Q = conj(Phit)^T Q on DMMA; the k-point of item sk0 + i is (sk0 + i) % nk: the range
+    // never wraps a spin boundary in the middle of a call unless it starts at a multiple of nk
+    nchunks = (int)std::max<long long>(1, std::min<long long>(NL_CHUNKS, p->ng / 256));
+    const int k0 = sk0 % p->nk;
+    int rc = launch_gram_rect(p, nsk, p->d_nl_phit + (long long)k0 * p->ng * p->nproj, p->nproj,
+                              p->nk - k0 >= nsk ? nsk : p->nk, q + (long long)sk0 * p->ng * p->nb,
+                              nchunks, p->d_nl_part, st);
+    if (rc) return rc;
+  }
   const long long n = (long long)nsk * p->nproj * p->nb;
-  k_nl_reduce<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(p->d_nl_part, NL_CHUNKS, n,
-                                                          p->d_nl_p + (long long)sk0 * p->nproj * p->nb);
+  k_nl_reduce<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(
+    p->d_nl_part, nchunks, n, p->d_nl_p + (long long)sk0 * p->nproj * p->nb,
+    p->d_nl_ps + (long long)sk0 * p->nproj * p->nb, 1.0 / p->vol);
   JRB_CHECK_LAUNCH("k_nl_reduce");
   return 0;
 }
@@ -198,6 +250,14 @@ int launch_nonlocal_energy(jrb_plan* p, const double* occ, double* e_inout, cuda
 }
 
 int launch_nonlocal_apply(jrb_plan* p, int sk0, int nsk, cplx* hq, cudaStream_t st) {
+  if (!nl_use_fma()) {
+    // hq += Phi^H P / vol = Phit (P / vol) on DMMA
+    const int k0 = sk0 % p->nk;
+    return launch_apply_rect(p, nsk, p->d_nl_phit + (long long)k0 * p->ng * p->nproj, p->nproj,
+                             p->nk - k0 >= nsk ? nsk : p->nk,
+                             p->d_nl_ps + (long long)sk0 * p->nproj * p->nb,
+                             hq + (long long)sk0 * p->ng * p->nb, st);
+  }
   dim3 grid((unsigned)((p->ng + NL_TG - 1) / NL_TG), (p->nb + NL_TB - 1) / NL_TB, nsk), block(32, 8);
   k_nl_apply<<<grid, block, 0, st>>>(p->d_nl_phi, p->d_nl_p + (long long)sk0 * p->nproj * p->nb,
                                      p->ng, p->nb, p->nproj, p->nk, sk0, 1.0 / p->vol,

@@ -167,7 +167,7 @@ extern "C" int jrb_plan_destroy(jrb_plan* p) {
   delete[] p->h_freq;
   delete[] p->h_kpts;
   void* ptrs[] = {p->d_zmap, p->d_ycol, p->d_xmap, p->d_gidx, p->d_gk2, p->d_tw_x, p->d_tw_y,
-                  p->d_tw_z, p->d_tw_half, p->d_a_keep, p->d_pos, p->d_chg, p->d_atom_part, p->d_nl_phi, p->d_nl_p, p->d_nl_part, p->d_ws_a, p->d_ws_b, p->d_rho_part, p->d_seg_z, p->d_focc, p->d_grid, p->d_vext,
+                  p->d_tw_z, p->d_tw_half, p->d_a_keep, p->d_pos, p->d_chg, p->d_atom_part, p->d_nl_phi, p->d_nl_p, p->d_nl_part, p->d_nl_phit, p->d_nl_ps, p->d_ws_a, p->d_ws_b, p->d_rho_part, p->d_seg_z, p->d_focc, p->d_grid, p->d_vext,
                   p->d_partials, p->d_veff, p->d_gga, p->d_vxc, p->d_q, p->d_hq, p->d_tmp, p->d_r, p->d_rinv, p->d_small, p->d_gpart,
                   p->d_tkb, p->d_eps, p->d_sphere_part, p->d_scal, p->d_skip, p->d_emax, p->d_wre, p->d_wim, p->d_gre, p->d_gim,
                   p->d_occ, p->d_rho, p->d_en};

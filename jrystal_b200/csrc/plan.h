@@ -95,6 +95,8 @@ struct jrb_plan {
   jrb::cplx* d_nl_phi;   // [nk][nproj][ng]
   jrb::cplx* d_nl_p;     // [ns*nk][nproj][nb]  P = Phi Q
   jrb::cplx* d_nl_part;  // [16 chunks][ns*nk][nproj][nb]
+  jrb::cplx* d_nl_phit;  // [nk][ng][nproj] conj(Phi) transposed: the tall operand of the DMMA products
+  jrb::cplx* d_nl_ps;    // [ns*nk][nproj][nb]  P / vol (the small operand of the apply)
   int nl_p_valid;        // d_nl_p holds Phi Q of the plan's own Q (jrb_eval_begin -> jrb_eval_finish)
   // evaluation work space (Q, R, R^-1, HQ, W-sized temp)
   jrb::cplx *d_q, *d_hq, *d_tmp;
@@ -190,6 +192,12 @@ int launch_density_partial(jrb_plan* p, const cplx* q, const double* occ, double
 
 // qr.cu
 int qr_gram_partial_mats(const jrb_plan* p);
+// rectangular products on the DMMA Gram / apply kernels (projector products, nonlocal.cu)
+int launch_gram_rect(jrb_plan* p, int nsk, const cplx* At, int nbA, int a_mod, const cplx* B,
+                     int nchunks, cplx* partial, cudaStream_t st);
+int launch_apply_rect(jrb_plan* p, int nsk, const cplx* In, int kdim, int in_mod, const cplx* T,
+                      cplx* out, cudaStream_t st);
+int launch_nonlocal_transpose(jrb_plan* p, cudaStream_t st);
 // split-phase QR (row-sharded callers all-reduce S / M between the phases)
 int launch_qr_gram_phase(jrb_plan* p, int sk0, int nsk, const double* w_re, const double* w_im,
                          int pass, cplx* S, cudaStream_t st);

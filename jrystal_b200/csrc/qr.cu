@@ -1200,6 +1200,59 @@ static int run_apply(jrb_plan* p, int nsk, TallMat in1, const cplx* t1, int tri1
   return run_apply_ncb<MODE, 9, false>(p, nsk, in1, t1, tri1, in2, t2, tri2, nterms, out_a, out_b, st);
 }
 
+// Rectangular products on the same DMMA kernels (the projector products of the non-local
+// pseudopotential, nonlocal.cu):
+//   gram : partial[chunk][sk][i][j] = sum_{g in chunk} conj(At[sk % a_mod][g][i]) B[sk][g][j]
+//   apply: out[sk][g][j] += sum_i In[sk % in_mod][g][i] T[sk][i][j]
+int launch_gram_rect(jrb_plan* p, int nsk, const cplx* At, int nbA, int a_mod, const cplx* B,
+                     int nchunks, cplx* partial, cudaStream_t st) {
+  constexpr int ST = 3;
+  const int ti = (nbA + QT - 1) / QT, tj = (p->nb + QT - 1) / QT;
+  long long rows = (p->ng + nchunks - 1) / nchunks;
+  rows = (rows + QK - 1) / QK * QK;
+  dim3 grid(ti * tj, nchunks, nsk);
+  const int smem = 2 * ST * QK * QLDB * (int)sizeof(cplx);
+  TallMat A{reinterpret_cast<const double*>(At), nullptr, nbA};
+  TallMat Bm{reinterpret_cast<const double*>(B), nullptr, p->nb};
+  const GramRect rect{p->nb, (long long)p->ng * nbA, a_mod};
+  const int blocks = ((std::min(nbA, QT) + 7) / 8) * ((std::min(p->nb, QT) + 7) / 8);
+  if (blocks <= 8 * QSLOT_DIAG) {
+    static int once = opt_in_smem(k_gram<ST, QSLOT_DIAG>, 2 * ST * QK * QLDB * (int)sizeof(cplx));
+    if (once) return once;
+    k_gram<ST, QSLOT_DIAG><<<grid, QTHREADS, smem, st>>>(A, Bm, 0, p->ng, nbA, p->ng * p->nb, 0, rows,
+                                                        partial, rect);
+  } else {
+    static int once = opt_in_smem(k_gram<ST, QMAXSLOT>, 2 * ST * QK * QLDB * (int)sizeof(cplx));
+    if (once) return once;
+    k_gram<ST, QMAXSLOT><<<grid, QTHREADS, smem, st>>>(A, Bm, 0, p->ng, nbA, p->ng * p->nb, 0, rows,
+                                                      partial, rect);
+  }
+  JRB_CHECK_LAUNCH("k_gram (rectangular)");
+  return 0;
+}
+
+template <int NCB>
+static int run_apply_rect(jrb_plan* p, int nsk, const cplx* In, int kdim, int in_mod, const cplx* T,
+                          cplx* out, cudaStream_t st) {
+  constexpr int ST = 2;
+  const int smem = ST * (QROWS * QLDA + QK * (8 * NCB + 2)) * (int)sizeof(cplx);
+  static int once = opt_in_smem(k_apply<0, NCB, ST, false>, smem);
+  if (once) return once;
+  dim3 grid((unsigned)((p->ng + QROWS - 1) / QROWS), (p->nb + 8 * NCB - 1) / (8 * NCB), nsk);
+  const ApplyRect rect{kdim, (long long)p->ng * kdim, in_mod};
+  k_apply<0, NCB, ST, false><<<grid, QTHREADS, smem, st>>>(
+    reinterpret_cast<const double*>(In), nullptr, T, TRI_FULL, nullptr, nullptr, TRI_FULL, 1, p->ng,
+    p->nb, p->ng * p->nb, reinterpret_cast<double*>(out), nullptr, rect);
+  JRB_CHECK_LAUNCH("k_apply (rectangular)");
+  return 0;
+}
+
+int launch_apply_rect(jrb_plan* p, int nsk, const cplx* In, int kdim, int in_mod, const cplx* T,
+                      cplx* out, cudaStream_t st) {
+  if (p->nb <= 32) return run_apply_rect<4>(p, nsk, In, kdim, in_mod, T, out, st);
+  return run_apply_rect<9>(p, nsk, In, kdim, in_mod, T, out, st);
+}
+
 // H_ij = <q_i | hq_j> for Hermitian H (hamiltonian.hamiltonian_matrix): one Gram on DMMA
 int launch_hamiltonian_matrix(jrb_plan* p, const cplx* q, const cplx* hq, cplx* h, cudaStream_t st) {
   int nchunks = 0, rc = 0;

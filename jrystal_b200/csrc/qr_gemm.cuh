@@ -90,29 +90,47 @@ struct TallMat {
 // LDB_T: panel leading dimension; 0 = narrow panels sized at run time (ldb = pw + 2, still == 2 mod
 // 8), used with a deeper ring for nb <= 32 where a 16-row stage carries too few DMMAs to hide the
 // load latency behind a 3-stage ring.
+// Rectangular form (GramRect with nbB > 0): A has nb columns, B has nbB, every super-tile pair
+// (ti, tj) is computed (grid.x = tiles_A * tiles_B), A is indexed by sk % a_mod with its own
+// stride -- the projector product P = Phi Q of the non-local pseudopotential, where Phi belongs
+// to the k-point, not to (spin, k).
+struct GramRect {
+  int nbB;              // 0: square Gram (the QR products)
+  long long a_stride;   // elements between consecutive A matrices
+  int a_mod;            // A matrix of item sk is sk % a_mod
+};
 template <int STAGES, int MAXSLOT, int LDB_T = QLDB>
 __global__ void __launch_bounds__(QTHREADS, (MAXSLOT <= 2 ? 3 : (MAXSLOT <= 6 ? 2 : 1)))
 k_gram(TallMat A, TallMat B, int same, long long ng, int nb, long long sk_stride, int ntiles,
-       long long rows_per_chunk, cplx* __restrict__ partial) {
+       long long rows_per_chunk, cplx* __restrict__ partial, GramRect rect = GramRect{0, 0, 1}) {
   extern __shared__ __align__(16) unsigned char smem_raw_[];
   cplx* sA = reinterpret_cast<cplx*>(smem_raw_);
-  // upper super-tile (ti <= tj) of this CTA
-  int ti = 0, rem = blockIdx.x;
-  while (rem >= ntiles - ti) {
-    rem -= ntiles - ti;
-    ++ti;
+  const int nbB = rect.nbB > 0 ? rect.nbB : nb;
+  int ti = 0, tj;
+  if (rect.nbB > 0) {
+    const int ntj = (nbB + QT - 1) / QT;
+    ti = blockIdx.x / ntj;
+    tj = blockIdx.x % ntj;
+  } else {
+    // upper super-tile (ti <= tj) of this CTA
+    int rem = blockIdx.x;
+    while (rem >= ntiles - ti) {
+      rem -= ntiles - ti;
+      ++ti;
+    }
+    tj = ti + rem;
   }
-  const int tj = ti + rem;
-  const bool diag = ti == tj;
+  const bool diag = rect.nbB == 0 && ti == tj;
   const bool one_panel = same && diag;
 
   const int chunk = blockIdx.y, sk = blockIdx.z, nsk = gridDim.z;
   const long long g_begin = (long long)chunk * rows_per_chunk;
   const long long g_end = min(ng, g_begin + rows_per_chunk);
   const int i0 = ti * QT, j0 = tj * QT;
-  const int wi_cols = min(QT, nb - i0), wj_cols = min(QT, nb - j0);
+  const int wi_cols = min(QT, nb - i0), wj_cols = min(QT, nbB - j0);
   const int nbi = (wi_cols + 7) >> 3, nbj = (wj_cols + 7) >> 3;
-  const TallMat a = A.offset(sk * sk_stride), bm = B.offset(sk * sk_stride);
+  const TallMat a = rect.nbB > 0 ? A.offset((sk % rect.a_mod) * rect.a_stride) : A.offset(sk * sk_stride);
+  const TallMat bm = B.offset(sk * sk_stride);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int lr = lane >> 2, lc = lane & 3;
   const int nsteps = g_end > g_begin ? (int)((g_end - g_begin + QK - 1) / QK) : 0;
@@ -219,15 +237,15 @@ k_gram(TallMat A, TallMat B, int same, long long ng, int nb, long long sk_stride
     }
   }
   cp_async_wait<0>();
-  cplx* out = partial + ((long long)chunk * nsk + sk) * nb * nb;
+  cplx* out = partial + ((long long)chunk * nsk + sk) * nb * nbB;
 #pragma unroll
   for (int s = 0; s < MAXSLOT; ++s) {
     if (blk[s] >= 0) {
       const int i = i0 + (blk[s] & 0xffff) + lr;
       const int j = j0 + (blk[s] >> 16) + 2 * lc;
       if (i < nb) {
-        if (j < nb) out[(long long)i * nb + j] = cmake(cre[s][0], cim[s][0]);
-        if (j + 1 < nb) out[(long long)i * nb + j + 1] = cmake(cre[s][1], cim[s][1]);
+        if (j < nbB) out[(long long)i * nbB + j] = cmake(cre[s][0], cim[s][0]);
+        if (j + 1 < nbB) out[(long long)i * nbB + j + 1] = cmake(cre[s][1], cim[s][1]);
       }
     }
   }
@@ -297,12 +315,21 @@ struct ApplyDispatch {
 
 // few bands (NCB <= 4): the k-loop is 2-4 steps, the kernel streams rows; three resident CTAs
 // (84 registers) overlap more row tiles
+// Rectangular form (ApplyRect with kdim > 0): In1 is [ng][kdim] (its own stride, indexed by
+// sk % in_mod), T1 is [kdim][nb], and the product is ADDED to the interleaved complex output --
+// hq += Phi^H P of the non-local pseudopotential.  MODE 0, one term, TRI_FULL only.
+struct ApplyRect {
+  int kdim;             // 0: square (the QR products: In1 is [ng][nb], T is [nb][nb])
+  long long in_stride;
+  int in_mod;
+};
 template <int MODE, int NCB, int STAGES, bool SPLIT>
 __global__ void __launch_bounds__(QTHREADS, (NCB <= 4 ? 3 : 2))
 k_apply(const double* __restrict__ in1_re, const double* __restrict__ in1_im,
         const cplx* __restrict__ T1, int tri1, const cplx* __restrict__ in2,
         const cplx* __restrict__ T2, int tri2, int nterms, long long ng, int nb,
-        long long sk_stride, double* __restrict__ out_a, double* __restrict__ out_b) {
+        long long sk_stride, double* __restrict__ out_a, double* __restrict__ out_b,
+        ApplyRect rect = ApplyRect{0, 0, 1}) {
   constexpr int LDB = 8 * NCB + 2;
   constexpr int ALOADS = QROWS * QK / QTHREADS;                    // 4
   constexpr int BLOADS = (QK * 8 * NCB + QTHREADS - 1) / QTHREADS;
@@ -318,12 +345,13 @@ k_apply(const double* __restrict__ in1_re, const double* __restrict__ in1_im,
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int lr = lane >> 2, lc = lane & 3;
   const long long skoff = (long long)sk * sk_stride;
-  const cplx* t1 = T1 + (long long)sk * nb * nb;
+  const int kdim = rect.kdim > 0 ? rect.kdim : nb;   // rows of T1 = columns of In1
+  const cplx* t1 = T1 + (long long)sk * kdim * nb;
   const cplx* t2 = nterms > 1 ? T2 + (long long)sk * nb * nb : t1;
 
   // k-range of each term for this column tile (multiples of 4 at the lower end)
   const int kb1 = tri1 == TRI_LOWER ? (j0 & ~3) : 0;
-  const int ke1 = tri1 == TRI_UPPER ? jend : nb;
+  const int ke1 = tri1 == TRI_UPPER ? jend : kdim;
   const int kb2 = tri2 == TRI_LOWER ? (j0 & ~3) : 0;
   const int ke2 = nterms > 1 ? (tri2 == TRI_UPPER ? jend : nb) : kb2;
   const int ns1 = (ke1 - kb1 + QK - 1) / QK;
@@ -335,7 +363,11 @@ k_apply(const double* __restrict__ in1_re, const double* __restrict__ in1_im,
   bool arow_ok[ALOADS];
 #pragma unroll
   for (int q = 0; q < ALOADS; ++q) arow_ok[q] = g0 + ar + (QTHREADS / QK) * q < ng;
-  const long long a_off = skoff + (g0 + ar) * (long long)nb + ac;  // + 16 q nb + k0
+  // + 16 q ld + k0; the rectangular In1 has its own leading dimension, stride and index
+  const long long a_off = rect.kdim > 0
+                            ? (long long)(sk % rect.in_mod) * rect.in_stride + (g0 + ar) * (long long)kdim + ac
+                            : skoff + (g0 + ar) * (long long)nb + ac;
+  const int ld_in = kdim;
   int b_r[BLOADS], b_c[BLOADS];
 #pragma unroll
   for (int q = 0; q < BLOADS; ++q) {
@@ -354,7 +386,7 @@ k_apply(const double* __restrict__ in1_re, const double* __restrict__ in1_im,
 #pragma unroll
     for (int q = 0; q < ALOADS; ++q) {
       const bool v = arow_ok[q] && kok;
-      const long long o = v ? a_off + (long long)(QTHREADS / QK) * q * nb + k0 : 0;
+      const long long o = v ? a_off + (long long)(QTHREADS / QK) * q * (second ? nb : ld_in) + k0 : 0;
       cplx* d = da + (QTHREADS / QK) * q * QLDA;
       if (SPLIT && !second) {
         cp_async8(&d->x, in1_re + o, v);
@@ -415,8 +447,13 @@ k_apply(const double* __restrict__ in1_re, const double* __restrict__ in1_im,
       const int j = j0 + 8 * u + 2 * lc;
       if (MODE == 0) {
         cplx* o = reinterpret_cast<cplx*>(out_a) + skoff + g * nb + j;
-        if (j < nb) o[0] = cmake(cre[u][0], cim[u][0]);
-        if (j + 1 < nb) o[1] = cmake(cre[u][1], cim[u][1]);
+        if (rect.kdim > 0) {  // accumulate
+          if (j < nb) o[0] = cmake(o[0].x + cre[u][0], o[0].y + cim[u][0]);
+          if (j + 1 < nb) o[1] = cmake(o[1].x + cre[u][1], o[1].y + cim[u][1]);
+        } else {
+          if (j < nb) o[0] = cmake(cre[u][0], cim[u][0]);
+          if (j + 1 < nb) o[1] = cmake(cre[u][1], cim[u][1]);
+        }
       } else {
         const long long o = skoff + g * nb + j;
         if (j < nb) {
