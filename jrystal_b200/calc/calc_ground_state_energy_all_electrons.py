@@ -143,14 +143,25 @@ def minimise(config: JrystalConfigDict, plan: Optional[Plan] = None, use_cuda_gr
   sched = temperature_scheduler(config)
   state = {'i': 0, 'entropy': entropy}
 
+  # On a k mesh the partial densities are all-reduced inside the library over NVLink peer memory
+  # (jrb_eval with the plan's communicator) when that can be set up, else by torch.distributed
+  # between jrb_eval_begin and jrb_eval_finish; one GPU: the one-call evaluation.
+  peer = bool(use_k_mesh and hasattr(plan, 'comm_init') and plan.comm_init())
+  one_call = hasattr(plan, 'eval') and (peer or not use_k_mesh)
+
+  def evaluate(want_occ_grad):
+    if one_call:
+      return plan.eval(w_re, w_im, occ, config.xc, want_occ_grad=want_occ_grad, out=out, rho=rho)[3]
+    plan.eval_begin(w_re, w_im, occ, rho, e_kin)
+    if use_k_mesh:
+      parallel.allreduce_density(rho, e_kin, dbuf)
+    return plan.eval_finish(occ, rho, e_kin, config.xc, want_occ_grad=want_occ_grad, out=out)[3]
+
   def step():
     if trainable:
       o = get_occupation()
       occ.copy_(o.detach()[:, k0:k1])
-    plan.eval_begin(w_re, w_im, occ, rho, e_kin)
-    if use_k_mesh:
-      parallel.allreduce_density(rho, e_kin, dbuf)
-    _, _, _, g_occ = plan.eval_finish(occ, rho, e_kin, config.xc, want_occ_grad=trainable, out=out)
+    g_occ = evaluate(trainable)
     optimizer.step([out[1], out[2]])
     if trainable:
       # d(free energy)/d(occupation parameters): dE/d occ from the evaluation, chained through the
@@ -169,7 +180,7 @@ def minimise(config: JrystalConfigDict, plan: Optional[Plan] = None, use_cuda_gr
   graph = None
   step()  # warm-up outside the capture (one-time attribute calls); counts as step 0
   first_energy = float(out[0].sum().item())
-  if use_cuda_graph and dev.type == 'cuda' and not use_k_mesh and not trainable:
+  if use_cuda_graph and dev.type == 'cuda' and (peer or not use_k_mesh) and not trainable:
     graph = torch.cuda.CUDAGraph()
     with torch.cuda.graph(graph):
       step()
@@ -200,10 +211,7 @@ def minimise(config: JrystalConfigDict, plan: Optional[Plan] = None, use_cuda_gr
     occ_t = get_occupation().detach()
     occ.copy_(occ_t[:, k0:k1])
     state['entropy'] = float(occupation.fermi_dirac_entropy_torch(occ_t, config.eps))
-  plan.eval_begin(w_re, w_im, occ, rho, e_kin)
-  if use_k_mesh:
-    parallel.allreduce_density(rho, e_kin, dbuf)
-  plan.eval_finish(occ, rho, e_kin, config.xc, out=out)
+  evaluate(False)
   en = out[0].cpu().numpy()
   energies = dict(kinetic=float(en[0]), external=float(en[1]), hartree=float(en[2]),
                   xc=float(en[3]), ewald=float(ew), entropy=float(state['entropy']))
