@@ -871,32 +871,25 @@ def run_b200_kshard(args, name, wl, world, rank, local_rank, full, steps=None):
   copy_only_ms = float(copy_s.item()) * 1e3
 
   # ---- phase split (outside the timed region; explains the number) ----------------------
-  # CUDA events on torch's current stream = the stream every kernel of the phase is launched on;
-  # outputs are preallocated so no allocator call lands inside a timed phase.
+  # Timed INSIDE the evaluation: jrb_plan_phase_timing records CUDA events at the phase boundaries
+  # of jrb_eval on the stream its kernels run on, so the H-apply measured here is the sweep the
+  # timed steps ran (with the psi(r) cache: k_x_vmul_cached, not the stand-alone jrb_hpsi).
   phases = {}
-  cdt = torch.complex128
-  q = torch.empty(w_re.shape, dtype=cdt, device='cuda')
-  r = torch.empty((1, k1 - k0, nb, nb), dtype=cdt, device='cuda')
-  hq = torch.empty_like(q)
-  rho2 = torch.empty((1,) + tuple(wl['grid']), dtype=torch.float64, device='cuda')
-  g_out = (torch.empty_like(w_re), torch.empty_like(w_im))
-  plan.qr_fwd(w_re, w_im, out=(q, r))
-  plan.density(q, occ, out=rho2)
-  gp_out = plan.grid_potential(rho2, 'lda_x', False)
-  veff = gp_out[1]
-  plan.hpsi(q, veff, out=hq)
-  plan.qr_bwd(q, r, hq, out=g_out)
   reps = 3
-  phases['qr_fwd'] = timed(lambda: plan.qr_fwd(w_re, w_im, out=(q, r)), reps) / reps
-  phases['density'] = timed(lambda: plan.density(q, occ, out=rho2), reps) / reps
-  phases['grid_potential'] = timed(
-    lambda: plan.grid_potential(rho2, 'lda_x', False, out=gp_out), reps) / reps
-  phases['hpsi'] = timed(lambda: plan.hpsi(q, veff, out=hq), reps) / reps
-  phases['qr_bwd'] = timed(lambda: plan.qr_bwd(q, r, hq, out=g_out), reps) / reps
+  plan.phase_timing(True)
+  step()
+  acc = dict.fromkeys(plan.PHASES, 0.0)
+  for _ in range(reps):
+    step()
+    for k, v in plan.phase_times().items():
+      acc[k] += v / reps
+  plan.phase_timing(False)
+  phases.update(acc)
   if world > 1 and ev.reduce_path == 'peer':
+    rho2 = torch.empty((1,) + tuple(wl['grid']), dtype=torch.float64, device='cuda')
     ebuf = torch.zeros(1, dtype=torch.float64, device='cuda')
     phases['allreduce_rho'] = timed(lambda: plan.allreduce_rho(rho2, ebuf), 10) / 10
-  del q, r, hq, rho2, veff, g_out, gp_out
+    del rho2, ebuf
 
   # ---- the caller of the path: one optimisation step of the energy-mode driver (evaluation +
   # device Adam), eager and replayed as a CUDA graph; informational

@@ -95,6 +95,12 @@ int jrb_plan_min_orbital_grid(const jrb_plan* plan, int32_t* dims);
 /* which kernels run the y and x passes on the current orbital box: 0 single pencil passes,
  * 1 fused y+x plane kernels (fft_fused.cuh), 2 the 128 x 128 fused family (fft_fused128.cuh) */
 int jrb_plan_orbital_fused(const jrb_plan* plan);
+/* bytes of the psi(r) cache of the current orbital box (0: none).  With it jrb_eval_begin stores
+ * every orbital's psi(r) while it accumulates the density and jrb_eval_finish applies v_eff to the
+ * stored values instead of repeating the inverse transforms (the passes are bound by the FP64 and
+ * shared-memory pipes while HBM idles).  Allocated at plan creation when the fused plane kernels
+ * run and it fits JRB_PSI_CACHE_MB (default 65536; 0 switches it off) and 60 % of the free memory */
+int64_t jrb_plan_psi_cache_bytes(const jrb_plan* plan);
 
 /* Pre-computes V_ext(G) once: potential.external_reciprocal (jrystal/_src/potential.py:
  * 153-166), which the reference re-evaluates every step although it is parameter free. */
@@ -296,6 +302,15 @@ int jrb_allreduce_rho(jrb_plan* plan, double* rho, double* e_kin, jrb_stream str
 int jrb_eval(jrb_plan* plan, const double* w_re, const double* w_im, const double* occ,
              int32_t xc_id, double* energies, double* g_re, double* g_im, double* g_occ,
              double* rho, jrb_stream stream);
+
+/* Phase timing of jrb_eval / jrb_eval_begin + jrb_eval_finish (a measurement aid for bench.py: the
+ * phases are timed where they run, inside the evaluation, by CUDA events on the caller's stream).
+ * enable != 0: every following evaluation records events at its phase boundaries (do not enable
+ * while the stream is being captured into a CUDA graph).  jrb_plan_phase_times waits for the last
+ * evaluation and returns ms[6] = QR forward, density sweep, density reduction + interpolation +
+ * kinetic / non-local energy, grid potential, H-apply sweep, QR adjoint. */
+int jrb_plan_phase_timing(jrb_plan* plan, int32_t enable);
+int jrb_plan_phase_times(jrb_plan* plan, double* ms);
 
 /* Same evaluation through HOST buffers (the reference-facing call a non-CUDA host makes):
  * copies w_re/w_im/occ in (k-point chunks, overlapped with the kernels), runs the evaluation,

@@ -36,6 +36,9 @@ SYMBOLS = {
   'jrb_plan_orbital_grid': (ctypes.c_int, [_P, _P]),
   'jrb_plan_min_orbital_grid': (ctypes.c_int, [_P, _P]),
   'jrb_plan_orbital_fused': (ctypes.c_int, [_P]),
+  'jrb_plan_psi_cache_bytes': (ctypes.c_int64, [_P]),
+  'jrb_plan_phase_timing': (ctypes.c_int, [_P, ctypes.c_int32]),
+  'jrb_plan_phase_times': (ctypes.c_int, [_P, _P]),
   'jrb_set_atoms': (ctypes.c_int, [_P, _P, _P, _I32, _P]),
   'jrb_set_external_potential': (ctypes.c_int, [_P, _P, _P]),
   'jrb_external_position_gradient': (ctypes.c_int, [_P, _P, _P, _P]),

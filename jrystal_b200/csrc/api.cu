@@ -296,6 +296,11 @@ extern "C" int jrb_fft3d(jrb_plan* p, const double* in, double* out, int32_t dir
   return launch_fft3d_dense(p, C(in), C(out), direction, batch, scale, S(st));
 }
 
+// phase boundary i of the evaluation in flight (jrb_plan_phase_timing)
+static inline void phase_mark(jrb_plan* p, int i, cudaStream_t st) {
+  if (p->phase_timing) cudaEventRecord(p->ev_phase[i], st);
+}
+
 // QR, density sweep, kinetic (+ non-local) energy.  reduce: all-reduce the partial density over the
 // plan's communicator where it is smallest -- on the box the sweep ran on (the orbital grid),
 // before the Fourier interpolation onto the plan's grid -- together with e_kin.
@@ -304,12 +309,15 @@ static int eval_begin_impl(jrb_plan* p, const double* w_re, const double* w_im, 
                            cudaStream_t st) {
   int rc = 0;
   JRB_CUDA(cudaMemsetAsync(p->d_scal + 32, 0, sizeof(double), st));  // Cholesky failure flag
+  phase_mark(p, 0, st);
   if ((rc = launch_qr_fwd(p, w_re, w_im, p->d_q, p->d_r, st))) return rc;
+  phase_mark(p, 1, st);
   p->keep_write = 1;
   rc = launch_density_partial(p, p->d_q, occ, rho, st);
   p->keep_write = 0;
   p->keep_filled = rc == 0;
   if (rc) return rc;
+  phase_mark(p, 2, st);
   if ((rc = launch_kinetic(p, p->d_q, p->d_tkb, st))) return rc;
   if ((rc = launch_weighted_sum(p, p->d_tkb, occ, (int64_t)p->ns * p->nk * p->nb, e_kin, st)))
     return rc;
@@ -352,6 +360,7 @@ static int eval_finish_impl(jrb_plan* p, const double* occ, const double* rho, c
   double* grid_e = p->d_scal;            // E_H, E_ext, E_xc
   double* veff = p->d_veff;
   p->veff_prepared = 0;                  // d_veff is overwritten by this evaluation's potential
+  phase_mark(p, 3, S(st));
   if (grid_fused_ok(p, xc_id)) {
     // energies + v_eff straight onto the orbital box (each field transformed once)
     if ((rc = launch_grid_potential_orbital(p, rho, rhohat_ready, xc_id, grid_e, S(st)))) return rc;
@@ -359,9 +368,11 @@ static int eval_finish_impl(jrb_plan* p, const double* occ, const double* rho, c
   } else if ((rc = launch_grid_potential(p, rho, xc_id, 0, 7, grid_e, veff, S(st)))) {
     return rc;
   }
+  phase_mark(p, 4, S(st));
   p->keep_read = p->keep_filled;
   rc = launch_hpsi(p, p->d_q, veff, p->d_hq, S(st));
   p->keep_read = 0;
+  phase_mark(p, 5, S(st));
   p->keep_filled = 0;  // the fused H-apply works in place on the kept columns
   p->nl_p_valid = 0;
   if (rc) return rc;
@@ -371,6 +382,30 @@ static int eval_finish_impl(jrb_plan* p, const double* occ, const double* rho, c
   if ((rc = launch_qr_bwd(p, p->d_q, p->d_r, p->d_hq, occ, g_re, g_im, S(st)))) return rc;
   k_pack_energies<<<1, 1, 0, S(st)>>>(e_kin, grid_e, energies);
   JRB_CHECK_LAUNCH("k_pack_energies");
+  phase_mark(p, 6, S(st));
+  return 0;
+}
+
+extern "C" int jrb_plan_phase_timing(jrb_plan* p, int32_t enable) {
+  int rc = enter(p);
+  if (rc) return rc;
+  if (enable && !p->ev_phase[0])
+    for (int i = 0; i < 8; ++i) JRB_CUDA(cudaEventCreate(&p->ev_phase[i]));
+  p->phase_timing = enable ? 1 : 0;
+  return 0;
+}
+
+extern "C" int jrb_plan_phase_times(jrb_plan* p, double* ms) {
+  int rc = enter(p);
+  if (rc) return rc;
+  REQUIRE(ms, "null array");
+  REQUIRE(p->phase_timing && p->ev_phase[0], "phase timing is off (jrb_plan_phase_timing)");
+  JRB_CUDA(cudaEventSynchronize(p->ev_phase[6]));
+  for (int i = 0; i < 6; ++i) {
+    float t = 0.f;
+    JRB_CUDA(cudaEventElapsedTime(&t, p->ev_phase[i], p->ev_phase[i + 1]));
+    ms[i] = (double)t;
+  }
   return 0;
 }
 

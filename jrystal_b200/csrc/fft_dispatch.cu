@@ -47,6 +47,18 @@ int fused_smem_group2(int n, int nxo, int ncol);
 int fused_threads_group0(int n);
 int fused_threads_group1(int n);
 int fused_threads_group2(int n);
+int fused_psi_plane_group0(int n, int nxo);
+int fused_psi_plane_group1(int n, int nxo);
+int fused_psi_plane_group2(int n, int nxo);
+
+// complex numbers per band-plane of the psi(r) cache for axis length n (< 0: length not
+// compiled, or the cached H-apply kernel does not fit shared memory)
+int fused_psi_plane_elems(int n, int nxo) {
+  int r = fused_psi_plane_group0(n, nxo);
+  if (r == -2) r = fused_psi_plane_group1(n, nxo);
+  if (r == -2) r = fused_psi_plane_group2(n, nxo);
+  return r;
+}
 
 int fused_smem_need(int n, int nxo, int ncol) {
   int r = fused_smem_group0(n, nxo, ncol);
@@ -139,6 +151,9 @@ static FusedArgs fused_args(jrb_plan* p, const PassArgs& a) {
       f.row0 = (a.wa - p->d_ws_a) / NB;
     }
   }
+  // psi(r) cache: written by the density sweep of jrb_eval_begin, read by the H-apply of
+  // jrb_eval_finish (the keep_* flags bracket exactly those two sweeps)
+  f.psi = (p->d_psi && (p->keep_write || p->keep_read)) ? p->d_psi : nullptr;
   return f;
 }
 
@@ -174,7 +189,8 @@ static int density_groups(jrb_plan* p, const cplx* q, double* rho_spin, int s, i
     a.ngroups = std::min(p->batch_groups, gb - g0);
     a.rho = rho_spin;
     a.tw = p->d_tw_z;
-    if (p->keep_write && p->d_a_keep) a.wa = p->d_a_keep + (long long)a.g0 * p->a_group_elems;
+    if (p->keep_write && p->d_a_keep && !p->d_psi)
+      a.wa = p->d_a_keep + (long long)a.g0 * p->a_group_elems;
     if ((rc = run_pass(PASS_Z_INV_SCATTER, p->nz, a, st))) return rc;
     if (p->fused == 2) {
       FusedArgs f = fused_args(p, a);
@@ -289,7 +305,10 @@ static int hpsi_groups(jrb_plan* p, const cplx* q, const double* veff_spin, cplx
     a.ngroups = std::min(p->batch_groups, gb - g0);
     a.veff = veff_spin;
     a.tw = p->d_tw_z;
-    if (p->keep_read && p->d_a_keep) {
+    const bool from_psi = p->keep_read && p->d_psi && p->fused == 1;  // psi(r) of the density sweep
+    if (from_psi) {
+      // nothing to recompute: the cached kernel only writes the columns
+    } else if (p->keep_read && p->d_a_keep) {
       a.wa = p->d_a_keep + (long long)a.g0 * p->a_group_elems;  // columns of the density sweep
     } else {
       if ((rc = run_pass(PASS_Z_INV_SCATTER, p->nz, a, st))) return rc;
@@ -301,7 +320,7 @@ static int hpsi_groups(jrb_plan* p, const cplx* q, const double* veff_spin, cplx
       a.wa_add = f.wout[1];
     } else if (p->fused) {
       FusedArgs f = fused_args(p, a);
-      if ((rc = run_fused(1, p->nx, f, p->fused_ctas, st))) return rc;
+      if ((rc = run_fused(from_psi ? 2 : 1, p->nx, f, p->fused_ctas, st))) return rc;
     } else {
       a.tw = p->d_tw_y;
       if ((rc = run_pass(PASS_Y_INV, p->ny, a, st))) return rc;

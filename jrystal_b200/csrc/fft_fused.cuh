@@ -52,6 +52,11 @@ struct FusedArgs {
   // [rows of 8 bands][16 doubles], and the row of wa[0]; null = cp.async staging
   const void* tmap;
   long long row0;
+  // psi(r) cache of the whole evaluation (null: none): k_yx_density stores every band-plane it
+  // transforms, k_x_vmul_cached reads it back instead of repeating the inverse transforms.
+  // Entry of (global group g, z, band): psi_plane complex numbers in the x-stage register layout
+  // [round][butterfly][element][thread] of the kernel (both kernels share the thread mapping)
+  cplx* psi;
 };
 
 // butterfly slots that can be non-zero for band-limited data (see dft_small.cuh)
@@ -79,6 +84,8 @@ struct FCfg {
   static constexpr int NR = (NG + SLOTS - 1) / SLOTS;  // x-stage rounds
   static constexpr int SX = N + ((N % 8 == 1) ? 0 : (9 - N % 8) % 8);  // Y row stride == 1 (mod 8)
   static constexpr int EXCH = SLOTS * N * NB;          // exchange buffers (complex)
+  // psi(r) cache entry of one band-plane (complex): x-stage registers of every thread
+  static constexpr int PSI_PLANE = NR * LineFFT<N, +1>::CB * LineFFT<N, +1>::RB * NT;
   // shared memory (complex numbers): 2 Y slabs, exchange buffers, 2 staging buffers
   static JRB_HD int ybuf_elems(int nxo) { return nxo * SX; }
   // staging buffers hold whole TMA boxes of 256 columns (the tail box is filled past ncol)
@@ -86,7 +93,25 @@ struct FCfg {
   static JRB_HD int smem_bytes(int nxo, int ncol) {
     return (2 * ybuf_elems(nxo) + EXCH + 2 * stage_elems(ncol)) * (int)sizeof(cplx);
   }
+  // k_x_vmul_cached: one Y slab, the exchange buffers and v_eff of the current plane (doubles,
+  // one private slot per x-stage register of every thread); no staging buffers
+  static JRB_HD int smem_bytes_cached(int nxo) {
+    return (ybuf_elems(nxo) + EXCH) * (int)sizeof(cplx) + PSI_PLANE * (int)sizeof(double);
+  }
 };
+
+// streaming (evict-first) 16-byte accesses of the psi(r) cache: written once, read once, far
+// larger than L2, so it should not displace the column work space and the tables
+__device__ __forceinline__ void psi_store(cplx* p, const cplx& v) {
+  __stcs(reinterpret_cast<double2*>(p), make_double2(v.x, v.y));
+}
+__device__ __forceinline__ cplx psi_load(const cplx* p) {
+  const double2 t = __ldcs(reinterpret_cast<const double2*>(p));
+  return cmake(t.x, t.y);
+}
+__device__ __forceinline__ long long psi_entry(const FusedArgs& a, int gl, int z, int band) {
+  return ((long long)(a.g0 + gl) * a.m.nz + z) * NB + band;
+}
 
 template <int N>
 __device__ __forceinline__ void slot_barrier(int slot) {
@@ -384,6 +409,7 @@ k_yx_density(FusedArgs a) {
       const double fw = fw_next;
       if (nxt.w < w_end) fw_next = a.focc[(a.g0 + nxt.gl) * NB + nxt.band];
       const cplx* ybuf = ybuf0 + par * ysz;
+      cplx* pc = a.psi ? a.psi + psi_entry(a, cur.gl, cur.z, cur.band) * C::PSI_PLANE + t : nullptr;
 #pragma unroll
       for (int r = 0; r < C::NR; ++r) {
         const int y = (r * C::SLOTS + slot) * NB + lane;
@@ -404,6 +430,13 @@ k_yx_density(FusedArgs a) {
         slot_barrier<N>(slot);
         cplx vb[F::CB][F::RB];
         F::template stageB_load<NB>(vb, ex, tw, tj);
+        if (pc && ok) {
+#pragma unroll
+          for (int i = 0; i < F::CB; ++i)
+#pragma unroll
+            for (int m = 0; m < F::RB; ++m)
+              if (F::activeB(i, tj)) psi_store(pc + ((r * F::CB + i) * F::RB + m) * C::NT, vb[i][m]);
+        }
 #pragma unroll
         for (int i = 0; i < F::CB; ++i)
 #pragma unroll
@@ -652,6 +685,179 @@ k_yx_vmul(FusedArgs a) {
 }
 
 // ---------------------------------------------------------------------------------------
+// Hamiltonian-apply middle from the psi(r) cache: psi(r) of the density sweep (global memory,
+// streamed once) -> * v_eff / N -> x forward -> y forward -> A.  Half the line transforms of
+// k_yx_vmul (the FP64 / shared-memory pipes bind that kernel, HBM idles at ~10 %), paid for
+// with one streaming read of the cache.  The loads of the next x-stage round are issued right
+// after the current round's registers are consumed, so their latency hides behind the round's
+// two exchanges; v_eff of the plane sits in shared memory (thread-private slots, conflict free)
+// to leave the registers to that prefetch.
+// grid: (G) persistent CTAs; dynamic smem: FCfg<N>::smem_bytes_cached(nxo)
+template <int N, bool ONE_ITER, bool SP>
+__global__ void __launch_bounds__(FCfg<N>::NT, (FCfg<N>::NT <= 256 ? 2 : 1))
+k_x_vmul_cached(FusedArgs a) {
+  using FI = LineFFT<N, +1>;
+  using FF = LineFFT<N, -1>;
+  using C = FCfg<N>;
+  static_assert(FI::CB == FF::CA && FI::RB == FF::RA, "register chaining contract");
+  static_assert(FF::CB == FI::CA && FF::RB == FI::RA, "x index sets of inverse-in / forward-out");
+  extern __shared__ __align__(128) unsigned char smem_fused_[];
+  cplx* ybuf = reinterpret_cast<cplx*>(smem_fused_);
+  cplx* exbase = ybuf + C::ybuf_elems(a.m.nxo);
+  const int t = threadIdx.x;
+  double* vs = reinterpret_cast<double*>(exbase + C::EXCH) + t;  // [round][butterfly][element][thread]
+  const int lane = t % NB;
+  const int tj = (t / NB) % C::TPL;
+  const int slot = t / C::SLOT_THREADS;
+  cplx* ex = exbase + (size_t)slot * N * NB + lane;
+  constexpr bool SHARE_TW = LinePlan<N>::r1 == LinePlan<N>::r2;
+  // forward twiddles; equal radices: held as the inverse plan's set and conjugated on use, like
+  // k_yx_vmul, so the band-limited butterflies are shared
+  cplx twi[SHARE_TW ? FI::CB : 1][SHARE_TW ? FI::NTW : 1];
+  cplx twf[SHARE_TW ? 1 : FF::CB][SHARE_TW ? 1 : FF::NTW];
+  if constexpr (SHARE_TW) FI::load_twiddles(twi, a.tw, tj);
+  else FF::load_twiddles(twf, a.tw, tj);
+  auto fwd_stageB = [&](cplx (&v)[FF::CB][FF::RB]) {
+    if constexpr (SP) {
+      static_assert(!SP || SHARE_TW, "band-limited variant needs equal radices");
+      FF::template stageB_load_sparse<NB, true>(v, ex, twi, tj);
+    } else if constexpr (SHARE_TW) {
+      FF::template stageB_load<NB, true>(v, ex, twi, tj);
+    } else {
+      FF::template stageB_load<NB, false>(v, ex, twf, tj);
+    }
+  };
+  // packed per-thread indices (see fused_y_inverse): Y rows of the x-stage outputs and the
+  // columns of the single-pass y stage
+  unsigned pk[FI::CA][FI::RA];
+  {
+    const int xo0 = slot * NB + lane;
+#pragma unroll
+    for (int i = 0; i < FI::CA; ++i)
+#pragma unroll
+      for (int m = 0; m < FI::RA; ++m) {
+        unsigned lo = 0, hi = 0;
+        if (FI::activeA(i, tj)) {
+          const int xo = a.m.xmap[FI::idxA(i, m, tj)];
+          if (xo >= 0) hi = (unsigned)(xo * C::SX + 1);
+          if (xo0 < a.m.nxo) lo = (unsigned)(a.m.ycol[(long long)xo0 * N + FI::idxA(i, m, tj)] + 1);
+        }
+        pk[i][m] = lo | (hi << 16);
+      }
+  }
+  // v_eff(x, y, z) / N at the points this thread owns in the x stage -> its shared-memory slots
+  auto load_v = [&](int z) {
+    const long long nyz = (long long)N * a.m.nz;
+#pragma unroll
+    for (int r = 0; r < C::NR; ++r) {
+      const int y = (r * C::SLOTS + slot) * NB + lane;
+#pragma unroll
+      for (int i = 0; i < FI::CB; ++i)
+#pragma unroll
+        for (int m = 0; m < FI::RB; ++m) {
+          double v = 0.0;
+          if (FI::activeB(i, tj) && y < N)
+            v = a.veff[(long long)FI::idxB(i, m, tj) * nyz + (long long)y * a.m.nz + z] * a.vscale;
+          vs[((r * FI::CB + i) * FI::RB + m) * C::NT] = v;
+        }
+    }
+  };
+  // prefetch registers: psi(r) of the next x-stage round
+  cplx pf[FI::CB][FI::RB];
+  auto issue = [&](const BandPos& p, int r) {
+    const int y = (r * C::SLOTS + slot) * NB + lane;
+    const cplx* src = a.psi + psi_entry(a, p.gl, p.z, p.band) * C::PSI_PLANE + t;
+#pragma unroll
+    for (int i = 0; i < FI::CB; ++i)
+#pragma unroll
+      for (int m = 0; m < FI::RB; ++m)
+        pf[i][m] = (FI::activeB(i, tj) && y < N) ? psi_load(src + ((r * FI::CB + i) * FI::RB + m) * C::NT)
+                                                 : czero();
+  };
+
+  const int ngx = (a.m.nxo + NB - 1) / NB;
+  const long long W = (long long)a.m.nz * a.ngroups;
+  const int c = blockIdx.x, G = gridDim.x;
+  const int w_end = (int)((c + 1) * W / G);
+  const int gmod0 = a.g0 % a.ngpk;
+  BandPos cur = band_first(a, (int)(c * W / G));
+  if (cur.w >= w_end) return;
+  issue(cur, 0);
+  int cur_z = cur.z;
+  load_v(cur_z);  // thread-private slots: no barrier needed
+  while (cur.w < w_end) {
+    const BandPos nxt = band_next(a, cur, w_end, gmod0);
+    if (cur.z != cur_z) {
+      cur_z = cur.z;
+      load_v(cur_z);
+    }
+#pragma unroll
+    for (int r = 0; r < C::NR; ++r) {
+      const int y = (r * C::SLOTS + slot) * NB + lane;
+      const bool ok = y < N;
+      cplx vb[FI::CB][FI::RB];
+#pragma unroll
+      for (int i = 0; i < FI::CB; ++i)
+#pragma unroll
+        for (int m = 0; m < FI::RB; ++m)
+          vb[i][m] = cscale(pf[i][m], vs[((r * FI::CB + i) * FI::RB + m) * C::NT]);
+      if (r + 1 < C::NR) issue(cur, r + 1);
+      else if (nxt.w < w_end) issue(nxt, 0);
+      FF::template stageA_store<NB>(vb, ex, tj);
+      slot_barrier<N>(slot);
+      cplx vc[FF::CB][FF::RB];
+      fwd_stageB(vc);
+      if (ok) {
+#pragma unroll
+        for (int i = 0; i < FF::CB; ++i)
+#pragma unroll
+          for (int m = 0; m < FF::RB; ++m) {
+            if (SP && !JRB_SPARSE_M(m)) continue;
+            if ((pk[i][m] >> 16) != 0) ybuf[(int)(pk[i][m] >> 16) - 1 + y] = vc[i][m];
+          }
+      }
+      slot_barrier<N>(slot);
+    }
+    __syncthreads();  // Y complete
+    // y stage, forward: Y -> occupied columns of A (global)
+    cplx* dst = band_plane(a, cur);
+    const int grp_end = ONE_ITER ? slot + 1 : (ngx + C::SLOTS - 1) / C::SLOTS * C::SLOTS;
+    for (int grp = slot; grp < grp_end; grp += C::SLOTS) {
+      const int xo = grp * NB + lane;
+      const bool ok = grp < ngx && xo < a.m.nxo;
+      const cplx* in = ybuf + (long long)(ok ? xo : 0) * C::SX;
+      cplx va[FF::CA][FF::RA];
+#pragma unroll
+      for (int i = 0; i < FF::CA; ++i)
+#pragma unroll
+        for (int m = 0; m < FF::RA; ++m)
+          va[i][m] = (FF::activeA(i, tj) && ok) ? in[FF::idxA(i, m, tj)] : czero();
+      FF::template stageA_store<NB>(va, ex, tj);
+      slot_barrier<N>(slot);
+      cplx vb[FF::CB][FF::RB];
+      fwd_stageB(vb);
+      if (ok) {
+        const int32_t* yc = a.m.ycol + (long long)xo * N;
+#pragma unroll
+        for (int i = 0; i < FF::CB; ++i) {
+          if (FF::activeB(i, tj)) {
+#pragma unroll
+            for (int m = 0; m < FF::RB; ++m) {
+              if (SP && !JRB_SPARSE_M(m)) continue;
+              const int col = ONE_ITER ? (int)(pk[i][m] & 0xffffu) - 1 : yc[FF::idxB(i, m, tj)];
+              if (col >= 0) dst[(long long)col * NB] = vb[i][m];
+            }
+          }
+        }
+      }
+      slot_barrier<N>(slot);
+    }
+    __syncthreads();  // everybody is done reading Y before the next band's x stage rewrites it
+    cur = nxt;
+  }
+}
+
+// ---------------------------------------------------------------------------------------
 template <int N>
 int launch_fused(int kind, const FusedArgs& a, int ctas, cudaStream_t st) {
   using C = FCfg<N>;
@@ -669,6 +875,15 @@ int launch_fused(int kind, const FusedArgs& a, int ctas, cudaStream_t st) {
     if (sp) k_yx_density<N, true, SP_OK><<<ctas, C::NT, smem, st>>>(a);
     else if (one) k_yx_density<N, true, false><<<ctas, C::NT, smem, st>>>(a);
     else k_yx_density<N, false, false><<<ctas, C::NT, smem, st>>>(a);
+  } else if (kind == 2) {
+    static int once = set_smem_attr(k_x_vmul_cached<N, true, false>, 200 * 1024) |
+                      set_smem_attr(k_x_vmul_cached<N, false, false>, 200 * 1024) |
+                      set_smem_attr(k_x_vmul_cached<N, true, SP_OK>, 200 * 1024);
+    if (once) return once;
+    const int smem_c = C::smem_bytes_cached(a.m.nxo);
+    if (sp) k_x_vmul_cached<N, true, SP_OK><<<ctas, C::NT, smem_c, st>>>(a);
+    else if (one) k_x_vmul_cached<N, true, false><<<ctas, C::NT, smem_c, st>>>(a);
+    else k_x_vmul_cached<N, false, false><<<ctas, C::NT, smem_c, st>>>(a);
   } else {
     static int once = set_smem_attr(k_yx_vmul<N, true, false>, 200 * 1024) |
                       set_smem_attr(k_yx_vmul<N, false, false>, 200 * 1024) |
@@ -689,6 +904,12 @@ int fused_smem_bytes(int nxo, int ncol) {
 template <int N>
 int fused_threads() {
   return FCfg<N>::NT;
+}
+// psi(r) cache: complex numbers per band-plane, or -1 when k_x_vmul_cached does not fit shared
+// memory for this many occupied x planes
+template <int N>
+int fused_psi_plane(int nxo) {
+  return FCfg<N>::smem_bytes_cached(nxo) <= 200 * 1024 ? FCfg<N>::PSI_PLANE : -1;
 }
 
 // per-translation-unit dispatch (fft_fused_g*.cu); return 1 if n is not in the group

@@ -41,4 +41,16 @@ int fused_threads_group1(int n) {
   }
 }
 
+int fused_psi_plane_group1(int n, int nxo) {
+  switch (n) {
+#define X(N_) \
+  case N_:    \
+    return fused_psi_plane<N_>(nxo);
+    JRB_SIZES(X)
+#undef X
+    default:
+      return -2;
+  }
+}
+
 }  // namespace jrb

@@ -167,7 +167,7 @@ extern "C" int jrb_plan_destroy(jrb_plan* p) {
   delete[] p->h_freq;
   delete[] p->h_kpts;
   void* ptrs[] = {p->d_zmap, p->d_ycol, p->d_xmap, p->d_gidx, p->d_gk2, p->d_tw_x, p->d_tw_y,
-                  p->d_tw_z, p->d_tw_half, p->d_a_keep, p->d_pos, p->d_chg, p->d_atom_part, p->d_nl_phi, p->d_nl_p, p->d_nl_part, p->d_nl_phit, p->d_nl_ps, p->d_ws_a, p->d_ws_b, p->d_rho_part, p->d_seg_z, p->d_focc, p->d_grid, p->d_vext,
+                  p->d_tw_z, p->d_tw_half, p->d_a_keep, p->d_psi, p->d_pos, p->d_chg, p->d_atom_part, p->d_nl_phi, p->d_nl_p, p->d_nl_part, p->d_nl_phit, p->d_nl_ps, p->d_ws_a, p->d_ws_b, p->d_rho_part, p->d_seg_z, p->d_focc, p->d_grid, p->d_vext,
                   p->d_partials, p->d_veff, p->d_gga, p->d_vxc, p->d_q, p->d_hq, p->d_tmp, p->d_r, p->d_rinv, p->d_small, p->d_gpart,
                   p->d_tkb, p->d_eps, p->d_sphere_part, p->d_scal, p->d_skip, p->d_emax, p->d_wre, p->d_wim, p->d_gre, p->d_gim,
                   p->d_occ, p->d_rho, p->d_en};
@@ -177,6 +177,7 @@ extern "C" int jrb_plan_destroy(jrb_plan* p) {
   if (p->h2d_stream) cudaStreamDestroy(p->h2d_stream);
   if (p->d2h_stream) cudaStreamDestroy(p->d2h_stream);
   for (int i = 0; i < 16; ++i) {
+    if (i < 8 && p->ev_phase[i]) cudaEventDestroy(p->ev_phase[i]);
     if (p->ev_in[i]) cudaEventDestroy(p->ev_in[i]);
     if (p->ev_out[i]) cudaEventDestroy(p->ev_out[i]);
   }
@@ -425,7 +426,29 @@ static int plan_create_impl(const jrb_plan_desc* d, bool orbital_only, jrb_plan*
   p->fused_segmax = p->fused ? (nplanes + p->fused_ctas - 1) / p->fused_ctas + 2 : 0;
   p->a_copy_elems = (long long)(a_per_group * bg);
   p->a_group_elems = (long long)a_per_group;
-  {
+  // psi(r) cache of a whole evaluation (plan.h: d_psi): HBM3e capacity traded for half of the
+  // H-apply's line transforms.  Optional: over budget or out of memory falls back to d_a_keep.
+  p->psi_group_elems = 0;
+  if (p->fused == 1) {
+    double cap_mb = 65536.0;
+    if (const char* env = std::getenv("JRB_PSI_CACHE_MB")) cap_mb = std::atof(env);
+    const long long plane = fused_psi_plane_elems(nx, nxo);
+    const size_t per_group = (size_t)plane * nz * NB;
+    const double need_mb = (double)total_groups * per_group * sizeof(cplx) / (1024.0 * 1024.0);
+    size_t free_b = 0, total_b = 0;
+    if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) free_b = 0;
+    if (plane > 0 && need_mb <= cap_mb && need_mb * 1024.0 * 1024.0 <= 0.6 * (double)free_b) {
+      void* q = nullptr;
+      if (cudaMalloc(&q, per_group * total_groups * sizeof(cplx)) == cudaSuccess) {
+        p->d_psi = static_cast<cplx*>(q);
+        p->psi_group_elems = (long long)per_group;
+        tot += (long long)(per_group * total_groups * sizeof(cplx));
+      } else {
+        cudaGetLastError();  // not an error: the cache is optional
+      }
+    }
+  }
+  if (!p->d_psi) {
     double cap_mb = 8192.0;
     if (const char* env = std::getenv("JRB_KEEP_A_MB")) cap_mb = std::atof(env);
     const double need_mb = (double)total_groups * a_per_group * sizeof(cplx) / (1024.0 * 1024.0);
@@ -546,9 +569,10 @@ extern "C" int jrb_plan_set_orbital_grid(jrb_plan* p, int32_t nxw, int32_t nyw, 
   {
     const long long total_groups = (long long)p->ns * p->nk * p->ngroups_per_k;
     if (p->d_a_keep) p->ws_bytes -= total_groups * p->a_group_elems * (long long)sizeof(cplx);
+    if (p->d_psi) p->ws_bytes -= total_groups * p->psi_group_elems * (long long)sizeof(cplx);
     if (p->d_ws_a) p->ws_bytes -= p->a_copy_elems * (p->fused == 2 ? 3 : 1) * (long long)sizeof(cplx);
   }
-  for (cplx** q : {&p->d_a_keep, &p->d_ws_a, &p->d_ws_b}) {
+  for (cplx** q : {&p->d_a_keep, &p->d_psi, &p->d_ws_a, &p->d_ws_b}) {
     if (*q) cudaFree(*q);
     *q = nullptr;
   }
@@ -570,6 +594,13 @@ extern "C" int jrb_plan_orbital_grid(const jrb_plan* p, int32_t* dims) {
 extern "C" int jrb_plan_orbital_fused(const jrb_plan* p) {
   if (!p) return JRB_EINVAL;
   return (p->wf ? p->wf : p)->fused;
+}
+
+extern "C" int64_t jrb_plan_psi_cache_bytes(const jrb_plan* p) {
+  if (!p) return 0;
+  const jrb_plan* o = p->wf ? p->wf : p;
+  if (!o->d_psi) return 0;
+  return (int64_t)o->ns * o->nk * o->ngroups_per_k * o->psi_group_elems * (int64_t)sizeof(cplx);
 }
 
 /* smallest alias-free orbital box per axis: 4 gmax + 1 */

@@ -64,6 +64,13 @@ struct jrb_plan {
   jrb::cplx* d_a_keep;
   long long a_group_elems;
   int keep_write, keep_read, keep_filled;
+  // psi(r) of EVERY orbital on the box the passes run on, in the register layout of the fused
+  // x stage (fft_fused.cuh: FusedArgs::psi): stored by the density sweep of jrb_eval_begin, read
+  // by the H-apply of jrb_eval_finish, which then runs only the forward transforms.  Takes
+  // precedence over d_a_keep; null when the passes are not fused (fused != 1) or it exceeds the
+  // budget (JRB_PSI_CACHE_MB, default 65536, and at most 60 % of the free device memory)
+  jrb::cplx* d_psi;
+  long long psi_group_elems;  // complex numbers per band group (nz planes x 8 bands)
   jrb::cplx* d_ws_b;  // [batch][nxo][ny][nz][NB]
   double* d_focc;     // [ns*nk*ngroups_per_k][NB] occupation / Omega, zero padded
   int fused;          // 1: y and x passes fused per z-plane (fft_fused.cuh); B slab unused;
@@ -109,6 +116,10 @@ struct jrb_plan {
   double* d_emax;                     // [ns*nk] max|Q1^H Q1 - I| of the second pass (bit pattern)
   cudaStream_t own_stream, h2d_stream, d2h_stream;
   cudaEvent_t ev_in[16], ev_out[16];  // per k-chunk events of jrb_energy_grad_host
+  // jrb_eval phase timing (jrb_plan_phase_timing): events at the phase boundaries of the LAST
+  // evaluation, recorded on the caller's stream; 0 = off (the default; never during capture)
+  int phase_timing;
+  cudaEvent_t ev_phase[8];
   // host staging for jrb_energy_grad_host
   double *d_wre, *d_wim, *d_gre, *d_gim, *d_occ, *d_rho, *d_en;
   int64_t ws_bytes;
@@ -154,6 +165,7 @@ bool line_length_supported(int n);
 bool fused_available(int nx, int ny, int nxo, int ncol);
 bool fused128_available(int nx, int ny, int nxo, int ncol, int band_limited32);
 int fused_cta_count(int n, int nxo, int ncol);
+int fused_psi_plane_elems(int n, int nxo);
 
 // grid_kernels.cu
 // fused grid part of an evaluation (orbital box, LDA, one spin): see launch_grid_potential_orbital

@@ -154,6 +154,26 @@ class Plan(_CommMixin):
     _lib.check(self.lib.jrb_plan_set_orbital_grid(self._h, *dims))
     self.orbital_grid = dims
 
+  PHASES = ('qr_fwd', 'density', 'reduce_interp', 'grid_potential', 'hpsi', 'qr_bwd')
+
+  def phase_timing(self, enable=True):
+    """Record CUDA events at the phase boundaries of every following eval (jrb_plan_phase_timing).
+    Not while capturing a CUDA graph."""
+    _lib.check(self.lib.jrb_plan_phase_timing(self._h, 1 if enable else 0))
+
+  def phase_times(self):
+    """{phase: ms} of the last eval, timed inside it (jrb_plan_phase_times); waits for it."""
+    import ctypes
+    buf = (ctypes.c_double * 6)()
+    _lib.check(self.lib.jrb_plan_phase_times(self._h, ctypes.cast(buf, ctypes.c_void_p)))
+    return dict(zip(self.PHASES, [float(v) for v in buf]))
+
+  @property
+  def psi_cache_bytes(self):
+    """Size of the psi(r) cache of the current orbital box (jrb_plan_psi_cache_bytes); 0 = the
+    H-apply of eval_finish repeats the inverse transforms."""
+    return int(self.lib.jrb_plan_psi_cache_bytes(self._h))
+
   def __del__(self):
     h = getattr(self, '_h', None)
     if h:

@@ -157,15 +157,22 @@ def test_hpsi_and_band_trace(cuda_device, case):
 
 @pytest.mark.parametrize('case', list(CASES))
 @pytest.mark.parametrize('batch_groups', [0, 1, 3])
-@pytest.mark.parametrize('fuse', ['fused', 'fused_dense_butterflies', 'unfused'])
+@pytest.mark.parametrize('fuse', ['fused', 'fused_dense_butterflies', 'fused_no_psi_cache', 'unfused'])
 def test_energy_and_grad(cuda_device, case, batch_groups, fuse, monkeypatch):
   # 'unfused' forces the single-pass pencil kernels (the path non-cubic grids and 128^3 take);
-  # 'fused_dense_butterflies' disables the band-limited (sparse radix-8) variant
+  # 'fused_dense_butterflies' disables the band-limited (sparse radix-8) variant;
+  # 'fused_no_psi_cache' makes the H-apply repeat the inverse transforms on the kept z columns
+  # instead of reading psi(r) of the density sweep back (the path a plan over budget takes)
   monkeypatch.setenv('JRB_NO_FUSE', '1' if fuse == 'unfused' else '0')
   monkeypatch.setenv('JRB_NO_SPARSE', '1' if fuse == 'fused_dense_butterflies' else '0')
+  monkeypatch.setenv('JRB_PSI_CACHE_MB', '0' if fuse == 'fused_no_psi_cache' else '65536')
   if fuse == 'fused_dense_butterflies' and case != 'si8_64':
     pytest.skip('only the band-limited 64^3 case has a sparse variant to switch off')
   s, plan, w_re, w_im, occ = _setup(case, batch_groups=batch_groups)
+  if plan.lib.jrb_plan_orbital_fused(plan._h) == 1:
+    assert (plan.psi_cache_bytes > 0) == (fuse != 'fused_no_psi_cache')
+  else:
+    assert plan.psi_cache_bytes == 0
   ref = rp.energy_and_grad(s, w_re, w_im, occ, occ_grad=True)
   occ_d = to_dev(occ)
   rho, e_kin = plan.eval_begin(to_dev(w_re), to_dev(w_im), occ_d)
