@@ -209,12 +209,13 @@ FP64_PEAK_SOURCE = ('measured: tools/fp64_dmma_dfma_mix.cu, profiles/r01_fp64_dm
                     '(DFMA + DMMA mixed on one datapath, 35.1-35.5 TFLOP/s)')
 
 
-def fp64_flops(mask, orbital_grid, num_orbitals, num_sk, ng, nb):
+def fp64_flops(mask, orbital_grid, num_orbitals, num_sk, ng, nb, psi_cache=False):
   """FP64 flops of one evaluation as the kernels execute it, counted with the nominal
   5 n log2 n per length-n line on the PRUNED passes of the orbital box (z passes on the occupied
   (x, y) columns only, y passes on the occupied x planes only): per orbital 2 z passes (scatter
   side of the density sweep, gather side of the H-apply; the H-apply reuses the z-transformed
-  columns), 3 y and 3 x passes (density; H-apply inverse and forward).  QR products: 8 ng nb^2 per
+  columns), 3 y and 3 x passes (density; H-apply inverse and forward) -- 2 y and 2 x with the psi(r)
+  cache, where the H-apply reads psi(r) back instead of repeating its inverse passes.  QR products: 8 ng nb^2 per
   full complex tall-skinny product; Hermitian Gram, upper-triangle-only Gram and triangular
   factors charged one half: 2 x 1/2 (Gram) + 2 x 1/2 (apply, triangular R^-1) forward,
   1/2 (upper triangle of Q^H G) + 1/2 + 1 (two-term apply) backward = 4 products per (spin, k)."""
@@ -222,7 +223,8 @@ def fp64_flops(mask, orbital_grid, num_orbitals, num_sk, ng, nb):
   ncol = int(np.asarray(mask).any(axis=2).sum())
   nxo = int(np.asarray(mask).any(axis=(1, 2)).sum())
   line = lambda n: 5.0 * n * np.log2(n)
-  per_orbital = (2 * ncol * line(nzw) + 3 * nxo * nzw * line(nyw) + 3 * nyw * nzw * line(nxw))
+  nyx = 2 if psi_cache else 3
+  per_orbital = (2 * ncol * line(nzw) + nyx * nxo * nzw * line(nyw) + nyx * nyw * nzw * line(nxw))
   fft = per_orbital * num_orbitals
   qr = 4.0 * 8.0 * ng * nb * nb * num_sk
   return fft, qr
@@ -933,18 +935,23 @@ def run_b200_kshard(args, name, wl, world, rank, local_rank, full, steps=None):
   traffic, traffic_note = measured_traffic(name, world)
   # FP64 ceiling: what ncu says binds the path (the sweeps keep psi(r) in shared memory; DRAM runs
   # at ~10 % of peak, the FP64 pipe at 45-60 %, the shared-memory pipe at 50-65 %)
-  fft_fl, qr_fl = fp64_flops(wl['mask'], plan.orbital_grid, m_local, k1 - k0, ng, nb)
+  psi_cache = plan.psi_cache_bytes > 0
+  fft_fl, qr_fl = fp64_flops(wl['mask'], plan.orbital_grid, m_local, k1 - k0, ng, nb, psi_cache)
   fp64_tf = (fft_fl + qr_fl) / (ms_per_step * 1e-3) / 1e12
   roofline = {
     'bound': 'fp64', 'achieved': happly_achieved, 'peak': peak, 'unit': 'GB/s',
     'frac': happly_achieved / peak, 'traffic': traffic, 'traffic_source': traffic_note,
     'peak_source': peak_src,
-    'bound_note': 'ncu (profiles/): the dominant kernels are bound by FP64 issue + the shared-memory '
-                  'exchange of the line FFTs, not by HBM; achieved/peak/frac keep the HBM-convention '
+    'bound_note': 'ncu (profiles/): the plane kernels are bound by the L1/shared-memory data pipe '
+                  '(the exchanges of the line FFTs, ~70 % busy) and FP64 issue, the QR products by '
+                  'the FP64 tensor pipe; none by HBM.  achieved/peak/frac keep the HBM-convention '
                   'contract figure of SURVEY 8d (algorithmic bytes of the reference grid), '
-                  'roofline.fp64 is the fraction of the bounding roof',
-    'kernel': 'H-apply sweep (k_yx_vmul + k_z_fwd_gather on the kept z columns; k_yx_vmul is the '
-              'dominant kernel)',
+                  'roofline.fp64 is the fraction of the FP64 roof over the flops actually executed',
+    'kernel': ('H-apply sweep (k_x_vmul_cached on psi(r) of the density sweep + k_z_fwd_gather)'
+               if psi_cache else
+               'H-apply sweep (k_yx_vmul + k_z_fwd_gather on the kept z columns; k_yx_vmul is the '
+               'dominant kernel)'),
+    'psi_cache_bytes': plan.psi_cache_bytes,
     'bytes_per_launch': happly_bytes,
     'bytes_formula': 'M*(32*N + 32*ng): one dense transform (read+write of the box) per orbital '
                      '+ Q read + HQ write, SURVEY 8d',
@@ -952,8 +959,9 @@ def run_b200_kshard(args, name, wl, world, rank, local_rank, full, steps=None):
     'fp64': {'flops_per_eval': fft_fl + qr_fl, 'fft_flops': fft_fl, 'qr_flops': qr_fl,
              'achieved': fp64_tf, 'peak': FP64_PEAK_TFLOPS, 'unit': 'TFLOP/s',
              'frac': fp64_tf / FP64_PEAK_TFLOPS, 'peak_source': FP64_PEAK_SOURCE,
-             'flops_formula': 'pruned line FFTs at 5 n log2 n (2 z + 3 y + 3 x passes per orbital on '
+             'flops_formula': 'pruned line FFTs at 5 n log2 n (2 z + %d y + %d x passes per orbital on '
                               'the orbital box) + 4 x 8 ng nb^2 per (spin, k) for the QR products '
+                              % ((2, 2) if psi_cache else (3, 3)) +
                               '(Hermitian / triangular halves not charged); whole evaluation over '
                               'ms_per_step'},
     'whole_evaluation': {'achieved': whole_achieved, 'frac': whole_achieved / peak,

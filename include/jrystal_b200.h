@@ -99,7 +99,7 @@ int jrb_plan_orbital_fused(const jrb_plan* plan);
  * every orbital's psi(r) while it accumulates the density and jrb_eval_finish applies v_eff to the
  * stored values instead of repeating the inverse transforms (the passes are bound by the FP64 and
  * shared-memory pipes while HBM idles).  Allocated at plan creation when the fused plane kernels
- * run and it fits JRB_PSI_CACHE_MB (default 65536; 0 switches it off) and 60 % of the free memory */
+ * run and it fits JRB_PSI_CACHE_MB (default 65536; 0 switches it off) and 40 % of the free memory */
 int64_t jrb_plan_psi_cache_bytes(const jrb_plan* plan);
 
 /* Pre-computes V_ext(G) once: potential.external_reciprocal (jrystal/_src/potential.py:

@@ -100,14 +100,47 @@ struct FCfg {
   }
 };
 
-// streaming (evict-first) 16-byte accesses of the psi(r) cache: written once, read once, far
-// larger than L2, so it should not displace the column work space and the tables
+// streaming (evict-first) accesses of the psi(r) cache: written once, read once, far larger than
+// L2, so it should not displace the column work space and the tables.  Two complex numbers per
+// 256-bit access (LDG.256 / STG.256 of sm_100): half the instructions on the LSU queue.
+// Layout of round r of a band-plane entry, E = CB * RB registers per thread, NT threads:
+//   pair j (registers 2j, 2j+1) of thread t at (r E + 2 j) NT + 2 t, an odd E's last register
+//   at (r E + E - 1) NT + t
+__device__ __forceinline__ void psi_store2(cplx* p, const cplx& a, const cplx& b) {
+  asm volatile("st.global.cs.v4.f64 [%0], {%1, %2, %3, %4};\n" ::"l"(p), "d"(a.x), "d"(a.y), "d"(b.x),
+               "d"(b.y)
+               : "memory");
+}
+__device__ __forceinline__ void psi_load2(const cplx* p, cplx& a, cplx& b) {
+  asm volatile("ld.global.cs.v4.f64 {%0, %1, %2, %3}, [%4];\n"
+               : "=d"(a.x), "=d"(a.y), "=d"(b.x), "=d"(b.y)
+               : "l"(p));
+}
 __device__ __forceinline__ void psi_store(cplx* p, const cplx& v) {
   __stcs(reinterpret_cast<double2*>(p), make_double2(v.x, v.y));
 }
 __device__ __forceinline__ cplx psi_load(const cplx* p) {
   const double2 t = __ldcs(reinterpret_cast<const double2*>(p));
   return cmake(t.x, t.y);
+}
+// registers v[CB][RB] of round r <-> the entry at `base` (thread offset NOT included)
+template <int CB, int RB, int NT>
+__device__ __forceinline__ void psi_store_round(cplx* base, int r, int t, const cplx (&v)[CB][RB]) {
+  constexpr int E = CB * RB;
+  cplx* p = base + (long long)r * E * NT;
+#pragma unroll
+  for (int j = 0; j < E / 2; ++j)
+    psi_store2(p + 2 * j * NT + 2 * t, v[(2 * j) / RB][(2 * j) % RB], v[(2 * j + 1) / RB][(2 * j + 1) % RB]);
+  if constexpr (E % 2 == 1) psi_store(p + (E - 1) * NT + t, v[CB - 1][RB - 1]);
+}
+template <int CB, int RB, int NT>
+__device__ __forceinline__ void psi_load_round(const cplx* base, int r, int t, cplx (&v)[CB][RB]) {
+  constexpr int E = CB * RB;
+  const cplx* p = base + (long long)r * E * NT;
+#pragma unroll
+  for (int j = 0; j < E / 2; ++j)
+    psi_load2(p + 2 * j * NT + 2 * t, v[(2 * j) / RB][(2 * j) % RB], v[(2 * j + 1) / RB][(2 * j + 1) % RB]);
+  if constexpr (E % 2 == 1) v[CB - 1][RB - 1] = psi_load(p + (E - 1) * NT + t);
 }
 __device__ __forceinline__ long long psi_entry(const FusedArgs& a, int gl, int z, int band) {
   return ((long long)(a.g0 + gl) * a.m.nz + z) * NB + band;
@@ -409,7 +442,7 @@ k_yx_density(FusedArgs a) {
       const double fw = fw_next;
       if (nxt.w < w_end) fw_next = a.focc[(a.g0 + nxt.gl) * NB + nxt.band];
       const cplx* ybuf = ybuf0 + par * ysz;
-      cplx* pc = a.psi ? a.psi + psi_entry(a, cur.gl, cur.z, cur.band) * C::PSI_PLANE + t : nullptr;
+      cplx* pc = a.psi ? a.psi + psi_entry(a, cur.gl, cur.z, cur.band) * C::PSI_PLANE : nullptr;
 #pragma unroll
       for (int r = 0; r < C::NR; ++r) {
         const int y = (r * C::SLOTS + slot) * NB + lane;
@@ -431,11 +464,14 @@ k_yx_density(FusedArgs a) {
         cplx vb[F::CB][F::RB];
         F::template stageB_load<NB>(vb, ex, tw, tj);
         if (pc && ok) {
+          if constexpr (F::RA % F::TPL != 0) {  // idle butterfly slots: defined values
 #pragma unroll
-          for (int i = 0; i < F::CB; ++i)
+            for (int i = 0; i < F::CB; ++i)
+              if (!F::activeB(i, tj))
 #pragma unroll
-            for (int m = 0; m < F::RB; ++m)
-              if (F::activeB(i, tj)) psi_store(pc + ((r * F::CB + i) * F::RB + m) * C::NT, vb[i][m]);
+                for (int m = 0; m < F::RB; ++m) vb[i][m] = czero();
+          }
+          psi_store_round<F::CB, F::RB, C::NT>(pc, r, t, vb);
         }
 #pragma unroll
         for (int i = 0; i < F::CB; ++i)
@@ -766,13 +802,15 @@ k_x_vmul_cached(FusedArgs a) {
   cplx pf[FI::CB][FI::RB];
   auto issue = [&](const BandPos& p, int r) {
     const int y = (r * C::SLOTS + slot) * NB + lane;
-    const cplx* src = a.psi + psi_entry(a, p.gl, p.z, p.band) * C::PSI_PLANE + t;
+    const cplx* src = a.psi + psi_entry(a, p.gl, p.z, p.band) * C::PSI_PLANE;
+    if (y < N) {
+      psi_load_round<FI::CB, FI::RB, C::NT>(src, r, t, pf);
+    } else {
 #pragma unroll
-    for (int i = 0; i < FI::CB; ++i)
+      for (int i = 0; i < FI::CB; ++i)
 #pragma unroll
-      for (int m = 0; m < FI::RB; ++m)
-        pf[i][m] = (FI::activeB(i, tj) && y < N) ? psi_load(src + ((r * FI::CB + i) * FI::RB + m) * C::NT)
-                                                 : czero();
+        for (int m = 0; m < FI::RB; ++m) pf[i][m] = czero();
+    }
   };
 
   const int ngx = (a.m.nxo + NB - 1) / NB;

@@ -437,7 +437,7 @@ static int plan_create_impl(const jrb_plan_desc* d, bool orbital_only, jrb_plan*
     const double need_mb = (double)total_groups * per_group * sizeof(cplx) / (1024.0 * 1024.0);
     size_t free_b = 0, total_b = 0;
     if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) free_b = 0;
-    if (plane > 0 && need_mb <= cap_mb && need_mb * 1024.0 * 1024.0 <= 0.6 * (double)free_b) {
+    if (plane > 0 && need_mb <= cap_mb && need_mb * 1024.0 * 1024.0 <= 0.4 * (double)free_b) {
       void* q = nullptr;
       if (cudaMalloc(&q, per_group * total_groups * sizeof(cplx)) == cudaSuccess) {
         p->d_psi = static_cast<cplx*>(q);

@@ -68,7 +68,7 @@ struct jrb_plan {
   // x stage (fft_fused.cuh: FusedArgs::psi): stored by the density sweep of jrb_eval_begin, read
   // by the H-apply of jrb_eval_finish, which then runs only the forward transforms.  Takes
   // precedence over d_a_keep; null when the passes are not fused (fused != 1) or it exceeds the
-  // budget (JRB_PSI_CACHE_MB, default 65536, and at most 60 % of the free device memory)
+  // budget (JRB_PSI_CACHE_MB, default 65536, and at most 40 % of the free device memory)
   jrb::cplx* d_psi;
   long long psi_group_elems;  // complex numbers per band group (nz planes x 8 bands)
   jrb::cplx* d_ws_b;  // [batch][nxo][ny][nz][NB]

@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Write profiles/traffic.json from an `ncu --set full --page raw --csv` export of ONE whole
 evaluation of `bench.py`'s workload: DRAM bytes (dram__bytes_read.sum + dram__bytes_write.sum) of
-the H-apply sweep kernels (k_yx_vmul / k_yx128_vmul + k_z_fwd_gather), stamped with the sha256 of
+the H-apply sweep kernels (k_x_vmul_cached / k_yx_vmul / k_yx128_vmul + k_z_fwd_gather), stamped with the sha256 of
 the kernel sources they were captured with.  bench.py refuses the entry when the stamp differs from
 the sources the library is built from.   Usage: capture_traffic.py CONFIG raw.csv [source-note]"""
 import csv
@@ -31,7 +31,8 @@ kernels = {}
 total = 0.0
 for r in rows[2:]:
   name = r[ki]
-  if 'k_yx_vmul' in name or 'k_yx128_vmul' in name or 'k_z_fwd_gather' in name:
+  if ('k_x_vmul_cached' in name or 'k_yx_vmul' in name or 'k_yx128_vmul' in name or
+      'k_z_fwd_gather' in name):
     short = name.split('jrb::')[-1].split('(')[0]
     b = num(r[ri]) * scale[unit_r] + num(r[wi]) * scale[unit_w]
     k = kernels.setdefault(short, {'launches': 0, 'dram_bytes': 0.0})
@@ -49,8 +50,10 @@ m = wl['kpts'].shape[0] * wl['nb']
 prof[config] = {
   'happly_dram_bytes_per_eval': total, 'kernels': kernels, 'kernels_sha': bench.kernels_stamp(),
   'algorithmic_bytes_per_eval': m * (32.0 * ngrid + 32.0 * wl['ng']), 'source': note,
-  'note': 'one whole evaluation captured with ncu --set full (every launch); the sweep works on the '
-          'z-transformed columns kept from the density sweep, so it has no scatter pass',
+  'note': 'one whole evaluation captured with ncu --set full (every launch); with the psi(r) cache '
+          'the sweep streams psi(r) of the density sweep back from HBM (k_x_vmul_cached), so its '
+          'traffic is close to the algorithmic figure by design; without it the sweep works on the '
+          'kept z columns and moves ~6x fewer bytes',
 }
 json.dump(prof, open(path, 'w'), indent=1)
 print(config, 'H-apply DRAM bytes per evaluation', total, 'algorithmic', prof[config]['algorithmic_bytes_per_eval'],
