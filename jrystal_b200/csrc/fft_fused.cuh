@@ -442,7 +442,6 @@ k_yx_density(FusedArgs a) {
       const double fw = fw_next;
       if (nxt.w < w_end) fw_next = a.focc[(a.g0 + nxt.gl) * NB + nxt.band];
       const cplx* ybuf = ybuf0 + par * ysz;
-      cplx* pc = a.psi ? a.psi + psi_entry(a, cur.gl, cur.z, cur.band) * C::PSI_PLANE : nullptr;
 #pragma unroll
       for (int r = 0; r < C::NR; ++r) {
         const int y = (r * C::SLOTS + slot) * NB + lane;
@@ -463,7 +462,9 @@ k_yx_density(FusedArgs a) {
         slot_barrier<N>(slot);
         cplx vb[F::CB][F::RB];
         F::template stageB_load<NB>(vb, ex, tw, tj);
-        if (pc && ok) {
+        if (a.psi && ok) {
+          // entry address recomputed per round: a pointer kept across the round costs registers
+          cplx* pc = a.psi + psi_entry(a, cur.gl, cur.z, cur.band) * C::PSI_PLANE;
           if constexpr (F::RA % F::TPL != 0) {  // idle butterfly slots: defined values
 #pragma unroll
             for (int i = 0; i < F::CB; ++i)
