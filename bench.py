@@ -938,15 +938,45 @@ def run_b200_kshard(args, name, wl, world, rank, local_rank, full, steps=None):
   psi_cache = plan.psi_cache_bytes > 0
   fft_fl, qr_fl = fp64_flops(wl['mask'], plan.orbital_grid, m_local, k1 - k0, ng, nb, psi_cache)
   fp64_tf = (fft_fl + qr_fl) / (ms_per_step * 1e-3) / 1e12
+  # the design's own compulsory bytes of the sweep: with the psi(r) cache it streams psi(r) of the
+  # orbital box once, writes and re-reads the z columns, reads Q and writes HQ
+  ncol = int(np.asarray(wl['mask']).any(axis=2).sum())
+  og = [int(v) for v in plan.orbital_grid]
+  design_bytes = m_local * ((16.0 * og[0] * og[1] * og[2] if psi_cache else 16.0 * ncol * og[2]) +
+                            32.0 * ncol * og[2] + 32.0 * ng)
+  measured = None
+  if traffic:
+    measured = {'bytes_per_launch': traffic, 'achieved': traffic / (phases['hpsi'] * 1e-3) / 1e9,
+                'frac': traffic / (phases['hpsi'] * 1e-3) / 1e9 / peak,
+                'what': 'dram__bytes_read + dram__bytes_write of the sweep (roofline.traffic) over '
+                        'its time in this run: the fraction of the measured HBM copy bandwidth the '
+                        'sweep really sustains'}
   roofline = {
-    'bound': 'fp64', 'achieved': happly_achieved, 'peak': peak, 'unit': 'GB/s',
+    'bound': 'hbm' if psi_cache else 'fp64', 'achieved': happly_achieved, 'peak': peak, 'unit': 'GB/s',
     'frac': happly_achieved / peak, 'traffic': traffic, 'traffic_source': traffic_note,
     'peak_source': peak_src,
-    'bound_note': 'ncu (profiles/): the plane kernels are bound by the L1/shared-memory data pipe '
-                  '(the exchanges of the line FFTs, ~70 % busy) and FP64 issue, the QR products by '
-                  'the FP64 tensor pipe; none by HBM.  achieved/peak/frac keep the HBM-convention '
-                  'contract figure of SURVEY 8d (algorithmic bytes of the reference grid), '
-                  'roofline.fp64 is the fraction of the FP64 roof over the flops actually executed',
+    'bound_note': ('ncu (profiles/r02_kernel_tables.md): with the psi(r) cache the dominant sweep '
+                   'streams psi(r) from HBM at ~0.74 of the measured copy bandwidth while its L1 data '
+                   'pipe (shared-memory exchanges of the line FFTs + that global stream) is ~76 % busy: '
+                   'HBM and the L1 pipe bind it together; the QR products are bound by the FP64 tensor '
+                   'pipe.  achieved/peak/frac keep the HBM-convention contract figure of SURVEY 8d '
+                   '(algorithmic bytes of the REFERENCE grid: one read + one write of the dense box per '
+                   'transform), which exceeds 1 because the pruned passes on the smaller orbital box '
+                   'never move those bytes; roofline.measured is the sustained fraction on the bytes '
+                   'really moved, roofline.design_bytes what this design must move, roofline.fp64 the '
+                   'fraction of the FP64 roof over the flops executed'
+                   if psi_cache else
+                   'ncu (profiles/): without the psi(r) cache the plane kernels are bound by the '
+                   'L1/shared-memory data pipe and FP64 issue, the QR products by the FP64 tensor pipe; '
+                   'none by HBM.  achieved/peak/frac keep the HBM-convention contract figure of SURVEY '
+                   '8d, roofline.fp64 is the fraction of the FP64 roof over the flops executed'),
+    'measured': measured,
+    'design_bytes': {'bytes_per_launch': design_bytes,
+                     'formula': 'M*(16*nxw*nyw*nzw [psi(r) cache read] + 32*ncol*nzw [z columns '
+                                'written and re-read] + 32*ng [Q read, HQ write])' if psi_cache else
+                                'M*(48*ncol*nzw [kept z columns read, written, re-read] + 32*ng)',
+                     'achieved': design_bytes / (phases['hpsi'] * 1e-3) / 1e9,
+                     'frac': design_bytes / (phases['hpsi'] * 1e-3) / 1e9 / peak},
     'kernel': ('H-apply sweep (k_x_vmul_cached on psi(r) of the density sweep + k_z_fwd_gather)'
                if psi_cache else
                'H-apply sweep (k_yx_vmul + k_z_fwd_gather on the kept z columns; k_yx_vmul is the '

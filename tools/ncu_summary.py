@@ -24,6 +24,9 @@ WANT = [
   ('launch__occupancy_limit_shared_mem', 'limS', 1),
   ('smsp__cycles_active.avg', 'cyc', 1),
   ('l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum', 'bankconf', 1),
+  # the L1 data pipe carries shared-memory AND global/local wavefronts: the resource that binds
+  # the plane kernels once psi(r) streams through it
+  ('l1tex__data_pipe_lsu_wavefronts.sum.pct_of_peak_sustained_elapsed', 'l1pipe%', 1),
 ]
 
 
