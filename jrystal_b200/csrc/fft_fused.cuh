@@ -18,10 +18,15 @@
 //                    summed in a fixed order by k_rho_reduce (deterministic, no atomics);
 //     k_yx_vmul    : multiplies by v_eff(r) / N, transforms back along x in registers, keeps the
 //                    occupied x planes in Y, then y-transforms back and scatters into A in place.
-// psi(r), v psi(r) and the half-transformed slab never reach global memory.  Per 64^3 band-plane
-// the kernel needs ~1.7 k cycles of the SM's FP64 pipe and ~1.8 k cycles of its shared-memory
-// pipe (every element crosses the Stockham exchange once per line), so it is bound by those two
-// on-chip pipes, not by HBM.
+//     k_x_vmul_cached : the H-apply of jrb_eval when the plan holds the psi(r) cache: reads
+//                    psi(r) as k_yx_density stored it (FusedArgs::psi), multiplies, and runs only
+//                    the forward x and y transforms (no stage, no inverse).
+// v psi(r) and the half-transformed slab never reach global memory; psi(r) does only as the
+// optional cache (written once by the density sweep, read once by the H-apply).  Per 64 x 64
+// band-plane the recomputing pair needs ~1.7 k cycles of the SM's FP64 pipe and ~1.8 k cycles of
+// its shared-memory pipe per transform direction (every element crosses the Stockham exchange
+// once per line): bound by those two on-chip pipes with HBM idle, which is what the cache trades
+// against.
 //
 // Thread layout: t = lane + 8 (tj + TPL slot); the 8 "lanes" are 8 ADJACENT LINES of the
 // dimension that is not being transformed (x planes in the y stage, y lines in the x stage), so
