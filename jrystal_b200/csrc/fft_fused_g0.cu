@@ -1,7 +1,7 @@
 // Instantiations of the fused y+x kernels (fft_fused.cuh) for one group of axis lengths.
 #include "fft_fused.cuh"
 
-#define JRB_SIZES(X) X(7) X(8) X(9) X(12) X(16) X(24) X(32)
+#define JRB_SIZES(X) X(7) X(8) X(9) X(12) X(16) X(24) X(32) X(36)
 
 namespace jrb {
 

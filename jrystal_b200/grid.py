@@ -171,7 +171,8 @@ def orbital_grid_candidates(full, need) -> list:
   """Boxes `orbital_grid='auto'` tries, best first; the last one never depends on the fused plane
   kernels being available.  z (the axis the fused y+x kernels loop over) shrinks to the smallest
   light line length >= need; x and y keep the grid's lengths except 128 -> 81 (fused 81 x 81
-  kernels); grids below 48^3 are launch-latency bound and left alone."""
+  kernels) and 48 -> 36 (fused 36 x 36 kernels: C5 48.2 k -> 68.6 k band-mode evaluations/s,
+  profiles/r02_bench_C5*.json); grids below 48^3 are launch-latency bound and left alone."""
   full = tuple(int(v) for v in full)
   need = tuple(int(v) for v in need)
   # an axis the caller's own grid under-resolves (need > n) is left as it is: the reference
@@ -182,5 +183,7 @@ def orbital_grid_candidates(full, need) -> list:
   out = []
   if full[0] == full[1] == 128 and max(need[:2]) <= 81:
     out.append((81, 81, nz))
+  if full[0] == full[1] == 48 and max(need[:2]) <= 36:
+    out.append((36, 36, nz))
   out.append((full[0], full[1], nz))
   return out

@@ -45,7 +45,7 @@ def test_workload_matches_baseline_table(name):
 def test_auto_orbital_boxes_of_the_benchmarks():
   box = {n: grid.orbital_grid_candidates(EXPECT[n][0], EXPECT[n][4])[0] for n in EXPECT}
   assert box == {'C1': (32, 32, 32), 'C2': (64, 64, 49), 'C3a': (81, 81, 81), 'C3b': (81, 81, 81),
-                 'C4': (64, 64, 49), 'C5': (48, 48, 36)}
+                 'C4': (64, 64, 49), 'C5': (36, 36, 36)}
 
 
 def test_synthetic_params_are_rank_independent():

@@ -312,6 +312,8 @@ def test_orbital_grid_selection():
   assert grid.orbital_grid_candidates((32, 32, 32), (21, 21, 21)) == [(32, 32, 32)]
   assert grid.orbital_grid_candidates((12, 12, 12), (13, 13, 13)) == [(12, 12, 12)]
   assert grid.orbital_grid_candidates((48, 48, 48), (49, 49, 49)) == [(48, 48, 48)]
+  assert grid.orbital_grid_candidates((48, 48, 48), (33, 33, 33)) == [(36, 36, 36), (48, 48, 36)]
+  assert grid.orbital_grid_candidates((48, 48, 48), (37, 33, 33)) == [(48, 48, 36)]
   assert grid.orbital_grid_candidates((48, 48, 64), (49, 49, 49)) == [(48, 48, 49)]
   # anisotropic mask: per-axis minimum
   m = np.zeros((16, 24, 32), dtype=bool)

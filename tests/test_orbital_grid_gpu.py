@@ -24,6 +24,9 @@ CASES = {
                          (128, 128, 90), (64, 64, 64), (72, 72, 60), (81, 81, 81)]),
   'diamond_24x32x48': dict(name='diamond', grid=[24, 32, 48], kgrid=[1, 1, 2], cutoff=30, nb=10,
                            boxes=[(24, 24, 32), (24, 32, 40), (24, 24, 45)]),
+  # 48^3 (the C5 band-mode grid): 36 x 36 planes (6 x 6 line plan) instead of 48 x 48
+  'si_48': dict(name='si', grid=48, kgrid=[1, 1, 2], cutoff=15, nb=21,
+                boxes=[(36, 36, 36), (48, 48, 36)]),
   # x and y under-resolved by the caller's own grid (4 gmax + 1 = 13 > 12: the reference aliases
   # there, and so must we, Nyquist planes included) while z shrinks exactly
   'diamond_12x12x32_aliasing': dict(name='diamond', grid=[12, 12, 32], kgrid=[1, 1, 1], cutoff=10,
@@ -129,9 +132,23 @@ def test_band_mode_on_orbital_grid(cuda_device, box):
     assert (hq2 - hq).abs().max().item() <= 1e-14 * hq.abs().max().item()
 
 
+def test_hpsi_on_36_box_equals_full_grid(cuda_device):
+  """Band mode calls jrb_hpsi alone (no psi(r) cache): the recomputing plane kernel of the 36 x 36
+  box against the same H-apply on the plan's own 48^3 grid."""
+  s, plan, w_re, w_im, occ = _setup('si_48')
+  rng = np.random.default_rng(3)
+  veff = to_dev(rng.standard_normal((1,) + tuple(s.mask.shape)))
+  qd, _ = plan.qr_fwd(to_dev(w_re), to_dev(w_im))
+  hq_full = plan.hpsi(qd, veff).clone()
+  plan.set_orbital_grid((36, 36, 36))
+  assert plan.lib.jrb_plan_orbital_fused(plan._h) == 1
+  hq = plan.hpsi(qd, veff)
+  assert (hq - hq_full).abs().max().item() <= 1e-12 * hq_full.abs().max().item()
+
+
 def test_prepared_potential_rules(cuda_device):
   """veff = NULL without a prepared potential is an error; an explicit veff or an evaluation
-  replaces the prepared one; works on a plan without an orbital grid too (48^3 -> z = 36 with)."""
+  replaces the prepared one; works on a plan without an orbital grid too (48^3 -> 36^3 with)."""
   from jrystal_b200._lib import JrbError
   s = make_system('si', 48, [1, 1, 2], 15, 'spherical')
   nb = 9
@@ -139,7 +156,7 @@ def test_prepared_potential_rules(cuda_device):
   for og in (None, 'auto'):
     plan = make_plan(s, nb, orbital_grid=og)
     if og == 'auto':
-      assert plan.orbital_grid[:2] == (48, 48) and plan.orbital_grid[2] < 48, plan.orbital_grid
+      assert plan.orbital_grid[:2] == (36, 36) and plan.orbital_grid[2] < 48, plan.orbital_grid
     q, r = plan.qr_fwd(to_dev(w_re), to_dev(w_im))
     with pytest.raises(JrbError):
       plan.hpsi(q, None)
