@@ -675,8 +675,16 @@ def run_b200(args):
     if args.config is None and not args.emulate_ranks > 1:
       extra = {}
       for other in ('C3b', 'C3a'):
-        sub = measure(args, other, world, rank, local_rank, full=False,
-                      steps=max(3, min(args.steps, 10)))
+        # the headline line must survive a failure of an extra configuration (the same exception
+        # on every rank: a layout the shapes do not allow, out of memory); it is reported instead
+        try:
+          sub = measure(args, other, world, rank, local_rank, full=False,
+                        steps=max(3, min(args.steps, 10)))
+        except Exception as e:  # noqa: BLE001
+          import traceback
+          traceback.print_exc(file=sys.stderr)
+          sub = {'error': f'{type(e).__name__}: {e}'[:400]} if rank == 0 else None
+          torch.cuda.empty_cache()
         if sub is not None:
           extra[other] = sub
       if line is not None:
