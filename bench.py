@@ -648,6 +648,43 @@ def run_b200_band(args, wl, world, rank, local_rank):
   return None
 
 
+def numa_place_for_gpu(local_rank, enable):
+  """Prefer the NUMA node of this rank's GPU for the pinned host buffers allocated next (multi-GPU
+  e2e: eight ranks copying from one socket's memory share its controllers and the inter-socket
+  link).  set_mempolicy(MPOL_PREFERRED) through libc; a box that exposes one node, or forbids the
+  call, is left alone.  Returns what was found / done (reported in the line's e2e object)."""
+  info = {'nodes_visible': None, 'gpu_node': None, 'action': 'none'}
+  try:
+    import ctypes
+    import torch
+    nodes = sorted(int(d[4:]) for d in os.listdir('/sys/devices/system/node') if d.startswith('node')
+                   and d[4:].isdigit())
+    info['nodes_visible'] = nodes
+    pr = torch.cuda.get_device_properties(local_rank)
+    path = f'/sys/bus/pci/devices/{pr.pci_domain_id:04x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0/numa_node'
+    node = int(open(path).read().strip())
+    info['gpu_node'] = node
+    if not enable or node < 0 or node not in nodes or len(nodes) < 2:
+      return info
+    libc = ctypes.CDLL('libc.so.6', use_errno=True)
+    mask = ctypes.c_ulong(1 << node)
+    SYS_set_mempolicy, MPOL_PREFERRED = 238, 1   # x86-64
+    rc = libc.syscall(SYS_set_mempolicy, MPOL_PREFERRED, ctypes.byref(mask), ctypes.c_ulong(64))
+    info['action'] = f'set_mempolicy(MPOL_PREFERRED, node {node})' if rc == 0 else \
+        f'set_mempolicy failed (errno {ctypes.get_errno()})'
+  except Exception as e:  # noqa: BLE001 - diagnostics only
+    info['action'] = f'none ({type(e).__name__}: {e})'[:160]
+  return info
+
+
+def numa_place_default():
+  try:
+    import ctypes
+    ctypes.CDLL('libc.so.6').syscall(238, 0, None, ctypes.c_ulong(0))   # MPOL_DEFAULT
+  except Exception:  # noqa: BLE001
+    pass
+
+
 def parse_orbital_grid(text):
   if text in ('auto', 'full'):
     return text
@@ -825,11 +862,15 @@ def run_b200_kshard(args, name, wl, world, rank, local_rank, full, steps=None):
   nw = w_re_h.size
   h2d = 2 * nw * 8 + occ_h.size * 8
   d2h = 2 * nw * 8 + 4 * 8
+  # N > 1: the pinned buffers of a rank go to the NUMA node of its GPU when the box exposes one
+  numa = numa_place_for_gpu(local_rank, enable=world > 1 and os.environ.get('JRB_NO_NUMA') != '1')
   pin = lambda a: torch.from_numpy(a).pin_memory()
   w_re_p, w_im_p, occ_p = pin(w_re_h), pin(w_im_h), pin(occ_h)
   en_p = torch.empty(4, dtype=torch.float64).pin_memory()
   g_re_p = torch.empty(w_re_h.shape, dtype=torch.float64).pin_memory()
   g_im_p = torch.empty(w_re_h.shape, dtype=torch.float64).pin_memory()
+  if numa['action'].startswith('set_mempolicy(MPOL_PREFERRED'):
+    numa_place_default()
   if ev.reduce_path != 'nccl':
     # the reference-facing call with HOST buffers: k-chunked copies overlapped with the kernels,
     # the density all-reduce (world > 1) inside the library
@@ -1032,7 +1073,7 @@ def run_b200_kshard(args, name, wl, world, rank, local_rank, full, steps=None):
                  'batch_groups': int(os.environ.get('JRB_BATCH_GROUPS', 0))},
       'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': h2d,
               'd2h_bytes_per_step': d2h, 'path': e2e_path, 'ms_per_step': 1e3 / e2e_value,
-              'copies_alone_ms': copy_only_ms,
+              'copies_alone_ms': copy_only_ms, 'host_numa': numa,
               'copies_alone_note': 'the same H2D + D2H with no kernel in between, all ranks at once: '
                                    'the PCIe / host-memory floor of this box under e2e',
               'energy_rel_diff_vs_device_path': abs(e2e_energy - sum(energies)) / abs(sum(energies))},
