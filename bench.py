@@ -664,8 +664,9 @@ def numa_place_for_gpu(local_rank, enable):
     path = f'/sys/bus/pci/devices/{pr.pci_domain_id:04x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0/numa_node'
     node = int(open(path).read().strip())
     info['gpu_node'] = node
-    if not enable or node < 0 or node not in nodes or len(nodes) < 2:
-      return info
+    import platform
+    if not enable or node < 0 or node not in nodes or len(nodes) < 2 or platform.machine() != 'x86_64':
+      return info   # (the syscall number below is the x86-64 one)
     libc = ctypes.CDLL('libc.so.6', use_errno=True)
     mask = ctypes.c_ulong(1 << node)
     SYS_set_mempolicy, MPOL_PREFERRED = 238, 1   # x86-64
@@ -680,6 +681,9 @@ def numa_place_for_gpu(local_rank, enable):
 def numa_place_default():
   try:
     import ctypes
+    import platform
+    if platform.machine() != 'x86_64':
+      return
     ctypes.CDLL('libc.so.6').syscall(238, 0, None, ctypes.c_ulong(0))   # MPOL_DEFAULT
   except Exception:  # noqa: BLE001
     pass
